@@ -1,0 +1,179 @@
+/* linon_b200.h — C ABI of the B200-native ray-march path of linon.
+ *
+ * This is the drop-in boundary: the entry points are what a Rust `extern "C"` block in the reference's
+ * src/main_view.rs would bind in place of its wgpu compute pipelines.  Plain pointers and
+ * sizes only; no C++ or torch types.  Every function returns 0 on success and a non-zero LINON_ERR_* code on
+ * failure (never aborts, never throws across the boundary); linon_last_error() returns the message.
+ *
+ * Threading: a handle is not thread-safe; use it from one thread (the reference calls MainView only from the
+ * winit event-loop thread, src/main.rs:125-195).  Work is enqueued on the handle's CUDA stream; readers
+ * synchronise that stream.  Host pointers are borrowed only for the duration of a call.
+ *
+ * Image layout: every per-pixel buffer is [height][width] row-major in TEXTURE space (row 0 = top of the image,
+ * because the shaders write at coords = (gid.x, H-1-gid.y), src/main_view.wgsl:342).
+ */
+#ifndef LINON_B200_H
+#define LINON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct linon_view linon_view; /* replaces struct MainView, src/main_view.rs:53-79 */
+
+/* CameraUniform, src/main_view.rs:12-19 / struct Camera, src/main_view.wgsl:7-12.  112 bytes. */
+typedef struct linon_camera {
+    float origin[4];
+    float view_direction[4];
+    float up[4];
+    float view_matrix[16]; /* identity in the reference (CameraUniform::moving); unused on the path */
+} linon_camera;
+
+/* Settings, src/main_view.rs:43-51 / src/main_view.wgsl:16-23.  24 bytes. */
+typedef struct linon_settings {
+    float field_weight;
+    float mouse_pos[2];
+    int32_t overlay_mode;             /* 0 = disabled, 1 = Lyapunov exponents */
+    int32_t central_difference_delta; /* 1..10, src/application.rs:297 */
+    float lyapunov_scaling;
+} linon_settings;
+
+enum {
+    LINON_OK = 0,
+    LINON_ERR_INVALID = 1,     /* bad argument / call order */
+    LINON_ERR_CUDA = 2,        /* CUDA runtime or driver error */
+    LINON_ERR_COMPILE = 3,     /* field function rejected (translator or NVRTC); previous kernel stays live */
+    LINON_ERR_NO_DRIVER = 4,   /* libcuda.so.1 / a CUDA device is not available: there is NO CPU fallback */
+    LINON_ERR_SIZE = 5         /* caller buffer too small */
+};
+
+/* render flags.  The reference toggles these by string replacement on the WGSL source
+ * (src/main_view.rs:752-829); two of the three replacements are dead at HEAD — the flags implement
+ * the intended behaviour (report/Sources/2-Approach.tex:192,218). */
+enum {
+    LINON_RENDER_DEFAULT = 0,
+    LINON_RENDER_ENHANCE = 1,         /* h_initial 0.1 -> 0.001, MainView::render_high_accuracy, :778-802 */
+    LINON_RENDER_OUTLINE = 2,         /* sample rays on the outline of exponents >= 0.8, render_outline_rays, :804-829 */
+    LINON_RENDER_ADAPTIVE_OFF = 4,    /* disable_adaptive_sampling (while dragging), :765-776 */
+    LINON_RENDER_NO_OVERLAY = 8,      /* skip the overlay dispatch (sharded march; overlay runs after the gather) */
+    LINON_RENDER_NO_MARCH = 16,       /* overlay (+ sample rays) only, on buffers already in place */
+    LINON_RENDER_NO_SAMPLE_RAYS = 32  /* skip the 8 reference-view rays */
+};
+
+/* buffers (linon_read / linon_device_ptr).  Element sizes in bytes per pixel unless noted. */
+enum {
+    LINON_BUF_FINAL_RGBA8 = 0,   /* `texture`: overlay output shown on screen, 4 B     (src/main_view.rs:107-113) */
+    LINON_BUF_RAYCAST_RGBA8 = 1, /* `ray_casting_texture`: march colour, 4 B            (:117-123) */
+    LINON_BUF_ENDPOINT_F32X4 = 2,/* `mapping_texture`: ray endpoint (x,y,z,1), 16 B     (:125-131) */
+    LINON_BUF_EXPONENTS_F32 = 3, /* `exponents_buffer`, 4 B, stride = width (:146-151) */
+    LINON_BUF_HIT_ID_I32 = 4,    /* NEW: index of the first face hit, -1 = none, 4 B */
+    LINON_BUF_RAY_SAMPLES = 5,   /* `ray_samples_buffer`: 800 x {vec4 position, vec4 colour} = 25,600 B total
+                                    (src/ray_samples.rs:8-27, src/application.rs:125-130) */
+    LINON_BUF_SAMPLE_POS = 6     /* the 8 normalised (x,y) start positions used for the sample rays, 64 B total */
+};
+
+/* tunables (linon_set_option) */
+enum {
+    LINON_OPT_MATH = 0,          /* 0 strict (no FMA contraction, IEEE div/sqrt; comparable with the CPU oracle bit
+                                    for bit on bodies without transcendentals), 1 fused (FMA contraction),
+                                    2 fast (--use_fast_math).  Default 1. */
+    LINON_OPT_KERNEL = 1,        /* 0 one thread per pixel, 1 persistent warps with phase split + lane refill. Default 1 */
+    LINON_OPT_BLOCK = 2,         /* threads per CTA of the march kernel (multiple of 32). Default 256 */
+    LINON_OPT_CTAS_PER_SM = 3,   /* persistent grid = this x #SM; 0 = occupancy query. Default 0 */
+    LINON_OPT_REFILL_MIN = 4,    /* idle lanes a warp tolerates before refilling. Default 1 */
+    LINON_OPT_FACE_UNROLL = 5,   /* unroll of the face loop. Default 4 */
+    LINON_OPT_MAX_REGS = 6       /* NVRTC --maxrregcount (0 = none). Default 0 */
+};
+
+typedef struct linon_counters { /* per-frame totals over every ray of the last march */
+    uint64_t rays;              /* rays marched */
+    uint64_t accepted_steps;    /* accepted RK4 steps */
+    uint64_t prehit_steps;      /* accepted steps that also ran the all-face intersection */
+    uint64_t rejected_steps;    /* RK4 attempts rejected by adaptive sampling */
+} linon_counters;
+
+typedef struct linon_timings { /* CUDA-event times of the last render, milliseconds (0 when the pass did not run) */
+    float march_ms;
+    float overlay_ms;
+    float sample_rays_ms;
+    float outline_search_ms;
+    float jit_ms;               /* host time spent in translate + NVRTC for this render (0 on a cache hit) */
+    int32_t march_regs;         /* registers per thread of the march kernel */
+    int32_t march_grid;         /* CTAs launched */
+    int32_t march_block;        /* threads per CTA */
+} linon_timings;
+
+/* MainView::new (src/main_view.rs:82-458): allocates textures/buffers for width x height on CUDA device
+ * `device`, installs the reference's start-up state: Settings {1.0, [0.5,0.6], 0, 1, 50.0} (:133-139), the
+ * MirageSphericalSigmoid body (:100) and NO mesh/camera (call linon_set_mesh / linon_set_camera).
+ * The caller applies the discrete_gpu down-scale (:93) itself. */
+int linon_create(int device, uint32_t width, uint32_t height, linon_view** out);
+void linon_destroy(linon_view* v);
+
+/* MainView::update_model (:460-488) + the vertices/faces storage buffers (src/application.rs:112-122).
+ * verts: n_verts x 3 f32, faces: n_faces x 3 u32 (copied). */
+int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces);
+/* MainView::update_camera (:490-494): uploads the 112-byte uniform. */
+int linon_set_camera(linon_view* v, const linon_camera* camera);
+/* MainView::update_settings (:547-550): uploads the 24-byte uniform. */
+int linon_set_settings(linon_view* v, const linon_settings* settings);
+/* MainView::resize_texture (:552-647): reallocates the per-pixel buffers (contents zeroed). */
+int linon_resize(linon_view* v, uint32_t width, uint32_t height);
+/* MainView::reload_shader(device, None, body) (:649-690): wgsl_body is the text spliced into
+ * fn field_function(p_prev, p, v0, v: vec3<f32>, t: f32) -> vec3<f32> (:852-861).  On failure returns
+ * LINON_ERR_COMPILE, writes the diagnostic (line numbers refer to the body) to err (if non-null) and keeps the
+ * previous function live, like the reference (:677-679). */
+int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, size_t err_len);
+/* MainView::render (:831-849), render_high_accuracy (:778-802), render_outline_rays (:804-829) by flags.
+ * Enqueues: [outline search | click positions] -> march (+ sample rays on a second stream) -> overlay. */
+int linon_render(linon_view* v, uint32_t flags);
+/* Waits for everything enqueued by the handle. */
+int linon_sync(linon_view* v);
+
+/* Copies a whole buffer to host memory (synchronises the handle's stream first). */
+int linon_read(linon_view* v, int buffer, void* dst, size_t dst_bytes);
+/* Size in bytes of a buffer at the current resolution. */
+size_t linon_buffer_bytes(const linon_view* v, int buffer);
+/* Device pointer of a buffer (for CUDA interop, e.g. NCCL gather of row tiles or display hand-off). */
+void* linon_device_ptr(linon_view* v, int buffer);
+/* cudaStream_t the handle launches on (so callers can record their own events on it). */
+void* linon_stream(linon_view* v);
+
+/* Row-block sharding for multi-GPU frames: the rows are cut into blocks of rows_per_block; block b belongs to
+ * rank b % world.  The march then only renders this rank's rows (buffers stay full-frame; other rows untouched). */
+int linon_set_shard(linon_view* v, uint32_t rank, uint32_t world, uint32_t rows_per_block);
+
+int linon_set_option(linon_view* v, int option, int value);
+int linon_get_counters(linon_view* v, linon_counters* out);
+int linon_get_timings(linon_view* v, linon_timings* out);
+/* Last error message of the handle (or of the failed linon_create when v is NULL). */
+const char* linon_last_error(const linon_view* v);
+
+/* Translator alone (no device needed): WGSL body -> CUDA C++ body. Returns LINON_ERR_COMPILE with the reason in err. */
+int linon_translate_wgsl(const char* wgsl_body, char* out, size_t out_len, char* err, size_t err_len);
+/* Full JIT without a device: translate + NVRTC compile the march module for sm_100a; returns cubin size in
+ * *cubin_bytes and the registers/thread of the persistent kernel are not known without loading (set to 0). */
+int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, uint32_t n_faces, size_t* cubin_bytes,
+                        char* err, size_t err_len);
+
+/* Parity/debug entry points: evaluate the CURRENT field function / helper library / hit_triangle on arrays
+ * (host pointers; n elements; vec3 arrays are n x 3 f32). `which` numbering for helpers:
+ * 0 rotateX 1 rotateY 2 rotateZ 3 translate 4 refraction 5 point_plane_distance 6 sigmoid 7 refraction_index
+ * 8 reflect 9 normalize 10 cross. */
+int linon_debug_eval_field(linon_view* v, uint32_t n, const float* p_prev, const float* p, const float* v0,
+                           const float* vel, const float* t, float* out);
+int linon_debug_eval_helper(linon_view* v, int which, uint32_t n, const float* vec, const float* nrm, const float* p0,
+                            const float* a, const float* b, const float* c, float* out);
+int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const float* origin, const float* dir,
+                             float* t_out);
+
+/* FFMA-chain microbenchmark on `device`: the measured FP32 peak used as the roofline denominator. */
+int linon_measure_fp32_peak(int device, double* tflops, int* sm_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINON_B200_H */

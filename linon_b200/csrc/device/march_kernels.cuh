@@ -1,0 +1,584 @@
+// march_kernels.cuh — the JIT kernel template of the nonlinear ray march (sm_100a, NVRTC).
+//
+// The module NVRTC compiles is:   wgsl_prelude.cuh  +  field_function (translated WGSL body)  +  this file.
+// It replaces the `main_view` dispatch of the reference (src/main_view.wgsl:339-375 with
+// nonlinear_ray_color :229-279, ray_color :177-220, hit_triangle :150-175) and sample_rays (:281-314).
+//
+// Variant macros (-D on the NVRTC command line; the host keys its module cache on them):
+//   LINON_H_INITIAL      initial RK4 step (0.1f, or 0.001f for "Enhance", src/main_view.rs:785-787)
+//   LINON_ADAPTIVE       adaptive sampling on/off (src/main_view.wgsl:227,252-255,267-269).  The host passes 0
+//                        when H_INITIAL <= 0.002: the rejection test needs h > 0.002 and the restore test
+//                        needs h < h_initial, so neither can fire and h is a compile-time constant.
+//   LINON_N_FACES        faces of the bound mesh (arrayLength(&faces.data), src/main_view.wgsl:182)
+//   LINON_FACE_UNROLL    unroll factor of the face loop
+//   LINON_BLOCK          threads per CTA of the march kernels
+//   LINON_REFILL_MIN     idle lanes a warp tolerates before it refills (persistent kernel)
+//
+// Two march kernels share every per-ray device function, so their per-pixel results are bit-identical:
+//   linon_march_tiles       one thread per pixel, 8x4 pixel tiles per warp (the straightforward mapping)
+//   linon_march_persistent  persistent CTAs (grid = k * #SM).  Every warp keeps 32 rays in flight; a lane whose
+//                           ray leaves its phase is refilled through a warp-aggregated atomic.  Phase A = rays
+//                           that have not hit yet (RK4 + all-face intersection every step); on a hit the lane
+//                           writes colour + hit id, pushes {p, dir, t, h, last_v, last_diff} to a device queue and
+//                           takes a fresh ray.  Phase B = queued rays (RK4 only, src/main_view.wgsl:259 skips the
+//                           intersection once has_color) until t > 5.  Rays never stop early in the reference
+//                           (SURVEY F1), so the divergence to remove is pre-hit vs post-hit lanes, and this split
+//                           makes every warp homogeneous.
+//
+// Mesh: staged once per CTA into shared memory as {v0, e1 = v1-v0, e2 = v2-v0} (3 x float4 per face).
+// All lanes read the same face at the same time, so every LDS.128 is a broadcast (no bank conflicts).
+// Precomputing e1/e2 performs the same two fp32 subtractions the reference does per test, once.
+
+#ifndef LINON_H_INITIAL
+#define LINON_H_INITIAL 0.1f
+#endif
+#ifndef LINON_ADAPTIVE
+#define LINON_ADAPTIVE 1
+#endif
+#ifndef LINON_N_FACES
+#define LINON_N_FACES 36
+#endif
+#ifndef LINON_FACE_UNROLL
+#define LINON_FACE_UNROLL 4
+#endif
+#ifndef LINON_BLOCK
+#define LINON_BLOCK 256
+#endif
+#ifndef LINON_REFILL_MIN
+#define LINON_REFILL_MIN 1
+#endif
+
+#define LINON_EPS 0.0000001f  // const eps, src/main_view.wgsl:74
+
+struct MarchParams {
+    float cam_origin[4];          // Camera.origin          (src/main_view.wgsl:7-12)
+    float cam_view[4];            // Camera.view_direction
+    float cam_up[4];              // Camera.up
+    WgslSettings settings;        // 24 B, src/main_view.rs:43-51
+    int width, height;            // full frame (texture) size
+    int local_rows;               // rows this shard renders
+    int shard_rank, shard_world;  // row blocks are dealt round-robin: block b -> rank b % world
+    int rows_per_block;
+    const float4* tris;           // LINON_N_FACES x {v0, e1, e2}
+    uchar4* raycast;              // [local_rows][width]  ray_casting_texture (rgba8unorm)
+    float4* endpoint;             // [local_rows][width]  mapping_texture (rgba32float)
+    int* hit_id;                  // [local_rows][width]  face index of the first hit, -1 = none
+    unsigned long long* counters; // [0] accepted steps  [1] steps that ran the face loop  [2] rejected attempts
+    // persistent kernel only
+    unsigned int* work;           // [0] next fresh ray  [1] queue tail  [2] queue head  [3] rays that left phase A
+    int* q_pixel;                 // queue: local pixel index, -1 until the entry is published
+    float4* q_state;              // queue: 3 x float4 per entry, SoA planes of q_capacity
+    unsigned int q_capacity;
+    unsigned int n_ray_slots;     // tiles * 32 (index space of fresh rays incl. out-of-frame padding lanes)
+};
+
+struct Ray {
+    vec3f p, dir, sdir, last_v;
+    float t, h, last_diff;
+};
+
+__device__ __forceinline__ vec3f ld3(const float* a) { return vec3f(a[0], a[1], a[2]); }
+
+// local row -> texture row for the round-robin row-block sharding (identity when world == 1)
+__device__ __forceinline__ int texture_row(const MarchParams& P, int local_row) {
+    const int lb = local_row / P.rows_per_block;
+    const int off = local_row - lb * P.rows_per_block;
+    return (lb * P.shard_world + P.shard_rank) * P.rows_per_block + off;
+}
+
+// src/main_view.wgsl:347-366: pinhole ray through pixel (gid.x, gid.y), gid.y counted from the bottom row.
+__device__ __forceinline__ vec3f camera_ray_dir(const MarchParams& P, float px, float py_from_bottom, bool normalised_pos) {
+    const float width = (float)P.width;
+    const float height = (float)P.height;
+    const float aspect_ratio = width / height;
+    const vec3f view_direction = ld3(P.cam_view);
+    const vec3f up = ld3(P.cam_up);
+    const float focal_length = 0.035f;
+    const float viewport_height = 0.025f;
+    const float viewport_width = aspect_ratio * viewport_height;
+    const vec3f w = -view_direction;
+    const vec3f horizontal = w_cross(up, w);
+    const vec3f vertical = w_cross(w, horizontal);
+    float u, v;
+    if (normalised_pos) {  // sample rays, src/main_view.wgsl:475-476
+        u = px * viewport_width - 0.5f * viewport_width;
+        v = py_from_bottom * viewport_height - 0.5f * viewport_height;
+    } else {               // pixels, src/main_view.wgsl:363-364
+        u = px / (width - 1.0f) * viewport_width - 0.5f * viewport_width;
+        v = py_from_bottom / (height - 1.0f) * viewport_height - 0.5f * viewport_height;
+    }
+    const vec3f s = u * w_normalize(horizontal) + v * w_normalize(vertical) + focal_length * view_direction;
+    return w_normalize(s);
+}
+
+__device__ __forceinline__ WgslCamera make_camera(const MarchParams& P) {
+    WgslCamera c;
+    c.origin = vec4f(P.cam_origin[0], P.cam_origin[1], P.cam_origin[2], P.cam_origin[3]);
+    c.view_direction = vec4f(P.cam_view[0], P.cam_view[1], P.cam_view[2], P.cam_view[3]);
+    c.up = vec4f(P.cam_up[0], P.cam_up[1], P.cam_up[2], P.cam_up[3]);
+    return c;
+}
+
+// One Runge-Kutta evaluation, src/main_view.wgsl:246-250 (p_prev = cur_point in all four stages).
+__device__ __forceinline__ vec3f rk4_velocity(const Ray& r, float h, const WgslSettings& st, const WgslCamera& cam) {
+    const vec3f k1 = field_function(r.p, r.p, r.sdir, r.dir, r.t, st, cam);
+    const vec3f k2 = field_function(r.p, r.p + 0.5f * h * k1, r.sdir, k1, r.t + 0.5f * h, st, cam);
+    const vec3f k3 = field_function(r.p, r.p + 0.5f * h * k2, r.sdir, k2, r.t + 0.5f * h, st, cam);
+    const vec3f k4 = field_function(r.p, r.p + h * k3, r.sdir, k3, r.t + h, st, cam);
+    return (k1 + 2.0f * k2 + 2.0f * k3 + k4) / 6.0f;
+}
+
+// hit_triangle over every face, keeping the closest hit in (0, max_dist): src/main_view.wgsl:150-198.
+// Branch-free restatement of the reference's early returns (same comparisons, same NaN behaviour).
+__device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri, vec3f origin, vec3f direction,
+                                               float max_dist, float& t_best, int& id_best) {
+    t_best = -1.0f;
+    id_best = -1;
+#pragma unroll LINON_FACE_UNROLL
+    for (int i = 0; i < LINON_N_FACES; ++i) {
+        const float4 a = s_tri[3 * i], b = s_tri[3 * i + 1], c = s_tri[3 * i + 2];
+        const vec3f v0(a.x, a.y, a.z), edge1(b.x, b.y, b.z), edge2(c.x, c.y, c.z);
+        const vec3f h = w_cross(direction, edge2);
+        const float det = w_dot(edge1, h);
+        const float f = 1.0f / det;
+        const vec3f s = origin - v0;
+        const float u = f * w_dot(s, h);
+        const vec3f q = w_cross(s, edge1);
+        const float v = f * w_dot(direction, q);
+        const float t = f * w_dot(edge2, q);
+        const bool ok = !(det > -LINON_EPS && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) &&
+                        !(v < 0.0f || u + v > 1.0f) && (t > LINON_EPS);
+        const float t_new = ok ? t : -1.0f;
+        if (t_new > 0.0f && t_new < max_dist && (t_best < 0.0f || t_new < t_best)) {
+            t_best = t_new;
+            id_best = i;
+        }
+    }
+}
+
+// Blinn-Phong with the camera as light, src/main_view.wgsl:199-217.
+__device__ __forceinline__ vec3f shade(const float4* __restrict__ s_tri, int id, vec3f direction) {
+    const float4 b = s_tri[3 * id + 1], c = s_tri[3 * id + 2];
+    const vec3f normal = w_normalize(w_cross(vec3f(b.x, b.y, b.z), vec3f(c.x, c.y, c.z)));
+    const vec3f light_color(1.0f, 1.0f, 1.0f);
+    const vec3f ambient = 0.01f * light_color;
+    float intensity = w_max(w_dot(normal, -direction), 0.0f);
+    if (intensity == 0.0f) intensity = w_max(w_dot(-normal, -direction), 0.0f);
+    const vec3f diffuse = intensity * light_color;
+    const vec3f specular = w_pow(intensity, 64.0f) * light_color;
+    return (ambient + diffuse + specular) * w_abs(normal);
+}
+
+// rgba8unorm store conversion: clamp to [0,1], x255, round to nearest even; NaN -> 0.
+__device__ __forceinline__ unsigned char unorm8(float x) {
+    x = fminf(fmaxf(x, 0.0f), 1.0f);  // fmaxf(NaN, 0) = 0
+    return (unsigned char)__float2int_rn(x * 255.0f);
+}
+__device__ __forceinline__ uchar4 pack_color(vec3f c) { return make_uchar4(unorm8(c.x), unorm8(c.y), unorm8(c.z), 255); }
+
+__device__ __forceinline__ void stage_mesh(float4* s_tri, const float4* __restrict__ g_tri) {
+    for (int i = threadIdx.x; i < 3 * LINON_N_FACES; i += blockDim.x) s_tri[i] = g_tri[i];
+    __syncthreads();
+}
+
+// 32 consecutive ray slots form an 8x4 pixel tile; returns false for padding lanes outside the shard.
+__device__ __forceinline__ bool slot_to_pixel(const MarchParams& P, unsigned int slot, int& x, int& local_row) {
+    const unsigned int tiles_x = (unsigned int)(P.width + 7) >> 3;
+    const unsigned int tile = slot >> 5, lane = slot & 31u;
+    const unsigned int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    x = (int)(tx * 8u + (lane & 7u));
+    local_row = (int)(ty * 4u + (lane >> 3));
+    return x < P.width && local_row < P.local_rows;
+}
+
+__device__ __forceinline__ void init_ray(const MarchParams& P, int x, int local_row, Ray& r) {
+    const int gid_y = P.height - 1 - texture_row(P, local_row);  // src/main_view.wgsl:342
+    r.p = ld3(P.cam_origin);
+    r.sdir = camera_ray_dir(P, (float)x, (float)gid_y, false);
+    r.dir = r.sdir;
+    r.t = 0.0f;
+    r.last_v = vec3f(0.0f, 0.0f, 0.0f);
+    r.last_diff = -1.0f;
+    r.h = LINON_H_INITIAL;
+}
+
+struct StepCounters {
+    unsigned int accepted, prehit, rejected;
+};
+
+__device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounters c) {
+    unsigned int a = c.accepted, b = c.prehit, r = c.rejected;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&P.counters[0], (unsigned long long)a);
+        atomicAdd(&P.counters[1], (unsigned long long)b);
+        atomicAdd(&P.counters[2], (unsigned long long)r);
+    }
+}
+
+// One loop iteration of nonlinear_ray_color up to (not including) the intersection, src/main_view.wgsl:246-258.
+// Returns false when the adaptive test rejects the attempt (h <- 0.001, state unchanged).
+__device__ __forceinline__ bool rk4_attempt(Ray& r, const WgslSettings& st, const WgslCamera& cam, vec3f& v, float& diff,
+                                            vec3f& step_dir) {
+#if LINON_ADAPTIVE
+    const float h = r.h;
+#else
+    const float h = LINON_H_INITIAL;
+#endif
+    v = rk4_velocity(r, h, st, cam);
+#if LINON_ADAPTIVE
+    diff = w_length(v - r.last_v);
+    if (r.last_diff >= 0.0f && diff > 10.0f * r.last_diff && h > 0.002f) {
+        r.h = 0.001f;
+        return false;
+    }
+#else
+    diff = 0.0f;
+#endif
+    r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+    step_dir = r.dir * h;
+    return true;
+}
+
+// The tail of an accepted iteration, src/main_view.wgsl:264-270.
+__device__ __forceinline__ void rk4_advance(Ray& r, vec3f v, float diff, vec3f step_dir) {
+    r.p = r.p + step_dir;
+#if LINON_ADAPTIVE
+    r.t = r.t + r.h;
+    r.last_v = v;
+    if (2.0f * diff < r.last_diff && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
+    r.last_diff = diff;
+#else
+    r.t = r.t + LINON_H_INITIAL;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel 1: one thread per pixel.
+// ------------------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_tiles(const MarchParams P) {
+    __shared__ float4 s_tri[3 * LINON_N_FACES];
+    stage_mesh(s_tri, P.tris);
+
+    const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
+    int x, local_row;
+    const bool valid = slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row);
+    StepCounters cnt = {0u, 0u, 0u};
+    if (valid) {
+        const WgslCamera cam = make_camera(P);
+        const WgslSettings st = P.settings;
+        Ray r;
+        init_ray(P, x, local_row, r);
+        bool has_color = false;
+        vec3f color(0.0f, 0.0f, 0.0f);
+        int hit = -1;
+        for (; r.t <= 5.0f;) {
+            vec3f v, step_dir;
+            float diff;
+            if (!rk4_attempt(r, st, cam, v, diff, step_dir)) {
+                ++cnt.rejected;
+                continue;
+            }
+            if (!has_color) {
+                const float max_dist = w_length(step_dir);
+                const vec3f dirn = w_normalize(step_dir);
+                float t_hit;
+                int id;
+                intersect_mesh(s_tri, r.p, dirn, max_dist, t_hit, id);
+                if (t_hit > 0.0f && t_hit < max_dist) {
+                    color = shade(s_tri, id, dirn);
+                    hit = id;
+                    has_color = true;  // result.color.a = t > 0
+                }
+                ++cnt.prehit;
+            }
+            rk4_advance(r, v, diff, step_dir);
+            ++cnt.accepted;
+        }
+        const size_t pix = (size_t)local_row * P.width + x;
+        P.raycast[pix] = pack_color(color);  // black when !has_color, alpha = 1 (src/main_view.wgsl:274-277)
+        P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+        P.hit_id[pix] = hit;
+    }
+    flush_counters(P, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel 2: persistent warps, phase A (pre-hit) / phase B (post-hit) with lane refill.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int lane_rank(unsigned int mask) { return __popc(mask & ((1u << (threadIdx.x & 31)) - 1u)); }
+
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_persistent(const MarchParams P) {
+    __shared__ float4 s_tri[3 * LINON_N_FACES];
+    stage_mesh(s_tri, P.tris);
+
+    const unsigned int lane = threadIdx.x & 31;
+    const WgslCamera cam = make_camera(P);
+    const WgslSettings st = P.settings;
+    unsigned int* const w_next = P.work + 0;
+    unsigned int* const w_tail = P.work + 1;
+    unsigned int* const w_head = P.work + 2;
+    unsigned int* const w_adone = P.work + 3;
+    const size_t plane = P.q_capacity;
+
+    Ray r;
+    r.p = r.dir = r.sdir = r.last_v = vec3f(0.0f, 0.0f, 0.0f);
+    r.t = 0.0f; r.h = LINON_H_INITIAL; r.last_diff = -1.0f;
+    int pix = -1;           // local pixel index of the ray this lane carries
+    bool alive = false;
+    bool phase_b = false;   // warp-uniform
+    bool fresh_left = true; // warp-uniform
+    StepCounters cnt = {0u, 0u, 0u};
+
+    for (;;) {
+        const unsigned int idle = __ballot_sync(0xffffffffu, !alive);
+        if (__popc(idle) >= LINON_REFILL_MIN || idle == 0xffffffffu) {
+            if (!phase_b && fresh_left) {
+                // ---- refill from the fresh-ray cursor (warp-aggregated) ----
+                const unsigned int need = __popc(idle);
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(w_next, need);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                unsigned int padding = 0;  // slots outside the frame leave phase A immediately
+                if (!alive) {
+                    const unsigned int slot = base + lane_rank(idle);
+                    if (slot < P.n_ray_slots) {
+                        int x, local_row;
+                        if (slot_to_pixel(P, slot, x, local_row)) {
+                            init_ray(P, x, local_row, r);
+                            pix = local_row * P.width + x;
+                            alive = true;
+                        } else {
+                            padding = 1;
+                        }
+                    }
+                }
+                const unsigned int pad_mask = __ballot_sync(0xffffffffu, padding);
+                if (lane == 0 && pad_mask) atomicAdd(w_adone, (unsigned int)__popc(pad_mask));
+                if (base + need >= P.n_ray_slots) fresh_left = false;
+            } else if (phase_b) {
+                // ---- refill from the post-hit queue ----
+                const unsigned int need = __popc(idle);
+                unsigned int base = 0, take = 0;
+                if (lane == 0) {
+                    for (;;) {
+                        const unsigned int head = *(volatile unsigned int*)w_head;
+                        const unsigned int tail = *(volatile unsigned int*)w_tail;
+                        const unsigned int avail = tail - head;
+                        take = avail < need ? avail : need;
+                        if (take == 0) break;
+                        if (atomicCAS(w_head, head, head + take) == head) {
+                            base = head;
+                            break;
+                        }
+                    }
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                take = __shfl_sync(0xffffffffu, take, 0);
+                if (!alive) {
+                    const unsigned int k = lane_rank(idle);
+                    if (k < take) {
+                        const unsigned int e = base + k;
+                        int px;
+                        while ((px = *(volatile int*)(P.q_pixel + e)) < 0) __nanosleep(64);
+                        __threadfence();  // the entry was published after its payload
+                        const float4 a = __ldcg(P.q_state + e);
+                        const float4 b = __ldcg(P.q_state + plane + e);
+                        const float4 c = __ldcg(P.q_state + 2 * plane + e);
+                        r.p = vec3f(a.x, a.y, a.z); r.t = a.w;
+                        r.dir = vec3f(b.x, b.y, b.z); r.h = b.w;
+                        r.last_v = vec3f(c.x, c.y, c.z); r.last_diff = c.w;
+                        pix = px;
+                        const int local_row = px / P.width;
+                        const int gid_y = P.height - 1 - texture_row(P, local_row);
+                        r.sdir = camera_ray_dir(P, (float)(px - local_row * P.width), (float)gid_y, false);
+                        alive = true;
+                    }
+                }
+            }
+            if (__ballot_sync(0xffffffffu, alive) == 0u) {
+                // the warp is empty: move to phase B once the fresh rays are gone, finish when everything drained
+                if (!phase_b) {
+                    if (fresh_left) continue;
+                    phase_b = true;
+                    continue;
+                }
+                unsigned int done = 0;
+                if (lane == 0) {
+                    const unsigned int adone = *(volatile unsigned int*)w_adone;
+                    const unsigned int head = *(volatile unsigned int*)w_head;
+                    const unsigned int tail = *(volatile unsigned int*)w_tail;
+                    // every ray left phase A and every queued ray has been claimed
+                    done = (adone >= P.n_ray_slots && head == tail) ? 1u : 0u;
+                    if (!done) __nanosleep(256);
+                }
+                if (__shfl_sync(0xffffffffu, done, 0)) break;
+                continue;
+            }
+        }
+
+        // ---- one RK4 attempt for every live lane ----
+        const bool stepping = alive;
+        bool finished = false, hit_now = false;
+        if (alive) {
+            vec3f v, step_dir;
+            float diff;
+            if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
+                if (!phase_b) {
+                    const float max_dist = w_length(step_dir);
+                    const vec3f dirn = w_normalize(step_dir);
+                    float t_hit;
+                    int id;
+                    intersect_mesh(s_tri, r.p, dirn, max_dist, t_hit, id);
+                    ++cnt.prehit;
+                    if (t_hit > 0.0f && t_hit < max_dist) {
+                        P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
+                        P.hit_id[pix] = id;
+                        hit_now = true;
+                    }
+                }
+                rk4_advance(r, v, diff, step_dir);
+                ++cnt.accepted;
+                finished = !(r.t <= 5.0f);
+                if (finished) {
+                    P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+                    if (!phase_b && !hit_now) {  // never hit: black, alpha 1 (src/main_view.wgsl:275-277)
+                        P.raycast[pix] = make_uchar4(0, 0, 0, 255);
+                        P.hit_id[pix] = -1;
+                    }
+                }
+                if (finished || hit_now) alive = false;
+            } else {
+                ++cnt.rejected;
+            }
+        }
+        if (!phase_b) {
+            // Rays that hit and still have steps left continue in phase B through the queue.  The payload is
+            // written first, then the entry is published by storing its pixel index (consumers spin on it).
+            const bool left_a = stepping && !alive;
+            const bool push = left_a && !finished;
+            const unsigned int push_mask = __ballot_sync(0xffffffffu, push);
+            const unsigned int left_mask = __ballot_sync(0xffffffffu, left_a);
+            if (push_mask) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(w_tail, (unsigned int)__popc(push_mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (push) {
+                    const unsigned int e = base + lane_rank(push_mask);
+                    __stcg(P.q_state + e, make_float4(r.p.x, r.p.y, r.p.z, r.t));
+                    __stcg(P.q_state + plane + e, make_float4(r.dir.x, r.dir.y, r.dir.z, r.h));
+                    __stcg(P.q_state + 2 * plane + e, make_float4(r.last_v.x, r.last_v.y, r.last_v.z, r.last_diff));
+                    __threadfence();
+                    *(volatile int*)(P.q_pixel + e) = pix;
+                }
+            }
+            if (left_mask && lane == 0) atomicAdd(w_adone, (unsigned int)__popc(left_mask));
+        }
+    }
+    flush_counters(P, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sample_rays: the 8 reference-view rays, src/main_view.wgsl:281-314 + :469-479.  One thread per ray.
+// pos16 = 8 x (x, y) normalised image positions (click ring or outline search results).
+// ------------------------------------------------------------------------------------------------------------
+struct SampleParams {
+    MarchParams march;
+    const float* pos16;
+    float4* ray_samples;  // 800 x {position, colour}
+};
+
+__constant__ float c_sample_colors[8][3] = {  // src/main_view.wgsl:326-335
+    {1.0f, 0.0f, 0.0f}, {0.5f, 0.5f, 0.0f}, {0.0f, 1.0f, 0.0f}, {0.5f, 1.0f, 0.0f},
+    {1.0f, 1.0f, 0.0f}, {0.5f, 0.5f, 0.5f}, {0.0f, 0.0f, 1.0f}, {0.5f, 0.0f, 0.5f}};
+
+extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleParams S) {
+    const int k = threadIdx.x;
+    if (k >= 8) return;
+    const MarchParams& P = S.march;
+    const WgslCamera cam = make_camera(P);
+    const WgslSettings st = P.settings;
+    Ray r;
+    r.p = ld3(P.cam_origin);
+    r.sdir = camera_ray_dir(P, S.pos16[2 * k], S.pos16[2 * k + 1], true);
+    r.dir = r.sdir;
+    r.t = 0.0f;
+    r.last_v = vec3f(0.0f, 0.0f, 0.0f);
+    r.last_diff = -1.0f;
+    r.h = 0.001f;
+    const float h = 0.001f;
+    const float4 colour = make_float4(c_sample_colors[k][0], c_sample_colors[k][1], c_sample_colors[k][2], 0.5f);
+    for (int i = 0; i < 5000; ++i) {
+        const vec3f v = rk4_velocity(r, h, st, cam);
+        r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+        const vec3f step_dir = r.dir * h;
+        if (i % 50 == 0) {
+            const int index = k * 100 + i / 50;
+            S.ray_samples[2 * index] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+            S.ray_samples[2 * index + 1] = colour;
+        }
+        r.p = r.p + step_dir;
+        r.t = r.t + h;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Debug / parity entry points (unit tests call these through linon_debug_*; not used by render).
+// ------------------------------------------------------------------------------------------------------------
+extern "C" __global__ void linon_eval_field(int n, const float* p_prev, const float* p, const float* v0, const float* v,
+                                            const float* t, WgslSettings st, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    WgslCamera cam;
+    const vec3f r = field_function(ld3(p_prev + 3 * i), ld3(p + 3 * i), ld3(v0 + 3 * i), ld3(v + 3 * i), t[i], st, cam);
+    out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+}
+
+// which: 0 rotateX 1 rotateY 2 rotateZ 3 translate 4 refraction 5 point_plane_distance 6 sigmoid 7 refraction_index
+//        8 reflect 9 normalize 10 cross        (same numbering as the oracle's oracle_helper)
+extern "C" __global__ void linon_eval_helper(int which, int n, const float* v, const float* nrm, const float* p0,
+                                             const float* a, const float* b, const float* c, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vec3f V = ld3(v + 3 * i), N = ld3(nrm + 3 * i), P0 = ld3(p0 + 3 * i);
+    vec3f r(0.0f, 0.0f, 0.0f);
+    switch (which) {
+        case 0: r = rotateX(V, a[i]); break;
+        case 1: r = rotateY(V, a[i]); break;
+        case 2: r = rotateZ(V, a[i]); break;
+        case 3: r = translate(V, a[i], b[i], c[i]); break;
+        case 4: r = refraction(a[i], b[i], V, N); break;
+        case 5: r.x = point_plane_distance(V, N, P0); break;
+        case 6: r.x = sigmoid(a[i]); break;
+        case 7: r.x = refraction_index(a[i]); break;
+        case 8: r = w_reflect(V, N); break;
+        case 9: r = w_normalize(V); break;
+        case 10: r = w_cross(V, N); break;
+    }
+    out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+}
+
+// hit_triangle on n independent (triangle, origin, direction) triples -> t or -1 (src/main_view.wgsl:150-175)
+extern "C" __global__ void linon_eval_hit_triangle(int n, const float* tri, const float* origin, const float* dir, float* t_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vec3f v0 = ld3(tri + 9 * i), v1 = ld3(tri + 9 * i + 3), v2 = ld3(tri + 9 * i + 6);
+    const vec3f edge1 = v1 - v0, edge2 = v2 - v0;
+    const vec3f o = ld3(origin + 3 * i), d = ld3(dir + 3 * i);
+    const vec3f h = w_cross(d, edge2);
+    const float det = w_dot(edge1, h);
+    const float f = 1.0f / det;
+    const vec3f s = o - v0;
+    const float u = f * w_dot(s, h);
+    const vec3f q = w_cross(s, edge1);
+    const float v = f * w_dot(d, q);
+    const float t = f * w_dot(edge2, q);
+    const bool ok = !(det > -LINON_EPS && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) && !(v < 0.0f || u + v > 1.0f) &&
+                    (t > LINON_EPS);
+    t_out[i] = ok ? t : -1.0f;
+}

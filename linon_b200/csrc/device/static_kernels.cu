@@ -1,0 +1,250 @@
+// static_kernels.cu — kernels that do not depend on the field function (compiled ahead of time by nvcc
+// for sm_100a and linked into liblinon_b200.so).
+//
+//   overlay_kernel       Lyapunov-exponent overlay, src/overlay.wgsl:99-146 (overlay_desktop).  HBM-bound
+//                        stencil: 28 algorithmic bytes per pixel in mode 1 (4 colour in, 16 endpoint in, 4 colour
+//                        out, 4 exponent out), 8 in mode 0.  Endpoints are staged per CTA into shared memory
+//                        (tile + halo of `delta`, three float planes) so every texel is fetched from L2/HBM once
+//                        per tile instead of four times.
+//   outline_search       the eight extreme / first-hit searches over exponents >= 0.8 that pick the "Outline"
+//                        sample rays (src/main_view.wgsl:381-468), restated as ONE parallel arg-reduction with
+//                        the intended stride W instead of eight serial W*H scans.
+//   click_positions      sample-ray positions around the clicked fragment, src/main_view.wgsl:469-472.
+//   fp32_peak_kernel     FFMA-chain microbenchmark: the measured FP32 roofline denominator.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "static_kernels.h"
+
+namespace linon {
+
+// ------------------------------------------------------------------------------------------------------------
+// overlay
+// ------------------------------------------------------------------------------------------------------------
+constexpr int OV_TX = 32;   // tile width  (pixels)
+constexpr int OV_TY = 16;   // tile height (pixels)
+constexpr int OV_MAX_DELTA = 10;  // GUI slider range, src/application.rs:297
+constexpr int OV_SW = OV_TX + 2 * OV_MAX_DELTA;
+constexpr int OV_SH = OV_TY + 2 * OV_MAX_DELTA;
+
+__device__ __forceinline__ unsigned char ov_unorm8(float x) {
+    x = fminf(fmaxf(x, 0.0f), 1.0f);
+    return (unsigned char)__float2int_rn(x * 255.0f);
+}
+
+// src/overlay.wgsl:15-35 (vec2squareroots) on a = (det, -trace)
+__device__ __forceinline__ float2 vec2squareroots(float a0, float a1) {
+    const float discrim = a1 * a1 - 4.0f * a0;
+    if (discrim >= 0.0f) {
+        const float root = sqrtf(discrim);
+        return make_float2((-a1 - root) / 2.0f, (-a1 + root) / 2.0f);
+    }
+    const float root = sqrtf(-discrim);
+    return make_float2(-a1 / 2.0f, root / 2.0f);
+}
+
+__global__ void __launch_bounds__(OV_TX * 8)
+overlay_kernel(int W, int H, int overlay_mode, int delta, float scaling, const uchar4* __restrict__ raycast,
+               const float4* __restrict__ endpoint, uchar4* __restrict__ final_rgba, float* __restrict__ exponents) {
+    __shared__ float s_x[OV_SH][OV_SW + 1];
+    __shared__ float s_y[OV_SH][OV_SW + 1];
+    __shared__ float s_z[OV_SH][OV_SW + 1];
+
+    const int x0 = blockIdx.x * OV_TX, y0 = blockIdx.y * OV_TY;
+    const int tid = threadIdx.y * OV_TX + threadIdx.x;
+    const bool stencil = overlay_mode == 1;
+    if (stencil) {
+        const int sw = OV_TX + 2 * delta, sh = OV_TY + 2 * delta;
+        for (int i = tid; i < sw * sh; i += OV_TX * 8) {
+            const int sy = i / sw, sx = i - sy * sw;
+            const int gx = x0 + sx - delta, gy = y0 + sy - delta;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                const float4 e = __ldg(endpoint + (size_t)gy * W + gx);
+                s_x[sy][sx] = e.x; s_y[sy][sx] = e.y; s_z[sy][sx] = e.z;
+            }
+        }
+        __syncthreads();
+    }
+    const int padding = 2 * delta;
+#pragma unroll
+    for (int r = 0; r < OV_TY / 8; ++r) {
+        const int ly = threadIdx.y + 8 * r;
+        const int x = x0 + threadIdx.x, y = y0 + ly;
+        if (x >= W || y >= H) continue;
+        const size_t idx = (size_t)y * W + x;
+        uchar4 c = raycast[idx];
+        const bool inner = !(x < padding || y < padding || x >= W - padding || y >= H - padding);
+        if (stencil && inner) {
+            const int sx = threadIdx.x + delta, sy = ly + delta;
+            // lyapunov_exponent, src/overlay.wgsl:99-112
+            const float gxx = 0.5f * (s_x[sy][sx + delta] - s_x[sy][sx - delta]);
+            const float gxy = 0.5f * (s_y[sy][sx + delta] - s_y[sy][sx - delta]);
+            const float gxz = 0.5f * (s_z[sy][sx + delta] - s_z[sy][sx - delta]);
+            const float gyx = 0.5f * (s_x[sy + delta][sx] - s_x[sy - delta][sx]);
+            const float gyy = 0.5f * (s_y[sy + delta][sx] - s_y[sy - delta][sx]);
+            const float gyz = 0.5f * (s_z[sy + delta][sx] - s_z[sy - delta][sx]);
+            const float m00 = gxx * gxx + gxy * gxy + gxz * gxz;
+            const float m01 = gxx * gyx + gxy * gyy + gxz * gyz;
+            const float m11 = gyx * gyx + gyy * gyy + gyz * gyz;
+            const float det = m00 * m11 - m01 * m01;       // mat2det, src/overlay.wgsl:4-6
+            const float2 eig = vec2squareroots(det, -(m00 + m11));
+            const float exponent = sqrtf(fmaxf(eig.x, eig.y));
+            const float scaled = expf(scaling * exponent - 5.0f);
+            exponents[idx] = scaled;                        // stride W (the reference uses size.y)
+            if (scaled >= 0.8f) {
+                const float alpha = fminf(1.0f, scaled) * 0.5f;
+                const float inv = 1.0f - alpha;
+                c = make_uchar4(ov_unorm8(alpha * 1.0f + inv * ((float)c.x / 255.0f)),
+                                ov_unorm8(alpha * 1.0f + inv * ((float)c.y / 255.0f)),
+                                ov_unorm8(alpha * 1.0f + inv * ((float)c.z / 255.0f)),
+                                ov_unorm8(alpha * 1.0f + inv * ((float)c.w / 255.0f)));
+            }
+        }
+        final_rgba[idx] = c;
+    }
+}
+
+void launch_overlay(cudaStream_t stream, int W, int H, int overlay_mode, int delta, float scaling, const void* raycast,
+                    const void* endpoint, void* final_rgba, float* exponents) {
+    dim3 block(OV_TX, 8), grid((W + OV_TX - 1) / OV_TX, (H + OV_TY - 1) / OV_TY);
+    overlay_kernel<<<grid, block, 0, stream>>>(W, H, overlay_mode, delta, scaling, (const uchar4*)raycast,
+                                               (const float4*)endpoint, (uchar4*)final_rgba, exponents);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// outline search: 8 simultaneous arg-reductions.  Keys are 64-bit, larger wins, 0 = nothing found.
+//   "max sum, last in scan order (x outer, y inner)"  -> (sum, x, y) lexicographic maximum
+//   "first found in scan order (a outer, b inner)"    -> (a, b) lexicographic minimum, stored inverted
+// ------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long KEY_VALID = 1ull << 63;
+__device__ __forceinline__ unsigned long long key3(unsigned int a, unsigned int b, unsigned int c) {
+    return KEY_VALID | ((unsigned long long)a << 42) | ((unsigned long long)b << 21) | (unsigned long long)c;
+}
+constexpr unsigned int M21 = (1u << 21) - 1u;
+
+__global__ void __launch_bounds__(256) outline_search_kernel(int W, int H, const float* __restrict__ exponents,
+                                                             unsigned long long* __restrict__ keys) {
+    unsigned long long best[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t n = (size_t)W * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!(exponents[i] >= 0.8f)) continue;
+        const unsigned int y = (unsigned int)(i / W), x = (unsigned int)(i - (size_t)y * W);
+        const unsigned int uw = (unsigned int)W, uh = (unsigned int)H;
+        unsigned long long k[8];
+        k[0] = key3((uw - x) + y, x, y);                   // bottom left   :385-394
+        k[1] = key3(0, M21 - (uh - 1 - y), M21 - x);       // bottom middle :395-404 (rows from the bottom)
+        k[2] = key3(x + y, x, y);                          // bottom right  :405-414
+        k[3] = key3(0, M21 - (uw - 1 - x), M21 - y);       // middle right  :415-424
+        k[4] = key3(x + (uh - y), x, y);                   // top right     :425-434
+        k[5] = key3(0, M21 - y, M21 - x);                  // top middle    :435-444
+        k[6] = key3((uw - x) + (uh - y), x, y);            // top left      :445-454
+        k[7] = key3(0, M21 - x, M21 - y);                  // middle left   :455-464
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = best[j] > k[j] ? best[j] : k[j];
+    }
+    __shared__ unsigned long long s_best[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        unsigned long long v = best[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+            v = v > other ? v : other;
+        }
+        if (lane == 0) s_best[j][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        unsigned long long v = 0;
+        for (int w = 0; w < 8; ++w) v = v > s_best[threadIdx.x][w] ? v : s_best[threadIdx.x][w];
+        if (v) atomicMax(keys + threadIdx.x, v);
+    }
+}
+
+// keys -> normalised positions, src/main_view.wgsl:467-468
+__global__ void outline_finalize_kernel(int W, int H, const unsigned long long* __restrict__ keys, float* __restrict__ pos16) {
+    const int j = threadIdx.x;
+    if (j >= 8) return;
+    const unsigned long long k = keys[j];
+    float px = 0.0f, py = 0.0f;
+    if (k & KEY_VALID) {
+        const unsigned int b = (unsigned int)(k >> 21) & M21, c = (unsigned int)k & M21;
+        unsigned int x, y;
+        switch (j) {
+            case 1: y = (unsigned int)H - 1 - (M21 - b); x = M21 - c; break;
+            case 3: x = (unsigned int)W - 1 - (M21 - b); y = M21 - c; break;
+            case 5: y = M21 - b; x = M21 - c; break;
+            case 7: x = M21 - b; y = M21 - c; break;
+            default: x = b; y = c; break;
+        }
+        px = (float)x; py = (float)y;
+    }
+    const float width = (float)W, height = (float)H;
+    pos16[2 * j] = px / (width - 1.0f);
+    pos16[2 * j + 1] = (height - 1.0f - py) / (height - 1.0f);
+}
+
+void launch_outline_search(cudaStream_t stream, int W, int H, const float* exponents, unsigned long long* keys,
+                           float* pos16, int n_sm) {
+    cudaMemsetAsync(keys, 0, 8 * sizeof(unsigned long long), stream);
+    const size_t n = (size_t)W * H;
+    int blocks = (int)((n + 255) / 256);
+    const int cap = n_sm * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    outline_search_kernel<<<blocks, 256, 0, stream>>>(W, H, exponents, keys);
+    outline_finalize_kernel<<<1, 32, 0, stream>>>(W, H, keys, pos16);
+}
+
+// src/main_view.wgsl:316-325, :470-471
+__global__ void click_positions_kernel(float mouse_x, float mouse_y, float* __restrict__ pos16) {
+    const float table[8][2] = {{-1.0f, -1.0f}, {0.0f, -1.0f}, {1.0f, -1.0f}, {1.0f, 0.0f},
+                               {1.0f, 1.0f},   {0.0f, 1.0f},  {-1.0f, 1.0f}, {-1.0f, 0.0f}};
+    const int j = threadIdx.x;
+    if (j >= 8) return;
+    pos16[2 * j] = mouse_x + 0.01f * table[j][0];
+    pos16[2 * j + 1] = mouse_y + 0.01f * table[j][1];
+}
+
+void launch_click_positions(cudaStream_t stream, float mouse_x, float mouse_y, float* pos16) {
+    click_positions_kernel<<<1, 32, 0, stream>>>(mouse_x, mouse_y, pos16);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FP32 peak microbenchmark: 8 independent FFMA chains per thread, no memory traffic in the loop.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float a, float b, float* out) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f;
+    float x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123456.789f) out[0] = s;  // keeps the chains alive without a store on the hot path
+}
+
+double run_fp32_peak(int n_sm, int iters, float* d_scratch, float* ms_out) {
+    const int blocks = n_sm * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp32_peak_kernel<<<blocks, 256>>>(iters / 8 + 1, 0.999f, 0.001f, d_scratch);  // warm-up
+    cudaEventRecord(e0);
+    fp32_peak_kernel<<<blocks, 256>>>(iters, 0.999f, 0.001f, d_scratch);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+    return flops / (ms * 1e-3) * 1e-12;  // TFLOP/s
+}
+
+}  // namespace linon

@@ -1,0 +1,872 @@
+// capi.cpp — implementation of include/linon_b200.h: the device-facing half of the reference's MainView
+// (src/main_view.rs:53-849) on CUDA.  wgpu textures/buffers become linear device buffers, the WGSL splice +
+// pipeline rebuild (:649-690, :852-861) becomes WGSL->CUDA translation + NVRTC JIT for sm_100a with a variant
+// cache, the two compute dispatches of MainView::render (:831-849) become the march kernel (+ sample rays on a
+// second stream) and the overlay kernel.
+//
+// There is no CPU fallback: without libcuda.so.1 and a device every entry point that needs one fails with
+// LINON_ERR_NO_DRIVER.
+
+#include "../../../include/linon_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../device/static_kernels.h"
+#include "functions.hpp"
+#include "wgsl_translate.h"
+
+namespace {
+
+#include "embedded_sources.inc"  // kPreludeSrc, kMarchSrc (generated from device/*.cuh by build.py)
+
+std::string g_create_error;
+
+std::string fmt(const char* f, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof(buf), f, ap);
+    va_end(ap);
+    return buf;
+}
+
+// ---- CUDA driver API, loaded at run time so the library itself loads on a machine without a driver ---------
+struct Driver {
+    void* lib = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                             void**, void**) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    std::string error;
+
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) {
+            error = "libcuda.so.1 not found: a CUDA driver and a B200 are required (no CPU fallback)";
+            return false;
+        }
+        auto sym = [&](const char* n) { return dlsym(lib, n); };
+        ModuleLoadData = (decltype(ModuleLoadData))sym("cuModuleLoadData");
+        ModuleUnload = (decltype(ModuleUnload))sym("cuModuleUnload");
+        ModuleGetFunction = (decltype(ModuleGetFunction))sym("cuModuleGetFunction");
+        LaunchKernel = (decltype(LaunchKernel))sym("cuLaunchKernel");
+        GetErrorString = (decltype(GetErrorString))sym("cuGetErrorString");
+        FuncGetAttribute = (decltype(FuncGetAttribute))sym("cuFuncGetAttribute");
+        OccupancyMaxActiveBlocksPerMultiprocessor =
+            (decltype(OccupancyMaxActiveBlocksPerMultiprocessor))sym("cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString ||
+            !FuncGetAttribute || !OccupancyMaxActiveBlocksPerMultiprocessor) {
+            error = "libcuda.so.1 lacks a required entry point";
+            dlclose(lib);
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+    std::string err_str(CUresult r) {
+        const char* s = nullptr;
+        if (GetErrorString) GetErrorString(r, &s);
+        return s ? s : "unknown driver error";
+    }
+};
+Driver g_drv;
+std::mutex g_drv_mutex;
+
+// ---- device-side parameter blocks (must match device/march_kernels.cuh) -------------------------------------
+struct MarchParamsH {
+    float cam_origin[4], cam_view[4], cam_up[4];
+    linon_settings settings;
+    int width, height, local_rows, shard_rank, shard_world, rows_per_block;
+    const void* tris;
+    void* raycast;
+    void* endpoint;
+    int* hit_id;
+    unsigned long long* counters;
+    unsigned int* work;
+    int* q_pixel;
+    void* q_state;
+    unsigned int q_capacity;
+    unsigned int n_ray_slots;
+};
+struct SampleParamsH {
+    MarchParamsH march;
+    const float* pos16;
+    void* ray_samples;
+};
+static_assert(sizeof(linon_camera) == 112, "CameraUniform is 112 bytes (src/main_view.rs:12-19)");
+static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view.rs:43-51)");
+
+struct Variant {
+    float h_initial;
+    int adaptive, n_faces, math, block, unroll, refill_min, max_regs;
+};
+
+struct Module {
+    CUmodule mod = nullptr;
+    CUfunction tiles = nullptr, persistent = nullptr, sample = nullptr, eval_field = nullptr, eval_helper = nullptr,
+               eval_hit = nullptr;
+    int regs_tiles = 0, regs_persistent = 0;
+};
+
+const char kFieldHead[] =
+    "__device__ __forceinline__ vec3f field_function(const vec3f p_prev, const vec3f p, const vec3f v0, const vec3f v,\n"
+    "                                                const float t, const WgslSettings& settings, const WgslCamera& camera) {\n"
+    "#line 1 \"field_function.wgsl\"\n";
+const char kFieldTail[] = "\n}\n#line 1 \"march_kernels.cuh\"\n";
+
+std::string build_source(const std::string& cuda_body) {
+    std::string s;
+    s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + cuda_body.size() + 512);
+    s += "#line 1 \"wgsl_prelude.cuh\"\n";
+    s += kPreludeSrc;
+    s += "\n";
+    s += kFieldHead;
+    s += cuda_body;
+    s += kFieldTail;
+    s += kMarchSrc;
+    return s;
+}
+
+std::string float_literal(float x) {
+    char b[64];
+    snprintf(b, sizeof(b), "%.9gf", (double)x);
+    std::string s = b;
+    if (s.find('.') == std::string::npos && s.find('e') == std::string::npos) s.insert(s.size() - 1, ".0");
+    return s;
+}
+
+// Translate + NVRTC compile to an sm_100a cubin.  No device needed.
+bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector<char>& cubin, std::string& log) {
+    std::string cuda_body, terr;
+    if (!linon::translate_wgsl_body(wgsl_body, cuda_body, terr)) {
+        log = terr;
+        return false;
+    }
+    const std::string src = build_source(cuda_body);
+    nvrtcProgram prog = nullptr;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "linon_march.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+        log = "nvrtcCreateProgram failed";
+        return false;
+    }
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+                                     "-DLINON_H_INITIAL=" + float_literal(var.h_initial),
+                                     "-DLINON_ADAPTIVE=" + std::to_string(var.adaptive),
+                                     "-DLINON_N_FACES=" + std::to_string(var.n_faces),
+                                     "-DLINON_FACE_UNROLL=" + std::to_string(var.unroll),
+                                     "-DLINON_BLOCK=" + std::to_string(var.block),
+                                     "-DLINON_REFILL_MIN=" + std::to_string(var.refill_min)};
+    if (var.math == 0) {
+        opts.insert(opts.end(), {"--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
+    } else if (var.math == 1) {
+        opts.insert(opts.end(), {"--fmad=true", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
+    } else {
+        opts.push_back("--use_fast_math");
+    }
+    if (var.max_regs > 0) opts.push_back("--maxrregcount=" + std::to_string(var.max_regs));
+    std::vector<const char*> copts;
+    for (auto& o : opts) copts.push_back(o.c_str());
+    const nvrtcResult rc = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    std::string full_log(log_size, '\0');
+    if (log_size > 1) nvrtcGetProgramLog(prog, &full_log[0]);
+    if (rc != NVRTC_SUCCESS) {
+        // keep the diagnostics that point into the user's body first; fall back to the whole log
+        std::string mine;
+        size_t pos = 0;
+        while (pos < full_log.size()) {
+            size_t e = full_log.find('\n', pos);
+            if (e == std::string::npos) e = full_log.size();
+            const std::string line = full_log.substr(pos, e - pos);
+            if (line.find("field_function.wgsl") != std::string::npos) mine += line + "\n";
+            pos = e + 1;
+        }
+        log = mine.empty() ? full_log : mine;
+        if (log.empty()) log = nvrtcGetErrorString(rc);
+        nvrtcDestroyProgram(&prog);
+        return false;
+    }
+    size_t n = 0;
+    nvrtcGetCUBINSize(prog, &n);
+    cubin.resize(n);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    log = full_log;
+    return true;
+}
+
+std::string variant_key(const std::string& body, const Variant& v) {
+    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.math, v.block, v.unroll,
+               v.refill_min, v.max_regs) + body;
+}
+
+}  // namespace
+
+// =============================================================================================================
+struct linon_view {
+    int device = 0;
+    int sm_count = 0;
+    uint32_t W = 0, H = 0;
+    cudaStream_t stream = nullptr, aux = nullptr;
+    cudaEvent_t ev[10] = {};  // 0,1 march  2,3 overlay  4,5 sample rays  6,7 outline  8 pos ready  9 aux done
+    bool ran_march = false, ran_overlay = false, ran_sample = false, ran_outline = false;
+
+    linon_camera camera{};
+    bool has_camera = false;
+    linon_settings settings{};
+    uint32_t n_faces = 0;
+    void* d_tris = nullptr;
+
+    void *d_final = nullptr, *d_raycast = nullptr, *d_endpoint = nullptr;
+    float* d_exponents = nullptr;
+    int* d_hit = nullptr;
+    void* d_ray_samples = nullptr;
+    float* d_pos16 = nullptr;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* d_outline_keys = nullptr;
+    unsigned int* d_work = nullptr;
+    int* d_q_pixel = nullptr;
+    void* d_q_state = nullptr;
+    size_t q_capacity = 0;
+
+    uint32_t shard_rank = 0, shard_world = 1, rows_per_block = 32;
+    uint32_t local_rows = 0;
+
+    std::string body;  // current WGSL body
+    std::map<std::string, Module> modules;
+
+    int opt_math = 1, opt_kernel = 1, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
+        opt_max_regs = 0;
+
+    linon_timings timings{};
+    uint64_t last_rays = 0;
+    std::string error;
+
+    int fail(int code, const std::string& msg) {
+        error = msg;
+        return code;
+    }
+};
+
+namespace {
+
+#define CK(v, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return (v)->fail(LINON_ERR_CUDA, fmt("%s failed: %s", #call, cudaGetErrorString(e__)));     \
+    } while (0)
+
+uint32_t count_local_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t rpb) {
+    uint32_t n = 0;
+    for (uint32_t b = 0, y = 0; y < H; ++b, y += rpb)
+        if (b % world == rank) n += (y + rpb <= H) ? rpb : (H - y);
+    return n;
+}
+
+void free_frame_buffers(linon_view* v) {
+    cudaFree(v->d_final); cudaFree(v->d_raycast); cudaFree(v->d_endpoint); cudaFree(v->d_exponents);
+    cudaFree(v->d_hit); cudaFree(v->d_q_pixel); cudaFree(v->d_q_state);
+    v->d_final = v->d_raycast = v->d_endpoint = nullptr;
+    v->d_exponents = nullptr; v->d_hit = nullptr; v->d_q_pixel = nullptr; v->d_q_state = nullptr;
+    v->q_capacity = 0;
+}
+
+int alloc_queue(linon_view* v) {
+    v->local_rows = count_local_rows(v->H, v->shard_rank, v->shard_world, v->rows_per_block);
+    const size_t cap = (size_t)v->local_rows * v->W;
+    if (cap == v->q_capacity && v->d_q_pixel) return LINON_OK;
+    cudaFree(v->d_q_pixel); cudaFree(v->d_q_state);
+    v->d_q_pixel = nullptr; v->d_q_state = nullptr; v->q_capacity = 0;
+    if (cap == 0) return LINON_OK;
+    CK(v, cudaMalloc(&v->d_q_pixel, cap * sizeof(int)));
+    CK(v, cudaMalloc(&v->d_q_state, cap * 3 * 16));
+    v->q_capacity = cap;
+    return LINON_OK;
+}
+
+int alloc_frame_buffers(linon_view* v, uint32_t W, uint32_t H) {
+    free_frame_buffers(v);
+    v->W = W; v->H = H;
+    const size_t n = (size_t)W * H;
+    CK(v, cudaMalloc(&v->d_final, n * 4));
+    CK(v, cudaMalloc(&v->d_raycast, n * 4));
+    CK(v, cudaMalloc(&v->d_endpoint, n * 16));
+    CK(v, cudaMalloc(&v->d_exponents, n * 4));
+    CK(v, cudaMalloc(&v->d_hit, n * 4));
+    CK(v, cudaMemsetAsync(v->d_final, 0, n * 4, v->stream));
+    CK(v, cudaMemsetAsync(v->d_raycast, 0, n * 4, v->stream));
+    CK(v, cudaMemsetAsync(v->d_endpoint, 0, n * 16, v->stream));
+    CK(v, cudaMemsetAsync(v->d_exponents, 0, n * 4, v->stream));  // wgpu zero-initialises buffers
+    CK(v, cudaMemsetAsync(v->d_hit, 0xFF, n * 4, v->stream));
+    return alloc_queue(v);
+}
+
+int get_module(linon_view* v, const std::string& body, const Variant& var, Module** out, float* jit_ms) {
+    const std::string key = variant_key(body, var);
+    auto it = v->modules.find(key);
+    if (it != v->modules.end()) {
+        *out = &it->second;
+        return LINON_OK;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_cubin(body, var, cubin, log)) return v->fail(LINON_ERR_COMPILE, log);
+    Module m;
+    CUresult r = g_drv.ModuleLoadData(&m.mod, cubin.data());
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
+    struct { const char* name; CUfunction* f; } fns[] = {
+        {"linon_march_tiles", &m.tiles},       {"linon_march_persistent", &m.persistent},
+        {"linon_sample_rays", &m.sample},      {"linon_eval_field", &m.eval_field},
+        {"linon_eval_helper", &m.eval_helper}, {"linon_eval_hit_triangle", &m.eval_hit}};
+    for (auto& f : fns) {
+        r = g_drv.ModuleGetFunction(f.f, m.mod, f.name);
+        if (r != CUDA_SUCCESS) {
+            g_drv.ModuleUnload(m.mod);
+            return v->fail(LINON_ERR_CUDA, fmt("cuModuleGetFunction(%s): %s", f.name, g_drv.err_str(r).c_str()));
+        }
+    }
+    g_drv.FuncGetAttribute(&m.regs_tiles, CU_FUNC_ATTRIBUTE_NUM_REGS, m.tiles);
+    g_drv.FuncGetAttribute(&m.regs_persistent, CU_FUNC_ATTRIBUTE_NUM_REGS, m.persistent);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (jit_ms) *jit_ms += std::chrono::duration<float, std::milli>(t1 - t0).count();
+    auto ins = v->modules.emplace(key, m);
+    *out = &ins.first->second;
+    return LINON_OK;
+}
+
+Variant make_variant(const linon_view* v, uint32_t flags) {
+    Variant var;
+    var.h_initial = (flags & LINON_RENDER_ENHANCE) ? 0.001f : 0.1f;  // src/main_view.rs:785-787
+    // adaptive sampling can only act while h_initial > 0.002 (src/main_view.wgsl:252,267)
+    var.adaptive = (!(flags & LINON_RENDER_ADAPTIVE_OFF) && var.h_initial > 0.002f) ? 1 : 0;
+    var.n_faces = (int)v->n_faces;
+    var.math = v->opt_math;
+    var.block = v->opt_block;
+    var.unroll = v->opt_unroll;
+    var.refill_min = v->opt_refill_min;
+    var.max_regs = v->opt_max_regs;
+    return var;
+}
+
+void fill_march_params(const linon_view* v, MarchParamsH& P) {
+    memset(&P, 0, sizeof(P));
+    memcpy(P.cam_origin, v->camera.origin, 16);
+    memcpy(P.cam_view, v->camera.view_direction, 16);
+    memcpy(P.cam_up, v->camera.up, 16);
+    P.settings = v->settings;
+    P.width = (int)v->W; P.height = (int)v->H;
+    P.local_rows = (int)v->local_rows;
+    P.shard_rank = (int)v->shard_rank; P.shard_world = (int)v->shard_world; P.rows_per_block = (int)v->rows_per_block;
+    P.tris = v->d_tris;
+    P.raycast = v->d_raycast; P.endpoint = v->d_endpoint; P.hit_id = v->d_hit;
+    P.counters = v->d_counters;
+    P.work = v->d_work; P.q_pixel = v->d_q_pixel; P.q_state = v->d_q_state;
+    P.q_capacity = (unsigned int)v->q_capacity;
+    const unsigned int tiles_x = (v->W + 7) / 8, tiles_y = (v->local_rows + 3) / 4;
+    P.n_ray_slots = tiles_x * tiles_y * 32u;
+}
+
+int launch(linon_view* v, CUfunction f, unsigned grid, unsigned block, cudaStream_t s, void* params) {
+    void* args[] = {params};
+    const CUresult r = g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)s, args, nullptr);
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel: " + g_drv.err_str(r));
+    return LINON_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+const char* linon_last_error(const linon_view* v) { return v ? v->error.c_str() : g_create_error.c_str(); }
+
+int linon_create(int device, uint32_t width, uint32_t height, linon_view** out) {
+    if (!out || width < 2 || height < 2) {
+        g_create_error = "linon_create: need out != NULL and width, height >= 2";
+        return LINON_ERR_INVALID;
+    }
+    *out = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_drv_mutex);
+        if (!g_drv.load()) {
+            g_create_error = g_drv.error;
+            return LINON_ERR_NO_DRIVER;
+        }
+    }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || device < 0 || device >= n_dev) {
+        g_create_error = fmt("CUDA device %d not available (%d devices, %s): no CPU fallback", device, n_dev,
+                             cudaGetErrorString(e));
+        return LINON_ERR_NO_DRIVER;
+    }
+    std::unique_ptr<linon_view> v(new linon_view);
+    v->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = fmt("%s: %s", what, cudaGetErrorString(err));
+        return LINON_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaFree(nullptr)) != cudaSuccess) return bail("context init", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        g_create_error = fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                             prop.minor);
+        return LINON_ERR_NO_DRIVER;
+    }
+    v->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&v->aux, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    for (auto& ev : v->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaMalloc(&v->d_ray_samples, 800 * 32)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(v->d_ray_samples, 0, 800 * 32);
+    if ((e = cudaMalloc(&v->d_pos16, 64)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(v->d_pos16, 0, 64);
+    if ((e = cudaMalloc(&v->d_counters, 3 * 8)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(v->d_counters, 0, 24);
+    if ((e = cudaMalloc(&v->d_outline_keys, 8 * 8)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&v->d_work, 64)) != cudaSuccess) return bail("cudaMalloc", e);
+    // start-up state of MainView::new
+    v->settings = linon_settings{1.0f, {0.5f, 0.6f}, 0, 1, 50.0f};                 // src/main_view.rs:133-139
+    v->body = linon::to_code(linon::PredefinedFunction::MirageSphericalSigmoid);   // src/main_view.rs:100
+    const int rc = alloc_frame_buffers(v.get(), width, height);
+    if (rc != LINON_OK) {
+        g_create_error = v->error;
+        return rc;
+    }
+    *out = v.release();
+    return LINON_OK;
+}
+
+void linon_destroy(linon_view* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaStreamSynchronize(v->stream);
+    cudaStreamSynchronize(v->aux);
+    for (auto& kv : v->modules) g_drv.ModuleUnload(kv.second.mod);
+    free_frame_buffers(v);
+    cudaFree(v->d_tris); cudaFree(v->d_ray_samples); cudaFree(v->d_pos16); cudaFree(v->d_counters);
+    cudaFree(v->d_outline_keys); cudaFree(v->d_work);
+    for (auto& ev : v->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(v->stream);
+    cudaStreamDestroy(v->aux);
+    delete v;
+}
+
+int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces) {
+    if (!v || !verts || !faces || n_faces == 0) return v ? v->fail(LINON_ERR_INVALID, "linon_set_mesh: null/empty mesh") : LINON_ERR_INVALID;
+    if (n_faces > 1024) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: more than 1024 faces do not fit the shared-memory mesh stage");
+    // {v0, e1, e2} per face; the two subtractions are the ones hit_triangle performs (src/main_view.wgsl:152-153)
+    std::vector<float> tris((size_t)n_faces * 12, 0.0f);
+    for (uint32_t i = 0; i < n_faces; ++i) {
+        const uint32_t ia = faces[3 * i], ib = faces[3 * i + 1], ic = faces[3 * i + 2];
+        if (ia >= n_verts || ib >= n_verts || ic >= n_verts) return v->fail(LINON_ERR_INVALID, fmt("face %u indexes past the vertex array", i));
+        const float* a = verts + 3 * ia; const float* b = verts + 3 * ib; const float* c = verts + 3 * ic;
+        float* t = tris.data() + 12 * i;
+        for (int k = 0; k < 3; ++k) {
+            t[k] = a[k];
+            t[4 + k] = b[k] - a[k];
+            t[8 + k] = c[k] - a[k];
+        }
+    }
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaStreamSynchronize(v->stream));
+    cudaFree(v->d_tris);
+    v->d_tris = nullptr;
+    CK(v, cudaMalloc(&v->d_tris, tris.size() * sizeof(float)));
+    CK(v, cudaMemcpy(v->d_tris, tris.data(), tris.size() * sizeof(float), cudaMemcpyHostToDevice));
+    v->n_faces = n_faces;
+    return LINON_OK;
+}
+
+int linon_set_camera(linon_view* v, const linon_camera* camera) {
+    if (!v || !camera) return LINON_ERR_INVALID;
+    v->camera = *camera;
+    v->has_camera = true;
+    return LINON_OK;
+}
+
+int linon_set_settings(linon_view* v, const linon_settings* settings) {
+    if (!v || !settings) return LINON_ERR_INVALID;
+    if (settings->central_difference_delta < 1 || settings->central_difference_delta > 10)
+        return v->fail(LINON_ERR_INVALID, "central_difference_delta must be in 1..10 (src/application.rs:297)");
+    v->settings = *settings;
+    return LINON_OK;
+}
+
+int linon_resize(linon_view* v, uint32_t width, uint32_t height) {
+    if (!v || width < 2 || height < 2) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaStreamSynchronize(v->stream));
+    return alloc_frame_buffers(v, width, height);
+}
+
+int linon_set_shard(linon_view* v, uint32_t rank, uint32_t world, uint32_t rows_per_block) {
+    if (!v || world == 0 || rank >= world || rows_per_block == 0) return v ? v->fail(LINON_ERR_INVALID, "linon_set_shard: bad arguments") : LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaStreamSynchronize(v->stream));
+    v->shard_rank = rank; v->shard_world = world; v->rows_per_block = rows_per_block;
+    return alloc_queue(v);
+}
+
+int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, size_t err_len) {
+    if (!v || !wgsl_body) return LINON_ERR_INVALID;
+    if (err && err_len) err[0] = '\0';
+    CK(v, cudaSetDevice(v->device));
+    // validate by building the default variant now; the previous body stays live on failure (src/main_view.rs:677-679)
+    Variant var = make_variant(v, LINON_RENDER_DEFAULT);
+    if (var.n_faces == 0) var.n_faces = 36;
+    Module* m = nullptr;
+    float jit = 0.0f;
+    const int rc = get_module(v, wgsl_body, var, &m, &jit);
+    if (rc != LINON_OK) {
+        if (err && err_len) snprintf(err, err_len, "%s", v->error.c_str());
+        return rc;
+    }
+    v->body = wgsl_body;
+    return LINON_OK;
+}
+
+int linon_render(linon_view* v, uint32_t flags) {
+    if (!v) return LINON_ERR_INVALID;
+    const bool do_march = !(flags & LINON_RENDER_NO_MARCH);
+    const bool do_overlay = !(flags & LINON_RENDER_NO_OVERLAY);
+    const bool do_sample = !(flags & LINON_RENDER_NO_SAMPLE_RAYS);
+    if ((do_march || do_sample) && (!v->d_tris || !v->has_camera))
+        return v->fail(LINON_ERR_INVALID, "linon_render: set a mesh and a camera first");
+    CK(v, cudaSetDevice(v->device));
+    v->timings = linon_timings{};
+    v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = false;
+
+    Module* mod = nullptr;
+    MarchParamsH P;
+    fill_march_params(v, P);
+    if (do_march || do_sample) {
+        const Variant var = make_variant(v, flags);
+        const int rc = get_module(v, v->body, var, &mod, &v->timings.jit_ms);
+        if (rc != LINON_OK) return rc;
+    }
+
+    if (do_sample) {
+        // sample-ray start positions: outline search over the exponents of the PREVIOUS overlay pass (the march
+        // dispatch runs before the overlay dispatch in the reference, src/main_view.rs:838-846) or the click ring
+        if (flags & LINON_RENDER_OUTLINE) {
+            CK(v, cudaEventRecord(v->ev[6], v->stream));
+            linon::launch_outline_search(v->stream, (int)v->W, (int)v->H, v->d_exponents, v->d_outline_keys, v->d_pos16,
+                                         v->sm_count);
+            CK(v, cudaEventRecord(v->ev[7], v->stream));
+            v->ran_outline = true;
+        } else {
+            linon::launch_click_positions(v->stream, v->settings.mouse_pos[0], v->settings.mouse_pos[1], v->d_pos16);
+        }
+        CK(v, cudaGetLastError());
+        CK(v, cudaEventRecord(v->ev[8], v->stream));
+        CK(v, cudaStreamWaitEvent(v->aux, v->ev[8], 0));
+        SampleParamsH S;
+        S.march = P;
+        S.pos16 = v->d_pos16;
+        S.ray_samples = v->d_ray_samples;
+        CK(v, cudaEventRecord(v->ev[4], v->aux));
+        const int rc = launch(v, mod->sample, 1, 32, v->aux, &S);
+        if (rc != LINON_OK) return rc;
+        CK(v, cudaEventRecord(v->ev[5], v->aux));
+        v->ran_sample = true;
+    }
+
+    if (do_march && v->local_rows > 0) {
+        CK(v, cudaMemsetAsync(v->d_counters, 0, 24, v->stream));
+        unsigned grid, block = (unsigned)v->opt_block;
+        CUfunction f;
+        if (v->opt_kernel == 1) {
+            CK(v, cudaMemsetAsync(v->d_work, 0, 64, v->stream));
+            CK(v, cudaMemsetAsync(v->d_q_pixel, 0xFF, v->q_capacity * sizeof(int), v->stream));
+            int per_sm = v->opt_ctas_per_sm;
+            if (per_sm <= 0) {
+                const CUresult r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mod->persistent, (int)block, 0);
+                if (r != CUDA_SUCCESS || per_sm <= 0) return v->fail(LINON_ERR_CUDA, "occupancy query failed: " + g_drv.err_str(r));
+            }
+            grid = (unsigned)(per_sm * v->sm_count);
+            const unsigned needed = (P.n_ray_slots + block - 1) / block;
+            if (grid > needed) grid = needed;
+            f = mod->persistent;
+            v->timings.march_regs = mod->regs_persistent;
+        } else {
+            grid = (P.n_ray_slots + block - 1) / block;
+            f = mod->tiles;
+            v->timings.march_regs = mod->regs_tiles;
+        }
+        v->timings.march_grid = (int)grid;
+        v->timings.march_block = (int)block;
+        CK(v, cudaEventRecord(v->ev[0], v->stream));
+        const int rc = launch(v, f, grid, block, v->stream, &P);
+        if (rc != LINON_OK) return rc;
+        CK(v, cudaEventRecord(v->ev[1], v->stream));
+        v->ran_march = true;
+        v->last_rays = (uint64_t)v->local_rows * v->W;
+    }
+
+    if (do_overlay) {
+        CK(v, cudaEventRecord(v->ev[2], v->stream));
+        linon::launch_overlay(v->stream, (int)v->W, (int)v->H, v->settings.overlay_mode, v->settings.central_difference_delta,
+                              v->settings.lyapunov_scaling, v->d_raycast, v->d_endpoint, v->d_final, v->d_exponents);
+        CK(v, cudaGetLastError());
+        CK(v, cudaEventRecord(v->ev[3], v->stream));
+        v->ran_overlay = true;
+    }
+    if (v->ran_sample) {  // join the sample-ray stream so one sync covers the frame
+        CK(v, cudaEventRecord(v->ev[9], v->aux));
+        CK(v, cudaStreamWaitEvent(v->stream, v->ev[9], 0));
+    }
+    return LINON_OK;
+}
+
+int linon_sync(linon_view* v) {
+    if (!v) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaStreamSynchronize(v->stream));
+    CK(v, cudaStreamSynchronize(v->aux));
+    return LINON_OK;
+}
+
+size_t linon_buffer_bytes(const linon_view* v, int buffer) {
+    if (!v) return 0;
+    const size_t n = (size_t)v->W * v->H;
+    switch (buffer) {
+        case LINON_BUF_FINAL_RGBA8:
+        case LINON_BUF_RAYCAST_RGBA8:
+        case LINON_BUF_EXPONENTS_F32:
+        case LINON_BUF_HIT_ID_I32: return n * 4;
+        case LINON_BUF_ENDPOINT_F32X4: return n * 16;
+        case LINON_BUF_RAY_SAMPLES: return 800 * 32;
+        case LINON_BUF_SAMPLE_POS: return 64;
+    }
+    return 0;
+}
+
+void* linon_device_ptr(linon_view* v, int buffer) {
+    if (!v) return nullptr;
+    switch (buffer) {
+        case LINON_BUF_FINAL_RGBA8: return v->d_final;
+        case LINON_BUF_RAYCAST_RGBA8: return v->d_raycast;
+        case LINON_BUF_ENDPOINT_F32X4: return v->d_endpoint;
+        case LINON_BUF_EXPONENTS_F32: return v->d_exponents;
+        case LINON_BUF_HIT_ID_I32: return v->d_hit;
+        case LINON_BUF_RAY_SAMPLES: return v->d_ray_samples;
+        case LINON_BUF_SAMPLE_POS: return v->d_pos16;
+    }
+    return nullptr;
+}
+
+void* linon_stream(linon_view* v) { return v ? (void*)v->stream : nullptr; }
+
+int linon_read(linon_view* v, int buffer, void* dst, size_t dst_bytes) {
+    if (!v || !dst) return LINON_ERR_INVALID;
+    const size_t n = linon_buffer_bytes(v, buffer);
+    void* src = linon_device_ptr(v, buffer);
+    if (!n || !src) return v->fail(LINON_ERR_INVALID, "linon_read: unknown buffer");
+    if (dst_bytes < n) return v->fail(LINON_ERR_SIZE, fmt("linon_read: need %zu bytes, got %zu", n, dst_bytes));
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, v->stream));
+    CK(v, cudaStreamSynchronize(v->stream));
+    return LINON_OK;
+}
+
+int linon_set_option(linon_view* v, int option, int value) {
+    if (!v) return LINON_ERR_INVALID;
+    switch (option) {
+        case LINON_OPT_MATH: if (value < 0 || value > 2) break; v->opt_math = value; return LINON_OK;
+        case LINON_OPT_KERNEL: if (value < 0 || value > 1) break; v->opt_kernel = value; return LINON_OK;
+        case LINON_OPT_BLOCK: if (value < 32 || value > 1024 || value % 32) break; v->opt_block = value; return LINON_OK;
+        case LINON_OPT_CTAS_PER_SM: if (value < 0 || value > 32) break; v->opt_ctas_per_sm = value; return LINON_OK;
+        case LINON_OPT_REFILL_MIN: if (value < 1 || value > 32) break; v->opt_refill_min = value; return LINON_OK;
+        case LINON_OPT_FACE_UNROLL: if (value < 1 || value > 1024) break; v->opt_unroll = value; return LINON_OK;
+        case LINON_OPT_MAX_REGS: if (value < 0 || value > 255) break; v->opt_max_regs = value; return LINON_OK;
+    }
+    return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));
+}
+
+int linon_get_counters(linon_view* v, linon_counters* out) {
+    if (!v || !out) return LINON_ERR_INVALID;
+    unsigned long long c[3];
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaMemcpyAsync(c, v->d_counters, 24, cudaMemcpyDeviceToHost, v->stream));
+    CK(v, cudaStreamSynchronize(v->stream));
+    out->rays = v->last_rays;
+    out->accepted_steps = c[0];
+    out->prehit_steps = c[1];
+    out->rejected_steps = c[2];
+    return LINON_OK;
+}
+
+int linon_get_timings(linon_view* v, linon_timings* out) {
+    if (!v || !out) return LINON_ERR_INVALID;
+    const int rc = linon_sync(v);
+    if (rc != LINON_OK) return rc;
+    if (v->ran_march) cudaEventElapsedTime(&v->timings.march_ms, v->ev[0], v->ev[1]);
+    if (v->ran_overlay) cudaEventElapsedTime(&v->timings.overlay_ms, v->ev[2], v->ev[3]);
+    if (v->ran_sample) cudaEventElapsedTime(&v->timings.sample_rays_ms, v->ev[4], v->ev[5]);
+    if (v->ran_outline) cudaEventElapsedTime(&v->timings.outline_search_ms, v->ev[6], v->ev[7]);
+    *out = v->timings;
+    return LINON_OK;
+}
+
+int linon_translate_wgsl(const char* wgsl_body, char* out, size_t out_len, char* err, size_t err_len) {
+    if (!wgsl_body || !out) return LINON_ERR_INVALID;
+    std::string cuda, e;
+    if (!linon::translate_wgsl_body(wgsl_body, cuda, e)) {
+        if (err && err_len) snprintf(err, err_len, "%s", e.c_str());
+        return LINON_ERR_COMPILE;
+    }
+    if (cuda.size() + 1 > out_len) return LINON_ERR_SIZE;
+    memcpy(out, cuda.c_str(), cuda.size() + 1);
+    return LINON_OK;
+}
+
+int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, uint32_t n_faces, size_t* cubin_bytes,
+                        char* err, size_t err_len) {
+    if (!wgsl_body) return LINON_ERR_INVALID;
+    linon_view tmp;
+    tmp.n_faces = n_faces;
+    tmp.opt_math = math_mode;
+    const Variant var = make_variant(&tmp, flags);
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_cubin(wgsl_body, var, cubin, log)) {
+        if (err && err_len) snprintf(err, err_len, "%s", log.c_str());
+        return LINON_ERR_COMPILE;
+    }
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (const char* dump = getenv("LINON_DUMP_CUBIN")) {  // developer aid: inspect with cuobjdump -sass / -res-usage
+        if (FILE* f = fopen(dump, "wb")) {
+            fwrite(cubin.data(), 1, cubin.size(), f);
+            fclose(f);
+        }
+    }
+    if (err && err_len) snprintf(err, err_len, "%s", log.c_str());  // warnings, if any
+    return LINON_OK;
+}
+
+// ---- parity / debug ------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t up(const void* src, size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 4);
+        if (e != cudaSuccess) return e;
+        return src ? cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) : cudaMemset(p, 0, bytes);
+    }
+};
+int debug_module(linon_view* v, Module** m) {
+    Variant var = make_variant(v, LINON_RENDER_DEFAULT);
+    if (var.n_faces == 0) var.n_faces = 36;
+    return get_module(v, v->body, var, m, nullptr);
+}
+}  // namespace
+
+int linon_debug_eval_field(linon_view* v, uint32_t n, const float* p_prev, const float* p, const float* v0,
+                           const float* vel, const float* t, float* out) {
+    if (!v || !n) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    Module* m = nullptr;
+    int rc = debug_module(v, &m);
+    if (rc != LINON_OK) return rc;
+    DevBuf a, b, c, d, e, o;
+    CK(v, a.up(p_prev, n * 12)); CK(v, b.up(p, n * 12)); CK(v, c.up(v0, n * 12)); CK(v, d.up(vel, n * 12));
+    CK(v, e.up(t, n * 4)); CK(v, o.up(nullptr, n * 12));
+    int ni = (int)n;
+    linon_settings st = v->settings;
+    void* args[] = {&ni, &a.p, &b.p, &c.p, &d.p, &e.p, &st, &o.p};
+    const CUresult r = g_drv.LaunchKernel(m->eval_field, (n + 127) / 128, 1, 1, 128, 1, 1, 0, (CUstream)v->stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel(eval_field): " + g_drv.err_str(r));
+    CK(v, cudaStreamSynchronize(v->stream));
+    CK(v, cudaMemcpy(out, o.p, n * 12, cudaMemcpyDeviceToHost));
+    return LINON_OK;
+}
+
+int linon_debug_eval_helper(linon_view* v, int which, uint32_t n, const float* vec, const float* nrm, const float* p0,
+                            const float* a_, const float* b_, const float* c_, float* out) {
+    if (!v || !n) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    Module* m = nullptr;
+    int rc = debug_module(v, &m);
+    if (rc != LINON_OK) return rc;
+    DevBuf dv, dn, dp, da, db, dc, o;
+    CK(v, dv.up(vec, n * 12)); CK(v, dn.up(nrm, n * 12)); CK(v, dp.up(p0, n * 12));
+    CK(v, da.up(a_, n * 4)); CK(v, db.up(b_, n * 4)); CK(v, dc.up(c_, n * 4)); CK(v, o.up(nullptr, n * 12));
+    int ni = (int)n;
+    void* args[] = {&which, &ni, &dv.p, &dn.p, &dp.p, &da.p, &db.p, &dc.p, &o.p};
+    const CUresult r = g_drv.LaunchKernel(m->eval_helper, (n + 127) / 128, 1, 1, 128, 1, 1, 0, (CUstream)v->stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel(eval_helper): " + g_drv.err_str(r));
+    CK(v, cudaStreamSynchronize(v->stream));
+    CK(v, cudaMemcpy(out, o.p, n * 12, cudaMemcpyDeviceToHost));
+    return LINON_OK;
+}
+
+int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const float* origin, const float* dir,
+                             float* t_out) {
+    if (!v || !n) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    Module* m = nullptr;
+    int rc = debug_module(v, &m);
+    if (rc != LINON_OK) return rc;
+    DevBuf dt, dorg, dd, o;
+    CK(v, dt.up(tri9, n * 36)); CK(v, dorg.up(origin, n * 12)); CK(v, dd.up(dir, n * 12)); CK(v, o.up(nullptr, n * 4));
+    int ni = (int)n;
+    void* args[] = {&ni, &dt.p, &dorg.p, &dd.p, &o.p};
+    const CUresult r = g_drv.LaunchKernel(m->eval_hit, (n + 127) / 128, 1, 1, 128, 1, 1, 0, (CUstream)v->stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel(eval_hit): " + g_drv.err_str(r));
+    CK(v, cudaStreamSynchronize(v->stream));
+    CK(v, cudaMemcpy(t_out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return LINON_OK;
+}
+
+int linon_measure_fp32_peak(int device, double* tflops, int* sm_count) {
+    if (!tflops) return LINON_ERR_INVALID;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        g_create_error = "linon_measure_fp32_peak: no CUDA device (no CPU fallback)";
+        return LINON_ERR_NO_DRIVER;
+    }
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    float* scratch = nullptr;
+    if (cudaMalloc(&scratch, 256) != cudaSuccess) return LINON_ERR_CUDA;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        float ms = 0.0f;
+        const double t = linon::run_fp32_peak(prop.multiProcessorCount, 20000, scratch, &ms);
+        if (t > best) best = t;
+    }
+    cudaFree(scratch);
+    if (cudaGetLastError() != cudaSuccess) return LINON_ERR_CUDA;
+    *tflops = best;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return LINON_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,464 @@
+// wgsl_translate.cpp — turns the BODY of a linon field function (WGSL) into CUDA C++ that compiles
+// against device/wgsl_prelude.cuh.
+//
+// Reference contract: src/main_view.rs:852-861 splices the body text into
+//   fn field_function(p_prev: vec3<f32>, p: vec3<f32>, v0: vec3<f32>, v: vec3<f32>, t: f32) -> vec3<f32> { <body> }
+// The nine predefined bodies are src/functions.rs:36-126; the subset that must work is SURVEY Appendix A.
+//
+// The rewrite is token based and line preserving (every output line is the same source line, so NVRTC
+// diagnostics under `#line 1 "field_function.wgsl"` cite the user's own line numbers):
+//   * comments are dropped (they hold non-ASCII text in the predefined bodies), newlines kept
+//   * float literals get an `f` suffix (WGSL abstract floats concretise to f32; without it the whole
+//     expression would silently become fp64), `1f` -> `1.0f`, i32 suffix dropped, u32 suffix kept
+//   * a `let`/`const` initialiser made only of literals and + - * / ( ) is emitted as (float)(double expr):
+//     naga folds such expressions in abstract float (f64) and then concretises (e.g. `8.0 / 3.0`)
+//   * let/const/var declarations -> const auto / auto / typed C++ declarations; `var x: T;` zero-initialises
+//   * vecN<f32> / vecNf / vecN( -> vecNf, matCxR<f32> -> matCxRf, f32/i32/u32 -> float/int/unsigned
+//   * WGSL builtins called as functions -> w_<name>
+//   * multi-component swizzles .xyz/.rgb -> .xyz(); .r/.g/.b/.a -> .x/.y/.z/.w
+//   * `if cond {` / `while cond {` get their parentheses; a trailing comma before `)` is removed
+//   * identifiers that are C++ keywords get a trailing underscore
+// Anything outside the subset is passed through and reported by NVRTC against the user's line.
+
+#include "wgsl_translate.h"
+
+#include <cctype>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace linon {
+namespace {
+
+enum Kind { WS, NL, IDENT, NUMBER, PUNCT };
+
+struct Tok {
+    Kind kind;
+    std::string text;
+};
+
+const char* const kBuiltins[] = {
+    "abs", "min", "max", "clamp", "saturate", "sqrt", "inverseSqrt", "exp", "exp2", "log", "log2", "pow", "sin", "cos",
+    "tan", "asin", "acos", "atan", "atan2", "sinh", "cosh", "tanh", "floor", "ceil", "round", "trunc", "fract", "sign",
+    "step", "mix", "smoothstep", "fma", "degrees", "radians", "select", "dot", "cross", "length", "distance",
+    "normalize", "reflect", "faceForward", "transpose", "determinant"};
+
+const char* const kCppKeywords[] = {
+    "auto", "char", "class", "delete", "double", "extern", "float", "friend", "goto", "inline", "int", "long",
+    "mutable", "namespace", "new", "operator", "register", "short", "signed", "sizeof", "static", "struct",
+    "template", "this", "typedef", "union", "unsigned", "virtual", "void", "volatile", "asm", "and", "or", "not",
+    "xor", "catch", "try", "throw", "explicit", "export", "public", "private", "protected", "typename", "using",
+    "wchar_t", "nullptr", "constexpr", "decltype", "noexcept", "alignas", "alignof", "concept", "requires"};
+
+bool is_ident_start(char c) { return std::isalpha((unsigned char)c) || c == '_'; }
+bool is_ident_char(char c) { return std::isalnum((unsigned char)c) || c == '_'; }
+
+struct Lexer {
+    const std::string& s;
+    size_t i = 0;
+    std::vector<Tok> out;
+    std::string err;
+    explicit Lexer(const std::string& src) : s(src) {}
+
+    bool number() {
+        size_t j = i;
+        bool is_float = false, is_hex = false;
+        if (s[j] == '0' && j + 1 < s.size() && (s[j + 1] == 'x' || s[j + 1] == 'X')) {
+            is_hex = true;
+            j += 2;
+            while (j < s.size() && std::isxdigit((unsigned char)s[j])) ++j;
+        } else {
+            while (j < s.size() && std::isdigit((unsigned char)s[j])) ++j;
+            if (j < s.size() && s[j] == '.' && !(j + 1 < s.size() && is_ident_start(s[j + 1]) && s[j + 1] != 'e' &&
+                                                 s[j + 1] != 'E' && s[j + 1] != 'f' && s[j + 1] != 'h')) {
+                is_float = true;
+                ++j;
+                while (j < s.size() && std::isdigit((unsigned char)s[j])) ++j;
+            }
+            if (j < s.size() && (s[j] == 'e' || s[j] == 'E')) {
+                size_t k = j + 1;
+                if (k < s.size() && (s[k] == '+' || s[k] == '-')) ++k;
+                if (k < s.size() && std::isdigit((unsigned char)s[k])) {
+                    is_float = true;
+                    j = k;
+                    while (j < s.size() && std::isdigit((unsigned char)s[j])) ++j;
+                }
+            }
+        }
+        std::string body = s.substr(i, j - i);
+        char suffix = 0;
+        if (j < s.size() && (s[j] == 'f' || s[j] == 'h' || s[j] == 'i' || s[j] == 'u') &&
+            !(j + 1 < s.size() && is_ident_char(s[j + 1]))) {
+            suffix = s[j];
+            ++j;
+        }
+        if (suffix == 'h') {
+            err = "f16 literals are not supported";
+            return false;
+        }
+        std::string text;
+        if (is_hex) {
+            text = body + (suffix == 'u' ? "u" : "");
+        } else if (is_float || suffix == 'f') {
+            if (body.find('.') == std::string::npos && body.find('e') == std::string::npos &&
+                body.find('E') == std::string::npos)
+                body += ".0";
+            if (body[0] == '.') body = "0" + body;
+            text = body + "f";
+        } else {
+            text = body + (suffix == 'u' ? "u" : "");
+        }
+        out.push_back({NUMBER, text});
+        i = j;
+        return true;
+    }
+
+    bool run() {
+        static const char* const multi[] = {"<<=", ">>=", "->", "==", "!=", "<=", ">=", "&&", "||", "+=", "-=", "*=",
+                                            "/=",  "%=",  "&=", "|=", "^=", "++", "--", "<<", ">>"};
+        while (i < s.size()) {
+            const char c = s[i];
+            if (c == '\n') {
+                out.push_back({NL, "\n"});
+                ++i;
+            } else if (c == '\r') {
+                ++i;
+            } else if (c == ' ' || c == '\t') {
+                size_t j = i;
+                while (j < s.size() && (s[j] == ' ' || s[j] == '\t')) ++j;
+                out.push_back({WS, s.substr(i, j - i)});
+                i = j;
+            } else if (c == '/' && i + 1 < s.size() && s[i + 1] == '/') {
+                while (i < s.size() && s[i] != '\n') ++i;
+            } else if (c == '/' && i + 1 < s.size() && s[i + 1] == '*') {
+                int depth = 1;  // WGSL block comments nest
+                i += 2;
+                while (i < s.size() && depth > 0) {
+                    if (s[i] == '/' && i + 1 < s.size() && s[i + 1] == '*') {
+                        ++depth;
+                        i += 2;
+                    } else if (s[i] == '*' && i + 1 < s.size() && s[i + 1] == '/') {
+                        --depth;
+                        i += 2;
+                    } else {
+                        if (s[i] == '\n') out.push_back({NL, "\n"});
+                        ++i;
+                    }
+                }
+                if (depth > 0) {
+                    err = "unterminated block comment";
+                    return false;
+                }
+                out.push_back({WS, " "});
+            } else if (is_ident_start(c)) {
+                size_t j = i;
+                while (j < s.size() && is_ident_char(s[j])) ++j;
+                out.push_back({IDENT, s.substr(i, j - i)});
+                i = j;
+            } else if (std::isdigit((unsigned char)c) ||
+                       (c == '.' && i + 1 < s.size() && std::isdigit((unsigned char)s[i + 1]))) {
+                if (!number()) return false;
+            } else if ((unsigned char)c >= 0x80) {
+                err = "non-ASCII character outside a comment";
+                return false;
+            } else {
+                bool matched = false;
+                for (const char* m : multi) {
+                    const size_t n = std::strlen(m);
+                    if (s.compare(i, n, m) == 0) {
+                        out.push_back({PUNCT, m});
+                        i += n;
+                        matched = true;
+                        break;
+                    }
+                }
+                if (!matched) {
+                    out.push_back({PUNCT, std::string(1, c)});
+                    ++i;
+                }
+            }
+        }
+        return true;
+    }
+};
+
+struct Rewriter {
+    std::vector<Tok> t;
+    std::string err;
+    std::set<std::string> builtins, keywords;
+
+    Rewriter() {
+        for (const char* b : kBuiltins) builtins.insert(b);
+        for (const char* k : kCppKeywords) keywords.insert(k);
+    }
+
+    // index of the next / previous token that is not whitespace or a newline (-1 if none)
+    int next_sig(int i) const {
+        for (int j = i + 1; j < (int)t.size(); ++j)
+            if (t[j].kind != WS && t[j].kind != NL) return j;
+        return -1;
+    }
+    int prev_sig(int i) const {
+        for (int j = i - 1; j >= 0; --j)
+            if (t[j].kind != WS && t[j].kind != NL) return j;
+        return -1;
+    }
+    bool is_p(int i, const char* p) const { return i >= 0 && t[i].kind == PUNCT && t[i].text == p; }
+    void blank(int i) { t[i] = {WS, ""}; }
+
+    // Parses a type starting at token i; returns the C++ spelling and sets `end` to the last token used.
+    bool parse_type(int i, std::string& cpp, int& end) {
+        if (i < 0 || t[i].kind != IDENT) return false;
+        const std::string& n = t[i].text;
+        end = i;
+        auto scalar = [](const std::string& s, std::string& o) {
+            if (s == "f32") o = "float";
+            else if (s == "i32") o = "int";
+            else if (s == "u32") o = "unsigned";
+            else if (s == "bool") o = "bool";
+            else return false;
+            return true;
+        };
+        if (scalar(n, cpp)) return true;
+        const bool is_vec = n == "vec2" || n == "vec3" || n == "vec4";
+        const bool is_mat = n == "mat2x2" || n == "mat3x3";
+        if (is_vec || is_mat) {
+            const int a = next_sig(i);
+            if (is_p(a, "<")) {
+                const int b = next_sig(a), c = b >= 0 ? next_sig(b) : -1;
+                if (b < 0 || t[b].kind != IDENT || !is_p(c, ">")) return false;
+                if (t[b].text != "f32") {
+                    err = n + "<" + t[b].text + "> is not supported (only f32 vectors and matrices)";
+                    return false;
+                }
+                end = c;
+            }
+            cpp = n + "f";
+            return true;
+        }
+        if (n == "vec2f" || n == "vec3f" || n == "vec4f" || n == "mat2x2f" || n == "mat3x3f") {
+            cpp = n;
+            return true;
+        }
+        return false;
+    }
+
+    // ---- pass 1: types (vec3<f32> -> vec3f, f32( -> float( ...) --------------------------------------
+    bool pass_types() {
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT) continue;
+            const int p = prev_sig(i);
+            if (is_p(p, ".")) continue;  // member name
+            std::string cpp;
+            int end = i;
+            const std::string before = err;
+            if (parse_type(i, cpp, end)) {
+                const std::string& n = t[i].text;
+                const bool templ = end != i;
+                const bool bare_vec = (n == "vec2" || n == "vec3" || n == "vec4" || n == "mat2x2" || n == "mat3x3");
+                // a bare `vec3` is only a type when used as a constructor: vec3(...)
+                if (bare_vec && !templ && !is_p(next_sig(i), "(")) continue;
+                // f32/i32/... only as type position or cast; identifiers named e.g. `bool` cannot occur in WGSL
+                t[i].text = cpp;
+                for (int j = i + 1; j <= end; ++j) blank(j);
+            } else if (err != before) {
+                return false;
+            } else if (t[i].text == "array" || t[i].text == "ptr" || t[i].text == "atomic" ||
+                       t[i].text == "mat4x4" || t[i].text == "mat4x4f" || t[i].text == "bitcast") {
+                err = "'" + t[i].text + "' is not supported in a field function body";
+                return false;
+            }
+        }
+        return true;
+    }
+
+    bool literal_only(int a, int b) const {  // tokens (a, b) exclusive, at least one operator and one number
+        bool has_op = false, has_num = false;
+        for (int j = a + 1; j < b; ++j) {
+            if (t[j].kind == WS || t[j].kind == NL) continue;
+            if (t[j].kind == NUMBER) {
+                if (t[j].text.back() != 'f') return false;  // only float literals
+                has_num = true;
+            } else if (t[j].kind == PUNCT && (t[j].text == "+" || t[j].text == "-" || t[j].text == "*" ||
+                                              t[j].text == "/" || t[j].text == "(" || t[j].text == ")")) {
+                if (t[j].text != "(" && t[j].text != ")") has_op = true;
+            } else {
+                return false;
+            }
+        }
+        return has_op && has_num;
+    }
+
+    // ---- pass 2: declarations ------------------------------------------------------------------------------
+    bool pass_decls() {
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT) continue;
+            const std::string kw = t[i].text;
+            if (kw != "let" && kw != "var" && kw != "const") continue;
+            if (is_p(prev_sig(i), ".")) continue;
+            int n = next_sig(i);
+            if (kw == "var" && is_p(n, "<")) {  // var<function> / var<private>
+                int j = n;
+                while (j >= 0 && !is_p(j, ">")) {
+                    blank(j);
+                    j = next_sig(j);
+                }
+                if (j < 0) {
+                    err = "malformed var<...> declaration";
+                    return false;
+                }
+                blank(j);
+                n = next_sig(j);
+            }
+            if (n < 0 || t[n].kind != IDENT) {
+                err = "expected a name after '" + kw + "'";
+                return false;
+            }
+            const int name = n;
+            int after = next_sig(name);
+            std::string type;
+            if (is_p(after, ":")) {
+                const int ty = next_sig(after);
+                int end = ty;
+                // types were already rewritten by pass_types: a single IDENT token
+                if (ty < 0 || t[ty].kind != IDENT) {
+                    err = "expected a type after ':' in the declaration of '" + t[name].text + "'";
+                    return false;
+                }
+                type = t[ty].text;
+                blank(after);
+                for (int j = ty; j <= end; ++j) blank(j);
+                after = next_sig(end);
+            }
+            const bool is_const = kw != "var";
+            if (is_p(after, "=")) {
+                t[i].text = std::string(is_const ? "const " : "") + (type.empty() ? "auto" : type);
+                // literal-only initialiser: fold in double like naga's abstract-float const evaluation
+                int semi = after;
+                int depth = 0;
+                for (int j = after + 1; j < (int)t.size(); ++j) {
+                    if (is_p(j, "(")) ++depth;
+                    if (is_p(j, ")")) --depth;
+                    if (depth == 0 && (is_p(j, ";") || is_p(j, ","))) {
+                        semi = j;
+                        break;
+                    }
+                }
+                if (semi > after && type.empty() && literal_only(after, semi)) {
+                    for (int j = after + 1; j < semi; ++j)
+                        if (t[j].kind == NUMBER) t[j].text.pop_back();  // drop the f: double literal
+                    const int first = next_sig(after);
+                    t[first].text = "(float)(" + t[first].text;
+                    const int last = prev_sig(semi);
+                    t[last].text += ")";
+                }
+            } else if (is_p(after, ";")) {
+                if (type.empty()) {
+                    err = "declaration of '" + t[name].text + "' needs a type or an initialiser";
+                    return false;
+                }
+                t[i].text = type;
+                t[name].text += " = " + type + "()";  // WGSL zero-initialises
+            } else {
+                err = "malformed declaration of '" + t[name].text + "'";
+                return false;
+            }
+        }
+        return true;
+    }
+
+    // ---- pass 3: control flow parentheses --------------------------------------------------------------------
+    bool pass_control() {
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT) continue;
+            const std::string& kw = t[i].text;
+            if (kw == "loop" || kw == "continuing" || kw == "switch" || kw == "fn" || kw == "discard") {
+                if (!is_p(prev_sig(i), ".")) {
+                    err = "'" + kw + "' is not supported in a field function body (use if / for / while)";
+                    return false;
+                }
+            }
+            if (kw != "if" && kw != "while") continue;
+            const int first = next_sig(i);
+            if (first < 0) {
+                err = "dangling '" + kw + "'";
+                return false;
+            }
+            int depth = 0, brace = -1;
+            for (int j = first; j < (int)t.size(); ++j) {
+                if (is_p(j, "(")) ++depth;
+                if (is_p(j, ")")) --depth;
+                if (depth == 0 && is_p(j, "{")) {
+                    brace = j;
+                    break;
+                }
+                if (depth == 0 && is_p(j, ";")) break;
+            }
+            if (brace < 0) {
+                err = "expected '{' after the condition of '" + kw + "'";
+                return false;
+            }
+            const int last = prev_sig(brace);
+            t[first].text = "(" + t[first].text;
+            t[last].text += ")";
+        }
+        return true;
+    }
+
+    // ---- pass 4: builtins, swizzles, keywords, trailing commas --------------------------------------------------
+    bool pass_names() {
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind == PUNCT && t[i].text == ",") {
+                if (is_p(next_sig(i), ")")) blank(i);
+                continue;
+            }
+            if (t[i].kind != IDENT) continue;
+            const int p = prev_sig(i);
+            const int n = next_sig(i);
+            std::string& s = t[i].text;
+            if (is_p(p, ".")) {
+                if (is_p(n, "(")) continue;
+                const bool xyzw = s.find_first_not_of("xyzw") == std::string::npos;
+                const bool rgba = s.find_first_not_of("rgba") == std::string::npos;
+                if ((xyzw || rgba) && s.size() <= 4) {
+                    if (rgba && !xyzw)
+                        for (char& c : s) c = (c == 'r') ? 'x' : (c == 'g') ? 'y' : (c == 'b') ? 'z' : 'w';
+                    if (s.size() > 1) s += "()";
+                }
+                continue;
+            }
+            if (is_p(n, "(") && builtins.count(s)) {
+                s = "w_" + s;
+                continue;
+            }
+            if (s.find(' ') == std::string::npos && keywords.count(s)) {
+                // produced by our own rewrites? those contain these words only as whole replaced tokens
+                if (!(s == "float" || s == "int" || s == "unsigned" || s == "auto")) s += "_";
+            }
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string& error) {
+    Lexer lx(body);
+    if (!lx.run()) {
+        error = "WGSL translation error: " + lx.err;
+        return false;
+    }
+    Rewriter rw;
+    rw.t = std::move(lx.out);
+    // keyword-clash renaming must see the user's identifiers before passes introduce C++ keywords
+    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control()) {
+        error = "WGSL translation error: " + rw.err;
+        return false;
+    }
+    cuda.clear();
+    for (const Tok& k : rw.t) cuda += k.text;
+    return true;
+}
+
+}  // namespace linon
