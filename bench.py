@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the linon ray-march path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (CPU port)
+
+One "step" = one frame of the hot path: [click positions] -> march (+ 8 sample rays on a second stream) -> Lyapunov
+overlay.  N = 1 runs BASELINE.json configs[2]: 3840x2160, Enhance step size (h = 0.001, 5001 RK4 steps per ray),
+overlay on, the application's default field function (MirageSphericalSigmoid), default camera / mesh / settings.
+N > 1 is weak scaling of the same frame: N times the pixels over the same field of view (round(3840 sqrt N) x
+round(2160 sqrt N), so the per-ray work mix is unchanged), rows cut into blocks dealt round-robin to the ranks, one
+grouped NCCL exchange of the RGBA / endpoint / hit-id row blocks to rank 0, overlay on rank 0.
+
+Prints ONE JSON line (rank 0).  value = Mrays/s of the whole job (rays of all ranks / max-over-ranks device time);
+e2e = the same through the public MainView API with host buffers (camera+settings upload, final image read back into
+pinned memory) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FN_ID = 3  # MirageSphericalSigmoid: the function the application starts with (src/main_view.rs:100)
+BASE_W, BASE_H = 3840, 2160
+ROWS_PER_BLOCK = 32
+
+
+def workload_size(n_gpus: int):
+    s = math.sqrt(n_gpus)
+    return int(round(BASE_W * s)), int(round(BASE_H * s))
+
+
+def workload_name(n_gpus: int, w: int, h: int) -> str:
+    base = "C3: Cornell box, MirageSphericalSigmoid, Enhance h=0.001 (5001 RK4 steps/ray), Lyapunov overlay delta=1 scaling=50"
+    if n_gpus == 1:
+        return f"{base}, {w}x{h}, 1xB200"
+    return f"{base}, weak-scaled to {w}x{h} ({n_gpus}x the pixels, same field of view), {ROWS_PER_BLOCK}-row blocks round-robin over {n_gpus} GPUs + gather to rank 0"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def oracle_sample(w: int, h: int, budget_s: float, threads: int = 0):
+    """Times the CPU restatement of the reference on a bounded sample of the same frame: every `stride`-th row, full
+    width (pixels are independent; cost is per ray), sized by a short calibration run to ~budget_s seconds."""
+    import numpy as np
+    from oracle import cpu_oracle as co
+    from oracle import np_oracle as npo
+
+    co.build()
+    verts, faces, center = npo.default_scene()
+    cam = npo.camera_uniform(npo.default_camera(center, w, h))
+    st = dict(npo.default_settings(), overlay_mode=1)
+    cores = co.num_threads() if threads <= 0 else threads
+
+    def run(rows):
+        y_step = max(1, h // rows)
+        t0 = time.perf_counter()
+        out = co.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, y_step // 2, h),
+                       y_step=y_step, n_threads=threads)
+        dt = time.perf_counter() - t0
+        done = out["accepted"] > 0
+        return dt, int(done.sum()), int(out["accepted"].sum() + out["rejected"].sum()), int(done.any(axis=1).sum())
+
+    # calibration on a strided part of one row
+    xs = max(1, w // (cores * 16))
+    t0 = time.perf_counter()
+    co.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, h // 2, h // 2 + 1),
+             x_step=xs, n_threads=threads)
+    per_ray = (time.perf_counter() - t0) / len(range(0, w, xs))
+    rows = max(1, min(h, int(budget_s / (per_ray * w))))
+    t, rays, steps, rows = run(rows)
+    return dict(seconds=t, rays=rays, steps=steps, rows=rows, cores=cores,
+                sample=f"{rows} full rows of the {w}x{h} frame, evenly spaced ({rays} rays, {steps} RK4 steps), {cores} OpenMP threads")
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself (Rust + wgpu through
+    Mesa lavapipe) cannot be built or run in this image (no rustc/cargo, no Vulkan ICD), so this is the
+    CPU port in oracle/ (kind = "port"), all host threads, on a bounded sample of the same frame per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, h = workload_size(args.gpus)
+    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    for _ in range(args.warmup):
+        oracle_sample(w, h, budget)
+    tot_t = tot_rays = tot_steps = 0
+    last = None
+    for _ in range(args.steps):
+        last = oracle_sample(w, h, budget)
+        tot_t += last["seconds"]; tot_rays += last["rays"]; tot_steps += last["steps"]
+    mrays = tot_rays / tot_t / 1e6
+    line = dict(impl="reference", metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=tot_t / args.steps * 1e3 * (w * h) / (tot_rays / args.steps),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                rk4_gsteps_per_s=tot_steps / tot_t / 1e9,
+                config=dict(workload=workload_name(args.gpus, w, h), width=w, height=h,
+                            note="ms_per_step is the sampled time scaled to the full frame (pixels are independent)"),
+                cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=last["cores"], kind="port", sample=last["sample"]),
+                e2e=dict(value=mrays, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                reference_unavailable="niklaskorz/linon is Rust+wgpu: no rustc/cargo/Vulkan in this image; CPU port of the same WGSL timed instead")
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _DevBuf:
+    """Exposes a device pointer of the library to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=3,
+                                             strides=None)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from linon_b200 import _capi as capi
+    from linon_b200 import flops as fl
+    from linon_b200 import sharding
+    from linon_b200.main_view import MainView, PredefinedFunction, default_scene, make_settings, measure_fp32_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, H = workload_size(world)
+    verts, faces, center = default_scene()
+    mv = MainView(verts, faces, center, W, H, discrete_gpu=True, device=local_rank)
+    mv.reload_shader(PredefinedFunction(FN_ID).to_code())
+    settings = make_settings(overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0)
+    mv.update_settings(settings)
+    mv.set_shard(rank, world, ROWS_PER_BLOCK)
+    stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank))
+
+    ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")
+    rc = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_RAYCAST_RGBA8), (H, W, 4), "|u1"), device="cuda")
+    hid = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_HIT_ID_I32), (H, W), "<i4"), device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    final_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+
+    march_flags = capi.RENDER_ENHANCE
+    if world > 1:
+        march_flags |= capi.RENDER_NO_OVERLAY
+        if rank != 0:
+            march_flags |= capi.RENDER_NO_SAMPLE_RAYS
+
+    def frame():
+        """One step of the hot path on this rank; returns launches of our kernels."""
+        mv.render_flags(march_flags)
+        n = 1 + (2 if not (march_flags & capi.RENDER_NO_SAMPLE_RAYS) else 0)  # march (+ click positions + sample rays)
+        if world > 1:
+            mv.sync()
+            with torch.cuda.stream(stream):
+                sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, ROWS_PER_BLOCK)
+            if rank == 0:
+                mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)  # overlay on the assembled image
+                n += 1
+        else:
+            n += 1  # overlay
+        return n
+
+    def barrier():
+        mv.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # JIT + warm-up (untimed)
+    for _ in range(max(args.warmup, 3 if args.steps > 0 else 0)):
+        frame()
+        barrier()
+
+    # ---- device-timed steps: CUDA events on the stream the kernels are launched on; L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches = 0
+    dev_ms = []
+    march_ms = []
+    overlay_ms = []
+    counters = None
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        launches += frame()
+        e1.record(stream)
+        barrier()
+        dev_ms.append(e0.elapsed_time(e1))
+        t = mv.timings()
+        march_ms.append(t.march_ms)
+        overlay_ms.append(t.overlay_ms)
+        counters = mv.counters()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    total_ms = float(sum(dev_ms))
+    tm = torch.tensor([total_ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+
+    # ---- e2e: public API with host buffers (uniform upload + final image read back) inside the timed region ----
+    e2e_ms = 0.0
+    barrier()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        mv.update_camera()                 # 112-byte camera uniform from the host-side arcball (MainView::update_camera)
+        mv.update_settings(settings)       # 24-byte settings uniform (MainView::update_settings)
+        frame()
+        if rank == 0:
+            # result read back into pinned host memory (what a headless caller of the reference-facing API receives)
+            mv.read_into_ptr(capi.BUF_FINAL_RGBA8, final_host.data_ptr(), final_host.numel())
+        barrier()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    te = torch.tensor([e2e_ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    # counters of all ranks (rays / steps processed by the whole job in one step)
+    cvec = torch.tensor([counters.rays, counters.accepted_steps, counters.rejected_steps, counters.prehit_steps,
+                         counters.face_tests, counters.plane_tests], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(cvec)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    rays, acc, rej, pre, ftests, ptests = [float(x) for x in cvec.tolist()]
+
+    steps = max(args.steps, 1)
+    ms_per_step = total_ms / steps
+    value = rays / (ms_per_step * 1e-3) / 1e6
+    gsteps = (acc + rej) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (the march): algorithmic FLOPs (only work actually executed) / duration ----
+    fp32_peak, sms = measure_fp32_peak(local_rank)
+    m_ms = float(np.mean(march_ms))
+    alg_flops = fl.march_flops(counters, FN_ID, adaptive=False)
+    achieved = alg_flops / (m_ms * 1e-3) / 1e12
+    peaks, peak_src = measured_peaks()
+    o_ms = float(np.mean(overlay_ms)) if overlay_ms and overlay_ms[0] > 0 else None
+    overlay_roof = None
+    if o_ms:
+        ob = fl.OVERLAY_BYTES[1] * W * H
+        a = ob / (o_ms * 1e-3) / 1e9
+        overlay_roof = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
+                            traffic=None, kernel="overlay_kernel", algorithmic_bytes_per_launch=ob, peak_source=peak_src)
+
+    line = dict(
+        metric="Mrays/s", value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        rk4_gsteps_per_s=gsteps,
+        config=dict(workload=workload_name(world, W, H), width=W, height=H, rays_per_step=rays,
+                    rk4_steps_per_step=acc + rej, field_function="MirageSphericalSigmoid", h_initial=0.001,
+                    math_mode="fast (--use_fast_math)", kernel="tiles (one thread per pixel, 8x4 tiles)", plane_culling=True,
+                    parallelism=f"row-blocks x{world}" if world > 1 else "single GPU",
+                    l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
+        clocks=clocks,
+        e2e=dict(value=rays / (e2e_ms / steps * 1e-3) / 1e6, unit="Mrays/s", ms_per_step=e2e_ms / steps,
+                 h2d_bytes_per_step=112 + 24, d2h_bytes_per_step=W * H * 4),
+        gpu_launches=launches,
+        roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=None,
+                      kernel="linon_march_tiles", algorithmic_flops_per_launch=alg_flops, launch_ms=m_ms,
+                      peak_source="FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no fp32 entry; nominal 74.45)",
+                      frac_of_nominal=achieved / 74.45,
+                      as_written_equivalent_tflops=fl.as_written_flops(counters, FN_ID) / (m_ms * 1e-3) / 1e12,
+                      note="fp32 CUDA-core bound (no dense contraction on the path); numerator counts only executed work: "
+                           "plane tests + the ray-triangle tests that survived culling"),
+        roofline_overlay=overlay_roof,
+        counters=dict(accepted=acc, rejected=rej, prehit=pre, face_tests=ftests, plane_tests=ptests),
+        wall_s=t_wall,
+    )
+    if world == 1 and not args.no_cpu_baseline:
+        s = oracle_sample(W, H, args.cpu_seconds)
+        line["cpu_baseline"] = dict(value=s["rays"] / s["seconds"] / 1e6, unit="Mrays/s", cores=s["cores"], kind="port",
+                                    sample=s["sample"], rk4_gsteps_per_s=s["steps"] / s["seconds"] / 1e9,
+                                    note="CPU restatement of the reference WGSL (oracle/), not wgpu-on-lavapipe: no Rust/Vulkan in this image")
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

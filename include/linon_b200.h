@@ -79,13 +79,19 @@ enum {
 enum {
     LINON_OPT_MATH = 0,          /* 0 strict (no FMA contraction, IEEE div/sqrt; comparable with the CPU oracle bit
                                     for bit on bodies without transcendentals), 1 fused (FMA contraction),
-                                    2 fast (--use_fast_math).  Default 1. */
-    LINON_OPT_KERNEL = 1,        /* 0 one thread per pixel, 1 persistent warps with phase split + lane refill. Default 1 */
+                                    2 fast (--use_fast_math: MUFU rcp/rsqrt/ex2/sin/cos, ftz).  Default 2: measured 2x faster
+                                    than fused and inside the north-star tolerances (tests/test_gpu_parity.py). */
+    LINON_OPT_KERNEL = 1,        /* 0 one thread per pixel in 8x4 tiles, 1 persistent warps: pre-hit / post-hit phase kernels
+                                    with lane refill.  Default 0: measured faster on B200 once culling removed the pre-hit /
+                                    post-hit cost gap (profiles/) */
     LINON_OPT_BLOCK = 2,         /* threads per CTA of the march kernel (multiple of 32). Default 256 */
     LINON_OPT_CTAS_PER_SM = 3,   /* persistent grid = this x #SM; 0 = occupancy query. Default 0 */
     LINON_OPT_REFILL_MIN = 4,    /* idle lanes a warp tolerates before refilling. Default 1 */
     LINON_OPT_FACE_UNROLL = 5,   /* unroll of the face loop. Default 4 */
-    LINON_OPT_MAX_REGS = 6       /* NVRTC --maxrregcount (0 = none). Default 0 */
+    LINON_OPT_MAX_REGS = 6,      /* NVRTC --maxrregcount (0 = none). Default 0 */
+    LINON_OPT_PROFILE = 7,       /* 1: persistent kernel accumulates clock64 section timers (linon_debug_profile) */
+    LINON_OPT_CULL = 8           /* 1 (default): skip faces whose plane the step segment cannot reach (exact, results
+                                    unchanged); 0: test every face on every pre-hit step like the reference */
 };
 
 typedef struct linon_counters { /* per-frame totals over every ray of the last march */
@@ -93,6 +99,8 @@ typedef struct linon_counters { /* per-frame totals over every ray of the last m
     uint64_t accepted_steps;    /* accepted RK4 steps */
     uint64_t prehit_steps;      /* accepted steps that also ran the all-face intersection */
     uint64_t rejected_steps;    /* RK4 attempts rejected by adaptive sampling */
+    uint64_t face_tests;        /* ray-triangle tests actually executed (36 per pre-hit step without culling) */
+    uint64_t plane_tests;       /* plane-distance culling tests executed (0 when culling is off) */
 } linon_counters;
 
 typedef struct linon_timings { /* CUDA-event times of the last render, milliseconds (0 when the pass did not run) */
@@ -104,6 +112,7 @@ typedef struct linon_timings { /* CUDA-event times of the last render, milliseco
     int32_t march_regs;         /* registers per thread of the march kernel */
     int32_t march_grid;         /* CTAs launched */
     int32_t march_block;        /* threads per CTA */
+    float march_phase_a_ms;     /* persistent kernel: time of the pre-hit phase (march_ms covers both phases) */
 } linon_timings;
 
 /* MainView::new (src/main_view.rs:82-458): allocates textures/buffers for width x height on CUDA device
@@ -169,6 +178,11 @@ int linon_debug_eval_helper(linon_view* v, int which, uint32_t n, const float* v
                             const float* a, const float* b, const float* c, float* out);
 int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const float* origin, const float* dir,
                              float* t_out);
+
+/* Raw counter block of the last march (16 x u64): [0..3] as linon_counters, then section timers of the persistent
+ * kernels when LINON_OPT_PROFILE = 1: [4..8] phase A, [9..13] phase B = refill cycles, step cycles, warp iterations,
+ * live lanes summed over iterations, warp lifetime cycles. */
+int linon_debug_profile(linon_view* v, uint64_t* out16);
 
 /* FFMA-chain microbenchmark on `device`: the measured FP32 peak used as the roofline denominator. */
 int linon_measure_fp32_peak(int device, double* tflops, int* sm_count);

@@ -18,7 +18,7 @@ RENDER_DEFAULT, RENDER_ENHANCE, RENDER_OUTLINE, RENDER_ADAPTIVE_OFF = 0, 1, 2, 4
 RENDER_NO_OVERLAY, RENDER_NO_MARCH, RENDER_NO_SAMPLE_RAYS = 8, 16, 32
 BUF_FINAL_RGBA8, BUF_RAYCAST_RGBA8, BUF_ENDPOINT_F32X4, BUF_EXPONENTS_F32, BUF_HIT_ID_I32 = range(5)
 BUF_RAY_SAMPLES, BUF_SAMPLE_POS = 5, 6
-OPT_MATH, OPT_KERNEL, OPT_BLOCK, OPT_CTAS_PER_SM, OPT_REFILL_MIN, OPT_FACE_UNROLL, OPT_MAX_REGS = range(7)
+OPT_MATH, OPT_KERNEL, OPT_BLOCK, OPT_CTAS_PER_SM, OPT_REFILL_MIN, OPT_FACE_UNROLL, OPT_MAX_REGS, OPT_PROFILE, OPT_CULL = range(9)
 MATH_STRICT, MATH_FUSED, MATH_FAST = 0, 1, 2
 KERNEL_TILES, KERNEL_PERSISTENT = 0, 1
 
@@ -42,13 +42,13 @@ class Settings(C.Structure):  # linon_settings, 24 B
 
 class Counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("accepted_steps", C.c_uint64), ("prehit_steps", C.c_uint64),
-                ("rejected_steps", C.c_uint64)]
+                ("rejected_steps", C.c_uint64), ("face_tests", C.c_uint64), ("plane_tests", C.c_uint64)]
 
 
 class Timings(C.Structure):
     _fields_ = [("march_ms", C.c_float), ("overlay_ms", C.c_float), ("sample_rays_ms", C.c_float),
                 ("outline_search_ms", C.c_float), ("jit_ms", C.c_float), ("march_regs", C.c_int32),
-                ("march_grid", C.c_int32), ("march_block", C.c_int32)]
+                ("march_grid", C.c_int32), ("march_block", C.c_int32), ("march_phase_a_ms", C.c_float)]
 
 
 assert C.sizeof(Camera) == 112 and C.sizeof(Settings) == 24
@@ -81,6 +81,7 @@ PROTOTYPES = [
     ("linon_debug_eval_field", _I, [_P, _U, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_eval_helper", _I, [_P, _I, _U, _P, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_hit_triangle", _I, [_P, _U, _P, _P, _P, _P]),
+    ("linon_debug_profile", _I, [_P, _P]),
     ("linon_measure_fp32_peak", _I, [_I, C.POINTER(C.c_double), C.POINTER(_I)]),
     # include/linon_b200_host.h
     ("linon_host_default_scene", None, [_P, _P, _P, _I]),

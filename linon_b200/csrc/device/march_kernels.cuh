@@ -13,17 +13,19 @@
 //   LINON_FACE_UNROLL    unroll factor of the face loop
 //   LINON_BLOCK          threads per CTA of the march kernels
 //   LINON_REFILL_MIN     idle lanes a warp tolerates before it refills (persistent kernel)
+//   LINON_CULL / LINON_N_GROUPS  plane culling of the face loop (see intersect_mesh) and the number of plane groups
+//   LINON_PROFILE        1 adds clock64 section timers to the persistent kernels (counters[4..13])
 //
 // Two march kernels share every per-ray device function, so their per-pixel results are bit-identical:
 //   linon_march_tiles       one thread per pixel, 8x4 pixel tiles per warp (the straightforward mapping)
-//   linon_march_persistent  persistent CTAs (grid = k * #SM).  Every warp keeps 32 rays in flight; a lane whose
-//                           ray leaves its phase is refilled through a warp-aggregated atomic.  Phase A = rays
+//   linon_march_phase_a/_b  persistent CTAs (grid = k * #SM).  Every warp keeps 32 rays in flight; a lane whose
+//                           ray leaves its phase is refilled through a warp-aggregated atomicAdd.  Phase A = rays
 //                           that have not hit yet (RK4 + all-face intersection every step); on a hit the lane
 //                           writes colour + hit id, pushes {p, dir, t, h, last_v, last_diff} to a device queue and
-//                           takes a fresh ray.  Phase B = queued rays (RK4 only, src/main_view.wgsl:259 skips the
-//                           intersection once has_color) until t > 5.  Rays never stop early in the reference
-//                           (SURVEY F1), so the divergence to remove is pre-hit vs post-hit lanes, and this split
-//                           makes every warp homogeneous.
+//                           takes a fresh ray.  Phase B (second launch) = queued rays (RK4 only,
+//                           src/main_view.wgsl:259 skips the intersection once has_color) until t > 5.  Rays never
+//                           stop early in the reference, so the divergence to remove is pre-hit vs
+//                           post-hit lanes, and this split makes every warp homogeneous.
 //
 // Mesh: staged once per CTA into shared memory as {v0, e1 = v1-v0, e2 = v2-v0} (3 x float4 per face).
 // All lanes read the same face at the same time, so every LDS.128 is a broadcast (no bank conflicts).
@@ -47,6 +49,21 @@
 #ifndef LINON_REFILL_MIN
 #define LINON_REFILL_MIN 1
 #endif
+#ifndef LINON_GROUP_UNROLL
+#define LINON_GROUP_UNROLL 5
+#endif
+#ifndef LINON_MIN_BLOCKS
+#define LINON_MIN_BLOCKS (1024 / LINON_BLOCK)  // ask for 32 resident warps / SM: caps the kernels at 64 registers
+#endif
+#ifndef LINON_CULL
+#define LINON_CULL 1      // 1: skip faces whose plane the step segment cannot reach (exact: never changes a result)
+#endif
+#ifndef LINON_N_GROUPS
+#define LINON_N_GROUPS LINON_N_FACES  // plane groups: runs of consecutive coplanar faces (built by the host)
+#endif
+#ifndef LINON_PROFILE
+#define LINON_PROFILE 0  // 1: the persistent kernel also accumulates per-section clock64 cycles (developer aid)
+#endif
 
 #define LINON_EPS 0.0000001f  // const eps, src/main_view.wgsl:74
 
@@ -59,14 +76,18 @@ struct MarchParams {
     int local_rows;               // rows this shard renders
     int shard_rank, shard_world;  // row blocks are dealt round-robin: block b -> rank b % world
     int rows_per_block;
-    const float4* tris;           // LINON_N_FACES x {v0, e1, e2}
-    uchar4* raycast;              // [local_rows][width]  ray_casting_texture (rgba8unorm)
-    float4* endpoint;             // [local_rows][width]  mapping_texture (rgba32float)
-    int* hit_id;                  // [local_rows][width]  face index of the first hit, -1 = none
+    const float4* tris;           // LINON_N_FACES x {v0, e1, e2}, then LINON_N_GROUPS x {unit normal, plane offset}
+    const int* group_range;       // LINON_N_GROUPS x (first face | face count << 16)
+    uchar4* raycast;              // [height][width]  ray_casting_texture (rgba8unorm); a shard writes only its rows
+    float4* endpoint;             // [height][width]  mapping_texture (rgba32float)
+    int* hit_id;                  // [height][width]  face index of the first hit, -1 = none
     unsigned long long* counters; // [0] accepted steps  [1] steps that ran the face loop  [2] rejected attempts
+                                  // [3] ray-triangle tests actually performed (after culling)
+                                  // LINON_PROFILE: phase A [4..8], phase B [9..13] = refill cycles, step cycles,
+                                  // warp iterations, live lanes summed over iterations, warp lifetime cycles
     // persistent kernel only
-    unsigned int* work;           // [0] next fresh ray  [1] queue tail  [2] queue head  [3] rays that left phase A
-    int* q_pixel;                 // queue: local pixel index, -1 until the entry is published
+    unsigned int* work;           // [0] next fresh ray slot  [1] queue tail (phase A pushes)  [2] queue head (phase B pops)
+    int* q_pixel;                 // queue: pixel index (texture space) of the entry
     float4* q_state;              // queue: 3 x float4 per entry, SoA planes of q_capacity
     unsigned int q_capacity;
     unsigned int n_ray_slots;     // tiles * 32 (index space of fresh rays incl. out-of-frame padding lanes)
@@ -128,32 +149,67 @@ __device__ __forceinline__ vec3f rk4_velocity(const Ray& r, float h, const WgslS
     return (k1 + 2.0f * k2 + 2.0f * k3 + k4) / 6.0f;
 }
 
-// hit_triangle over every face, keeping the closest hit in (0, max_dist): src/main_view.wgsl:150-198.
+// hit_triangle for one face (src/main_view.wgsl:150-175) + the closest-hit update of ray_color (:193-197).
 // Branch-free restatement of the reference's early returns (same comparisons, same NaN behaviour).
-__device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri, vec3f origin, vec3f direction,
-                                               float max_dist, float& t_best, int& id_best) {
+__device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int i, vec3f origin, vec3f direction,
+                                          float max_dist, float& t_best, int& id_best) {
+    const float4 a = s_tri[3 * i], b = s_tri[3 * i + 1], c = s_tri[3 * i + 2];
+    const vec3f v0(a.x, a.y, a.z), edge1(b.x, b.y, b.z), edge2(c.x, c.y, c.z);
+    const vec3f h = w_cross(direction, edge2);
+    const float det = w_dot(edge1, h);
+    const float f = 1.0f / det;
+    const vec3f s = origin - v0;
+    const float u = f * w_dot(s, h);
+    const vec3f q = w_cross(s, edge1);
+    const float v = f * w_dot(direction, q);
+    const float t = f * w_dot(edge2, q);
+    const bool ok = !(det > -LINON_EPS && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) &&
+                    !(v < 0.0f || u + v > 1.0f) && (t > LINON_EPS);
+    const float t_new = ok ? t : -1.0f;
+    if (t_new > 0.0f && t_new < max_dist && (t_best < 0.0f || t_new < t_best)) {
+        t_best = t_new;
+        id_best = i;
+    }
+}
+
+// ray_color's loop over every face (src/main_view.wgsl:182-198), keeping the closest hit in (0, max_dist).
+//
+// LINON_CULL: a face can only report t in (eps, max_dist) if the step segment reaches its plane, i.e. if the distance
+// of the segment origin to the plane is at most max_dist (direction is a unit vector).  The host groups runs of
+// consecutive coplanar faces; one signed distance (3 FFMA) + one compare per group decides whether the group's faces
+// are tested at all.  The margin (2e-3 relative on max_dist plus 1e-5 (1 + |origin|_1) absolute) is orders of magnitude
+// above the rounding error of either computation, so a skipped face is one the full test would have rejected:
+// results are bit-identical with LINON_CULL = 0 (tests/test_gpu_parity.py checks it).  Faces are still visited in
+// index order, so the strict `t_new < t` tie-break of the reference (lowest index wins) is preserved.
+__device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri, const int* __restrict__ s_range,
+                                               vec3f origin, vec3f direction, float max_dist, float& t_best,
+                                               int& id_best, unsigned int& face_tests) {
     t_best = -1.0f;
     id_best = -1;
-#pragma unroll LINON_FACE_UNROLL
-    for (int i = 0; i < LINON_N_FACES; ++i) {
-        const float4 a = s_tri[3 * i], b = s_tri[3 * i + 1], c = s_tri[3 * i + 2];
-        const vec3f v0(a.x, a.y, a.z), edge1(b.x, b.y, b.z), edge2(c.x, c.y, c.z);
-        const vec3f h = w_cross(direction, edge2);
-        const float det = w_dot(edge1, h);
-        const float f = 1.0f / det;
-        const vec3f s = origin - v0;
-        const float u = f * w_dot(s, h);
-        const vec3f q = w_cross(s, edge1);
-        const float v = f * w_dot(direction, q);
-        const float t = f * w_dot(edge2, q);
-        const bool ok = !(det > -LINON_EPS && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) &&
-                        !(v < 0.0f || u + v > 1.0f) && (t > LINON_EPS);
-        const float t_new = ok ? t : -1.0f;
-        if (t_new > 0.0f && t_new < max_dist && (t_best < 0.0f || t_new < t_best)) {
-            t_best = t_new;
-            id_best = i;
+#if LINON_CULL
+    const float reach = 1.002f * max_dist + 1e-5f * (1.0f + fabsf(origin.x) + fabsf(origin.y) + fabsf(origin.z));
+    const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES;
+    // partial unroll on purpose: a fully unrolled loop lets the compiler hoist all plane loads out of the time loop
+    // (60 live registers, spills); with a loop-carried index the planes stay in shared memory (broadcast LDS.128)
+#pragma unroll LINON_GROUP_UNROLL
+    for (int g = 0; g < LINON_N_GROUPS; ++g) {
+        const float4 pl = s_plane[g];
+        const float dist = __fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w)));
+        if (fabsf(dist) <= reach) {
+            const int range = s_range[g];
+            const int first = range & 0xffff, last = first + (range >> 16);
+#pragma unroll 1
+            for (int i = first; i < last; ++i) {
+                test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
+                ++face_tests;
+            }
         }
     }
+#else
+#pragma unroll LINON_FACE_UNROLL
+    for (int i = 0; i < LINON_N_FACES; ++i) test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
+    face_tests += LINON_N_FACES;
+#endif
 }
 
 // Blinn-Phong with the camera as light, src/main_view.wgsl:199-217.
@@ -176,8 +232,10 @@ __device__ __forceinline__ unsigned char unorm8(float x) {
 }
 __device__ __forceinline__ uchar4 pack_color(vec3f c) { return make_uchar4(unorm8(c.x), unorm8(c.y), unorm8(c.z), 255); }
 
-__device__ __forceinline__ void stage_mesh(float4* s_tri, const float4* __restrict__ g_tri) {
-    for (int i = threadIdx.x; i < 3 * LINON_N_FACES; i += blockDim.x) s_tri[i] = g_tri[i];
+#define LINON_MESH_F4 (3 * LINON_N_FACES + LINON_N_GROUPS)
+__device__ __forceinline__ void stage_mesh(float4* s_tri, int* s_range, const MarchParams& P) {
+    for (int i = threadIdx.x; i < LINON_MESH_F4; i += blockDim.x) s_tri[i] = P.tris[i];
+    for (int i = threadIdx.x; i < LINON_N_GROUPS; i += blockDim.x) s_range[i] = P.group_range[i];
     __syncthreads();
 }
 
@@ -203,21 +261,24 @@ __device__ __forceinline__ void init_ray(const MarchParams& P, int x, int local_
 }
 
 struct StepCounters {
-    unsigned int accepted, prehit, rejected;
+    unsigned int accepted, prehit, rejected, face_tests;
 };
 
 __device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounters c) {
-    unsigned int a = c.accepted, b = c.prehit, r = c.rejected;
+    // per-lane 32-bit counts are widened before the reduction (a persistent lane can exceed 2^32 face tests)
+    unsigned long long a = c.accepted, b = c.prehit, r = c.rejected, f = c.face_tests;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
         r += __shfl_xor_sync(0xffffffffu, r, o);
+        f += __shfl_xor_sync(0xffffffffu, f, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&P.counters[0], (unsigned long long)a);
-        atomicAdd(&P.counters[1], (unsigned long long)b);
-        atomicAdd(&P.counters[2], (unsigned long long)r);
+        atomicAdd(&P.counters[0], a);
+        atomicAdd(&P.counters[1], b);
+        atomicAdd(&P.counters[2], r);
+        atomicAdd(&P.counters[3], f);
     }
 }
 
@@ -261,14 +322,15 @@ __device__ __forceinline__ void rk4_advance(Ray& r, vec3f v, float diff, vec3f s
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1: one thread per pixel.
 // ------------------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_tiles(const MarchParams P) {
-    __shared__ float4 s_tri[3 * LINON_N_FACES];
-    stage_mesh(s_tri, P.tris);
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_tiles(const MarchParams P) {
+    __shared__ float4 s_tri[LINON_MESH_F4];
+    __shared__ int s_range[LINON_N_GROUPS];
+    stage_mesh(s_tri, s_range, P);
 
     const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
     int x, local_row;
     const bool valid = slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row);
-    StepCounters cnt = {0u, 0u, 0u};
+    StepCounters cnt = {0u, 0u, 0u, 0u};
     if (valid) {
         const WgslCamera cam = make_camera(P);
         const WgslSettings st = P.settings;
@@ -289,7 +351,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_tiles(cons
                 const vec3f dirn = w_normalize(step_dir);
                 float t_hit;
                 int id;
-                intersect_mesh(s_tri, r.p, dirn, max_dist, t_hit, id);
+                intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, t_hit, id, cnt.face_tests);
                 if (t_hit > 0.0f && t_hit < max_dist) {
                     color = shade(s_tri, id, dirn);
                     hit = id;
@@ -300,7 +362,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_tiles(cons
             rk4_advance(r, v, diff, step_dir);
             ++cnt.accepted;
         }
-        const size_t pix = (size_t)local_row * P.width + x;
+        const size_t pix = (size_t)texture_row(P, local_row) * P.width + x;
         P.raycast[pix] = pack_color(color);  // black when !has_color, alpha = 1 (src/main_view.wgsl:274-277)
         P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
         P.hit_id[pix] = hit;
@@ -309,178 +371,210 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_tiles(cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Kernel 2: persistent warps, phase A (pre-hit) / phase B (post-hit) with lane refill.
+// Kernels 2a/2b: persistent warps with lane refill, split by phase.
+//
+//   linon_march_phase_a   every lane carries a ray that has NOT hit yet (RK4 + face loop each step).  A lane whose
+//                         ray hits writes colour + hit id, appends {p, dir, t, h, last_v, last_diff, pixel} to the
+//                         device queue (warp-aggregated atomicAdd on the tail) and is refilled with a fresh ray from
+//                         the cursor (warp-aggregated atomicAdd).  A ray that reaches t > 5 without a hit writes
+//                         black / -1 / endpoint.
+//   linon_march_phase_b   launched after phase A on the same stream, so the queue is complete and immutable: lanes
+//                         pop entries with a plain atomicAdd on the head (no CAS, no publication flags, no fences)
+//                         and integrate RK4 only until t > 5, then write the endpoint.
+// All waiting is removed by construction: neither kernel ever spins on another warp's progress.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int lane_rank(unsigned int mask) { return __popc(mask & ((1u << (threadIdx.x & 31)) - 1u)); }
 
-extern "C" __global__ void __launch_bounds__(LINON_BLOCK) linon_march_persistent(const MarchParams P) {
-    __shared__ float4 s_tri[3 * LINON_N_FACES];
-    stage_mesh(s_tri, P.tris);
+#if LINON_PROFILE
+#define PF_DECL unsigned long long pf_refill = 0, pf_step = 0, pf_iters = 0, pf_lanes = 0; const long long pf_start = clock64();
+#define PF_BEGIN(name) const long long name = clock64();
+#define PF_END(acc, name) acc += (unsigned long long)(clock64() - name);
+#define PF_FLUSH(base)                                                                   \
+    if ((threadIdx.x & 31) == 0) {                                                       \
+        atomicAdd(&P.counters[(base) + 0], pf_refill);                                   \
+        atomicAdd(&P.counters[(base) + 1], pf_step);                                     \
+        atomicAdd(&P.counters[(base) + 2], pf_iters);                                    \
+        atomicAdd(&P.counters[(base) + 3], pf_lanes);                                    \
+        atomicAdd(&P.counters[(base) + 4], (unsigned long long)(clock64() - pf_start));  \
+    }
+#else
+#define PF_DECL
+#define PF_BEGIN(name)
+#define PF_END(acc, name)
+#define PF_FLUSH(base)
+#endif
+
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_phase_a(const MarchParams P) {
+    __shared__ float4 s_tri[LINON_MESH_F4];
+    __shared__ int s_range[LINON_N_GROUPS];
+    stage_mesh(s_tri, s_range, P);
 
     const unsigned int lane = threadIdx.x & 31;
     const WgslCamera cam = make_camera(P);
     const WgslSettings st = P.settings;
     unsigned int* const w_next = P.work + 0;
     unsigned int* const w_tail = P.work + 1;
-    unsigned int* const w_head = P.work + 2;
-    unsigned int* const w_adone = P.work + 3;
     const size_t plane = P.q_capacity;
 
     Ray r;
     r.p = r.dir = r.sdir = r.last_v = vec3f(0.0f, 0.0f, 0.0f);
     r.t = 0.0f; r.h = LINON_H_INITIAL; r.last_diff = -1.0f;
-    int pix = -1;           // local pixel index of the ray this lane carries
+    int pix = -1;            // pixel index of the ray this lane carries
     bool alive = false;
-    bool phase_b = false;   // warp-uniform
-    bool fresh_left = true; // warp-uniform
-    StepCounters cnt = {0u, 0u, 0u};
+    bool fresh_left = true;  // warp-uniform
+    StepCounters cnt = {0u, 0u, 0u, 0u};
+    PF_DECL
 
     for (;;) {
         const unsigned int idle = __ballot_sync(0xffffffffu, !alive);
-        if (__popc(idle) >= LINON_REFILL_MIN || idle == 0xffffffffu) {
-            if (!phase_b && fresh_left) {
-                // ---- refill from the fresh-ray cursor (warp-aggregated) ----
-                const unsigned int need = __popc(idle);
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(w_next, need);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                unsigned int padding = 0;  // slots outside the frame leave phase A immediately
-                if (!alive) {
-                    const unsigned int slot = base + lane_rank(idle);
-                    if (slot < P.n_ray_slots) {
-                        int x, local_row;
-                        if (slot_to_pixel(P, slot, x, local_row)) {
-                            init_ray(P, x, local_row, r);
-                            pix = local_row * P.width + x;
-                            alive = true;
-                        } else {
-                            padding = 1;
-                        }
-                    }
-                }
-                const unsigned int pad_mask = __ballot_sync(0xffffffffu, padding);
-                if (lane == 0 && pad_mask) atomicAdd(w_adone, (unsigned int)__popc(pad_mask));
-                if (base + need >= P.n_ray_slots) fresh_left = false;
-            } else if (phase_b) {
-                // ---- refill from the post-hit queue ----
-                const unsigned int need = __popc(idle);
-                unsigned int base = 0, take = 0;
-                if (lane == 0) {
-                    for (;;) {
-                        const unsigned int head = *(volatile unsigned int*)w_head;
-                        const unsigned int tail = *(volatile unsigned int*)w_tail;
-                        const unsigned int avail = tail - head;
-                        take = avail < need ? avail : need;
-                        if (take == 0) break;
-                        if (atomicCAS(w_head, head, head + take) == head) {
-                            base = head;
-                            break;
-                        }
-                    }
-                }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                take = __shfl_sync(0xffffffffu, take, 0);
-                if (!alive) {
-                    const unsigned int k = lane_rank(idle);
-                    if (k < take) {
-                        const unsigned int e = base + k;
-                        int px;
-                        while ((px = *(volatile int*)(P.q_pixel + e)) < 0) __nanosleep(64);
-                        __threadfence();  // the entry was published after its payload
-                        const float4 a = __ldcg(P.q_state + e);
-                        const float4 b = __ldcg(P.q_state + plane + e);
-                        const float4 c = __ldcg(P.q_state + 2 * plane + e);
-                        r.p = vec3f(a.x, a.y, a.z); r.t = a.w;
-                        r.dir = vec3f(b.x, b.y, b.z); r.h = b.w;
-                        r.last_v = vec3f(c.x, c.y, c.z); r.last_diff = c.w;
-                        pix = px;
-                        const int local_row = px / P.width;
-                        const int gid_y = P.height - 1 - texture_row(P, local_row);
-                        r.sdir = camera_ray_dir(P, (float)(px - local_row * P.width), (float)gid_y, false);
-                        alive = true;
-                    }
+        if (fresh_left && (__popc(idle) >= LINON_REFILL_MIN)) {
+            PF_BEGIN(pf_r0)
+            const unsigned int need = __popc(idle);
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(w_next, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!alive) {
+                const unsigned int slot = base + lane_rank(idle);
+                int x, local_row;
+                if (slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row)) {
+                    init_ray(P, x, local_row, r);
+                    pix = texture_row(P, local_row) * P.width + x;
+                    alive = true;
                 }
             }
-            if (__ballot_sync(0xffffffffu, alive) == 0u) {
-                // the warp is empty: move to phase B once the fresh rays are gone, finish when everything drained
-                if (!phase_b) {
-                    if (fresh_left) continue;
-                    phase_b = true;
-                    continue;
-                }
-                unsigned int done = 0;
-                if (lane == 0) {
-                    const unsigned int adone = *(volatile unsigned int*)w_adone;
-                    const unsigned int head = *(volatile unsigned int*)w_head;
-                    const unsigned int tail = *(volatile unsigned int*)w_tail;
-                    // every ray left phase A and every queued ray has been claimed
-                    done = (adone >= P.n_ray_slots && head == tail) ? 1u : 0u;
-                    if (!done) __nanosleep(256);
-                }
-                if (__shfl_sync(0xffffffffu, done, 0)) break;
-                continue;
-            }
+            if (base + need >= P.n_ray_slots) fresh_left = false;
+            PF_END(pf_refill, pf_r0)
         }
-
-        // ---- one RK4 attempt for every live lane ----
-        const bool stepping = alive;
-        bool finished = false, hit_now = false;
+        const unsigned int live = __ballot_sync(0xffffffffu, alive);
+        if (live == 0u) {
+            if (fresh_left) continue;
+            break;
+        }
+#if LINON_PROFILE
+        ++pf_iters;
+        pf_lanes += __popc(live);
+#endif
+        PF_BEGIN(pf_s0)
+        bool push = false;
         if (alive) {
             vec3f v, step_dir;
             float diff;
             if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
-                if (!phase_b) {
-                    const float max_dist = w_length(step_dir);
-                    const vec3f dirn = w_normalize(step_dir);
-                    float t_hit;
-                    int id;
-                    intersect_mesh(s_tri, r.p, dirn, max_dist, t_hit, id);
-                    ++cnt.prehit;
-                    if (t_hit > 0.0f && t_hit < max_dist) {
-                        P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
-                        P.hit_id[pix] = id;
-                        hit_now = true;
-                    }
+                const float max_dist = w_length(step_dir);
+                const vec3f dirn = w_normalize(step_dir);
+                float t_hit;
+                int id;
+                intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, t_hit, id, cnt.face_tests);
+                ++cnt.prehit;
+                const bool hit_now = t_hit > 0.0f && t_hit < max_dist;
+                if (hit_now) {
+                    P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
+                    P.hit_id[pix] = id;
                 }
                 rk4_advance(r, v, diff, step_dir);
                 ++cnt.accepted;
-                finished = !(r.t <= 5.0f);
+                const bool finished = !(r.t <= 5.0f);
                 if (finished) {
                     P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
-                    if (!phase_b && !hit_now) {  // never hit: black, alpha 1 (src/main_view.wgsl:275-277)
+                    if (!hit_now) {  // never hit: black, alpha 1 (src/main_view.wgsl:275-277)
                         P.raycast[pix] = make_uchar4(0, 0, 0, 255);
                         P.hit_id[pix] = -1;
                     }
                 }
+                push = hit_now && !finished;
                 if (finished || hit_now) alive = false;
             } else {
                 ++cnt.rejected;
             }
         }
-        if (!phase_b) {
-            // Rays that hit and still have steps left continue in phase B through the queue.  The payload is
-            // written first, then the entry is published by storing its pixel index (consumers spin on it).
-            const bool left_a = stepping && !alive;
-            const bool push = left_a && !finished;
-            const unsigned int push_mask = __ballot_sync(0xffffffffu, push);
-            const unsigned int left_mask = __ballot_sync(0xffffffffu, left_a);
-            if (push_mask) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(w_tail, (unsigned int)__popc(push_mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (push) {
-                    const unsigned int e = base + lane_rank(push_mask);
-                    __stcg(P.q_state + e, make_float4(r.p.x, r.p.y, r.p.z, r.t));
-                    __stcg(P.q_state + plane + e, make_float4(r.dir.x, r.dir.y, r.dir.z, r.h));
-                    __stcg(P.q_state + 2 * plane + e, make_float4(r.last_v.x, r.last_v.y, r.last_v.z, r.last_diff));
-                    __threadfence();
-                    *(volatile int*)(P.q_pixel + e) = pix;
-                }
+        const unsigned int push_mask = __ballot_sync(0xffffffffu, push);
+        if (push_mask) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(w_tail, (unsigned int)__popc(push_mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (push) {
+                const unsigned int e = base + lane_rank(push_mask);
+                P.q_state[e] = make_float4(r.p.x, r.p.y, r.p.z, r.t);
+                P.q_state[plane + e] = make_float4(r.dir.x, r.dir.y, r.dir.z, r.h);
+                P.q_state[2 * plane + e] = make_float4(r.last_v.x, r.last_v.y, r.last_v.z, r.last_diff);
+                P.q_pixel[e] = pix;
             }
-            if (left_mask && lane == 0) atomicAdd(w_adone, (unsigned int)__popc(left_mask));
         }
+        PF_END(pf_step, pf_s0)
     }
     flush_counters(P, cnt);
+    PF_FLUSH(4)
+}
+
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_phase_b(const MarchParams P) {
+    const unsigned int lane = threadIdx.x & 31;
+    const WgslCamera cam = make_camera(P);
+    const WgslSettings st = P.settings;
+    unsigned int* const w_head = P.work + 2;
+    const unsigned int total = P.work[1];  // final queue length: phase A has completed
+    const size_t plane = P.q_capacity;
+
+    Ray r;
+    r.p = r.dir = r.sdir = r.last_v = vec3f(0.0f, 0.0f, 0.0f);
+    r.t = 0.0f; r.h = LINON_H_INITIAL; r.last_diff = -1.0f;
+    int pix = -1;
+    bool alive = false;
+    bool queue_left = true;  // warp-uniform
+    StepCounters cnt = {0u, 0u, 0u, 0u};
+    PF_DECL
+
+    for (;;) {
+        const unsigned int idle = __ballot_sync(0xffffffffu, !alive);
+        if (queue_left && (__popc(idle) >= LINON_REFILL_MIN)) {
+            PF_BEGIN(pf_r0)
+            const unsigned int need = __popc(idle);
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(w_head, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!alive) {
+                const unsigned int e = base + lane_rank(idle);
+                if (e < total) {
+                    const float4 a = P.q_state[e], b = P.q_state[plane + e], c = P.q_state[2 * plane + e];
+                    pix = P.q_pixel[e];
+                    r.p = vec3f(a.x, a.y, a.z); r.t = a.w;
+                    r.dir = vec3f(b.x, b.y, b.z); r.h = b.w;
+                    r.last_v = vec3f(c.x, c.y, c.z); r.last_diff = c.w;
+                    const int row = pix / P.width;  // texture row
+                    r.sdir = camera_ray_dir(P, (float)(pix - row * P.width), (float)(P.height - 1 - row), false);
+                    alive = true;
+                }
+            }
+            if (base + need >= total) queue_left = false;
+            PF_END(pf_refill, pf_r0)
+        }
+        const unsigned int live = __ballot_sync(0xffffffffu, alive);
+        if (live == 0u) {
+            if (queue_left) continue;
+            break;
+        }
+#if LINON_PROFILE
+        ++pf_iters;
+        pf_lanes += __popc(live);
+#endif
+        PF_BEGIN(pf_s0)
+        if (alive) {
+            vec3f v, step_dir;
+            float diff;
+            if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
+                rk4_advance(r, v, diff, step_dir);
+                ++cnt.accepted;
+                if (!(r.t <= 5.0f)) {
+                    P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+                    alive = false;
+                }
+            } else {
+                ++cnt.rejected;
+            }
+        }
+        PF_END(pf_step, pf_s0)
+    }
+    flush_counters(P, cnt);
+    PF_FLUSH(9)
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 #include <nvrtc.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -97,6 +98,7 @@ struct MarchParamsH {
     linon_settings settings;
     int width, height, local_rows, shard_rank, shard_world, rows_per_block;
     const void* tris;
+    const int* group_range;
     void* raycast;
     void* endpoint;
     int* hit_id;
@@ -117,14 +119,14 @@ static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view
 
 struct Variant {
     float h_initial;
-    int adaptive, n_faces, math, block, unroll, refill_min, max_regs;
+    int adaptive, n_faces, n_groups, cull, math, block, unroll, refill_min, max_regs, profile;
 };
 
 struct Module {
     CUmodule mod = nullptr;
-    CUfunction tiles = nullptr, persistent = nullptr, sample = nullptr, eval_field = nullptr, eval_helper = nullptr,
-               eval_hit = nullptr;
-    int regs_tiles = 0, regs_persistent = 0;
+    CUfunction tiles = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr, eval_field = nullptr,
+               eval_helper = nullptr, eval_hit = nullptr;
+    int regs_tiles = 0, regs_phase_a = 0, regs_phase_b = 0;
 };
 
 const char kFieldHead[] =
@@ -171,9 +173,12 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
                                      "-DLINON_H_INITIAL=" + float_literal(var.h_initial),
                                      "-DLINON_ADAPTIVE=" + std::to_string(var.adaptive),
                                      "-DLINON_N_FACES=" + std::to_string(var.n_faces),
+                                     "-DLINON_N_GROUPS=" + std::to_string(var.n_groups),
+                                     "-DLINON_CULL=" + std::to_string(var.cull),
                                      "-DLINON_FACE_UNROLL=" + std::to_string(var.unroll),
                                      "-DLINON_BLOCK=" + std::to_string(var.block),
-                                     "-DLINON_REFILL_MIN=" + std::to_string(var.refill_min)};
+                                     "-DLINON_REFILL_MIN=" + std::to_string(var.refill_min),
+                                     "-DLINON_PROFILE=" + std::to_string(var.profile)};
     if (var.math == 0) {
         opts.insert(opts.end(), {"--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
     } else if (var.math == 1) {
@@ -215,8 +220,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
 }
 
 std::string variant_key(const std::string& body, const Variant& v) {
-    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.math, v.block, v.unroll,
-               v.refill_min, v.max_regs) + body;
+    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile) + body;
 }
 
 }  // namespace
@@ -227,14 +232,16 @@ struct linon_view {
     int sm_count = 0;
     uint32_t W = 0, H = 0;
     cudaStream_t stream = nullptr, aux = nullptr;
-    cudaEvent_t ev[10] = {};  // 0,1 march  2,3 overlay  4,5 sample rays  6,7 outline  8 pos ready  9 aux done
+    cudaEvent_t ev[11] = {};  // 0,1 march  2,3 overlay  4,5 sample rays  6,7 outline  8 pos ready  9 aux done  10 phase A end
+    bool ran_phases = false;
     bool ran_march = false, ran_overlay = false, ran_sample = false, ran_outline = false;
 
     linon_camera camera{};
     bool has_camera = false;
     linon_settings settings{};
-    uint32_t n_faces = 0;
-    void* d_tris = nullptr;
+    uint32_t n_faces = 0, n_groups = 0;
+    void* d_tris = nullptr;   // n_faces x {v0, e1, e2} then n_groups x {unit normal, offset}
+    int* d_group_range = nullptr;
 
     void *d_final = nullptr, *d_raycast = nullptr, *d_endpoint = nullptr;
     float* d_exponents = nullptr;
@@ -254,8 +261,8 @@ struct linon_view {
     std::string body;  // current WGSL body
     std::map<std::string, Module> modules;
 
-    int opt_math = 1, opt_kernel = 1, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0;
+    int opt_math = 2, opt_kernel = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
@@ -336,9 +343,10 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     CUresult r = g_drv.ModuleLoadData(&m.mod, cubin.data());
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
     struct { const char* name; CUfunction* f; } fns[] = {
-        {"linon_march_tiles", &m.tiles},       {"linon_march_persistent", &m.persistent},
-        {"linon_sample_rays", &m.sample},      {"linon_eval_field", &m.eval_field},
-        {"linon_eval_helper", &m.eval_helper}, {"linon_eval_hit_triangle", &m.eval_hit}};
+        {"linon_march_tiles", &m.tiles},       {"linon_march_phase_a", &m.phase_a},
+        {"linon_march_phase_b", &m.phase_b},   {"linon_sample_rays", &m.sample},
+        {"linon_eval_field", &m.eval_field},   {"linon_eval_helper", &m.eval_helper},
+        {"linon_eval_hit_triangle", &m.eval_hit}};
     for (auto& f : fns) {
         r = g_drv.ModuleGetFunction(f.f, m.mod, f.name);
         if (r != CUDA_SUCCESS) {
@@ -347,7 +355,8 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
         }
     }
     g_drv.FuncGetAttribute(&m.regs_tiles, CU_FUNC_ATTRIBUTE_NUM_REGS, m.tiles);
-    g_drv.FuncGetAttribute(&m.regs_persistent, CU_FUNC_ATTRIBUTE_NUM_REGS, m.persistent);
+    g_drv.FuncGetAttribute(&m.regs_phase_a, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_a);
+    g_drv.FuncGetAttribute(&m.regs_phase_b, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_b);
     const auto t1 = std::chrono::steady_clock::now();
     if (jit_ms) *jit_ms += std::chrono::duration<float, std::milli>(t1 - t0).count();
     auto ins = v->modules.emplace(key, m);
@@ -361,11 +370,14 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     // adaptive sampling can only act while h_initial > 0.002 (src/main_view.wgsl:252,267)
     var.adaptive = (!(flags & LINON_RENDER_ADAPTIVE_OFF) && var.h_initial > 0.002f) ? 1 : 0;
     var.n_faces = (int)v->n_faces;
+    var.n_groups = (int)v->n_groups;
+    var.cull = v->opt_cull;
     var.math = v->opt_math;
     var.block = v->opt_block;
     var.unroll = v->opt_unroll;
     var.refill_min = v->opt_refill_min;
     var.max_regs = v->opt_max_regs;
+    var.profile = v->opt_profile;
     return var;
 }
 
@@ -379,6 +391,7 @@ void fill_march_params(const linon_view* v, MarchParamsH& P) {
     P.local_rows = (int)v->local_rows;
     P.shard_rank = (int)v->shard_rank; P.shard_world = (int)v->shard_world; P.rows_per_block = (int)v->rows_per_block;
     P.tris = v->d_tris;
+    P.group_range = v->d_group_range;
     P.raycast = v->d_raycast; P.endpoint = v->d_endpoint; P.hit_id = v->d_hit;
     P.counters = v->d_counters;
     P.work = v->d_work; P.q_pixel = v->d_q_pixel; P.q_state = v->d_q_state;
@@ -445,8 +458,8 @@ int linon_create(int device, uint32_t width, uint32_t height, linon_view** out) 
     cudaMemset(v->d_ray_samples, 0, 800 * 32);
     if ((e = cudaMalloc(&v->d_pos16, 64)) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(v->d_pos16, 0, 64);
-    if ((e = cudaMalloc(&v->d_counters, 3 * 8)) != cudaSuccess) return bail("cudaMalloc", e);
-    cudaMemset(v->d_counters, 0, 24);
+    if ((e = cudaMalloc(&v->d_counters, 16 * 8)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(v->d_counters, 0, 128);
     if ((e = cudaMalloc(&v->d_outline_keys, 8 * 8)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&v->d_work, 64)) != cudaSuccess) return bail("cudaMalloc", e);
     // start-up state of MainView::new
@@ -468,7 +481,7 @@ void linon_destroy(linon_view* v) {
     cudaStreamSynchronize(v->aux);
     for (auto& kv : v->modules) g_drv.ModuleUnload(kv.second.mod);
     free_frame_buffers(v);
-    cudaFree(v->d_tris); cudaFree(v->d_ray_samples); cudaFree(v->d_pos16); cudaFree(v->d_counters);
+    cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_ray_samples); cudaFree(v->d_pos16); cudaFree(v->d_counters);
     cudaFree(v->d_outline_keys); cudaFree(v->d_work);
     for (auto& ev : v->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(v->stream);
@@ -492,12 +505,61 @@ int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const ui
             t[8 + k] = c[k] - a[k];
         }
     }
+    // Plane groups for the culling test of intersect_mesh: runs of consecutive faces that lie in one plane.  A face
+    // joins the current group when its three vertices are within 1e-6 (scene units are O(1) after normalisation)
+    // of the group's plane; degenerate faces get a group of their own that is never culled (zero normal, offset -inf).
+    std::vector<float> planes;
+    std::vector<int> ranges;
+    {
+        auto plane_of = [&](uint32_t i, double n[3], double& d0) {
+            const float* t = tris.data() + 12 * i;
+            const double e1[3] = {t[4], t[5], t[6]}, e2[3] = {t[8], t[9], t[10]};
+            n[0] = e1[1] * e2[2] - e1[2] * e2[1];
+            n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+            n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+            const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (!(len > 1e-20)) return false;
+            for (int k = 0; k < 3; ++k) n[k] /= len;
+            d0 = n[0] * t[0] + n[1] * t[1] + n[2] * t[2];
+            return true;
+        };
+        uint32_t i = 0;
+        while (i < n_faces) {
+            double n[3], d0 = 0.0;
+            const bool ok = plane_of(i, n, d0);
+            uint32_t j = i + 1;
+            if (ok) {
+                for (; j < n_faces && j - i < 64; ++j) {
+                    const float* t = tris.data() + 12 * j;
+                    bool coplanar = true;
+                    for (int vtx = 0; vtx < 3 && coplanar; ++vtx) {
+                        double p[3];
+                        for (int k = 0; k < 3; ++k) p[k] = (double)t[k] + (vtx == 1 ? t[4 + k] : vtx == 2 ? t[8 + k] : 0.0f);
+                        if (std::fabs(n[0] * p[0] + n[1] * p[1] + n[2] * p[2] - d0) > 1e-6) coplanar = false;
+                    }
+                    if (!coplanar) break;
+                }
+                planes.insert(planes.end(), {(float)n[0], (float)n[1], (float)n[2], (float)d0});
+            } else {
+                planes.insert(planes.end(), {0.0f, 0.0f, 0.0f, 0.0f});  // distance 0 <= reach: always tested
+            }
+            ranges.push_back((int)i | (int)((j - i) << 16));
+            i = j;
+        }
+    }
+    const uint32_t n_groups = (uint32_t)ranges.size();
+    tris.insert(tris.end(), planes.begin(), planes.end());
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
     cudaFree(v->d_tris);
+    cudaFree(v->d_group_range);
     v->d_tris = nullptr;
+    v->d_group_range = nullptr;
     CK(v, cudaMalloc(&v->d_tris, tris.size() * sizeof(float)));
     CK(v, cudaMemcpy(v->d_tris, tris.data(), tris.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(v, cudaMalloc(&v->d_group_range, ranges.size() * sizeof(int)));
+    CK(v, cudaMemcpy(v->d_group_range, ranges.data(), ranges.size() * sizeof(int), cudaMemcpyHostToDevice));
+    v->n_groups = n_groups;
     v->n_faces = n_faces;
     return LINON_OK;
 }
@@ -538,7 +600,7 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
     CK(v, cudaSetDevice(v->device));
     // validate by building the default variant now; the previous body stays live on failure (src/main_view.rs:677-679)
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
-    if (var.n_faces == 0) var.n_faces = 36;
+    if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
     Module* m = nullptr;
     float jit = 0.0f;
     const int rc = get_module(v, wgsl_body, var, &m, &jit);
@@ -559,7 +621,7 @@ int linon_render(linon_view* v, uint32_t flags) {
         return v->fail(LINON_ERR_INVALID, "linon_render: set a mesh and a camera first");
     CK(v, cudaSetDevice(v->device));
     v->timings = linon_timings{};
-    v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = false;
+    v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = v->ran_phases = false;
 
     Module* mod = nullptr;
     MarchParamsH P;
@@ -597,32 +659,40 @@ int linon_render(linon_view* v, uint32_t flags) {
     }
 
     if (do_march && v->local_rows > 0) {
-        CK(v, cudaMemsetAsync(v->d_counters, 0, 24, v->stream));
-        unsigned grid, block = (unsigned)v->opt_block;
-        CUfunction f;
-        if (v->opt_kernel == 1) {
-            CK(v, cudaMemsetAsync(v->d_work, 0, 64, v->stream));
-            CK(v, cudaMemsetAsync(v->d_q_pixel, 0xFF, v->q_capacity * sizeof(int), v->stream));
-            int per_sm = v->opt_ctas_per_sm;
-            if (per_sm <= 0) {
-                const CUresult r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mod->persistent, (int)block, 0);
-                if (r != CUDA_SUCCESS || per_sm <= 0) return v->fail(LINON_ERR_CUDA, "occupancy query failed: " + g_drv.err_str(r));
-            }
-            grid = (unsigned)(per_sm * v->sm_count);
-            const unsigned needed = (P.n_ray_slots + block - 1) / block;
-            if (grid > needed) grid = needed;
-            f = mod->persistent;
-            v->timings.march_regs = mod->regs_persistent;
-        } else {
-            grid = (P.n_ray_slots + block - 1) / block;
-            f = mod->tiles;
-            v->timings.march_regs = mod->regs_tiles;
-        }
-        v->timings.march_grid = (int)grid;
+        CK(v, cudaMemsetAsync(v->d_counters, 0, 128, v->stream));
+        const unsigned block = (unsigned)v->opt_block;
+        const unsigned needed = (P.n_ray_slots + block - 1) / block;
         v->timings.march_block = (int)block;
         CK(v, cudaEventRecord(v->ev[0], v->stream));
-        const int rc = launch(v, f, grid, block, v->stream, &P);
-        if (rc != LINON_OK) return rc;
+        if (v->opt_kernel == 1) {
+            // persistent warps: phase A (pre-hit rays, lane refill from the fresh cursor) then phase B (queued post-hit
+            // rays) as two launches on the same stream, so phase B sees a complete, immutable queue
+            CK(v, cudaMemsetAsync(v->d_work, 0, 64, v->stream));
+            unsigned grids[2];
+            CUfunction fns[2] = {mod->phase_a, mod->phase_b};
+            for (int k = 0; k < 2; ++k) {
+                int per_sm = v->opt_ctas_per_sm;
+                if (per_sm <= 0) {
+                    const CUresult r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fns[k], (int)block, 0);
+                    if (r != CUDA_SUCCESS || per_sm <= 0) return v->fail(LINON_ERR_CUDA, "occupancy query failed: " + g_drv.err_str(r));
+                }
+                grids[k] = (unsigned)(per_sm * v->sm_count);
+                if (grids[k] > needed) grids[k] = needed;
+            }
+            int rc = launch(v, mod->phase_a, grids[0], block, v->stream, &P);
+            if (rc != LINON_OK) return rc;
+            CK(v, cudaEventRecord(v->ev[10], v->stream));
+            rc = launch(v, mod->phase_b, grids[1], block, v->stream, &P);
+            if (rc != LINON_OK) return rc;
+            v->timings.march_regs = mod->regs_phase_a;
+            v->timings.march_grid = (int)grids[0];
+            v->ran_phases = true;
+        } else {
+            const int rc = launch(v, mod->tiles, needed, block, v->stream, &P);
+            if (rc != LINON_OK) return rc;
+            v->timings.march_regs = mod->regs_tiles;
+            v->timings.march_grid = (int)needed;
+        }
         CK(v, cudaEventRecord(v->ev[1], v->stream));
         v->ran_march = true;
         v->last_rays = (uint64_t)v->local_rows * v->W;
@@ -704,20 +774,32 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_REFILL_MIN: if (value < 1 || value > 32) break; v->opt_refill_min = value; return LINON_OK;
         case LINON_OPT_FACE_UNROLL: if (value < 1 || value > 1024) break; v->opt_unroll = value; return LINON_OK;
         case LINON_OPT_MAX_REGS: if (value < 0 || value > 255) break; v->opt_max_regs = value; return LINON_OK;
+        case LINON_OPT_PROFILE: if (value < 0 || value > 1) break; v->opt_profile = value; return LINON_OK;
+        case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));
 }
 
 int linon_get_counters(linon_view* v, linon_counters* out) {
     if (!v || !out) return LINON_ERR_INVALID;
-    unsigned long long c[3];
+    unsigned long long c[4];
     CK(v, cudaSetDevice(v->device));
-    CK(v, cudaMemcpyAsync(c, v->d_counters, 24, cudaMemcpyDeviceToHost, v->stream));
+    CK(v, cudaMemcpyAsync(c, v->d_counters, 32, cudaMemcpyDeviceToHost, v->stream));
     CK(v, cudaStreamSynchronize(v->stream));
     out->rays = v->last_rays;
     out->accepted_steps = c[0];
     out->prehit_steps = c[1];
     out->rejected_steps = c[2];
+    out->face_tests = c[3];
+    out->plane_tests = v->opt_cull ? c[1] * v->n_groups : 0;
+    return LINON_OK;
+}
+
+int linon_debug_profile(linon_view* v, uint64_t* out16) {
+    if (!v || !out16) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaMemcpyAsync(out16, v->d_counters, 128, cudaMemcpyDeviceToHost, v->stream));
+    CK(v, cudaStreamSynchronize(v->stream));
     return LINON_OK;
 }
 
@@ -726,6 +808,7 @@ int linon_get_timings(linon_view* v, linon_timings* out) {
     const int rc = linon_sync(v);
     if (rc != LINON_OK) return rc;
     if (v->ran_march) cudaEventElapsedTime(&v->timings.march_ms, v->ev[0], v->ev[1]);
+    if (v->ran_march && v->ran_phases) cudaEventElapsedTime(&v->timings.march_phase_a_ms, v->ev[0], v->ev[10]);
     if (v->ran_overlay) cudaEventElapsedTime(&v->timings.overlay_ms, v->ev[2], v->ev[3]);
     if (v->ran_sample) cudaEventElapsedTime(&v->timings.sample_rays_ms, v->ev[4], v->ev[5]);
     if (v->ran_outline) cudaEventElapsedTime(&v->timings.outline_search_ms, v->ev[6], v->ev[7]);
@@ -750,6 +833,7 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     if (!wgsl_body) return LINON_ERR_INVALID;
     linon_view tmp;
     tmp.n_faces = n_faces;
+    tmp.n_groups = n_faces == 36 ? 15 : n_faces;  // the Cornell box has 15 plane groups
     tmp.opt_math = math_mode;
     const Variant var = make_variant(&tmp, flags);
     std::vector<char> cubin;
@@ -782,7 +866,7 @@ struct DevBuf {
 };
 int debug_module(linon_view* v, Module** m) {
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
-    if (var.n_faces == 0) var.n_faces = 36;
+    if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
     return get_module(v, v->body, var, m, nullptr);
 }
 }  // namespace

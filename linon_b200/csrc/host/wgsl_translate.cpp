@@ -432,10 +432,8 @@ struct Rewriter {
                 s = "w_" + s;
                 continue;
             }
-            if (s.find(' ') == std::string::npos && keywords.count(s)) {
-                // produced by our own rewrites? those contain these words only as whole replaced tokens
-                if (!(s == "float" || s == "int" || s == "unsigned" || s == "auto")) s += "_";
-            }
+            // runs before the other passes, so every keyword seen here is the user's own identifier
+            if (keywords.count(s)) s += "_";
         }
         return true;
     }

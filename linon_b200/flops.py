@@ -1,0 +1,52 @@
+"""Algorithmic FLOP model of the march (SURVEY 8(d) counting convention) — used for the roofline line of bench.py.
+
+Convention: 1 FLOP per scalar fp32 + - * / sqrt min max and per transcendental; negation, abs, compares, selects,
+integer work and loads are free; an FMA counts 2.  Counted on the WGSL as written (src/main_view.wgsl:246-270),
+scalarised.  Work the kernel skips is NOT credited: with plane culling on, only the plane tests and the
+ray-triangle tests that were actually executed are counted (the kernel reports both).
+
+Per accepted step (as written, adaptive variant): 9+9+7 stage inputs, 18 combine, 9 diff, 1 threshold, 10 blend,
+3 step_dir, 3+1 advance, 1 restore test = 71, plus 4 field evaluations of F FLOPs each.
+Fixed-step variant (Enhance, or adaptive off): the kernel drops diff / threshold / restore (11 FLOPs): 60 + 4F.
+Rejected attempt: 53 + 4F.  Pre-hit step: +15 (normalize + length of step_dir).
+Ray-triangle test with e1, e2 precomputed: 45.  Plane-distance test: 6 (3 FMA) + 5 once per pre-hit step for the reach.
+"""
+from __future__ import annotations
+
+# F per predefined function, enum order of src/functions.rs
+FIELD_FLOPS = {1: 84, 2: 79, 3: 94, 4: 89, 5: 4, 6: 4, 7: 32, 8: 8, 9: 6}
+
+STEP_ADAPTIVE = 71
+STEP_FIXED = 60
+STEP_REJECTED = 53
+PREHIT_EXTRA = 15
+FACE_TEST = 45
+PLANE_TEST = 6
+REACH = 5
+
+
+def march_flops(counters, fn_id: int, adaptive: bool, n_faces: int = 36, field_flops: int | None = None) -> float:
+    """counters: object with accepted_steps, prehit_steps, rejected_steps, face_tests, plane_tests."""
+    F = FIELD_FLOPS[fn_id] if field_flops is None else field_flops
+    step = (STEP_ADAPTIVE if adaptive else STEP_FIXED) + 4 * F
+    flops = counters.accepted_steps * step
+    flops += counters.rejected_steps * (STEP_REJECTED + 4 * F)
+    flops += counters.prehit_steps * PREHIT_EXTRA
+    flops += counters.face_tests * FACE_TEST
+    if counters.plane_tests:
+        flops += counters.plane_tests * PLANE_TEST + counters.prehit_steps * REACH
+    return float(flops)
+
+
+def as_written_flops(counters, fn_id: int, n_faces: int = 36) -> float:
+    """FLOPs the reference shader would execute for the same step counts (every face on every pre-hit step).
+    Reported for context only; never used as a roofline numerator."""
+    F = FIELD_FLOPS[fn_id]
+    return float(counters.accepted_steps * (STEP_ADAPTIVE + 4 * F) + counters.rejected_steps * (STEP_REJECTED + 4 * F)
+                 + counters.prehit_steps * (PREHIT_EXTRA + n_faces * 51))
+
+
+# Overlay stencil, algorithmic bytes per pixel: mode 1 = 4 colour in + 16 endpoint in + 4 colour out
+# + 4 exponent out; mode 0 = 4 in + 4 out.
+OVERLAY_BYTES = {0: 8, 1: 28}
+MARCH_BYTES_PER_PIXEL = 24  # 4 rgba8 + 16 endpoint + 4 hit id

@@ -250,6 +250,11 @@ class MainView:
         self._check_view(capi.lib().linon_get_timings(self._view, C.byref(t)))
         return t
 
+    def debug_profile(self) -> np.ndarray:
+        out = np.zeros(16, np.uint64)
+        self._check_view(capi.lib().linon_debug_profile(self._view, out.ctypes.data))
+        return out
+
     def device_ptr(self, buffer: int) -> int:
         return capi.lib().linon_device_ptr(self._view, buffer)
 
@@ -261,6 +266,10 @@ class MainView:
 
     def read_into(self, buffer: int, dst: np.ndarray):
         self._check_view(capi.lib().linon_read(self._view, buffer, dst.ctypes.data, dst.nbytes))
+
+    def read_into_ptr(self, buffer: int, host_ptr: int, nbytes: int):
+        """Reads a buffer into caller-owned host memory (e.g. a pinned torch tensor's data_ptr())."""
+        self._check_view(capi.lib().linon_read(self._view, buffer, host_ptr, nbytes))
 
     def read(self, buffer: int) -> np.ndarray:
         w, h = self.size

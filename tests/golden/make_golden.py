@@ -1,0 +1,42 @@
+"""Generates tests/golden/*.npz: outputs of the CPU oracle (oracle/linon_oracle.cpp) for small frames.
+
+The reference ships no golden vectors and cannot run here, so these fixtures pin the ORACLE, not the
+reference: they freeze its outputs at commit time (tests/test_golden_cpu.py re-checks the oracle against them, the
+GPU tests check the CUDA path against them without re-running the oracle).  Run: python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import cpu_oracle as co  # noqa: E402
+from oracle import np_oracle as npo  # noqa: E402
+
+W, H = 96, 72
+NAMES = {1: "MirageSpherical", 2: "MiragePlane", 3: "MirageSphericalSigmoid", 4: "MiragePlaneSigmoid", 5: "TranslationX",
+         6: "TranslationZ", 7: "Rotation", 8: "LorenzAttractor", 9: "RoesslerAttractor"}
+
+
+def main():
+    verts, faces, center = npo.default_scene()
+    cam = npo.camera_uniform(npo.default_camera(center, W, H))
+    st = npo.default_settings()
+    frames = []
+    for fn, name in NAMES.items():
+        for adaptive in ((False, True) if fn <= 4 else (False,)):
+            out = co.march(verts, faces, cam, st, fn, W, H, h_initial=0.1, adaptive=adaptive)
+            _, exps = co.overlay(out["rgba8"], out["endpoint"], dict(st, overlay_mode=1))
+            fname = f"{name}_{'adaptive' if adaptive else 'fixed'}.npz"
+            np.savez_compressed(os.path.join(HERE, fname), hit_id=out["hit_id"].astype(np.int8), rgba8=out["rgba8"],
+                                endpoint=out["endpoint"], high_lyapunov=exps >= 0.8,
+                                accepted=out["accepted"].astype(np.int16), rejected=out["rejected"].astype(np.int16))
+            frames.append(dict(file=fname, function=name, function_id=fn, adaptive=adaptive))
+    json.dump(dict(width=W, height=H, h_initial=0.1, camera={k: [float(x) for x in v] for k, v in cam.items()},
+                   settings=st, frames=frames), open(os.path.join(HERE, "index.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

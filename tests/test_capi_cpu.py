@@ -1,0 +1,109 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/*.h declares, keeps its POD layouts, and
+fails loudly (no CPU fallback) when asked to compute without a device.  CPU only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from linon_b200 import _capi as capi
+from linon_b200.main_view import ArcballCamera, LinonError, MainView, default_scene, orbit_camera
+from oracle import np_oracle as npo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in ("linon_b200.h", "linon_b200_host.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(linon_\w+)\s*\(", text))
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound(product_lib):
+    declared = declared_symbols()
+    assert len(declared) > 50
+    bound = {name for name, _, _ in capi.PROTOTYPES}
+    assert declared == bound, (declared - bound, bound - declared)
+    for name in declared:
+        assert hasattr(product_lib, name), name
+
+
+def test_pod_layouts_match_the_reference_uniforms():
+    assert C.sizeof(capi.Camera) == 112       # CameraUniform, src/main_view.rs:12-19
+    assert C.sizeof(capi.Settings) == 24      # Settings, src/main_view.rs:43-51
+    assert capi.Settings.overlay_mode.offset == 12 and capi.Settings.lyapunov_scaling.offset == 20
+    assert capi.Camera.view_direction.offset == 16 and capi.Camera.view_matrix.offset == 48
+
+
+def test_no_gpu_means_a_loud_failure_not_a_fallback(product_lib, scene):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    verts, faces, center = scene
+    with pytest.raises(LinonError) as e:
+        MainView(verts, faces, center, 64, 48)
+    assert e.value.code == capi.ERR_NO_DRIVER
+    assert "no CPU fallback" in e.value.message
+    out = C.c_void_p()
+    assert product_lib.linon_create(0, 64, 48, C.byref(out)) == capi.ERR_NO_DRIVER and not out.value
+    t = C.c_double()
+    assert product_lib.linon_measure_fp32_peak(0, C.byref(t), None) != capi.OK
+
+
+def test_product_never_touches_the_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    for root, _, files in os.walk(os.path.join(ROOT, "linon_b200")):
+        if os.path.basename(root) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(root, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "liblinon_oracle" not in text and "oracle/" not in text.replace("the CPU oracle", ""), f
+
+
+def test_host_mirror_scene_equals_the_numpy_restatement(scene):
+    verts, faces, center = scene
+    v2, f2, c2 = npo.default_scene()
+    assert np.array_equal(verts, v2) and np.array_equal(faces, f2) and np.array_equal(center, c2)
+    raw, _, _ = default_scene(negate_xz=False)  # the `r` key scene, src/application.rs:194-197
+    rv, _ = npo.cornell_box()
+    assert np.array_equal(raw, npo.normalize_vertices(rv))
+
+
+def test_host_mirror_arcball_equals_the_numpy_restatement(scene):
+    _, _, center = scene
+    for (w, h) in ((800, 600), (1920, 1080)):
+        a = ArcballCamera(center, 1.0, (w, h))
+        b = npo.Arcball(center, 1.0, [w, h])
+        a.zoom(-1.0, 1.0)
+        b.zoom(-1.0, 1.0)
+        for prev, cur in (((w / 2, h / 2), (w / 2 + 50, h / 2 + 20)), ((10, 10), (w - 5, 30)), ((w, h), (0, 0))):
+            a.rotate(prev, cur)
+            b.rotate(prev, cur)
+            u = npo.camera_uniform(b)
+            assert np.allclose(a.eye_pos(), u["origin"], atol=1e-6)
+            assert np.allclose(a.eye_dir(), u["view_direction"], atol=1e-6)
+            assert np.allclose(a.up_dir(), u["up"], atol=1e-6)
+    for k in (0, 1, 7, 32):
+        a = orbit_camera(center, 640, 480, k)
+        u = npo.camera_uniform(npo.orbit_camera(center, 640, 480, k))
+        assert np.allclose(a.eye_pos(), u["origin"], atol=1e-5) and np.allclose(a.eye_dir(), u["view_direction"], atol=1e-5)
+
+
+def test_default_camera_is_the_reference_start_up_camera(scene):
+    """eye = centre + (0,0,2), looking down -z, up +y; view_matrix is identity."""
+    _, _, center = scene
+    cam = ArcballCamera(center, 1.0, (800, 600))
+    cam.zoom(-1.0, 1.0)
+    u = cam.uniform()
+    assert np.allclose(u.origin[:3], center + np.array([0, 0, 2], np.float32), atol=1e-6)
+    assert list(u.view_direction[:3]) == [0.0, 0.0, -1.0] and list(u.up[:3]) == [0.0, 1.0, 0.0]
+    assert np.array_equal(np.array(u.view_matrix[:]).reshape(4, 4), np.eye(4))

@@ -1,0 +1,215 @@
+"""Parity of the CUDA path (through the C ABI / MainView mirror) with the CPU oracle.  Needs a B200: -m gpu.
+
+North-star bar: >= 99.9 % of pixels share the hit id (per surface group; raw reported),
+matching pixels within 1/255 per colour channel and 1e-3 relative endpoint error; pixels whose oracle Lyapunov value
+exp(50*lambda - 5) >= 0.8 are excluded and counted.  The endpoint criterion is applied to fixed-step variants only
+(adaptive step sequences are rounding-noise driven).  Strict math mode must be BIT-EXACT with the oracle on
+every body without transcendentals (integer/index work and IEEE + - * / sqrt only).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import camera_dict, settings_dict
+from linon_b200 import _capi as capi
+from linon_b200 import parity
+from linon_b200.main_view import MainView, PredefinedFunction, default_scene, make_settings, orbit_camera
+
+pytestmark = pytest.mark.gpu
+
+PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
+NO_TRANSCENDENTALS = {PredefinedFunction.MirageSpherical, PredefinedFunction.MiragePlane, PredefinedFunction.TranslationX,
+                      PredefinedFunction.TranslationZ, PredefinedFunction.LorenzAttractor, PredefinedFunction.RoesslerAttractor}
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def view(product_lib, scene):
+    verts, faces, center = scene
+    mv = MainView(verts, faces, center, 160, 120)
+    yield mv
+    mv.close()
+
+
+def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_TILES, cull=1, settings=None):
+    mv.set_option(capi.OPT_MATH, math)
+    mv.set_option(capi.OPT_KERNEL, kernel)
+    mv.set_option(capi.OPT_CULL, cull)
+    mv.reload_shader(fn.to_code() if isinstance(fn, PredefinedFunction) else fn)
+    mv.update_settings(settings if settings is not None else make_settings())
+    mv.render_flags(flags)
+    mv.sync()
+    return dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
+
+
+def oracle_frame(oracle, scene, mv, fn, h_initial=0.1, adaptive=True, settings=None, **kw):
+    verts, faces, _ = scene
+    W, H = mv.size
+    st = settings_dict(settings if settings is not None else make_settings())
+    cam = camera_dict(mv.camera.uniform())
+    ref = oracle.march(verts, faces, cam, st, int(fn), W, H, h_initial=h_initial, adaptive=adaptive, **kw)
+    # high-Lyapunov pixels as the reference itself defines them (src/overlay.wgsl:127-129, delta 1, scaling 50)
+    st1 = dict(st, overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0)
+    _, exps = oracle.overlay(ref["rgba8"], ref["endpoint"], st1)
+    return ref, parity.high_lyapunov_mask(exps)
+
+
+# ---- strict mode: bit-exact ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fn", sorted(NO_TRANSCENDENTALS))
+@pytest.mark.parametrize("adaptive", [False, True])
+@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT])
+def test_strict_mode_is_bit_exact_with_the_oracle(view, oracle, scene, fn, adaptive, kernel):
+    ref, _ = oracle_frame(oracle, scene, view, fn, adaptive=adaptive)
+    flags = 0 if adaptive else capi.RENDER_ADAPTIVE_OFF
+    got = render(view, fn, flags=flags, math=capi.MATH_STRICT, kernel=kernel)
+    assert np.array_equal(got["hit_id"], ref["hit_id"])
+    assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+    assert np.abs(got["rgba8"].astype(int) - ref["rgba8"].astype(int)).max() <= 1  # pow(x, 64): libdevice vs glibc
+    c = view.counters()
+    assert c.accepted_steps == int(ref["accepted"].sum())
+    assert c.rejected_steps == int(ref["rejected"].sum())
+    assert c.prehit_steps == int(ref["prehit"].sum())
+
+
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSpherical, PredefinedFunction.TranslationX, PredefinedFunction.Rotation])
+@pytest.mark.parametrize("flags", [0, capi.RENDER_ADAPTIVE_OFF])
+def test_plane_culling_never_changes_a_result(view, fn, flags):
+    """Exactness of the culling test: identical buffers with and without it (strict mode: same arithmetic per ray)."""
+    a = render(view, fn, flags=flags, math=capi.MATH_STRICT, cull=0)
+    ca = view.counters()
+    b = render(view, fn, flags=flags, math=capi.MATH_STRICT, cull=1)
+    cb = view.counters()
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    assert ca.face_tests == 36 * ca.prehit_steps and cb.face_tests < ca.face_tests / 10
+    assert (ca.accepted_steps, ca.prehit_steps, ca.rejected_steps) == (cb.accepted_steps, cb.prehit_steps, cb.rejected_steps)
+
+
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.LorenzAttractor])
+def test_tile_and_persistent_kernels_agree_in_strict_mode(view, fn):
+    a = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT, kernel=capi.KERNEL_TILES)
+    b = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT, kernel=capi.KERNEL_PERSISTENT)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+
+
+# ---- production modes: north-star tolerances --------------------------------------------------------------------------
+@pytest.mark.parametrize("fn", PREDEFINED)
+@pytest.mark.parametrize("math", [capi.MATH_FUSED, capi.MATH_FAST])
+def test_fixed_step_frames_meet_the_north_star(view, oracle, scene, fn, math):
+    """C1/C2 at reduced resolution, adaptive off (exactly 51 steps): hit id, colour and endpoint."""
+    ref, excl = oracle_frame(oracle, scene, view, fn, adaptive=False)
+    got = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=math)
+    m = parity.compare_frames(got, ref, exclude=excl)
+    assert parity.passes_north_star(m, check_endpoint=True), m
+    assert view.counters().accepted_steps == 160 * 120 * 51
+
+
+@pytest.mark.parametrize("fn", PREDEFINED)
+@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT])
+def test_adaptive_frames_meet_the_north_star_on_hit_and_colour(view, oracle, scene, fn, kernel):
+    """C1/C2 as the application renders them (adaptive on): graded on hit id and colour; endpoint agreement is
+    reported only (rounding-noise-driven step sequences)."""
+    ref, excl = oracle_frame(oracle, scene, view, fn, adaptive=True)
+    got = render(view, fn, flags=0, math=capi.MATH_FAST, kernel=kernel)
+    m = parity.compare_frames(got, ref, exclude=excl)
+    assert parity.passes_north_star(m, check_endpoint=False), m
+
+
+def test_enhance_frame_meets_the_north_star(product_lib, oracle, scene):
+    """C3 at reduced resolution: h = 0.001, exactly 5001 steps per ray, default function of the application."""
+    verts, faces, center = scene
+    with MainView(verts, faces, center, 64, 48) as mv:
+        fn = PredefinedFunction.MirageSphericalSigmoid
+        ref, excl = oracle_frame(oracle, scene, mv, fn, h_initial=0.001, adaptive=True)
+        for kernel in (capi.KERNEL_TILES, capi.KERNEL_PERSISTENT):
+            mv.set_option(capi.OPT_KERNEL, kernel)
+            mv.render_high_accuracy(fn.to_code())
+            mv.sync()
+            got = dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
+            m = parity.compare_frames(got, ref, exclude=excl)
+            assert parity.passes_north_star(m), m
+            c = mv.counters()
+            assert c.accepted_steps == 64 * 48 * 5001 and c.rejected_steps == 0
+            assert not mv.needs_redraw  # src/main_view.rs:801
+
+
+def test_rotated_cameras_and_partial_field_weight(product_lib, oracle, scene):
+    """Orbit cameras (C5) and field_weight < 1 (the non-degenerate attractor images of SURVEY F14)."""
+    verts, faces, center = scene
+    W, H = 128, 96
+    with MainView(verts, faces, center, W, H) as mv:
+        for frame, fn, fw in ((5, PredefinedFunction.MirageSphericalSigmoid, 1.0), (23, PredefinedFunction.MiragePlane, 1.0),
+                              (40, PredefinedFunction.LorenzAttractor, 0.05), (0, PredefinedFunction.RoesslerAttractor, 0.05)):
+            mv.set_camera_uniform(orbit_camera(center, W, H, frame).uniform())
+            st = make_settings(field_weight=fw)
+            got = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF, settings=st)
+            cam = camera_dict(orbit_camera(center, W, H, frame).uniform())
+            ref = oracle.march(verts, faces, cam, settings_dict(st), int(fn), W, H, h_initial=0.1, adaptive=False)
+            _, exps = oracle.overlay(ref["rgba8"], ref["endpoint"], dict(settings_dict(st), overlay_mode=1))
+            m = parity.compare_frames(got, ref, exclude=parity.high_lyapunov_mask(exps))
+            assert parity.passes_north_star(m), (frame, fn, m)
+
+
+def test_golden_fixtures(product_lib, scene):
+    """Committed oracle outputs (tests/golden/, made by tests/golden/make_golden.py): the GPU path is checked against
+    the fixture bytes, so a silent change of either side shows up."""
+    verts, faces, center = scene
+    idx = json.load(open(os.path.join(GOLDEN, "index.json")))
+    with MainView(verts, faces, center, idx["width"], idx["height"]) as mv:
+        for entry in idx["frames"]:
+            z = np.load(os.path.join(GOLDEN, entry["file"]))
+            fn = PredefinedFunction[entry["function"]]
+            flags = 0 if entry["adaptive"] else capi.RENDER_ADAPTIVE_OFF
+            got = render(mv, fn, flags=flags, math=capi.MATH_FAST)
+            ref = dict(hit_id=z["hit_id"].astype(np.int32), rgba8=z["rgba8"], endpoint=z["endpoint"])
+            m = parity.compare_frames(got, ref, exclude=z["high_lyapunov"])
+            assert parity.passes_north_star(m, check_endpoint=not entry["adaptive"]), (entry, m)
+            if fn in NO_TRANSCENDENTALS:
+                strict = render(mv, fn, flags=flags, math=capi.MATH_STRICT)
+                assert np.array_equal(strict["hit_id"], ref["hit_id"])
+                assert np.array_equal(strict["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+
+
+# ---- invariants that need no oracle -------------------------------------------------------------------------------------
+def test_field_weight_zero_gives_straight_rays(view):
+    st = make_settings(field_weight=0.0)
+    a = render(view, PredefinedFunction.MirageSpherical, flags=capi.RENDER_ADAPTIVE_OFF, settings=st, math=capi.MATH_STRICT)
+    b = render(view, PredefinedFunction.LorenzAttractor, flags=capi.RENDER_ADAPTIVE_OFF, settings=st, math=capi.MATH_STRICT)
+    for k in a:  # the field is ignored entirely: identical images whatever the function
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8))
+    assert (a["hit_id"] >= 0).mean() > 0.5
+
+
+def test_full_size_properties_c2_c3(product_lib, scene):
+    """Size-independent properties at BASELINE.json's full sizes (no oracle): step counts, buffer invariants,
+    determinism, and kernel-to-kernel agreement."""
+    verts, faces, center = scene
+    with MainView(verts, faces, center, 1920, 1080) as mv:
+        fn = PredefinedFunction.MirageSphericalSigmoid
+        a = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF)
+        c = mv.counters()
+        assert c.rays == 1920 * 1080 and c.accepted_steps == 1920 * 1080 * 51 and c.rejected_steps == 0
+        assert (a["endpoint"][..., 3] == 1.0).all() and (a["rgba8"][..., 3] == 255).all()
+        miss = a["hit_id"] < 0
+        assert (a["rgba8"][miss][:, :3] == 0).all() and 0.25 < miss.mean() < 0.45  # 34.9 % of rays miss
+        assert a["hit_id"].max() < 36
+        b = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF)
+        for k in a:  # deterministic
+            assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8))
+        p = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF, kernel=capi.KERNEL_PERSISTENT)
+        m = parity.compare_frames(p, a)
+        assert m["hit_group_agree"] >= 0.9999 and m["endpoint_within_1e3"] >= 0.9999, m
+    with MainView(verts, faces, center, 3840, 2160) as mv:
+        mv.update_settings(make_settings(overlay_mode=1))
+        mv.render_high_accuracy(PredefinedFunction.MirageSphericalSigmoid.to_code())
+        mv.sync()
+        c = mv.counters()
+        assert c.rays == 3840 * 2160 and c.accepted_steps == 3840 * 2160 * 5001 and c.rejected_steps == 0
+        ep = mv.mapping_texture()
+        assert np.isfinite(ep).all() and (ep[..., 3] == 1.0).all()
+        ex = mv.exponents()
+        assert (ex[:2] == 0).all() and (ex[-2:] == 0).all() and (ex[:, :2] == 0).all() and (ex[:, -2:] == 0).all()
+        assert (ex[2:-2, 2:-2] > 0).all()

@@ -1,0 +1,302 @@
+"""Unit-level parity on the GPU: helper library, hit_triangle, field functions, overlay stencil, outline search, sample
+rays, error behaviour of reload_shader, row-block shards.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+from conftest import camera_dict, settings_dict
+from linon_b200 import _capi as capi
+from linon_b200 import sharding
+from linon_b200.main_view import LinonError, MainView, PredefinedFunction, default_scene, make_settings
+
+pytestmark = pytest.mark.gpu
+
+PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
+HELPERS = dict(rotateX=0, rotateY=1, rotateZ=2, translate=3, refraction=4, point_plane_distance=5, sigmoid=6,
+               refraction_index=7, reflect=8, normalize=9, cross=10)
+EXACT_HELPERS = ("translate", "refraction", "point_plane_distance", "refraction_index", "reflect", "normalize", "cross")
+
+
+@pytest.fixture(scope="module")
+def view(product_lib, scene):
+    verts, faces, center = scene
+    mv = MainView(verts, faces, center, 128, 96)
+    yield mv
+    mv.close()
+
+
+def rand_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    nrm = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    p0 = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    a = rng.uniform(-6, 6, n).astype(np.float32)
+    b = rng.uniform(10, 200, n).astype(np.float32)
+    c = rng.uniform(-2, 2, n).astype(np.float32)
+    return v, nrm, p0, a, b, c
+
+
+@pytest.mark.parametrize("name", list(HELPERS))
+def test_helper_library_strict_mode(view, oracle, name):
+    n = 8192
+    v, nrm, p0, a, b, c = rand_inputs(n, HELPERS[name])
+    if name == "refraction":  # temperatures; includes the total-reflection branch (eta > 1, grazing incidence)
+        a = np.random.default_rng(1).uniform(10, 200, n).astype(np.float32)
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v[: n // 4] = (nrm[: n // 4] * 1e-3 + np.cross(nrm[: n // 4], p0[: n // 4])).astype(np.float32)
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    got = view.debug_eval_helper(HELPERS[name], n, v=v, nrm=nrm, p0=p0, a=a, b=b, c=c)
+    ref = oracle.helper(name, n, v=v, nrm=nrm, p0=p0, a=a, b=b, c=c)
+    if name in EXACT_HELPERS:  # IEEE + - * / sqrt, no contraction: bit-exact
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
+    else:  # sin / cos / exp: libdevice vs glibc, both within a few ulp
+        assert np.allclose(got, ref, rtol=2e-6, atol=2e-7), name
+
+
+@pytest.mark.parametrize("math,tol", [(capi.MATH_FUSED, 2e-6), (capi.MATH_FAST, 2e-5)])
+def test_helper_library_production_modes(view, oracle, math, tol):
+    n = 4096
+    v, nrm, p0, a, b, c = rand_inputs(n, 99)
+    a_t = np.random.default_rng(2).uniform(10, 200, n).astype(np.float32)
+    view.set_option(capi.OPT_MATH, math)
+    for name in HELPERS:
+        aa = a_t if name == "refraction" else a
+        got = view.debug_eval_helper(HELPERS[name], n, v=v, nrm=nrm, p0=p0, a=aa, b=b, c=c)
+        ref = oracle.helper(name, n, v=v, nrm=nrm, p0=p0, a=aa, b=b, c=c)
+        scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
+        assert (np.abs(got - ref) <= tol * 40 * scale).all(), name
+
+
+def test_rotateZ_drops_z_and_clamp_has_no_lower_bound(view):
+    """SURVEY F4 and F3 on the device."""
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    v = np.array([[1.0, 2.0, 3.0]], np.float32)
+    r = view.debug_eval_helper(HELPERS["rotateZ"], 1, v=v, a=np.zeros(1, np.float32))
+    assert np.array_equal(r, [[1.0, 2.0, 0.0]])
+    n = np.array([[0.0, 0.0, 1.0]], np.float32)
+    vin = np.array([[0.0, 0.0, -4.0]], np.float32)  # dot = -4: a real clamp(-1, 1) would change the result
+    r = view.debug_eval_helper(HELPERS["refraction"], 1, v=vin, nrm=n, a=np.array([15.0], np.float32), b=np.array([15.0], np.float32))
+    assert np.allclose(r, vin)
+
+
+def test_hit_triangle_matches_the_oracle(view, oracle):
+    rng = np.random.default_rng(7)
+    n = 20000
+    tri = rng.uniform(-1, 1, (n, 9)).astype(np.float32)
+    o = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    target = (tri[:, 0:3] + tri[:, 3:6] + tri[:, 6:9]) / 3 + rng.normal(0, 0.3, (n, 3)).astype(np.float32)
+    d = target - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # edge cases: parallel rays, origin on the plane, degenerate triangle
+    tri[0] = [0, 0, 0, 1, 0, 0, 0, 1, 0]; o[0] = [0.2, 0.2, 1]; d[0] = [1, 0, 0]
+    tri[1] = [0, 0, 0, 1, 0, 0, 0, 1, 0]; o[1] = [0.2, 0.2, 0]; d[1] = [0, 0, -1]
+    tri[2] = [0, 0, 0, 1, 1, 1, 2, 2, 2]; o[2] = [0, 0, 1]; d[2] = [0, 0, -1]
+    ref = oracle.hit_triangle(tri, o, d)
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    got = view.debug_hit_triangle(tri, o, d)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert 0.2 < (ref > 0).mean() < 0.8 and ref[0] == -1 and ref[1] == -1 and ref[2] == -1
+    view.set_option(capi.OPT_MATH, capi.MATH_FAST)
+    fast = view.debug_hit_triangle(tri, o, d)
+    same = (fast > 0) == (ref > 0)
+    assert same.mean() > 0.999
+    both = (fast > 0) & (ref > 0)
+    assert np.allclose(fast[both], ref[both], rtol=1e-4)
+
+
+@pytest.mark.parametrize("fn", PREDEFINED)
+def test_field_functions_match_the_oracle(view, oracle, fn):
+    rng = np.random.default_rng(int(fn))
+    n = 8192
+    p = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    p[: n // 2] = np.array([-0.5, 0.5, -0.5], np.float32) + rng.normal(0, 0.15, (n // 2, 3)).astype(np.float32)
+    p[n // 2: 3 * n // 4, 1] = 0.1 + rng.normal(0, 0.006, n // 4).astype(np.float32)
+    p_prev = (p + rng.normal(0, 0.01, (n, 3))).astype(np.float32)
+    v = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    v0 = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    t = rng.uniform(0, 5.1, n).astype(np.float32)
+    ref = oracle.field(int(fn), settings_dict(make_settings()), p_prev, p, v0, v, t)
+    view.reload_shader(fn.to_code())
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    got = view.debug_eval_field(p_prev, p, v0, v, t)
+    if fn in (PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.MiragePlaneSigmoid, PredefinedFunction.Rotation):
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
+    else:
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    view.set_option(capi.OPT_MATH, capi.MATH_FAST)
+    fast = view.debug_eval_field(p_prev, p, v0, v, t)
+    assert np.allclose(fast, ref, rtol=2e-4, atol=2e-5)
+
+
+def test_user_edited_function_runs_and_errors_keep_the_old_kernel(view):
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    body = "var q = p * 2.0;\nif (t > 1.0) { q = q + vec3<f32>(1.0, 0.0, 0.0); }\nreturn q.zyx + v0 * settings.field_weight;"
+    view.reload_shader(body)
+    p = np.array([[1, 2, 3], [4, 5, 6]], np.float32)
+    z = np.zeros_like(p)
+    v0 = np.array([[10, 20, 30], [10, 20, 30]], np.float32)
+    t = np.array([0.5, 2.0], np.float32)
+    got = view.debug_eval_field(z, p, v0, z, t)
+    assert np.array_equal(got, [[6 + 10, 4 + 20, 2 + 30], [12 + 10, 10 + 20, 9 + 30]])
+    with pytest.raises(LinonError) as e:  # src/main_view.rs:677-679: Err returned, old pipeline kept
+        view.reload_shader("let x = ;\nreturn v;")
+    assert e.value.code == capi.ERR_COMPILE and "field_function.wgsl(1)" in e.value.message
+    with pytest.raises(LinonError):
+        view.reload_shader("return undefined_thing;")
+    again = view.debug_eval_field(z, p, v0, z, t)
+    assert np.array_equal(again, got)
+    view.render()
+    view.sync()  # the frame still renders with the last good function
+
+
+# ---- overlay ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("delta", [1, 2, 5, 10])
+def test_overlay_matches_the_oracle(product_lib, oracle, scene, delta):
+    verts, faces, center = scene
+    W, H = 200, 150  # not a multiple of the 32x16 tile
+    with MainView(verts, faces, center, W, H) as mv:
+        fn = PredefinedFunction.MirageSphericalSigmoid
+        mv.reload_shader(fn.to_code())
+        st = make_settings(overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0)
+        mv.update_settings(st)
+        mv.disable_adaptive_sampling()
+        mv.render()
+        mv.sync()
+        raycast, ep = mv.ray_casting_texture(), mv.mapping_texture()
+        final, ex = mv.texture(), mv.exponents()
+        ref_final, ref_ex = oracle.overlay(raycast, ep, settings_dict(st))  # same inputs: isolates the stencil
+        assert np.allclose(ex, ref_ex, rtol=1e-5, atol=1e-7)
+        assert np.abs(final.astype(int) - ref_final.astype(int)).max() <= 1
+        assert (final == ref_final).mean() > 0.999
+        pad = 2 * delta
+        assert (ex[:pad] == 0).all() and (ex[:, :pad] == 0).all() and (ex[-pad:] == 0).all() and (ex[:, -pad:] == 0).all()
+        assert (final[:pad] == raycast[:pad]).all() and (final[:, -pad:] == raycast[:, -pad:]).all()
+        assert (ex >= 0.8).any()  # the mirage rim diverges
+        # mode 0 is an exact copy and leaves the exponents alone (src/overlay.wgsl:116-118)
+        mv.update_settings(make_settings(overlay_mode=0, central_difference_delta=delta))
+        mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+        mv.sync()
+        assert np.array_equal(mv.texture(), raycast) and np.array_equal(mv.exponents(), ex)
+
+
+# ---- sample rays + outline search ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.TranslationX, PredefinedFunction.LorenzAttractor])
+def test_click_mode_sample_rays(product_lib, oracle, scene, fn):
+    verts, faces, center = scene
+    W, H = 160, 120
+    with MainView(verts, faces, center, W, H) as mv:
+        mv.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+        mv.reload_shader(fn.to_code())
+        st = make_settings(mouse_pos=(0.43, 0.57), field_weight=0.3 if fn == PredefinedFunction.LorenzAttractor else 1.0)
+        mv.update_settings(st)
+        mv.render()
+        mv.sync()
+        cam = camera_dict(mv.camera.uniform())
+        pos = oracle.sample_positions(cam, settings_dict(st), W, H)
+        assert np.array_equal(mv.read(capi.BUF_SAMPLE_POS), pos)
+        ref = oracle.sample_rays(cam, settings_dict(st), int(fn), W, H, pos)
+        got = mv.ray_samples()
+        assert got.shape == (800, 8)
+        assert np.array_equal(got[:, 3:], ref[:, 3:])  # w = 1, colours, alpha 0.5 (src/ray_samples.rs layout)
+        if fn == PredefinedFunction.MirageSphericalSigmoid:
+            assert np.allclose(got[:, :3], ref[:, :3], rtol=1e-4, atol=1e-5)
+        else:
+            assert np.array_equal(got[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
+
+
+def test_outline_mode_positions_match_the_serial_search(product_lib, oracle, scene):
+    """The parallel arg-reduction must pick the same 8 pixels as the reference's serial scans (stride W)."""
+    verts, faces, center = scene
+    W, H = 240, 135
+    with MainView(verts, faces, center, W, H) as mv:
+        fn = PredefinedFunction.MirageSphericalSigmoid
+        st = make_settings(overlay_mode=1)
+        mv.update_settings(st)
+        mv.disable_adaptive_sampling()
+        mv.render()  # fills the exponents
+        mv.sync()
+        ex = mv.exponents()
+        assert (ex >= 0.8).sum() > 50
+        mv.render_outline_rays(fn.to_code())
+        mv.sync()
+        cam = camera_dict(mv.camera.uniform())
+        ref_pos = oracle.sample_positions(cam, settings_dict(st), W, H, outline=True, exponents=ex)
+        assert np.array_equal(mv.read(capi.BUF_SAMPLE_POS), ref_pos)
+        ref = oracle.sample_rays(cam, settings_dict(st), int(fn), W, H, ref_pos)
+        assert np.allclose(mv.ray_samples()[:, :3], ref[:, :3], rtol=1e-3, atol=1e-4)
+        assert mv.timings().outline_search_ms > 0
+    # nothing above the threshold: every search falls back to pixel (0, 0) -> (0, 1)
+    with MainView(verts, faces, center, 64, 48) as mv:
+        mv.render_outline_rays(PredefinedFunction.TranslationX.to_code())
+        mv.sync()
+        assert np.array_equal(mv.read(capi.BUF_SAMPLE_POS), np.tile(np.array([0.0, 1.0], np.float32), (8, 1)))
+
+
+# ---- shards ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,rpb,kernel", [(2, 32, capi.KERNEL_TILES), (3, 8, capi.KERNEL_PERSISTENT), (8, 16, capi.KERNEL_TILES)])
+def test_row_block_shards_reassemble_bit_exactly(product_lib, scene, world, rpb, kernel):
+    """N-GPU output must equal 1-GPU output bit for bit; here the N shards are rendered one after the
+    other on one GPU and merged by row ownership."""
+    verts, faces, center = scene
+    W, H = 200, 150
+    fn = PredefinedFunction.MirageSphericalSigmoid
+    with MainView(verts, faces, center, W, H) as mv:
+        mv.set_option(capi.OPT_KERNEL, kernel)
+        mv.reload_shader(fn.to_code())
+        mv.render_flags(capi.RENDER_NO_SAMPLE_RAYS)
+        mv.sync()
+        full = dict(h=mv.hit_ids(), c=mv.ray_casting_texture(), e=mv.mapping_texture())
+        rays_full = mv.counters().rays
+        merged = {k: np.zeros_like(v) for k, v in full.items()}
+        rays = 0
+        for rank in range(world):
+            mv.resize_texture(W, H)  # fresh (zeroed) buffers, like another GPU's
+            mv.set_shard(rank, world, rpb)
+            mv.render_flags(capi.RENDER_NO_SAMPLE_RAYS | capi.RENDER_NO_OVERLAY)
+            mv.sync()
+            rows = sharding.local_rows(H, rank, world, rpb)
+            part = dict(h=mv.hit_ids(), c=mv.ray_casting_texture(), e=mv.mapping_texture())
+            other = np.setdiff1d(np.arange(H), rows)
+            assert (part["c"][other] == 0).all() and (part["h"][other] == -1).all()  # other ranks' rows untouched
+            for k in merged:
+                merged[k][rows] = part[k][rows]
+            rays += mv.counters().rays
+        assert rays == rays_full == W * H
+        for k in full:
+            assert np.array_equal(full[k].view(np.uint8), merged[k].view(np.uint8)), k
+
+
+# ---- host mirror behaviour ----------------------------------------------------------------------------------------------------
+def test_main_view_mirror_follows_the_reference(product_lib, scene):
+    verts, faces, center = scene
+    with MainView(verts, faces, center, 200, 100, discrete_gpu=False) as mv:
+        assert mv.size == (100, 50)  # downscale_factor 2 on non-discrete adapters (src/main_view.rs:93,104-105)
+        assert mv.needs_redraw
+        mv.render()
+        assert not mv.needs_redraw
+        mv.update_settings(make_settings(field_weight=0.5))
+        assert mv.needs_redraw
+        mv.render()
+        mv.on_zoom(1.0)
+        assert mv.needs_redraw
+        mv.resize_texture(320, 240)
+        assert mv.size == (160, 120) and mv.texture().shape == (120, 160, 4)
+        mv.on_pointer_moved("rotate", (10, 10), (60, 40))  # dragging disables adaptive sampling (:524)
+        mv.render()
+        mv.sync()
+        assert mv.counters().rejected_steps == 0 and mv.counters().accepted_steps == 160 * 120 * 51
+        mv.enable_adaptive_sampling()
+        mv.render()
+        mv.sync()
+        assert mv.counters().rejected_steps > 0
+        cam0 = np.array(mv.camera.uniform().origin[:3])
+        mv.reset_camera()
+        assert np.allclose(mv.camera.uniform().origin[:3], center + np.array([0, 0, 2], np.float32), atol=1e-6)
+        assert not np.allclose(cam0, mv.camera.uniform().origin[:3])
+        # update_model: the `r` key scene (no axis inversion, src/application.rs:194-197)
+        v2, f2, c2 = default_scene(negate_xz=False)
+        mv.update_model(v2, f2, c2)
+        mv.render()
+        mv.sync()
+        assert (mv.hit_ids() >= 0).any()

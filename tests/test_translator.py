@@ -1,0 +1,169 @@
+"""WGSL -> CUDA translator (linon_b200/csrc/host/wgsl_translate.cpp): the nine predefined bodies byte-for-byte from
+the reference, user-edit constructs, error reporting, NVRTC compile for sm_100a without a GPU,
+and execution of the translated text on the CPU against the oracle's hand-transcribed functions.  CPU only."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from linon_b200 import _capi as capi
+from linon_b200.main_view import LinonError, PredefinedFunction, compile_check, translate_wgsl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="reference mount not present")
+def test_bodies_are_byte_identical_with_functions_rs(product_lib):
+    src = open(os.path.join(REFERENCE, "src/functions.rs"), encoding="utf-8").read()
+    body = src[src.index("pub fn to_code"):]
+    ref = {m.group(1): m.group(2) for m in
+           re.finditer(r'Self::(\w+) => "((?:[^"\\]|\\.)*)"\s*\.to_string\(\)', body, re.S)}
+    assert len(ref) == 10
+    for fn in PredefinedFunction:
+        assert fn.to_code() == ref[fn.name], fn.name
+    names = src[src.index("fn to_string"):src.index("pub fn to_code")]
+    for fn in PredefinedFunction:
+        assert f'"{fn.to_string()}"' in names
+
+
+def test_translation_of_predefined_bodies(product_lib):
+    t = translate_wgsl(PredefinedFunction.MirageSpherical.to_code())
+    assert "const auto t_env = 15.0f;" in t and "°" not in t           # literal suffixed, UTF-8 comment dropped
+    assert "const auto center = vec3f(-0.5f, 0.5f, -0.5f);" in t
+    assert "w_clamp(0.0f, 1.0f, dist_in / max_dist)" in t                   # misordered arguments kept as written
+    assert "return refraction(t_in, t_out, v, normal);" in t
+    t = translate_wgsl(PredefinedFunction.LorenzAttractor.to_code())
+    assert "const auto beta = (float)(8.0 / 3.0);" in t                     # folded in f64 like naga's abstract floats
+    assert re.search(r"p\.x \* p\.y - beta \* p\.z\s*\)", t)                # trailing comma removed
+    t = translate_wgsl(PredefinedFunction.Rotation.to_code())
+    assert t.strip() == "return w_normalize(v0 + rotateZ(v0, PI * t));"
+    for fn in PREDEFINED:  # line structure is preserved (diagnostics map 1:1)
+        assert translate_wgsl(fn.to_code()).count("\n") == fn.to_code().count("\n")
+
+
+USER_EDITS = {
+    "typed let / var / if-else": """
+        var q: vec3<f32> = p;
+        let s: f32 = sin(t) * 0.5;
+        if (q.y > 0.5) { q.y = q.y - s; } else if q.x < 0.0 { q = -q; } else { q.x += 1e-3; }
+        return normalize(q + v0 * f32(2));""",
+    "for loop, i32, swizzles": """
+        var acc = vec3<f32>(0.0);
+        for (var i: i32 = 0; i < 4; i = i + 1) { acc = acc + v.zyx * f32(i); }
+        let w = vec3(acc.xy, 1.0);
+        return mix(w, p.xxy, 0.25) + vec3f(1, 2, 3).rgb;""",
+    "select / settings / while / builtins": """
+        var k = 0u;
+        var x = abs(p.x) + min(p.y, max(p.z, 0.0)) + pow(2.0, 3.0) + exp(-t) + sqrt(dot(v, v)) + tan(0.1);
+        while (k < 3u) { x = x * 0.5; k = k + 1u; }
+        let c = cross(v, v0) + reflect(v, normalize(p)) * step(0.5, x);
+        return select(c, -c, settings.field_weight < 0.5) + camera.origin.xyz * 0.0;""",
+    "block comment, var without init, matrices": """
+        /* nested /* comment */ with
+           two lines */
+        var m: vec3<f32>;
+        let r = mat3x3<f32>(vec3<f32>(1.0, 0.0, 0.0), vec3<f32>(0.0, 1.0, 0.0), vec3<f32>(0.0, 0.0, 1.0));
+        m = r * v + rotateX(v, 0.5) + rotateY(v, PI) + translate(p, 1.0, 2.0, 3.0);
+        let int = 3.0; // a C++ keyword is a fine WGSL name
+        return m * int + vec3<f32>(sigmoid(t), refraction_index(20.0), point_plane_distance(p, v0, p_prev));""",
+}
+
+
+@pytest.mark.parametrize("name", list(USER_EDITS))
+def test_user_edit_constructs_compile_for_sm100a(product_lib, name):
+    assert compile_check(USER_EDITS[name]) > 0
+
+
+@pytest.mark.parametrize("fn", PREDEFINED)
+@pytest.mark.parametrize("flags,math", [(0, capi.MATH_FUSED), (capi.RENDER_ENHANCE, capi.MATH_FAST),
+                                        (capi.RENDER_ADAPTIVE_OFF, capi.MATH_STRICT)])
+def test_predefined_bodies_compile_for_sm100a(product_lib, fn, flags, math):
+    assert compile_check(fn.to_code(), flags=flags, math_mode=math) > 100_000  # a real cubin came back
+
+
+def test_compile_errors_cite_the_users_line(product_lib):
+    body = "let a = 1.0;\nlet b = a +* 2.0;\nreturn vec3<f32>(a, b, undefined_name);"
+    with pytest.raises(LinonError) as e:
+        compile_check(body)
+    assert e.value.code == capi.ERR_COMPILE
+    assert "field_function.wgsl(2)" in e.value.message or "field_function.wgsl(3)" in e.value.message
+    with pytest.raises(LinonError) as e:
+        compile_check("return vec3<f32>(1.0, 2.0, nope);")
+    assert "field_function.wgsl(1)" in e.value.message and "nope" in e.value.message
+
+
+@pytest.mark.parametrize("body,needle", [
+    ("loop { break; }\nreturn v;", "loop"),
+    ("let x = 1.0h;\nreturn v;", "f16"),
+    ("let a: array<f32, 3> = array<f32, 3>(1.0, 2.0, 3.0);\nreturn v;", "array"),
+    ("let x = vec3<i32>(1, 2, 3);\nreturn v;", "vec3<i32>"),
+    ("/* never closed\nreturn v;", "comment"),
+    ("let ° = 1.0;\nreturn v;", "non-ASCII"),
+])
+def test_unsupported_wgsl_is_rejected_by_the_translator(product_lib, body, needle):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl(body)
+    assert e.value.code == capi.ERR_COMPILE and needle in e.value.message
+
+
+# ---- run the translated text on the CPU against the oracle ------------------------------------------------------
+HOST_WRAPPER = r'''
+#include "%(prelude)s"
+struct SettingsPOD { float field_weight, mouse_x, mouse_y; int overlay_mode, central_difference_delta; float lyapunov_scaling; };
+static inline vec3f field_function(const vec3f p_prev, const vec3f p, const vec3f v0, const vec3f v, const float t,
+                                   const WgslSettings& settings, const WgslCamera& camera) {
+%(body)s
+}
+extern "C" void custom_field(const float* a, const float* b, const float* c, const float* d, float t,
+                             const SettingsPOD* st, float* out) {
+    WgslSettings s = {st->field_weight, st->mouse_x, st->mouse_y, st->overlay_mode, st->central_difference_delta, st->lyapunov_scaling};
+    WgslCamera cam;
+    const vec3f r = field_function(vec3f(a[0], a[1], a[2]), vec3f(b[0], b[1], b[2]), vec3f(c[0], c[1], c[2]),
+                                   vec3f(d[0], d[1], d[2]), t, s, cam);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+'''
+
+
+def build_host_field(body: str, workdir: str, name: str):
+    """Compiles the TRANSLATOR OUTPUT for the host against the product's own prelude and returns the CDLL."""
+    src = os.path.join(workdir, name + ".cpp")
+    so = os.path.join(workdir, name + ".so")
+    with open(src, "w") as f:
+        f.write(HOST_WRAPPER % dict(prelude=os.path.join(ROOT, "linon_b200/csrc/device/wgsl_prelude.cuh"),
+                                    body=translate_wgsl(body)))
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-fPIC",
+                    "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", so], check=True, capture_output=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("fn", PREDEFINED)
+def test_translated_bodies_equal_the_oracles_transcriptions(product_lib, oracle, fn):
+    rng = np.random.default_rng(int(fn))
+    n = 4096
+    p = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    p[: n // 2] = np.array([-0.5, 0.5, -0.5], np.float32) + rng.normal(0, 0.15, (n // 2, 3)).astype(np.float32)  # in the heat sphere
+    p[n // 2: 3 * n // 4, 1] = 0.1 + rng.normal(0, 0.006, n // 4).astype(np.float32)                          # near the mirage plane
+    p_prev = (p + rng.normal(0, 0.01, (n, 3))).astype(np.float32)
+    v = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    v0 = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    t = rng.uniform(0, 5.1, n).astype(np.float32)
+    st = dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=0, central_difference_delta=1, lyapunov_scaling=50.0)
+    expect = oracle.field(int(fn), st, p_prev, p, v0, v, t)
+    with tempfile.TemporaryDirectory() as d:
+        lib = build_host_field(fn.to_code(), d, fn.name)
+        fnptr = C.cast(lib.custom_field, C.c_void_p)
+        oracle.lib().oracle_set_custom_field(fnptr)
+        try:
+            got = oracle.field(0, st, p_prev, p, v0, v, t)
+        finally:
+            oracle.lib().oracle_set_custom_field(None)
+    # same compiler, same libm, no contraction: the translated text must reproduce the transcription bit for bit
+    assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))

@@ -43,11 +43,18 @@ for fn in PredefinedFunction:
                 mv.set_option(capi.OPT_MATH, math)
                 mv.set_option(capi.OPT_KERNEL, kernel)
                 flags = 0 if adaptive else capi.RENDER_ADAPTIVE_OFF
+                mv.set_option(capi.OPT_CULL, 0)
+                mv.render_flags(flags)
+                mv.sync()
+                nocull = dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
+                mv.set_option(capi.OPT_CULL, 1)
                 mv.render_flags(flags)
                 mv.sync()
                 test = dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
                 m = parity.compare_frames(test, ref)
                 c = mv.counters()
+                m["cull_identical"] = bool(all(np.array_equal(test[k].view(np.uint8), nocull[k].view(np.uint8)) for k in test))
+                m["face_tests"] = c.face_tests
                 m.update(fn=fn.name, adaptive=adaptive, math=math, kernel=kernel,
                          accepted=c.accepted_steps, prehit=c.prehit_steps, rejected=c.rejected_steps,
                          oracle_accepted=int(ref["accepted"].sum()), oracle_prehit=int(ref["prehit"].sum()),
@@ -56,28 +63,33 @@ for fn in PredefinedFunction:
                 print(json.dumps(m), flush=True)
 
 # timing at larger sizes
-for (w, h, flags, name) in ((1920, 1080, 0, "1080p default"), (960, 540, capi.RENDER_ENHANCE, "540p enhance"),
-                            (1920, 1080, capi.RENDER_ENHANCE, "1080p enhance")):
+for (w, h, flags, name) in ((1920, 1080, 0, "1080p default"), (1920, 1080, capi.RENDER_ENHANCE, "1080p enhance")):
     mv.resize_texture(w, h)
     mv.reload_shader(PredefinedFunction.MirageSphericalSigmoid.to_code())
     for math in (1, 2):
         for kernel in (0, 1):
-            mv.set_option(capi.OPT_MATH, math)
-            mv.set_option(capi.OPT_KERNEL, kernel)
-            for rep in range(2):
-                t0 = time.time()
-                mv.render_flags(flags)
-                mv.sync()
-                wall = time.time() - t0
-            t = mv.timings()
-            c = mv.counters()
-            rec = dict(name=name, math=math, kernel=kernel, march_ms=t.march_ms, overlay_ms=t.overlay_ms,
-                       sample_ms=t.sample_rays_ms, jit_ms=t.jit_ms, regs=t.march_regs, grid=t.march_grid, wall_s=wall,
-                       accepted=c.accepted_steps, prehit=c.prehit_steps, rejected=c.rejected_steps,
-                       gsteps_per_s=(c.accepted_steps + c.rejected_steps) / (t.march_ms * 1e-3) / 1e9,
-                       mrays_per_s=c.rays / (t.march_ms * 1e-3) / 1e6)
-            out["timing"].append(rec)
-            print(json.dumps(rec), flush=True)
+            for cull in (0, 1):
+                for refill in ((1, 8) if kernel == 1 else (1,)):
+                    mv.set_option(capi.OPT_MATH, math)
+                    mv.set_option(capi.OPT_KERNEL, kernel)
+                    mv.set_option(capi.OPT_CULL, cull)
+                    mv.set_option(capi.OPT_REFILL_MIN, refill)
+                    for rep in range(2):
+                        t0 = time.time()
+                        mv.render_flags(flags)
+                        mv.sync()
+                        wall = time.time() - t0
+                    t = mv.timings()
+                    c = mv.counters()
+                    rec = dict(name=name, math=math, kernel=kernel, cull=cull, refill=refill, march_ms=t.march_ms,
+                               phase_a_ms=t.march_phase_a_ms, overlay_ms=t.overlay_ms,
+                               sample_ms=t.sample_rays_ms, jit_ms=t.jit_ms, regs=t.march_regs, grid=t.march_grid, wall_s=wall,
+                               accepted=c.accepted_steps, prehit=c.prehit_steps, rejected=c.rejected_steps,
+                               face_tests=c.face_tests, plane_tests=c.plane_tests,
+                               gsteps_per_s=(c.accepted_steps + c.rejected_steps) / (t.march_ms * 1e-3) / 1e9,
+                               mrays_per_s=c.rays / (t.march_ms * 1e-3) / 1e6)
+                    out["timing"].append(rec)
+                    print(json.dumps(rec), flush=True)
 
 json.dump(out, open("gpurun_out/first_light.json", "w"), indent=1)
 print("done")
