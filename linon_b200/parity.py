@@ -34,6 +34,16 @@ def high_lyapunov_mask(exponents_scaled: np.ndarray, threshold: float = 0.8) -> 
     return exponents_scaled >= threshold
 
 
+def disagreement_mask(a: dict, b: dict, n_faces: int = 36) -> np.ndarray:
+    """Pixels where two renderings differ in surface group or by more than 1/255 in a colour channel.  Used to mark
+    pixels that the ORACLE ITSELF cannot decide in adaptive mode (fp32 vs fp64 vs a 1-ulp perturbed run): adaptive
+    step sequences are driven by rounding noise, so such pixels are excluded and counted, like the
+    high-Lyapunov ones."""
+    g = canonical_hits(a["hit_id"], n_faces) != canonical_hits(b["hit_id"], n_faces)
+    c = np.abs(a["rgba8"].astype(np.int16) - b["rgba8"].astype(np.int16)).max(axis=-1) > 1
+    return g | c
+
+
 def compare_frames(test: dict, ref: dict, exclude: np.ndarray | None = None, sample: np.ndarray | None = None,
                    n_faces: int = 36) -> dict:
     """test / ref: dicts with hit_id [H,W] i32, rgba8 [H,W,4] u8, endpoint [H,W,>=3] f32.

@@ -29,9 +29,16 @@ def main():
         for adaptive in ((False, True) if fn <= 4 else (False,)):
             out = co.march(verts, faces, cam, st, fn, W, H, h_initial=0.1, adaptive=adaptive)
             _, exps = co.overlay(out["rgba8"], out["endpoint"], dict(st, overlay_mode=1))
+            undecided = np.zeros((H, W), bool)
+            if adaptive:  # pixels the oracle itself cannot decide in adaptive mode
+                from linon_b200 import parity  # pure numpy bookkeeping
+                alt64 = co.march(verts, faces, cam, st, fn, W, H, h_initial=0.1, adaptive=True, use_fp64=True)
+                st_ulp = dict(st, field_weight=float(np.nextafter(np.float32(1.0), np.float32(0))))
+                alt_ulp = co.march(verts, faces, cam, st_ulp, fn, W, H, h_initial=0.1, adaptive=True)
+                undecided = parity.disagreement_mask(alt64, out) | parity.disagreement_mask(alt_ulp, out)
             fname = f"{name}_{'adaptive' if adaptive else 'fixed'}.npz"
             np.savez_compressed(os.path.join(HERE, fname), hit_id=out["hit_id"].astype(np.int8), rgba8=out["rgba8"],
-                                endpoint=out["endpoint"], high_lyapunov=exps >= 0.8,
+                                endpoint=out["endpoint"], high_lyapunov=exps >= 0.8, undecided=undecided,
                                 accepted=out["accepted"].astype(np.int16), rejected=out["rejected"].astype(np.int16))
             frames.append(dict(file=fname, function=name, function_id=fn, adaptive=adaptive))
     json.dump(dict(width=W, height=H, h_initial=0.1, camera={k: [float(x) for x in v] for k, v in cam.items()},
