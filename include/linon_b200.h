@@ -90,8 +90,10 @@ enum {
     LINON_OPT_FACE_UNROLL = 5,   /* unroll of the face loop. Default 4 */
     LINON_OPT_MAX_REGS = 6,      /* NVRTC --maxrregcount (0 = none). Default 0 */
     LINON_OPT_PROFILE = 7,       /* 1: persistent kernel accumulates clock64 section timers (linon_debug_profile) */
-    LINON_OPT_CULL = 8           /* 1 (default): skip faces whose plane the step segment cannot reach (exact, results
-                                    unchanged); 0: test every face on every pre-hit step like the reference */
+    LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
+                                    nearest face plane skips the loop entirely while no plane is in reach, and plane groups
+                                    out of reach are skipped inside it; results are bit-identical with 0.
+                                    0: test every face on every pre-hit step like the reference */
 };
 
 typedef struct linon_counters { /* per-frame totals over every ray of the last march */
@@ -101,6 +103,7 @@ typedef struct linon_counters { /* per-frame totals over every ray of the last m
     uint64_t rejected_steps;    /* RK4 attempts rejected by adaptive sampling */
     uint64_t face_tests;        /* ray-triangle tests actually executed (36 per pre-hit step without culling) */
     uint64_t plane_tests;       /* plane-distance culling tests executed (0 when culling is off) */
+    uint64_t culling_checks;    /* pre-hit steps whose safe-distance bound expired, i.e. that ran the plane-group loop */
 } linon_counters;
 
 typedef struct linon_timings { /* CUDA-event times of the last render, milliseconds (0 when the pass did not run) */
@@ -179,8 +182,8 @@ int linon_debug_eval_helper(linon_view* v, int which, uint32_t n, const float* v
 int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const float* origin, const float* dir,
                              float* t_out);
 
-/* Raw counter block of the last march (16 x u64): [0..3] as linon_counters, then section timers of the persistent
- * kernels when LINON_OPT_PROFILE = 1: [4..8] phase A, [9..13] phase B = refill cycles, step cycles, warp iterations,
+/* Raw counter block of the last march (16 x u64): [0..4] accepted, pre-hit, rejected, face tests, culling checks; then section timers of the persistent
+ * kernels when LINON_OPT_PROFILE = 1: [5..9] phase A, [10..14] phase B = refill cycles, step cycles, warp iterations,
  * live lanes summed over iterations, warp lifetime cycles. */
 int linon_debug_profile(linon_view* v, uint64_t* out16);
 

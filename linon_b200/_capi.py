@@ -42,7 +42,8 @@ class Settings(C.Structure):  # linon_settings, 24 B
 
 class Counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("accepted_steps", C.c_uint64), ("prehit_steps", C.c_uint64),
-                ("rejected_steps", C.c_uint64), ("face_tests", C.c_uint64), ("plane_tests", C.c_uint64)]
+                ("rejected_steps", C.c_uint64), ("face_tests", C.c_uint64), ("plane_tests", C.c_uint64),
+                ("culling_checks", C.c_uint64)]
 
 
 class Timings(C.Structure):

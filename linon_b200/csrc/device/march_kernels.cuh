@@ -14,7 +14,7 @@
 //   LINON_BLOCK          threads per CTA of the march kernels
 //   LINON_REFILL_MIN     idle lanes a warp tolerates before it refills (persistent kernel)
 //   LINON_CULL / LINON_N_GROUPS  plane culling of the face loop (see intersect_mesh) and the number of plane groups
-//   LINON_PROFILE        1 adds clock64 section timers to the persistent kernels (counters[4..13])
+//   LINON_PROFILE        1 adds clock64 section timers to the persistent kernels (counters[5..14])
 //
 // Two march kernels share every per-ray device function, so their per-pixel results are bit-identical:
 //   linon_march_tiles       one thread per pixel, 8x4 pixel tiles per warp (the straightforward mapping)
@@ -83,7 +83,8 @@ struct MarchParams {
     int* hit_id;                  // [height][width]  face index of the first hit, -1 = none
     unsigned long long* counters; // [0] accepted steps  [1] steps that ran the face loop  [2] rejected attempts
                                   // [3] ray-triangle tests actually performed (after culling)
-                                  // LINON_PROFILE: phase A [4..8], phase B [9..13] = refill cycles, step cycles,
+                                  // [4] pre-hit steps that ran the plane-group loop (all of them without culling)
+                                  // LINON_PROFILE: phase A [5..9], phase B [10..14] = refill cycles, step cycles,
                                   // warp iterations, live lanes summed over iterations, warp lifetime cycles
     // persistent kernel only
     unsigned int* work;           // [0] next fresh ray slot  [1] queue tail (phase A pushes)  [2] queue head (phase B pops)
@@ -174,28 +175,32 @@ __device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int 
 
 // ray_color's loop over every face (src/main_view.wgsl:182-198), keeping the closest hit in (0, max_dist).
 //
-// LINON_CULL: a face can only report t in (eps, max_dist) if the step segment reaches its plane, i.e. if the distance
-// of the segment origin to the plane is at most max_dist (direction is a unit vector).  The host groups runs of
-// consecutive coplanar faces; one signed distance (3 FFMA) + one compare per group decides whether the group's faces
-// are tested at all.  The margin (2e-3 relative on max_dist plus 1e-5 (1 + |origin|_1) absolute) is orders of magnitude
-// above the rounding error of either computation, so a skipped face is one the full test would have rejected:
-// results are bit-identical with LINON_CULL = 0 (tests/test_gpu_parity.py checks it).  Faces are still visited in
-// index order, so the strict `t_new < t` tie-break of the reference (lowest index wins) is preserved.
+// LINON_CULL, level 1 (here): a face can only report t in (eps, max_dist) if the step segment reaches its plane, i.e.
+// if the distance of the segment origin to the plane is at most max_dist (direction is a unit vector).  The host groups
+// runs of consecutive coplanar faces; one signed distance (3 FFMA) + one compare per group decides whether the group's
+// faces are tested at all.  The margin (2e-3 relative on max_dist plus 1e-5 (1 + |origin|_1) absolute) is orders of
+// magnitude above the rounding error of either computation, so a skipped face is one the full test would have
+// rejected: results are bit-identical with LINON_CULL = 0 (tests/test_gpu_parity.py checks it).  Faces are still
+// visited in index order, so the strict `t_new < t` tie-break of the reference (lowest index wins) is preserved.
+// The smallest plane distance is returned for level 2 (see SafeDistance).
 __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri, const int* __restrict__ s_range,
-                                               vec3f origin, vec3f direction, float max_dist, float& t_best,
-                                               int& id_best, unsigned int& face_tests) {
+                                               vec3f origin, vec3f direction, float max_dist, float origin_l1,
+                                               float& t_best, int& id_best, float& min_plane_dist,
+                                               unsigned int& face_tests) {
     t_best = -1.0f;
     id_best = -1;
 #if LINON_CULL
-    const float reach = 1.002f * max_dist + 1e-5f * (1.0f + fabsf(origin.x) + fabsf(origin.y) + fabsf(origin.z));
+    const float reach = 1.002f * max_dist + 1e-5f * (1.0f + origin_l1);
     const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES;
+    float nearest = 3.0e38f;
     // partial unroll on purpose: a fully unrolled loop lets the compiler hoist all plane loads out of the time loop
     // (60 live registers, spills); with a loop-carried index the planes stay in shared memory (broadcast LDS.128)
 #pragma unroll LINON_GROUP_UNROLL
     for (int g = 0; g < LINON_N_GROUPS; ++g) {
         const float4 pl = s_plane[g];
-        const float dist = __fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w)));
-        if (fabsf(dist) <= reach) {
+        const float dist = fabsf(__fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w))));
+        nearest = fminf(nearest, dist);
+        if (dist <= reach) {
             const int range = s_range[g];
             const int first = range & 0xffff, last = first + (range >> 16);
 #pragma unroll 1
@@ -205,12 +210,37 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
             }
         }
     }
+    min_plane_dist = nearest;
 #else
 #pragma unroll LINON_FACE_UNROLL
     for (int i = 0; i < LINON_N_FACES; ++i) test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
     face_tests += LINON_N_FACES;
+    min_plane_dist = 0.0f;
 #endif
 }
+
+// LINON_CULL, level 2: a lower bound `safe` on the distance from the ray's current point to the nearest face plane.
+// After a full check at p it is (min plane distance - rounding allowance); every step then subtracts an upper bound of
+// the distance moved (the L1 norm of step_dir, added with round-up, subtracted with round-down, so `safe` stays a
+// valid lower bound).  While safe exceeds what this step can reach, no plane group could pass the level-1 test, so the
+// whole face loop - including normalize(step_dir) and length(step_dir), which only feed it - is skipped.  Exact for the
+// same reason as level 1; a pre-hit step then costs ~9 instructions instead of ~110.
+struct SafeDistance {
+    float safe;
+    __device__ __forceinline__ void reset() { safe = 0.0f; }
+    // true: the face loop must run for the step p -> p + step_dir
+    __device__ __forceinline__ bool must_check(vec3f p, vec3f step_dir, float& travel, float& p_l1) const {
+        travel = __fadd_ru(__fadd_ru(fabsf(step_dir.x), fabsf(step_dir.y)), fabsf(step_dir.z));
+        p_l1 = fabsf(p.x) + fabsf(p.y) + fabsf(p.z);
+#if LINON_CULL
+        return !(safe > __fmaf_rn(1.003f, travel, 1e-5f * (1.0f + p_l1)));  // NaN-safe: unordered -> check
+#else
+        return true;
+#endif
+    }
+    __device__ __forceinline__ void checked(float min_plane_dist, float p_l1) { safe = min_plane_dist - 1e-6f * (1.0f + p_l1); }
+    __device__ __forceinline__ void moved(float travel) { safe = __fsub_rd(safe, travel); }
+};
 
 // Blinn-Phong with the camera as light, src/main_view.wgsl:199-217.
 __device__ __forceinline__ vec3f shade(const float4* __restrict__ s_tri, int id, vec3f direction) {
@@ -261,24 +291,26 @@ __device__ __forceinline__ void init_ray(const MarchParams& P, int x, int local_
 }
 
 struct StepCounters {
-    unsigned int accepted, prehit, rejected, face_tests;
+    unsigned int accepted, prehit, rejected, face_tests, checks;
 };
 
 __device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounters c) {
     // per-lane 32-bit counts are widened before the reduction (a persistent lane can exceed 2^32 face tests)
-    unsigned long long a = c.accepted, b = c.prehit, r = c.rejected, f = c.face_tests;
+    unsigned long long a = c.accepted, b = c.prehit, r = c.rejected, f = c.face_tests, k = c.checks;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
         r += __shfl_xor_sync(0xffffffffu, r, o);
         f += __shfl_xor_sync(0xffffffffu, f, o);
+        k += __shfl_xor_sync(0xffffffffu, k, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&P.counters[0], a);
         atomicAdd(&P.counters[1], b);
         atomicAdd(&P.counters[2], r);
         atomicAdd(&P.counters[3], f);
+        atomicAdd(&P.counters[4], k);
     }
 }
 
@@ -330,13 +362,15 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
     const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
     int x, local_row;
     const bool valid = slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row);
-    StepCounters cnt = {0u, 0u, 0u, 0u};
+    StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
     if (valid) {
         const WgslCamera cam = make_camera(P);
         const WgslSettings st = P.settings;
         Ray r;
         init_ray(P, x, local_row, r);
         bool has_color = false;
+        SafeDistance sd;
+        sd.reset();
         vec3f color(0.0f, 0.0f, 0.0f);
         int hit = -1;
         for (; r.t <= 5.0f;) {
@@ -347,16 +381,22 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 continue;
             }
             if (!has_color) {
-                const float max_dist = w_length(step_dir);
-                const vec3f dirn = w_normalize(step_dir);
-                float t_hit;
-                int id;
-                intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, t_hit, id, cnt.face_tests);
-                if (t_hit > 0.0f && t_hit < max_dist) {
-                    color = shade(s_tri, id, dirn);
-                    hit = id;
-                    has_color = true;  // result.color.a = t > 0
+                float travel, p_l1;
+                if (sd.must_check(r.p, step_dir, travel, p_l1)) {
+                    const float max_dist = w_length(step_dir);
+                    const vec3f dirn = w_normalize(step_dir);
+                    float t_hit, nearest;
+                    int id;
+                    intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                    ++cnt.checks;
+                    sd.checked(nearest, p_l1);
+                    if (t_hit > 0.0f && t_hit < max_dist) {
+                        color = shade(s_tri, id, dirn);
+                        hit = id;
+                        has_color = true;  // result.color.a = t > 0
+                    }
                 }
+                sd.moved(travel);
                 ++cnt.prehit;
             }
             rk4_advance(r, v, diff, step_dir);
@@ -422,7 +462,9 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
     int pix = -1;            // pixel index of the ray this lane carries
     bool alive = false;
     bool fresh_left = true;  // warp-uniform
-    StepCounters cnt = {0u, 0u, 0u, 0u};
+    SafeDistance sd;
+    sd.reset();
+    StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
     PF_DECL
 
     for (;;) {
@@ -438,6 +480,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 int x, local_row;
                 if (slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row)) {
                     init_ray(P, x, local_row, r);
+                    sd.reset();
                     pix = texture_row(P, local_row) * P.width + x;
                     alive = true;
                 }
@@ -460,17 +503,24 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             vec3f v, step_dir;
             float diff;
             if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
-                const float max_dist = w_length(step_dir);
-                const vec3f dirn = w_normalize(step_dir);
-                float t_hit;
-                int id;
-                intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, t_hit, id, cnt.face_tests);
-                ++cnt.prehit;
-                const bool hit_now = t_hit > 0.0f && t_hit < max_dist;
-                if (hit_now) {
-                    P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
-                    P.hit_id[pix] = id;
+                float travel, p_l1;
+                bool hit_now = false;
+                if (sd.must_check(r.p, step_dir, travel, p_l1)) {
+                    const float max_dist = w_length(step_dir);
+                    const vec3f dirn = w_normalize(step_dir);
+                    float t_hit, nearest;
+                    int id;
+                    intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                    ++cnt.checks;
+                    sd.checked(nearest, p_l1);
+                    hit_now = t_hit > 0.0f && t_hit < max_dist;
+                    if (hit_now) {
+                        P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
+                        P.hit_id[pix] = id;
+                    }
                 }
+                sd.moved(travel);
+                ++cnt.prehit;
                 rk4_advance(r, v, diff, step_dir);
                 ++cnt.accepted;
                 const bool finished = !(r.t <= 5.0f);
@@ -503,7 +553,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         PF_END(pf_step, pf_s0)
     }
     flush_counters(P, cnt);
-    PF_FLUSH(4)
+    PF_FLUSH(5)
 }
 
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_phase_b(const MarchParams P) {
@@ -520,7 +570,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
     int pix = -1;
     bool alive = false;
     bool queue_left = true;  // warp-uniform
-    StepCounters cnt = {0u, 0u, 0u, 0u};
+    StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
     PF_DECL
 
     for (;;) {
@@ -574,7 +624,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         PF_END(pf_step, pf_s0)
     }
     flush_counters(P, cnt);
-    PF_FLUSH(9)
+    PF_FLUSH(10)
 }
 
 // ------------------------------------------------------------------------------------------------------------

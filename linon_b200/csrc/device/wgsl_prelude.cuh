@@ -280,9 +280,26 @@ LINON_HD float refraction_index(float t) {
     const float c2 = 0.00366f;
     return c1 * air_pressure * (1.0f + air_pressure * (60.1f - 0.972f * t) * 1e-10f) / (1.0f + c2 * t);
 }
+#ifndef LINON_FAST_MATH
+#define LINON_FAST_MATH 0
+#endif
+// eta = n(t_in) / n(t_out).  Fast mode folds the two refraction indices into one quotient: n(t) = A(t) / B(t) with
+// A(t) = c1 p (1 + p 1e-10 (60.1 - 0.972 t)) = a0 - a1 t and B(t) = 1 + c2 t, so eta = A(t_in) B(t_out) / (A(t_out) B(t_in))
+// costs one reciprocal instead of three (same fp32 error class: every factor is 1 + O(1e-3)).
+LINON_HD float refraction_eta(float t_in, float t_out) {
+#if LINON_FAST_MATH
+    const float c1p = 0.0000104f * 101325.0f;
+    const float a0 = c1p * (1.0f + 101325.0f * 1e-10f * 60.1f);
+    const float a1 = c1p * 101325.0f * 1e-10f * 0.972f;
+    const float c2 = 0.00366f;
+    const float num = (a0 - a1 * t_in) * (1.0f + c2 * t_out);
+    const float den = (a0 - a1 * t_out) * (1.0f + c2 * t_in);
+    return num / den;
+#else
+    return refraction_index(t_in) / refraction_index(t_out);
+#endif
+}
 LINON_HD vec3f refraction(float t_in, float t_out, vec3f v_in, vec3f n) {
-    const float eta_in = refraction_index(t_in);
-    const float eta_out = refraction_index(t_out);
     float cosi = w_clamp(-1.0f, 1.0f, w_dot(v_in, n));  // misordered in the reference: min(1, dot)
     vec3f n_ref = n;
     if (cosi < 0.0f) {
@@ -290,7 +307,7 @@ LINON_HD vec3f refraction(float t_in, float t_out, vec3f v_in, vec3f n) {
     } else {
         n_ref = -n;
     }
-    const float eta = eta_in / eta_out;
+    const float eta = refraction_eta(t_in, t_out);  // eta_in / eta_out, src/main_view.wgsl:120-121,129
     const float k = 1.0f - eta * eta * (1.0f - cosi * cosi);
     if (k < 0.0f) {
         return w_reflect(v_in, n_ref);  // total reflection

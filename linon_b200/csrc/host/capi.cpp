@@ -185,6 +185,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
         opts.insert(opts.end(), {"--fmad=true", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
     } else {
         opts.push_back("--use_fast_math");
+        opts.push_back("-DLINON_FAST_MATH=1");
     }
     if (var.max_regs > 0) opts.push_back("--maxrregcount=" + std::to_string(var.max_regs));
     std::vector<const char*> copts;
@@ -782,16 +783,17 @@ int linon_set_option(linon_view* v, int option, int value) {
 
 int linon_get_counters(linon_view* v, linon_counters* out) {
     if (!v || !out) return LINON_ERR_INVALID;
-    unsigned long long c[4];
+    unsigned long long c[5];
     CK(v, cudaSetDevice(v->device));
-    CK(v, cudaMemcpyAsync(c, v->d_counters, 32, cudaMemcpyDeviceToHost, v->stream));
+    CK(v, cudaMemcpyAsync(c, v->d_counters, 40, cudaMemcpyDeviceToHost, v->stream));
     CK(v, cudaStreamSynchronize(v->stream));
     out->rays = v->last_rays;
     out->accepted_steps = c[0];
     out->prehit_steps = c[1];
     out->rejected_steps = c[2];
     out->face_tests = c[3];
-    out->plane_tests = v->opt_cull ? c[1] * v->n_groups : 0;
+    out->culling_checks = c[4];
+    out->plane_tests = v->opt_cull ? c[4] * v->n_groups : 0;
     return LINON_OK;
 }
 

@@ -9,7 +9,10 @@ Per accepted step (as written, adaptive variant): 9+9+7 stage inputs, 18 combine
 3 step_dir, 3+1 advance, 1 restore test = 71, plus 4 field evaluations of F FLOPs each.
 Fixed-step variant (Enhance, or adaptive off): the kernel drops diff / threshold / restore (11 FLOPs): 60 + 4F.
 Rejected attempt: 53 + 4F.  Pre-hit step: +15 (normalize + length of step_dir).
-Ray-triangle test with e1, e2 precomputed: 45.  Plane-distance test: 6 (3 FMA) + 5 once per pre-hit step for the reach.
+Ray-triangle test with e1, e2 precomputed: 45.  Culling: every pre-hit step pays the safe-distance bookkeeping (8: two
+L1 norms, margin, compare operand, subtraction); a step whose bound expired ("culling check") additionally pays
+normalize + length of step_dir (15), the reach (3), the bound reset (2) and 6 per plane group (3 FMA).  Without culling
+every pre-hit step pays 15 + 45 per face.
 """
 from __future__ import annotations
 
@@ -19,10 +22,11 @@ FIELD_FLOPS = {1: 84, 2: 79, 3: 94, 4: 89, 5: 4, 6: 4, 7: 32, 8: 8, 9: 6}
 STEP_ADAPTIVE = 71
 STEP_FIXED = 60
 STEP_REJECTED = 53
-PREHIT_EXTRA = 15
+PREHIT_EXTRA = 15      # normalize(step_dir) + length(step_dir), src/main_view.wgsl:260
 FACE_TEST = 45
 PLANE_TEST = 6
-REACH = 5
+SAFE_STEP = 8          # per pre-hit step with culling on
+CHECK_EXTRA = 5        # reach + bound reset, per culling check
 
 
 def march_flops(counters, fn_id: int, adaptive: bool, n_faces: int = 36, field_flops: int | None = None) -> float:
@@ -31,10 +35,12 @@ def march_flops(counters, fn_id: int, adaptive: bool, n_faces: int = 36, field_f
     step = (STEP_ADAPTIVE if adaptive else STEP_FIXED) + 4 * F
     flops = counters.accepted_steps * step
     flops += counters.rejected_steps * (STEP_REJECTED + 4 * F)
-    flops += counters.prehit_steps * PREHIT_EXTRA
     flops += counters.face_tests * FACE_TEST
-    if counters.plane_tests:
-        flops += counters.plane_tests * PLANE_TEST + counters.prehit_steps * REACH
+    if counters.plane_tests:  # culling on: normalize/length only run on culling checks
+        flops += counters.prehit_steps * SAFE_STEP
+        flops += counters.culling_checks * (PREHIT_EXTRA + CHECK_EXTRA) + counters.plane_tests * PLANE_TEST
+    else:
+        flops += counters.prehit_steps * PREHIT_EXTRA
     return float(flops)
 
 
