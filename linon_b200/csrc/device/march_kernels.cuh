@@ -393,15 +393,16 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     if (t_hit > 0.0f && t_hit < max_dist) {
                         color = shade(s_tri, id, dirn);
                         hit = id;
-                        has_color = true;  // result.color.a = t > 0
+                        has_color = true;           // result.color.a = t > 0
+                        cnt.prehit = cnt.accepted + 1;  // accepted steps that ran the pre-hit path, this one included
                     }
                 }
                 sd.moved(travel);
-                ++cnt.prehit;
             }
             rk4_advance(r, v, diff, step_dir);
             ++cnt.accepted;
         }
+        if (!has_color) cnt.prehit = cnt.accepted;
         const size_t pix = (size_t)texture_row(P, local_row) * P.width + x;
         P.raycast[pix] = pack_color(color);  // black when !has_color, alpha = 1 (src/main_view.wgsl:274-277)
         P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);

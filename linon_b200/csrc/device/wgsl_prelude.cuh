@@ -299,20 +299,33 @@ LINON_HD float refraction_eta(float t_in, float t_out) {
     return refraction_index(t_in) / refraction_index(t_out);
 #endif
 }
+// Total reflection is rare; keeping it out of line keeps its instructions out of the hot loop (the compiler otherwise
+// hoists them ahead of the branch as predicated-off work in each of the four RK4 stages).
+#if LINON_DEVICE_BUILD
+__device__ __noinline__
+#else
+inline
+#endif
+vec3f linon_total_reflection(vec3f v_in, vec3f n, float d) { return v_in - (2.0f * d) * n; }
+
+// refraction, src/main_view.wgsl:119-136.  Restated without materialising n_ref = +-n: negation is exact in IEEE
+// arithmetic, so with s = -1 when cosi >= 0 (n_ref = -n) and +1 otherwise (n_ref = n)
+//     eta * v_in + (eta * |cosi| - sqrt(k)) * n_ref  ==  eta * v_in + (s * (eta * |cosi| - sqrt(k))) * n      bit for bit,
+//     reflect(v_in, n_ref) = v_in - 2 dot(n_ref, v_in) n_ref  ==  v_in - 2 dot(n, v_in) n                     bit for bit
+// (tests/test_translator.py and tests/test_gpu_units.py compare against the oracle's literal transcription).
+// Total reflection (k < 0) is rare, so it is a real branch instead of seven predicated instructions per evaluation.
 LINON_HD vec3f refraction(float t_in, float t_out, vec3f v_in, vec3f n) {
-    float cosi = w_clamp(-1.0f, 1.0f, w_dot(v_in, n));  // misordered in the reference: min(1, dot)
-    vec3f n_ref = n;
-    if (cosi < 0.0f) {
-        cosi = -cosi;
-    } else {
-        n_ref = -n;
-    }
-    const float eta = refraction_eta(t_in, t_out);  // eta_in / eta_out, src/main_view.wgsl:120-121,129
+    const float d = w_dot(v_in, n);
+    const float cosi_raw = w_clamp(-1.0f, 1.0f, d);  // misordered in the reference: min(max(-1, 1), d) = min(1, d)
+    const float cosi = w_abs(cosi_raw);              // `if (cosi < 0) cosi = -cosi`
+    const float eta = refraction_eta(t_in, t_out);   // eta_in / eta_out, src/main_view.wgsl:120-121,129
     const float k = 1.0f - eta * eta * (1.0f - cosi * cosi);
-    if (k < 0.0f) {
-        return w_reflect(v_in, n_ref);  // total reflection
+    if (__builtin_expect(k < 0.0f, 0)) {
+        return linon_total_reflection(v_in, n, d);  // reflect(v_in, n_ref); dot(n_ref, v_in) n_ref = dot(n, v_in) n
     }
-    return eta * v_in + (eta * cosi - w_sqrt(k)) * n_ref;
+    const float c = eta * cosi - w_sqrt(k);
+    const float cs = (cosi_raw < 0.0f) ? c : -c;     // n_ref = n when cosi < 0, else -n
+    return eta * v_in + cs * n;
 }
 LINON_HD float point_plane_distance(vec3f p, vec3f n, vec3f p0) {
     const float d = w_dot(p0, n);
