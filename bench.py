@@ -219,12 +219,15 @@ def run_ours(args):
         if rank != 0:
             march_flags |= capi.RENDER_NO_SAMPLE_RAYS
 
+    last = {}
+
     def frame():
         """One step of the hot path on this rank; returns launches of our kernels."""
         mv.render_flags(march_flags)
         n = 1 + (2 if not (march_flags & capi.RENDER_NO_SAMPLE_RAYS) else 0)  # march (+ click positions + sample rays)
         if world > 1:
             mv.sync()
+            last["timings"], last["counters"] = mv.timings(), mv.counters()  # of the march render (reset per render)
             with torch.cuda.stream(stream):
                 sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, ROWS_PER_BLOCK)
             if rank == 0:
@@ -266,9 +269,12 @@ def run_ours(args):
         barrier()
         dev_ms.append(e0.elapsed_time(e1))
         t = mv.timings()
-        march_ms.append(t.march_ms)
         overlay_ms.append(t.overlay_ms)
-        counters = mv.counters()
+        if world > 1:
+            t, counters = last["timings"], last["counters"]
+        else:
+            counters = mv.counters()
+        march_ms.append(t.march_ms)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     total_ms = float(sum(dev_ms))
