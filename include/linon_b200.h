@@ -82,14 +82,17 @@ enum {
                                     2 fast (--use_fast_math: MUFU rcp/rsqrt/ex2/sin/cos, ftz).  Default 2: measured 2x faster
                                     than fused and inside the north-star tolerances (tests/test_gpu_parity.py). */
     LINON_OPT_KERNEL = 1,        /* 0 one thread per pixel in 8x4 tiles, 1 persistent warps: pre-hit / post-hit phase kernels
-                                    with lane refill.  Default 0: measured faster on B200 once culling removed the pre-hit /
-                                    post-hit cost gap (profiles/) */
+                                    with lane refill, 2 (default) two rays per thread on the packed fp32 instructions of
+                                    sm_100 (FFMA2/FMUL2/FADD2) in 16x4 tiles.  A user body that does not instantiate for two
+                                    rays at once (data-dependent control flow) falls back to 0 automatically
+                                    (linon_timings.march_kernel tells which kernel ran).  profiles/, DESIGN.md */
     LINON_OPT_BLOCK = 2,         /* threads per CTA of the march kernel (multiple of 32). Default 256 */
     LINON_OPT_CTAS_PER_SM = 3,   /* persistent grid = this x #SM; 0 = occupancy query. Default 0 */
     LINON_OPT_REFILL_MIN = 4,    /* idle lanes a warp tolerates before refilling. Default 1 */
     LINON_OPT_FACE_UNROLL = 5,   /* unroll of the face loop. Default 4 */
     LINON_OPT_MAX_REGS = 6,      /* NVRTC --maxrregcount (0 = none). Default 0 */
     LINON_OPT_PROFILE = 7,       /* 1: persistent kernel accumulates clock64 section timers (linon_debug_profile) */
+    LINON_OPT_PAIR_MIN_BLOCKS = 9, /* resident CTAs / SM requested for the pair kernel (register cap); 0 = default (512/block) */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.
@@ -116,6 +119,7 @@ typedef struct linon_timings { /* CUDA-event times of the last render, milliseco
     int32_t march_grid;         /* CTAs launched */
     int32_t march_block;        /* threads per CTA */
     float march_phase_a_ms;     /* persistent kernel: time of the pre-hit phase (march_ms covers both phases) */
+    int32_t march_kernel;       /* the kernel that ran: 0 tiles, 1 persistent, 2 pairs */
 } linon_timings;
 
 /* MainView::new (src/main_view.rs:82-458): allocates textures/buffers for width x height on CUDA device

@@ -15,9 +15,17 @@
 //   LINON_REFILL_MIN     idle lanes a warp tolerates before it refills (persistent kernel)
 //   LINON_CULL / LINON_N_GROUPS  plane culling of the face loop (see intersect_mesh) and the number of plane groups
 //   LINON_PROFILE        1 adds clock64 section timers to the persistent kernels (counters[5..14])
+//   LINON_PAIRS          1 also builds linon_march_pairs: two rays per thread on the packed fp32 instructions of
+//                        sm_100 (FFMA2 / FMUL2 / FADD2), LinonField<f32x2>.  The host retries with 0 when a user
+//                        body does not instantiate for f32x2 (data-dependent control flow).
+//   LINON_PAIR_MIN_BLOCKS  resident CTAs / SM requested for linon_march_pairs (register cap)
 //
-// Two march kernels share every per-ray device function, so their per-pixel results are bit-identical:
+// The march kernels share every per-ray device function, so their per-pixel results are bit-identical in strict mode:
 //   linon_march_tiles       one thread per pixel, 8x4 pixel tiles per warp (the straightforward mapping)
+//   linon_march_pairs       one thread per PAIR of horizontally adjacent pixels, 16x4 pixel tiles per warp.  The RK4
+//                           arithmetic of both rays is issued as packed f32x2 instructions (half the issue slots for
+//                           the same FMA-pipe work: the tile kernel is issue-bound at 89 % of the slots); MUFU,
+//                           min/max, compares and the rare mesh check stay per ray.
 //   linon_march_phase_a/_b  persistent CTAs (grid = k * #SM).  Every warp keeps 32 rays in flight; a lane whose
 //                           ray leaves its phase is refilled through a warp-aggregated atomicAdd.  Phase A = rays
 //                           that have not hit yet (RK4 + all-face intersection every step); on a hit the lane
@@ -64,6 +72,12 @@
 #ifndef LINON_PROFILE
 #define LINON_PROFILE 0  // 1: the persistent kernel also accumulates per-section clock64 cycles (developer aid)
 #endif
+#ifndef LINON_PAIRS
+#define LINON_PAIRS 0
+#endif
+#ifndef LINON_PAIR_MIN_BLOCKS
+#define LINON_PAIR_MIN_BLOCKS (512 / LINON_BLOCK)  // 16 resident warps / SM = 32 rays per scheduler slot pair: <= 128 registers
+#endif
 
 #define LINON_EPS 0.0000001f  // const eps, src/main_view.wgsl:74
 
@@ -92,12 +106,21 @@ struct MarchParams {
     float4* q_state;              // queue: 3 x float4 per entry, SoA planes of q_capacity
     unsigned int q_capacity;
     unsigned int n_ray_slots;     // tiles * 32 (index space of fresh rays incl. out-of-frame padding lanes)
+    unsigned int n_pair_slots;    // 16x4 tiles * 32 (linon_march_pairs: one slot = two horizontally adjacent pixels)
 };
 
-struct Ray {
-    vec3f p, dir, sdir, last_v;
-    float t, h, last_diff;
+template <class S> struct RayT {
+    vec3t<S> p, dir, sdir, last_v;
+    S t, h, last_diff;
 };
+typedef RayT<float> Ray;
+
+// the spliced body, instantiated per scalar type (LinonField is emitted by the host around the translated text)
+template <class S>
+__device__ __forceinline__ vec3t<S> field_function(const vec3t<S> p_prev, const vec3t<S> p, const vec3t<S> v0, const vec3t<S> v,
+                                                   const S t, const WgslSettings& settings, const WgslCamera& camera) {
+    return LinonField<S>::eval(p_prev, p, v0, v, t, settings, camera);
+}
 
 __device__ __forceinline__ vec3f ld3(const float* a) { return vec3f(a[0], a[1], a[2]); }
 
@@ -109,7 +132,8 @@ __device__ __forceinline__ int texture_row(const MarchParams& P, int local_row) 
 }
 
 // src/main_view.wgsl:347-366: pinhole ray through pixel (gid.x, gid.y), gid.y counted from the bottom row.
-__device__ __forceinline__ vec3f camera_ray_dir(const MarchParams& P, float px, float py_from_bottom, bool normalised_pos) {
+template <class S>
+__device__ __forceinline__ vec3t<S> camera_ray_dir(const MarchParams& P, S px, S py_from_bottom, bool normalised_pos) {
     const float width = (float)P.width;
     const float height = (float)P.height;
     const float aspect_ratio = width / height;
@@ -121,7 +145,7 @@ __device__ __forceinline__ vec3f camera_ray_dir(const MarchParams& P, float px, 
     const vec3f w = -view_direction;
     const vec3f horizontal = w_cross(up, w);
     const vec3f vertical = w_cross(w, horizontal);
-    float u, v;
+    S u, v;
     if (normalised_pos) {  // sample rays, src/main_view.wgsl:475-476
         u = px * viewport_width - 0.5f * viewport_width;
         v = py_from_bottom * viewport_height - 0.5f * viewport_height;
@@ -129,7 +153,7 @@ __device__ __forceinline__ vec3f camera_ray_dir(const MarchParams& P, float px, 
         u = px / (width - 1.0f) * viewport_width - 0.5f * viewport_width;
         v = py_from_bottom / (height - 1.0f) * viewport_height - 0.5f * viewport_height;
     }
-    const vec3f s = u * w_normalize(horizontal) + v * w_normalize(vertical) + focal_length * view_direction;
+    const vec3t<S> s = u * w_normalize(horizontal) + v * w_normalize(vertical) + focal_length * view_direction;
     return w_normalize(s);
 }
 
@@ -142,11 +166,13 @@ __device__ __forceinline__ WgslCamera make_camera(const MarchParams& P) {
 }
 
 // One Runge-Kutta evaluation, src/main_view.wgsl:246-250 (p_prev = cur_point in all four stages).
-__device__ __forceinline__ vec3f rk4_velocity(const Ray& r, float h, const WgslSettings& st, const WgslCamera& cam) {
-    const vec3f k1 = field_function(r.p, r.p, r.sdir, r.dir, r.t, st, cam);
-    const vec3f k2 = field_function(r.p, r.p + 0.5f * h * k1, r.sdir, k1, r.t + 0.5f * h, st, cam);
-    const vec3f k3 = field_function(r.p, r.p + 0.5f * h * k2, r.sdir, k2, r.t + 0.5f * h, st, cam);
-    const vec3f k4 = field_function(r.p, r.p + h * k3, r.sdir, k3, r.t + h, st, cam);
+// h is a float (compile-time constant or uniform) or per-ray (adaptive sampling in the pair kernel).
+template <class S, class H>
+__device__ __forceinline__ vec3t<S> rk4_velocity(const RayT<S>& r, H h, const WgslSettings& st, const WgslCamera& cam) {
+    const vec3t<S> k1 = field_function<S>(r.p, r.p, r.sdir, r.dir, r.t, st, cam);
+    const vec3t<S> k2 = field_function<S>(r.p, r.p + 0.5f * h * k1, r.sdir, k1, r.t + 0.5f * h, st, cam);
+    const vec3t<S> k3 = field_function<S>(r.p, r.p + 0.5f * h * k2, r.sdir, k2, r.t + 0.5f * h, st, cam);
+    const vec3t<S> k4 = field_function<S>(r.p, r.p + h * k3, r.sdir, k3, r.t + h, st, cam);
     return (k1 + 2.0f * k2 + 2.0f * k3 + k4) / 6.0f;
 }
 
@@ -282,7 +308,7 @@ __device__ __forceinline__ bool slot_to_pixel(const MarchParams& P, unsigned int
 __device__ __forceinline__ void init_ray(const MarchParams& P, int x, int local_row, Ray& r) {
     const int gid_y = P.height - 1 - texture_row(P, local_row);  // src/main_view.wgsl:342
     r.p = ld3(P.cam_origin);
-    r.sdir = camera_ray_dir(P, (float)x, (float)gid_y, false);
+    r.sdir = camera_ray_dir<float>(P, (float)x, (float)gid_y, false);
     r.dir = r.sdir;
     r.t = 0.0f;
     r.last_v = vec3f(0.0f, 0.0f, 0.0f);
@@ -410,6 +436,152 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
     }
     flush_counters(P, cnt);
 }
+
+#if LINON_PAIRS
+// ------------------------------------------------------------------------------------------------------------
+// Kernel 1b: one thread per pair of horizontally adjacent pixels (packed f32x2 arithmetic).
+//
+// 32 consecutive pair slots form a 16x4 pixel tile: lane l owns pixels (16 tx + 2 (l & 7) + {0, 1}, 4 ty + (l >> 3)),
+// so a warp's stores are as contiguous as the tile kernel's.  The RK4 stages, the direction blend and the position
+// update of both rays are packed instructions; the safe-distance bookkeeping and the (rare) mesh check run per ray on
+// the unpacked component, through the same device functions as the tile kernel.  A ray's result does not depend on its
+// partner: in strict mode (component-wise f32x2 arithmetic) the frame is bit-identical with linon_march_tiles.
+// An odd frame width leaves the last column's partner outside the frame: it is integrated (harmless) and not stored.
+// ------------------------------------------------------------------------------------------------------------
+typedef RayT<f32x2> Ray2;
+__device__ __forceinline__ vec3f lane_lo(const vec3t<f32x2>& a) { return vec3f(a.x.lo, a.y.lo, a.z.lo); }
+__device__ __forceinline__ vec3f lane_hi(const vec3t<f32x2>& a) { return vec3f(a.x.hi, a.y.hi, a.z.hi); }
+
+struct PixelState {  // what one ray of the pair carries besides its packed RK4 state
+    SafeDistance sd;
+    vec3f color;
+    int hit;
+    bool has_color;
+    unsigned int prehit;
+};
+
+// The pre-hit part of one accepted step for one ray, src/main_view.wgsl:259-262.  Out of line: it runs on ~3 % of
+// the pre-hit steps (SafeDistance), and inlining it twice per pair would only enlarge the hot loop.
+__device__ __noinline__ void pair_mesh_check(const float4* __restrict__ s_tri, const int* __restrict__ s_range, vec3f p,
+                                             vec3f step_dir, float p_l1, unsigned int step_index, PixelState& px,
+                                             StepCounters& cnt) {
+    const float max_dist = w_length(step_dir);
+    const vec3f dirn = w_normalize(step_dir);
+    float t_hit, nearest;
+    int id;
+    intersect_mesh(s_tri, s_range, p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+    ++cnt.checks;
+    px.sd.checked(nearest, p_l1);
+    if (t_hit > 0.0f && t_hit < max_dist) {
+        px.color = shade(s_tri, id, dirn);
+        px.hit = id;
+        px.has_color = true;
+        px.prehit = step_index + 1;  // accepted steps that ran the pre-hit path, this one included
+    }
+}
+
+__device__ __forceinline__ void pair_prehit(const float4* __restrict__ s_tri, const int* __restrict__ s_range, vec3f p,
+                                            vec3f step_dir, unsigned int step_index, PixelState& px, StepCounters& cnt) {
+    float travel, p_l1;
+    if (px.sd.must_check(p, step_dir, travel, p_l1)) pair_mesh_check(s_tri, s_range, p, step_dir, p_l1, step_index, px, cnt);
+    px.sd.moved(travel);
+}
+
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS) linon_march_pairs(const MarchParams P) {
+    __shared__ float4 s_tri[LINON_MESH_F4];
+    __shared__ int s_range[LINON_N_GROUPS];
+    stage_mesh(s_tri, s_range, P);
+
+    const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
+    const unsigned int tiles_x = (unsigned int)(P.width + 15) >> 4;
+    const unsigned int tile = slot >> 5, lane = slot & 31u;
+    const unsigned int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int x0 = (int)(tx * 16u + 2u * (lane & 7u));
+    const int local_row = (int)(ty * 4u + (lane >> 3));
+    const bool valid0 = slot < P.n_pair_slots && x0 < P.width && local_row < P.local_rows;
+    const bool valid1 = valid0 && x0 + 1 < P.width;
+    StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
+    if (valid0) {
+        const WgslCamera cam = make_camera(P);
+        const WgslSettings st = P.settings;
+        const int tex_row = texture_row(P, local_row);
+        const float gid_y = (float)(P.height - 1 - tex_row);  // src/main_view.wgsl:342
+        Ray2 r;
+        r.p = vec3t<f32x2>(ld3(P.cam_origin));
+        r.sdir = camera_ray_dir<f32x2>(P, f32x2((float)x0, (float)(x0 + 1)), f32x2(gid_y), false);
+        r.dir = r.sdir;
+        r.t = f32x2(0.0f);
+        r.last_v = vec3t<f32x2>(0.0f, 0.0f, 0.0f);
+        r.last_diff = f32x2(-1.0f);
+        r.h = f32x2(LINON_H_INITIAL);
+        PixelState px0, px1;
+        px0.sd.reset(); px1.sd.reset();
+        px0.color = px1.color = vec3f(0.0f, 0.0f, 0.0f);
+        px0.hit = px1.hit = -1;
+        px0.has_color = false;
+        px1.has_color = !valid1;  // the out-of-frame partner never searches the mesh
+        px0.prehit = px1.prehit = 0u;
+        unsigned int acc0 = 0u, acc1 = 0u;  // accepted steps per ray
+#if LINON_ADAPTIVE
+        // src/main_view.wgsl:244-271 with a per-ray `continue`: a rejected or finished ray keeps its state (selects)
+        // while its partner goes on
+        bool act0 = true, act1 = valid1;
+        while (act0 || act1) {
+            const f32x2 h = r.h;
+            const vec3t<f32x2> v = rk4_velocity(r, h, st, cam);
+            const f32x2 diff = w_length(v - r.last_v);
+            const bool2 rej = (r.last_diff >= 0.0f) && (diff > 10.0f * r.last_diff) && (h > 0.002f);
+            const bool2 rejected(act0 && rej.lo, act1 && rej.hi);
+            const bool2 accepted(act0 && !rej.lo, act1 && !rej.hi);
+            cnt.rejected += (rejected.lo ? 1u : 0u) + (rejected.hi ? 1u : 0u);
+            r.h = s_sel(rejected, f32x2(0.001f), r.h);
+            const vec3t<f32x2> new_dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+            const vec3t<f32x2> step_dir = new_dir * h;
+            r.dir = w_select(r.dir, new_dir, accepted);
+            if (accepted.lo && !px0.has_color) pair_prehit(s_tri, s_range, lane_lo(r.p), lane_lo(step_dir), acc0, px0, cnt);
+            if (accepted.hi && !px1.has_color) pair_prehit(s_tri, s_range, lane_hi(r.p), lane_hi(step_dir), acc1, px1, cnt);
+            r.p = w_select(r.p, r.p + step_dir, accepted);
+            r.t = s_sel(accepted, r.t + h, r.t);
+            r.last_v = w_select(r.last_v, v, accepted);
+            const bool2 restore = accepted && (2.0f * diff < r.last_diff) && (r.h < LINON_H_INITIAL);
+            r.h = s_sel(restore, f32x2(LINON_H_INITIAL), r.h);
+            r.last_diff = s_sel(accepted, diff, r.last_diff);
+            acc0 += accepted.lo ? 1u : 0u;
+            acc1 += accepted.hi ? 1u : 0u;
+            act0 = act0 && (r.t.lo <= 5.0f);
+            act1 = act1 && (r.t.hi <= 5.0f);
+        }
+#else
+        // fixed step: both rays are in lockstep (same t), every attempt is accepted
+        for (; r.t.lo <= 5.0f;) {
+            const vec3t<f32x2> v = rk4_velocity(r, LINON_H_INITIAL, st, cam);
+            r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+            const vec3t<f32x2> step_dir = r.dir * LINON_H_INITIAL;
+            if (!px0.has_color) pair_prehit(s_tri, s_range, lane_lo(r.p), lane_lo(step_dir), acc0, px0, cnt);
+            if (!px1.has_color) pair_prehit(s_tri, s_range, lane_hi(r.p), lane_hi(step_dir), acc0, px1, cnt);
+            r.p = r.p + step_dir;
+            r.t = r.t + LINON_H_INITIAL;
+            ++acc0;
+        }
+        acc1 = valid1 ? acc0 : 0u;
+#endif
+        if (!px0.has_color) px0.prehit = acc0;
+        if (valid1 && px1.hit < 0) px1.prehit = acc1;
+        cnt.accepted = acc0 + acc1;
+        cnt.prehit = px0.prehit + (valid1 ? px1.prehit : 0u);
+        const size_t pix = (size_t)tex_row * P.width + x0;
+        P.raycast[pix] = pack_color(px0.color);  // black when !has_color, alpha = 1 (src/main_view.wgsl:274-277)
+        P.endpoint[pix] = make_float4(r.p.x.lo, r.p.y.lo, r.p.z.lo, 1.0f);
+        P.hit_id[pix] = px0.hit;
+        if (valid1) {
+            P.raycast[pix + 1] = pack_color(px1.color);
+            P.endpoint[pix + 1] = make_float4(r.p.x.hi, r.p.y.hi, r.p.z.hi, 1.0f);
+            P.hit_id[pix + 1] = px1.hit;
+        }
+    }
+    flush_counters(P, cnt);
+}
+#endif  // LINON_PAIRS
 
 // ------------------------------------------------------------------------------------------------------------
 // Kernels 2a/2b: persistent warps with lane refill, split by phase.
@@ -591,7 +763,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     r.dir = vec3f(b.x, b.y, b.z); r.h = b.w;
                     r.last_v = vec3f(c.x, c.y, c.z); r.last_diff = c.w;
                     const int row = pix / P.width;  // texture row
-                    r.sdir = camera_ray_dir(P, (float)(pix - row * P.width), (float)(P.height - 1 - row), false);
+                    r.sdir = camera_ray_dir<float>(P, (float)(pix - row * P.width), (float)(P.height - 1 - row), false);
                     alive = true;
                 }
             }
@@ -650,7 +822,7 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
     const WgslSettings st = P.settings;
     Ray r;
     r.p = ld3(P.cam_origin);
-    r.sdir = camera_ray_dir(P, S.pos16[2 * k], S.pos16[2 * k + 1], true);
+    r.sdir = camera_ray_dir<float>(P, S.pos16[2 * k], S.pos16[2 * k + 1], true);
     r.dir = r.sdir;
     r.t = 0.0f;
     r.last_v = vec3f(0.0f, 0.0f, 0.0f);
@@ -680,7 +852,7 @@ extern "C" __global__ void linon_eval_field(int n, const float* p_prev, const fl
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     WgslCamera cam;
-    const vec3f r = field_function(ld3(p_prev + 3 * i), ld3(p + 3 * i), ld3(v0 + 3 * i), ld3(v + 3 * i), t[i], st, cam);
+    const vec3f r = field_function<float>(ld3(p_prev + 3 * i), ld3(p + 3 * i), ld3(v0 + 3 * i), ld3(v + 3 * i), t[i], st, cam);
     out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
 }
 

@@ -108,6 +108,7 @@ struct MarchParamsH {
     void* q_state;
     unsigned int q_capacity;
     unsigned int n_ray_slots;
+    unsigned int n_pair_slots;
 };
 struct SampleParamsH {
     MarchParamsH march;
@@ -120,20 +121,30 @@ static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view
 struct Variant {
     float h_initial;
     int adaptive, n_faces, n_groups, cull, math, block, unroll, refill_min, max_regs, profile;
+    int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
+    int pair_min_blocks;  // resident CTAs / SM requested for it (0 = kernel default)
 };
 
 struct Module {
     CUmodule mod = nullptr;
-    CUfunction tiles = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr, eval_field = nullptr,
-               eval_helper = nullptr, eval_hit = nullptr;
-    int regs_tiles = 0, regs_phase_a = 0, regs_phase_b = 0;
+    CUfunction tiles = nullptr, pairs = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr,
+               eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr;
+    int regs_tiles = 0, regs_pairs = 0, regs_phase_a = 0, regs_phase_b = 0;
 };
 
+// The translated body becomes LinonField<S>::eval.  The member typedefs re-declare the type names the translator
+// emits (vec3f, wg_f32, ...) for the scalar type of the instantiation: S = float is the reference's one ray per
+// invocation, S = f32x2 carries two rays through the same text (linon_march_pairs).
 const char kFieldHead[] =
-    "__device__ __forceinline__ vec3f field_function(const vec3f p_prev, const vec3f p, const vec3f v0, const vec3f v,\n"
-    "                                                const float t, const WgslSettings& settings, const WgslCamera& camera) {\n"
+    "template <class S> struct LinonField {\n"
+    "    typedef S wg_f32;\n"
+    "    typedef vec2t<S> vec2f; typedef vec3t<S> vec3f; typedef vec4t<S> vec4f;\n"
+    "    typedef mat2x2t<S> mat2x2f; typedef mat3x3t<S> mat3x3f;\n"
+    "    static __device__ __forceinline__ vec3t<S> eval(const vec3t<S> p_prev, const vec3t<S> p, const vec3t<S> v0,\n"
+    "                                                    const vec3t<S> v, const S t, const WgslSettings& settings,\n"
+    "                                                    const WgslCamera& camera) {\n"
     "#line 1 \"field_function.wgsl\"\n";
-const char kFieldTail[] = "\n}\n#line 1 \"march_kernels.cuh\"\n";
+const char kFieldTail[] = "\n    }\n};\n#line 1 \"march_kernels.cuh\"\n";
 
 std::string build_source(const std::string& cuda_body) {
     std::string s;
@@ -178,7 +189,11 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
                                      "-DLINON_FACE_UNROLL=" + std::to_string(var.unroll),
                                      "-DLINON_BLOCK=" + std::to_string(var.block),
                                      "-DLINON_REFILL_MIN=" + std::to_string(var.refill_min),
-                                     "-DLINON_PROFILE=" + std::to_string(var.profile)};
+                                     "-DLINON_PROFILE=" + std::to_string(var.profile),
+                                     "-DLINON_PAIRS=" + std::to_string(var.pairs),
+                                     // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
+                                     "-DLINON_PACKED_OPS=" + std::to_string(var.math == 0 ? 0 : 1)};
+    if (var.pair_min_blocks > 0) opts.push_back("-DLINON_PAIR_MIN_BLOCKS=" + std::to_string(var.pair_min_blocks));
     if (var.math == 0) {
         opts.insert(opts.end(), {"--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
     } else if (var.math == 1) {
@@ -221,8 +236,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
 }
 
 std::string variant_key(const std::string& body, const Variant& v) {
-    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
-               v.block, v.unroll, v.refill_min, v.max_regs, v.profile) + body;
+    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks) + body;
 }
 
 }  // namespace
@@ -261,8 +276,9 @@ struct linon_view {
 
     std::string body;  // current WGSL body
     std::map<std::string, Module> modules;
+    std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
-    int opt_math = 2, opt_kernel = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
+    int opt_math = 2, opt_kernel = 2, opt_pair_min_blocks = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
         opt_max_regs = 0, opt_profile = 0, opt_cull = 1;
 
     linon_timings timings{};
@@ -345,10 +361,12 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
     struct { const char* name; CUfunction* f; } fns[] = {
         {"linon_march_tiles", &m.tiles},       {"linon_march_phase_a", &m.phase_a},
+        {"linon_march_pairs", var.pairs ? &m.pairs : nullptr},
         {"linon_march_phase_b", &m.phase_b},   {"linon_sample_rays", &m.sample},
         {"linon_eval_field", &m.eval_field},   {"linon_eval_helper", &m.eval_helper},
         {"linon_eval_hit_triangle", &m.eval_hit}};
     for (auto& f : fns) {
+        if (!f.f) continue;
         r = g_drv.ModuleGetFunction(f.f, m.mod, f.name);
         if (r != CUDA_SUCCESS) {
             g_drv.ModuleUnload(m.mod);
@@ -356,6 +374,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
         }
     }
     g_drv.FuncGetAttribute(&m.regs_tiles, CU_FUNC_ATTRIBUTE_NUM_REGS, m.tiles);
+    if (m.pairs) g_drv.FuncGetAttribute(&m.regs_pairs, CU_FUNC_ATTRIBUTE_NUM_REGS, m.pairs);
     g_drv.FuncGetAttribute(&m.regs_phase_a, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_a);
     g_drv.FuncGetAttribute(&m.regs_phase_b, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_b);
     const auto t1 = std::chrono::steady_clock::now();
@@ -379,7 +398,25 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.refill_min = v->opt_refill_min;
     var.max_regs = v->opt_max_regs;
     var.profile = v->opt_profile;
+    var.pairs = (v->opt_kernel == 2 && !v->pair_unfit.count(v->body)) ? 1 : 0;
+    var.pair_min_blocks = var.pairs ? v->opt_pair_min_blocks : 0;
     return var;
+}
+
+// get_module for the current body; when the two-rays-per-thread instantiation of a user body does not compile
+// (data-dependent control flow, integer casts of per-ray values ...) the body is remembered as unfit and the module is
+// built without the pair kernel - the caller then launches the tile kernel.
+int get_module_for_body(linon_view* v, const std::string& body, Variant& var, Module** out, float* jit_ms) {
+    int rc = get_module(v, body, var, out, jit_ms);
+    if (rc == LINON_ERR_COMPILE && var.pairs) {
+        const std::string pair_error = v->error;
+        var.pairs = 0;
+        var.pair_min_blocks = 0;
+        rc = get_module(v, body, var, out, jit_ms);
+        if (rc == LINON_OK) v->pair_unfit[body] = true;  // else: a genuine error of the body, reported by the scalar build
+        (void)pair_error;
+    }
+    return rc;
 }
 
 void fill_march_params(const linon_view* v, MarchParamsH& P) {
@@ -399,6 +436,7 @@ void fill_march_params(const linon_view* v, MarchParamsH& P) {
     P.q_capacity = (unsigned int)v->q_capacity;
     const unsigned int tiles_x = (v->W + 7) / 8, tiles_y = (v->local_rows + 3) / 4;
     P.n_ray_slots = tiles_x * tiles_y * 32u;
+    P.n_pair_slots = ((v->W + 15) / 16) * tiles_y * 32u;
 }
 
 int launch(linon_view* v, CUfunction f, unsigned grid, unsigned block, cudaStream_t s, void* params) {
@@ -600,16 +638,18 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
     if (err && err_len) err[0] = '\0';
     CK(v, cudaSetDevice(v->device));
     // validate by building the default variant now; the previous body stays live on failure (src/main_view.rs:677-679)
+    const std::string previous = v->body;
+    v->body = wgsl_body;  // make_variant consults pair_unfit for the body being installed
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
     if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
     Module* m = nullptr;
     float jit = 0.0f;
-    const int rc = get_module(v, wgsl_body, var, &m, &jit);
+    const int rc = get_module_for_body(v, v->body, var, &m, &jit);
     if (rc != LINON_OK) {
+        v->body = previous;
         if (err && err_len) snprintf(err, err_len, "%s", v->error.c_str());
         return rc;
     }
-    v->body = wgsl_body;
     return LINON_OK;
 }
 
@@ -628,8 +668,8 @@ int linon_render(linon_view* v, uint32_t flags) {
     MarchParamsH P;
     fill_march_params(v, P);
     if (do_march || do_sample) {
-        const Variant var = make_variant(v, flags);
-        const int rc = get_module(v, v->body, var, &mod, &v->timings.jit_ms);
+        Variant var = make_variant(v, flags);
+        const int rc = get_module_for_body(v, v->body, var, &mod, &v->timings.jit_ms);
         if (rc != LINON_OK) return rc;
     }
 
@@ -662,7 +702,9 @@ int linon_render(linon_view* v, uint32_t flags) {
     if (do_march && v->local_rows > 0) {
         CK(v, cudaMemsetAsync(v->d_counters, 0, 128, v->stream));
         const unsigned block = (unsigned)v->opt_block;
-        const unsigned needed = (P.n_ray_slots + block - 1) / block;
+        const bool use_pairs = v->opt_kernel == 2 && mod->pairs != nullptr;
+        const unsigned needed = ((use_pairs ? P.n_pair_slots : P.n_ray_slots) + block - 1) / block;
+        v->timings.march_kernel = use_pairs ? 2 : (v->opt_kernel == 1 ? 1 : 0);
         v->timings.march_block = (int)block;
         CK(v, cudaEventRecord(v->ev[0], v->stream));
         if (v->opt_kernel == 1) {
@@ -688,6 +730,11 @@ int linon_render(linon_view* v, uint32_t flags) {
             v->timings.march_regs = mod->regs_phase_a;
             v->timings.march_grid = (int)grids[0];
             v->ran_phases = true;
+        } else if (use_pairs) {
+            const int rc = launch(v, mod->pairs, needed, block, v->stream, &P);
+            if (rc != LINON_OK) return rc;
+            v->timings.march_regs = mod->regs_pairs;
+            v->timings.march_grid = (int)needed;
         } else {
             const int rc = launch(v, mod->tiles, needed, block, v->stream, &P);
             if (rc != LINON_OK) return rc;
@@ -769,7 +816,8 @@ int linon_set_option(linon_view* v, int option, int value) {
     if (!v) return LINON_ERR_INVALID;
     switch (option) {
         case LINON_OPT_MATH: if (value < 0 || value > 2) break; v->opt_math = value; return LINON_OK;
-        case LINON_OPT_KERNEL: if (value < 0 || value > 1) break; v->opt_kernel = value; return LINON_OK;
+        case LINON_OPT_KERNEL: if (value < 0 || value > 2) break; v->opt_kernel = value; return LINON_OK;
+        case LINON_OPT_PAIR_MIN_BLOCKS: if (value < 0 || value > 32) break; v->opt_pair_min_blocks = value; return LINON_OK;
         case LINON_OPT_BLOCK: if (value < 32 || value > 1024 || value % 32) break; v->opt_block = value; return LINON_OK;
         case LINON_OPT_CTAS_PER_SM: if (value < 0 || value > 32) break; v->opt_ctas_per_sm = value; return LINON_OK;
         case LINON_OPT_REFILL_MIN: if (value < 1 || value > 32) break; v->opt_refill_min = value; return LINON_OK;
@@ -837,10 +885,19 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     tmp.n_faces = n_faces;
     tmp.n_groups = n_faces == 36 ? 15 : n_faces;  // the Cornell box has 15 plane groups
     tmp.opt_math = math_mode;
-    const Variant var = make_variant(&tmp, flags);
+    tmp.body = wgsl_body;
+    if (const char* k = getenv("LINON_CHECK_KERNEL")) tmp.opt_kernel = atoi(k);  // developer aid: 0 = without the pair kernel
+    Variant var = make_variant(&tmp, flags);
     std::vector<char> cubin;
     std::string log;
-    if (!compile_cubin(wgsl_body, var, cubin, log)) {
+    bool ok = compile_cubin(wgsl_body, var, cubin, log);
+    if (!ok && var.pairs) {  // same fallback as linon_render: the body may not instantiate for two rays per thread
+        var.pairs = 0;
+        std::string log2;
+        ok = compile_cubin(wgsl_body, var, cubin, log2);
+        log = ok ? "pair kernel not built for this body:\n" + log : log2;
+    }
+    if (!ok) {
         if (err && err_len) snprintf(err, err_len, "%s", log.c_str());
         return LINON_ERR_COMPILE;
     }
@@ -869,7 +926,7 @@ struct DevBuf {
 int debug_module(linon_view* v, Module** m) {
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
     if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
-    return get_module(v, v->body, var, m, nullptr);
+    return get_module_for_body(v, v->body, var, m, nullptr);
 }
 }  // namespace
 

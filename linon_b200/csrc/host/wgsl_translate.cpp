@@ -13,7 +13,8 @@
 //   * a `let`/`const` initialiser made only of literals and + - * / ( ) is emitted as (float)(double expr):
 //     naga folds such expressions in abstract float (f64) and then concretises (e.g. `8.0 / 3.0`)
 //   * let/const/var declarations -> const auto / auto / typed C++ declarations; `var x: T;` zero-initialises
-//   * vecN<f32> / vecNf / vecN( -> vecNf, matCxR<f32> -> matCxRf, f32/i32/u32 -> float/int/unsigned
+//   * vecN<f32> / vecNf / vecN( -> vecNf, matCxR<f32> -> matCxRf, f32 -> wg_f32, i32/u32 -> int/unsigned
+//     (vecNf, matCxRf and wg_f32 are re-declared per instantiation by LinonField<S>: float or two rays at once)
 //   * WGSL builtins called as functions -> w_<name>
 //   * multi-component swizzles .xyz/.rgb -> .xyz(); .r/.g/.b/.a -> .x/.y/.z/.w
 //   * `if cond {` / `while cond {` get their parentheses; a trailing comma before `)` is removed
@@ -213,7 +214,7 @@ struct Rewriter {
         const std::string& n = t[i].text;
         end = i;
         auto scalar = [](const std::string& s, std::string& o) {
-            if (s == "f32") o = "float";
+            if (s == "f32") o = "wg_f32";  // float, or the two-ray scalar of the instantiation (LinonField<S>)
             else if (s == "i32") o = "int";
             else if (s == "u32") o = "unsigned";
             else if (s == "bool") o = "bool";

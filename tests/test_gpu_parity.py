@@ -33,7 +33,10 @@ def view(product_lib, scene):
     mv.close()
 
 
-def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_TILES, cull=1, settings=None):
+KERNELS = [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS]
+
+
+def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_PAIRS, cull=1, settings=None):
     mv.set_option(capi.OPT_MATH, math)
     mv.set_option(capi.OPT_KERNEL, kernel)
     mv.set_option(capi.OPT_CULL, cull)
@@ -67,7 +70,7 @@ def oracle_frame(oracle, scene, mv, fn, h_initial=0.1, adaptive=True, settings=N
 # ---- strict mode: bit-exact ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("fn", sorted(NO_TRANSCENDENTALS))
 @pytest.mark.parametrize("adaptive", [False, True])
-@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT])
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_strict_mode_is_bit_exact_with_the_oracle(view, oracle, scene, fn, adaptive, kernel):
     ref, _ = oracle_frame(oracle, scene, view, fn, adaptive=adaptive)
     flags = 0 if adaptive else capi.RENDER_ADAPTIVE_OFF
@@ -79,6 +82,7 @@ def test_strict_mode_is_bit_exact_with_the_oracle(view, oracle, scene, fn, adapt
     assert c.accepted_steps == int(ref["accepted"].sum())
     assert c.rejected_steps == int(ref["rejected"].sum())
     assert c.prehit_steps == int(ref["prehit"].sum())
+    assert view.timings().march_kernel == kernel  # the kernel asked for is the one that ran
 
 
 @pytest.mark.parametrize("fn", [PredefinedFunction.MirageSpherical, PredefinedFunction.TranslationX, PredefinedFunction.Rotation])
@@ -95,28 +99,72 @@ def test_plane_culling_never_changes_a_result(view, fn, flags):
     assert (ca.accepted_steps, ca.prehit_steps, ca.rejected_steps) == (cb.accepted_steps, cb.prehit_steps, cb.rejected_steps)
 
 
-@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.LorenzAttractor])
-def test_tile_and_persistent_kernels_agree_in_strict_mode(view, fn):
-    a = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT, kernel=capi.KERNEL_TILES)
-    b = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT, kernel=capi.KERNEL_PERSISTENT)
-    for k in a:
-        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.LorenzAttractor,
+                                PredefinedFunction.Rotation])
+@pytest.mark.parametrize("flags", [0, capi.RENDER_ADAPTIVE_OFF])
+def test_all_march_kernels_agree_in_strict_mode(view, fn, flags):
+    """Same per-ray arithmetic whatever the mapping of rays to threads: one ray per thread, persistent warps, or two
+    rays per thread (f32x2 done per component in strict mode) give bit-identical frames and counters."""
+    a = render(view, fn, flags=flags, math=capi.MATH_STRICT, kernel=capi.KERNEL_TILES)
+    ca = view.counters()
+    for kernel in (capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS):
+        b = render(view, fn, flags=flags, math=capi.MATH_STRICT, kernel=kernel)
+        cb = view.counters()
+        for k in a:
+            assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), (kernel, k)
+        assert (ca.accepted_steps, ca.prehit_steps, ca.rejected_steps, ca.face_tests) == \
+               (cb.accepted_steps, cb.prehit_steps, cb.rejected_steps, cb.face_tests), kernel
+
+
+@pytest.mark.parametrize("size", [(161, 120), (33, 17), (16, 4), (2, 2), (15, 3)])
+def test_pair_kernel_handles_odd_and_tiny_frames(product_lib, scene, size):
+    """An odd width leaves the last column's partner outside the frame; tiny frames leave most of a 16x4 tile empty."""
+    verts, faces, center = scene
+    W, H = size
+    with MainView(verts, faces, center, W, H) as mv:
+        fn = PredefinedFunction.MirageSpherical
+        for flags in (0, capi.RENDER_ADAPTIVE_OFF):
+            a = render(mv, fn, flags=flags, math=capi.MATH_STRICT, kernel=capi.KERNEL_TILES)
+            ca = mv.counters()
+            b = render(mv, fn, flags=flags, math=capi.MATH_STRICT, kernel=capi.KERNEL_PAIRS)
+            cb = mv.counters()
+            assert mv.timings().march_kernel == capi.KERNEL_PAIRS
+            for k in a:
+                assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+            assert (ca.rays, ca.accepted_steps, ca.prehit_steps, ca.rejected_steps) == \
+                   (cb.rays, cb.accepted_steps, cb.prehit_steps, cb.rejected_steps)
+
+
+def test_pair_kernel_falls_back_for_bodies_with_per_ray_control_flow(view, oracle, scene):
+    """A straight-line user body runs two rays per thread; a body that branches on per-ray values cannot be
+    instantiated for f32x2, so the same request runs the one-ray-per-thread kernel - same results either way."""
+    straight = "let c = vec3<f32>(-0.5, 0.5, -0.5);\nlet d = p - c;\nreturn normalize(v + 0.05 * d / (0.1 + dot(d, d)));"
+    branchy = ("let c = vec3<f32>(-0.5, 0.5, -0.5);\nlet d = p - c;\nvar w = v + 0.05 * d / (0.1 + dot(d, d));\n"
+               "if (p.y < 0.2) { w = w + vec3<f32>(0.0, 0.02, 0.0); }\nreturn normalize(w);")
+    for body, expect in ((straight, capi.KERNEL_PAIRS), (branchy, capi.KERNEL_TILES)):
+        got = render(view, body, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT, kernel=capi.KERNEL_PAIRS)
+        assert view.timings().march_kernel == expect
+        tiles = render(view, body, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT, kernel=capi.KERNEL_TILES)
+        for k in got:
+            assert np.array_equal(got[k].view(np.uint8), tiles[k].view(np.uint8)), k
+        assert (got["hit_id"] >= 0).mean() > 0.01
 
 
 # ---- production modes: north-star tolerances --------------------------------------------------------------------------
 @pytest.mark.parametrize("fn", PREDEFINED)
 @pytest.mark.parametrize("math", [capi.MATH_FUSED, capi.MATH_FAST])
-def test_fixed_step_frames_meet_the_north_star(view, oracle, scene, fn, math):
+@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PAIRS])
+def test_fixed_step_frames_meet_the_north_star(view, oracle, scene, fn, math, kernel):
     """C1/C2 at reduced resolution, adaptive off (exactly 51 steps): hit id, colour and endpoint."""
     ref, excl = oracle_frame(oracle, scene, view, fn, adaptive=False)
-    got = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=math)
+    got = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=math, kernel=kernel)
     m = parity.compare_frames(got, ref, exclude=excl)
     assert parity.passes_north_star(m, check_endpoint=True), m
     assert view.counters().accepted_steps == 160 * 120 * 51  # SURVEY F2
 
 
 @pytest.mark.parametrize("fn", PREDEFINED)
-@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT])
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_adaptive_frames_meet_the_north_star_on_hit_and_colour(view, oracle, scene, fn, kernel):
     """C1/C2 as the application renders them (adaptive on): graded on hit id and colour; endpoint agreement is
     reported only (rounding-noise-driven step sequences)."""
@@ -135,7 +183,7 @@ def test_enhance_frame_meets_the_north_star(product_lib, oracle, scene):
     with MainView(verts, faces, center, 64, 48) as mv:
         fn = PredefinedFunction.MirageSphericalSigmoid
         ref, excl = oracle_frame(oracle, scene, mv, fn, h_initial=0.001, adaptive=True)
-        for kernel in (capi.KERNEL_TILES, capi.KERNEL_PERSISTENT):
+        for kernel in KERNELS:
             mv.set_option(capi.OPT_KERNEL, kernel)
             mv.render_high_accuracy(fn.to_code())
             mv.sync()
@@ -213,9 +261,10 @@ def test_full_size_properties_c2_c3(product_lib, scene):
         b = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF)
         for k in a:  # deterministic
             assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8))
-        p = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF, kernel=capi.KERNEL_PERSISTENT)
-        m = parity.compare_frames(p, a)
-        assert m["hit_group_agree"] >= 0.9999 and m["endpoint_within_1e3"] >= 0.9999, m
+        for kernel in (capi.KERNEL_PERSISTENT, capi.KERNEL_TILES):  # `a` came from the default pair kernel
+            p = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF, kernel=kernel)
+            m = parity.compare_frames(p, a)
+            assert m["hit_group_agree"] >= 0.9999 and m["endpoint_within_1e3"] >= 0.9999, (kernel, m)
     with MainView(verts, faces, center, 3840, 2160) as mv:
         mv.update_settings(make_settings(overlay_mode=1))
         mv.render_high_accuracy(PredefinedFunction.MirageSphericalSigmoid.to_code())
