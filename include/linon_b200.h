@@ -82,16 +82,22 @@ enum {
                                     2 fast (--use_fast_math: MUFU rcp/rsqrt/ex2/sin/cos, ftz).  Default 2: measured 2x faster
                                     than fused and inside the north-star tolerances (tests/test_gpu_parity.py). */
     LINON_OPT_KERNEL = 1,        /* 0 one thread per pixel in 8x4 tiles, 1 persistent warps: pre-hit / post-hit phase kernels
-                                    with lane refill, 2 (default) two rays per thread on the packed fp32 instructions of
-                                    sm_100 (FFMA2/FMUL2/FADD2) in 16x4 tiles.  A user body that does not instantiate for two
-                                    rays at once (data-dependent control flow) falls back to 0 automatically
-                                    (linon_timings.march_kernel tells which kernel ran).  profiles/, DESIGN.md */
+                                    with lane refill, 2 two rays per thread on the packed fp32 instructions of sm_100
+                                    (FFMA2/FMUL2/FADD2) in 16x4 tiles; a user body that does not instantiate for two rays at
+                                    once (data-dependent control flow) falls back to 0 automatically
+                                    (linon_timings.march_kernel tells which kernel ran).  Default 0: measured fastest - FFMA2
+                                    occupies the issue port for two cycles on B200, so packing does not relieve the
+                                    issue-slot bound (profiles/r1_ffma2_microbench.md) */
     LINON_OPT_BLOCK = 2,         /* threads per CTA of the march kernel (multiple of 32). Default 256 */
     LINON_OPT_CTAS_PER_SM = 3,   /* persistent grid = this x #SM; 0 = occupancy query. Default 0 */
     LINON_OPT_REFILL_MIN = 4,    /* idle lanes a warp tolerates before refilling. Default 1 */
     LINON_OPT_FACE_UNROLL = 5,   /* unroll of the face loop. Default 4 */
     LINON_OPT_MAX_REGS = 6,      /* NVRTC --maxrregcount (0 = none). Default 0 */
     LINON_OPT_PROFILE = 7,       /* 1: persistent kernel accumulates clock64 section timers (linon_debug_profile) */
+    LINON_OPT_SPECIALIZE = 10,   /* 1 (default): in fast math mode a body that is byte-identical with one of the four predefined
+                                    mirage functions (src/functions.rs:36-94) runs its hand-fused restatement
+                                    (csrc/device/mirage_fused.cuh: one reciprocal for eta, no sigmoid reciprocal, shared
+                                    inverse square root, Runge-Kutta stage 1 = identity).  0: always the generic translation */
     LINON_OPT_PAIR_MIN_BLOCKS = 9, /* resident CTAs / SM requested for the pair kernel (register cap); 0 = default (512/block) */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups

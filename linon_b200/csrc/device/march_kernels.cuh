@@ -75,6 +75,12 @@
 #ifndef LINON_PAIRS
 #define LINON_PAIRS 0
 #endif
+#ifndef LINON_FW_ONE
+#define LINON_FW_ONE 0  // 1: settings.field_weight == 1 (host-checked): the direction blend of src/main_view.wgsl:256 is cur_dir = v
+#endif
+#ifndef LINON_STAGE1_IDENTITY
+#define LINON_STAGE1_IDENTITY 0  // 1: the field body guarantees f(p_prev = p, v) = v, so Runge-Kutta stage 1 is not evaluated
+#endif
 #ifndef LINON_PAIR_MIN_BLOCKS
 #define LINON_PAIR_MIN_BLOCKS (512 / LINON_BLOCK)  // 16 resident warps / SM = 32 rays per scheduler slot pair: <= 128 registers
 #endif
@@ -107,6 +113,7 @@ struct MarchParams {
     unsigned int q_capacity;
     unsigned int n_ray_slots;     // tiles * 32 (index space of fresh rays incl. out-of-frame padding lanes)
     unsigned int n_pair_slots;    // 16x4 tiles * 32 (linon_march_pairs: one slot = two horizontally adjacent pixels)
+    float plane_w_max;            // max |plane offset| over the plane groups (rounding bound of SafeDistance)
 };
 
 template <class S> struct RayT {
@@ -169,7 +176,11 @@ __device__ __forceinline__ WgslCamera make_camera(const MarchParams& P) {
 // h is a float (compile-time constant or uniform) or per-ray (adaptive sampling in the pair kernel).
 template <class S, class H>
 __device__ __forceinline__ vec3t<S> rk4_velocity(const RayT<S>& r, H h, const WgslSettings& st, const WgslCamera& cam) {
+#if LINON_STAGE1_IDENTITY
+    const vec3t<S> k1 = r.dir;  // the spliced body declares field(p, p, v0, v, t) == v (mirage_fused.cuh)
+#else
     const vec3t<S> k1 = field_function<S>(r.p, r.p, r.sdir, r.dir, r.t, st, cam);
+#endif
     const vec3t<S> k2 = field_function<S>(r.p, r.p + 0.5f * h * k1, r.sdir, k1, r.t + 0.5f * h, st, cam);
     const vec3t<S> k3 = field_function<S>(r.p, r.p + 0.5f * h * k2, r.sdir, k2, r.t + 0.5f * h, st, cam);
     const vec3t<S> k4 = field_function<S>(r.p, r.p + h * k3, r.sdir, k3, r.t + h, st, cam);
@@ -245,28 +256,46 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
 #endif
 }
 
-// LINON_CULL, level 2: a lower bound `safe` on the distance from the ray's current point to the nearest face plane.
-// After a full check at p it is (min plane distance - rounding allowance); every step then subtracts an upper bound of
-// the distance moved (the L1 norm of step_dir, added with round-up, subtracted with round-down, so `safe` stays a
-// valid lower bound).  While safe exceeds what this step can reach, no plane group could pass the level-1 test, so the
-// whole face loop - including normalize(step_dir) and length(step_dir), which only feed it - is skipped.  Exact for the
-// same reason as level 1; a pre-hit step then costs ~9 instructions instead of ~110.
+// LINON_CULL, level 2: a per-ray budget that stays positive only while NO plane group can pass the level-1 test, so
+// the whole face loop - including normalize(step_dir) and length(step_dir), which only feed it - is skipped and a
+// pre-hit step costs 6 instructions instead of ~110.
+//
+// At a full check at p0 the loop returns nearest0 = min over groups of the COMPUTED plane distance.  For a later point
+// p of the same ray, with d_i the displacement of step i and e(.) <= 3 2^-24 (|p|_1 + |w|) the rounding of the computed
+// distance (three FMAs on a unit normal and the plane offset w):
+//     computed_dist(p, g) >= nearest0 - e(p0) - e(p) - sum_i |d_i|_2 ,
+//     |d_i|_2 <= |step_i|_1 + 1.5 2^-23 |p|_inf        (p + step is rounded once per component).
+// Level 1 tests a group only if computed_dist <= 1.002 |step|_2 + 1e-5 (1 + |p|_1).  While the budget below is positive
+// the travelled distance is below nearest0, hence |p|_1 <= M = |p0|_1 + nearest0, and with C = 1 + M + max_g |w_g|
+//     budget = nearest0 - 1.1e-5 C - sum_{i <= now} (1.003 |step_i|_1 + 2e-7 C)  >  0
+// implies computed_dist(p, g) > reach for every group (1e-5 C covers the absolute term of the level-1 test, 1e-6 C both
+// e(.) terms, 2e-7 C the rounding of each position update, 1.003 the L1 >= L2 slack and the rounding of |step|_2).
+// All sums are rounded against the skip (additions up, the budget down), NaNs compare false -> check.  A skipped loop
+// is therefore one in which level 1 would have skipped every group: results are bit-identical with LINON_CULL = 0.
 struct SafeDistance {
-    float safe;
-    __device__ __forceinline__ void reset() { safe = 0.0f; }
+    float budget, drift;
+    __device__ __forceinline__ void reset() { budget = 0.0f; drift = 0.0f; }
+    // what this step takes from the budget
+    __device__ __forceinline__ float cost(vec3f step_dir) const {
+        const float travel = __fadd_ru(__fadd_ru(fabsf(step_dir.x), fabsf(step_dir.y)), fabsf(step_dir.z));
+        return __fmaf_ru(1.003f, travel, drift);
+    }
     // true: the face loop must run for the step p -> p + step_dir
-    __device__ __forceinline__ bool must_check(vec3f p, vec3f step_dir, float& travel, float& p_l1) const {
-        travel = __fadd_ru(__fadd_ru(fabsf(step_dir.x), fabsf(step_dir.y)), fabsf(step_dir.z));
-        p_l1 = fabsf(p.x) + fabsf(p.y) + fabsf(p.z);
+    __device__ __forceinline__ bool must_check(float step_cost) const {
 #if LINON_CULL
-        return !(safe > __fmaf_rn(1.003f, travel, 1e-5f * (1.0f + p_l1)));  // NaN-safe: unordered -> check
+        return !(__fsub_rd(budget, step_cost) > 0.0f);
 #else
         return true;
 #endif
     }
-    __device__ __forceinline__ void checked(float min_plane_dist, float p_l1) { safe = min_plane_dist - 1e-6f * (1.0f + p_l1); }
-    __device__ __forceinline__ void moved(float travel) { safe = __fsub_rd(safe, travel); }
+    __device__ __forceinline__ void checked(float min_plane_dist, float p_l1, float plane_w_max) {
+        const float c = __fadd_ru(__fadd_ru(__fadd_ru(1.0f, p_l1), min_plane_dist), plane_w_max);
+        budget = __fmaf_rd(-1.1e-5f, c, min_plane_dist);
+        drift = __fmul_ru(2e-7f, c);
+    }
+    __device__ __forceinline__ void moved(float step_cost) { budget = __fsub_rd(budget, step_cost); }
 };
+__device__ __forceinline__ float l1_norm(vec3f p) { return fabsf(p.x) + fabsf(p.y) + fabsf(p.z); }
 
 // Blinn-Phong with the camera as light, src/main_view.wgsl:199-217.
 __device__ __forceinline__ vec3f shade(const float4* __restrict__ s_tri, int id, vec3f direction) {
@@ -359,7 +388,11 @@ __device__ __forceinline__ bool rk4_attempt(Ray& r, const WgslSettings& st, cons
 #else
     diff = 0.0f;
 #endif
+#if LINON_FW_ONE
+    r.dir = v;  // field_weight == 1: (1 - 1) * cur_dir + 1 * v
+#else
     r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+#endif
     step_dir = r.dir * h;
     return true;
 }
@@ -407,15 +440,16 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 continue;
             }
             if (!has_color) {
-                float travel, p_l1;
-                if (sd.must_check(r.p, step_dir, travel, p_l1)) {
+                const float step_cost = sd.cost(step_dir);
+                if (sd.must_check(step_cost)) {
                     const float max_dist = w_length(step_dir);
                     const vec3f dirn = w_normalize(step_dir);
+                    const float p_l1 = l1_norm(r.p);
                     float t_hit, nearest;
                     int id;
                     intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                     ++cnt.checks;
-                    sd.checked(nearest, p_l1);
+                    sd.checked(nearest, p_l1, P.plane_w_max);
                     if (t_hit > 0.0f && t_hit < max_dist) {
                         color = shade(s_tri, id, dirn);
                         hit = id;
@@ -423,7 +457,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                         cnt.prehit = cnt.accepted + 1;  // accepted steps that ran the pre-hit path, this one included
                     }
                 }
-                sd.moved(travel);
+                sd.moved(step_cost);
             }
             rk4_advance(r, v, diff, step_dir);
             ++cnt.accepted;
@@ -460,31 +494,40 @@ struct PixelState {  // what one ray of the pair carries besides its packed RK4 
     unsigned int prehit;
 };
 
-// The pre-hit part of one accepted step for one ray, src/main_view.wgsl:259-262.  Out of line: it runs on ~3 % of
-// the pre-hit steps (SafeDistance), and inlining it twice per pair would only enlarge the hot loop.
-__device__ __noinline__ void pair_mesh_check(const float4* __restrict__ s_tri, const int* __restrict__ s_range, vec3f p,
-                                             vec3f step_dir, float p_l1, unsigned int step_index, PixelState& px,
-                                             StepCounters& cnt) {
-    const float max_dist = w_length(step_dir);
-    const vec3f dirn = w_normalize(step_dir);
+// ray_color's face loop for one ray of a pair.  Out of line: it runs on ~3 % of the pre-hit steps (SafeDistance) and
+// inlining it twice per pair would only enlarge the hot loop.  Everything travels in registers: 8 floats in,
+// {t_hit, face id, nearest plane distance, tests performed} out as one float4 (no per-ray state in local memory).
+__device__ __noinline__ float4 pair_intersect(const float4* __restrict__ s_tri, const int* __restrict__ s_range, float px,
+                                              float py, float pz, float dx, float dy, float dz, float max_dist, float p_l1) {
     float t_hit, nearest;
     int id;
-    intersect_mesh(s_tri, s_range, p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
-    ++cnt.checks;
-    px.sd.checked(nearest, p_l1);
-    if (t_hit > 0.0f && t_hit < max_dist) {
-        px.color = shade(s_tri, id, dirn);
-        px.hit = id;
-        px.has_color = true;
-        px.prehit = step_index + 1;  // accepted steps that ran the pre-hit path, this one included
-    }
+    unsigned int tests = 0u;
+    intersect_mesh(s_tri, s_range, vec3f(px, py, pz), vec3f(dx, dy, dz), max_dist, p_l1, t_hit, id, nearest, tests);
+    return make_float4(t_hit, __int_as_float(id), nearest, __uint_as_float(tests));
 }
 
-__device__ __forceinline__ void pair_prehit(const float4* __restrict__ s_tri, const int* __restrict__ s_range, vec3f p,
-                                            vec3f step_dir, unsigned int step_index, PixelState& px, StepCounters& cnt) {
-    float travel, p_l1;
-    if (px.sd.must_check(p, step_dir, travel, p_l1)) pair_mesh_check(s_tri, s_range, p, step_dir, p_l1, step_index, px, cnt);
-    px.sd.moved(travel);
+// The pre-hit part of one accepted step for one ray, src/main_view.wgsl:259-262.
+__device__ __forceinline__ void pair_prehit(const float4* __restrict__ s_tri, const int* __restrict__ s_range,
+                                            float plane_w_max, vec3f p, vec3f step_dir, unsigned int step_index,
+                                            PixelState& px, StepCounters& cnt) {
+    const float step_cost = px.sd.cost(step_dir);
+    if (px.sd.must_check(step_cost)) {
+        const float max_dist = w_length(step_dir);
+        const vec3f dirn = w_normalize(step_dir);
+        const float p_l1 = l1_norm(p);
+        const float4 r = pair_intersect(s_tri, s_range, p.x, p.y, p.z, dirn.x, dirn.y, dirn.z, max_dist, p_l1);
+        cnt.face_tests += __float_as_uint(r.w);
+        ++cnt.checks;
+        px.sd.checked(r.z, p_l1, plane_w_max);
+        if (r.x > 0.0f && r.x < max_dist) {
+            const int id = __float_as_int(r.y);
+            px.color = shade(s_tri, id, dirn);
+            px.hit = id;
+            px.has_color = true;
+            px.prehit = step_index + 1;  // accepted steps that ran the pre-hit path, this one included
+        }
+    }
+    px.sd.moved(step_cost);
 }
 
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS) linon_march_pairs(const MarchParams P) {
@@ -535,11 +578,15 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS)
             const bool2 accepted(act0 && !rej.lo, act1 && !rej.hi);
             cnt.rejected += (rejected.lo ? 1u : 0u) + (rejected.hi ? 1u : 0u);
             r.h = s_sel(rejected, f32x2(0.001f), r.h);
+#if LINON_FW_ONE
+            const vec3t<f32x2> new_dir = v;
+#else
             const vec3t<f32x2> new_dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+#endif
             const vec3t<f32x2> step_dir = new_dir * h;
             r.dir = w_select(r.dir, new_dir, accepted);
-            if (accepted.lo && !px0.has_color) pair_prehit(s_tri, s_range, lane_lo(r.p), lane_lo(step_dir), acc0, px0, cnt);
-            if (accepted.hi && !px1.has_color) pair_prehit(s_tri, s_range, lane_hi(r.p), lane_hi(step_dir), acc1, px1, cnt);
+            if (accepted.lo && !px0.has_color) pair_prehit(s_tri, s_range, P.plane_w_max, lane_lo(r.p), lane_lo(step_dir), acc0, px0, cnt);
+            if (accepted.hi && !px1.has_color) pair_prehit(s_tri, s_range, P.plane_w_max, lane_hi(r.p), lane_hi(step_dir), acc1, px1, cnt);
             r.p = w_select(r.p, r.p + step_dir, accepted);
             r.t = s_sel(accepted, r.t + h, r.t);
             r.last_v = w_select(r.last_v, v, accepted);
@@ -555,10 +602,14 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS)
         // fixed step: both rays are in lockstep (same t), every attempt is accepted
         for (; r.t.lo <= 5.0f;) {
             const vec3t<f32x2> v = rk4_velocity(r, LINON_H_INITIAL, st, cam);
+#if LINON_FW_ONE
+            r.dir = v;
+#else
             r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+#endif
             const vec3t<f32x2> step_dir = r.dir * LINON_H_INITIAL;
-            if (!px0.has_color) pair_prehit(s_tri, s_range, lane_lo(r.p), lane_lo(step_dir), acc0, px0, cnt);
-            if (!px1.has_color) pair_prehit(s_tri, s_range, lane_hi(r.p), lane_hi(step_dir), acc0, px1, cnt);
+            if (!px0.has_color) pair_prehit(s_tri, s_range, P.plane_w_max, lane_lo(r.p), lane_lo(step_dir), acc0, px0, cnt);
+            if (!px1.has_color) pair_prehit(s_tri, s_range, P.plane_w_max, lane_hi(r.p), lane_hi(step_dir), acc0, px1, cnt);
             r.p = r.p + step_dir;
             r.t = r.t + LINON_H_INITIAL;
             ++acc0;
@@ -676,23 +727,24 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             vec3f v, step_dir;
             float diff;
             if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
-                float travel, p_l1;
+                const float step_cost = sd.cost(step_dir);
                 bool hit_now = false;
-                if (sd.must_check(r.p, step_dir, travel, p_l1)) {
+                if (sd.must_check(step_cost)) {
                     const float max_dist = w_length(step_dir);
                     const vec3f dirn = w_normalize(step_dir);
+                    const float p_l1 = l1_norm(r.p);
                     float t_hit, nearest;
                     int id;
                     intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                     ++cnt.checks;
-                    sd.checked(nearest, p_l1);
+                    sd.checked(nearest, p_l1, P.plane_w_max);
                     hit_now = t_hit > 0.0f && t_hit < max_dist;
                     if (hit_now) {
                         P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
                         P.hit_id[pix] = id;
                     }
                 }
-                sd.moved(travel);
+                sd.moved(step_cost);
                 ++cnt.prehit;
                 rk4_advance(r, v, diff, step_dir);
                 ++cnt.accepted;
@@ -832,7 +884,11 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
     const float4 colour = make_float4(c_sample_colors[k][0], c_sample_colors[k][1], c_sample_colors[k][2], 0.5f);
     for (int i = 0; i < 5000; ++i) {
         const vec3f v = rk4_velocity(r, h, st, cam);
+#if LINON_FW_ONE
+        r.dir = v;
+#else
         r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+#endif
         const vec3f step_dir = r.dir * h;
         if (i % 50 == 0) {
             const int index = k * 100 + i / 50;

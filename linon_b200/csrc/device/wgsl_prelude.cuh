@@ -539,34 +539,33 @@ inline
 #endif
 vec3f linon_total_reflection(vec3f v_in, vec3f n, float d) { return v_in - (2.0f * d) * n; }
 
-// refraction, src/main_view.wgsl:119-136.  Restated without materialising n_ref = +-n: negation is exact in IEEE
-// arithmetic, so with s = -1 when cosi >= 0 (n_ref = -n) and +1 otherwise (n_ref = n)
-//     eta * v_in + (eta * |cosi| - sqrt(k)) * n_ref  ==  eta * v_in + (s * (eta * |cosi| - sqrt(k))) * n      bit for bit,
-//     reflect(v_in, n_ref) = v_in - 2 dot(n_ref, v_in) n_ref  ==  v_in - 2 dot(n, v_in) n                     bit for bit
+// refraction, src/main_view.wgsl:119-136.  Restated without materialising n_ref = +-n or |cosi|: negation is exact in
+// IEEE arithmetic and round-to-nearest is sign-symmetric, so with sk = sqrt(k) and cosi the clamped dot product
+//     cosi <  0 (n_ref =  n):   (eta |cosi| - sk) n_ref  ==  (-sk - eta cosi) n      bit for bit
+//     cosi >= 0 (n_ref = -n):   (eta |cosi| - sk) n_ref  ==  ( sk - eta cosi) n      bit for bit   (also when contracted to FMA),
+//     reflect(v_in, n_ref) = v_in - 2 dot(n_ref, v_in) n_ref  ==  v_in - 2 dot(n, v_in) n            bit for bit
 // (tests/test_translator.py and tests/test_gpu_units.py compare against the oracle's literal transcription).
 // Total reflection (k < 0) is rare, so it is a real branch instead of seven predicated instructions per evaluation.
 LINON_HD vec3f refraction_s(float t_in, float t_out, vec3f v_in, vec3f n) {
     const float d = w_dot(v_in, n);
-    const float cosi_raw = w_clamp(-1.0f, 1.0f, d);  // misordered in the reference: min(max(-1, 1), d) = min(1, d)
-    const float cosi = w_abs(cosi_raw);              // `if (cosi < 0) cosi = -cosi`
-    const float eta = refraction_eta(t_in, t_out);   // eta_in / eta_out, src/main_view.wgsl:120-121,129
+    const float cosi = w_clamp(-1.0f, 1.0f, d);     // misordered in the reference: min(max(-1, 1), d) = min(1, d)
+    const float eta = refraction_eta(t_in, t_out);  // eta_in / eta_out, src/main_view.wgsl:120-121,129
     const float k = 1.0f - eta * eta * (1.0f - cosi * cosi);
     if (__builtin_expect(k < 0.0f, 0)) {
         return linon_total_reflection(v_in, n, d);  // reflect(v_in, n_ref); dot(n_ref, v_in) n_ref = dot(n, v_in) n
     }
-    const float c = eta * cosi - w_sqrt(k);
-    const float cs = (cosi_raw < 0.0f) ? c : -c;     // n_ref = n when cosi < 0, else -n
+    const float sk = w_sqrt(k);
+    const float cs = ((cosi < 0.0f) ? -sk : sk) - eta * cosi;
     return eta * v_in + cs * n;
 }
 // The same arithmetic on two rays at once; the rare total-reflection component is patched by a select.
 LINON_HD vec3t<f32x2> refraction_s(f32x2 t_in, f32x2 t_out, vec3t<f32x2> v_in, vec3t<f32x2> n) {
     const f32x2 d = w_dot(v_in, n);
-    const f32x2 cosi_raw = w_clamp(-1.0f, 1.0f, d);
-    const f32x2 cosi = w_abs(cosi_raw);
+    const f32x2 cosi = w_clamp(-1.0f, 1.0f, d);
     const f32x2 eta = refraction_eta(t_in, t_out);
     const f32x2 k = 1.0f - eta * eta * (1.0f - cosi * cosi);
-    const f32x2 c = eta * cosi - w_sqrt(k);  // NaN in a totally reflected component, replaced below
-    const f32x2 cs = s_sel(cosi_raw < 0.0f, c, -c);
+    const f32x2 sk = w_sqrt(k);  // NaN in a totally reflected component, replaced below
+    const f32x2 cs = f32x2((cosi.lo < 0.0f) ? -sk.lo : sk.lo, (cosi.hi < 0.0f) ? -sk.hi : sk.hi) - eta * cosi;
     vec3t<f32x2> r = eta * v_in + cs * n;
     const bool2 total = k < 0.0f;
     if (__builtin_expect(s_any(total), 0)) {

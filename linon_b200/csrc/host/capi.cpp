@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -109,6 +110,7 @@ struct MarchParamsH {
     unsigned int q_capacity;
     unsigned int n_ray_slots;
     unsigned int n_pair_slots;
+    float plane_w_max;
 };
 struct SampleParamsH {
     MarchParamsH march;
@@ -121,6 +123,8 @@ static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view
 struct Variant {
     float h_initial;
     int adaptive, n_faces, n_groups, cull, math, block, unroll, refill_min, max_regs, profile;
+    int fw_one;           // 1: settings.field_weight == 1 (the application's default): cur_dir = v without the blend
+    int specialize;       // 1: fast math may splice the hand-fused restatement of a predefined mirage body
     int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
     int pair_min_blocks;  // resident CTAs / SM requested for it (0 = kernel default)
 };
@@ -146,15 +150,31 @@ const char kFieldHead[] =
     "#line 1 \"field_function.wgsl\"\n";
 const char kFieldTail[] = "\n    }\n};\n#line 1 \"march_kernels.cuh\"\n";
 
-std::string build_source(const std::string& cuda_body) {
+// 1..4 when `wgsl_body` is byte-identical with one of the predefined mirage bodies (src/functions.rs:36-94), else 0
+int mirage_kind(const std::string& wgsl_body) {
+    using linon::PredefinedFunction;
+    const PredefinedFunction kinds[4] = {PredefinedFunction::MirageSpherical, PredefinedFunction::MiragePlane,
+                                         PredefinedFunction::MirageSphericalSigmoid, PredefinedFunction::MiragePlaneSigmoid};
+    for (int k = 0; k < 4; ++k)
+        if (wgsl_body == linon::to_code(kinds[k])) return k + 1;
+    return 0;
+}
+
+std::string build_source(const std::string& cuda_body, int fused_kind) {
     std::string s;
-    s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + cuda_body.size() + 512);
+    s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + sizeof(kMirageFusedSrc) + cuda_body.size() + 512);
     s += "#line 1 \"wgsl_prelude.cuh\"\n";
     s += kPreludeSrc;
     s += "\n";
-    s += kFieldHead;
-    s += cuda_body;
-    s += kFieldTail;
+    if (fused_kind > 0) {  // hand-fused restatement of a predefined mirage body (fast math only)
+        s += "#define LINON_MIRAGE_KIND " + std::to_string(fused_kind) + "\n#line 1 \"mirage_fused.cuh\"\n";
+        s += kMirageFusedSrc;
+        s += "\n#line 1 \"march_kernels.cuh\"\n";
+    } else {
+        s += kFieldHead;
+        s += cuda_body;
+        s += kFieldTail;
+    }
     s += kMarchSrc;
     return s;
 }
@@ -174,7 +194,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
         log = terr;
         return false;
     }
-    const std::string src = build_source(cuda_body);
+    const int fused_kind = (var.math == 2 && var.specialize) ? mirage_kind(wgsl_body) : 0;
+    const std::string src = build_source(cuda_body, fused_kind);
     nvrtcProgram prog = nullptr;
     if (nvrtcCreateProgram(&prog, src.c_str(), "linon_march.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
         log = "nvrtcCreateProgram failed";
@@ -191,6 +212,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
                                      "-DLINON_REFILL_MIN=" + std::to_string(var.refill_min),
                                      "-DLINON_PROFILE=" + std::to_string(var.profile),
                                      "-DLINON_PAIRS=" + std::to_string(var.pairs),
+                                     "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
                                      "-DLINON_PACKED_OPS=" + std::to_string(var.math == 0 ? 0 : 1)};
     if (var.pair_min_blocks > 0) opts.push_back("-DLINON_PAIR_MIN_BLOCKS=" + std::to_string(var.pair_min_blocks));
@@ -236,8 +258,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
 }
 
 std::string variant_key(const std::string& body, const Variant& v) {
-    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
-               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks) + body;
+    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one) + body;
 }
 
 }  // namespace
@@ -256,6 +278,7 @@ struct linon_view {
     bool has_camera = false;
     linon_settings settings{};
     uint32_t n_faces = 0, n_groups = 0;
+    float plane_w_max = 0.0f;  // max |offset| of the plane groups
     void* d_tris = nullptr;   // n_faces x {v0, e1, e2} then n_groups x {unit normal, offset}
     int* d_group_range = nullptr;
 
@@ -278,7 +301,7 @@ struct linon_view {
     std::map<std::string, Module> modules;
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
-    int opt_math = 2, opt_kernel = 2, opt_pair_min_blocks = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
+    int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
         opt_max_regs = 0, opt_profile = 0, opt_cull = 1;
 
     linon_timings timings{};
@@ -398,6 +421,9 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.refill_min = v->opt_refill_min;
     var.max_regs = v->opt_max_regs;
     var.profile = v->opt_profile;
+    var.specialize = v->opt_specialize;
+    // production math modes only: strict mode keeps the blend as written (0 * dir + 1 * v differs from v in the sign of a zero)
+    var.fw_one = (v->opt_math != 0 && v->settings.field_weight == 1.0f) ? 1 : 0;
     var.pairs = (v->opt_kernel == 2 && !v->pair_unfit.count(v->body)) ? 1 : 0;
     var.pair_min_blocks = var.pairs ? v->opt_pair_min_blocks : 0;
     return var;
@@ -437,6 +463,7 @@ void fill_march_params(const linon_view* v, MarchParamsH& P) {
     const unsigned int tiles_x = (v->W + 7) / 8, tiles_y = (v->local_rows + 3) / 4;
     P.n_ray_slots = tiles_x * tiles_y * 32u;
     P.n_pair_slots = ((v->W + 15) / 16) * tiles_y * 32u;
+    P.plane_w_max = v->plane_w_max;
 }
 
 int launch(linon_view* v, CUfunction f, unsigned grid, unsigned block, cudaStream_t s, void* params) {
@@ -600,6 +627,8 @@ int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const ui
     CK(v, cudaMemcpy(v->d_group_range, ranges.data(), ranges.size() * sizeof(int), cudaMemcpyHostToDevice));
     v->n_groups = n_groups;
     v->n_faces = n_faces;
+    v->plane_w_max = 0.0f;
+    for (size_t g = 0; g < planes.size() / 4; ++g) v->plane_w_max = std::max(v->plane_w_max, std::fabs(planes[4 * g + 3]));
     return LINON_OK;
 }
 
@@ -818,6 +847,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_MATH: if (value < 0 || value > 2) break; v->opt_math = value; return LINON_OK;
         case LINON_OPT_KERNEL: if (value < 0 || value > 2) break; v->opt_kernel = value; return LINON_OK;
         case LINON_OPT_PAIR_MIN_BLOCKS: if (value < 0 || value > 32) break; v->opt_pair_min_blocks = value; return LINON_OK;
+        case LINON_OPT_SPECIALIZE: if (value < 0 || value > 1) break; v->opt_specialize = value; return LINON_OK;
         case LINON_OPT_BLOCK: if (value < 32 || value > 1024 || value % 32) break; v->opt_block = value; return LINON_OK;
         case LINON_OPT_CTAS_PER_SM: if (value < 0 || value > 32) break; v->opt_ctas_per_sm = value; return LINON_OK;
         case LINON_OPT_REFILL_MIN: if (value < 1 || value > 32) break; v->opt_refill_min = value; return LINON_OK;
@@ -886,7 +916,11 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     tmp.n_groups = n_faces == 36 ? 15 : n_faces;  // the Cornell box has 15 plane groups
     tmp.opt_math = math_mode;
     tmp.body = wgsl_body;
+    tmp.settings.field_weight = 1.0f;  // the application's default (src/main_view.rs:133-139)
     if (const char* k = getenv("LINON_CHECK_KERNEL")) tmp.opt_kernel = atoi(k);  // developer aid: 0 = without the pair kernel
+    if (const char* k = getenv("LINON_CHECK_PAIR_MIN_BLOCKS")) tmp.opt_pair_min_blocks = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_BLOCK")) tmp.opt_block = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_SPECIALIZE")) tmp.opt_specialize = atoi(k);
     Variant var = make_variant(&tmp, flags);
     std::vector<char> cubin;
     std::string log;

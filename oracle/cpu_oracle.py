@@ -143,13 +143,14 @@ def overlay(raycast_rgba8, endpoint, settings, exponents=None):
     return final, exps
 
 
-def field(fn_id, settings, p_prev, p, v0, v, t):
+def field(fn_id, settings, p_prev, p, v0, v, t, use_fp64=False):
+    """field_function on n samples; use_fp64 evaluates the same restatement in double (diagnostic, rounded to f32)."""
     arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (p_prev, p, v0, v, t)]
     n = arrs[4].shape[0]
     out = np.zeros((n, 3), np.float32)
     st = make_settings(settings)
-    lib().oracle_field(int(fn_id), C.byref(st), n, *[C.c_void_p(a.ctypes.data) for a in arrs],
-                       C.c_void_p(out.ctypes.data))
+    fn = lib().oracle_field_fp64 if use_fp64 else lib().oracle_field
+    fn(int(fn_id), C.byref(st), n, *[C.c_void_p(a.ctypes.data) for a in arrs], C.c_void_p(out.ctypes.data))
     return out
 
 

@@ -718,6 +718,18 @@ void oracle_field(int fn_id, const SettingsPOD* st, int n, const float* p_prev, 
     }
 }
 
+// The same restatement evaluated in double (diagnostic): where the reference's own fp32 formulation is ill-conditioned
+// (refraction at grazing incidence computes sqrt(1 - (1 - cosi^2))), this is what it is a rounding of.
+void oracle_field_fp64(int fn_id, const SettingsPOD* st, int n, const float* p_prev, const float* p, const float* v0,
+                       const float* v, const float* t, float* out) {
+    for (int i = 0; i < n; ++i) {
+        const V3<double> r = field_function<double>(fn_id, *st, {p_prev[3 * i], p_prev[3 * i + 1], p_prev[3 * i + 2]},
+                                                    {p[3 * i], p[3 * i + 1], p[3 * i + 2]}, {v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]},
+                                                    {v[3 * i], v[3 * i + 1], v[3 * i + 2]}, (double)t[i]);
+        out[3 * i] = (float)r.x; out[3 * i + 1] = (float)r.y; out[3 * i + 2] = (float)r.z;
+    }
+}
+
 // which: 0 rotateX 1 rotateY 2 rotateZ 3 translate(v, a, b, c) 4 refraction(a, b, v, n) 5 point_plane_distance(v, n, p0)
 //        6 sigmoid(a) 7 refraction_index(a) 8 reflect(v, n) 9 normalize(v) 10 cross(v, n)
 void oracle_helper(int which, int n, const float* v, const float* nrm, const float* p0, const float* a, const float* b,

@@ -36,10 +36,11 @@ def view(product_lib, scene):
 KERNELS = [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS]
 
 
-def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_PAIRS, cull=1, settings=None):
+def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_TILES, cull=1, settings=None, specialize=1):
     mv.set_option(capi.OPT_MATH, math)
     mv.set_option(capi.OPT_KERNEL, kernel)
     mv.set_option(capi.OPT_CULL, cull)
+    mv.set_option(capi.OPT_SPECIALIZE, specialize)
     mv.reload_shader(fn.to_code() if isinstance(fn, PredefinedFunction) else fn)
     mv.update_settings(settings if settings is not None else make_settings())
     mv.render_flags(flags)
@@ -163,6 +164,27 @@ def test_fixed_step_frames_meet_the_north_star(view, oracle, scene, fn, math, ke
     assert view.counters().accepted_steps == 160 * 120 * 51
 
 
+MIRAGES = [PredefinedFunction.MirageSpherical, PredefinedFunction.MiragePlane, PredefinedFunction.MirageSphericalSigmoid,
+           PredefinedFunction.MiragePlaneSigmoid]
+
+
+@pytest.mark.parametrize("fn", MIRAGES)
+@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PAIRS])
+def test_fused_mirage_restatements_agree_with_the_generic_translation(view, oracle, scene, fn, kernel):
+    """Fast mode runs a hand-fused restatement of the predefined mirage bodies (csrc/device/mirage_fused.cuh: one
+    reciprocal for eta, Runge-Kutta stage 1 = identity).  Both it and the generic translation of the same WGSL text must
+    meet the north star against the oracle, and a body that differs by a single character runs the generic path."""
+    ref, excl = oracle_frame(oracle, scene, view, fn, adaptive=False)
+    fused = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, kernel=kernel, specialize=1)
+    generic = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, kernel=kernel, specialize=0)
+    assert parity.passes_north_star(parity.compare_frames(fused, ref, exclude=excl), check_endpoint=True)
+    assert parity.passes_north_star(parity.compare_frames(generic, ref, exclude=excl), check_endpoint=True)
+    assert not np.array_equal(fused["endpoint"], generic["endpoint"])  # the restatement really ran
+    edited = render(view, fn.to_code() + " ", flags=capi.RENDER_ADAPTIVE_OFF, kernel=kernel, specialize=1)
+    for k in generic:  # not byte-identical with the predefined text: generic translation, bit for bit
+        assert np.array_equal(edited[k].view(np.uint8), generic[k].view(np.uint8)), k
+
+
 @pytest.mark.parametrize("fn", PREDEFINED)
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_adaptive_frames_meet_the_north_star_on_hit_and_colour(view, oracle, scene, fn, kernel):
@@ -261,7 +283,7 @@ def test_full_size_properties_c2_c3(product_lib, scene):
         b = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF)
         for k in a:  # deterministic
             assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8))
-        for kernel in (capi.KERNEL_PERSISTENT, capi.KERNEL_TILES):  # `a` came from the default pair kernel
+        for kernel in (capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS):  # `a` came from the default tile kernel
             p = render(mv, fn, flags=capi.RENDER_ADAPTIVE_OFF, kernel=kernel)
             m = parity.compare_frames(p, a)
             assert m["hit_group_agree"] >= 0.9999 and m["endpoint_within_1e3"] >= 0.9999, (kernel, m)

@@ -124,9 +124,18 @@ def test_field_functions_match_the_oracle(view, oracle, fn):
         assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
     else:
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # fast math: within tolerance of the fp32 oracle, or - where the reference's own formulation is ill-conditioned
+    # (refraction at grazing incidence rounds sqrt(1 - (1 - cosi^2)); its fp32 result is then itself 1e-4 away from
+    # the function it rounds) - of the same restatement evaluated in double.  Both the generic translation and the
+    # hand-fused restatement of the mirage bodies (mirage_fused.cuh) are graded.
+    ref64 = oracle.field(int(fn), settings_dict(make_settings()), p_prev, p, v0, v, t, use_fp64=True)
     view.set_option(capi.OPT_MATH, capi.MATH_FAST)
-    fast = view.debug_eval_field(p_prev, p, v0, v, t)
-    assert np.allclose(fast, ref, rtol=2e-4, atol=2e-5)
+    for specialize in (0, 1):
+        view.set_option(capi.OPT_SPECIALIZE, specialize)
+        fast = view.debug_eval_field(p_prev, p, v0, v, t)
+        ok = np.isclose(fast, ref, rtol=2e-4, atol=2e-5) | np.isclose(fast, ref64, rtol=2e-4, atol=2e-5)
+        assert ok.all(), (specialize, np.argwhere(~ok)[:5])
+    view.set_option(capi.OPT_SPECIALIZE, 1)
 
 
 def test_user_edited_function_runs_and_errors_keep_the_old_kernel(view):

@@ -17,6 +17,7 @@ fn = PredefinedFunction.MirageSphericalSigmoid
 variants = "0:256:0:0,2:256:0:0,2:128:0:0,2:256:3:0,2:128:5:0"
 flags = capi.RENDER_ENHANCE
 reps = 3
+body_file = None
 i = 0
 pos = []
 while i < len(args):
@@ -24,6 +25,8 @@ while i < len(args):
         fn = PredefinedFunction(int(args[i + 1])); i += 2
     elif args[i] == "--variants":
         variants = args[i + 1]; i += 2
+    elif args[i] == "--body-file":
+        body_file = args[i + 1]; i += 2
     elif args[i] == "--reps":
         reps = int(args[i + 1]); i += 2
     elif args[i] == "--default-step":
@@ -36,11 +39,21 @@ if len(pos) == 2:
 verts, faces, center = default_scene()
 os.makedirs("gpurun_out", exist_ok=True)
 out = open("gpurun_out/kernel_compare.jsonl", "a")
+from linon_b200 import parity  # noqa: E402
+
 with MainView(verts, faces, center, W, H) as mv:
-    mv.reload_shader(fn.to_code())
+    ref = None
+    if body_file:  # a custom body: report its agreement with the predefined function it restates
+        mv.reload_shader(fn.to_code())
+        mv.render_flags(flags | capi.RENDER_NO_SAMPLE_RAYS)
+        mv.sync()
+        ref = dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
+    mv.reload_shader(open(body_file).read() if body_file else fn.to_code())
     mv.update_settings(make_settings(overlay_mode=1))
     for var in variants.split(","):
-        kernel, block, pmb, regs = (int(x) for x in var.split(":"))
+        f = [int(x) for x in var.split(":")] + [0, 0, 0, 1]
+        kernel, block, pmb, regs, spec = f[0], f[1], f[2], f[3], (f[4] if len(var.split(":")) > 4 else 1)
+        mv.set_option(capi.OPT_SPECIALIZE, spec)
         mv.set_option(capi.OPT_KERNEL, kernel)
         mv.set_option(capi.OPT_BLOCK, block)
         mv.set_option(capi.OPT_PAIR_MIN_BLOCKS, pmb)
@@ -54,8 +67,12 @@ with MainView(verts, faces, center, W, H) as mv:
                 best = t
         c = mv.counters()
         line = dict(fn=fn.name, W=W, H=H, kernel=best.march_kernel, block=block, pair_min_blocks=pmb, max_regs=regs,
-                    regs=best.march_regs, grid=best.march_grid, march_ms=round(best.march_ms, 3),
+                    regs=best.march_regs, grid=best.march_grid, specialize=spec, march_ms=round(best.march_ms, 3),
                     mrays_s=round(W * H / best.march_ms / 1e3, 2),
                     gsteps_s=round((c.accepted_steps + c.rejected_steps) / best.march_ms / 1e6, 2))
+        if ref is not None:
+            got = dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
+            m = parity.compare_frames(got, ref)
+            line.update(body=os.path.basename(body_file), vs_predefined={k: (round(float(v), 6) if isinstance(v, float) else v) for k, v in m.items()})
         print(json.dumps(line), flush=True)
         out.write(json.dumps(line) + "\n")
