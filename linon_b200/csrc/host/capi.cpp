@@ -338,10 +338,12 @@ void free_frame_buffers(linon_view* v) {
     v->q_capacity = 0;
 }
 
-int alloc_queue(linon_view* v) {
+// The post-hit queue of the persistent kernel (52 B per ray of the shard) is allocated on first use: the default tile
+// kernel never touches it, and at 8192 x 8192 it would be 3.5 GB.
+int alloc_queue(linon_view* v, bool needed) {
     v->local_rows = count_local_rows(v->H, v->shard_rank, v->shard_world, v->rows_per_block);
-    const size_t cap = (size_t)v->local_rows * v->W;
-    if (cap == v->q_capacity && v->d_q_pixel) return LINON_OK;
+    const size_t cap = needed ? (size_t)v->local_rows * v->W : 0;
+    if (cap == v->q_capacity && (v->d_q_pixel || cap == 0)) return LINON_OK;
     cudaFree(v->d_q_pixel); cudaFree(v->d_q_state);
     v->d_q_pixel = nullptr; v->d_q_state = nullptr; v->q_capacity = 0;
     if (cap == 0) return LINON_OK;
@@ -365,7 +367,7 @@ int alloc_frame_buffers(linon_view* v, uint32_t W, uint32_t H) {
     CK(v, cudaMemsetAsync(v->d_endpoint, 0, n * 16, v->stream));
     CK(v, cudaMemsetAsync(v->d_exponents, 0, n * 4, v->stream));  // wgpu zero-initialises buffers
     CK(v, cudaMemsetAsync(v->d_hit, 0xFF, n * 4, v->stream));
-    return alloc_queue(v);
+    return alloc_queue(v, false);
 }
 
 int get_module(linon_view* v, const std::string& body, const Variant& var, Module** out, float* jit_ms) {
@@ -659,7 +661,7 @@ int linon_set_shard(linon_view* v, uint32_t rank, uint32_t world, uint32_t rows_
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
     v->shard_rank = rank; v->shard_world = world; v->rows_per_block = rows_per_block;
-    return alloc_queue(v);
+    return alloc_queue(v, false);
 }
 
 int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, size_t err_len) {
@@ -693,6 +695,10 @@ int linon_render(linon_view* v, uint32_t flags) {
     v->timings = linon_timings{};
     v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = v->ran_phases = false;
 
+    if (do_march && v->opt_kernel == 1) {
+        const int rc = alloc_queue(v, true);
+        if (rc != LINON_OK) return rc;
+    }
     Module* mod = nullptr;
     MarchParamsH P;
     fill_march_params(v, P);

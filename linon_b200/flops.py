@@ -29,6 +29,29 @@ SAFE_STEP = 8          # per pre-hit step with culling on
 CHECK_EXTRA = 5        # reach + bound reset, per culling check
 
 
+# Hand-fused mirage restatements (csrc/device/mirage_fused.cuh, fast math): executed work per accepted step.
+# Stage 1 is the identity (not evaluated), stages 2-4 evaluate the fused body (F_EVAL), the previous point's share
+# (distance, E or part, A, B) is computed once per step (F_PREV).  Counted like the rest: FMA = 2, rsqrt/exp2/sqrt/div = 1.
+#   spherical sigmoid: eval 3 (p - c) + 5 (dot) + 1 (rsqrt) + 3 (normal) + 1 (dist) + 3 (E) + 4 (A', B') + 3 (eta)
+#                      + 5 (v . n) + 1 (min) + 5 (k) + 1 (sqrt) + 2 (cs) + 9 (eta v + cs n) = 46;  prev 3+5+1+1+3+4 = 17
+#   spherical linear:  E (3) becomes part = min(1, dist / max_dist) (2): 45 / 16
+#   plane sigmoid:     no normalisation, v . n = v.y, normal term on y only: 2 (dist) + 3 + 4 + 3 + 1 + 5 + 1 + 2 + 4 = 25;  prev 2+3+4 = 9
+#   plane linear:      24 / 8
+FUSED_FLOPS = {1: (45, 16), 2: (24, 8), 3: (46, 17), 4: (25, 9)}
+FUSED_STEP_FIXED = 18 + 18 + 3 + 4   # stage inputs of stages 2-4, combine, step_dir, advance (+10 blend when field_weight != 1)
+SAFE_STEP_V2 = 6                     # |s|_1 (2), cost (2), budget - cost (1), compare operand (1)
+
+
+def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True) -> float:
+    """Executed-work model of the fast-mode mirage path in fixed-step variants (Enhance, adaptive off)."""
+    f_eval, f_prev = FUSED_FLOPS[fn_id]
+    step = FUSED_STEP_FIXED + (0 if field_weight_is_one else 10) + 3 * f_eval + f_prev
+    flops = counters.accepted_steps * step + counters.face_tests * FACE_TEST
+    flops += counters.prehit_steps * SAFE_STEP_V2
+    flops += counters.culling_checks * (PREHIT_EXTRA + CHECK_EXTRA + 3) + counters.plane_tests * PLANE_TEST
+    return float(flops)
+
+
 def march_flops(counters, fn_id: int, adaptive: bool, n_faces: int = 36, field_flops: int | None = None) -> float:
     """counters: object with accepted_steps, prehit_steps, rejected_steps, face_tests, plane_tests."""
     F = FIELD_FLOPS[fn_id] if field_flops is None else field_flops

@@ -54,6 +54,10 @@ with MainView(verts, faces, center, W, H) as mv:
         f = [int(x) for x in var.split(":")] + [0, 0, 0, 1]
         kernel, block, pmb, regs, spec = f[0], f[1], f[2], f[3], (f[4] if len(var.split(":")) > 4 else 1)
         mv.set_option(capi.OPT_SPECIALIZE, spec)
+        refill = f[5] if len(var.split(":")) > 5 else 1
+        ctas = f[6] if len(var.split(":")) > 6 else 0
+        mv.set_option(capi.OPT_REFILL_MIN, refill)
+        mv.set_option(capi.OPT_CTAS_PER_SM, ctas)
         mv.set_option(capi.OPT_KERNEL, kernel)
         mv.set_option(capi.OPT_BLOCK, block)
         mv.set_option(capi.OPT_PAIR_MIN_BLOCKS, pmb)
@@ -67,7 +71,7 @@ with MainView(verts, faces, center, W, H) as mv:
                 best = t
         c = mv.counters()
         line = dict(fn=fn.name, W=W, H=H, kernel=best.march_kernel, block=block, pair_min_blocks=pmb, max_regs=regs,
-                    regs=best.march_regs, grid=best.march_grid, specialize=spec, march_ms=round(best.march_ms, 3),
+                    regs=best.march_regs, grid=best.march_grid, specialize=spec, refill_min=refill, ctas_per_sm=ctas, march_ms=round(best.march_ms, 3),
                     mrays_s=round(W * H / best.march_ms / 1e3, 2),
                     gsteps_s=round((c.accepted_steps + c.rejected_steps) / best.march_ms / 1e6, 2))
         if ref is not None:
