@@ -94,6 +94,8 @@ enum {
     LINON_OPT_FACE_UNROLL = 5,   /* unroll of the face loop. Default 4 */
     LINON_OPT_MAX_REGS = 6,      /* NVRTC --maxrregcount (0 = none). Default 0 */
     LINON_OPT_PROFILE = 7,       /* 1: persistent kernel accumulates clock64 section timers (linon_debug_profile) */
+    LINON_OPT_FORCE_BVH = 11,    /* 1: stage the mesh as faces + bounding-volume hierarchy in global memory even when it would fit
+                                    shared memory (meshes above 1024 faces always do).  Results are identical; for tests */
     LINON_OPT_SPECIALIZE = 10,   /* 1 (default): in fast math mode a body that is byte-identical with one of the four predefined
                                     mirage functions (src/functions.rs:36-94) runs its hand-fused restatement
                                     (csrc/device/mirage_fused.cuh: one reciprocal for eta, no sigmoid reciprocal, shared
@@ -136,7 +138,10 @@ int linon_create(int device, uint32_t width, uint32_t height, linon_view** out);
 void linon_destroy(linon_view* v);
 
 /* MainView::update_model (:460-488) + the vertices/faces storage buffers (src/application.rs:112-122).
- * verts: n_verts x 3 f32, faces: n_faces x 3 u32 (copied). */
+ * verts: n_verts x 3 f32, faces: n_faces x 3 u32 (copied).  Up to 1024 faces are staged per CTA in shared memory with
+ * plane-group culling; larger meshes (an OBJ dropped on the window, src/main.rs:139-157) are staged in global memory with
+ * a bounding-volume hierarchy whose traversal is exact: the closest hit and the lowest-index tie-break of the
+ * reference's loop over every face (src/main_view.wgsl:182-198) are preserved. */
 int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces);
 /* MainView::update_camera (:490-494): uploads the 112-byte uniform. */
 int linon_set_camera(linon_view* v, const linon_camera* camera);

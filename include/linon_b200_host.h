@@ -19,6 +19,13 @@ extern "C" {
  * negate_xz = 0 gives load_default_model (src/application.rs:194-197). */
 void linon_host_default_scene(float* verts216, uint32_t* faces108, float* center3, int negate_xz);
 void linon_host_normalize_vertices(float* verts, uint32_t n_floats);
+/* The OBJ drag-and-drop path: tobj::load_obj(triangulate) -> models[0] -> Application::load_model (src/main.rs:139-157,
+ * src/application.rs:199-226).  Parses `obj_text`, fan-triangulates, keeps the first model, re-indexes its positions in
+ * order of first use, normalises them (src/vertices.rs:3-17, no x/z negation on this path) and returns the bounding-box
+ * centre.  Call with verts = faces = NULL to query the sizes (vertices / faces, not floats); capacities count vertices
+ * and faces.  Returns LINON_ERR_INVALID with a message for malformed text, LINON_ERR_SIZE when a capacity is too small. */
+int linon_host_load_obj(const char* obj_text, float* verts, uint32_t verts_capacity, uint32_t* faces, uint32_t faces_capacity,
+                        uint32_t* n_verts, uint32_t* n_faces, float* center3, char* err, size_t err_len);
 void linon_host_get_center(const float* verts, uint32_t n_floats, float* center3);
 
 /* PredefinedFunction (src/functions.rs): id in enum order 0..9. Returns the byte length (excluding NUL) or -1. */

@@ -19,7 +19,7 @@ RENDER_NO_OVERLAY, RENDER_NO_MARCH, RENDER_NO_SAMPLE_RAYS = 8, 16, 32
 BUF_FINAL_RGBA8, BUF_RAYCAST_RGBA8, BUF_ENDPOINT_F32X4, BUF_EXPONENTS_F32, BUF_HIT_ID_I32 = range(5)
 BUF_RAY_SAMPLES, BUF_SAMPLE_POS = 5, 6
 OPT_MATH, OPT_KERNEL, OPT_BLOCK, OPT_CTAS_PER_SM, OPT_REFILL_MIN, OPT_FACE_UNROLL, OPT_MAX_REGS, OPT_PROFILE, OPT_CULL = range(9)
-OPT_PAIR_MIN_BLOCKS, OPT_SPECIALIZE = 9, 10
+OPT_PAIR_MIN_BLOCKS, OPT_SPECIALIZE, OPT_FORCE_BVH = 9, 10, 11
 MATH_STRICT, MATH_FUSED, MATH_FAST = 0, 1, 2
 KERNEL_TILES, KERNEL_PERSISTENT, KERNEL_PAIRS = 0, 1, 2
 
@@ -89,6 +89,7 @@ PROTOTYPES = [
     # include/linon_b200_host.h
     ("linon_host_default_scene", None, [_P, _P, _P, _I]),
     ("linon_host_normalize_vertices", None, [_P, _U]),
+    ("linon_host_load_obj", _I, [_CP, _P, _U, _P, _U, C.POINTER(_U), C.POINTER(_U), _P, _P, _S]),
     ("linon_host_get_center", None, [_P, _U, _P]),
     ("linon_host_function_code", _I, [_I, _P, _S]),
     ("linon_host_function_name", _I, [_I, _P, _S]),

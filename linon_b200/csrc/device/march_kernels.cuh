@@ -15,6 +15,8 @@
 //   LINON_REFILL_MIN     idle lanes a warp tolerates before it refills (persistent kernel)
 //   LINON_CULL / LINON_N_GROUPS  plane culling of the face loop (see intersect_mesh) and the number of plane groups
 //   LINON_PROFILE        1 adds clock64 section timers to the persistent kernels (counters[5..14])
+//   LINON_BVH            1 for meshes beyond the shared-memory stage (OBJ models, src/main.rs:139-157): the face loop
+//                        becomes an exact traversal of a bounding-volume hierarchy (see intersect_mesh)
 //   LINON_PAIRS          1 also builds linon_march_pairs: two rays per thread on the packed fp32 instructions of
 //                        sm_100 (FFMA2 / FMUL2 / FADD2), LinonField<f32x2>.  The host retries with 0 when a user
 //                        body does not instantiate for f32x2 (data-dependent control flow).
@@ -75,6 +77,9 @@
 #ifndef LINON_PAIRS
 #define LINON_PAIRS 0
 #endif
+#ifndef LINON_BVH
+#define LINON_BVH 0  // 1: the mesh is too large for shared memory (> 1024 faces): faces + a bounding-volume hierarchy in global memory
+#endif
 #ifndef LINON_FW_ONE
 #define LINON_FW_ONE 0  // 1: settings.field_weight == 1 (host-checked): the direction blend of src/main_view.wgsl:256 is cur_dir = v
 #endif
@@ -113,7 +118,9 @@ struct MarchParams {
     unsigned int q_capacity;
     unsigned int n_ray_slots;     // tiles * 32 (index space of fresh rays incl. out-of-frame padding lanes)
     unsigned int n_pair_slots;    // 16x4 tiles * 32 (linon_march_pairs: one slot = two horizontally adjacent pixels)
-    float plane_w_max;            // max |plane offset| over the plane groups (rounding bound of SafeDistance)
+    float plane_w_max;            // max |plane offset| over the plane groups / max |coordinate| of a BVH mesh
+                                  // (rounding bound of SafeDistance)
+    const float4* bvh;            // LINON_BVH: 2 x float4 per node {lo.xyz, left child | first slot}, {hi.xyz, 0 | face count}
 };
 
 template <class S> struct RayT {
@@ -191,7 +198,11 @@ __device__ __forceinline__ vec3t<S> rk4_velocity(const RayT<S>& r, H h, const Wg
 // Branch-free restatement of the reference's early returns (same comparisons, same NaN behaviour).
 __device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int i, vec3f origin, vec3f direction,
                                           float max_dist, float& t_best, int& id_best) {
+#if LINON_BVH
+    const float4 a = __ldg(s_tri + 3 * i), b = __ldg(s_tri + 3 * i + 1), c = __ldg(s_tri + 3 * i + 2);
+#else
     const float4 a = s_tri[3 * i], b = s_tri[3 * i + 1], c = s_tri[3 * i + 2];
+#endif
     const vec3f v0(a.x, a.y, a.z), edge1(b.x, b.y, b.z), edge2(c.x, c.y, c.z);
     const vec3f h = w_cross(direction, edge2);
     const float det = w_dot(edge1, h);
@@ -204,10 +215,23 @@ __device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int 
     const bool ok = !(det > -LINON_EPS && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) &&
                     !(v < 0.0f || u + v > 1.0f) && (t > LINON_EPS);
     const float t_new = ok ? t : -1.0f;
+#if LINON_BVH
+    // the hierarchy visits faces out of index order: the reference's strict `<` over ascending indices (lowest index
+    // wins an exact tie) becomes a lexicographic comparison on (t, original face index); a.w carries that index
+    if (t_new > 0.0f && t_new < max_dist) {
+        const bool better = t_best < 0.0f || t_new < t_best ||
+                            (t_new == t_best && __float_as_int(a.w) < __float_as_int(__ldg(s_tri + 3 * id_best).w));
+        if (better) {
+            t_best = t_new;
+            id_best = i;  // slot in the hierarchy's face order
+        }
+    }
+#else
     if (t_new > 0.0f && t_new < max_dist && (t_best < 0.0f || t_new < t_best)) {
         t_best = t_new;
         id_best = i;
     }
+#endif
 }
 
 // ray_color's loop over every face (src/main_view.wgsl:182-198), keeping the closest hit in (0, max_dist).
@@ -221,12 +245,55 @@ __device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int 
 // visited in index order, so the strict `t_new < t` tie-break of the reference (lowest index wins) is preserved.
 // The smallest plane distance is returned for level 2 (see SafeDistance).
 __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri, const int* __restrict__ s_range,
-                                               vec3f origin, vec3f direction, float max_dist, float origin_l1,
-                                               float& t_best, int& id_best, float& min_plane_dist,
-                                               unsigned int& face_tests) {
+                                               const float4* __restrict__ bvh, vec3f origin, vec3f direction,
+                                               float max_dist, float origin_l1, float& t_best, int& id_best,
+                                               float& min_plane_dist, unsigned int& face_tests) {
     t_best = -1.0f;
     id_best = -1;
-#if LINON_CULL
+#if LINON_BVH
+    // Exact traversal.  A face can only report t in (eps, max_dist) if its (slightly inflated) bounding box is within
+    // max_dist of the segment origin, so a subtree whose box is farther than `reach` (same margins as the plane test
+    // below) cannot contain the closest hit: skipping it never changes a result (tests compare with the oracle's loop
+    // over every face).  The smallest box distance seen - of skipped subtrees and of visited leaves - is a lower bound on
+    // the distance to any face and feeds SafeDistance like the plane distances do.  s_tri = faces in hierarchy order
+    // (global memory, L2 resident), s_range = unused, bvh = P.bvh.
+    {
+        const float reach = 1.002f * max_dist + 1e-5f * (1.0f + origin_l1);
+        const float reach2 = reach * reach * 1.0001f;
+        float nearest2 = 3.0e38f;
+        int stack[40];
+        int sp = 0, node = 0;
+        for (;;) {
+            const float4 lo = __ldg(bvh + 2 * node), hi = __ldg(bvh + 2 * node + 1);
+            const float dx = fmaxf(fmaxf(lo.x - origin.x, origin.x - hi.x), 0.0f);
+            const float dy = fmaxf(fmaxf(lo.y - origin.y, origin.y - hi.y), 0.0f);
+            const float dz = fmaxf(fmaxf(lo.z - origin.z, origin.z - hi.z), 0.0f);
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            bool descend = false;
+            if (!(d2 <= reach2)) {
+                nearest2 = fminf(nearest2, d2);  // skipped subtree: every face in it is at least this far
+            } else {
+                const int count = __float_as_int(hi.w), first = __float_as_int(lo.w);
+                if (count > 0) {
+                    nearest2 = fminf(nearest2, d2);  // visited leaf
+                    for (int i = first; i < first + count; ++i) {
+                        test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
+                        ++face_tests;
+                    }
+                } else {
+                    stack[sp++] = first + 1;  // children are adjacent: left = first, right = first + 1
+                    node = first;
+                    descend = true;
+                }
+            }
+            if (!descend) {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        }
+        min_plane_dist = sqrtf(nearest2);
+    }
+#elif LINON_CULL
     const float reach = 1.002f * max_dist + 1e-5f * (1.0f + origin_l1);
     const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES;
     float nearest = 3.0e38f;
@@ -323,6 +390,17 @@ __device__ __forceinline__ void stage_mesh(float4* s_tri, int* s_range, const Ma
     for (int i = threadIdx.x; i < LINON_N_GROUPS; i += blockDim.x) s_range[i] = P.group_range[i];
     __syncthreads();
 }
+#if LINON_BVH
+// large mesh: faces (in hierarchy order, original index in .w of the first float4) stay in global memory
+#define LINON_MESH_PROLOGUE(P) const float4* const s_tri = (P).tris; const int* const s_range = nullptr;
+#define LINON_FACE_ID(tris, slot) __float_as_int(__ldg((tris) + 3 * (slot)).w)
+#else
+#define LINON_MESH_PROLOGUE(P)                   \
+    __shared__ float4 s_tri[LINON_MESH_F4];      \
+    __shared__ int s_range[LINON_N_GROUPS];      \
+    stage_mesh(s_tri, s_range, P);
+#define LINON_FACE_ID(tris, slot) (slot)
+#endif
 
 // 32 consecutive ray slots form an 8x4 pixel tile; returns false for padding lanes outside the shard.
 __device__ __forceinline__ bool slot_to_pixel(const MarchParams& P, unsigned int slot, int& x, int& local_row) {
@@ -414,9 +492,7 @@ __device__ __forceinline__ void rk4_advance(Ray& r, vec3f v, float diff, vec3f s
 // Kernel 1: one thread per pixel.
 // ------------------------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_tiles(const MarchParams P) {
-    __shared__ float4 s_tri[LINON_MESH_F4];
-    __shared__ int s_range[LINON_N_GROUPS];
-    stage_mesh(s_tri, s_range, P);
+    LINON_MESH_PROLOGUE(P)
 
     const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
     int x, local_row;
@@ -453,12 +529,12 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     const float p_l1 = l1_norm(r.p);
                     float t_hit, nearest;
                     int id;
-                    intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                    intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                     ++cnt.checks;
                     sd.checked(nearest, p_l1, P.plane_w_max);
                     if (t_hit > 0.0f && t_hit < max_dist) {
                         color = shade(s_tri, id, dirn);
-                        hit = id;
+                        hit = LINON_FACE_ID(s_tri, id);
                         has_color = true;           // result.color.a = t > 0
                         cnt.prehit = cnt.accepted + 1;  // accepted steps that ran the pre-hit path, this one included
                     }
@@ -477,7 +553,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
     flush_counters(P, cnt);
 }
 
-#if LINON_PAIRS
+#if LINON_PAIRS && !LINON_BVH
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1b: one thread per pair of horizontally adjacent pixels (packed f32x2 arithmetic).
 //
@@ -508,7 +584,7 @@ __device__ __noinline__ float4 pair_intersect(const float4* __restrict__ s_tri, 
     float t_hit, nearest;
     int id;
     unsigned int tests = 0u;
-    intersect_mesh(s_tri, s_range, vec3f(px, py, pz), vec3f(dx, dy, dz), max_dist, p_l1, t_hit, id, nearest, tests);
+    intersect_mesh(s_tri, s_range, nullptr, vec3f(px, py, pz), vec3f(dx, dy, dz), max_dist, p_l1, t_hit, id, nearest, tests);
     return make_float4(t_hit, __int_as_float(id), nearest, __uint_as_float(tests));
 }
 
@@ -537,9 +613,7 @@ __device__ __forceinline__ void pair_prehit(const float4* __restrict__ s_tri, co
 }
 
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS) linon_march_pairs(const MarchParams P) {
-    __shared__ float4 s_tri[LINON_MESH_F4];
-    __shared__ int s_range[LINON_N_GROUPS];
-    stage_mesh(s_tri, s_range, P);
+    LINON_MESH_PROLOGUE(P)
 
     const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
     const unsigned int tiles_x = (unsigned int)(P.width + 15) >> 4;
@@ -675,9 +749,7 @@ __device__ __forceinline__ unsigned int lane_rank(unsigned int mask) { return __
 #endif
 
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_phase_a(const MarchParams P) {
-    __shared__ float4 s_tri[LINON_MESH_F4];
-    __shared__ int s_range[LINON_N_GROUPS];
-    stage_mesh(s_tri, s_range, P);
+    LINON_MESH_PROLOGUE(P)
 
     const unsigned int lane = threadIdx.x & 31;
     const WgslCamera cam = make_camera(P);
@@ -741,13 +813,13 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     const float p_l1 = l1_norm(r.p);
                     float t_hit, nearest;
                     int id;
-                    intersect_mesh(s_tri, s_range, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                    intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                     ++cnt.checks;
                     sd.checked(nearest, p_l1, P.plane_w_max);
                     hit_now = t_hit > 0.0f && t_hit < max_dist;
                     if (hit_now) {
                         P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
-                        P.hit_id[pix] = id;
+                        P.hit_id[pix] = LINON_FACE_ID(s_tri, id);
                     }
                 }
                 sd.moved(step_cost);

@@ -111,6 +111,7 @@ struct MarchParamsH {
     unsigned int n_ray_slots;
     unsigned int n_pair_slots;
     float plane_w_max;
+    const void* bvh;
 };
 struct SampleParamsH {
     MarchParamsH march;
@@ -123,6 +124,7 @@ static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view
 struct Variant {
     float h_initial;
     int adaptive, n_faces, n_groups, cull, math, block, unroll, refill_min, max_regs, profile;
+    int bvh;              // 1: large mesh, faces + bounding-volume hierarchy in global memory (n_faces / n_groups are 0 then)
     int fw_one;           // 1: settings.field_weight == 1 (the application's default): cur_dir = v without the blend
     int specialize;       // 1: fast math may splice the hand-fused restatement of a predefined mirage body
     int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
@@ -213,6 +215,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
                                      "-DLINON_PROFILE=" + std::to_string(var.profile),
                                      "-DLINON_PAIRS=" + std::to_string(var.pairs),
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
+                                     "-DLINON_BVH=" + std::to_string(var.bvh),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
                                      "-DLINON_PACKED_OPS=" + std::to_string(var.math == 0 ? 0 : 1)};
     if (var.pair_min_blocks > 0) opts.push_back("-DLINON_PAIR_MIN_BLOCKS=" + std::to_string(var.pair_min_blocks));
@@ -258,8 +261,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
 }
 
 std::string variant_key(const std::string& body, const Variant& v) {
-    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
-               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one) + body;
+    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh) + body;
 }
 
 }  // namespace
@@ -278,7 +281,12 @@ struct linon_view {
     bool has_camera = false;
     linon_settings settings{};
     uint32_t n_faces = 0, n_groups = 0;
-    float plane_w_max = 0.0f;  // max |offset| of the plane groups
+    float plane_w_max = 0.0f;  // max |offset| of the plane groups (BVH meshes: max |coordinate|)
+    bool use_bvh = false;      // mesh beyond the shared-memory stage: faces in hierarchy order + nodes in global memory
+    void* d_bvh = nullptr;
+    uint32_t bvh_nodes = 0, bvh_depth = 0;
+    std::vector<float> host_verts;     // copy of the last mesh (re-staged when LINON_OPT_FORCE_BVH changes)
+    std::vector<uint32_t> host_faces;
     void* d_tris = nullptr;   // n_faces x {v0, e1, e2} then n_groups x {unit normal, offset}
     int* d_group_range = nullptr;
 
@@ -301,7 +309,7 @@ struct linon_view {
     std::map<std::string, Module> modules;
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
-    int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
+    int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
         opt_max_regs = 0, opt_profile = 0, opt_cull = 1;
 
     linon_timings timings{};
@@ -414,8 +422,9 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.h_initial = (flags & LINON_RENDER_ENHANCE) ? 0.001f : 0.1f;  // src/main_view.rs:785-787
     // adaptive sampling can only act while h_initial > 0.002 (src/main_view.wgsl:252,267)
     var.adaptive = (!(flags & LINON_RENDER_ADAPTIVE_OFF) && var.h_initial > 0.002f) ? 1 : 0;
-    var.n_faces = (int)v->n_faces;
-    var.n_groups = (int)v->n_groups;
+    var.bvh = v->use_bvh ? 1 : 0;
+    var.n_faces = v->use_bvh ? 1 : (int)v->n_faces;   // the hierarchy kernels do not depend on the face count
+    var.n_groups = v->use_bvh ? 1 : (int)v->n_groups;
     var.cull = v->opt_cull;
     var.math = v->opt_math;
     var.block = v->opt_block;
@@ -426,7 +435,7 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.specialize = v->opt_specialize;
     // production math modes only: strict mode keeps the blend as written (0 * dir + 1 * v differs from v in the sign of a zero)
     var.fw_one = (v->opt_math != 0 && v->settings.field_weight == 1.0f) ? 1 : 0;
-    var.pairs = (v->opt_kernel == 2 && !v->pair_unfit.count(v->body)) ? 1 : 0;
+    var.pairs = (v->opt_kernel == 2 && !v->use_bvh && !v->pair_unfit.count(v->body)) ? 1 : 0;
     var.pair_min_blocks = var.pairs ? v->opt_pair_min_blocks : 0;
     return var;
 }
@@ -466,12 +475,129 @@ void fill_march_params(const linon_view* v, MarchParamsH& P) {
     P.n_ray_slots = tiles_x * tiles_y * 32u;
     P.n_pair_slots = ((v->W + 15) / 16) * tiles_y * 32u;
     P.plane_w_max = v->plane_w_max;
+    P.bvh = v->d_bvh;
 }
 
 int launch(linon_view* v, CUfunction f, unsigned grid, unsigned block, cudaStream_t s, void* params) {
     void* args[] = {params};
     const CUresult r = g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)s, args, nullptr);
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel: " + g_drv.err_str(r));
+    return LINON_OK;
+}
+
+constexpr uint32_t kSharedMeshFaces = 1024;  // 48 B per face + plane groups fit the static shared memory of a CTA
+
+// ---- bounding-volume hierarchy for meshes beyond the shared-memory stage (OBJ models, src/main.rs:139-157) --------
+// Binary tree, median split of the face centroids along the longest axis, <= 4 faces per leaf, the two children of a
+// node in adjacent slots.  Node = 2 x float4: {lo.xyz, int bits: left child (inner) | first face slot (leaf)},
+// {hi.xyz, int bits: 0 (inner) | face count (leaf)}.  Boxes are inflated by a few ulps of the mesh extent and rounded
+// outwards, so a point of a face as the kernel sees it ({v0, e1, e2} in fp32) is always inside its leaf box.
+struct BvhBuild {
+    struct Box { float lo[3], hi[3]; };
+    std::vector<Box> face_box;
+    std::vector<float> centroid;  // 3 per face
+    std::vector<uint32_t> order;  // face slots in hierarchy order -> original face index
+    std::vector<float> nodes;     // 8 floats per node
+    uint32_t depth = 0;
+
+    static void put_int(float* dst, int32_t x) { memcpy(dst, &x, 4); }
+
+    void build(uint32_t node, uint32_t b, uint32_t e, uint32_t level) {
+        depth = std::max(depth, level);
+        Box box = face_box[order[b]];
+        float clo[3], chi[3];
+        for (int k = 0; k < 3; ++k) clo[k] = chi[k] = centroid[3 * order[b] + k];
+        for (uint32_t i = b + 1; i < e; ++i) {
+            const Box& f = face_box[order[i]];
+            for (int k = 0; k < 3; ++k) {
+                box.lo[k] = std::min(box.lo[k], f.lo[k]);
+                box.hi[k] = std::max(box.hi[k], f.hi[k]);
+                clo[k] = std::min(clo[k], centroid[3 * order[i] + k]);
+                chi[k] = std::max(chi[k], centroid[3 * order[i] + k]);
+            }
+        }
+        float* n = nodes.data() + 8 * (size_t)node;
+        for (int k = 0; k < 3; ++k) { n[k] = box.lo[k]; n[4 + k] = box.hi[k]; }
+        if (e - b <= 4) {
+            put_int(n + 3, (int32_t)b);
+            put_int(n + 7, (int32_t)(e - b));
+            return;
+        }
+        int axis = 0;
+        for (int k = 1; k < 3; ++k)
+            if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+        const uint32_t mid = b + (e - b) / 2;
+        std::nth_element(order.begin() + b, order.begin() + mid, order.begin() + e, [&](uint32_t x, uint32_t y) {
+            const float cx = centroid[3 * x + axis], cy = centroid[3 * y + axis];
+            return cx < cy || (cx == cy && x < y);
+        });
+        const uint32_t left = (uint32_t)(nodes.size() / 8);
+        nodes.resize(nodes.size() + 16);
+        n = nodes.data() + 8 * (size_t)node;  // resize may have moved the storage
+        put_int(n + 3, (int32_t)left);
+        put_int(n + 7, 0);
+        build(left, b, mid, level + 1);
+        build(left + 1, mid, e, level + 1);
+    }
+};
+
+int set_mesh_bvh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces) {
+    std::vector<float> tris((size_t)n_faces * 12, 0.0f);
+    BvhBuild bb;
+    bb.face_box.resize(n_faces);
+    bb.centroid.resize((size_t)3 * n_faces);
+    bb.order.resize(n_faces);
+    float extent = 0.0f;
+    for (uint32_t i = 0; i < n_faces; ++i) {
+        const uint32_t ia = faces[3 * i], ib = faces[3 * i + 1], ic = faces[3 * i + 2];
+        if (ia >= n_verts || ib >= n_verts || ic >= n_verts) return v->fail(LINON_ERR_INVALID, fmt("face %u indexes past the vertex array", i));
+        const float* a = verts + 3 * ia; const float* b = verts + 3 * ib; const float* c = verts + 3 * ic;
+        float* t = tris.data() + 12 * (size_t)i;
+        for (int k = 0; k < 3; ++k) {  // {v0, e1, e2}: the two subtractions hit_triangle performs (src/main_view.wgsl:152-153)
+            t[k] = a[k];
+            t[4 + k] = b[k] - a[k];
+            t[8 + k] = c[k] - a[k];
+            // the triangle the kernel tests is (v0, v0 + e1, v0 + e2); bound it together with the input vertices
+            const double p1 = (double)t[k] + (double)t[4 + k], p2 = (double)t[k] + (double)t[8 + k];
+            const double lo = std::min({(double)a[k], (double)b[k], (double)c[k], p1, p2});
+            const double hi = std::max({(double)a[k], (double)b[k], (double)c[k], p1, p2});
+            bb.face_box[i].lo[k] = (float)lo;
+            bb.face_box[i].hi[k] = (float)hi;
+            bb.centroid[3 * (size_t)i + k] = (float)((lo + hi) * 0.5);
+            extent = std::max({extent, std::fabs((float)lo), std::fabs((float)hi)});
+        }
+        bb.order[i] = i;
+    }
+    if (!std::isfinite(extent)) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: non-finite vertex coordinates");
+    const float pad = 4e-7f * (1.0f + extent);  // a few ulps of the largest coordinate
+    for (auto& f : bb.face_box)
+        for (int k = 0; k < 3; ++k) {
+            f.lo[k] = std::nextafter(f.lo[k] - pad, -INFINITY);
+            f.hi[k] = std::nextafter(f.hi[k] + pad, INFINITY);
+        }
+    bb.nodes.assign(8, 0.0f);
+    bb.build(0, 0, n_faces, 1);
+    if (bb.depth > 38) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: hierarchy deeper than the traversal stack");
+    // faces in hierarchy order; .w of the first float4 carries the original face index (the hit id and the tie-break)
+    std::vector<float> sorted((size_t)n_faces * 12);
+    for (uint32_t slot = 0; slot < n_faces; ++slot) {
+        memcpy(sorted.data() + 12 * (size_t)slot, tris.data() + 12 * (size_t)bb.order[slot], 48);
+        BvhBuild::put_int(sorted.data() + 12 * (size_t)slot + 3, (int32_t)bb.order[slot]);
+    }
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaStreamSynchronize(v->stream));
+    cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_bvh);
+    v->d_tris = nullptr; v->d_group_range = nullptr; v->d_bvh = nullptr;
+    CK(v, cudaMalloc(&v->d_tris, sorted.size() * sizeof(float)));
+    CK(v, cudaMemcpy(v->d_tris, sorted.data(), sorted.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(v, cudaMalloc(&v->d_bvh, bb.nodes.size() * sizeof(float)));
+    CK(v, cudaMemcpy(v->d_bvh, bb.nodes.data(), bb.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+    v->n_faces = n_faces;
+    v->n_groups = 0;
+    v->use_bvh = true;
+    v->bvh_nodes = (uint32_t)(bb.nodes.size() / 8);
+    v->bvh_depth = bb.depth;
+    v->plane_w_max = extent;
     return LINON_OK;
 }
 
@@ -549,6 +675,7 @@ void linon_destroy(linon_view* v) {
     cudaStreamSynchronize(v->aux);
     for (auto& kv : v->modules) g_drv.ModuleUnload(kv.second.mod);
     free_frame_buffers(v);
+    cudaFree(v->d_bvh);
     cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_ray_samples); cudaFree(v->d_pos16); cudaFree(v->d_counters);
     cudaFree(v->d_outline_keys); cudaFree(v->d_work);
     for (auto& ev : v->ev) cudaEventDestroy(ev);
@@ -559,7 +686,13 @@ void linon_destroy(linon_view* v) {
 
 int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces) {
     if (!v || !verts || !faces || n_faces == 0) return v ? v->fail(LINON_ERR_INVALID, "linon_set_mesh: null/empty mesh") : LINON_ERR_INVALID;
-    if (n_faces > 1024) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: more than 1024 faces do not fit the shared-memory mesh stage");
+    if (n_faces > (1u << 24)) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: more than 2^24 faces");
+    if (verts != v->host_verts.data()) v->host_verts.assign(verts, verts + (size_t)3 * n_verts);
+    if (faces != v->host_faces.data()) v->host_faces.assign(faces, faces + (size_t)3 * n_faces);
+    verts = v->host_verts.data();
+    faces = v->host_faces.data();
+    if (n_faces > kSharedMeshFaces || v->opt_force_bvh) return set_mesh_bvh(v, verts, n_verts, faces, n_faces);
+    v->use_bvh = false;
     // {v0, e1, e2} per face; the two subtractions are the ones hit_triangle performs (src/main_view.wgsl:152-153)
     std::vector<float> tris((size_t)n_faces * 12, 0.0f);
     for (uint32_t i = 0; i < n_faces; ++i) {
@@ -695,7 +828,7 @@ int linon_render(linon_view* v, uint32_t flags) {
     v->timings = linon_timings{};
     v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = v->ran_phases = false;
 
-    if (do_march && v->opt_kernel == 1) {
+    if (do_march && v->opt_kernel == 1 && !v->use_bvh) {
         const int rc = alloc_queue(v, true);
         if (rc != LINON_OK) return rc;
     }
@@ -739,10 +872,10 @@ int linon_render(linon_view* v, uint32_t flags) {
         const unsigned block = (unsigned)v->opt_block;
         const bool use_pairs = v->opt_kernel == 2 && mod->pairs != nullptr;
         const unsigned needed = ((use_pairs ? P.n_pair_slots : P.n_ray_slots) + block - 1) / block;
-        v->timings.march_kernel = use_pairs ? 2 : (v->opt_kernel == 1 ? 1 : 0);
+        v->timings.march_kernel = use_pairs ? 2 : ((v->opt_kernel == 1 && !v->use_bvh) ? 1 : 0);
         v->timings.march_block = (int)block;
         CK(v, cudaEventRecord(v->ev[0], v->stream));
-        if (v->opt_kernel == 1) {
+        if (v->opt_kernel == 1 && !v->use_bvh) {
             // persistent warps: phase A (pre-hit rays, lane refill from the fresh cursor) then phase B (queued post-hit
             // rays) as two launches on the same stream, so phase B sees a complete, immutable queue
             CK(v, cudaMemsetAsync(v->d_work, 0, 64, v->stream));
@@ -854,6 +987,15 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_KERNEL: if (value < 0 || value > 2) break; v->opt_kernel = value; return LINON_OK;
         case LINON_OPT_PAIR_MIN_BLOCKS: if (value < 0 || value > 32) break; v->opt_pair_min_blocks = value; return LINON_OK;
         case LINON_OPT_SPECIALIZE: if (value < 0 || value > 1) break; v->opt_specialize = value; return LINON_OK;
+        case LINON_OPT_FORCE_BVH:
+            if (value < 0 || value > 1) break;
+            if (v->opt_force_bvh != value) {
+                v->opt_force_bvh = value;
+                if (!v->host_faces.empty())  // re-stage the current mesh for the other intersection path
+                    return linon_set_mesh(v, v->host_verts.data(), (uint32_t)(v->host_verts.size() / 3), v->host_faces.data(),
+                                          (uint32_t)(v->host_faces.size() / 3));
+            }
+            return LINON_OK;
         case LINON_OPT_BLOCK: if (value < 32 || value > 1024 || value % 32) break; v->opt_block = value; return LINON_OK;
         case LINON_OPT_CTAS_PER_SM: if (value < 0 || value > 32) break; v->opt_ctas_per_sm = value; return LINON_OK;
         case LINON_OPT_REFILL_MIN: if (value < 1 || value > 32) break; v->opt_refill_min = value; return LINON_OK;
@@ -920,6 +1062,7 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     linon_view tmp;
     tmp.n_faces = n_faces;
     tmp.n_groups = n_faces == 36 ? 15 : n_faces;  // the Cornell box has 15 plane groups
+    if (n_faces > kSharedMeshFaces) tmp.use_bvh = true;
     tmp.opt_math = math_mode;
     tmp.body = wgsl_body;
     tmp.settings.field_weight = 1.0f;  // the application's default (src/main_view.rs:133-139)
@@ -927,6 +1070,7 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     if (const char* k = getenv("LINON_CHECK_PAIR_MIN_BLOCKS")) tmp.opt_pair_min_blocks = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BLOCK")) tmp.opt_block = atoi(k);
     if (const char* k = getenv("LINON_CHECK_SPECIALIZE")) tmp.opt_specialize = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_BVH")) tmp.use_bvh = atoi(k) != 0;
     Variant var = make_variant(&tmp, flags);
     std::vector<char> cubin;
     std::string log;

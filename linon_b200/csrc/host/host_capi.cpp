@@ -6,6 +6,7 @@
 #include <string>
 
 #include "main_view.hpp"
+#include "obj_loader.hpp"
 
 struct linon_host_arcball {
     linon::ArcballCamera cam;
@@ -57,6 +58,26 @@ void linon_host_get_center(const float* verts, uint32_t n_floats, float* center3
     const std::vector<float> v(verts, verts + n_floats);
     const auto c = linon::get_center(v);
     memcpy(center3, c.data(), 12);
+}
+
+int linon_host_load_obj(const char* obj_text, float* verts, uint32_t verts_capacity, uint32_t* faces, uint32_t faces_capacity,
+                        uint32_t* n_verts, uint32_t* n_faces, float* center3, char* err, size_t err_len) {
+    if (!obj_text || !n_verts || !n_faces) return LINON_ERR_INVALID;
+    linon::Mesh m;
+    std::string error;
+    if (!linon::load_obj_text(obj_text, m, error)) {
+        if (err && err_len) snprintf(err, err_len, "%s", error.c_str());
+        return LINON_ERR_INVALID;
+    }
+    const std::array<float, 3> c = linon::prepare_loaded_model(m);
+    *n_verts = (uint32_t)(m.vertices.size() / 3);
+    *n_faces = (uint32_t)(m.indices.size() / 3);
+    if (center3) memcpy(center3, c.data(), 12);
+    if (!verts && !faces) return LINON_OK;  // size query
+    if (*n_verts > verts_capacity || *n_faces > faces_capacity) return LINON_ERR_SIZE;
+    if (verts) memcpy(verts, m.vertices.data(), m.vertices.size() * sizeof(float));
+    if (faces) memcpy(faces, m.indices.data(), m.indices.size() * sizeof(uint32_t));
+    return LINON_OK;
 }
 
 int linon_host_function_code(int id, char* out, size_t out_len) {

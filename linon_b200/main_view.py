@@ -49,6 +49,25 @@ def default_scene(negate_xz: bool = True):
     return verts, faces, center
 
 
+def load_obj(text: str):
+    """The OBJ drop path (src/main.rs:139-157 -> Application::load_model): (verts [n,3] f32 normalised, faces [m,3] u32, centre)."""
+    L = capi.lib()
+    nv, nf = C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(1024)
+    data = text.encode("utf-8")
+    rc = L.linon_host_load_obj(data, None, 0, None, 0, C.byref(nv), C.byref(nf), None, err, len(err))
+    if rc != capi.OK:
+        raise LinonError(rc, err.value.decode("utf-8", "replace"))
+    verts = np.zeros((nv.value, 3), np.float32)
+    faces = np.zeros((nf.value, 3), np.uint32)
+    center = np.zeros(3, np.float32)
+    rc = L.linon_host_load_obj(data, verts.ctypes.data, nv.value, faces.ctypes.data, nf.value, C.byref(nv), C.byref(nf),
+                               center.ctypes.data, err, len(err))
+    if rc != capi.OK:
+        raise LinonError(rc, err.value.decode("utf-8", "replace"))
+    return verts, faces, center
+
+
 def make_settings(field_weight=1.0, mouse_pos=(0.5, 0.6), overlay_mode=0, central_difference_delta=1,
                   lyapunov_scaling=50.0) -> Settings:
     """Defaults are MainView::new's initial uniform (src/main_view.rs:133-139)."""

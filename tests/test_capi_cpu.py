@@ -107,3 +107,20 @@ def test_default_camera_is_the_reference_start_up_camera(scene):
     assert np.allclose(u.origin[:3], center + np.array([0, 0, 2], np.float32), atol=1e-6)
     assert list(u.view_direction[:3]) == [0.0, 0.0, -1.0] and list(u.up[:3]) == [0.0, 1.0, 0.0]
     assert np.array_equal(np.array(u.view_matrix[:]).reshape(4, 4), np.eye(4))
+
+
+def test_obj_loader_follows_the_drop_path(product_lib):
+    """src/main.rs:139-157 (tobj triangulate, first model) -> Application::load_model (normalise, centre)."""
+    from linon_b200.main_view import LinonError, load_obj
+    text = ("# a quad, a relative-index triangle, then a second object that must be ignored\n"
+            "v 0 0 0\nv 2 0 0\nv 2 2 0\nv 0 2 0\nv 9 9 9\nvt 0 0\nvn 0 0 1\n"
+            "o first\nf 1/1/1 2/1/1 3/1/1 4/1/1\nf -4//1 -3//1 -2//1\no second\nf 1 2 5\n")
+    verts, faces, center = load_obj(text)
+    assert faces.tolist() == [[0, 1, 2], [0, 2, 3], [1, 2, 3]]          # fan (0, i, i+1); -4 counts back from the 5th vertex
+    assert verts.shape == (4, 3)                                        # vertex 5 belongs to the second model only
+    assert verts.min() == -1.0 and verts.max() == 1.0                   # one global min / max (src/vertices.rs:3-17)
+    assert np.allclose(center, [0.0, 0.0, -1.0])                        # bounding-box centre (src/vertices.rs:19-57)
+    with pytest.raises(LinonError):
+        load_obj("v 0 0 0\nf 1 2 3\n")                                  # index past the vertex list
+    with pytest.raises(LinonError):
+        load_obj("v 0 0 0\nv 1 0 0\n")                                  # no faces

@@ -298,3 +298,97 @@ def test_full_size_properties_c2_c3(product_lib, scene):
         ex = mv.exponents()
         assert (ex[:2] == 0).all() and (ex[-2:] == 0).all() and (ex[:, :2] == 0).all() and (ex[:, -2:] == 0).all()
         assert (ex[2:-2, 2:-2] > 0).all()
+
+
+# ---- meshes beyond the shared-memory stage: bounding-volume hierarchy ------------------------------
+def uv_sphere_obj(n_lat=24, n_lon=48, radius=120.0, centre=(278.0, 274.4, 279.6)):
+    """A UV sphere inside the Cornell box (box units) as OBJ text: quads on the body, triangles at the poles."""
+    lines = []
+    for i in range(n_lat + 1):
+        th = np.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2 * np.pi * j / n_lon
+            lines.append("v %.6f %.6f %.6f" % (centre[0] + radius * np.sin(th) * np.cos(ph), centre[1] + radius * np.cos(th),
+                                               centre[2] + radius * np.sin(th) * np.sin(ph)))
+    for i in range(n_lat):
+        for j in range(n_lon):
+            a, b = i * n_lon + j + 1, i * n_lon + (j + 1) % n_lon + 1
+            c, d = a + n_lon, b + n_lon
+            lines.append(f"f {a} {b} {d} {c}")  # a quad: the loader fans it into two triangles like tobj
+    return "\n".join(lines) + "\n"
+
+
+def test_hierarchy_path_is_bit_identical_on_the_cornell_box(view, scene):
+    """LINON_OPT_FORCE_BVH stages the same 36 faces as a hierarchy in global memory: same frames, same step counters."""
+    for fn in (PredefinedFunction.MirageSpherical, PredefinedFunction.TranslationX):
+        for flags in (0, capi.RENDER_ADAPTIVE_OFF, capi.RENDER_ENHANCE):
+            if flags == capi.RENDER_ENHANCE and fn != PredefinedFunction.MirageSpherical:
+                continue
+            view.set_option(capi.OPT_FORCE_BVH, 0)
+            a = render(view, fn, flags=flags, math=capi.MATH_STRICT)
+            ca = view.counters()
+            view.set_option(capi.OPT_FORCE_BVH, 1)
+            try:
+                b = render(view, fn, flags=flags, math=capi.MATH_STRICT)
+                cb = view.counters()
+            finally:
+                view.set_option(capi.OPT_FORCE_BVH, 0)
+            for k in a:
+                assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), (fn, flags, k)
+            assert (ca.accepted_steps, ca.prehit_steps, ca.rejected_steps) == (cb.accepted_steps, cb.prehit_steps, cb.rejected_steps)
+
+
+def test_large_obj_mesh_matches_the_oracles_loop_over_every_face(product_lib, oracle, scene):
+    """An OBJ model of 2304 triangles (a sphere in the box) plus the box itself: 2340 faces, beyond the shared-memory stage.
+    The exact hierarchy traversal must reproduce the reference's loop over all faces (the oracle) bit for bit in strict mode,
+    including the lowest-index tie-break on shared edges, and meet the north star in fast mode."""
+    from linon_b200.main_view import load_obj
+    sv, sf, _ = load_obj(uv_sphere_obj())                      # the drop path normalises the sphere on its own ...
+    assert sf.shape[0] == 24 * 48 * 2 and np.abs(sv).max() == 1.0
+    # ... so build the combined scene in box units and normalise once, like Application::load_model does
+    text = uv_sphere_obj()
+    bv = scene_box_units()
+    lines = ["v %.6f %.6f %.6f" % tuple(p) for p in bv[0]] + ["f %d %d %d" % tuple(int(i) + 1 for i in f) for f in bv[1]]
+    n_box = bv[0].shape[0]
+    shifted = []
+    for ln in text.splitlines():
+        if ln.startswith("f "):
+            shifted.append("f " + " ".join(str(int(t) + n_box) for t in ln.split()[1:]))
+        else:
+            shifted.append(ln)
+    verts, faces, center = load_obj("\n".join(lines + shifted) + "\n")
+    assert faces.shape[0] == 36 + 2304
+    W, H = 96, 72
+    with MainView(verts, faces, center, W, H) as mv:
+        cam = camera_dict(mv.camera.uniform())
+        for fn, adaptive in ((PredefinedFunction.TranslationX, False), (PredefinedFunction.MirageSpherical, True)):
+            st = make_settings()
+            ref = oracle.march(verts, faces, cam, settings_dict(st), int(fn), W, H, h_initial=0.1, adaptive=adaptive)
+            got = render(mv, fn, flags=0 if adaptive else capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT)
+            assert np.array_equal(got["hit_id"], ref["hit_id"])
+            assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+            assert (got["hit_id"] >= 36).mean() > 0.05  # the sphere is really hit
+            c = mv.counters()
+            assert c.accepted_steps == int(ref["accepted"].sum()) and c.prehit_steps == int(ref["prehit"].sum())
+            assert c.face_tests < 0.05 * c.prehit_steps * faces.shape[0]  # the traversal prunes: < 5 % of a full loop
+            fast = render(mv, fn, flags=0 if adaptive else capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_FAST)
+            m = parity.compare_frames(fast, ref, n_faces=faces.shape[0])
+            assert m["hit_raw_agree"] >= 0.99 and m["colour_within_1"] >= 0.99, m
+        # Enhance on the large mesh: property check (5001 steps per ray) and agreement of the two math modes
+        mv.render_high_accuracy(PredefinedFunction.MirageSphericalSigmoid.to_code())
+        mv.sync()
+        c = mv.counters()
+        assert c.accepted_steps == W * H * 5001
+        assert (mv.hit_ids() >= 36).mean() > 0.05
+
+
+def scene_box_units():
+    """The Cornell box before normalisation, x and z negated like Application::new (src/application.rs:105-111)."""
+    import ctypes as C
+    verts = np.zeros((72, 3), np.float32)
+    faces = np.zeros((36, 3), np.uint32)
+    center = np.zeros(3, np.float32)
+    capi.lib().linon_host_default_scene(verts.ctypes.data, faces.ctypes.data, center.ctypes.data, 1)
+    # undo the normalisation: x = (n + 1) / 2 * (max - min) + min with the box's global min / max (SURVEY F12)
+    mn, mx = -559.2, 548.8
+    return ((verts.astype(np.float64) + 1.0) / 2.0 * (mx - mn) + mn).astype(np.float32), faces
