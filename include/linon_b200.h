@@ -85,7 +85,9 @@ enum {
                                     with lane refill, 2 two rays per thread on the packed fp32 instructions of sm_100
                                     (FFMA2/FMUL2/FADD2) in 16x4 tiles; a user body that does not instantiate for two rays at
                                     once (data-dependent control flow) falls back to 0 automatically
-                                    (linon_timings.march_kernel tells which kernel ran).  Default 0: measured fastest - FFMA2
+                                    (linon_timings.march_kernel tells which kernel ran), 3 persistent warps in ONE phase: a lane
+                                    carries a ray from its first step to t > 5 and then takes the next slot of a chunked cursor
+                                    (made for adaptive frames; within +-15 % of the tile kernel there).  Default 0: measured fastest - FFMA2
                                     occupies the issue port for two cycles on B200, so packing does not relieve the
                                     issue-slot bound (profiles/r1_ffma2_microbench.md) */
     LINON_OPT_BLOCK = 2,         /* threads per CTA of the march kernel (multiple of 32). Default 256 */
@@ -127,7 +129,7 @@ typedef struct linon_timings { /* CUDA-event times of the last render, milliseco
     int32_t march_grid;         /* CTAs launched */
     int32_t march_block;        /* threads per CTA */
     float march_phase_a_ms;     /* persistent kernel: time of the pre-hit phase (march_ms covers both phases) */
-    int32_t march_kernel;       /* the kernel that ran: 0 tiles, 1 persistent, 2 pairs */
+    int32_t march_kernel;       /* the kernel that ran: 0 tiles, 1 persistent (two phases), 2 pairs, 3 persistent (one phase) */
 } linon_timings;
 
 /* MainView::new (src/main_view.rs:82-458): allocates textures/buffers for width x height on CUDA device

@@ -59,6 +59,9 @@
 #ifndef LINON_REFILL_MIN
 #define LINON_REFILL_MIN 1
 #endif
+#ifndef LINON_REFILL_CHUNK
+#define LINON_REFILL_CHUNK 64u  // ray slots a warp of linon_march_refill takes from the global cursor at once (2 tiles)
+#endif
 #ifndef LINON_GROUP_UNROLL
 #define LINON_GROUP_UNROLL 5
 #endif
@@ -302,15 +305,27 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
 #pragma unroll LINON_GROUP_UNROLL
     for (int g = 0; g < LINON_N_GROUPS; ++g) {
         const float4 pl = s_plane[g];
-        const float dist = fabsf(__fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w))));
+        const float sigma = __fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w)));
+        const float dist = fabsf(sigma);
         nearest = fminf(nearest, dist);
         if (dist <= reach) {
-            const int range = s_range[g];
-            const int first = range & 0xffff, last = first + (range >> 16);
+            // Second look, only for groups in reach: the segment must also CROSS the plane.  With long steps (h = 0.1)
+            // most planes in reach are approached obliquely or left behind; their face tests ran with one or two
+            // active lanes each and made default-step frames three times dearer than the arithmetic (ncu: 10.7 of 32
+            // lanes active).  sigma is the signed distance at the origin, sigma_end at the end of the segment
+            // (direction is a unit vector); same sign and both farther than the margin -> no face of the group can
+            // report t in (eps, max_dist).  The margin is 20x the absolute slack of the reach test.
+            const float sigma_end = __fmaf_rn(__fmaf_rn(direction.x, pl.x, __fmaf_rn(direction.y, pl.y, direction.z * pl.z)),
+                                              max_dist, sigma);
+            const bool same_side = sigma * sigma_end > 0.0f && fminf(dist, fabsf(sigma_end)) > 2e-4f * (1.0f + origin_l1);
+            if (!same_side) {
+                const int range = s_range[g];
+                const int first = range & 0xffff, last = first + (range >> 16);
 #pragma unroll 1
-            for (int i = first; i < last; ++i) {
-                test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
-                ++face_tests;
+                for (int i = first; i < last; ++i) {
+                    test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
+                    ++face_tests;
+                }
             }
         }
     }
@@ -747,6 +762,115 @@ __device__ __forceinline__ unsigned int lane_rank(unsigned int mask) { return __
 #define PF_END(acc, name)
 #define PF_FLUSH(base)
 #endif
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel 3: persistent warps, ONE phase.  Every lane carries a ray from its first step to t > 5 (pre-hit and post-hit
+// in the same lane, like the tile kernel); a lane whose ray finishes takes the next ray slot from a global cursor
+// (one warp-aggregated atomicAdd per refill, and only once LINON_REFILL_MIN lanes are idle).  Made for ADAPTIVE frames:
+// with adaptive sampling on, accepted + rejected attempts per ray spread from 52 to several thousand between
+// neighbouring pixels (rounding-noise driven), so a tile warp idles most of its lanes while the slowest ray
+// finishes.  Fixed-step frames have no such spread and stay on the tile kernel.
+// ------------------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_refill(const MarchParams P) {
+    LINON_MESH_PROLOGUE(P)
+
+    const unsigned int lane = threadIdx.x & 31;
+    const WgslCamera cam = make_camera(P);
+    const WgslSettings st = P.settings;
+    unsigned int* const w_next = P.work + 0;
+
+    Ray r;
+    r.p = r.dir = r.sdir = r.last_v = vec3f(0.0f, 0.0f, 0.0f);
+    r.t = 0.0f; r.h = LINON_H_INITIAL; r.last_diff = -1.0f;
+    int pix = -1;
+    bool alive = false, has_color = false;
+    bool fresh_left = true;  // warp-uniform
+    SafeDistance sd;
+    sd.reset();
+    vec3f color(0.0f, 0.0f, 0.0f);
+    int hit = -1;
+    unsigned int steps = 0u;  // accepted steps of the ray this lane carries
+    unsigned int chunk_next = 0u, chunk_end = 0u;  // warp-uniform: the slots this warp still owns
+    StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
+
+    for (;;) {
+        const unsigned int idle = __ballot_sync(0xffffffffu, !alive);
+        if (fresh_left && (__popc(idle) >= LINON_REFILL_MIN)) {
+            // ray slots come in chunks of 2 tiles: ONE global atomicAdd per 64 rays (a single cursor address serialises
+            // at ~10 ns per atomic in L2 - with one atomic per refill that alone cost more than the march), then the warp
+            // hands the chunk out from registers
+            if (chunk_next >= chunk_end) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(w_next, LINON_REFILL_CHUNK);
+                chunk_next = __shfl_sync(0xffffffffu, base, 0);
+                chunk_end = min(chunk_next + LINON_REFILL_CHUNK, P.n_ray_slots);
+                if (chunk_next >= P.n_ray_slots) {
+                    fresh_left = false;
+                    chunk_end = chunk_next;
+                }
+            }
+            const unsigned int rank = lane_rank(idle);
+            if (!alive && chunk_next + rank < chunk_end) {
+                const unsigned int slot = chunk_next + rank;
+                int x, local_row;
+                if (slot_to_pixel(P, slot, x, local_row)) {
+                    init_ray(P, x, local_row, r);
+                    sd.reset();
+                    pix = texture_row(P, local_row) * P.width + x;
+                    alive = true;
+                    has_color = false;
+                    color = vec3f(0.0f, 0.0f, 0.0f);
+                    hit = -1;
+                    steps = 0u;
+                }
+            }
+            chunk_next = min(chunk_next + (unsigned int)__popc(idle), chunk_end);
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u) {
+            if (fresh_left) continue;
+            break;
+        }
+        if (alive) {
+            vec3f v, step_dir;
+            float diff;
+            if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
+                if (!has_color) {
+                    const float step_cost = sd.cost(step_dir);
+                    if (__any_sync(__activemask(), sd.must_check(step_cost))) {
+                        const float max_dist = w_length(step_dir);
+                        const vec3f dirn = w_normalize(step_dir);
+                        const float p_l1 = l1_norm(r.p);
+                        float t_hit, nearest;
+                        int id;
+                        intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                        ++cnt.checks;
+                        sd.checked(nearest, p_l1, P.plane_w_max);
+                        if (t_hit > 0.0f && t_hit < max_dist) {
+                            color = shade(s_tri, id, dirn);
+                            hit = LINON_FACE_ID(s_tri, id);
+                            has_color = true;
+                            cnt.prehit += steps + 1;
+                        }
+                    }
+                    sd.moved(step_cost);
+                }
+                rk4_advance(r, v, diff, step_dir);
+                ++steps;
+                ++cnt.accepted;
+                if (!(r.t <= 5.0f)) {
+                    if (!has_color) cnt.prehit += steps;
+                    P.raycast[pix] = pack_color(color);
+                    P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+                    P.hit_id[pix] = hit;
+                    alive = false;
+                }
+            } else {
+                ++cnt.rejected;
+            }
+        }
+    }
+    flush_counters(P, cnt);
+}
 
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_phase_a(const MarchParams P) {
     LINON_MESH_PROLOGUE(P)

@@ -133,9 +133,9 @@ struct Variant {
 
 struct Module {
     CUmodule mod = nullptr;
-    CUfunction tiles = nullptr, pairs = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr,
+    CUfunction tiles = nullptr, pairs = nullptr, refill = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr,
                eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr;
-    int regs_tiles = 0, regs_pairs = 0, regs_phase_a = 0, regs_phase_b = 0;
+    int regs_tiles = 0, regs_pairs = 0, regs_refill = 0, regs_phase_a = 0, regs_phase_b = 0;
 };
 
 // The translated body becomes LinonField<S>::eval.  The member typedefs re-declare the type names the translator
@@ -394,7 +394,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
     struct { const char* name; CUfunction* f; } fns[] = {
         {"linon_march_tiles", &m.tiles},       {"linon_march_phase_a", &m.phase_a},
-        {"linon_march_pairs", var.pairs ? &m.pairs : nullptr},
+        {"linon_march_pairs", var.pairs ? &m.pairs : nullptr}, {"linon_march_refill", &m.refill},
         {"linon_march_phase_b", &m.phase_b},   {"linon_sample_rays", &m.sample},
         {"linon_eval_field", &m.eval_field},   {"linon_eval_helper", &m.eval_helper},
         {"linon_eval_hit_triangle", &m.eval_hit}};
@@ -408,6 +408,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     }
     g_drv.FuncGetAttribute(&m.regs_tiles, CU_FUNC_ATTRIBUTE_NUM_REGS, m.tiles);
     if (m.pairs) g_drv.FuncGetAttribute(&m.regs_pairs, CU_FUNC_ATTRIBUTE_NUM_REGS, m.pairs);
+    g_drv.FuncGetAttribute(&m.regs_refill, CU_FUNC_ATTRIBUTE_NUM_REGS, m.refill);
     g_drv.FuncGetAttribute(&m.regs_phase_a, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_a);
     g_drv.FuncGetAttribute(&m.regs_phase_b, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_b);
     const auto t1 = std::chrono::steady_clock::now();
@@ -872,7 +873,8 @@ int linon_render(linon_view* v, uint32_t flags) {
         const unsigned block = (unsigned)v->opt_block;
         const bool use_pairs = v->opt_kernel == 2 && mod->pairs != nullptr;
         const unsigned needed = ((use_pairs ? P.n_pair_slots : P.n_ray_slots) + block - 1) / block;
-        v->timings.march_kernel = use_pairs ? 2 : ((v->opt_kernel == 1 && !v->use_bvh) ? 1 : 0);
+        const bool use_refill = v->opt_kernel == 3;
+        v->timings.march_kernel = use_pairs ? 2 : ((v->opt_kernel == 1 && !v->use_bvh) ? 1 : (use_refill ? 3 : 0));
         v->timings.march_block = (int)block;
         CK(v, cudaEventRecord(v->ev[0], v->stream));
         if (v->opt_kernel == 1 && !v->use_bvh) {
@@ -898,6 +900,19 @@ int linon_render(linon_view* v, uint32_t flags) {
             v->timings.march_regs = mod->regs_phase_a;
             v->timings.march_grid = (int)grids[0];
             v->ran_phases = true;
+        } else if (use_refill) {
+            CK(v, cudaMemsetAsync(v->d_work, 0, 64, v->stream));
+            int per_sm = v->opt_ctas_per_sm;
+            if (per_sm <= 0) {
+                const CUresult r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mod->refill, (int)block, 0);
+                if (r != CUDA_SUCCESS || per_sm <= 0) return v->fail(LINON_ERR_CUDA, "occupancy query failed: " + g_drv.err_str(r));
+            }
+            unsigned grid = (unsigned)(per_sm * v->sm_count);
+            if (grid > needed) grid = needed;
+            const int rc = launch(v, mod->refill, grid, block, v->stream, &P);
+            if (rc != LINON_OK) return rc;
+            v->timings.march_regs = mod->regs_refill;
+            v->timings.march_grid = (int)grid;
         } else if (use_pairs) {
             const int rc = launch(v, mod->pairs, needed, block, v->stream, &P);
             if (rc != LINON_OK) return rc;
@@ -984,7 +999,7 @@ int linon_set_option(linon_view* v, int option, int value) {
     if (!v) return LINON_ERR_INVALID;
     switch (option) {
         case LINON_OPT_MATH: if (value < 0 || value > 2) break; v->opt_math = value; return LINON_OK;
-        case LINON_OPT_KERNEL: if (value < 0 || value > 2) break; v->opt_kernel = value; return LINON_OK;
+        case LINON_OPT_KERNEL: if (value < 0 || value > 3) break; v->opt_kernel = value; return LINON_OK;
         case LINON_OPT_PAIR_MIN_BLOCKS: if (value < 0 || value > 32) break; v->opt_pair_min_blocks = value; return LINON_OK;
         case LINON_OPT_SPECIALIZE: if (value < 0 || value > 1) break; v->opt_specialize = value; return LINON_OK;
         case LINON_OPT_FORCE_BVH:

@@ -33,7 +33,7 @@ def view(product_lib, scene):
     mv.close()
 
 
-KERNELS = [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS]
+KERNELS = [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL]
 
 
 def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_TILES, cull=1, settings=None, specialize=1):
@@ -108,7 +108,7 @@ def test_all_march_kernels_agree_in_strict_mode(view, fn, flags):
     rays per thread (f32x2 done per component in strict mode) give bit-identical frames and counters."""
     a = render(view, fn, flags=flags, math=capi.MATH_STRICT, kernel=capi.KERNEL_TILES)
     ca = view.counters()
-    for kernel in (capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS):
+    for kernel in (capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL):
         b = render(view, fn, flags=flags, math=capi.MATH_STRICT, kernel=kernel)
         cb = view.counters()
         for k in a:
