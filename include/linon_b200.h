@@ -194,6 +194,11 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
  * 8 reflect 9 normalize 10 cross. */
 int linon_debug_eval_field(linon_view* v, uint32_t n, const float* p_prev, const float* p, const float* v0,
                            const float* vel, const float* t, float* out);
+/* One Runge-Kutta velocity v = (k1 + 2 k2 + 2 k3 + k4) / 6 (src/main_view.wgsl:246-251) per element for the CURRENT field
+ * function, through the device function the march kernels call (in fast math mode: the whole-step restatement of the
+ * predefined mirage bodies).  p, dir, v0: n x 3 f32; t, h: n f32. */
+int linon_debug_eval_rk4(linon_view* v, uint32_t n, const float* p, const float* dir, const float* v0, const float* t,
+                         const float* h, float* out);
 int linon_debug_eval_helper(linon_view* v, int which, uint32_t n, const float* vec, const float* nrm, const float* p0,
                             const float* a, const float* b, const float* c, float* out);
 int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const float* origin, const float* dir,

@@ -82,6 +82,7 @@ PROTOTYPES = [
     ("linon_translate_wgsl", _I, [_CP, _P, _S, _P, _S]),
     ("linon_compile_check", _I, [_CP, _U, _I, _U, C.POINTER(_S), _P, _S]),
     ("linon_debug_eval_field", _I, [_P, _U, _P, _P, _P, _P, _P, _P]),
+    ("linon_debug_eval_rk4", _I, [_P, _U, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_eval_helper", _I, [_P, _I, _U, _P, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_hit_triangle", _I, [_P, _U, _P, _P, _P, _P]),
     ("linon_debug_profile", _I, [_P, _P]),

@@ -89,6 +89,12 @@
 #ifndef LINON_STAGE1_IDENTITY
 #define LINON_STAGE1_IDENTITY 0  // 1: the field body guarantees f(p_prev = p, v) = v, so Runge-Kutta stage 1 is not evaluated
 #endif
+#ifndef LINON_FUSED_RK4
+#define LINON_FUSED_RK4 0  // 1: the field body provides LinonField<S>::rk4, one whole Runge-Kutta step as a single expression
+#endif
+#ifndef LINON_STRICT_MATH
+#define LINON_STRICT_MATH 0  // 1: the bit-comparable build (--fmad=false ...): no explicit FMA either
+#endif
 #ifndef LINON_PAIR_MIN_BLOCKS
 #define LINON_PAIR_MIN_BLOCKS (512 / LINON_BLOCK)  // 16 resident warps / SM = 32 rays per scheduler slot pair: <= 128 registers
 #endif
@@ -124,6 +130,8 @@ struct MarchParams {
     float plane_w_max;            // max |plane offset| over the plane groups / max |coordinate| of a BVH mesh
                                   // (rounding bound of SafeDistance)
     const float4* bvh;            // LINON_BVH: 2 x float4 per node {lo.xyz, left child | first slot}, {hi.xyz, 0 | face count}
+    int n_fixed_steps;            // !LINON_ADAPTIVE: iterations of the reference's `t <= 5` loop for h = LINON_H_INITIAL (the
+                                  // host runs the same fp32 recurrence once: 5001 for 0.001, 51 for 0.1)
 };
 
 template <class S> struct RayT {
@@ -186,6 +194,9 @@ __device__ __forceinline__ WgslCamera make_camera(const MarchParams& P) {
 // h is a float (compile-time constant or uniform) or per-ray (adaptive sampling in the pair kernel).
 template <class S, class H>
 __device__ __forceinline__ vec3t<S> rk4_velocity(const RayT<S>& r, H h, const WgslSettings& st, const WgslCamera& cam) {
+#if LINON_FUSED_RK4
+    return LinonField<S>::rk4(r.p, r.dir, h);  // the spliced body restates the whole step (mirage_fused.cuh)
+#endif
 #if LINON_STAGE1_IDENTITY
     const vec3t<S> k1 = r.dir;  // the spliced body declares field(p, p, v0, v, t) == v (mirage_fused.cuh)
 #else
@@ -376,6 +387,9 @@ struct SafeDistance {
         drift = __fmul_ru(2e-7f, c);
     }
     __device__ __forceinline__ void moved(float step_cost) { budget = __fsub_rd(budget, step_cost); }
+    // what the budget will be after this step; the face loop must run when it is not positive (same test as must_check)
+    __device__ __forceinline__ float left(float step_cost) const { return __fsub_rd(budget, step_cost); }
+    __device__ __forceinline__ void retire() { budget = __int_as_float(0x7f800000); }  // the ray has hit: never check again
 };
 __device__ __forceinline__ float l1_norm(vec3f p) { return fabsf(p.x) + fabsf(p.y) + fabsf(p.z); }
 
@@ -506,13 +520,113 @@ __device__ __forceinline__ void rk4_advance(Ray& r, vec3f v, float diff, vec3f s
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1: one thread per pixel.
 // ------------------------------------------------------------------------------------------------------------
+// src/main_view.wgsl:264 in the production builds is one FFMA per component; the strict build rounds step_dir first,
+// like the reference's two statements (:257, :264).
+__device__ __forceinline__ vec3f advance_point(vec3f p, vec3f dir, float h) {
+#if LINON_STRICT_MATH
+    return p + dir * h;
+#else
+    return vec3f(__fmaf_rn(dir.x, h, p.x), __fmaf_rn(dir.y, h, p.y), __fmaf_rn(dir.z, h, p.z));
+#endif
+}
+
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_tiles(const MarchParams P) {
     LINON_MESH_PROLOGUE(P)
 
     const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
     int x, local_row;
-    const bool valid = slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row);
     StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
+#if !LINON_ADAPTIVE
+    // Fixed step (Enhance, or adaptive sampling switched off): every ray runs the same P.n_fixed_steps iterations, so
+    // the whole warp stays converged from the first step to the last.  Padding lanes outside the frame repeat the nearest
+    // pixel and store nothing.  That makes every vote a full-mask vote and splits the loop by WARP phase:
+    //   searching   some lane has not hit yet.  All lanes keep the safe-distance budget (a lane that has hit carries
+    //               +inf), ONE vote per step decides whether the face loop runs, and the common path has no divergent
+    //               branch at all (no BSSY/BSYNC pair, no per-lane has_color test);
+    //   coasting    every lane has hit: the loop is the Runge-Kutta step and nothing else.
+    // A ray's arithmetic is the same in both phases (advance_point, rk4_velocity), so its result does not depend on its
+    // neighbours; only the counters of executed tests do, as before.
+    if (P.local_rows <= 0) return;
+    const bool valid = slot_to_pixel(P, slot, x, local_row) && slot < P.n_ray_slots;
+    x = min(x, P.width - 1);
+    local_row = min(local_row, P.local_rows - 1);
+    {
+        const WgslCamera cam = make_camera(P);
+        const WgslSettings st = P.settings;
+        const float h = LINON_H_INITIAL;
+        Ray r;
+        init_ray(P, x, local_row, r);
+        bool has_color = false;
+        SafeDistance sd;
+        sd.reset();
+        vec3f color(0.0f, 0.0f, 0.0f);
+        int hit = -1;
+        const int n_steps = P.n_fixed_steps;
+        int i = 0;
+        bool searching = true;  // warp-uniform
+        for (; i < n_steps && searching; ++i) {
+            const vec3f v = rk4_velocity(r, h, st, cam);
+#if LINON_FW_ONE
+            r.dir = v;  // field_weight == 1: (1 - 1) * cur_dir + 1 * v
+#else
+            r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+#endif
+            const vec3f step_dir = r.dir * h;
+            const float step_cost = sd.cost(step_dir);
+            float left = sd.left(step_cost);
+            // Warp-coherent checks (see the adaptive loop below): when one lane's budget expires every searching lane of
+            // the warp refreshes its budget with it.
+#if LINON_CULL
+            if (__any_sync(0xffffffffu, !(left > 0.0f)))
+#endif
+            {
+                if (!has_color) {
+                    const float max_dist = w_length(step_dir);
+                    const vec3f dirn = w_normalize(step_dir);
+                    const float p_l1 = l1_norm(r.p);
+                    float t_hit, nearest;
+                    int id;
+                    intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                    ++cnt.checks;
+                    sd.checked(nearest, p_l1, P.plane_w_max);
+                    left = sd.left(step_cost);
+                    if (t_hit > 0.0f && t_hit < max_dist) {
+                        color = shade(s_tri, id, dirn);
+                        hit = LINON_FACE_ID(s_tri, id);
+                        has_color = true;        // result.color.a = t > 0
+                        cnt.prehit = i + 1;      // accepted steps that ran the pre-hit path, this one included
+                        left = __int_as_float(0x7f800000);  // +inf: this lane never asks for a check again
+                    }
+                }
+                searching = __any_sync(0xffffffffu, !has_color);
+            }
+            sd.budget = left;
+            r.p = advance_point(r.p, r.dir, h);
+            r.t = r.t + h;
+        }
+        for (; i < n_steps; ++i) {
+            const vec3f v = rk4_velocity(r, h, st, cam);
+#if LINON_FW_ONE
+            r.dir = v;
+#else
+            r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
+#endif
+            r.p = advance_point(r.p, r.dir, h);
+            r.t = r.t + h;
+        }
+        cnt.accepted = n_steps;
+        if (!has_color) cnt.prehit = n_steps;
+        if (valid) {
+            const size_t pix = (size_t)texture_row(P, local_row) * P.width + x;
+            P.raycast[pix] = pack_color(color);  // black when !has_color, alpha = 1 (src/main_view.wgsl:274-277)
+            P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+            P.hit_id[pix] = hit;
+        } else {
+            cnt.accepted = cnt.prehit = cnt.rejected = cnt.face_tests = cnt.checks = 0u;
+        }
+    }
+#else
+    const bool valid = slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row);
     if (valid) {
         const WgslCamera cam = make_camera(P);
         const WgslSettings st = P.settings;
@@ -565,6 +679,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
         P.hit_id[pix] = hit;
     }
+#endif
     flush_counters(P, cnt);
 }
 
@@ -1112,6 +1227,25 @@ extern "C" __global__ void linon_eval_field(int n, const float* p_prev, const fl
     WgslCamera cam;
     const vec3f r = field_function<float>(ld3(p_prev + 3 * i), ld3(p + 3 * i), ld3(v0 + 3 * i), ld3(v + 3 * i), t[i], st, cam);
     out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+}
+
+// One Runge-Kutta velocity (src/main_view.wgsl:246-251) per element, through the SAME rk4_velocity the march kernels call
+// (generic four-stage evaluation, or the whole-step restatement of mirage_fused.cuh): v0 = start direction, h per element.
+extern "C" __global__ void linon_eval_rk4(int n, const float* p, const float* dir, const float* v0, const float* t,
+                                          const float* h, WgslSettings st, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    WgslCamera cam;
+    Ray r;
+    r.p = ld3(p + 3 * i);
+    r.dir = ld3(dir + 3 * i);
+    r.sdir = ld3(v0 + 3 * i);
+    r.t = t[i];
+    r.h = h[i];
+    r.last_v = vec3f(0.0f, 0.0f, 0.0f);
+    r.last_diff = -1.0f;
+    const vec3f v = rk4_velocity<float, float>(r, r.h, st, cam);
+    out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
 }
 
 // which: 0 rotateX 1 rotateY 2 rotateZ 3 translate 4 refraction 5 point_plane_distance 6 sigmoid 7 refraction_index

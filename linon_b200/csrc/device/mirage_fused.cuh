@@ -27,11 +27,26 @@
 //     (k = cosi^2, the normal term cancels).  The reference's own evaluation returns v plus rounding noise of its
 //     1 - (1 - cosi^2) formulation; the fast build returns v, i.e. k1 = cur_dir, and evaluates three stages per step.
 //     Only the work actually executed is counted in the roofline numerator (linon_b200/flops.py).
+//
+//   * LINON_FUSED_RK4: the march kernels call LinonField<S>::rk4 - one Runge-Kutta step (src/main_view.wgsl:246-251) of
+//     this body as ONE expression - instead of three eval() calls.  Same real-number function, fewer issue slots
+//     (the kernel is issue-bound, profiles/):
+//       - the distance profile runs in scaled coordinates c' = s (p - centre) with s = 12 log2(e) / max_dist (sigmoid)
+//         or 1 / max_dist (linear), so E = exp2(k0 - |c'|) is one FFMA + MUFU.EX2 on (q, rsqrt q), every stage point is
+//         ONE FFMA per component from the step's scaled origin (s h k + c'_prev), and the normal c' / |c'| is unchanged;
+//       - A and B are divided by their slopes: a~ = u + A1/A2, b~ = u + B1/B2 (u = E or min(1, |c'|)); the slopes cancel
+//         in eta = a~(in) b~(out) / (a~(out) b~(in)), so two FFMAs with register constants become two FADDs with immediates;
+//       - the normal is never materialised: d = (v . c') rq and the refracted direction is eta v + (cs rq) c';
+//       - stage 4 is accumulated straight into k1 + 2 k2 + 2 k3 (two FFMAs per component, no k4);
+//       - total reflection (k < 0, a thin band of grazing rays) is detected once per step on min(k2, k3, k4); such a step
+//         is recomputed by the same code with the reflect() select compiled in, behind a real branch, instead of four
+//         predicated instructions in each stage of every step.  A ray's result does not depend on which copy ran.
 
 #ifndef LINON_MIRAGE_KIND
 #error "mirage_fused.cuh needs -DLINON_MIRAGE_KIND=1..4"
 #endif
 #define LINON_STAGE1_IDENTITY 1
+#define LINON_FUSED_RK4 1
 
 template <class S> struct LinonField {
     // refraction (src/main_view.wgsl:119-136) for a given eta and d = dot(v, n); see refraction_s in wgsl_prelude.cuh
@@ -113,5 +128,158 @@ template <class S> struct LinonField {
         if (__builtin_expect(s_any(total), 0)) r = w_select(r, vec3t<S>(v.x, -v.y, v.z), total);
         return r;
 #endif
+    }
+    // ---- LINON_FUSED_RK4 -------------------------------------------------------------------------------------------
+    // profile constants in slope-normalised form (see the header): u + RA, u + RB
+    struct Fused {
+        static constexpr float t_env = 15.0f;
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+        static constexpr float t_src = 200.0f, max_dist = 0.25f;
+#else
+        static constexpr float t_src = 30.0f, max_dist = 0.01f;
+#endif
+        static constexpr float c1p = 0.0000104f * 101325.0f;
+        static constexpr float a0 = c1p * (1.0f + 101325.0f * 1e-10f * 60.1f);
+        static constexpr float a1 = c1p * 101325.0f * 1e-10f * 0.972f;
+        static constexpr float c2 = 0.00366f;
+#if LINON_MIRAGE_KIND >= 3
+        static constexpr float log2e = 1.4426950408889634f;
+        static constexpr float scale = 12.0f / max_dist * log2e;  // E = exp2(k0 - scale dist)
+        static constexpr float k0 = 6.0f * log2e;
+        static constexpr float RA = (a0 - t_env * a1) / (a0 - t_src * a1);
+        static constexpr float RB = (1.0f + t_env * c2) / (1.0f + t_src * c2);
+#else
+        static constexpr float scale = 1.0f / max_dist;           // part = min(1, scale dist)
+        static constexpr float RA = (a0 - a1 * t_src) / (a1 * (t_src - t_env));
+        static constexpr float RB = (1.0f + c2 * t_src) / (-c2 * (t_src - t_env));
+#endif
+        static constexpr float D = RB - RA;  // b~ / a~ = 1 + D / (u + RA)
+    };
+
+    // sign transfer for a magnitude m >= +0: m with the sign bit of s (one LOP3 instead of a compare and a negation).
+    // Differs from `s < 0 ? -m : m` only for s == -0.0, which min(1, dot) cannot produce from non-zero operands.
+    static __device__ __forceinline__ float with_sign_of(float m, float s) {
+        return __int_as_float(__float_as_int(m) | (__float_as_int(s) & (int)0x80000000));
+    }
+    static __device__ __forceinline__ f32x2 with_sign_of(f32x2 m, f32x2 s) {
+        return f32x2(with_sign_of(m.lo, s.lo), with_sign_of(m.hi, s.hi));
+    }
+    static __device__ __forceinline__ float min3(float a, float b, float c) {
+#if __CUDACC_VER_MAJOR__ > 12 || (__CUDACC_VER_MAJOR__ == 12 && __CUDACC_VER_MINOR__ >= 9)
+        float r;
+        asm("min.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3 (sm_100); NVRTC 12.8 rejects it
+        return r;
+#else
+        return fminf(fminf(a, b), c);
+#endif
+    }
+    static __device__ __forceinline__ f32x2 min3(f32x2 a, f32x2 b, f32x2 c) {
+        return f32x2(min3(a.lo, b.lo, c.lo), min3(a.hi, b.hi, c.hi));
+    }
+
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+    typedef vec3t<S> Pos;  // scaled offset from the sphere centre
+    static __device__ __forceinline__ Pos scaled_origin(const vec3t<S> p) {
+        return vec3t<S>(p.x * Fused::scale + 0.5f * Fused::scale, p.y * Fused::scale - 0.5f * Fused::scale,
+                        p.z * Fused::scale + 0.5f * Fused::scale);  // scale (p - (-0.5, 0.5, -0.5))
+    }
+    // u(|c'|) from q = c'.c' and rq = rsqrt(q)
+    static __device__ __forceinline__ S profile(S q, S rq) {
+#if LINON_MIRAGE_KIND == 3
+        return w_exp2(Fused::k0 - q * rq);
+#else
+        return w_min(1.0f, q * rq);
+#endif
+    }
+#else
+    typedef S Pos;         // scaled signed height above the plane y = 0.1
+    static __device__ __forceinline__ Pos scaled_origin(const vec3t<S> p) { return p.y * Fused::scale - 0.1f * Fused::scale; }
+    static __device__ __forceinline__ S profile(S y) {
+#if LINON_MIRAGE_KIND == 4
+        return w_exp2(Fused::k0 - w_abs(y));
+#else
+        return w_min(1.0f, w_abs(y));
+#endif
+    }
+#endif
+
+    // One stage: the field at p_prev + off k_prev with incoming direction k_prev, as the pair (eta, w) of
+    //     k = eta k_prev + w  (w = (cs rq) c' for the sphere, (0, cs, 0) for the plane); kk = Snell's discriminant.
+    // EXACT = true compiles the reflect() select in; EXACT = false leaves a NaN in a totally reflected stage (kk < 0),
+    // which rk4() detects and recomputes.
+    template <bool EXACT, bool ACC, class H>
+    static __device__ __forceinline__ vec3t<S> stage(const Pos pc, const vec3t<S> kp, const H off_scaled, const S g_in,
+                                                     const S gd_in, S& kk, const vec3t<S> acc) {
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+        const vec3t<S> c(pc.x + off_scaled * kp.x, pc.y + off_scaled * kp.y, pc.z + off_scaled * kp.z);
+        const S q = w_dot(c, c);
+        const S rq = w_inverseSqrt(q);
+        const S u = profile(q, rq);
+        const S d = w_dot(kp, c) * rq;
+#else
+        const S y = pc + off_scaled * kp.y;
+        const S u = profile(y);
+        const S d = kp.y;
+#endif
+        // eta = g(u) / g(u_in) with g = b~ / a~ = 1 + D / (u + RA):  g_in = 1 / g(u_in), gd_in = D g_in
+        const S eta = g_in + gd_in * (1.0f / (u + Fused::RA));
+        const S cr = w_min(1.0f, d);  // clamp(-1, 1, d) with its misordered arguments
+        kk = 1.0f - eta * eta * (1.0f - cr * cr);
+        const S sk = w_sqrt(kk);
+        const S cs = with_sign_of(sk, cr) - eta * cr;  // (cr < 0 ? -sk : sk) - eta cr
+        // ACC: the stage value is added to acc (the last stage goes straight into the Runge-Kutta sum)
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+        const S csr = cs * rq;
+        vec3t<S> r = ACC ? vec3t<S>(eta * kp.x + (csr * c.x + acc.x), eta * kp.y + (csr * c.y + acc.y), eta * kp.z + (csr * c.z + acc.z))
+                         : vec3t<S>(eta * kp.x + csr * c.x, eta * kp.y + csr * c.y, eta * kp.z + csr * c.z);
+        if (EXACT) {  // reflect(v, n) = v - 2 dot(n, v) n
+            const S two_drq = (2.0f * d) * rq;
+            const vec3t<S> refl(kp.x - two_drq * c.x, kp.y - two_drq * c.y, kp.z - two_drq * c.z);
+            r = w_select(r, ACC ? vec3t<S>(acc + refl) : refl, kk < 0.0f);
+        }
+#else
+        vec3t<S> r = ACC ? vec3t<S>(eta * kp.x + acc.x, eta * kp.y + (cs + acc.y), eta * kp.z + acc.z)
+                         : vec3t<S>(eta * kp.x, eta * kp.y + cs, eta * kp.z);
+        if (EXACT) {
+            const vec3t<S> refl(kp.x, -kp.y, kp.z);
+            r = w_select(r, ACC ? vec3t<S>(acc + refl) : refl, kk < 0.0f);
+        }
+#endif
+        return r;
+    }
+
+    template <bool EXACT, class H>
+    static __device__ __forceinline__ vec3t<S> rk4_sum(const Pos pc, const S g_in, const S gd_in, const vec3t<S> k1, const H h,
+                                                       S& kk_min) {
+        const H half = (0.5f * Fused::scale) * h, full = Fused::scale * h;
+        const vec3t<S> none(0.0f, 0.0f, 0.0f);
+        S kk2, kk3, kk4;
+        const vec3t<S> k2 = stage<EXACT, false>(pc, k1, half, g_in, gd_in, kk2, none);
+        const vec3t<S> k3 = stage<EXACT, false>(pc, k2, half, g_in, gd_in, kk3, none);
+        const vec3t<S> acc = k1 + 2.0f * k2 + 2.0f * k3;
+        const vec3t<S> sum = stage<EXACT, true>(pc, k3, full, g_in, gd_in, kk4, acc);  // acc + k4
+        kk_min = min3(kk2, kk3, kk4);  // NaN (from an earlier totally reflected stage) is ignored by min
+        return sum;
+    }
+
+    // v = (k1 + 2 k2 + 2 k3 + k4) / 6 with k1 = dir (LINON_STAGE1_IDENTITY), src/main_view.wgsl:246-251
+    template <class H>
+    static __device__ __forceinline__ vec3t<S> rk4(const vec3t<S> p, const vec3t<S> dir, const H h) {
+        const Pos pc = scaled_origin(p);
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+        const S q_in = w_dot(pc, pc);
+        const S u_in = profile(q_in, w_inverseSqrt(q_in));
+#else
+        const S u_in = profile(pc);
+#endif
+        const S g_in = 1.0f - Fused::D * (1.0f / (u_in + Fused::RB));  // a~ / b~ at the step's origin
+        const S gd_in = Fused::D * g_in;
+        S kk_min;
+        vec3t<S> sum = rk4_sum<false>(pc, g_in, gd_in, dir, h, kk_min);
+        if (__builtin_expect(s_any(kk_min < 0.0f), 0)) {
+            S unused;
+            sum = rk4_sum<true>(pc, g_in, gd_in, dir, h, unused);
+        }
+        return sum * (1.0f / 6.0f);
     }
 };

@@ -112,6 +112,7 @@ struct MarchParamsH {
     unsigned int n_pair_slots;
     float plane_w_max;
     const void* bvh;
+    int n_fixed_steps;
 };
 struct SampleParamsH {
     MarchParamsH march;
@@ -134,7 +135,7 @@ struct Variant {
 struct Module {
     CUmodule mod = nullptr;
     CUfunction tiles = nullptr, pairs = nullptr, refill = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr,
-               eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr;
+               eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr, eval_rk4 = nullptr;
     int regs_tiles = 0, regs_pairs = 0, regs_refill = 0, regs_phase_a = 0, regs_phase_b = 0;
 };
 
@@ -217,7 +218,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      "-DLINON_BVH=" + std::to_string(var.bvh),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
-                                     "-DLINON_PACKED_OPS=" + std::to_string(var.math == 0 ? 0 : 1)};
+                                     "-DLINON_PACKED_OPS=" + std::to_string(var.math == 0 ? 0 : 1),
+                                     "-DLINON_STRICT_MATH=" + std::to_string(var.math == 0 ? 1 : 0)};
     if (var.pair_min_blocks > 0) opts.push_back("-DLINON_PAIR_MIN_BLOCKS=" + std::to_string(var.pair_min_blocks));
     if (var.math == 0) {
         opts.insert(opts.end(), {"--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
@@ -397,7 +399,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
         {"linon_march_pairs", var.pairs ? &m.pairs : nullptr}, {"linon_march_refill", &m.refill},
         {"linon_march_phase_b", &m.phase_b},   {"linon_sample_rays", &m.sample},
         {"linon_eval_field", &m.eval_field},   {"linon_eval_helper", &m.eval_helper},
-        {"linon_eval_hit_triangle", &m.eval_hit}};
+        {"linon_eval_hit_triangle", &m.eval_hit}, {"linon_eval_rk4", &m.eval_rk4}};
     for (auto& f : fns) {
         if (!f.f) continue;
         r = g_drv.ModuleGetFunction(f.f, m.mod, f.name);
@@ -455,6 +457,20 @@ int get_module_for_body(linon_view* v, const std::string& body, Variant& var, Mo
         (void)pair_error;
     }
     return rc;
+}
+
+// Iterations of `loop { if (t > 5.0) { break; } ...; t = t + h; }` (src/main_view.wgsl:244-266) when h never changes: the
+// same fp32 recurrence, evaluated once on the host (g++ -ffp-contract=off, IEEE binary32 additions), so fixed-step
+// kernels count to an integer instead of comparing a per-lane float.  5001 for h = 0.001, 51 for h = 0.1.
+int fixed_step_count(float h) {
+    if (!(h > 0.0f)) return 0;
+    volatile float t = 0.0f;
+    int n = 0;
+    while (t <= 5.0f && n < (1 << 24)) {
+        t = t + h;
+        ++n;
+    }
+    return n;
 }
 
 void fill_march_params(const linon_view* v, MarchParamsH& P) {
@@ -840,6 +856,7 @@ int linon_render(linon_view* v, uint32_t flags) {
         Variant var = make_variant(v, flags);
         const int rc = get_module_for_body(v, v->body, var, &mod, &v->timings.jit_ms);
         if (rc != LINON_OK) return rc;
+        P.n_fixed_steps = var.adaptive ? 0 : fixed_step_count(var.h_initial);
     }
 
     if (do_sample) {
@@ -1144,6 +1161,26 @@ int linon_debug_eval_field(linon_view* v, uint32_t n, const float* p_prev, const
     void* args[] = {&ni, &a.p, &b.p, &c.p, &d.p, &e.p, &st, &o.p};
     const CUresult r = g_drv.LaunchKernel(m->eval_field, (n + 127) / 128, 1, 1, 128, 1, 1, 0, (CUstream)v->stream, args, nullptr);
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel(eval_field): " + g_drv.err_str(r));
+    CK(v, cudaStreamSynchronize(v->stream));
+    CK(v, cudaMemcpy(out, o.p, n * 12, cudaMemcpyDeviceToHost));
+    return LINON_OK;
+}
+
+int linon_debug_eval_rk4(linon_view* v, uint32_t n, const float* p, const float* dir, const float* v0, const float* t,
+                         const float* h, float* out) {
+    if (!v || !n) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    Module* m = nullptr;
+    int rc = debug_module(v, &m);
+    if (rc != LINON_OK) return rc;
+    DevBuf a, b, c, d, e, o;
+    CK(v, a.up(p, n * 12)); CK(v, b.up(dir, n * 12)); CK(v, c.up(v0, n * 12)); CK(v, d.up(t, n * 4));
+    CK(v, e.up(h, n * 4)); CK(v, o.up(nullptr, n * 12));
+    int ni = (int)n;
+    linon_settings st = v->settings;
+    void* args[] = {&ni, &a.p, &b.p, &c.p, &d.p, &e.p, &st, &o.p};
+    const CUresult r = g_drv.LaunchKernel(m->eval_rk4, (n + 127) / 128, 1, 1, 128, 1, 1, 0, (CUstream)v->stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel(eval_rk4): " + g_drv.err_str(r));
     CK(v, cudaStreamSynchronize(v->stream));
     CK(v, cudaMemcpy(out, o.p, n * 12, cudaMemcpyDeviceToHost));
     return LINON_OK;

@@ -29,23 +29,28 @@ SAFE_STEP = 8          # per pre-hit step with culling on
 CHECK_EXTRA = 5        # reach + bound reset, per culling check
 
 
-# Hand-fused mirage restatements (csrc/device/mirage_fused.cuh, fast math): executed work per accepted step.
-# Stage 1 is the identity (not evaluated), stages 2-4 evaluate the fused body (F_EVAL), the previous point's share
-# (distance, E or part, A, B) is computed once per step (F_PREV).  Counted like the rest: FMA = 2, rsqrt/exp2/sqrt/div = 1.
-#   spherical sigmoid: eval 3 (p - c) + 5 (dot) + 1 (rsqrt) + 3 (normal) + 1 (dist) + 3 (E) + 4 (A', B') + 3 (eta)
-#                      + 5 (v . n) + 1 (min) + 5 (k) + 1 (sqrt) + 2 (cs) + 9 (eta v + cs n) = 46;  prev 3+5+1+1+3+4 = 17
-#   spherical linear:  E (3) becomes part = min(1, dist / max_dist) (2): 45 / 16
-#   plane sigmoid:     no normalisation, v . n = v.y, normal term on y only: 2 (dist) + 3 + 4 + 3 + 1 + 5 + 1 + 2 + 4 = 25;  prev 2+3+4 = 9
-#   plane linear:      24 / 8
-FUSED_FLOPS = {1: (45, 16), 2: (24, 8), 3: (46, 17), 4: (25, 9)}
-FUSED_STEP_FIXED = 18 + 18 + 3 + 4   # stage inputs of stages 2-4, combine, step_dir, advance (+10 blend when field_weight != 1)
-SAFE_STEP_V2 = 6                     # |s|_1 (2), cost (2), budget - cost (1), compare operand (1)
+# Hand-fused mirage restatements (csrc/device/mirage_fused.cuh, fast math, LINON_FUSED_RK4): executed work per accepted step.
+# Stage 1 is the identity (not evaluated); the step's origin contributes once (PREV), stages 2 and 3 evaluate STAGE, stage 4
+# is accumulated straight into the Runge-Kutta sum (LAST).  Counted like the rest: FMA = 2, rsqrt / exp2 / sqrt / rcp = 1,
+# sign transfer, compares and selects = 0.
+#   spherical sigmoid  PREV  6 (scaled origin, 3 FMA) + 5 (q) + 1 (rsqrt) + 2 + 1 (E = exp2(k0 - q rq)) + 1 (b~) + 1 (rcp)
+#                            + 2 (g_in) + 1 (D g_in) = 20
+#                      STAGE 6 (c' = origin + s h k, 3 FMA) + 5 (q) + 1 (rsqrt) + 3 (E) + 1 (a~) + 1 (rcp) + 2 (eta)
+#                            + 5 (k . c') + 1 (d) + 1 (min) + 2 (1 - cr^2) + 1 (eta^2) + 2 (kk) + 1 (sqrt) + 2 (cs) + 1 (cs rq)
+#                            + 9 (eta k + csr c') = 44;   LAST: the last 9 become 12 (6 FMA into the sum) = 47
+#   spherical linear   E (3) becomes min(1, q rq) (2): 19 / 43 / 46
+#   plane sigmoid      PREV 2 (y') + 2 (E) + 1 + 1 + 2 + 1 = 9;  STAGE 2 (y') + 2 (E) + 1 (a~) + 1 (rcp) + 2 (eta) + 1 (min) + 2 + 1 + 2
+#                      + 1 (sqrt) + 2 (cs) + 4 (eta k + (0, cs, 0)) = 22;  LAST 25
+#   plane linear       E (2) becomes min(1, |y'|) (1)
+FUSED_FLOPS = {1: (43, 46, 19), 2: (21, 24, 8), 3: (44, 47, 20), 4: (22, 25, 9)}
+FUSED_STEP_FIXED = 12 + 2 + 3 + 6    # k1 + 2 k2 + 2 k3 (6 FMA), min3 of the discriminants, / 6, advance (3 FMA); +10 blend when field_weight != 1
+SAFE_STEP_V2 = 8                     # step_dir (3), |s|_1 (2), cost (2), budget - cost (1)
 
 
 def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True) -> float:
     """Executed-work model of the fast-mode mirage path in fixed-step variants (Enhance, adaptive off)."""
-    f_eval, f_prev = FUSED_FLOPS[fn_id]
-    step = FUSED_STEP_FIXED + (0 if field_weight_is_one else 10) + 3 * f_eval + f_prev
+    f_stage, f_last, f_prev = FUSED_FLOPS[fn_id]
+    step = FUSED_STEP_FIXED + (0 if field_weight_is_one else 10) + 2 * f_stage + f_last + f_prev
     flops = counters.accepted_steps * step + counters.face_tests * FACE_TEST
     flops += counters.prehit_steps * SAFE_STEP_V2
     flops += counters.culling_checks * (PREHIT_EXTRA + CHECK_EXTRA + 3) + counters.plane_tests * PLANE_TEST

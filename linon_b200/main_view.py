@@ -332,6 +332,13 @@ class MainView:
         self._check_view(capi.lib().linon_debug_eval_field(self._view, n, *[x.ctypes.data for x in a], out.ctypes.data))
         return out
 
+    def debug_eval_rk4(self, p, direction, v0, t, h):
+        a = [np.ascontiguousarray(x, np.float32) for x in (p, direction, v0, t, h)]
+        n = a[3].shape[0]
+        out = np.zeros((n, 3), np.float32)
+        self._check_view(capi.lib().linon_debug_eval_rk4(self._view, n, *[x.ctypes.data for x in a], out.ctypes.data))
+        return out
+
     def debug_eval_helper(self, which: int, n: int, v=None, nrm=None, p0=None, a=None, b=None, c=None):
         z3, z1 = np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
         arrs = [np.ascontiguousarray(x if x is not None else d, np.float32)

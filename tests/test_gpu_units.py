@@ -138,6 +138,72 @@ def test_field_functions_match_the_oracle(view, oracle, fn):
     view.set_option(capi.OPT_SPECIALIZE, 1)
 
 
+def _oracle_rk4(oracle, fn, p, d, v0, t, h, use_fp64):
+    """v = (k1 + 2 k2 + 2 k3 + k4) / 6 of src/main_view.wgsl:246-251 out of four calls of the oracle's field function
+    (p_prev = p in every stage); stage inputs in fp32 like the shader."""
+    st = settings_dict(make_settings())
+    f = lambda q, k, tt: oracle.field(int(fn), st, p, q.astype(np.float32), v0, k, tt.astype(np.float32), use_fp64=use_fp64)
+    hh = h[:, None]
+    k1 = f(p, d, t)
+    k2 = f(p + np.float32(0.5) * hh * k1, k1, t + np.float32(0.5) * h)
+    k3 = f(p + np.float32(0.5) * hh * k2, k2, t + np.float32(0.5) * h)
+    k4 = f(p + hh * k3, k3, t + h)
+    return ((k1 + np.float32(2) * k2 + np.float32(2) * k3 + k4) / np.float32(6)).astype(np.float32), k1, k2
+
+
+@pytest.mark.parametrize("fn", PREDEFINED)
+def test_rk4_velocity_matches_the_oracle(view, oracle, fn):
+    """The device function the march kernels call for one Runge-Kutta step - in fast mode the whole-step restatement of
+    the mirage bodies (scaled coordinates, slope-normalised eta, deferred total reflection) - against four calls of the
+    oracle's field function.  Inputs concentrate on the temperature gradient zones and on grazing incidence, where
+    Snell's discriminant changes sign (total reflection: the classic mirage rays above the hot plane)."""
+    rng = np.random.default_rng(100 + int(fn))
+    n = 16384
+    centre = np.array([-0.5, 0.5, -0.5], np.float32)
+    p = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    p[: n // 4] = centre + rng.normal(0, 0.15, (n // 4, 3)).astype(np.float32)
+    p[n // 4: n // 2, 1] = 0.1 + rng.uniform(-0.012, 0.012, n // 4).astype(np.float32)
+    d = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # grazing incidence: almost tangent to the sphere shells / almost parallel to the plane, heading into the hot side
+    q = n // 8
+    radial = p[:q] - centre
+    radial /= np.linalg.norm(radial, axis=1, keepdims=True)
+    tang = np.cross(radial, rng.normal(0, 1, (q, 3)))
+    tang /= np.linalg.norm(tang, axis=1, keepdims=True)
+    d[:q] = (tang - radial * rng.uniform(0, 0.3, (q, 1))).astype(np.float32)
+    d[n // 4: n // 4 + q, 1] = -np.abs(rng.uniform(0, 0.02, q)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    v0 = d.copy()
+    t = rng.uniform(0, 5, n).astype(np.float32)
+    h = np.where(rng.uniform(size=n) < 0.5, np.float32(0.1), np.float32(0.001)).astype(np.float32)
+    ref, k1, k2 = _oracle_rk4(oracle, fn, p, d, v0, t, h, use_fp64=False)
+    ref64, _, _ = _oracle_rk4(oracle, fn, p, d, v0, t, h, use_fp64=True)
+    view.reload_shader(fn.to_code())
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    strict = view.debug_eval_rk4(p, d, v0, t, h)
+    if fn in (PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.MiragePlaneSigmoid, PredefinedFunction.Rotation):
+        assert np.allclose(strict, ref, rtol=1e-4, atol=1e-5)
+    else:
+        assert np.array_equal(strict.view(np.uint32), ref.view(np.uint32))
+    view.set_option(capi.OPT_MATH, capi.MATH_FAST)
+    # a sample the oracle itself cannot decide (fp32 and fp64 evaluation land on different sides of the discriminant: the
+    # refracted and the reflected direction differ by O(|cos i|)) is not graded; everything else must agree
+    undecided = ~np.isclose(ref, ref64, rtol=1e-3, atol=1e-4).all(axis=1)
+    for specialize in (0, 1):
+        view.set_option(capi.OPT_SPECIALIZE, specialize)
+        fast = view.debug_eval_rk4(p, d, v0, t, h)
+        ok = (np.isclose(fast, ref, rtol=3e-4, atol=3e-5) | np.isclose(fast, ref64, rtol=3e-4, atol=3e-5)).all(axis=1)
+        bad = ~ok & ~undecided
+        assert bad.mean() <= 5e-4, (specialize, int(bad.sum()), np.argwhere(bad)[:5].ravel())
+    view.set_option(capi.OPT_SPECIALIZE, 1)
+    assert undecided.mean() < 0.01
+    if fn in (PredefinedFunction.MiragePlane, PredefinedFunction.MiragePlaneSigmoid):
+        # the inputs do exercise total reflection: stage 2 mirrors the incoming direction at the plane
+        mirrored = np.isclose(k2[:, 1], -k1[:, 1], rtol=1e-6) & (np.abs(k1[:, 1]) > 1e-4) & np.isclose(k2[:, 0], k1[:, 0], rtol=1e-6)
+        assert mirrored.sum() > 50, int(mirrored.sum())
+
+
 def test_user_edited_function_runs_and_errors_keep_the_old_kernel(view):
     view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
     body = "var q = p * 2.0;\nif (t > 1.0) { q = q + vec3<f32>(1.0, 0.0, 0.0); }\nreturn q.zyx + v0 * settings.field_weight;"
