@@ -36,6 +36,8 @@
 //         ONE FFMA per component from the step's scaled origin (s h k + c'_prev), and the normal c' / |c'| is unchanged;
 //       - A and B are divided by their slopes: a~ = u + A1/A2, b~ = u + B1/B2 (u = E or min(1, |c'|)); the slopes cancel
 //         in eta = a~(in) b~(out) / (a~(out) b~(in)), so two FFMAs with register constants become two FADDs with immediates;
+//         a~(in) / b~(in) is formed once per step, and for the sigmoid profiles b~ / a~ = 1 + D / a~ is one FFMA on the
+//         reciprocal (the linear profiles have A1/A2 ~ 550, where that form would cancel: they multiply b~ by 1 / a~);
 //       - the normal is never materialised: d = (v . c') rq and the refracted direction is eta v + (cs rq) c';
 //       - stage 4 is accumulated straight into k1 + 2 k2 + 2 k3 (two FFMAs per component, no k4);
 //       - total reflection (k < 0, a thin band of grazing rays) is detected once per step on min(k2, k3, k4); such a step
@@ -221,8 +223,13 @@ template <class S> struct LinonField {
         const S u = profile(y);
         const S d = kp.y;
 #endif
-        // eta = g(u) / g(u_in) with g = b~ / a~ = 1 + D / (u + RA):  g_in = 1 / g(u_in), gd_in = D g_in
+#if LINON_MIRAGE_KIND >= 3
+        // eta = g(u) / g(u_in) with g = b~ / a~ = 1 + D / (u + RA):  g_in = 1 / g(u_in), gd_in = D g_in.  Sigmoid profiles
+        // only: there RA ~ 1 and g lies in [0.6, 1]; with the linear profile RA ~ 550 and 1 + D / (u + RA) would cancel.
         const S eta = g_in + gd_in * (1.0f / (u + Fused::RA));
+#else
+        const S eta = ((u + Fused::RB) * (1.0f / (u + Fused::RA))) * g_in;  // g_in = a~(in) / b~(in)
+#endif
         const S cr = w_min(1.0f, d);  // clamp(-1, 1, d) with its misordered arguments
         kk = 1.0f - eta * eta * (1.0f - cr * cr);
         const S sk = w_sqrt(kk);
@@ -272,8 +279,13 @@ template <class S> struct LinonField {
 #else
         const S u_in = profile(pc);
 #endif
+#if LINON_MIRAGE_KIND >= 3
         const S g_in = 1.0f - Fused::D * (1.0f / (u_in + Fused::RB));  // a~ / b~ at the step's origin
         const S gd_in = Fused::D * g_in;
+#else
+        const S g_in = (u_in + Fused::RA) * (1.0f / (u_in + Fused::RB));
+        const S gd_in = g_in;  // unused by the linear profile
+#endif
         S kk_min;
         vec3t<S> sum = rk4_sum<false>(pc, g_in, gd_in, dir, h, kk_min);
         if (__builtin_expect(s_any(kk_min < 0.0f), 0)) {

@@ -38,11 +38,11 @@ CHECK_EXTRA = 5        # reach + bound reset, per culling check
 #                      STAGE 6 (c' = origin + s h k, 3 FMA) + 5 (q) + 1 (rsqrt) + 3 (E) + 1 (a~) + 1 (rcp) + 2 (eta)
 #                            + 5 (k . c') + 1 (d) + 1 (min) + 2 (1 - cr^2) + 1 (eta^2) + 2 (kk) + 1 (sqrt) + 2 (cs) + 1 (cs rq)
 #                            + 9 (eta k + csr c') = 44;   LAST: the last 9 become 12 (6 FMA into the sum) = 47
-#   spherical linear   E (3) becomes min(1, q rq) (2): 19 / 43 / 46
+#   spherical linear   E (3) becomes min(1, q rq) (2); eta = (b~ (1 / a~)) g_in is 5 instead of 4 per stage, g_in 4 instead of 5: 18 / 44 / 47
 #   plane sigmoid      PREV 2 (y') + 2 (E) + 1 + 1 + 2 + 1 = 9;  STAGE 2 (y') + 2 (E) + 1 (a~) + 1 (rcp) + 2 (eta) + 1 (min) + 2 + 1 + 2
 #                      + 1 (sqrt) + 2 (cs) + 4 (eta k + (0, cs, 0)) = 22;  LAST 25
-#   plane linear       E (2) becomes min(1, |y'|) (1)
-FUSED_FLOPS = {1: (43, 46, 19), 2: (21, 24, 8), 3: (44, 47, 20), 4: (22, 25, 9)}
+#   plane linear       E (2) becomes min(1, |y'|) (1), eta as above: 7 / 22 / 25
+FUSED_FLOPS = {1: (44, 47, 18), 2: (22, 25, 7), 3: (44, 47, 20), 4: (22, 25, 9)}
 FUSED_STEP_FIXED = 12 + 2 + 3 + 6    # k1 + 2 k2 + 2 k3 (6 FMA), min3 of the discriminants, / 6, advance (3 FMA); +10 blend when field_weight != 1
 SAFE_STEP_V2 = 8                     # step_dir (3), |s|_1 (2), cost (2), budget - cost (1)
 
