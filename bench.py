@@ -355,8 +355,8 @@ def run_ours(args):
         rk4_gsteps_per_s=gsteps,
         config=dict(workload=workload_name(world, W, H), width=W, height=H, rays_per_step=rays,
                     rk4_steps_per_step=acc + rej, field_function="MirageSphericalSigmoid", h_initial=0.001,
-                    math_mode="fast (--use_fast_math; hand-fused restatement of the predefined mirage body, RK4 stage 1 = identity)",
-                    kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, warp-coherent culling checks)", plane_culling=True,
+                    math_mode="fast (--use_fast_math; whole-step restatement of the predefined mirage body: RK4 stage 1 = identity, scaled coordinates, one reciprocal per stage)",
+                    kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass culling checks)", plane_culling=True,
                     parallelism=f"row-blocks x{world}" if world > 1 else "single GPU",
                     l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
         clocks=clocks,

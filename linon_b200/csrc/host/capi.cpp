@@ -229,7 +229,12 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
         opts.push_back("--use_fast_math");
         opts.push_back("-DLINON_FAST_MATH=1");
     }
-    if (var.max_regs > 0) opts.push_back("--maxrregcount=" + std::to_string(var.max_regs));
+    if (var.max_regs > 0) {
+        // __launch_bounds__ wins over --maxrregcount, so the cap is passed as resident CTAs per SM as well
+        opts.push_back("--maxrregcount=" + std::to_string(var.max_regs));
+        const int ctas = 65536 / (var.max_regs * var.block);
+        if (ctas >= 1) opts.push_back("-DLINON_MIN_BLOCKS=" + std::to_string(ctas));
+    }
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
     const nvrtcResult rc = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
@@ -1101,6 +1106,7 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     if (const char* k = getenv("LINON_CHECK_KERNEL")) tmp.opt_kernel = atoi(k);  // developer aid: 0 = without the pair kernel
     if (const char* k = getenv("LINON_CHECK_PAIR_MIN_BLOCKS")) tmp.opt_pair_min_blocks = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BLOCK")) tmp.opt_block = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_MAX_REGS")) tmp.opt_max_regs = atoi(k);
     if (const char* k = getenv("LINON_CHECK_SPECIALIZE")) tmp.opt_specialize = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BVH")) tmp.use_bvh = atoi(k) != 0;
     Variant var = make_variant(&tmp, flags);
