@@ -218,7 +218,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      "-DLINON_BVH=" + std::to_string(var.bvh),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
-                                     "-DLINON_PACKED_OPS=" + std::to_string(var.math == 0 ? 0 : 1),
+                                     "-DLINON_PACKED_OPS=" + std::to_string((var.math == 0 || getenv("LINON_DEV_UNPACKED")) ? 0 : 1),
                                      "-DLINON_STRICT_MATH=" + std::to_string(var.math == 0 ? 1 : 0)};
     if (var.pair_min_blocks > 0) opts.push_back("-DLINON_PAIR_MIN_BLOCKS=" + std::to_string(var.pair_min_blocks));
     if (var.math == 0) {
