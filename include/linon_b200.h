@@ -47,7 +47,8 @@ enum {
     LINON_ERR_CUDA = 2,        /* CUDA runtime or driver error */
     LINON_ERR_COMPILE = 3,     /* field function rejected (translator or NVRTC); previous kernel stays live */
     LINON_ERR_NO_DRIVER = 4,   /* libcuda.so.1 / a CUDA device is not available: there is NO CPU fallback */
-    LINON_ERR_SIZE = 5         /* caller buffer too small */
+    LINON_ERR_SIZE = 5,        /* caller buffer too small */
+    LINON_ERR_UNSUPPORTED = 6  /* linon_reload_shader_source: the edited module changes the march itself, not its helper layer */
 };
 
 /* render flags.  The reference toggles these by string replacement on the WGSL source
@@ -156,6 +157,22 @@ int linon_resize(linon_view* v, uint32_t width, uint32_t height);
  * LINON_ERR_COMPILE, writes the diagnostic (line numbers refer to the body) to err (if non-null) and keeps the
  * previous function live, like the reference (:677-679). */
 int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, size_t err_len);
+/* MainView::reload_shader(device, Some(new_src), field_function) (:649-690), reached from the file watcher on
+ * src/main_view.wgsl (src/main.rs:206-222 -> Application::reload_compute_shader, src/application.rs:228-232) and the
+ * README's extension point "Additional helper functions can be defined by adding them to the compute shader"
+ * (README.md:46).  wgsl_module_source is the text of the edited main_view.wgsl; NULL or "" returns to the stock module.
+ * What the CUDA path hot-reloads is the module's HELPER LAYER: new functions, edited versions of the library helpers
+ * (rotateX/Y/Z, translate, refraction_index, refraction, point_plane_distance, sigmoid - and every unchanged helper
+ * that calls an edited one), new module-scope constants and an edited PI; they are translated to CUDA and take part
+ * in the NVRTC build of every variant.  The placeholder field_function of the module is ignored (the body comes from
+ * linon_set_field_function).  An edit to the march itself (hit_triangle, ray_color, nonlinear_ray_color, sample_rays,
+ * main_view, their constants, structs or bindings - recognised by token hashes of the reference's declarations)
+ * returns LINON_ERR_UNSUPPORTED naming the declaration; a syntax or compile error returns LINON_ERR_COMPILE with
+ * diagnostics that cite main_view.wgsl line numbers.  In both cases the previous module and kernel stay live (:677-679).
+ * While a helper layer is installed the predefined mirage bodies run their generic translation. */
+int linon_reload_shader_source(linon_view* v, const char* wgsl_module_source, char* err, size_t err_len);
+/* Comma-separated names of the declarations the installed helper layer overrides or adds ("" = stock module). */
+int linon_module_overrides(linon_view* v, char* names, size_t names_len);
 /* MainView::render (:831-849), render_high_accuracy (:778-802), render_outline_rays (:804-829) by flags.
  * Enqueues: [outline search | click positions] -> march (+ sample rays on a second stream) -> overlay. */
 int linon_render(linon_view* v, uint32_t flags);
@@ -187,6 +204,15 @@ int linon_translate_wgsl(const char* wgsl_body, char* out, size_t out_len, char*
  * *cubin_bytes and the registers/thread of the persistent kernel are not known without loading (set to 0). */
 int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, uint32_t n_faces, size_t* cubin_bytes,
                         char* err, size_t err_len);
+/* The same with the helper layer of an edited main_view.wgsl (see linon_reload_shader_source). */
+int linon_compile_check_module(const char* wgsl_module_source, const char* wgsl_body, uint32_t flags, int math_mode,
+                               uint32_t n_faces, size_t* cubin_bytes, char* err, size_t err_len);
+/* Module translator alone: the CUDA member functions generated for the helper layer (out) and the names emitted. */
+int linon_translate_wgsl_module(const char* wgsl_module_source, char* out, size_t out_len, char* names, size_t names_len,
+                                char* err, size_t err_len);
+/* Top-level declarations of a WGSL module, one per line: "<kind> <name> <token hash> <line>" (used to generate the
+ * table of the reference's own declarations, tools/gen_module_hashes.py). */
+int linon_scan_wgsl_module(const char* wgsl_module_source, char* out, size_t out_len, char* err, size_t err_len);
 
 /* Parity/debug entry points: evaluate the CURRENT field function / helper library / hit_triangle on arrays
  * (host pointers; n elements; vec3 arrays are n x 3 f32). `which` numbering for helpers:

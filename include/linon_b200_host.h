@@ -60,6 +60,9 @@ int linon_host_mv_on_pointer_moved(linon_host_mv* m, int camera_op /*0 none 1 ro
 int linon_host_mv_update_settings(linon_host_mv* m, const linon_settings* s);
 int linon_host_mv_resize_texture(linon_host_mv* m, uint32_t width, uint32_t height);
 int linon_host_mv_reload_shader(linon_host_mv* m, const char* field_function, char* err, size_t err_len);
+/* Application::reload_compute_shader(new_src) (src/application.rs:228-232): MainView::reload_shader with
+ * new_src = Some(..) and the current field function; see linon_reload_shader_source for what is honoured. */
+int linon_host_mv_reload_compute_shader(linon_host_mv* m, const char* new_src, char* err, size_t err_len);
 int linon_host_mv_set_adaptive_sampling(linon_host_mv* m, int enabled);
 int linon_host_mv_render(linon_host_mv* m);
 int linon_host_mv_render_high_accuracy(linon_host_mv* m, const char* field_function);

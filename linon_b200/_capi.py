@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "liblinon_b200.so")
 
 # --- enums of include/linon_b200.h ---------------------------------------------------------------
-OK, ERR_INVALID, ERR_CUDA, ERR_COMPILE, ERR_NO_DRIVER, ERR_SIZE = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_COMPILE, ERR_NO_DRIVER, ERR_SIZE, ERR_UNSUPPORTED = range(7)
 RENDER_DEFAULT, RENDER_ENHANCE, RENDER_OUTLINE, RENDER_ADAPTIVE_OFF = 0, 1, 2, 4
 RENDER_NO_OVERLAY, RENDER_NO_MARCH, RENDER_NO_SAMPLE_RAYS = 8, 16, 32
 BUF_FINAL_RGBA8, BUF_RAYCAST_RGBA8, BUF_ENDPOINT_F32X4, BUF_EXPONENTS_F32, BUF_HIT_ID_I32 = range(5)
@@ -68,6 +68,8 @@ PROTOTYPES = [
     ("linon_set_settings", _I, [_P, C.POINTER(Settings)]),
     ("linon_resize", _I, [_P, _U, _U]),
     ("linon_set_field_function", _I, [_P, _CP, _P, _S]),
+    ("linon_reload_shader_source", _I, [_P, _CP, _P, _S]),
+    ("linon_module_overrides", _I, [_P, _P, _S]),
     ("linon_render", _I, [_P, _U]),
     ("linon_sync", _I, [_P]),
     ("linon_read", _I, [_P, _I, _P, _S]),
@@ -81,6 +83,9 @@ PROTOTYPES = [
     ("linon_last_error", _CP, [_P]),
     ("linon_translate_wgsl", _I, [_CP, _P, _S, _P, _S]),
     ("linon_compile_check", _I, [_CP, _U, _I, _U, C.POINTER(_S), _P, _S]),
+    ("linon_compile_check_module", _I, [_CP, _CP, _U, _I, _U, C.POINTER(_S), _P, _S]),
+    ("linon_translate_wgsl_module", _I, [_CP, _P, _S, _P, _S, _P, _S]),
+    ("linon_scan_wgsl_module", _I, [_CP, _P, _S, _P, _S]),
     ("linon_debug_eval_field", _I, [_P, _U, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_eval_rk4", _I, [_P, _U, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_eval_helper", _I, [_P, _I, _U, _P, _P, _P, _P, _P, _P, _P]),
@@ -112,6 +117,7 @@ PROTOTYPES = [
     ("linon_host_mv_update_settings", _I, [_P, C.POINTER(Settings)]),
     ("linon_host_mv_resize_texture", _I, [_P, _U, _U]),
     ("linon_host_mv_reload_shader", _I, [_P, _CP, _P, _S]),
+    ("linon_host_mv_reload_compute_shader", _I, [_P, _CP, _P, _S]),
     ("linon_host_mv_set_adaptive_sampling", _I, [_P, _I]),
     ("linon_host_mv_render", _I, [_P]),
     ("linon_host_mv_render_high_accuracy", _I, [_P, _CP]),

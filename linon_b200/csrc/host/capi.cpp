@@ -163,9 +163,9 @@ int mirage_kind(const std::string& wgsl_body) {
     return 0;
 }
 
-std::string build_source(const std::string& cuda_body, int fused_kind) {
+std::string build_source(const std::string& cuda_body, int fused_kind, const linon::ModuleLayer& layer) {
     std::string s;
-    s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + sizeof(kMirageFusedSrc) + cuda_body.size() + 512);
+    s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + sizeof(kMirageFusedSrc) + cuda_body.size() + layer.members.size() + 512);
     s += "#line 1 \"wgsl_prelude.cuh\"\n";
     s += kPreludeSrc;
     s += "\n";
@@ -174,9 +174,25 @@ std::string build_source(const std::string& cuda_body, int fused_kind) {
         s += kMirageFusedSrc;
         s += "\n#line 1 \"march_kernels.cuh\"\n";
     } else {
-        s += kFieldHead;
+        // helper layer of an edited main_view.wgsl (linon_reload_shader_source): member functions of LinonField<S>, found by
+        // class-scope lookup before the prelude's helpers of the same name; module constants open every function body
+        const size_t cut = std::string(kFieldHead).find("    static __device__ __forceinline__ vec3t<S> eval(");
+        const std::string head(kFieldHead);
+        const size_t line_directive = head.rfind("#line 1 \"field_function.wgsl\"");
+        s += head.substr(0, cut);
+        s += layer.members;
+        s += head.substr(cut, line_directive - cut);
+        s += layer.preamble;
+        s += "\n";
+        s += head.substr(line_directive);
         s += cuda_body;
-        s += kFieldTail;
+        const std::string tail(kFieldTail);
+        const size_t tail_line = tail.find("#line");
+        s += tail.substr(0, tail_line);
+        // every helper of the module is compiled, called or not, like naga validates the whole module (an error in an
+        // unused helper is still an error of the reload)
+        if (!layer.members.empty()) s += "template struct LinonField<float>;\n";
+        s += tail.substr(tail_line);
     }
     s += kMarchSrc;
     return s;
@@ -191,14 +207,16 @@ std::string float_literal(float x) {
 }
 
 // Translate + NVRTC compile to an sm_100a cubin.  No device needed.
-bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector<char>& cubin, std::string& log) {
+bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon::ModuleLayer& layer, std::vector<char>& cubin,
+                   std::string& log) {
     std::string cuda_body, terr;
     if (!linon::translate_wgsl_body(wgsl_body, cuda_body, terr)) {
         log = terr;
         return false;
     }
-    const int fused_kind = (var.math == 2 && var.specialize) ? mirage_kind(wgsl_body) : 0;
-    const std::string src = build_source(cuda_body, fused_kind);
+    // an edited helper layer may redefine what the predefined bodies call: they then run the generic translation
+    const int fused_kind = (var.math == 2 && var.specialize && layer.empty()) ? mirage_kind(wgsl_body) : 0;
+    const std::string src = build_source(cuda_body, fused_kind, layer);
     nvrtcProgram prog = nullptr;
     if (nvrtcCreateProgram(&prog, src.c_str(), "linon_march.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
         log = "nvrtcCreateProgram failed";
@@ -250,7 +268,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
             size_t e = full_log.find('\n', pos);
             if (e == std::string::npos) e = full_log.size();
             const std::string line = full_log.substr(pos, e - pos);
-            if (line.find("field_function.wgsl") != std::string::npos) mine += line + "\n";
+            if (line.find("field_function.wgsl") != std::string::npos || line.find("main_view.wgsl") != std::string::npos) mine += line + "\n";
             pos = e + 1;
         }
         log = mine.empty() ? full_log : mine;
@@ -267,8 +285,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, std::vector
     return true;
 }
 
-std::string variant_key(const std::string& body, const Variant& v) {
-    return fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
+std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
+    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
                v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh) + body;
 }
 
@@ -289,6 +307,7 @@ struct linon_view {
     linon_settings settings{};
     uint32_t n_faces = 0, n_groups = 0;
     float plane_w_max = 0.0f;  // max |offset| of the plane groups (BVH meshes: max |coordinate|)
+    linon::ModuleLayer layer;  // helper layer of an edited main_view.wgsl (linon_reload_shader_source); empty = stock module
     bool use_bvh = false;      // mesh beyond the shared-memory stage: faces in hierarchy order + nodes in global memory
     void* d_bvh = nullptr;
     uint32_t bvh_nodes = 0, bvh_depth = 0;
@@ -386,7 +405,7 @@ int alloc_frame_buffers(linon_view* v, uint32_t W, uint32_t H) {
 }
 
 int get_module(linon_view* v, const std::string& body, const Variant& var, Module** out, float* jit_ms) {
-    const std::string key = variant_key(body, var);
+    const std::string key = variant_key(body, var, v->layer);
     auto it = v->modules.find(key);
     if (it != v->modules.end()) {
         *out = &it->second;
@@ -395,7 +414,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<char> cubin;
     std::string log;
-    if (!compile_cubin(body, var, cubin, log)) return v->fail(LINON_ERR_COMPILE, log);
+    if (!compile_cubin(body, var, v->layer, cubin, log)) return v->fail(LINON_ERR_COMPILE, log);
     Module m;
     CUresult r = g_drv.ModuleLoadData(&m.mod, cubin.data());
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
@@ -839,6 +858,43 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
     return LINON_OK;
 }
 
+int linon_reload_shader_source(linon_view* v, const char* wgsl_module_source, char* err, size_t err_len) {
+    if (!v) return LINON_ERR_INVALID;
+    if (err && err_len) err[0] = '\0';
+    CK(v, cudaSetDevice(v->device));
+    linon::ModuleLayer layer;  // NULL / "" = the stock module
+    if (wgsl_module_source && wgsl_module_source[0]) {
+        std::string merr;
+        bool unsupported = false;
+        if (!linon::translate_wgsl_module(wgsl_module_source, layer, merr, unsupported)) {
+            if (err && err_len) snprintf(err, err_len, "%s", merr.c_str());
+            return v->fail(unsupported ? LINON_ERR_UNSUPPORTED : LINON_ERR_COMPILE, merr);
+        }
+    }
+    // validate by building the default variant with the CURRENT field function; on failure the previous module text and
+    // kernel stay live (src/main_view.rs:677-679 returns before `self.shader_src = new_src`)
+    const linon::ModuleLayer previous = v->layer;
+    v->layer = layer;
+    Variant var = make_variant(v, LINON_RENDER_DEFAULT);
+    if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
+    Module* m = nullptr;
+    float jit = 0.0f;
+    const int rc = get_module_for_body(v, v->body, var, &m, &jit);
+    if (rc != LINON_OK) {
+        v->layer = previous;
+        if (err && err_len) snprintf(err, err_len, "%s", v->error.c_str());
+        return rc;
+    }
+    return LINON_OK;
+}
+
+int linon_module_overrides(linon_view* v, char* names, size_t names_len) {
+    if (!v || !names || !names_len) return LINON_ERR_INVALID;
+    if (v->layer.names.size() + 1 > names_len) return LINON_ERR_SIZE;
+    memcpy(names, v->layer.names.c_str(), v->layer.names.size() + 1);
+    return LINON_OK;
+}
+
 int linon_render(linon_view* v, uint32_t flags) {
     if (!v) return LINON_ERR_INVALID;
     const bool do_march = !(flags & LINON_RENDER_NO_MARCH);
@@ -1093,8 +1149,9 @@ int linon_translate_wgsl(const char* wgsl_body, char* out, size_t out_len, char*
     return LINON_OK;
 }
 
-int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, uint32_t n_faces, size_t* cubin_bytes,
-                        char* err, size_t err_len) {
+namespace {
+int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t flags, int math_mode, uint32_t n_faces,
+                       size_t* cubin_bytes, char* err, size_t err_len) {
     if (!wgsl_body) return LINON_ERR_INVALID;
     linon_view tmp;
     tmp.n_faces = n_faces;
@@ -1103,6 +1160,14 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     tmp.opt_math = math_mode;
     tmp.body = wgsl_body;
     tmp.settings.field_weight = 1.0f;  // the application's default (src/main_view.rs:133-139)
+    if (module_src && module_src[0]) {
+        std::string merr;
+        bool unsupported = false;
+        if (!linon::translate_wgsl_module(module_src, tmp.layer, merr, unsupported)) {
+            if (err && err_len) snprintf(err, err_len, "%s", merr.c_str());
+            return unsupported ? LINON_ERR_UNSUPPORTED : LINON_ERR_COMPILE;
+        }
+    }
     if (const char* k = getenv("LINON_CHECK_KERNEL")) tmp.opt_kernel = atoi(k);  // developer aid: 0 = without the pair kernel
     if (const char* k = getenv("LINON_CHECK_PAIR_MIN_BLOCKS")) tmp.opt_pair_min_blocks = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BLOCK")) tmp.opt_block = atoi(k);
@@ -1112,11 +1177,11 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
     Variant var = make_variant(&tmp, flags);
     std::vector<char> cubin;
     std::string log;
-    bool ok = compile_cubin(wgsl_body, var, cubin, log);
+    bool ok = compile_cubin(wgsl_body, var, tmp.layer, cubin, log);
     if (!ok && var.pairs) {  // same fallback as linon_render: the body may not instantiate for two rays per thread
         var.pairs = 0;
         std::string log2;
-        ok = compile_cubin(wgsl_body, var, cubin, log2);
+        ok = compile_cubin(wgsl_body, var, tmp.layer, cubin, log2);
         log = ok ? "pair kernel not built for this body:\n" + log : log2;
     }
     if (!ok) {
@@ -1131,6 +1196,51 @@ int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, ui
         }
     }
     if (err && err_len) snprintf(err, err_len, "%s", log.c_str());  // warnings, if any
+    return LINON_OK;
+}
+}  // namespace
+
+int linon_compile_check(const char* wgsl_body, uint32_t flags, int math_mode, uint32_t n_faces, size_t* cubin_bytes,
+                        char* err, size_t err_len) {
+    return compile_check_impl(nullptr, wgsl_body, flags, math_mode, n_faces, cubin_bytes, err, err_len);
+}
+
+int linon_compile_check_module(const char* wgsl_module_source, const char* wgsl_body, uint32_t flags, int math_mode,
+                               uint32_t n_faces, size_t* cubin_bytes, char* err, size_t err_len) {
+    return compile_check_impl(wgsl_module_source, wgsl_body, flags, math_mode, n_faces, cubin_bytes, err, err_len);
+}
+
+int linon_translate_wgsl_module(const char* wgsl_module_source, char* out, size_t out_len, char* names, size_t names_len,
+                                char* err, size_t err_len) {
+    if (!wgsl_module_source) return LINON_ERR_INVALID;
+    linon::ModuleLayer layer;
+    std::string merr;
+    bool unsupported = false;
+    if (!linon::translate_wgsl_module(wgsl_module_source, layer, merr, unsupported)) {
+        if (err && err_len) snprintf(err, err_len, "%s", merr.c_str());
+        return unsupported ? LINON_ERR_UNSUPPORTED : LINON_ERR_COMPILE;
+    }
+    const std::string text = layer.preamble.empty() ? layer.members : "// module constants: " + layer.preamble + "\n" + layer.members;
+    if (out && out_len) {
+        if (text.size() + 1 > out_len) return LINON_ERR_SIZE;
+        memcpy(out, text.c_str(), text.size() + 1);
+    }
+    if (names && names_len) snprintf(names, names_len, "%s", layer.names.c_str());
+    return LINON_OK;
+}
+
+int linon_scan_wgsl_module(const char* wgsl_module_source, char* out, size_t out_len, char* err, size_t err_len) {
+    if (!wgsl_module_source || !out || !out_len) return LINON_ERR_INVALID;
+    std::vector<linon::ModuleItem> items;
+    std::string merr;
+    if (!linon::scan_wgsl_module(wgsl_module_source, items, merr)) {
+        if (err && err_len) snprintf(err, err_len, "%s", merr.c_str());
+        return LINON_ERR_COMPILE;
+    }
+    std::string text;
+    for (const auto& it : items) text += fmt("%s %s 0x%016llx %d\n", it.kind.c_str(), it.name.c_str(), (unsigned long long)it.hash, it.line);
+    if (text.size() + 1 > out_len) return LINON_ERR_SIZE;
+    memcpy(out, text.c_str(), text.size() + 1);
     return LINON_OK;
 }
 

@@ -151,6 +151,17 @@ int linon_host_mv_reload_shader(linon_host_mv* m, const char* field_function, ch
     }
     return LINON_OK;
 }
+int linon_host_mv_reload_compute_shader(linon_host_mv* m, const char* new_src, char* err, size_t err_len) {
+    if (!m || !m->view) return LINON_ERR_INVALID;
+    std::string e;
+    if (!m->view->reload_compute_shader(new_src ? new_src : "", &e)) {
+        m->error = e;
+        if (err && err_len) snprintf(err, err_len, "%s", e.c_str());
+        const char* last = linon_last_error(m->view->handle());
+        return (last && e == last && e.find("the CUDA path hot-reloads") != std::string::npos) ? LINON_ERR_UNSUPPORTED : LINON_ERR_COMPILE;
+    }
+    return LINON_OK;
+}
 int linon_host_mv_set_adaptive_sampling(linon_host_mv* m, int enabled) {
     return guarded(m, [&](linon::MainView& v) { enabled ? v.enable_adaptive_sampling() : v.disable_adaptive_sampling(); });
 }

@@ -121,6 +121,30 @@ public:
         needs_redraw = true;
         return true;
     }
+    // src/main_view.rs:649-690 with new_src = Some(..): the whole-shader hot reload (file watcher on src/main_view.wgsl,
+    // src/main.rs:206-222 -> Application::reload_compute_shader, src/application.rs:228-232).  The helper layer of the
+    // edited module is installed first, then the field function is rebuilt against it; on an error nothing changes
+    // (:677-679 returns before `self.shader_src = new_src`).
+    bool reload_shader(const std::string& new_src, const std::string& field_function, std::string* error) {
+        char buf[8192];
+        int rc = linon_reload_shader_source(view_, new_src.c_str(), buf, sizeof(buf));
+        if (rc == LINON_OK && field_function != field_function_) {
+            rc = linon_set_field_function(view_, field_function.c_str(), buf, sizeof(buf));
+            if (rc != LINON_OK) linon_reload_shader_source(view_, shader_src_.c_str(), nullptr, 0);  // back to the old module
+        }
+        if (rc != LINON_OK) {
+            if (error) *error = buf;
+            return false;
+        }
+        shader_src_ = new_src;
+        field_function_ = field_function;
+        needs_redraw = true;
+        return true;
+    }
+    // Application::reload_compute_shader, src/application.rs:228-232
+    bool reload_compute_shader(const std::string& new_src, std::string* error = nullptr) {
+        return reload_shader(new_src, field_function_, error);
+    }
     // src/main_view.rs:752-776.  The reference's string replacement for these two is dead at HEAD; the
     // documented behaviour (fixed step while dragging) is implemented as a render flag.
     void enable_adaptive_sampling() { adaptive_sampling_ = true; }
@@ -162,6 +186,7 @@ private:
     uint32_t downscale_factor_;
     uint32_t width_, height_;
     std::string field_function_;
+    std::string shader_src_;  // text of the last accepted main_view.wgsl ("" = stock module), src/main_view.rs:75
     ArcballCamera camera_;
     linon_view* view_ = nullptr;
 

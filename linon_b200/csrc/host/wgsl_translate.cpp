@@ -460,4 +460,343 @@ bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string
     return true;
 }
 
+
+// =================================================================================================================
+// Whole-shader hot reload: the helper layer of an edited main_view.wgsl
+// =================================================================================================================
+namespace {
+
+// Top-level declarations of the reference's src/main_view.wgsl as (kind, name, token hash): generated by
+// tools/gen_module_hashes.py from the mounted reference (hashes only, no source text).  An item whose hash matches is
+// "unchanged" and keeps its hand-written CUDA counterpart.
+struct Pristine {
+    const char* kind;
+    const char* name;
+    uint64_t hash;
+};
+const Pristine kPristine[] = {
+#include "module_items.inc"
+    {"", "", 0}};
+
+// library helpers a field function may call (README.md:37-44): an edited version overrides the prelude's
+const char* const kLibraryHelpers[] = {"rotateX", "rotateY", "rotateZ", "translate", "refraction_index", "refraction",
+                                       "point_plane_distance", "sigmoid"};
+// names the generated struct already uses
+const char* const kReservedNames[] = {"eval", "rk4", "stage", "rk4_sum", "wg_f32", "vec2f", "vec3f", "vec4f", "mat2x2f",
+                                      "mat3x3f", "LinonField", "S", "settings", "camera"};
+
+uint64_t fnv1a(uint64_t h, const std::string& s) {
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ull;
+    }
+    h ^= ' ';
+    h *= 1099511628211ull;
+    return h;
+}
+
+struct RawItem {
+    ModuleItem info;
+    int begin, end;        // token range [begin, end)
+    int name_tok = -1;
+    int paren_open = -1, paren_close = -1, brace_open = -1, brace_close = -1;  // fn only
+};
+
+bool split_module(const std::vector<Tok>& t, std::vector<RawItem>& items, std::string& err) {
+    auto is_p = [&](int i, const char* p) { return i >= 0 && i < (int)t.size() && t[i].kind == PUNCT && t[i].text == p; };
+    auto sig = [&](int i) {  // first significant token at or after i
+        while (i < (int)t.size() && (t[i].kind == WS || t[i].kind == NL)) ++i;
+        return i;
+    };
+    std::vector<int> line_of(t.size() + 1, 1);
+    for (size_t i = 0, line = 1; i < t.size(); ++i) {
+        line_of[i] = (int)line;
+        if (t[i].kind == NL) ++line;
+    }
+    auto match = [&](int open, const char* o, const char* c) {  // index of the closing token, -1 if unbalanced
+        int depth = 0;
+        for (int j = open; j < (int)t.size(); ++j) {
+            if (is_p(j, o)) ++depth;
+            if (is_p(j, c) && --depth == 0) return j;
+        }
+        return -1;
+    };
+    int i = sig(0);
+    while (i < (int)t.size()) {
+        RawItem it;
+        it.begin = i;
+        it.info.line = line_of[i];
+        while (is_p(i, "@")) {  // attributes belong to the declaration that follows
+            i = sig(i + 1);
+            if (i >= (int)t.size() || t[i].kind != IDENT) { err = "malformed attribute"; return false; }
+            i = sig(i + 1);
+            if (is_p(i, "(")) {
+                const int c = match(i, "(", ")");
+                if (c < 0) { err = "unbalanced '(' in an attribute"; return false; }
+                i = sig(c + 1);
+            }
+        }
+        if (i >= (int)t.size()) { err = "attribute without a declaration"; return false; }
+        if (is_p(i, ";")) { i = sig(i + 1); continue; }
+        if (t[i].kind != IDENT) {
+            err = "line " + std::to_string(line_of[i]) + ": unexpected '" + t[i].text + "' at module scope";
+            return false;
+        }
+        const std::string kw = t[i].text;
+        auto until_semicolon = [&](int from) {
+            int depth = 0;
+            for (int j = from; j < (int)t.size(); ++j) {
+                if (is_p(j, "(") || is_p(j, "{") || is_p(j, "[")) ++depth;
+                if (is_p(j, ")") || is_p(j, "}") || is_p(j, "]")) --depth;
+                if (depth == 0 && is_p(j, ";")) return j;
+            }
+            return -1;
+        };
+        if (kw == "fn") {
+            it.info.kind = "fn";
+            it.name_tok = sig(i + 1);
+            if (it.name_tok >= (int)t.size() || t[it.name_tok].kind != IDENT) { err = "expected a name after 'fn'"; return false; }
+            it.paren_open = sig(it.name_tok + 1);
+            if (!is_p(it.paren_open, "(")) { err = "expected '(' after 'fn " + t[it.name_tok].text + "'"; return false; }
+            it.paren_close = match(it.paren_open, "(", ")");
+            if (it.paren_close < 0) { err = "unbalanced '(' in the parameters of '" + t[it.name_tok].text + "'"; return false; }
+            int j = it.paren_close + 1;
+            while (j < (int)t.size() && !is_p(j, "{")) {
+                if (is_p(j, ";")) { err = "function '" + t[it.name_tok].text + "' has no body"; return false; }
+                ++j;
+            }
+            it.brace_open = j;
+            it.brace_close = j < (int)t.size() ? match(j, "{", "}") : -1;
+            if (it.brace_close < 0) { err = "unbalanced '{' in function '" + t[it.name_tok].text + "'"; return false; }
+            it.end = it.brace_close + 1;
+        } else if (kw == "struct") {
+            it.info.kind = "struct";
+            it.name_tok = sig(i + 1);
+            int j = it.name_tok;
+            while (j < (int)t.size() && !is_p(j, "{")) ++j;
+            const int c = j < (int)t.size() ? match(j, "{", "}") : -1;
+            if (c < 0) { err = "malformed struct declaration"; return false; }
+            it.end = c + 1;
+        } else if (kw == "var" || kw == "const" || kw == "let" || kw == "override") {
+            it.info.kind = kw == "var" ? "var" : "const";
+            int j = sig(i + 1);
+            if (is_p(j, "<")) {  // var<uniform>, var<storage, read_write>, var<private>
+                while (j < (int)t.size() && !is_p(j, ">")) ++j;
+                j = sig(j + 1);
+            }
+            it.name_tok = j;
+            const int semi = until_semicolon(i);
+            if (semi < 0 || j >= (int)t.size() || t[j].kind != IDENT) { err = "malformed '" + kw + "' declaration at module scope"; return false; }
+            it.end = semi + 1;
+        } else {
+            it.info.kind = "other";  // alias, enable, requires, diagnostic, const_assert
+            it.name_tok = i;
+            const int semi = until_semicolon(i);
+            if (semi < 0) { err = "line " + std::to_string(line_of[i]) + ": unexpected '" + kw + "' at module scope"; return false; }
+            it.end = semi + 1;
+        }
+        it.info.name = t[it.name_tok].text;
+        uint64_t h = 1469598103934665603ull;
+        for (int j = it.begin; j < it.end; ++j)
+            if (t[j].kind != WS && t[j].kind != NL) h = fnv1a(h, t[j].text);
+        it.info.hash = h;
+        items.push_back(it);
+        i = sig(it.end);
+    }
+    return true;
+}
+
+const Pristine* find_pristine(const std::string& kind, const std::string& name) {
+    for (const Pristine* p = kPristine; p->kind[0]; ++p)
+        if (kind == p->kind && name == p->name) return p;
+    return nullptr;
+}
+template <size_t N> bool in_list(const char* const (&list)[N], const std::string& s) {
+    for (const char* x : list)
+        if (s == x) return true;
+    return false;
+}
+
+// translate tokens [b, e) with the statement passes; newlines are kept (keep_nl) or dropped
+bool translate_range(const std::vector<Tok>& t, int b, int e, bool keep_nl, std::string& out, std::string& err) {
+    Rewriter rw;
+    rw.t.assign(t.begin() + b, t.begin() + e);
+    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control()) {
+        err = rw.err;
+        return false;
+    }
+    out.clear();
+    for (const Tok& k : rw.t) {
+        if (k.kind == NL && !keep_nl) out += ' ';
+        else out += k.text;
+    }
+    return true;
+}
+
+// `fn name(a: T, b: U) -> R { body }` -> `static __device__ __forceinline__ R name(const T a, const U b) { preamble body }`
+bool emit_function(const std::vector<Tok>& t, const RawItem& it, const std::string& preamble, std::string& out, std::string& err) {
+    Rewriter rw;
+    rw.t.assign(t.begin() + it.paren_open, t.begin() + it.end);
+    const int off = it.paren_open;
+    const int pc = it.paren_close - off, bo = it.brace_open - off;
+    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control()) {
+        err = "function '" + it.info.name + "': " + rw.err;
+        return false;
+    }
+    // parameters: name : TYPE  ->  const TYPE name   (WGSL parameters are immutable)
+    for (int i = 1; i < pc; ++i) {
+        if (!rw.is_p(i, ":")) continue;
+        const int name = rw.prev_sig(i), type = rw.next_sig(i);
+        if (name < 1 || type < 0 || type >= pc || rw.t[name].kind != IDENT || rw.t[type].kind != IDENT) {
+            err = "function '" + it.info.name + "': unsupported parameter list";
+            return false;
+        }
+        rw.t[name].text = "const " + rw.t[type].text + " " + rw.t[name].text;
+        rw.blank(i);
+        rw.blank(type);
+    }
+    for (int i = 1; i < pc; ++i)
+        if (rw.is_p(i, "@")) {
+            err = "function '" + it.info.name + "': parameter attributes are not supported in a helper function";
+            return false;
+        }
+    // return type
+    std::string ret = "void";
+    for (int i = pc + 1; i < bo; ++i) {
+        if (rw.t[i].kind == WS || rw.t[i].kind == NL) continue;
+        if (rw.is_p(i, "->")) {
+            const int ty = rw.next_sig(i);
+            if (ty < 0 || ty >= bo || rw.t[ty].kind != IDENT) {
+                err = "function '" + it.info.name + "': unsupported return type";
+                return false;
+            }
+            ret = rw.t[ty].text;
+            rw.blank(i);
+            rw.blank(ty);
+            i = ty;
+        } else if (!rw.t[i].text.empty()) {
+            err = "function '" + it.info.name + "': unsupported return type";
+            return false;
+        }
+    }
+    out += "#line " + std::to_string(it.info.line) + " \"main_view.wgsl\"\n";
+    out += "    static __device__ __forceinline__ " + ret + " " + it.info.name;
+    for (int i = 0; i < (int)rw.t.size(); ++i) {
+        out += rw.t[i].text;
+        if (i == bo) out += " " + preamble;
+    }
+    out += "\n";
+    return true;
+}
+
+}  // namespace
+
+bool scan_wgsl_module(const std::string& src, std::vector<ModuleItem>& items, std::string& error) {
+    Lexer lx(src);
+    if (!lx.run()) {
+        error = "WGSL module error: " + lx.err;
+        return false;
+    }
+    std::vector<RawItem> raw;
+    std::string err;
+    if (!split_module(lx.out, raw, err)) {
+        error = "WGSL module error: " + err;
+        return false;
+    }
+    for (const RawItem& r : raw) items.push_back(r.info);
+    return true;
+}
+
+bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::string& error, bool& unsupported) {
+    unsupported = false;
+    layer = ModuleLayer();
+    Lexer lx(src);
+    if (!lx.run()) {
+        error = "WGSL module error: " + lx.err;
+        return false;
+    }
+    const std::vector<Tok>& t = lx.out;
+    std::vector<RawItem> items;
+    std::string err;
+    if (!split_module(t, items, err)) {
+        error = "WGSL module error: " + err;
+        return false;
+    }
+    // ---- classify ---------------------------------------------------------------------------------------------------
+    std::vector<int> emit_fn, emit_const, unchanged_helpers;
+    for (int k = 0; k < (int)items.size(); ++k) {
+        const RawItem& it = items[k];
+        const std::string& kind = it.info.kind;
+        const std::string& name = it.info.name;
+        for (int j = 0; j < k; ++j)
+            if (items[j].info.name == name && items[j].info.kind != "other" && kind != "other") {
+                error = "WGSL module error: line " + std::to_string(it.info.line) + ": redefinition of '" + name + "'";
+                return false;
+            }
+        if (kind == "fn" && name == "field_function") continue;  // the placeholder: the body is installed separately
+        const Pristine* p = find_pristine(kind, name);
+        if (p && p->hash == it.info.hash) {
+            if (kind == "fn" && in_list(kLibraryHelpers, name)) unchanged_helpers.push_back(k);
+            continue;
+        }
+        if (kind == "fn" && (!p || in_list(kLibraryHelpers, name))) {
+            if (in_list(kReservedNames, name) || name.compare(0, 2, "w_") == 0 || name.compare(0, 6, "linon_") == 0) {
+                error = "WGSL module error: line " + std::to_string(it.info.line) + ": the function name '" + name + "' is reserved on the CUDA path";
+                return false;
+            }
+            emit_fn.push_back(k);
+            continue;
+        }
+        if (kind == "const" && (!p || name == "PI")) {
+            emit_const.push_back(k);
+            continue;
+        }
+        unsupported = true;
+        error = "main_view.wgsl line " + std::to_string(it.info.line) + ": " + (p ? "the " : "a new ") + kind + " '" + name + "' " +
+                (p ? "was edited" : "was added") + "; the CUDA path hot-reloads helper functions, module constants and the field function - "
+                "the march itself (hit_triangle, ray_color, nonlinear_ray_color, sample_rays, main_view, their constants, structs and "
+                "bindings) is the hand-written kernel template";
+        return false;
+    }
+    // ---- an unchanged library helper that uses an emitted name must be emitted too (it has to bind to the override) ----
+    auto uses = [&](const RawItem& it, const std::string& name) {
+        for (int j = it.brace_open; j < it.brace_close; ++j)
+            if (t[j].kind == IDENT && t[j].text == name) return true;
+        return false;
+    };
+    for (bool grew = true; grew;) {
+        grew = false;
+        for (size_t u = 0; u < unchanged_helpers.size(); ++u) {
+            const RawItem& h = items[unchanged_helpers[u]];
+            bool hit = false;
+            for (int k : emit_fn) hit = hit || uses(h, items[k].info.name);
+            for (int k : emit_const) hit = hit || uses(h, items[k].info.name);
+            if (hit) {
+                emit_fn.push_back(unchanged_helpers[u]);
+                unchanged_helpers.erase(unchanged_helpers.begin() + u);
+                grew = true;
+                break;
+            }
+        }
+    }
+    // ---- constants: one line, re-declared at the top of every emitted function and of the field-function body ----
+    for (int k : emit_const) {
+        std::string text;
+        if (!translate_range(t, items[k].begin, items[k].end, false, text, err)) {
+            error = "WGSL module error: constant '" + items[k].info.name + "': " + err;
+            return false;
+        }
+        layer.preamble += text + " ";
+        layer.names += (layer.names.empty() ? "" : ",") + items[k].info.name;
+    }
+    for (int k : emit_fn) {
+        if (!emit_function(t, items[k], layer.preamble, layer.members, err)) {
+            error = "WGSL module error: " + err;
+            return false;
+        }
+        layer.names += (layer.names.empty() ? "" : ",") + items[k].info.name;
+    }
+    return true;
+}
+
 }  // namespace linon

@@ -1,6 +1,8 @@
 // wgsl_translate.h — WGSL field-function body -> CUDA C++ (see wgsl_translate.cpp).
 #pragma once
+#include <cstdint>
 #include <string>
+#include <vector>
 
 namespace linon {
 
@@ -8,5 +10,27 @@ namespace linon {
 // (src/main_view.rs:852-861).  Returns false and fills `error` when the body uses WGSL outside the
 // supported subset; line structure is preserved so compiler diagnostics map to the user's lines.
 bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string& error);
+
+// ---- whole-shader hot reload (src/main.rs:206-222 -> Application::reload_compute_shader, src/application.rs:228-232
+//      -> MainView::reload_shader(device, Some(new_src), field_function), src/main_view.rs:649-690) ------------------
+// One top-level declaration of a WGSL module.
+struct ModuleItem {
+    std::string kind;  // "fn" "const" "struct" "var" "other"
+    std::string name;
+    uint64_t hash;     // FNV-1a over the item's tokens (comments and white space do not count)
+    int line;          // 1-based line of the item's first token
+};
+bool scan_wgsl_module(const std::string& src, std::vector<ModuleItem>& items, std::string& error);
+
+// The part of an edited main_view.wgsl that the CUDA path can honour: the helper layer the field function calls.
+struct ModuleLayer {
+    std::string members;    // CUDA member functions of LinonField<S> (new helpers + overridden library helpers)
+    std::string preamble;   // module-scope constants, re-declared at the top of every emitted function and of the body
+    std::string names;      // comma-separated names emitted (introspection / tests)
+    bool empty() const { return members.empty() && preamble.empty(); }
+};
+// Returns false with `error` set when the module cannot be honoured; `unsupported` tells a change to the kernel's own
+// functions / bindings / constants (named in the message) from a syntax error.
+bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::string& error, bool& unsupported);
 
 }  // namespace linon

@@ -229,6 +229,20 @@ class MainView:
         if rc != capi.OK:
             raise LinonError(rc, err.value.decode("utf-8", "replace"))
 
+    def reload_compute_shader(self, new_src: str | None):
+        """Application::reload_compute_shader (src/application.rs:228-232): the text of an edited main_view.wgsl; None
+        or "" returns to the stock module.  Raises LinonError(ERR_UNSUPPORTED) when the edit changes the march itself,
+        LinonError(ERR_COMPILE) on a syntax / compile error; the previous module stays active either way."""
+        err = C.create_string_buffer(16384)
+        rc = capi.lib().linon_host_mv_reload_compute_shader(self._h, (new_src or "").encode("utf-8"), err, len(err))
+        if rc != capi.OK:
+            raise LinonError(rc, err.value.decode("utf-8", "replace"))
+
+    def module_overrides(self) -> list[str]:
+        buf = C.create_string_buffer(4096)
+        self._check_view(capi.lib().linon_module_overrides(self._view, buf, len(buf)))
+        return [n for n in buf.value.decode().split(",") if n]
+
     def enable_adaptive_sampling(self):
         self._check(capi.lib().linon_host_mv_set_adaptive_sampling(self._h, 1))
 
@@ -367,11 +381,41 @@ def translate_wgsl(body: str) -> str:
     return out.value.decode("utf-8")
 
 
-def compile_check(body: str, flags: int = 0, math_mode: int = capi.MATH_FUSED, n_faces: int = 36) -> int:
+def translate_wgsl_module(module_src: str):
+    """Helper layer of an edited main_view.wgsl -> (CUDA member functions, names emitted). No GPU needed."""
+    out = C.create_string_buffer(1 << 18)
+    names = C.create_string_buffer(4096)
+    err = C.create_string_buffer(4096)
+    rc = capi.lib().linon_translate_wgsl_module(module_src.encode("utf-8"), out, len(out), names, len(names), err, len(err))
+    if rc != capi.OK:
+        raise LinonError(rc, err.value.decode("utf-8", "replace"))
+    return out.value.decode("utf-8"), [n for n in names.value.decode().split(",") if n]
+
+
+def scan_wgsl_module(module_src: str):
+    """Top-level declarations of a WGSL module: list of (kind, name, hash, line)."""
+    out = C.create_string_buffer(1 << 16)
+    err = C.create_string_buffer(4096)
+    rc = capi.lib().linon_scan_wgsl_module(module_src.encode("utf-8"), out, len(out), err, len(err))
+    if rc != capi.OK:
+        raise LinonError(rc, err.value.decode("utf-8", "replace"))
+    items = []
+    for line in out.value.decode().splitlines():
+        kind, name, h, ln = line.split()
+        items.append((kind, name, int(h, 16), int(ln)))
+    return items
+
+
+def compile_check(body: str, flags: int = 0, math_mode: int = capi.MATH_FUSED, n_faces: int = 36,
+                  module_src: str | None = None) -> int:
     """Translate + NVRTC-compile the march module for sm_100a (no GPU needed). Returns the cubin size."""
     nb = C.c_size_t(0)
     err = C.create_string_buffer(16384)
-    rc = capi.lib().linon_compile_check(body.encode("utf-8"), flags, math_mode, n_faces, C.byref(nb), err, len(err))
+    if module_src is not None:
+        rc = capi.lib().linon_compile_check_module(module_src.encode("utf-8"), body.encode("utf-8"), flags, math_mode,
+                                                   n_faces, C.byref(nb), err, len(err))
+    else:
+        rc = capi.lib().linon_compile_check(body.encode("utf-8"), flags, math_mode, n_faces, C.byref(nb), err, len(err))
     if rc != capi.OK:
         raise LinonError(rc, err.value.decode("utf-8", "replace"))
     return nb.value

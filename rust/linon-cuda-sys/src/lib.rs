@@ -65,6 +65,7 @@ pub const LINON_ERR_CUDA: c_int = 2;
 pub const LINON_ERR_COMPILE: c_int = 3;
 pub const LINON_ERR_NO_DRIVER: c_int = 4;
 pub const LINON_ERR_SIZE: c_int = 5;
+pub const LINON_ERR_UNSUPPORTED: c_int = 6;
 
 pub const LINON_RENDER_DEFAULT: u32 = 0;
 pub const LINON_RENDER_ENHANCE: u32 = 1; // render_high_accuracy, src/main_view.rs:778-802
@@ -90,6 +91,9 @@ extern "C" {
     pub fn linon_set_settings(v: *mut linon_view, settings: *const linon_settings) -> c_int;
     pub fn linon_resize(v: *mut linon_view, width: u32, height: u32) -> c_int;
     pub fn linon_set_field_function(v: *mut linon_view, wgsl_body: *const c_char, err: *mut c_char, err_len: usize) -> c_int;
+    /// reload_shader(device, Some(new_src), ..): the helper layer of an edited main_view.wgsl; NULL / "" = stock module
+    pub fn linon_reload_shader_source(v: *mut linon_view, wgsl_module_source: *const c_char, err: *mut c_char, err_len: usize) -> c_int;
+    pub fn linon_module_overrides(v: *mut linon_view, names: *mut c_char, names_len: usize) -> c_int;
     pub fn linon_render(v: *mut linon_view, flags: u32) -> c_int;
     pub fn linon_sync(v: *mut linon_view) -> c_int;
     pub fn linon_read(v: *mut linon_view, buffer: c_int, dst: *mut c_void, dst_bytes: usize) -> c_int;

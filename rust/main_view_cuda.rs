@@ -105,6 +105,22 @@ impl MainView {
         Ok(())
     }
 
+    /// reload_shader(device, Some(new_src), field_function), :649-690, as Application::reload_compute_shader calls it
+    /// (src/application.rs:228-232) when the watcher on src/main_view.wgsl fires (src/main.rs:206-222): the CUDA path
+    /// installs the module's helper layer (new / edited helper functions and constants); an edit to the march itself is
+    /// an Err naming the declaration, and nothing changes on any Err (:677-679).
+    pub fn reload_compute_shader(&mut self, new_src: &str) -> Result<(), String> {
+        let src = CString::new(new_src).map_err(|e| e.to_string())?;
+        let mut err = vec![0u8; 16384];
+        let rc = unsafe { sys::linon_reload_shader_source(self.view, src.as_ptr(), err.as_mut_ptr() as *mut _, err.len()) };
+        if rc != sys::LINON_OK {
+            let end = err.iter().position(|&b| b == 0).unwrap_or(err.len());
+            return Err(String::from_utf8_lossy(&err[..end]).into_owned());
+        }
+        self.needs_redraw = true;
+        Ok(())
+    }
+
     /// :752-776 — a flag instead of the (dead at HEAD) string replacement on the WGSL source
     pub fn enable_adaptive_sampling(&mut self) { self.adaptive_sampling = true; self.needs_redraw = true; }
     pub fn disable_adaptive_sampling(&mut self) { self.adaptive_sampling = false; self.needs_redraw = true; }

@@ -219,6 +219,110 @@ def test_rk4_velocity_matches_the_oracle(view, oracle, fn):
         assert mirrored.sum() > 50, int(mirrored.sum())
 
 
+# ---- whole-shader hot reload: the helper layer of an edited main_view.wgsl ---------------------
+HELPER_MODULE = """
+const swirl_gain: f32 = 0.25;
+const up_axis = vec3<f32>(0.0, 1.0, 0.0);
+fn swirl(p: vec3<f32>, v: vec3<f32>, k: f32) -> vec3<f32> {
+    let r = cross(up_axis, p);
+    if (k > 0.5) {
+        return normalize(v + swirl_gain * k * r);
+    }
+    return v;
+}
+fn rotateZ(v: vec3<f32>, phi: f32) -> vec3<f32> {
+    return vec3<f32>(cos(phi) * v.x - sin(phi) * v.y, sin(phi) * v.x + cos(phi) * v.y, v.z);
+}
+"""
+
+
+def test_reloaded_module_helpers_run_on_the_device(view):
+    rng = np.random.default_rng(5)
+    n = 4096
+    p = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    v = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    z = np.zeros_like(p)
+    t = np.zeros(n, np.float32)
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    view.reload_shader("return rotateZ(v, 0.3);")
+    stock = view.debug_eval_field(z, p, z, v, t)
+    assert np.all(stock[:, 2] == 0.0)  # the reference's rotateZ drops z (SURVEY F4)
+    try:
+        view.reload_compute_shader(HELPER_MODULE)
+        assert view.module_overrides() == ["swirl_gain", "up_axis", "swirl", "rotateZ"]
+        got = view.debug_eval_field(z, p, z, v, t)  # same body, now bound to the module's rotateZ
+        c, s_ = np.float32(np.cos(np.float32(0.3))), np.float32(np.sin(np.float32(0.3)))
+        want = np.stack([c * v[:, 0] - s_ * v[:, 1], s_ * v[:, 0] + c * v[:, 1], v[:, 2]], axis=1)
+        assert np.allclose(got, want, rtol=2e-6, atol=2e-7) and np.array_equal(got[:, 2], v[:, 2])
+        # a new helper with module constants and control flow
+        view.reload_shader("return swirl(p, v, 0.7);")
+        got = view.debug_eval_field(z, p, z, v, t)
+        w = v + np.float32(0.25) * np.float32(0.7) * np.cross(np.array([0, 1, 0], np.float32), p)
+        want = w / np.linalg.norm(w, axis=1, keepdims=True)
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+        view.reload_shader("return swirl(p, v, 0.2);")
+        assert np.array_equal(view.debug_eval_field(z, p, z, v, t), v)
+        # errors keep the installed module and kernel (src/main_view.rs:677-679)
+        with pytest.raises(LinonError) as e:
+            view.reload_compute_shader(HELPER_MODULE.replace("cross(up_axis, p)", "crossx(up_axis, p)"))
+        assert e.value.code == capi.ERR_COMPILE and "main_view.wgsl(5)" in e.value.message
+        with pytest.raises(LinonError) as e:
+            view.reload_compute_shader(HELPER_MODULE + "const eps: f32 = 0.01;")
+        assert e.value.code == capi.ERR_UNSUPPORTED and "'eps'" in e.value.message
+        assert view.module_overrides() == ["swirl_gain", "up_axis", "swirl", "rotateZ"]
+        assert np.array_equal(view.debug_eval_field(z, p, z, v, t), v)
+        # frames render through every march kernel with the helper layer installed
+        view.reload_shader("return normalize(v + 0.02 * (swirl(p, rotateZ(v, 0.01), 0.7) - v));")  # gently bent rays
+        frames = []
+        for kernel in (capi.KERNEL_TILES, capi.KERNEL_PAIRS, capi.KERNEL_REFILL):
+            view.set_option(capi.OPT_KERNEL, kernel)
+            view.render_flags(capi.RENDER_ADAPTIVE_OFF)
+            view.sync()
+            frames.append((view.hit_ids(), view.mapping_texture()))
+        for h, e_ in frames[1:]:
+            assert np.array_equal(h, frames[0][0]) and np.array_equal(e_.view(np.uint32), frames[0][1].view(np.uint32))
+        assert (frames[0][0] >= 0).mean() > 0.05
+        # the stock module cannot come back while the field function still calls a helper of the edited one - the same
+        # compile error the reference reports for reload_shader(Some(stock), body) - and nothing changes
+        with pytest.raises(LinonError) as e:
+            view.reload_compute_shader(None)
+        assert e.value.code == capi.ERR_COMPILE and "swirl" in e.value.message
+        assert view.module_overrides() == ["swirl_gain", "up_axis", "swirl", "rotateZ"]
+    finally:
+        view.set_option(capi.OPT_KERNEL, capi.KERNEL_TILES)
+        view.reload_shader("return v;")
+        view.reload_compute_shader(None)  # back to the stock module
+    assert view.module_overrides() == []
+    view.reload_shader("return rotateZ(v, 0.3);")
+    assert np.array_equal(view.debug_eval_field(z, p, z, v, t), stock)
+
+
+def test_a_helper_layer_sends_the_predefined_mirage_bodies_through_the_generic_translation(view):
+    """While a module layer is installed a helper the mirage bodies call may have been redefined, so the hand-fused
+    restatement is not spliced: the frame equals the generic fast-math build bit for bit."""
+    fn = PredefinedFunction.MirageSphericalSigmoid
+    view.set_option(capi.OPT_MATH, capi.MATH_FAST)
+    view.reload_shader(fn.to_code())
+
+    def frame():
+        view.render_flags(capi.RENDER_ADAPTIVE_OFF)
+        view.sync()
+        return view.hit_ids(), view.mapping_texture()
+
+    try:
+        view.set_option(capi.OPT_SPECIALIZE, 0)
+        generic = frame()
+        view.set_option(capi.OPT_SPECIALIZE, 1)
+        fused = frame()
+        view.reload_compute_shader("fn unrelated(a: f32) -> f32 { return a + 1.0; }")
+        layered = frame()
+        assert np.array_equal(layered[0], generic[0]) and np.array_equal(layered[1].view(np.uint32), generic[1].view(np.uint32))
+        assert not np.array_equal(fused[1].view(np.uint32), generic[1].view(np.uint32))  # the splice was really off
+    finally:
+        view.set_option(capi.OPT_SPECIALIZE, 1)
+        view.reload_compute_shader(None)
+
+
 def test_user_edited_function_runs_and_errors_keep_the_old_kernel(view):
     view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
     body = "var q = p * 2.0;\nif (t > 1.0) { q = q + vec3<f32>(1.0, 0.0, 0.0); }\nreturn q.zyx + v0 * settings.field_weight;"
