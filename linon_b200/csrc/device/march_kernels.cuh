@@ -74,6 +74,12 @@
 #ifndef LINON_N_GROUPS
 #define LINON_N_GROUPS LINON_N_FACES  // plane groups: runs of consecutive coplanar faces (built by the host)
 #endif
+#ifndef LINON_N_P1
+#define LINON_N_P1 LINON_N_GROUPS  // first pass of a culling check: planes of the clusters that enclose the scene ...
+#endif
+#ifndef LINON_N_BOXES
+#define LINON_N_BOXES 0            // ... and one bounding box for every other cluster (host: mesh_tables.hpp)
+#endif
 #ifndef LINON_PROFILE
 #define LINON_PROFILE 0  // 1: the persistent kernel also accumulates per-section clock64 cycles (developer aid)
 #endif
@@ -110,7 +116,8 @@ struct MarchParams {
     int local_rows;               // rows this shard renders
     int shard_rank, shard_world;  // row blocks are dealt round-robin: block b -> rank b % world
     int rows_per_block;
-    const float4* tris;           // LINON_N_FACES x {v0, e1, e2}, then LINON_N_GROUPS x {unit normal, plane offset}
+    const float4* tris;           // LINON_N_FACES x {v0, e1, e2}, then LINON_N_GROUPS x {unit normal, plane offset}, then the
+                                  // first-pass bounds: LINON_N_P1 x {unit normal, offset}, LINON_N_BOXES x {lo, hi}
     const int* group_range;       // LINON_N_GROUPS x (first face | face count << 16)
     uchar4* raycast;              // [height][width]  ray_casting_texture (rgba8unorm); a shard writes only its rows
     float4* endpoint;             // [height][width]  mapping_texture (rgba32float)
@@ -349,20 +356,39 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
 #endif
 }
 
-// First pass of a culling check: the smallest computed plane distance and nothing else (5 instructions per group,
-// branch-free).  The sums are the ones intersect_mesh forms, so the value equals its min_plane_dist bit for bit.  When it
-// exceeds the reach, intersect_mesh would test no face at all and the caller skips it - including normalize(step_dir)
-// and length(step_dir), which only feed it.
+// First pass of a culling check: a lower bound of the distance from `origin` to any triangle, and nothing else.
+// The mesh is clustered on the host (mesh_tables.hpp): the clusters that enclose the scene (the room of the Cornell box)
+// contribute the planes of their groups - 5 instructions per plane, the same sums as intersect_mesh - and every other
+// cluster (light, short box, tall box) ONE inflated bounding box (13 instructions), because the planes of the rotated
+// inner boxes cut through the whole room and past the camera: with plane distances alone a ray paid ~20 checks per
+// crossing of such an extension for a box it never came near.  Every triangle lies in its plane and inside its
+// cluster's box, so the value bounds the distance to the geometry from below; the margins of SafeDistance and of the
+// reach (orders of magnitude above the rounding of either evaluation, the same assumption level 1 makes) do the rest.
+// When the bound exceeds the reach no face can be hit on this step and the caller skips intersect_mesh - including
+// normalize(step_dir) and length(step_dir), which only feed it.
 #if LINON_CULL && !LINON_BVH
-__device__ __forceinline__ float nearest_plane_distance(const float4* __restrict__ s_tri, vec3f origin) {
-    const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES;
+__device__ __forceinline__ float nearest_geometry_distance(const float4* __restrict__ s_tri, vec3f origin) {
+    const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES + LINON_N_GROUPS;
     float nearest = 3.0e38f;
 #pragma unroll LINON_GROUP_UNROLL
-    for (int g = 0; g < LINON_N_GROUPS; ++g) {
+    for (int g = 0; g < LINON_N_P1; ++g) {
         const float4 pl = s_plane[g];
         const float sigma = __fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w)));
         nearest = fminf(nearest, fabsf(sigma));
     }
+#if LINON_N_BOXES > 0
+    const float4* __restrict__ s_box = s_plane + LINON_N_P1;
+    float nearest2 = 3.0e38f;
+#pragma unroll 3
+    for (int b = 0; b < LINON_N_BOXES; ++b) {
+        const float4 lo = s_box[2 * b], hi = s_box[2 * b + 1];
+        const float dx = fmaxf(fmaxf(lo.x - origin.x, origin.x - hi.x), 0.0f);
+        const float dy = fmaxf(fmaxf(lo.y - origin.y, origin.y - hi.y), 0.0f);
+        const float dz = fmaxf(fmaxf(lo.z - origin.z, origin.z - hi.z), 0.0f);
+        nearest2 = fminf(nearest2, dx * dx + dy * dy + dz * dz);
+    }
+    nearest = fminf(nearest, sqrtf(nearest2));
+#endif
     return nearest;
 }
 #endif
@@ -441,7 +467,7 @@ __device__ __forceinline__ unsigned char unorm8(float x) {
 }
 __device__ __forceinline__ uchar4 pack_color(vec3f c) { return make_uchar4(unorm8(c.x), unorm8(c.y), unorm8(c.z), 255); }
 
-#define LINON_MESH_F4 (3 * LINON_N_FACES + LINON_N_GROUPS)
+#define LINON_MESH_F4 (3 * LINON_N_FACES + LINON_N_GROUPS + LINON_N_P1 + 2 * LINON_N_BOXES)
 __device__ __forceinline__ void stage_mesh(float4* s_tri, int* s_range, const MarchParams& P) {
     for (int i = threadIdx.x; i < LINON_MESH_F4; i += blockDim.x) s_tri[i] = P.tris[i];
     for (int i = threadIdx.x; i < LINON_N_GROUPS; i += blockDim.x) s_range[i] = P.group_range[i];
@@ -618,18 +644,21 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     // rare.  With the default step (0.1, a tenth of the room) most checks do find a plane in reach and the
                     // first pass would be paid on top (measured: +30 % on the 51-step frames), so it is compiled out.
                     constexpr bool two_pass = LINON_H_INITIAL < 0.01f;
-                    float nearest = two_pass ? nearest_plane_distance(s_tri, r.p) : 0.0f;
+                    float nearest = two_pass ? nearest_geometry_distance(s_tri, r.p) : 0.0f;
                     if (!two_pass || !(nearest > SafeDistance::reach_bound(v_inf, kh, p_l1)))
 #else
-                    float nearest;
+                    float nearest = 0.0f;
 #endif
                     {
                         const vec3f step_dir = r.dir * h;
                         const float max_dist = w_length(step_dir);
                         const vec3f dirn = w_normalize(step_dir);
-                        float t_hit;
+                        float t_hit, plane_nearest;
                         int id;
-                        intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
+                        intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, plane_nearest, cnt.face_tests);
+                        // both are lower bounds of the distance to the geometry: keep the better one (inside a cluster's
+                        // box the first-pass bound is 0 and the plane distances take over)
+                        nearest = fmaxf(nearest, plane_nearest);
                         if (t_hit > 0.0f && t_hit < max_dist) {
                             color = shade(s_tri, id, dirn);
                             hit = LINON_FACE_ID(s_tri, id);

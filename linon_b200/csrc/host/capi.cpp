@@ -29,6 +29,8 @@
 
 #include "../device/static_kernels.h"
 #include "functions.hpp"
+#include "mesh_tables.hpp"
+#include "scene.hpp"
 #include "wgsl_translate.h"
 
 namespace {
@@ -125,6 +127,7 @@ static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view
 struct Variant {
     float h_initial;
     int adaptive, n_faces, n_groups, cull, math, block, unroll, refill_min, max_regs, profile;
+    int n_p1, n_boxes;    // first pass of a culling check: planes of the enclosing clusters + one bounding box per other cluster
     int bvh;              // 1: large mesh, faces + bounding-volume hierarchy in global memory (n_faces / n_groups are 0 then)
     int fw_one;           // 1: settings.field_weight == 1 (the application's default): cur_dir = v without the blend
     int specialize;       // 1: fast math may splice the hand-fused restatement of a predefined mirage body
@@ -227,6 +230,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
                                      "-DLINON_ADAPTIVE=" + std::to_string(var.adaptive),
                                      "-DLINON_N_FACES=" + std::to_string(var.n_faces),
                                      "-DLINON_N_GROUPS=" + std::to_string(var.n_groups),
+                                     "-DLINON_N_P1=" + std::to_string(var.n_p1),
+                                     "-DLINON_N_BOXES=" + std::to_string(var.n_boxes),
                                      "-DLINON_CULL=" + std::to_string(var.cull),
                                      "-DLINON_FACE_UNROLL=" + std::to_string(var.unroll),
                                      "-DLINON_BLOCK=" + std::to_string(var.block),
@@ -286,7 +291,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
 }
 
 std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
-    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.cull, v.math,
+    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.cull, v.math,
                v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh) + body;
 }
 
@@ -305,7 +310,7 @@ struct linon_view {
     linon_camera camera{};
     bool has_camera = false;
     linon_settings settings{};
-    uint32_t n_faces = 0, n_groups = 0;
+    uint32_t n_faces = 0, n_groups = 0, n_p1 = 0, n_boxes = 0;
     float plane_w_max = 0.0f;  // max |offset| of the plane groups (BVH meshes: max |coordinate|)
     linon::ModuleLayer layer;  // helper layer of an edited main_view.wgsl (linon_reload_shader_source); empty = stock module
     bool use_bvh = false;      // mesh beyond the shared-memory stage: faces in hierarchy order + nodes in global memory
@@ -444,6 +449,21 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     return LINON_OK;
 }
 
+// Table sizes of the start-up mesh (src/application.rs:105-123), for builds that happen before a mesh is bound
+void default_mesh_counts(Variant& var) {
+    static const linon::MeshTables t = [] {
+        linon::MeshTables m;
+        const linon::Mesh mesh = linon::default_scene(nullptr);
+        linon::build_mesh_tables(mesh.vertices.data(), (uint32_t)(mesh.vertices.size() / 3), mesh.indices.data(),
+                                 (uint32_t)(mesh.indices.size() / 3), m);
+        return m;
+    }();
+    var.n_faces = (int)(t.tris.size() / 12);
+    var.n_groups = (int)t.n_groups();
+    var.n_p1 = (int)t.n_p1();
+    var.n_boxes = (int)t.n_boxes();
+}
+
 Variant make_variant(const linon_view* v, uint32_t flags) {
     Variant var;
     var.h_initial = (flags & LINON_RENDER_ENHANCE) ? 0.001f : 0.1f;  // src/main_view.rs:785-787
@@ -452,6 +472,8 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.bvh = v->use_bvh ? 1 : 0;
     var.n_faces = v->use_bvh ? 1 : (int)v->n_faces;   // the hierarchy kernels do not depend on the face count
     var.n_groups = v->use_bvh ? 1 : (int)v->n_groups;
+    var.n_p1 = v->use_bvh ? 1 : (int)v->n_p1;
+    var.n_boxes = v->use_bvh ? 0 : (int)v->n_boxes;
     var.cull = v->opt_cull;
     var.math = v->opt_math;
     var.block = v->opt_block;
@@ -734,63 +756,16 @@ int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const ui
     faces = v->host_faces.data();
     if (n_faces > kSharedMeshFaces || v->opt_force_bvh) return set_mesh_bvh(v, verts, n_verts, faces, n_faces);
     v->use_bvh = false;
-    // {v0, e1, e2} per face; the two subtractions are the ones hit_triangle performs (src/main_view.wgsl:152-153)
-    std::vector<float> tris((size_t)n_faces * 12, 0.0f);
-    for (uint32_t i = 0; i < n_faces; ++i) {
-        const uint32_t ia = faces[3 * i], ib = faces[3 * i + 1], ic = faces[3 * i + 2];
-        if (ia >= n_verts || ib >= n_verts || ic >= n_verts) return v->fail(LINON_ERR_INVALID, fmt("face %u indexes past the vertex array", i));
-        const float* a = verts + 3 * ia; const float* b = verts + 3 * ib; const float* c = verts + 3 * ic;
-        float* t = tris.data() + 12 * i;
-        for (int k = 0; k < 3; ++k) {
-            t[k] = a[k];
-            t[4 + k] = b[k] - a[k];
-            t[8 + k] = c[k] - a[k];
-        }
-    }
-    // Plane groups for the culling test of intersect_mesh: runs of consecutive faces that lie in one plane.  A face
-    // joins the current group when its three vertices are within 1e-6 (scene units are O(1) after normalisation)
-    // of the group's plane; degenerate faces get a group of their own that is never culled (zero normal, offset -inf).
-    std::vector<float> planes;
-    std::vector<int> ranges;
-    {
-        auto plane_of = [&](uint32_t i, double n[3], double& d0) {
-            const float* t = tris.data() + 12 * i;
-            const double e1[3] = {t[4], t[5], t[6]}, e2[3] = {t[8], t[9], t[10]};
-            n[0] = e1[1] * e2[2] - e1[2] * e2[1];
-            n[1] = e1[2] * e2[0] - e1[0] * e2[2];
-            n[2] = e1[0] * e2[1] - e1[1] * e2[0];
-            const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-            if (!(len > 1e-20)) return false;
-            for (int k = 0; k < 3; ++k) n[k] /= len;
-            d0 = n[0] * t[0] + n[1] * t[1] + n[2] * t[2];
-            return true;
-        };
-        uint32_t i = 0;
-        while (i < n_faces) {
-            double n[3], d0 = 0.0;
-            const bool ok = plane_of(i, n, d0);
-            uint32_t j = i + 1;
-            if (ok) {
-                for (; j < n_faces && j - i < 64; ++j) {
-                    const float* t = tris.data() + 12 * j;
-                    bool coplanar = true;
-                    for (int vtx = 0; vtx < 3 && coplanar; ++vtx) {
-                        double p[3];
-                        for (int k = 0; k < 3; ++k) p[k] = (double)t[k] + (vtx == 1 ? t[4 + k] : vtx == 2 ? t[8 + k] : 0.0f);
-                        if (std::fabs(n[0] * p[0] + n[1] * p[1] + n[2] * p[2] - d0) > 1e-6) coplanar = false;
-                    }
-                    if (!coplanar) break;
-                }
-                planes.insert(planes.end(), {(float)n[0], (float)n[1], (float)n[2], (float)d0});
-            } else {
-                planes.insert(planes.end(), {0.0f, 0.0f, 0.0f, 0.0f});  // distance 0 <= reach: always tested
-            }
-            ranges.push_back((int)i | (int)((j - i) << 16));
-            i = j;
-        }
-    }
-    const uint32_t n_groups = (uint32_t)ranges.size();
-    tris.insert(tris.end(), planes.begin(), planes.end());
+    // faces, plane groups and the first-pass bounds (mesh_tables.hpp)
+    linon::MeshTables mt;
+    uint32_t bad = 0;
+    if (!linon::build_mesh_tables(verts, n_verts, faces, n_faces, mt, &bad))
+        return v->fail(LINON_ERR_INVALID, fmt("face %u indexes past the vertex array", bad));
+    std::vector<float> tris = mt.tris;
+    tris.insert(tris.end(), mt.planes.begin(), mt.planes.end());
+    tris.insert(tris.end(), mt.p1_planes.begin(), mt.p1_planes.end());
+    tris.insert(tris.end(), mt.boxes.begin(), mt.boxes.end());
+    const std::vector<int>& ranges = mt.ranges;
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
     cudaFree(v->d_tris);
@@ -801,10 +776,11 @@ int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const ui
     CK(v, cudaMemcpy(v->d_tris, tris.data(), tris.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(v, cudaMalloc(&v->d_group_range, ranges.size() * sizeof(int)));
     CK(v, cudaMemcpy(v->d_group_range, ranges.data(), ranges.size() * sizeof(int), cudaMemcpyHostToDevice));
-    v->n_groups = n_groups;
+    v->n_groups = mt.n_groups();
+    v->n_p1 = mt.n_p1();
+    v->n_boxes = mt.n_boxes();
     v->n_faces = n_faces;
-    v->plane_w_max = 0.0f;
-    for (size_t g = 0; g < planes.size() / 4; ++g) v->plane_w_max = std::max(v->plane_w_max, std::fabs(planes[4 * g + 3]));
+    v->plane_w_max = mt.coord_max;
     return LINON_OK;
 }
 
@@ -846,7 +822,7 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
     const std::string previous = v->body;
     v->body = wgsl_body;  // make_variant consults pair_unfit for the body being installed
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
-    if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
+    if (var.n_faces == 0) default_mesh_counts(var);
     Module* m = nullptr;
     float jit = 0.0f;
     const int rc = get_module_for_body(v, v->body, var, &m, &jit);
@@ -876,7 +852,7 @@ int linon_reload_shader_source(linon_view* v, const char* wgsl_module_source, ch
     const linon::ModuleLayer previous = v->layer;
     v->layer = layer;
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
-    if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
+    if (var.n_faces == 0) default_mesh_counts(var);
     Module* m = nullptr;
     float jit = 0.0f;
     const int rc = get_module_for_body(v, v->body, var, &m, &jit);
@@ -1155,7 +1131,8 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (!wgsl_body) return LINON_ERR_INVALID;
     linon_view tmp;
     tmp.n_faces = n_faces;
-    tmp.n_groups = n_faces == 36 ? 15 : n_faces;  // the Cornell box has 15 plane groups
+    tmp.n_groups = tmp.n_p1 = n_faces;  // an arbitrary mesh of that size: every face its own plane group, no boxes
+    if (n_faces == 36) tmp.n_faces = 0;  // the start-up mesh: make_variant's caller fills the real table sizes
     if (n_faces > kSharedMeshFaces) tmp.use_bvh = true;
     tmp.opt_math = math_mode;
     tmp.body = wgsl_body;
@@ -1175,6 +1152,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (const char* k = getenv("LINON_CHECK_SPECIALIZE")) tmp.opt_specialize = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BVH")) tmp.use_bvh = atoi(k) != 0;
     Variant var = make_variant(&tmp, flags);
+    if (var.n_faces == 0 && !tmp.use_bvh) default_mesh_counts(var);
     std::vector<char> cubin;
     std::string log;
     bool ok = compile_cubin(wgsl_body, var, tmp.layer, cubin, log);
@@ -1257,7 +1235,7 @@ struct DevBuf {
 };
 int debug_module(linon_view* v, Module** m) {
     Variant var = make_variant(v, LINON_RENDER_DEFAULT);
-    if (var.n_faces == 0) { var.n_faces = 36; var.n_groups = 15; }
+    if (var.n_faces == 0) default_mesh_counts(var);
     return get_module_for_body(v, v->body, var, m, nullptr);
 }
 }  // namespace

@@ -1,0 +1,186 @@
+// mesh_tables.hpp — what the march kernels stage into shared memory for a mesh of up to 1024 faces (host side, pure).
+//
+//   faces     n_faces x {v0, e1 = v1 - v0, e2 = v2 - v0} (3 x float4): the two subtractions hit_triangle performs
+//             (src/main_view.wgsl:152-153), done once
+//   planes    one {unit normal, offset} per PLANE GROUP = run of consecutive coplanar faces (level 1 of the exact culling,
+//             see intersect_mesh in device/march_kernels.cuh); `ranges` holds (first face | count << 16)
+//   bounds    the first pass of a culling check (nearest_geometry_distance): a lower bound of the distance from a point
+//             to any triangle.  A plane group that spans the scene along two axes (floor, ceiling, walls of the Cornell box)
+//             keeps its plane - near it the plane IS the geometry.  The other groups are clustered by connectivity (faces
+//             sharing a vertex position) and each cluster (the short box, the tall box) contributes ONE axis-aligned
+//             bounding box instead of its planes: the planes of
+//             the rotated inner boxes cut through the whole room and past the camera, so with plane distances alone every
+//             ray crossing one of those extensions paid ~20 checks for a box it never came near.
+//             Boxes are inflated outwards (1e-6 relative + absolute) so rounding of the distance evaluation stays inside the
+//             margins of SafeDistance.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <numeric>
+#include <tuple>
+#include <vector>
+
+namespace linon {
+
+struct MeshTables {
+    std::vector<float> tris;     // 12 floats per face
+    std::vector<float> planes;   // 4 floats per group
+    std::vector<int> ranges;     // per group
+    std::vector<float> p1_planes;  // 4 floats per first-pass plane
+    std::vector<float> boxes;      // 8 floats per first-pass box {lo.xyz, 0, hi.xyz, 0}
+    float coord_max = 0.0f;        // max |plane offset| and |box coordinate| (rounding bound of SafeDistance)
+    uint32_t n_groups() const { return (uint32_t)ranges.size(); }
+    uint32_t n_p1() const { return (uint32_t)(p1_planes.size() / 4); }
+    uint32_t n_boxes() const { return (uint32_t)(boxes.size() / 8); }
+};
+
+constexpr uint32_t kMaxBoundBoxes = 24;
+
+// Returns false when a face indexes past the vertex array (bad_face = its index).
+inline bool build_mesh_tables(const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces, MeshTables& out,
+                              uint32_t* bad_face = nullptr) {
+    out = MeshTables();
+    out.tris.assign((size_t)n_faces * 12, 0.0f);
+    for (uint32_t i = 0; i < n_faces; ++i) {
+        const uint32_t ia = faces[3 * i], ib = faces[3 * i + 1], ic = faces[3 * i + 2];
+        if (ia >= n_verts || ib >= n_verts || ic >= n_verts) {
+            if (bad_face) *bad_face = i;
+            return false;
+        }
+        const float* a = verts + 3 * ia; const float* b = verts + 3 * ib; const float* c = verts + 3 * ic;
+        float* t = out.tris.data() + 12 * i;
+        for (int k = 0; k < 3; ++k) {
+            t[k] = a[k];
+            t[4 + k] = b[k] - a[k];
+            t[8 + k] = c[k] - a[k];
+        }
+    }
+    // ---- plane groups: runs of consecutive faces that lie in one plane.  A face joins the current group when its three
+    // vertices are within 1e-6 (scene units are O(1) after normalisation) of the group's plane; degenerate faces get a
+    // group of their own that is never culled (zero normal and offset: distance 0 <= reach, always tested).
+    auto plane_of = [&](uint32_t i, double n[3], double& d0) {
+        const float* t = out.tris.data() + 12 * i;
+        const double e1[3] = {t[4], t[5], t[6]}, e2[3] = {t[8], t[9], t[10]};
+        n[0] = e1[1] * e2[2] - e1[2] * e2[1];
+        n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+        n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (!(len > 1e-20)) return false;
+        for (int k = 0; k < 3; ++k) n[k] /= len;
+        d0 = n[0] * t[0] + n[1] * t[1] + n[2] * t[2];
+        return true;
+    };
+    std::vector<uint32_t> group_of_face(n_faces, 0);
+    std::vector<bool> degenerate;
+    for (uint32_t i = 0; i < n_faces;) {
+        double n[3], d0 = 0.0;
+        const bool ok = plane_of(i, n, d0);
+        uint32_t j = i + 1;
+        if (ok) {
+            for (; j < n_faces && j - i < 64; ++j) {
+                const float* t = out.tris.data() + 12 * j;
+                bool coplanar = true;
+                for (int vtx = 0; vtx < 3 && coplanar; ++vtx) {
+                    double p[3];
+                    for (int k = 0; k < 3; ++k) p[k] = (double)t[k] + (vtx == 1 ? t[4 + k] : vtx == 2 ? t[8 + k] : 0.0f);
+                    if (std::fabs(n[0] * p[0] + n[1] * p[1] + n[2] * p[2] - d0) > 1e-6) coplanar = false;
+                }
+                if (!coplanar) break;
+            }
+            out.planes.insert(out.planes.end(), {(float)n[0], (float)n[1], (float)n[2], (float)d0});
+        } else {
+            out.planes.insert(out.planes.end(), {0.0f, 0.0f, 0.0f, 0.0f});
+        }
+        degenerate.push_back(!ok);
+        for (uint32_t f = i; f < j; ++f) group_of_face[f] = (uint32_t)out.ranges.size();
+        out.ranges.push_back((int)i | (int)((j - i) << 16));
+        i = j;
+    }
+    const uint32_t G = out.n_groups();
+    for (uint32_t g = 0; g < G; ++g) out.coord_max = std::max(out.coord_max, std::fabs(out.planes[4 * g + 3]));
+
+    // ---- big groups keep their plane; small groups are clustered by connectivity and bounded by one box per cluster ----
+    struct Box { float lo[3], hi[3]; bool any = false; };
+    std::vector<Box> gbox(G);
+    Box scene;
+    auto grow = [](Box& b, const float* p) {
+        for (int k = 0; k < 3; ++k) {
+            b.lo[k] = b.any ? std::min(b.lo[k], p[k]) : p[k];
+            b.hi[k] = b.any ? std::max(b.hi[k], p[k]) : p[k];
+        }
+        b.any = true;
+    };
+    for (uint32_t f = 0; f < n_faces; ++f)
+        for (int vtx = 0; vtx < 3; ++vtx) {
+            const float* p = verts + 3 * faces[3 * f + vtx];
+            grow(gbox[group_of_face[f]], p);
+            grow(scene, p);
+        }
+    auto extent = [](const Box& b, int k) { return (double)b.hi[k] - (double)b.lo[k]; };
+    // "big": the group spans at least 75 % of the scene along two axes (a wall, the floor, the ceiling).  Near such a group
+    // its plane IS the geometry; a box around it would hold the whole room.
+    std::vector<bool> as_planes(G, false);
+    for (uint32_t g = 0; g < G; ++g) {
+        int wide = 0;
+        for (int k = 0; k < 3; ++k)
+            if (extent(scene, k) > 0.0 && extent(gbox[g], k) >= 0.75 * extent(scene, k)) ++wide;
+        as_planes[g] = degenerate[g] || wide >= 2;
+    }
+    // union-find over the vertex positions of the SMALL groups (the Cornell box repeats its corners per quad, so
+    // connectivity is by position, quantised to 1e-5; the boxes stand on the floor, which is why big groups stay out)
+    std::vector<uint32_t> parent(G);
+    std::iota(parent.begin(), parent.end(), 0u);
+    auto find = [&](uint32_t x) {
+        while (parent[x] != x) x = parent[x] = parent[parent[x]];
+        return x;
+    };
+    std::map<std::tuple<long long, long long, long long>, uint32_t> owner;
+    for (uint32_t f = 0; f < n_faces; ++f) {
+        const uint32_t g = group_of_face[f];
+        if (as_planes[g]) continue;
+        for (int vtx = 0; vtx < 3; ++vtx) {
+            const float* p = verts + 3 * faces[3 * f + vtx];
+            const auto key = std::make_tuple(std::llround((double)p[0] * 1e5), std::llround((double)p[1] * 1e5), std::llround((double)p[2] * 1e5));
+            auto it = owner.find(key);
+            if (it == owner.end()) owner.emplace(key, g);
+            else parent[find(g)] = find(it->second);
+        }
+    }
+    std::vector<Box> box(G);
+    std::vector<bool> cluster_has_box_member(G, false);
+    uint32_t n_boxes = 0;
+    for (uint32_t g = 0; g < G; ++g) {
+        if (as_planes[g]) continue;
+        const uint32_t r = find(g);
+        grow(box[r], gbox[g].lo);
+        grow(box[r], gbox[g].hi);
+        if (!cluster_has_box_member[r]) {
+            cluster_has_box_member[r] = true;
+            ++n_boxes;
+        }
+    }
+    // too many clusters (a mesh of many small parts): plane distances only - the hierarchy path serves such meshes better
+    if (n_boxes > kMaxBoundBoxes) {
+        std::fill(as_planes.begin(), as_planes.end(), true);
+        std::fill(cluster_has_box_member.begin(), cluster_has_box_member.end(), false);
+    }
+    for (uint32_t g = 0; g < G; ++g)
+        if (as_planes[g]) out.p1_planes.insert(out.p1_planes.end(), out.planes.begin() + 4 * g, out.planes.begin() + 4 * g + 4);
+    for (uint32_t r = 0; r < G; ++r) {
+        if (!cluster_has_box_member[r]) continue;
+        const Box& b = box[r];
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            const float pad = 1e-6f * (1.0f + std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+            lo[k] = std::nextafter(b.lo[k] - pad, -INFINITY);
+            hi[k] = std::nextafter(b.hi[k] + pad, INFINITY);
+            out.coord_max = std::max(out.coord_max, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+        }
+        out.boxes.insert(out.boxes.end(), {lo[0], lo[1], lo[2], 0.0f, hi[0], hi[1], hi[2], 0.0f});
+    }
+    return true;
+}
+
+}  // namespace linon
