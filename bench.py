@@ -207,6 +207,9 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # the contract is ONE JSON line on stdout: NCCL_DEBUG=VERSION (set on the GPU boxes) would print its banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, H = workload_size(world)
