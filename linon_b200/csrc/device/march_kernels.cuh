@@ -80,6 +80,9 @@
 #ifndef LINON_N_BOXES
 #define LINON_N_BOXES 0            // ... and one bounding box for every other cluster (host: mesh_tables.hpp)
 #endif
+#ifndef LINON_N_SEGS
+#define LINON_N_SEGS 1             // runs of consecutive plane groups that share a bound (one run of all groups = no boxes)
+#endif
 #ifndef LINON_PROFILE
 #define LINON_PROFILE 0  // 1: the persistent kernel also accumulates per-section clock64 cycles (developer aid)
 #endif
@@ -118,7 +121,8 @@ struct MarchParams {
     int rows_per_block;
     const float4* tris;           // LINON_N_FACES x {v0, e1, e2}, then LINON_N_GROUPS x {unit normal, plane offset}, then the
                                   // first-pass bounds: LINON_N_P1 x {unit normal, offset}, LINON_N_BOXES x {lo, hi}
-    const int* group_range;       // LINON_N_GROUPS x (first face | face count << 16)
+    const int* group_range;       // LINON_N_GROUPS x (first face | face count << 16), then LINON_N_SEGS x
+                                  // (first group | group count << 12 | (box + 1) << 24)
     uchar4* raycast;              // [height][width]  ray_casting_texture (rgba8unorm); a shard writes only its rows
     float4* endpoint;             // [height][width]  mapping_texture (rgba32float)
     int* hit_id;                  // [height][width]  face index of the first hit, -1 = none
@@ -318,34 +322,66 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
     const float reach = 1.002f * max_dist + 1e-5f * (1.0f + origin_l1);
     const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES;
     float nearest = 3.0e38f;
-    // partial unroll on purpose: a fully unrolled loop lets the compiler hoist all plane loads out of the time loop
-    // (60 live registers, spills); with a loop-carried index the planes stay in shared memory (broadcast LDS.128)
-#pragma unroll LINON_GROUP_UNROLL
-    for (int g = 0; g < LINON_N_GROUPS; ++g) {
-        const float4 pl = s_plane[g];
-        const float sigma = __fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w)));
-        const float dist = fabsf(sigma);
-        nearest = fminf(nearest, dist);
-        if (dist <= reach) {
-            // Second look, only for groups in reach: the segment must also CROSS the plane.  With long steps (h = 0.1)
-            // most planes in reach are approached obliquely or left behind; their face tests ran with one or two
-            // active lanes each and made default-step frames three times dearer than the arithmetic (ncu: 10.7 of 32
-            // lanes active).  sigma is the signed distance at the origin, sigma_end at the end of the segment
-            // (direction is a unit vector); same sign and both farther than the margin -> no face of the group can
-            // report t in (eps, max_dist).  The margin is 20x the absolute slack of the reach test.
-            const float sigma_end = __fmaf_rn(__fmaf_rn(direction.x, pl.x, __fmaf_rn(direction.y, pl.y, direction.z * pl.z)),
-                                              max_dist, sigma);
-            const bool same_side = sigma * sigma_end > 0.0f && fminf(dist, fabsf(sigma_end)) > 2e-4f * (1.0f + origin_l1);
-            if (!same_side) {
-                const int range = s_range[g];
-                const int first = range & 0xffff, last = first + (range >> 16);
+    // The groups are walked in index order (the reference's tie-break), one SEGMENT at a time: a run of consecutive groups
+    // whose cluster is bounded by a box (mesh_tables.hpp) is skipped as a whole when that box is farther than the reach -
+    // every face of the run lies inside the (inflated) box, so none can report t in (eps, max_dist); same argument and
+    // margins as the hierarchy traversal above.  A skipped run feeds its box distance into the lower bound; a visited
+    // one the larger of its box distance and its smallest plane distance (both bound the distance to its faces).
+#if LINON_N_BOXES > 0
+    const float reach2 = reach * reach * 1.0001f;
+    const float4* __restrict__ s_box = s_plane + LINON_N_GROUPS + LINON_N_P1;
+#endif
 #pragma unroll 1
-                for (int i = first; i < last; ++i) {
-                    test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
-                    ++face_tests;
+    for (int sg = 0; sg < LINON_N_SEGS; ++sg) {
+        const int seg = s_range[LINON_N_GROUPS + sg];
+        const int g_first = seg & 0xfff, g_last = g_first + ((seg >> 12) & 0xfff);
+        float box_dist = 0.0f;
+#if LINON_N_BOXES > 0
+        const int box = (seg >> 24) - 1;
+        if (box >= 0) {
+            const float4 lo = s_box[2 * box], hi = s_box[2 * box + 1];
+            const float dx = fmaxf(fmaxf(lo.x - origin.x, origin.x - hi.x), 0.0f);
+            const float dy = fmaxf(fmaxf(lo.y - origin.y, origin.y - hi.y), 0.0f);
+            const float dz = fmaxf(fmaxf(lo.z - origin.z, origin.z - hi.z), 0.0f);
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            box_dist = sqrtf(d2);
+            if (d2 > reach2) {  // NaN compares false -> the run is tested
+                nearest = fminf(nearest, box_dist);
+                continue;
+            }
+        }
+#endif
+        float seg_nearest = 3.0e38f;
+        // partial unroll on purpose: a fully unrolled loop lets the compiler hoist all plane loads out of the time loop
+        // (60 live registers, spills); with a loop-carried index the planes stay in shared memory (broadcast LDS.128)
+#pragma unroll LINON_GROUP_UNROLL
+        for (int g = g_first; g < g_last; ++g) {
+            const float4 pl = s_plane[g];
+            const float sigma = __fmaf_rn(origin.x, pl.x, __fmaf_rn(origin.y, pl.y, __fmaf_rn(origin.z, pl.z, -pl.w)));
+            const float dist = fabsf(sigma);
+            seg_nearest = fminf(seg_nearest, dist);
+            if (dist <= reach) {
+                // Second look, only for groups in reach: the segment must also CROSS the plane.  With long steps (h = 0.1)
+                // most planes in reach are approached obliquely or left behind; their face tests ran with one or two
+                // active lanes each and made default-step frames three times dearer than the arithmetic (ncu: 10.7 of 32
+                // lanes active).  sigma is the signed distance at the origin, sigma_end at the end of the segment
+                // (direction is a unit vector); same sign and both farther than the margin -> no face of the group can
+                // report t in (eps, max_dist).  The margin is 20x the absolute slack of the reach test.
+                const float sigma_end = __fmaf_rn(__fmaf_rn(direction.x, pl.x, __fmaf_rn(direction.y, pl.y, direction.z * pl.z)),
+                                                  max_dist, sigma);
+                const bool same_side = sigma * sigma_end > 0.0f && fminf(dist, fabsf(sigma_end)) > 2e-4f * (1.0f + origin_l1);
+                if (!same_side) {
+                    const int range = s_range[g];
+                    const int first = range & 0xffff, last = first + (range >> 16);
+#pragma unroll 1
+                    for (int i = first; i < last; ++i) {
+                        test_face(s_tri, i, origin, direction, max_dist, t_best, id_best);
+                        ++face_tests;
+                    }
                 }
             }
         }
+        nearest = fminf(nearest, fmaxf(seg_nearest, box_dist));
     }
     min_plane_dist = nearest;
 #else
@@ -470,7 +506,7 @@ __device__ __forceinline__ uchar4 pack_color(vec3f c) { return make_uchar4(unorm
 #define LINON_MESH_F4 (3 * LINON_N_FACES + LINON_N_GROUPS + LINON_N_P1 + 2 * LINON_N_BOXES)
 __device__ __forceinline__ void stage_mesh(float4* s_tri, int* s_range, const MarchParams& P) {
     for (int i = threadIdx.x; i < LINON_MESH_F4; i += blockDim.x) s_tri[i] = P.tris[i];
-    for (int i = threadIdx.x; i < LINON_N_GROUPS; i += blockDim.x) s_range[i] = P.group_range[i];
+    for (int i = threadIdx.x; i < LINON_N_GROUPS + LINON_N_SEGS; i += blockDim.x) s_range[i] = P.group_range[i];
     __syncthreads();
 }
 #if LINON_BVH
@@ -480,7 +516,7 @@ __device__ __forceinline__ void stage_mesh(float4* s_tri, int* s_range, const Ma
 #else
 #define LINON_MESH_PROLOGUE(P)                   \
     __shared__ float4 s_tri[LINON_MESH_F4];      \
-    __shared__ int s_range[LINON_N_GROUPS];      \
+    __shared__ int s_range[LINON_N_GROUPS + LINON_N_SEGS]; \
     stage_mesh(s_tri, s_range, P);
 #define LINON_FACE_ID(tris, slot) (slot)
 #endif

@@ -127,6 +127,7 @@ static_assert(sizeof(linon_settings) == 24, "Settings is 24 bytes (src/main_view
 struct Variant {
     float h_initial;
     int adaptive, n_faces, n_groups, cull, math, block, unroll, refill_min, max_regs, profile;
+    int n_segs;           // runs of consecutive plane groups that share a bound (intersect_mesh skips a run whose box is out of reach)
     int n_p1, n_boxes;    // first pass of a culling check: planes of the enclosing clusters + one bounding box per other cluster
     int bvh;              // 1: large mesh, faces + bounding-volume hierarchy in global memory (n_faces / n_groups are 0 then)
     int fw_one;           // 1: settings.field_weight == 1 (the application's default): cur_dir = v without the blend
@@ -232,6 +233,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
                                      "-DLINON_N_GROUPS=" + std::to_string(var.n_groups),
                                      "-DLINON_N_P1=" + std::to_string(var.n_p1),
                                      "-DLINON_N_BOXES=" + std::to_string(var.n_boxes),
+                                     "-DLINON_N_SEGS=" + std::to_string(var.n_segs),
                                      "-DLINON_CULL=" + std::to_string(var.cull),
                                      "-DLINON_FACE_UNROLL=" + std::to_string(var.unroll),
                                      "-DLINON_BLOCK=" + std::to_string(var.block),
@@ -291,7 +293,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
 }
 
 std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
-    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.cull, v.math,
+    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
                v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh) + body;
 }
 
@@ -310,7 +312,7 @@ struct linon_view {
     linon_camera camera{};
     bool has_camera = false;
     linon_settings settings{};
-    uint32_t n_faces = 0, n_groups = 0, n_p1 = 0, n_boxes = 0;
+    uint32_t n_faces = 0, n_groups = 0, n_p1 = 0, n_boxes = 0, n_segs = 0;
     float plane_w_max = 0.0f;  // max |offset| of the plane groups (BVH meshes: max |coordinate|)
     linon::ModuleLayer layer;  // helper layer of an edited main_view.wgsl (linon_reload_shader_source); empty = stock module
     bool use_bvh = false;      // mesh beyond the shared-memory stage: faces in hierarchy order + nodes in global memory
@@ -462,6 +464,7 @@ void default_mesh_counts(Variant& var) {
     var.n_groups = (int)t.n_groups();
     var.n_p1 = (int)t.n_p1();
     var.n_boxes = (int)t.n_boxes();
+    var.n_segs = (int)t.n_segments();
 }
 
 Variant make_variant(const linon_view* v, uint32_t flags) {
@@ -474,6 +477,7 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.n_groups = v->use_bvh ? 1 : (int)v->n_groups;
     var.n_p1 = v->use_bvh ? 1 : (int)v->n_p1;
     var.n_boxes = v->use_bvh ? 0 : (int)v->n_boxes;
+    var.n_segs = v->use_bvh ? 1 : (int)v->n_segs;
     var.cull = v->opt_cull;
     var.math = v->opt_math;
     var.block = v->opt_block;
@@ -765,7 +769,8 @@ int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const ui
     tris.insert(tris.end(), mt.planes.begin(), mt.planes.end());
     tris.insert(tris.end(), mt.p1_planes.begin(), mt.p1_planes.end());
     tris.insert(tris.end(), mt.boxes.begin(), mt.boxes.end());
-    const std::vector<int>& ranges = mt.ranges;
+    std::vector<int> ranges = mt.ranges;  // per group, then the segments
+    ranges.insert(ranges.end(), mt.segments.begin(), mt.segments.end());
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
     cudaFree(v->d_tris);
@@ -779,6 +784,7 @@ int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const ui
     v->n_groups = mt.n_groups();
     v->n_p1 = mt.n_p1();
     v->n_boxes = mt.n_boxes();
+    v->n_segs = mt.n_segments();
     v->n_faces = n_faces;
     v->plane_w_max = mt.coord_max;
     return LINON_OK;
@@ -1132,6 +1138,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     linon_view tmp;
     tmp.n_faces = n_faces;
     tmp.n_groups = tmp.n_p1 = n_faces;  // an arbitrary mesh of that size: every face its own plane group, no boxes
+    tmp.n_segs = 1;
     if (n_faces == 36) tmp.n_faces = 0;  // the start-up mesh: make_variant's caller fills the real table sizes
     if (n_faces > kSharedMeshFaces) tmp.use_bvh = true;
     tmp.opt_math = math_mode;

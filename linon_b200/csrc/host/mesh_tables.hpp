@@ -27,13 +27,15 @@ namespace linon {
 struct MeshTables {
     std::vector<float> tris;     // 12 floats per face
     std::vector<float> planes;   // 4 floats per group
-    std::vector<int> ranges;     // per group
+    std::vector<int> ranges;     // per group: first face | face count << 16
+    std::vector<int> segments;   // runs of consecutive groups with the same bound: first group | count << 12 | (box + 1) << 24
     std::vector<float> p1_planes;  // 4 floats per first-pass plane
     std::vector<float> boxes;      // 8 floats per first-pass box {lo.xyz, 0, hi.xyz, 0}
     float coord_max = 0.0f;        // max |plane offset| and |box coordinate| (rounding bound of SafeDistance)
     uint32_t n_groups() const { return (uint32_t)ranges.size(); }
     uint32_t n_p1() const { return (uint32_t)(p1_planes.size() / 4); }
     uint32_t n_boxes() const { return (uint32_t)(boxes.size() / 8); }
+    uint32_t n_segments() const { return (uint32_t)segments.size(); }
 };
 
 constexpr uint32_t kMaxBoundBoxes = 24;
@@ -168,8 +170,10 @@ inline bool build_mesh_tables(const float* verts, uint32_t n_verts, const uint32
     }
     for (uint32_t g = 0; g < G; ++g)
         if (as_planes[g]) out.p1_planes.insert(out.p1_planes.end(), out.planes.begin() + 4 * g, out.planes.begin() + 4 * g + 4);
+    std::vector<int> box_index(G, -1);
     for (uint32_t r = 0; r < G; ++r) {
         if (!cluster_has_box_member[r]) continue;
+        box_index[r] = (int)(out.boxes.size() / 8);
         const Box& b = box[r];
         float lo[3], hi[3];
         for (int k = 0; k < 3; ++k) {
@@ -179,6 +183,15 @@ inline bool build_mesh_tables(const float* verts, uint32_t n_verts, const uint32
             out.coord_max = std::max(out.coord_max, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
         }
         out.boxes.insert(out.boxes.end(), {lo[0], lo[1], lo[2], 0.0f, hi[0], hi[1], hi[2], 0.0f});
+    }
+    // segments: intersect_mesh walks the groups in index order (the reference's tie-break) and skips a whole run of groups
+    // when the box of their cluster is out of reach
+    for (uint32_t g = 0; g < G;) {
+        const int b = as_planes[g] ? -1 : box_index[find(g)];
+        uint32_t e = g + 1;
+        while (e < G && e - g < 4095 && (as_planes[e] ? -1 : box_index[find(e)]) == b) ++e;
+        out.segments.push_back((int)g | (int)((e - g) << 12) | ((b + 1) << 24));
+        g = e;
     }
     return true;
 }
