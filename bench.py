@@ -113,44 +113,64 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def oracle_sample(w: int, h: int, budget_s: float, threads: int = 0):
-    """Times the CPU restatement of the reference on a bounded sample of the same frame: every `stride`-th row, full
-    width (pixels are independent; cost is per ray), sized by a short calibration run to ~budget_s seconds."""
-    import numpy as np
+def cpu_reference():
+    """The CPU implementation timed beside the GPU path.  oracle/_ref (the reference's own WGSL, transpiled mechanically
+    to C++ by oracle/wgsl_ref and compiled with gcc; built where /root/reference is mounted, the .so travels) when it
+    exists -> kind "reference"; otherwise the hand-written restatement oracle/linon_oracle.cpp -> kind "port".  The two
+    are bit-identical (tests/test_wgsl_reference_cpu.py)."""
+    from oracle import wgsl_reference as wr
+    if wr.available():
+        wr.build()
+        return wr, "reference"
     from oracle import cpu_oracle as co
+    co.build()
+    return co, "port"
+
+
+def oracle_sample(w: int, h: int, budget_s: float, threads: int = 0):
+    """Times the CPU implementation of the reference's path on a bounded sample of the same frame: every `stride`-th
+    row, full width (pixels are independent; cost is per ray), sized by a short calibration run to ~budget_s seconds."""
     from oracle import np_oracle as npo
 
-    co.build()
+    impl, kind = cpu_reference()
     verts, faces, center = npo.default_scene()
     cam = npo.camera_uniform(npo.default_camera(center, w, h))
     st = dict(npo.default_settings(), overlay_mode=1)
-    cores = co.num_threads() if threads <= 0 else threads
+    cores = impl.num_threads() if threads <= 0 else threads
+    steps_per_ray = 5001  # h_initial = 0.001: the loop of src/main_view.wgsl:244 runs 5001 times, adaptive sampling cannot trigger (h <= 0.002)
 
     def run(rows):
         y_step = max(1, h // rows)
+        ys = range(y_step // 2, h, y_step)
         t0 = time.perf_counter()
-        out = co.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, y_step // 2, h),
-                       y_step=y_step, n_threads=threads)
+        out = impl.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, y_step // 2, h),
+                         y_step=y_step, n_threads=threads)
         dt = time.perf_counter() - t0
-        done = out["accepted"] > 0
-        return dt, int(done.sum()), int(out["accepted"].sum() + out["rejected"].sum()), int(done.any(axis=1).sum())
+        rays = len(ys) * w
+        if "accepted" in out:  # the port counts its steps; the transpiled shader has no such output
+            assert int(out["accepted"].sum() + out["rejected"].sum()) == rays * steps_per_ray
+        return dt, rays, rays * steps_per_ray, len(ys)
 
     # calibration on a strided part of one row
     xs = max(1, w // (cores * 16))
     t0 = time.perf_counter()
-    co.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, h // 2, h // 2 + 1),
-             x_step=xs, n_threads=threads)
+    impl.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, h // 2, h // 2 + 1),
+               x_step=xs, n_threads=threads)
     per_ray = (time.perf_counter() - t0) / len(range(0, w, xs))
     rows = max(1, min(h, int(budget_s / (per_ray * w))))
     t, rays, steps, rows = run(rows)
-    return dict(seconds=t, rays=rays, steps=steps, rows=rows, cores=cores,
-                sample=f"{rows} full rows of the {w}x{h} frame, evenly spaced ({rays} rays, {steps} RK4 steps), {cores} OpenMP threads")
+    what = ("the reference's main_view.wgsl + MirageSphericalSigmoid body transpiled to C++ (oracle/_ref), gcc -O2 -ffp-contract=off"
+            if kind == "reference" else "hand-written C++ restatement of the reference WGSL (oracle/linon_oracle.cpp)")
+    return dict(seconds=t, rays=rays, steps=steps, rows=rows, cores=cores, kind=kind,
+                sample=f"{rows} full rows of the {w}x{h} frame, evenly spaced ({rays} rays, {steps} RK4 steps), {cores} OpenMP threads; {what}")
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores.  The reference itself (Rust + wgpu through
-    Mesa lavapipe) cannot be built or run in this image (no rustc/cargo, no Vulkan ICD), so this is the
-    CPU port in oracle/ (kind = "port"), all host threads, on a bounded sample of the same frame per step."""
+    """--impl reference: the reference's own implementation of the path on the host cores.  The Rust + wgpu host cannot
+    be built or run in this image (no rustc/cargo, no Vulkan ICD / lavapipe); what runs is the reference's
+    shader itself: main_view.wgsl with the MirageSphericalSigmoid body of functions.rs spliced in, transpiled
+    mechanically to C++ and compiled with gcc (oracle/_ref, kind = "reference"; falls back to the hand-written port when
+    that library was never built), all host threads, on a bounded sample of the same frame per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -170,9 +190,9 @@ def run_reference(args):
                 rk4_gsteps_per_s=tot_steps / tot_t / 1e9,
                 config=dict(workload=workload_name(args.gpus, w, h), width=w, height=h,
                             note="ms_per_step is the sampled time scaled to the full frame (pixels are independent)"),
-                cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=last["cores"], kind="port", sample=last["sample"]),
+                cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=last["cores"], kind=last["kind"], sample=last["sample"]),
                 e2e=dict(value=mrays, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                reference_unavailable="niklaskorz/linon is Rust+wgpu: no rustc/cargo/Vulkan in this image; CPU port of the same WGSL timed instead")
+                note="niklaskorz/linon's host is Rust+wgpu (no rustc/cargo/Vulkan in this image): its WGSL compute shader is run on the host cores through a mechanical WGSL->C++ transpile, not through wgpu on lavapipe")
     print(json.dumps(line))
     return 0
 
@@ -386,9 +406,9 @@ def run_ours(args):
     )
     if world == 1 and not args.no_cpu_baseline:
         s = oracle_sample(W, H, args.cpu_seconds)
-        line["cpu_baseline"] = dict(value=s["rays"] / s["seconds"] / 1e6, unit="Mrays/s", cores=s["cores"], kind="port",
+        line["cpu_baseline"] = dict(value=s["rays"] / s["seconds"] / 1e6, unit="Mrays/s", cores=s["cores"], kind=s["kind"],
                                     sample=s["sample"], rk4_gsteps_per_s=s["steps"] / s["seconds"] / 1e9,
-                                    note="CPU restatement of the reference WGSL (oracle/), not wgpu-on-lavapipe: no Rust/Vulkan in this image")
+                                    note="the reference's WGSL run on the host cores (oracle/_ref transpile, or the bit-identical hand port), not wgpu-on-lavapipe: no Rust/Vulkan in this image")
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

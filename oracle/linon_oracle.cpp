@@ -4,9 +4,14 @@
 // import or execute this file; only tests/, __graft_entry__.smoke() and the
 // cpu_baseline / --impl reference legs of bench.py load it, as the checker.
 //
-// PARITY UNPINNED: the reference (niklaskorz/linon, Rust + wgpu) ships no tests,
-// golden vectors or usable images, and neither rustc/cargo nor a Vulkan/lavapipe
-// stack exists in this image, so the reference itself cannot be executed here.
+// PARITY: the reference (niklaskorz/linon, Rust + wgpu) ships no tests, golden
+// vectors or usable images, and neither rustc/cargo nor a Vulkan/lavapipe stack
+// exists in this image, so its host cannot be executed here.  Its shader text can:
+// oracle/_ref (main_view.wgsl + functions.rs bodies + overlay.wgsl, transpiled
+// mechanically to C++ by oracle/wgsl_ref and compiled with gcc) is what pins this
+// file - the two are bit-for-bit identical on every output the shader has
+// (tests/test_wgsl_reference_cpu.py).  Still unpinned: the last-ulp behaviour of
+// naga's / the Vulkan driver's builtins (see below).
 // This file follows the reference WGSL line by line (citations below), fp32,
 // no FMA contraction (build with -ffp-contract=off), expression order as
 // written (left-associative), WGSL builtin definitions:

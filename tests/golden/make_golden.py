@@ -1,8 +1,12 @@
 """Generates tests/golden/*.npz: outputs of the CPU oracle (oracle/linon_oracle.cpp) for small frames.
 
-The reference ships no golden vectors and cannot run here, so these fixtures pin the ORACLE, not the
-reference: they freeze its outputs at commit time (tests/test_golden_cpu.py re-checks the oracle against them, the
-GPU tests check the CUDA path against them without re-running the oracle).  Run: python tests/golden/make_golden.py
+The reference ships no golden vectors and its Rust/wgpu host cannot run here.  What CAN run here is its
+shader: oracle/_ref is main_view.wgsl + the functions.rs bodies transpiled mechanically to C++ (oracle/wgsl_ref/).
+Every fixture is written only if that library reproduces the oracle's rgba8 and endpoint bytes exactly, so the colour
+and endpoint planes are outputs of the reference's own shader source; hit ids, step counters and the exclusion masks
+come from the oracle (the shader has no such outputs).  tests/test_golden_cpu.py re-checks the oracle against the
+fixtures, tests/test_wgsl_reference_cpu.py re-checks the transpiled reference against them, the GPU tests check the
+CUDA path against them without running either.  Run (needs /root/reference): python tests/golden/make_golden.py
 """
 import json
 import os
@@ -14,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import cpu_oracle as co  # noqa: E402
 from oracle import np_oracle as npo  # noqa: E402
+from oracle import wgsl_reference as wr  # noqa: E402
 
 W, H = 96, 72
 NAMES = {1: "MirageSpherical", 2: "MiragePlane", 3: "MirageSphericalSigmoid", 4: "MiragePlaneSigmoid", 5: "TranslationX",
@@ -28,6 +33,9 @@ def main():
     for fn, name in NAMES.items():
         for adaptive in ((False, True) if fn <= 4 else (False,)):
             out = co.march(verts, faces, cam, st, fn, W, H, h_initial=0.1, adaptive=adaptive)
+            ref = wr.march(verts, faces, cam, st, fn, W, H, h_initial=0.1, adaptive=adaptive)
+            assert np.array_equal(ref["rgba8"], out["rgba8"]), name
+            assert np.array_equal(ref["endpoint"].view(np.uint32), out["endpoint"].view(np.uint32)), name
             _, exps = co.overlay(out["rgba8"], out["endpoint"], dict(st, overlay_mode=1))
             undecided = np.zeros((H, W), bool)
             if adaptive:  # pixels the oracle itself cannot decide in adaptive mode
@@ -41,7 +49,8 @@ def main():
                                 endpoint=out["endpoint"], high_lyapunov=exps >= 0.8, undecided=undecided,
                                 accepted=out["accepted"].astype(np.int16), rejected=out["rejected"].astype(np.int16))
             frames.append(dict(file=fname, function=name, function_id=fn, adaptive=adaptive))
-    json.dump(dict(width=W, height=H, h_initial=0.1, camera={k: [float(x) for x in v] for k, v in cam.items()},
+    json.dump(dict(pinned_by="oracle/_ref (transpiled reference WGSL)", reference_sources=wr.info()["sources"],
+                   width=W, height=H, h_initial=0.1, camera={k: [float(x) for x in v] for k, v in cam.items()},
                    settings=st, frames=frames), open(os.path.join(HERE, "index.json"), "w"), indent=1)
 
 

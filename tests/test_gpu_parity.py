@@ -257,6 +257,32 @@ def test_golden_fixtures(product_lib, scene):
                 assert np.array_equal(strict["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
 
 
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.MiragePlane,
+                                PredefinedFunction.Rotation, PredefinedFunction.LorenzAttractor])
+def test_cuda_path_against_the_transpiled_reference_shader(view, oracle, scene, fn):
+    """The CUDA path against oracle/_ref directly: the reference's own main_view.wgsl + functions.rs body, transpiled
+    mechanically to C++ in the build container (oracle/wgsl_ref/build_ref.py; the .so travels to the GPU box).
+    Colour and endpoint come from the reference's shader; hit ids (which the shader does not output) from the
+    hand-written oracle, which must equal the shader on everything both produce."""
+    from oracle import wgsl_reference as wr
+    if not wr.available():
+        pytest.skip("oracle/_ref was not built (needs /root/reference in the build container)")
+    verts, faces, _ = scene
+    W, H = view.size
+    st = settings_dict(make_settings())
+    cam = camera_dict(view.camera.uniform())
+    ref, excl = oracle_frame(oracle, scene, view, fn, adaptive=False)
+    shader = wr.march(verts, faces, cam, st, int(fn), W, H, h_initial=0.1, adaptive=False)
+    assert np.array_equal(shader["rgba8"], ref["rgba8"])
+    assert np.array_equal(shader["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+    got = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_FAST)
+    m = parity.compare_frames(got, dict(hit_id=ref["hit_id"], rgba8=shader["rgba8"], endpoint=shader["endpoint"]), exclude=excl)
+    assert parity.passes_north_star(m, check_endpoint=True), m
+    if fn in NO_TRANSCENDENTALS:  # strict mode: the reference shader's endpoints, bit for bit
+        strict = render(view, fn, flags=capi.RENDER_ADAPTIVE_OFF, math=capi.MATH_STRICT)
+        assert np.array_equal(strict["endpoint"].view(np.uint32), shader["endpoint"].view(np.uint32))
+
+
 # ---- invariants that need no oracle -------------------------------------------------------------------------------------
 def test_field_weight_zero_gives_straight_rays(view):
     st = make_settings(field_weight=0.0)
