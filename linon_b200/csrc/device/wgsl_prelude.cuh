@@ -216,6 +216,19 @@ template <class S> struct vec4t;
     LINON_FOR3_ROW3(M, x, x) LINON_FOR3_ROW3(M, x, y) LINON_FOR3_ROW3(M, x, z) LINON_FOR3_ROW3(M, y, x)     \
     LINON_FOR3_ROW3(M, y, y) LINON_FOR3_ROW3(M, y, z) LINON_FOR3_ROW3(M, z, x) LINON_FOR3_ROW3(M, z, y)     \
     LINON_FOR3_ROW3(M, z, z)
+// three- and four-component swizzles of a vec4 that involve w
+#define LINON_FOR3_ROW4W(M, a, b) M(a, b, w)
+#define LINON_FOR3_ROW4(M, a, b) LINON_FOR3_ROW3(M, a, b) M(a, b, w)
+#define LINON_FOR3_OF4_W(M)                                                                                 \
+    LINON_FOR3_ROW4W(M, x, x) LINON_FOR3_ROW4W(M, x, y) LINON_FOR3_ROW4W(M, x, z) LINON_FOR3_ROW4W(M, y, x) \
+    LINON_FOR3_ROW4W(M, y, y) LINON_FOR3_ROW4W(M, y, z) LINON_FOR3_ROW4W(M, z, x) LINON_FOR3_ROW4W(M, z, y) \
+    LINON_FOR3_ROW4W(M, z, z) LINON_FOR3_ROW4(M, x, w) LINON_FOR3_ROW4(M, y, w) LINON_FOR3_ROW4(M, z, w)    \
+    LINON_FOR3_ROW4(M, w, x) LINON_FOR3_ROW4(M, w, y) LINON_FOR3_ROW4(M, w, z) LINON_FOR3_ROW4(M, w, w)
+#define LINON_FOR4_ROW(M, a, b, c) M(a, b, c, x) M(a, b, c, y) M(a, b, c, z) M(a, b, c, w)
+#define LINON_FOR4_ROW2(M, a, b) LINON_FOR4_ROW(M, a, b, x) LINON_FOR4_ROW(M, a, b, y) LINON_FOR4_ROW(M, a, b, z) LINON_FOR4_ROW(M, a, b, w)
+#define LINON_FOR4_ROW3(M, a) LINON_FOR4_ROW2(M, a, x) LINON_FOR4_ROW2(M, a, y) LINON_FOR4_ROW2(M, a, z) LINON_FOR4_ROW2(M, a, w)
+#define LINON_FOR4_OF4(M) LINON_FOR4_ROW3(M, x) LINON_FOR4_ROW3(M, y) LINON_FOR4_ROW3(M, z) LINON_FOR4_ROW3(M, w)
+#define LINON_SWZ4_DEF(a, b, c, d) LINON_HD vec4t<S> a##b##c##d() const { return vec4t<S>(a, b, c, d); }
 
 template <class S> struct vec2t {
     S x, y;
@@ -258,8 +271,8 @@ template <class S> struct vec4t {
     LINON_HD S operator[](int i) const { return (&x)[i]; }
     LINON_FOR2_OF4(LINON_SWZ2_DECL)
     LINON_FOR3_OF3(LINON_SWZ3_DECL)
-    LINON_HD vec3t<S> yzw() const;
-    LINON_HD vec4t<S> xyzw() const { return *this; }
+    LINON_FOR3_OF4_W(LINON_SWZ3_DECL)
+    LINON_FOR4_OF4(LINON_SWZ4_DEF)
 };
 
 #define LINON_SWZ2_DEF_V2(a, b) template <class S> LINON_HD vec2t<S> vec2t<S>::a##b() const { return vec2t<S>(a, b); }
@@ -272,7 +285,7 @@ LINON_FOR2_OF3(LINON_SWZ2_DEF_V3)
 LINON_FOR2_OF4(LINON_SWZ2_DEF_V4)
 LINON_FOR3_OF3(LINON_SWZ3_DEF_V3)
 LINON_FOR3_OF3(LINON_SWZ3_DEF_V4)
-template <class S> LINON_HD vec3t<S> vec4t<S>::yzw() const { return vec3t<S>(y, z, w); }
+LINON_FOR3_OF4_W(LINON_SWZ3_DEF_V4)
 
 typedef float wg_f32;  // what the translator emits for the WGSL type f32; LinonField<S> re-declares it as S
 typedef vec2t<float> vec2f;

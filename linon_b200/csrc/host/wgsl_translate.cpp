@@ -19,11 +19,16 @@
 //   * multi-component swizzles .xyz/.rgb -> .xyz(); .r/.g/.b/.a -> .x/.y/.z/.w
 //   * `if cond {` / `while cond {` get their parentheses; a trailing comma before `)` is removed
 //   * identifiers that are C++ keywords get a trailing underscore
+//   * literal-only sub-expressions, including calls of const-evaluable builtins (`tan(0.1)`, `x + 1.0 / 3.0`), are
+//     evaluated in f64 on the host like naga's constant evaluator and emitted as one f32 literal (pass_fold)
 // Anything outside the subset is passed through and reported by NVRTC against the user's line.
 
 #include "wgsl_translate.h"
 
 #include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <string>
@@ -407,6 +412,155 @@ struct Rewriter {
         return true;
     }
 
+    // ---- pass 5: constant evaluation of literal-only sub-expressions -----------------------------------------------
+    // WGSL literals without suffix are AbstractFloats: an expression made only of them - including calls of the
+    // const-evaluable builtins, e.g. `tan(0.1) + sqrt(2.0)`, `pow(2.0, 0.5) * x`, `x + 1.0 / 3.0` - is evaluated by
+    // naga's constant evaluator in f64 and converted to f32 ONCE where it meets a concrete operand.  Evaluating the
+    // pieces in f32 at run time differs from that in the last bit.  This pass finds the literal-only SUBTREES of the
+    // expression tree on the token stream (unary minus, parentheses, calls, then * / before + -, left-associative: a
+    // run is only folded where WGSL's grammar makes it a subtree), evaluates them in double on the host and replaces
+    // them by one f32 literal.  A whole literal-only `let` initialiser was already turned into (float)(double
+    // expression) by pass_decls (its numbers lost their `f` and are not candidates here).  Newlines are kept.
+    struct FoldElem {
+        int tok;          // index into t of a raw token, or of the first token of a folded literal
+        int last;         // last token covered
+        bool lit;         // a literal value
+        bool nontrivial;  // involves an operator or a call (worth re-emitting)
+        double v;
+    };
+    static bool fold_call(const std::string& f, const std::vector<double>& a, double& r) {
+        const size_t n = a.size();
+        auto is = [&](const char* name, size_t arity) { return f == name && n == arity; };
+        if (is("w_sqrt", 1)) r = std::sqrt(a[0]);
+        else if (is("w_inverseSqrt", 1)) r = 1.0 / std::sqrt(a[0]);
+        else if (is("w_exp", 1)) r = std::exp(a[0]);
+        else if (is("w_exp2", 1)) r = std::exp2(a[0]);
+        else if (is("w_log", 1)) r = std::log(a[0]);
+        else if (is("w_log2", 1)) r = std::log2(a[0]);
+        else if (is("w_pow", 2)) r = std::pow(a[0], a[1]);
+        else if (is("w_sin", 1)) r = std::sin(a[0]);
+        else if (is("w_cos", 1)) r = std::cos(a[0]);
+        else if (is("w_tan", 1)) r = std::tan(a[0]);
+        else if (is("w_asin", 1)) r = std::asin(a[0]);
+        else if (is("w_acos", 1)) r = std::acos(a[0]);
+        else if (is("w_atan", 1)) r = std::atan(a[0]);
+        else if (is("w_atan2", 2)) r = std::atan2(a[0], a[1]);
+        else if (is("w_sinh", 1)) r = std::sinh(a[0]);
+        else if (is("w_cosh", 1)) r = std::cosh(a[0]);
+        else if (is("w_tanh", 1)) r = std::tanh(a[0]);
+        else if (is("w_abs", 1)) r = std::fabs(a[0]);
+        else if (is("w_floor", 1)) r = std::floor(a[0]);
+        else if (is("w_ceil", 1)) r = std::ceil(a[0]);
+        else if (is("w_trunc", 1)) r = std::trunc(a[0]);
+        else if (is("w_round", 1)) r = std::nearbyint(a[0]);  // ties to even
+        else if (is("w_fract", 1)) r = a[0] - std::floor(a[0]);
+        else if (is("w_sign", 1)) r = a[0] > 0.0 ? 1.0 : (a[0] < 0.0 ? -1.0 : 0.0);
+        else if (is("w_min", 2)) r = a[1] < a[0] ? a[1] : a[0];
+        else if (is("w_max", 2)) r = a[0] < a[1] ? a[1] : a[0];
+        else if (is("w_clamp", 3)) { const double m = a[0] < a[1] ? a[1] : a[0]; r = a[2] < m ? a[2] : m; }
+        else if (is("w_saturate", 1)) { const double m = a[0] < 0.0 ? 0.0 : a[0]; r = 1.0 < m ? 1.0 : m; }
+        else if (is("w_step", 2)) r = a[0] <= a[1] ? 1.0 : 0.0;
+        else if (is("w_radians", 1)) r = a[0] * 0.017453292519943295;
+        else if (is("w_degrees", 1)) r = a[0] * 57.29577951308232;
+        else return false;
+        return true;
+    }
+    bool pass_fold() {
+        std::vector<FoldElem> e;
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind == WS || t[i].kind == NL) continue;
+            FoldElem x{i, i, false, false, 0.0};
+            if (t[i].kind == NUMBER && t[i].text.size() > 1 && t[i].text.back() == 'f' &&
+                t[i].text.find_first_of("xX") == std::string::npos) {
+                x.lit = true;
+                x.v = std::strtod(t[i].text.substr(0, t[i].text.size() - 1).c_str(), nullptr);
+            }
+            e.push_back(x);
+        }
+        auto punct = [&](int k, const char* p) { return k >= 0 && k < (int)e.size() && !e[k].lit && is_p(e[k].tok, p); };
+        auto value_end = [&](int k) {  // can the element end an operand (so that a following + - is binary)?
+            if (k < 0) return false;
+            if (e[k].lit) return true;
+            const Tok& x = t[e[k].tok];
+            return x.kind == IDENT || x.kind == NUMBER || (x.kind == PUNCT && (x.text == ")" || x.text == "]"));
+        };
+        auto mul_op = [&](int k) { return punct(k, "*") || punct(k, "/") || punct(k, "%"); };
+        auto add_op = [&](int k) { return (punct(k, "+") || punct(k, "-")) && value_end(k - 1); };
+        auto merge = [&](int a, int b, double v) {  // elements [a, b] -> one nontrivial literal
+            if (!std::isfinite(v) || !std::isfinite((double)(float)v)) return false;  // naga rejects these: leave as written
+            FoldElem x{e[a].tok, e[b].last, true, true, v};
+            e.erase(e.begin() + a, e.begin() + b + 1);
+            e.insert(e.begin() + a, x);
+            return true;
+        };
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            for (int k = 0; k < (int)e.size() && !changed; ++k) {
+                // unary minus
+                if (punct(k, "-") && !value_end(k - 1) && k + 1 < (int)e.size() && e[k + 1].lit) {
+                    FoldElem x{e[k].tok, e[k + 1].last, true, e[k + 1].nontrivial, -e[k + 1].v};
+                    e.erase(e.begin() + k, e.begin() + k + 2);
+                    e.insert(e.begin() + k, x);
+                    changed = true;
+                    break;
+                }
+                // parentheses that are not a call's
+                if (punct(k, "(") && k + 2 < (int)e.size() && e[k + 1].lit && punct(k + 2, ")") &&
+                    !(k > 0 && !e[k - 1].lit && t[e[k - 1].tok].kind == IDENT)) {
+                    FoldElem x{e[k].tok, e[k + 2].last, true, e[k + 1].nontrivial, e[k + 1].v};
+                    e.erase(e.begin() + k, e.begin() + k + 3);
+                    e.insert(e.begin() + k, x);
+                    changed = true;
+                    break;
+                }
+                // call of a const-evaluable builtin with literal arguments
+                if (!e[k].lit && t[e[k].tok].kind == IDENT && punct(k + 1, "(") && !punct(k - 1, ".")) {
+                    std::vector<double> args;
+                    int j = k + 2;
+                    bool ok = true;
+                    while (ok && j < (int)e.size()) {
+                        if (!e[j].lit) { ok = false; break; }
+                        args.push_back(e[j].v);
+                        ++j;
+                        if (punct(j, ",")) { ++j; if (punct(j, ")")) break; continue; }
+                        break;
+                    }
+                    double r;
+                    if (ok && punct(j, ")") && !args.empty() && fold_call(t[e[k].tok].text, args, r) && merge(k, j, r)) {
+                        changed = true;
+                        break;
+                    }
+                }
+                if (!e[k].lit || k + 2 >= (int)e.size() || !e[k + 2].lit) continue;
+                // L * L, L / L: a subtree unless the left literal belongs to an earlier multiplicative chain
+                if ((punct(k + 1, "*") || punct(k + 1, "/")) && !mul_op(k - 1)) {
+                    const double r = punct(k + 1, "*") ? e[k].v * e[k + 2].v : e[k].v / e[k + 2].v;
+                    if (merge(k, k + 2, r)) { changed = true; break; }
+                }
+                // L + L, L - L: a subtree unless either literal is claimed by a tighter or earlier operator
+                if ((punct(k + 1, "+") || punct(k + 1, "-")) && !mul_op(k - 1) && !add_op(k - 1) && !mul_op(k + 3) &&
+                    !(punct(k - 1, "-") && !value_end(k - 2))) {
+                    const double r = punct(k + 1, "+") ? e[k].v + e[k + 2].v : e[k].v - e[k + 2].v;
+                    if (merge(k, k + 2, r)) { changed = true; break; }
+                }
+            }
+        }
+        for (const FoldElem& x : e) {
+            if (!x.lit || !x.nontrivial) continue;
+            char buf[64];
+            std::snprintf(buf, sizeof buf, "%.9g", (double)(float)x.v);
+            std::string lit = buf;
+            if (lit.find_first_of(".e") == std::string::npos) lit += ".0";
+            lit += "f";
+            if (lit[0] == '-') lit = "(" + lit + ")";
+            t[x.tok] = {NUMBER, lit};
+            for (int j = x.tok + 1; j <= x.last; ++j)
+                if (t[j].kind != NL) blank(j);
+        }
+        return true;
+    }
+
     // ---- pass 4: builtins, swizzles, keywords, trailing commas --------------------------------------------------
     bool pass_names() {
         for (int i = 0; i < (int)t.size(); ++i) {
@@ -451,7 +605,7 @@ bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string
     Rewriter rw;
     rw.t = std::move(lx.out);
     // keyword-clash renaming must see the user's identifiers before passes introduce C++ keywords
-    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control()) {
+    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_fold()) {
         error = "WGSL translation error: " + rw.err;
         return false;
     }
@@ -621,7 +775,7 @@ template <size_t N> bool in_list(const char* const (&list)[N], const std::string
 bool translate_range(const std::vector<Tok>& t, int b, int e, bool keep_nl, std::string& out, std::string& err) {
     Rewriter rw;
     rw.t.assign(t.begin() + b, t.begin() + e);
-    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control()) {
+    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_fold()) {
         err = rw.err;
         return false;
     }
@@ -639,7 +793,7 @@ bool emit_function(const std::vector<Tok>& t, const RawItem& it, const std::stri
     rw.t.assign(t.begin() + it.paren_open, t.begin() + it.end);
     const int off = it.paren_open;
     const int pc = it.paren_close - off, bo = it.brace_open - off;
-    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control()) {
+    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_fold()) {
         err = "function '" + it.info.name + "': " + rw.err;
         return false;
     }

@@ -156,6 +156,27 @@ def generate():
     return sources + [os.path.join(HERE, "ref_api.cpp")]
 
 
+def build_custom(body: str, workdir: str, name: str = "custom") -> str:
+    """One module with a user-edited field-function body spliced in (as shipped: h_initial 0.1, adaptive sampling),
+    compiled into `workdir`; exports `wgslref_custom_field(settings, n, p_prev, p, v0, v, t, out)` and
+    `wgslref_custom_main_view(frame, outputs)`.  For differential tests of the product's own WGSL translator."""
+    main_view = open(os.path.join(REFERENCE, "src", "main_view.wgsl"), encoding="utf-8").read()
+    text = with_field_function(main_view, body)
+    src = os.path.join(workdir, name + ".cpp")
+    lib = os.path.join(workdir, name + ".so")
+    open(src, "w").write(
+        '#include <cstring>\n#include <vector>\n#ifdef _OPENMP\n#include <omp.h>\n#endif\n'
+        '#include "wgsl_runtime.hpp"\n#include "harness_types.hpp"\n'
+        f'namespace custom_module {{\n{wgsl2cpp.transpile(text)}\n#include "harness_main_view.inc"\n}}\n'
+        'extern "C" void wgslref_custom_field(const RefSettings* st, int n, const float* a, const float* b, const float* c, '
+        'const float* d, const float* t, float* out) { custom_module::run_field(st, n, a, b, c, d, t, out); }\n'
+        'extern "C" int wgslref_custom_main_view(const RefFrame* f, const RefOutputs* o) { return custom_module::run_main_view(f, o); }\n')
+    r = subprocess.run([CXX, *CXXFLAGS, "-I", HERE, "-shared", src, "-o", lib], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{src}:\n{r.stderr[-4000:]}")
+    return lib
+
+
 def _stamp() -> str:
     h = hashlib.sha256()
     for n in sorted(os.listdir(HERE)):

@@ -42,7 +42,6 @@ SUFFIX_TYPES = {"f": "f32", "i": "i32", "u": "u32", "h": "f16"}
 TOKEN_RE = re.compile(r"""
     (?P<ws>\s+)
   | (?P<lc>//[^\n]*)
-  | (?P<bc>/\*.*?\*/)
   | (?P<hex>0[xX][0-9a-fA-F]+[iu]?)
   | (?P<flt>(?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?[fh]?|\d+[eE][+-]?\d+[fh]?|\d+[fh])
   | (?P<int>\d+[iu]?)
@@ -68,12 +67,26 @@ class Tok:
 def tokenize(src: str):
     toks, pos, line = [], 0, 1
     while pos < len(src):
+        if src.startswith("/*", pos):  # block comments nest in WGSL
+            depth, j = 1, pos + 2
+            while depth and j < len(src):
+                if src.startswith("/*", j):
+                    depth, j = depth + 1, j + 2
+                elif src.startswith("*/", j):
+                    depth, j = depth - 1, j + 2
+                else:
+                    j += 1
+            if depth:
+                raise WgslError(f"line {line}: block comment is never closed")
+            line += src.count("\n", pos, j)
+            pos = j
+            continue
         m = TOKEN_RE.match(src, pos)
         if not m:
             raise WgslError(f"line {line}: cannot tokenise {src[pos:pos + 20]!r}")
         kind = m.lastgroup
         text = m.group()
-        if kind not in ("ws", "lc", "bc"):
+        if kind not in ("ws", "lc"):
             toks.append(Tok(kind, text, line))
         line += text.count("\n")
         pos = m.end()
@@ -609,7 +622,10 @@ class Emitter:
             return f"(void)({self.conc(s[1])})"
         if k == "assign":
             lhs, _ = self.expr(s[2])
-            return f"{lhs} {s[1]} {self.conc(s[3])}"
+            if s[1] != "=":  # WGSL defines `a op= b` as `a = a op b`
+                text, _ = self.expr(("bin", s[1][:-1], s[2], s[3]))
+                return f"{lhs} = {text}"
+            return f"{lhs} = {self.conc(s[3])}"
         if k == "incr":
             lhs, _ = self.expr(s[2])
             return f"{lhs}{s[1]}"
