@@ -1,9 +1,11 @@
 """np_oracle.py — second, independent numpy restatement of linon's hot path + scene inputs.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md).  PARITY UNPINNED: the reference has no tests or
-golden vectors and cannot be executed in this image; this file and oracle/linon_oracle.cpp are two
+TEST INFRASTRUCTURE ONLY (see oracle/README.md).  The reference has no tests or golden vectors and
+its Rust host cannot be executed in this image; this file and oracle/linon_oracle.cpp are two
 separately written restatements of the same WGSL, cross-checked against each other in
-tests/test_oracle_selfcheck.py.
+tests/test_oracle_selfcheck.py.  What pins them to the reference is oracle/_ref: the reference's own
+shader text transpiled to C++ (oracle/wgsl_ref), bit-identical with linon_oracle.cpp
+(tests/test_wgsl_reference_cpu.py).
 
 What lives here
   * scene inputs the reference builds on the host (the product has its own C++ copy that the tests
