@@ -104,6 +104,13 @@ enum {
                                     (csrc/device/mirage_fused.cuh: one reciprocal for eta, no sigmoid reciprocal, shared
                                     inverse square root, Runge-Kutta stage 1 = identity).  0: always the generic translation */
     LINON_OPT_PAIR_MIN_BLOCKS = 9, /* resident CTAs / SM requested for the pair kernel (register cap); 0 = default (512/block) */
+    LINON_OPT_QUIET_ZONE = 12,   /* 1: fixed-step frames (Enhance, adaptive off) of a predefined mirage body in fast math mode take
+                                    straight steps - velocity = direction, no field evaluation - while every lane of the warp is
+                                    outside the body's zone of influence, where the reference's own fp32 evaluation returns
+                                    eta = 1 exactly and refraction(t, t, v, n) = v up to its rounding noise (csrc/device/
+                                    mirage_fused.cuh: quiet_steps).  Every Runge-Kutta step is still executed and counted.
+                                    Default 0 until measured on the GPU; validated on the host emulation of the device code
+                                    (tests/emu) against the oracle. */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.

@@ -101,6 +101,13 @@
 #ifndef LINON_FUSED_RK4
 #define LINON_FUSED_RK4 0  // 1: the field body provides LinonField<S>::rk4, one whole Runge-Kutta step as a single expression
 #endif
+#ifndef LINON_QUIET_ZONE
+#define LINON_QUIET_ZONE 0  // 1: fixed-step loops take straight steps where the spliced body declares itself the identity
+#endif
+#if LINON_QUIET_ZONE && !defined(LINON_HAS_QUIET_ZONE)
+#undef LINON_QUIET_ZONE
+#define LINON_QUIET_ZONE 0  // the body does not define LinonField<float>::quiet_steps (generic translations never do)
+#endif
 #ifndef LINON_STRICT_MATH
 #define LINON_STRICT_MATH 0  // 1: the bit-comparable build (--fmad=false ...): no explicit FMA either
 #endif
@@ -544,6 +551,7 @@ __device__ __forceinline__ void init_ray(const MarchParams& P, int x, int local_
 
 struct StepCounters {
     unsigned int accepted, prehit, rejected, face_tests, checks;
+    unsigned int quiet;  // LINON_QUIET_ZONE: accepted steps taken as straight steps (velocity = direction, no field evaluation)
 };
 
 __device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounters c) {
@@ -564,6 +572,12 @@ __device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounter
         atomicAdd(&P.counters[3], f);
         atomicAdd(&P.counters[4], k);
     }
+#if LINON_QUIET_ZONE
+    unsigned long long q = c.quiet;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&P.counters[15], q);
+#endif
 }
 
 // One loop iteration of nonlinear_ray_color up to (not including) the intersection, src/main_view.wgsl:246-258.
@@ -656,7 +670,40 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         int i = 0;
         bool searching = true;  // warp-uniform
         for (; i < n_steps && searching; ++i) {
+#if LINON_QUIET_ZONE
+            // Quiet zone (mirage_fused.cuh): while every lane of the warp is outside the body's zone of influence the field
+            // is the identity, a Runge-Kutta step is p += h dir with dir unchanged, and the cost a step takes from the
+            // safe-distance budget is a constant.  Plan a run of such steps - as many as the lane with the nearest zone
+            // entry and the lane with the smallest budget allow - and take them back to back: every step is still executed
+            // (one FFMA per component), none needs a field evaluation, a vote or a culling check.  The plan is warp-uniform
+            // (REDUX.MIN); lanes that have hit carry an infinite budget.  A run that the budget cuts short is followed by
+            // ONE quiet step through the regular check logic below (velocity = direction), which refreshes the budget.
+            bool quiet = false;  // warp-uniform: this step's velocity is the direction
+            if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
+                const int nq = LinonField<float>::quiet_steps(r.p, r.dir, h);
+                const float q_inf = fmaxf(fmaxf(fabsf(r.dir.x), fabsf(r.dir.y)), fabsf(r.dir.z));
+                // 1.000001: the run takes n * cost_up from the budget in one rounding instead of n roundings of cost
+                const float cost_up = __fmul_ru(sd.cost_linf(q_inf, kh), 1.000001f);
+                // steps whose budget stays positive (0.9999 covers the division and keeps the budget after the run > 0)
+                const int nb = (int)fminf(__fdividef(sd.budget * 0.9999f, cost_up), 268435456.0f);
+                const int n_lane = LINON_CULL ? min(nq, max(nb, 0)) : 0;  // without culling every pre-hit step runs the face loop
+                const int n = min(__reduce_min_sync(0xffffffffu, n_lane), n_steps - i);
+                if (n > 0) {
+#pragma unroll 4
+                    for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
+                    r.t = __fmaf_rn((float)n, h, r.t);
+                    sd.budget = __fmaf_rd(-(float)n, cost_up, sd.budget);  // +inf stays +inf
+                    cnt.quiet += (unsigned int)n;
+                    i += n - 1;  // the loop header adds the last one
+                    continue;
+                }
+                quiet = __all_sync(0xffffffffu, nq > 0);
+            }
+            if (quiet) ++cnt.quiet;
+            const vec3f v = quiet ? r.dir : rk4_velocity(r, h, st, cam);
+#else
             const vec3f v = rk4_velocity(r, h, st, cam);
+#endif
 #if LINON_FW_ONE
             r.dir = v;  // field_weight == 1: (1 - 1) * cur_dir + 1 * v
 #else
@@ -712,6 +759,20 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             r.t = r.t + h;
         }
         for (; i < n_steps; ++i) {
+#if LINON_QUIET_ZONE
+            // coasting through the quiet zone: the same plan without a budget
+            if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
+                const int n = min(__reduce_min_sync(0xffffffffu, LinonField<float>::quiet_steps(r.p, r.dir, h)), n_steps - i);
+                if (n > 0) {
+#pragma unroll 4
+                    for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
+                    r.t = __fmaf_rn((float)n, h, r.t);
+                    cnt.quiet += (unsigned int)n;
+                    i += n - 1;
+                    continue;
+                }
+            }
+#endif
             const vec3f v = rk4_velocity(r, h, st, cam);
 #if LINON_FW_ONE
             r.dir = v;
@@ -729,7 +790,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
             P.hit_id[pix] = hit;
         } else {
-            cnt.accepted = cnt.prehit = cnt.rejected = cnt.face_tests = cnt.checks = 0u;
+            cnt.accepted = cnt.prehit = cnt.rejected = cnt.face_tests = cnt.checks = cnt.quiet = 0u;
         }
     }
 #else

@@ -49,6 +49,7 @@
 #endif
 #define LINON_STAGE1_IDENTITY 1
 #define LINON_FUSED_RK4 1
+#define LINON_HAS_QUIET_ZONE 1  // LinonField<float>::quiet_steps: where this body is the identity (LINON_QUIET_ZONE)
 
 template <class S> struct LinonField {
     // refraction (src/main_view.wgsl:119-136) for a given eta and d = dot(v, n); see refraction_s in wgsl_prelude.cuh
@@ -267,6 +268,66 @@ template <class S> struct LinonField {
         const vec3t<S> sum = stage<EXACT, true>(pc, k3, full, g_in, gd_in, kk4, acc);  // acc + k4
         kk_min = min3(kk2, kk3, kk4);  // NaN (from an earlier totally reflected stage) is ignored by min
         return sum;
+    }
+
+    // ---- LINON_QUIET_ZONE ------------------------------------------------------------------------------------------
+    // Outside its zone of influence the body is the identity, and the reference's own fp32 evaluation says so:
+    //   linear profiles   part = clamp(0, 1, dist / max_dist) [= min(1, .)] is exactly 1 for dist >= max_dist, so
+    //                     t_in = t_out = t_env, eta = n(t_env) / n(t_env) = 1 and refraction(t, t, v, n) = v in real numbers;
+    //   sigmoid profiles  sigmoid(x) = 1 / (1 + exp(-x)) rounds to exactly 1 once exp(-x) <= 2^-24, i.e. x >= 16.64,
+    //                     dist >= 1.8866 max_dist: again t_in = t_out = t_env and eta = 1.0f exactly.  (In real numbers
+    //                     eta differs from 1 by < 1e-11 there.)
+    // With eta = 1 the reference returns v + (cosi - sqrt(1 - (1 - cosi^2))) n, i.e. v plus the rounding noise of its own
+    // formulation - the same situation as LINON_STAGE1_IDENTITY.  A step whose four stage points are all outside the zone
+    // therefore has k1 = k2 = k3 = k4 = dir, v = dir: a straight step.  `radius` carries a margin over those thresholds
+    // (0.1 % for the linear profiles, whose value is continuous across the boundary; 1.8 % for the sigmoids).
+    struct Quiet {
+#if LINON_MIRAGE_KIND >= 3
+        static constexpr float radius = 1.92f * Fused::max_dist;
+#else
+        static constexpr float radius = 1.001f * Fused::max_dist;
+#endif
+        static constexpr float T = Fused::scale * radius;  // in the scaled coordinates of scaled_origin()
+        static constexpr int many = 1 << 28;
+    };
+    // > 0: p lies outside the zone (necessary for a quiet step, not sufficient: quiet_steps looks along the step)
+    static __device__ __forceinline__ float quiet_clearance(const vec3t<float> p) {
+        const auto pc = LinonField<float>::scaled_origin(p);
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+        return w_dot(pc, pc) - Quiet::T * Quiet::T;
+#else
+        return fabsf(pc) - Quiet::T;
+#endif
+    }
+    // The number of consecutive Runge-Kutta steps of size h, starting at p with direction dir, whose stage points all stay
+    // outside the zone, PROVIDED the direction does not change - which is the case exactly while the steps are quiet.  Stage
+    // points of step j (0-based) lie on the straight line p + s h dir with s in [j, j + 1], so with s_enter the parameter at
+    // which that line enters the zone the answer is floor(s_enter); 0 = the next step is not known to be quiet, Quiet::many =
+    // the line never enters.  One ray per thread only (the tile kernel).
+    static __device__ __forceinline__ int quiet_steps(const vec3t<float> p, const vec3t<float> dir, const float h) {
+        const float sh = Fused::scale * h;
+        float s_enter;
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+        const vec3t<float> pc = LinonField<float>::scaled_origin(p);
+        const vec3t<float> ds(sh * dir.x, sh * dir.y, sh * dir.z);
+        const float c0 = w_dot(pc, pc) - Quiet::T * Quiet::T;
+        if (!(c0 > 0.0f)) return 0;                 // inside (or NaN)
+        const float b = w_dot(pc, ds);
+        if (!(b < 0.0f)) return Quiet::many;        // moving away from the centre
+        const float a = w_dot(ds, ds);
+        const float disc = b * b - a * c0;
+        if (disc < 0.0f) return Quiet::many;        // the line passes the ball
+        s_enter = c0 / (sqrtf(disc) - b);           // the smaller root of a s^2 + 2 b s + c0 = 0, cancellation-free
+#else
+        const float y = LinonField<float>::scaled_origin(p);
+        const float clearance = fabsf(y) - Quiet::T;
+        if (!(clearance > 0.0f)) return 0;
+        const float approach = (y > 0.0f) ? -sh * dir.y : sh * dir.y;  // scaled height lost per step
+        if (!(approach > 0.0f)) return Quiet::many;
+        s_enter = clearance / approach;
+#endif
+        // 0.9995: the rounding of the positions of up to ~5000 straight steps and of this estimate, with room to spare
+        return (int)fminf(s_enter * 0.9995f, (float)Quiet::many);
     }
 
     // v = (k1 + 2 k2 + 2 k3 + k4) / 6 with k1 = dir (LINON_STAGE1_IDENTITY), src/main_view.wgsl:246-251

@@ -134,6 +134,7 @@ struct Variant {
     int specialize;       // 1: fast math may splice the hand-fused restatement of a predefined mirage body
     int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
     int pair_min_blocks;  // resident CTAs / SM requested for it (0 = kernel default)
+    int quiet;            // 1: fixed-step loops take straight steps where a fused mirage body is the identity (LINON_QUIET_ZONE)
 };
 
 struct Module {
@@ -242,6 +243,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
                                      "-DLINON_PAIRS=" + std::to_string(var.pairs),
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      "-DLINON_BVH=" + std::to_string(var.bvh),
+                                     "-DLINON_QUIET_ZONE=" + std::to_string(var.quiet),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
                                      "-DLINON_PACKED_OPS=" + std::to_string((var.math == 0 || getenv("LINON_DEV_UNPACKED")) ? 0 : 1),
                                      "-DLINON_STRICT_MATH=" + std::to_string(var.math == 0 ? 1 : 0)};
@@ -262,6 +264,15 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
     }
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
+    if (const char* dump = getenv("LINON_DUMP_SOURCE")) {  // developer aid: the exact module text and options NVRTC gets
+        if (FILE* f = fopen(dump, "wb")) {                  // (tests/emu compiles this text for the host)
+            fputs("// nvrtc:", f);
+            for (auto& o : opts) fprintf(f, " %s", o.c_str());
+            fputs("\n", f);
+            fwrite(src.data(), 1, src.size(), f);
+            fclose(f);
+        }
+    }
     const nvrtcResult rc = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
     size_t log_size = 0;
     nvrtcGetProgramLogSize(prog, &log_size);
@@ -293,8 +304,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
 }
 
 std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
-    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
-               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh) + body;
+    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh, v.quiet) + body;
 }
 
 }  // namespace
@@ -343,7 +354,7 @@ struct linon_view {
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 0;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
@@ -490,6 +501,8 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.fw_one = (v->opt_math != 0 && v->settings.field_weight == 1.0f) ? 1 : 0;
     var.pairs = (v->opt_kernel == 2 && !v->use_bvh && !v->pair_unfit.count(v->body)) ? 1 : 0;
     var.pair_min_blocks = var.pairs ? v->opt_pair_min_blocks : 0;
+    // only the fixed-step loops of the tile kernel have the quiet-zone path, and only fused mirage bodies define the zone
+    var.quiet = (v->opt_quiet && !var.adaptive && v->opt_math == 2 && v->opt_specialize) ? 1 : 0;
     return var;
 }
 
@@ -1078,6 +1091,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_MAX_REGS: if (value < 0 || value > 255) break; v->opt_max_regs = value; return LINON_OK;
         case LINON_OPT_PROFILE: if (value < 0 || value > 1) break; v->opt_profile = value; return LINON_OK;
         case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
+        case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 1) break; v->opt_quiet = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));
 }
@@ -1158,6 +1172,8 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (const char* k = getenv("LINON_CHECK_MAX_REGS")) tmp.opt_max_regs = atoi(k);
     if (const char* k = getenv("LINON_CHECK_SPECIALIZE")) tmp.opt_specialize = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BVH")) tmp.use_bvh = atoi(k) != 0;
+    if (const char* k = getenv("LINON_CHECK_QUIET_ZONE")) tmp.opt_quiet = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_CULL")) tmp.opt_cull = atoi(k);
     Variant var = make_variant(&tmp, flags);
     if (var.n_faces == 0 && !tmp.use_bvh) default_mesh_counts(var);
     std::vector<char> cubin;

@@ -1,0 +1,96 @@
+// emu_driver.cpp — TEST INFRASTRUCTURE: runs linon_march_tiles, compiled for the host from the exact NVRTC source text of
+// a variant (-DLINON_EMU_SOURCE="path", dumped by LINON_DUMP_SOURCE), one warp per CTA through cuda_shim.hpp.
+// Mesh tables come from the product's own host code (mesh_tables.hpp), the launch geometry mirrors linon_render.
+#include "cuda_shim.hpp"
+
+#include LINON_EMU_SOURCE
+
+#undef threadIdx
+#undef blockIdx
+#undef blockDim
+#undef gridDim
+#include <vector>
+
+#include "mesh_tables.hpp"
+
+static_assert(LINON_BLOCK == 32, "the emulation runs one warp per CTA");
+
+extern "C" {
+
+struct EmuFrame {
+    int32_t width, height;
+    float cam_origin[4], cam_view[4], cam_up[4];
+    float settings[6];  // 24 bytes, src/main_view.rs:43-51 (two of them are i32: copied bytewise)
+    const float* verts;
+    const uint32_t* faces;
+    int32_t n_verts, n_faces;
+    uint8_t* rgba8;       // [H][W][4]
+    float* endpoint;      // [H][W][4]
+    int32_t* hit_id;      // [H][W]
+    uint64_t* counters;   // [16]
+    int32_t n_threads;
+};
+
+static int fixed_step_count(float h) {  // capi.cpp: fixed_step_count
+    if (!(h > 0.0f)) return 0;
+    volatile float t = 0.0f;
+    int n = 0;
+    while (t <= 5.0f && n < (1 << 24)) {
+        t = t + h;
+        ++n;
+    }
+    return n;
+}
+
+static void kernel_entry(void* arg) { linon_march_tiles(*(const MarchParams*)arg); }
+
+// returns 0 on success, 1 when the mesh tables do not match the variant, 2 when a warp collective was abandoned
+int emu_march(const EmuFrame* f) {
+    linon::MeshTables mt;
+    if (!linon::build_mesh_tables(f->verts, (uint32_t)f->n_verts, f->faces, (uint32_t)f->n_faces, mt)) return 1;
+#if !LINON_BVH
+    if ((int)mt.n_groups() != LINON_N_GROUPS || (int)mt.n_p1() != LINON_N_P1 || (int)mt.n_boxes() != LINON_N_BOXES ||
+        (int)mt.n_segments() != LINON_N_SEGS || f->n_faces != LINON_N_FACES)
+        return 1;
+#endif
+    std::vector<float> tris = mt.tris;
+    tris.insert(tris.end(), mt.planes.begin(), mt.planes.end());
+    tris.insert(tris.end(), mt.p1_planes.begin(), mt.p1_planes.end());
+    tris.insert(tris.end(), mt.boxes.begin(), mt.boxes.end());
+    std::vector<int> ranges = mt.ranges;
+    ranges.insert(ranges.end(), mt.segments.begin(), mt.segments.end());
+
+    MarchParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(P.cam_origin, f->cam_origin, 16);
+    memcpy(P.cam_view, f->cam_view, 16);
+    memcpy(P.cam_up, f->cam_up, 16);
+    memcpy(&P.settings, f->settings, 24);
+    P.width = f->width;
+    P.height = f->height;
+    P.local_rows = f->height;
+    P.shard_rank = 0;
+    P.shard_world = 1;
+    P.rows_per_block = 32;
+    P.tris = (const float4*)tris.data();
+    P.group_range = ranges.data();
+    P.raycast = (uchar4*)f->rgba8;
+    P.endpoint = (float4*)f->endpoint;
+    P.hit_id = f->hit_id;
+    P.counters = (unsigned long long*)f->counters;
+    const unsigned int tiles_x = (f->width + 7) / 8, tiles_y = (f->height + 3) / 4;
+    P.n_ray_slots = tiles_x * tiles_y * 32u;
+    P.plane_w_max = mt.coord_max;
+    P.n_fixed_steps = LINON_ADAPTIVE ? 0 : fixed_step_count(LINON_H_INITIAL);
+    const int n_blocks = (int)(P.n_ray_slots / 32u);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(f->n_threads > 0 ? f->n_threads : 8)
+    for (int b = 0; b < n_blocks; ++b) {
+        if (!emu::run_warp(kernel_entry, &P, (unsigned int)b)) {
+#pragma omp atomic write
+            bad = 1;
+        }
+    }
+    return bad ? 2 : 0;
+}
+}

@@ -1,0 +1,157 @@
+"""The march module's own device code, executed on the host cores (tests/emu), against the oracle.
+
+tests/emu compiles the exact NVRTC source text of a kernel variant with g++ behind a small CUDA shim (one warp per CTA,
+lanes as fibers that meet at the warp collectives) - so the logic of linon_march_tiles (tile mapping, phases, votes,
+culling budget, counters, stores) is covered without a GPU:
+  * strict-math variants must equal the oracle bit for bit (that also pins the emulation itself);
+  * the quiet-zone path (LINON_OPT_QUIET_ZONE, csrc/device/mirage_fused.cuh: straight steps where a fused mirage body is
+    the identity) must meet the north-star tolerances against the oracle, execute every step, and spend most of a C3-like
+    frame in straight steps.
+Fast-math variants differ from the device by the MUFU approximation error only (libm here).
+"""
+import numpy as np
+import pytest
+
+from linon_b200 import _capi as capi
+from linon_b200 import parity
+from linon_b200.main_view import PredefinedFunction
+from oracle import np_oracle as npo
+
+from emu import emu
+
+SETTINGS = dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0)
+MIRAGES = [PredefinedFunction.MirageSpherical, PredefinedFunction.MiragePlane, PredefinedFunction.MirageSphericalSigmoid,
+           PredefinedFunction.MiragePlaneSigmoid]
+
+
+def _frame_inputs(W, H, orbit_frame=0):
+    verts, faces, center = npo.default_scene()[:3]
+    cam = npo.camera_uniform(npo.orbit_camera(center, W, H, orbit_frame))
+    return verts, faces, cam
+
+
+def _oracle_frame(oracle, verts, faces, cam, fn, W, H, h_initial, adaptive):
+    ref = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=h_initial, adaptive=adaptive)
+    _, exponents = oracle.overlay(ref["rgba8"], ref["endpoint"], SETTINGS)
+    return ref, parity.high_lyapunov_mask(exponents)
+
+
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSpherical, PredefinedFunction.TranslationX, PredefinedFunction.LorenzAttractor])
+@pytest.mark.parametrize("cull", [0, 1])
+def test_emulated_strict_kernel_is_bit_exact_with_the_oracle(product_lib, oracle, fn, cull):
+    """Fixed default step, strict math: the device code on the host equals the oracle in every output bit and counter."""
+    W, H = 40, 27  # ragged: partial tiles on both edges
+    verts, faces, cam = _frame_inputs(W, H)
+    lib = emu.build(fn.to_code(), capi.RENDER_ADAPTIVE_OFF, capi.MATH_STRICT, cull=cull)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    ref = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=0.1, adaptive=False)
+    assert np.array_equal(got["hit_id"], ref["hit_id"])
+    assert np.array_equal(got["rgba8"], ref["rgba8"])
+    assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+    assert int(got["counters"][0]) == W * H * 51 == int(ref["accepted"].sum())
+    assert int(got["counters"][1]) == int(ref["prehit"].sum())
+    if not cull:
+        assert int(got["counters"][3]) == int(ref["prehit"].sum()) * 36  # every face on every pre-hit step
+
+
+def test_emulated_adaptive_strict_kernel_is_bit_exact_with_the_oracle(product_lib, oracle):
+    """Adaptive sampling (per-lane loop, votes among the lanes still marching)."""
+    W, H = 32, 20
+    fn = PredefinedFunction.MirageSpherical
+    verts, faces, cam = _frame_inputs(W, H)
+    lib = emu.build(fn.to_code(), 0, capi.MATH_STRICT)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    ref = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=0.1, adaptive=True)
+    assert np.array_equal(got["hit_id"], ref["hit_id"])
+    assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+    assert int(got["counters"][0]) == int(ref["accepted"].sum()) and int(got["counters"][2]) == int(ref["rejected"].sum())
+
+
+@pytest.mark.parametrize("fn", MIRAGES)
+def test_quiet_zone_default_step_frames_meet_the_north_star(product_lib, oracle, fn):
+    """Adaptive off, h = 0.1 (51 steps): quiet-zone straight steps against the oracle, all four predefined mirage bodies."""
+    W, H = 64, 48
+    verts, faces, cam = _frame_inputs(W, H)
+    ref, excl = _oracle_frame(oracle, verts, faces, cam, fn, W, H, 0.1, False)
+    lib = emu.build(fn.to_code(), capi.RENDER_ADAPTIVE_OFF, capi.MATH_FAST, quiet_zone=1)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    m = parity.compare_frames(got, ref, exclude=excl)
+    assert parity.passes_north_star(m), m
+    c = got["counters"]
+    assert int(c[0]) == W * H * 51              # every step is still executed and counted
+    assert int(c[15]) > 0.5 * int(c[0]), c      # ... most of them as straight steps
+
+
+@pytest.mark.parametrize("fn,orbit_frame", [(PredefinedFunction.MirageSphericalSigmoid, 0), (PredefinedFunction.MirageSphericalSigmoid, 24),
+                                            (PredefinedFunction.MirageSpherical, 0)])
+def test_quiet_zone_enhance_frames_meet_the_north_star(product_lib, oracle, fn, orbit_frame):
+    """C3 at reduced resolution (h = 0.001, 5001 steps per ray) with the quiet zone on: north star against the oracle, and no
+    worse than the same kernel without it."""
+    W, H = 48, 36
+    verts, faces, cam = _frame_inputs(W, H, orbit_frame)
+    ref, excl = _oracle_frame(oracle, verts, faces, cam, fn, W, H, 0.001, False)
+    frames = {}
+    for quiet in (0, 1):
+        lib = emu.build(fn.to_code(), capi.RENDER_ENHANCE, capi.MATH_FAST, quiet_zone=quiet)
+        frames[quiet] = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    m_off = parity.compare_frames(frames[0], ref, exclude=excl)
+    m_on = parity.compare_frames(frames[1], ref, exclude=excl)
+    assert parity.passes_north_star(m_on), m_on
+    assert m_on["hit_group_agree"] >= m_off["hit_group_agree"] - 1e-3 and m_on["endpoint_max_rel"] <= max(2.0 * m_off["endpoint_max_rel"], 5e-4), (m_on, m_off)
+    c_on, c_off = frames[1]["counters"], frames[0]["counters"]
+    assert int(c_on[0]) == int(c_off[0]) == W * H * 5001
+    assert int(c_off[15]) == 0
+    assert int(c_on[15]) > 0.9 * int(c_on[0]), c_on      # > 90 % of the steps of this frame are outside the zone
+    # on against off: the two builds differ only by rounding noise outside the zone
+    m = parity.compare_frames(frames[1], frames[0], exclude=excl)
+    assert m["hit_group_agree"] >= 0.999 and m["endpoint_within_1e3"] >= 0.999, m
+
+
+def test_quiet_zone_is_closer_to_the_fp64_reference_run(product_lib, oracle):
+    """Outside the zone the reference's fp32 result is `v + rounding noise`; a straight step has none.  Against the oracle's
+    fp64 evaluation of the same WGSL the quiet-zone frame must not be farther away than the plain fast build."""
+    W, H = 48, 36
+    fn = PredefinedFunction.MirageSphericalSigmoid
+    verts, faces, cam = _frame_inputs(W, H)
+    ref64 = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=0.001, adaptive=False, use_fp64=True)
+    _, exponents = oracle.overlay(ref64["rgba8"], ref64["endpoint"], SETTINGS)
+    excl = parity.high_lyapunov_mask(exponents)
+    err = {}
+    for quiet in (0, 1):
+        lib = emu.build(fn.to_code(), capi.RENDER_ENHANCE, capi.MATH_FAST, quiet_zone=quiet)
+        got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+        use = ~excl & (parity.canonical_hits(got["hit_id"]) == parity.canonical_hits(ref64["hit_id"]))
+        d = np.linalg.norm(got["endpoint"][use][:, :3].astype(np.float64) - ref64["endpoint"][use][:, :3], axis=-1)
+        err[quiet] = float(np.median(d))
+    assert err[1] <= 1.5 * err[0] + 1e-7, err
+
+
+def test_quiet_zone_needs_a_fused_mirage_body(product_lib):
+    """Generic translations, strict / fused math and adaptive variants never define the zone: the option compiles to the
+    same module as without it."""
+    import os
+    import tempfile
+    from linon_b200.main_view import compile_check
+
+    def module_text(body, flags, math, quiet):
+        fd, path = tempfile.mkstemp(suffix=".cu")
+        os.close(fd)
+        old = {k: os.environ.get(k) for k in ("LINON_DUMP_SOURCE", "LINON_CHECK_QUIET_ZONE")}
+        os.environ["LINON_DUMP_SOURCE"] = path
+        os.environ["LINON_CHECK_QUIET_ZONE"] = str(quiet)
+        try:
+            compile_check(body, flags=flags, math_mode=math)
+            return open(path).read()
+        finally:
+            os.unlink(path)
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+
+    sig = PredefinedFunction.MirageSphericalSigmoid.to_code()
+    assert "-DLINON_QUIET_ZONE=1" in module_text(sig, capi.RENDER_ENHANCE, capi.MATH_FAST, 1).splitlines()[0]
+    assert "-DLINON_QUIET_ZONE=0" in module_text(sig, capi.RENDER_ENHANCE, capi.MATH_FAST, 0).splitlines()[0]
+    assert "-DLINON_QUIET_ZONE=0" in module_text(sig, capi.RENDER_ENHANCE, capi.MATH_STRICT, 1).splitlines()[0]
+    assert "-DLINON_QUIET_ZONE=0" in module_text(sig, 0, capi.MATH_FAST, 1).splitlines()[0]  # adaptive sampling on
+    # a user-edited body runs the generic translation, which has no quiet_steps: the macro is switched off in the module
+    generic = module_text(sig + " ", capi.RENDER_ENHANCE, capi.MATH_FAST, 1)
+    assert "LINON_HAS_QUIET_ZONE" not in generic.split("march_kernels.cuh", 1)[0].replace("defined(LINON_HAS_QUIET_ZONE)", "")
