@@ -490,6 +490,71 @@ struct SafeDistance {
 };
 __device__ __forceinline__ float l1_norm(vec3f p) { return fabsf(p.x) + fabsf(p.y) + fabsf(p.z); }
 
+#if LINON_CULL && !LINON_BVH && LINON_QUIET_ZONE
+// LINON_QUIET_ZONE: the number of steps of a STRAIGHT ray - step j runs from p + j d to p + (j + 1) d, d = h dir unchanged -
+// during which no face can be hit, from the same first-pass bounds as nearest_geometry_distance but along the direction of
+// travel: the safe-distance budget shrinks with every step whatever the direction, so a ray running parallel to a wall
+// pays a culling check every few steps although it never approaches the wall.
+//   plane   a face of the group can report t in (eps, max_dist) on step j only if the segment reaches its plane, i.e. if
+//           the distance D_j at the start of the step is at most the distance r the step covers towards it.  D_j = D - j r
+//           while approaching, so steps 0 .. n - 1 are clear when D - n r > margin: n = floor((D - margin) / r).  A ray
+//           moving away from a plane never reaches it.
+//   box     every face of the cluster lies inside its box; the segment must be inside all three slabs of the box at once,
+//           so no step before the LATEST slab entry can reach a face: n = floor(max_k gap_k / rate_k).
+// Rounding: the k-th position differs from p + k d by at most k 2e-7 C per coordinate (C = 1 + |p|_1 + the longest possible
+// travel + max |w|: the bound SafeDistance uses, with the travel added because a run can be long), so every approach rate is
+// increased by delta = 2e-7 C, and margin = 2e-5 C covers the rounding of the distance evaluations and of hit_triangle's
+// own t.  A step declared clear is one on which the face loop would find nothing: skipping its check never changes a result
+// (tests/test_emulation_cpu.py compares with LINON_CULL = 0).
+__device__ __forceinline__ int straight_clear_steps(const float4* __restrict__ s_tri, vec3f p, vec3f d, float travel_max,
+                                                    float plane_w_max) {
+    const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES + LINON_N_GROUPS;
+    const float C = __fadd_ru(__fadd_ru(__fadd_ru(1.0f, l1_norm(p)), travel_max), plane_w_max);
+    const float margin = 2e-5f * C, delta = 2e-7f * C;
+    float clear = 3.0e8f;
+#pragma unroll LINON_GROUP_UNROLL
+    for (int g = 0; g < LINON_N_P1; ++g) {
+        const float4 pl = s_plane[g];
+        const float sigma = __fmaf_rn(p.x, pl.x, __fmaf_rn(p.y, pl.y, __fmaf_rn(p.z, pl.z, -pl.w)));
+        const float rate = __fmaf_rn(d.x, pl.x, __fmaf_rn(d.y, pl.y, d.z * pl.z));  // change of sigma per step
+        // approaching when sigma and rate have opposite signs: towards = -rate sign(sigma)
+        const float towards = fmaxf(sigma > 0.0f ? -rate : rate, 0.0f);
+        const float n = __fdividef(fabsf(sigma) - margin, towards + delta);  // <= 0 within the margin; NaN -> 0 below
+        clear = fminf(clear, n);
+    }
+#if LINON_N_BOXES > 0
+    const float4* __restrict__ s_box = s_plane + LINON_N_P1;
+#pragma unroll 2
+    for (int b = 0; b < LINON_N_BOXES; ++b) {
+        const float4 lo = s_box[2 * b], hi = s_box[2 * b + 1];
+        float latest = 0.0f;
+        {
+            const float below = lo.x - margin - p.x, above = p.x - hi.x - margin;
+            const float gap = fmaxf(fmaxf(below, above), 0.0f);
+            const float towards = fmaxf(below > 0.0f ? d.x : -d.x, 0.0f);
+            latest = fmaxf(latest, __fdividef(gap, towards + delta));
+        }
+        {
+            const float below = lo.y - margin - p.y, above = p.y - hi.y - margin;
+            const float gap = fmaxf(fmaxf(below, above), 0.0f);
+            const float towards = fmaxf(below > 0.0f ? d.y : -d.y, 0.0f);
+            latest = fmaxf(latest, __fdividef(gap, towards + delta));
+        }
+        {
+            const float below = lo.z - margin - p.z, above = p.z - hi.z - margin;
+            const float gap = fmaxf(fmaxf(below, above), 0.0f);
+            const float towards = fmaxf(below > 0.0f ? d.z : -d.z, 0.0f);
+            latest = fmaxf(latest, __fdividef(gap, towards + delta));
+        }
+        clear = fminf(clear, latest);
+    }
+#endif
+    // 0.999: the division; NaN (a NaN position) and negative values give 0
+    return (int)fmaxf(clear * 0.999f, 0.0f);
+}
+#endif
+
+
 // Blinn-Phong with the camera as light, src/main_view.wgsl:199-217.
 __device__ __forceinline__ vec3f shade(const float4* __restrict__ s_tri, int id, vec3f direction) {
     const float4 b = s_tri[3 * id + 1], c = s_tri[3 * id + 2];
@@ -551,7 +616,9 @@ __device__ __forceinline__ void init_ray(const MarchParams& P, int x, int local_
 
 struct StepCounters {
     unsigned int accepted, prehit, rejected, face_tests, checks;
-    unsigned int quiet;  // LINON_QUIET_ZONE: accepted steps taken as straight steps (velocity = direction, no field evaluation)
+#if LINON_QUIET_ZONE
+    unsigned int quiet;  // accepted steps taken as straight steps (velocity = direction, no field evaluation)
+#endif
 };
 
 __device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounters c) {
@@ -686,13 +753,25 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 const float cost_up = __fmul_ru(sd.cost_linf(q_inf, kh), 1.000001f);
                 // steps whose budget stays positive (0.9999 covers the division and keeps the budget after the run > 0)
                 const int nb = (int)fminf(__fdividef(sd.budget * 0.9999f, cost_up), 268435456.0f);
-                const int n_lane = LINON_CULL ? min(nq, max(nb, 0)) : 0;  // without culling every pre-hit step runs the face loop
+                int n_clear = max(nb, 0);  // steps this lane can take without a culling check
+#if LINON_CULL && !LINON_BVH
+                // the budget is what limits the run (a wall nearby, or a run that just ended): ask how far the straight ray
+                // really is from the geometry along its direction
+                if (__any_sync(0xffffffffu, n_clear < nq && !has_color)) {
+                    const vec3f d = r.dir * h;
+                    const float travel_max = (float)(n_steps - i) * l1_norm(d);
+                    if (!has_color) n_clear = max(n_clear, straight_clear_steps(s_tri, r.p, d, travel_max, P.plane_w_max));
+                }
+#endif
+                const int n_lane = LINON_CULL ? min(nq, n_clear) : 0;  // without culling every pre-hit step runs the face loop
                 const int n = min(__reduce_min_sync(0xffffffffu, n_lane), n_steps - i);
                 if (n > 0) {
 #pragma unroll 4
                     for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
                     r.t = __fmaf_rn((float)n, h, r.t);
-                    sd.budget = __fmaf_rd(-(float)n, cost_up, sd.budget);  // +inf stays +inf
+                    // within the budget: take the run from it (+inf stays +inf); beyond it (the directional bound allowed
+                    // more): the budget is spent, the next regular step runs a check and refreshes it
+                    sd.budget = (n <= nb) ? __fmaf_rd(-(float)n, cost_up, sd.budget) : 0.0f;
                     cnt.quiet += (unsigned int)n;
                     i += n - 1;  // the loop header adds the last one
                     continue;
@@ -790,7 +869,10 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
             P.hit_id[pix] = hit;
         } else {
-            cnt.accepted = cnt.prehit = cnt.rejected = cnt.face_tests = cnt.checks = cnt.quiet = 0u;
+            cnt.accepted = cnt.prehit = cnt.rejected = cnt.face_tests = cnt.checks = 0u;
+#if LINON_QUIET_ZONE
+            cnt.quiet = 0u;
+#endif
         }
     }
 #else

@@ -25,7 +25,7 @@ class EmuFrame(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cam_origin", C.c_float * 4), ("cam_view", C.c_float * 4),
                 ("cam_up", C.c_float * 4), ("settings", C.c_byte * 24), ("verts", C.c_void_p), ("faces", C.c_void_p),
                 ("n_verts", C.c_int32), ("n_faces", C.c_int32), ("rgba8", C.c_void_p), ("endpoint", C.c_void_p),
-                ("hit_id", C.c_void_p), ("counters", C.c_void_p), ("n_threads", C.c_int32)]
+                ("hit_id", C.c_void_p), ("counters", C.c_void_p), ("n_threads", C.c_int32), ("tile_row_step", C.c_int32)]
 
 
 def _cxx():
@@ -75,7 +75,7 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
     return lib
 
 
-def march(lib, verts, faces, camera, settings, W, H, n_threads=0):
+def march(lib, verts, faces, camera, settings, W, H, n_threads=0, tile_row_step=1):
     """camera: dict(origin, view_direction, up); settings: dict like the oracle's. -> dict(rgba8, endpoint, hit_id, counters)."""
     verts = np.ascontiguousarray(verts, np.float32)
     faces = np.ascontiguousarray(faces, np.uint32)
@@ -96,6 +96,7 @@ def march(lib, verts, faces, camera, settings, W, H, n_threads=0):
     f.rgba8, f.endpoint = out["rgba8"].ctypes.data, out["endpoint"].ctypes.data
     f.hit_id, f.counters = out["hit_id"].ctypes.data, out["counters"].ctypes.data
     f.n_threads = n_threads or (os.cpu_count() or 8)
+    f.tile_row_step = tile_row_step
     rc = lib.emu_march(C.byref(f))
     if rc != 0:
         raise RuntimeError(f"emu_march rc={rc}")

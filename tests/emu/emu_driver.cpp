@@ -29,6 +29,7 @@ struct EmuFrame {
     int32_t* hit_id;      // [H][W]
     uint64_t* counters;   // [16]
     int32_t n_threads;
+    int32_t tile_row_step;  // > 1: only every n-th row of 8x4 tiles is run (sampled counters of a large frame)
 };
 
 static int fixed_step_count(float h) {  // capi.cpp: fixed_step_count
@@ -86,6 +87,7 @@ int emu_march(const EmuFrame* f) {
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(f->n_threads > 0 ? f->n_threads : 8)
     for (int b = 0; b < n_blocks; ++b) {
+        if (f->tile_row_step > 1 && (b / (int)tiles_x) % f->tile_row_step != 0) continue;
         if (!emu::run_warp(kernel_entry, &P, (unsigned int)b)) {
 #pragma omp atomic write
             bad = 1;

@@ -107,6 +107,29 @@ def test_quiet_zone_enhance_frames_meet_the_north_star(product_lib, oracle, fn, 
     assert m["hit_group_agree"] >= 0.999 and m["endpoint_within_1e3"] >= 0.999, m
 
 
+@pytest.mark.parametrize("fn,flags,size,orbit_frame", [
+    (PredefinedFunction.MirageSphericalSigmoid, capi.RENDER_ENHANCE, (40, 28), 0),
+    (PredefinedFunction.MiragePlane, capi.RENDER_ENHANCE, (40, 28), 13),
+    (PredefinedFunction.MirageSpherical, capi.RENDER_ADAPTIVE_OFF, (96, 72), 40),
+    (PredefinedFunction.MiragePlaneSigmoid, capi.RENDER_ADAPTIVE_OFF, (96, 72), 0)])
+def test_quiet_zone_culling_never_changes_a_result(product_lib, fn, flags, size, orbit_frame):
+    """Straight runs skip culling checks on the strength of two bounds (the safe-distance budget and the directional bound
+    of straight_clear_steps).  With LINON_CULL = 0 every pre-hit step runs the loop over all 36 faces instead: the frames must
+    be identical bit for bit, i.e. no skipped check could have found a face."""
+    W, H = size
+    verts, faces, cam = _frame_inputs(W, H, orbit_frame)
+    frames = []
+    for cull in (1, 0):
+        lib = emu.build(fn.to_code(), flags, capi.MATH_FAST, quiet_zone=1, cull=cull)
+        frames.append(emu.march(lib, verts, faces, cam, SETTINGS, W, H))
+    a, b = frames
+    for k in ("hit_id", "rgba8", "endpoint"):
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    assert (a["hit_id"] >= 0).mean() > 0.3
+    assert int(a["counters"][15]) == int(b["counters"][15]) > 0          # the same steps are straight steps
+    assert int(a["counters"][4]) < 0.25 * int(b["counters"][4])           # ... and most checks are gone
+
+
 def test_quiet_zone_is_closer_to_the_fp64_reference_run(product_lib, oracle):
     """Outside the zone the reference's fp32 result is `v + rounding noise`; a straight step has none.  Against the oracle's
     fp64 evaluation of the same WGSL the quiet-zone frame must not be farther away than the plain fast build."""
