@@ -47,12 +47,20 @@ FUSED_STEP_FIXED = 12 + 2 + 3 + 6    # k1 + 2 k2 + 2 k3 (6 FMA), min3 of the dis
 SAFE_STEP_V2 = 8                     # step_dir (3), |s|_1 (2), cost (2), budget - cost (1)
 
 
-def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True) -> float:
-    """Executed-work model of the fast-mode mirage path in fixed-step variants (Enhance, adaptive off)."""
+QUIET_STEP = 6  # LINON_OPT_QUIET_ZONE: a straight step is the position update alone (3 FMA)
+
+
+def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True, quiet_steps: int = 0) -> float:
+    """Executed-work model of the fast-mode mirage path in fixed-step variants (Enhance, adaptive off).
+
+    quiet_steps: accepted steps taken as straight steps (counter 15 of linon_debug_profile with LINON_OPT_QUIET_ZONE on).
+    They are credited with the position update only; the planning of a run (zone entry, clear steps: ~150 FLOPs, a few
+    per ray) is not counted at all, and the per-step safe-distance bookkeeping only for the steps that are not straight."""
     f_stage, f_last, f_prev = FUSED_FLOPS[fn_id]
     step = FUSED_STEP_FIXED + (0 if field_weight_is_one else 10) + 2 * f_stage + f_last + f_prev
-    flops = counters.accepted_steps * step + counters.face_tests * FACE_TEST
-    flops += counters.prehit_steps * SAFE_STEP_V2
+    full_steps = counters.accepted_steps - quiet_steps
+    flops = full_steps * step + quiet_steps * QUIET_STEP + counters.face_tests * FACE_TEST
+    flops += counters.prehit_steps * SAFE_STEP_V2 * (full_steps / max(counters.accepted_steps, 1))
     flops += counters.culling_checks * (PREHIT_EXTRA + CHECK_EXTRA + 3) + counters.plane_tests * PLANE_TEST
     return float(flops)
 
