@@ -25,19 +25,20 @@ class EmuFrame(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cam_origin", C.c_float * 4), ("cam_view", C.c_float * 4),
                 ("cam_up", C.c_float * 4), ("settings", C.c_byte * 24), ("verts", C.c_void_p), ("faces", C.c_void_p),
                 ("n_verts", C.c_int32), ("n_faces", C.c_int32), ("rgba8", C.c_void_p), ("endpoint", C.c_void_p),
-                ("hit_id", C.c_void_p), ("counters", C.c_void_p), ("n_threads", C.c_int32), ("tile_row_step", C.c_int32)]
+                ("hit_id", C.c_void_p), ("counters", C.c_void_p), ("n_threads", C.c_int32), ("tile_row_step", C.c_int32),
+                ("kernel", C.c_int32), ("grid", C.c_int32), ("pos16", C.c_void_p), ("ray_samples", C.c_void_p)]
 
 
 def _cxx():
     return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1"):
-    """-> ctypes library with emu_march for this variant of the tile kernel."""
+def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1", pairs: bool = False):
+    """-> ctypes library with emu_march for this variant of the march module (pairs: also linon_march_pairs)."""
     from linon_b200.main_view import compile_check
     os.makedirs(_CACHE, exist_ok=True)
     env = {"LINON_CHECK_BLOCK": "32", "LINON_CHECK_QUIET_ZONE": str(quiet_zone), "LINON_CHECK_CULL": str(cull),
-           "LINON_CHECK_KERNEL": "0"}
+           "LINON_CHECK_KERNEL": "2" if pairs else "0"}
     old = {k: os.environ.get(k) for k in list(env) + ["LINON_DUMP_SOURCE"]}
     fd, dump = tempfile.mkstemp(suffix=".cu", dir=_CACHE)
     os.close(fd)
@@ -75,8 +76,10 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
     return lib
 
 
-def march(lib, verts, faces, camera, settings, W, H, n_threads=0, tile_row_step=1):
-    """camera: dict(origin, view_direction, up); settings: dict like the oracle's. -> dict(rgba8, endpoint, hit_id, counters)."""
+def march(lib, verts, faces, camera, settings, W, H, n_threads=0, tile_row_step=1, kernel=0, grid=0, sample_pos=None):
+    """camera: dict(origin, view_direction, up); settings: dict like the oracle's. -> dict(rgba8, endpoint, hit_id, counters).
+    kernel: LINON_OPT_KERNEL (0 tiles, 1 persistent two phases, 2 pairs, 3 persistent one phase).
+    sample_pos: float32[8,2] -> runs linon_sample_rays instead and returns dict(ray_samples float32[800,8])."""
     verts = np.ascontiguousarray(verts, np.float32)
     faces = np.ascontiguousarray(faces, np.uint32)
     out = dict(rgba8=np.zeros((H, W, 4), np.uint8), endpoint=np.zeros((H, W, 4), np.float32),
@@ -97,6 +100,11 @@ def march(lib, verts, faces, camera, settings, W, H, n_threads=0, tile_row_step=
     f.hit_id, f.counters = out["hit_id"].ctypes.data, out["counters"].ctypes.data
     f.n_threads = n_threads or (os.cpu_count() or 8)
     f.tile_row_step = tile_row_step
+    f.kernel, f.grid = kernel, grid
+    if sample_pos is not None:
+        pos = np.ascontiguousarray(sample_pos, np.float32).reshape(8, 2)
+        out["ray_samples"] = np.zeros((800, 8), np.float32)
+        f.pos16, f.ray_samples = pos.ctypes.data, out["ray_samples"].ctypes.data
     rc = lib.emu_march(C.byref(f))
     if rc != 0:
         raise RuntimeError(f"emu_march rc={rc}")

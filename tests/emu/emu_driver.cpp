@@ -30,6 +30,10 @@ struct EmuFrame {
     uint64_t* counters;   // [16]
     int32_t n_threads;
     int32_t tile_row_step;  // > 1: only every n-th row of 8x4 tiles is run (sampled counters of a large frame)
+    int32_t kernel;         // LINON_OPT_KERNEL: 0 tiles, 1 persistent (phase A, phase B), 2 pairs, 3 persistent (one phase)
+    int32_t grid;           // persistent kernels: CTAs (0 = one per host thread)
+    const float* pos16;     // emu_sample_rays: 8 normalised start positions
+    float* ray_samples;     // emu_sample_rays: 800 x {position, colour}
 };
 
 static int fixed_step_count(float h) {  // capi.cpp: fixed_step_count
@@ -44,6 +48,27 @@ static int fixed_step_count(float h) {  // capi.cpp: fixed_step_count
 }
 
 static void kernel_entry(void* arg) { linon_march_tiles(*(const MarchParams*)arg); }
+#if LINON_PAIRS && !LINON_BVH
+static void pairs_entry(void* arg) { linon_march_pairs(*(const MarchParams*)arg); }
+#endif
+static void refill_entry(void* arg) { linon_march_refill(*(const MarchParams*)arg); }
+static void phase_a_entry(void* arg) { linon_march_phase_a(*(const MarchParams*)arg); }
+static void phase_b_entry(void* arg) { linon_march_phase_b(*(const MarchParams*)arg); }
+static void sample_entry(void* arg) { linon_sample_rays(*(const SampleParams*)arg); }
+
+static int run_grid(void (*entry)(void*), void* arg, int n_blocks, int n_threads, int tile_row_step, int tiles_x) {
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+    for (int b = 0; b < n_blocks; ++b) {
+        if (tile_row_step > 1 && (b / tiles_x) % tile_row_step != 0) continue;
+        emu::g_grid_dim = {(unsigned int)n_blocks, 1, 1};
+        if (!emu::run_warp(entry, arg, (unsigned int)b)) {
+#pragma omp atomic write
+            bad = 1;
+        }
+    }
+    return bad;
+}
 
 // returns 0 on success, 1 when the mesh tables do not match the variant, 2 when a warp collective was abandoned
 int emu_march(const EmuFrame* f) {
@@ -83,15 +108,41 @@ int emu_march(const EmuFrame* f) {
     P.n_ray_slots = tiles_x * tiles_y * 32u;
     P.plane_w_max = mt.coord_max;
     P.n_fixed_steps = LINON_ADAPTIVE ? 0 : fixed_step_count(LINON_H_INITIAL);
-    const int n_blocks = (int)(P.n_ray_slots / 32u);
+    P.n_pair_slots = (((unsigned int)f->width + 15) / 16) * tiles_y * 32u;
+    const int n_threads = f->n_threads > 0 ? f->n_threads : 8;
+    const int grid = f->grid > 0 ? f->grid : n_threads;
+    std::vector<unsigned int> work(16, 0u);
+    std::vector<int> q_pixel;
+    std::vector<float4> q_state;
+    P.work = work.data();
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(f->n_threads > 0 ? f->n_threads : 8)
-    for (int b = 0; b < n_blocks; ++b) {
-        if (f->tile_row_step > 1 && (b / (int)tiles_x) % f->tile_row_step != 0) continue;
-        if (!emu::run_warp(kernel_entry, &P, (unsigned int)b)) {
-#pragma omp atomic write
-            bad = 1;
-        }
+    if (f->ray_samples) {  // linon_sample_rays: one CTA, lanes 0..7 carry the eight rays
+        SampleParams S;
+        S.march = P;
+        S.pos16 = f->pos16;
+        S.ray_samples = (float4*)f->ray_samples;
+        bad = run_grid(sample_entry, &S, 1, 1, 1, 1);
+    } else if (f->kernel == 0) {
+        bad = run_grid(kernel_entry, &P, (int)(P.n_ray_slots / 32u), n_threads, f->tile_row_step, (int)tiles_x);
+    } else if (f->kernel == 2) {
+#if LINON_PAIRS && !LINON_BVH
+        bad = run_grid(pairs_entry, &P, (int)(P.n_pair_slots / 32u), n_threads, 1, 1);
+#else
+        return 3;
+#endif
+    } else if (f->kernel == 3) {
+        bad = run_grid(refill_entry, &P, grid, n_threads, 1, 1);
+    } else if (f->kernel == 1) {
+        const size_t cap = (size_t)f->width * f->height;
+        q_pixel.assign(cap, 0);
+        q_state.assign(3 * cap, float4{0, 0, 0, 0});
+        P.q_pixel = q_pixel.data();
+        P.q_state = q_state.data();
+        P.q_capacity = (unsigned int)cap;
+        bad = run_grid(phase_a_entry, &P, grid, n_threads, 1, 1);
+        if (!bad) bad = run_grid(phase_b_entry, &P, grid, n_threads, 1, 1);  // phase B sees the complete queue
+    } else {
+        return 3;
     }
     return bad ? 2 : 0;
 }

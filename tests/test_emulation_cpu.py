@@ -67,6 +67,35 @@ def test_emulated_adaptive_strict_kernel_is_bit_exact_with_the_oracle(product_li
     assert int(got["counters"][0]) == int(ref["accepted"].sum()) and int(got["counters"][2]) == int(ref["rejected"].sum())
 
 
+@pytest.mark.parametrize("adaptive", [False, True])
+@pytest.mark.parametrize("kernel", [capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL])
+def test_every_emulated_march_kernel_is_bit_exact_with_the_oracle(product_lib, oracle, kernel, adaptive):
+    """The tile kernel, two rays per thread (f32x2, component-wise here), persistent warps in two phases (device queue between
+    them) and in one phase (lane refill from a chunked cursor): the same frame, bit for bit, counters included."""
+    W, H = 41, 27
+    fn = PredefinedFunction.MirageSpherical
+    verts, faces, cam = _frame_inputs(W, H)
+    lib = emu.build(fn.to_code(), 0 if adaptive else capi.RENDER_ADAPTIVE_OFF, capi.MATH_STRICT, pairs=True)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H, kernel=kernel, grid=5)
+    ref = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=0.1, adaptive=adaptive)
+    for k in ("hit_id", "rgba8", "endpoint"):
+        assert np.array_equal(got[k].view(np.uint8), ref[k].view(np.uint8)), k
+    assert int(got["counters"][0]) == int(ref["accepted"].sum())
+    assert int(got["counters"][2]) == int(ref["rejected"].sum())
+
+
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSpherical, PredefinedFunction.RoesslerAttractor])
+def test_emulated_sample_ray_kernel_is_bit_exact_with_the_oracle(product_lib, oracle, fn):
+    """linon_sample_rays (src/main_view.wgsl:281-314): eight rays, 5000 fixed steps, a sample every 50th step."""
+    W, H = 64, 48
+    verts, faces, cam = _frame_inputs(W, H)
+    pos = oracle.sample_positions(cam, SETTINGS, W, H)
+    ref = np.asarray(oracle.sample_rays(cam, SETTINGS, int(fn), W, H, pos), np.float32).reshape(800, 8)
+    lib = emu.build(fn.to_code(), 0, capi.MATH_STRICT)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H, sample_pos=pos)["ray_samples"]
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("fn", MIRAGES)
 def test_quiet_zone_default_step_frames_meet_the_north_star(product_lib, oracle, fn):
     """Adaptive off, h = 0.1 (51 steps): quiet-zone straight steps against the oracle, all four predefined mirage bodies."""
