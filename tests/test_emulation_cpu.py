@@ -96,6 +96,24 @@ def test_emulated_sample_ray_kernel_is_bit_exact_with_the_oracle(product_lib, or
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
+
+
+@pytest.mark.parametrize("fn", PREDEFINED)
+def test_emulated_fast_build_meets_the_north_star(product_lib, oracle, fn):
+    """The production build (fast math; hand-fused whole-step restatement for the four mirage bodies, generic translation
+    for the rest) against the oracle, adaptive off: the algebra of the restatements is checked here with libm's special
+    functions, the MUFU approximations on top of it by tests/test_gpu_parity.py on the device."""
+    W, H = 64, 48
+    verts, faces, cam = _frame_inputs(W, H)
+    ref, excl = _oracle_frame(oracle, verts, faces, cam, fn, W, H, 0.1, False)
+    lib = emu.build(fn.to_code(), capi.RENDER_ADAPTIVE_OFF, capi.MATH_FAST)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    m = parity.compare_frames(got, ref, exclude=excl)
+    assert parity.passes_north_star(m), m
+    assert int(got["counters"][0]) == W * H * 51
+
+
 @pytest.mark.parametrize("fn", MIRAGES)
 def test_quiet_zone_default_step_frames_meet_the_north_star(product_lib, oracle, fn):
     """Adaptive off, h = 0.1 (51 steps): quiet-zone straight steps against the oracle, all four predefined mirage bodies."""
