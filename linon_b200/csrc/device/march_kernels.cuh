@@ -752,8 +752,9 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 // 1.000001: the run takes n * cost_up from the budget in one rounding instead of n roundings of cost
                 const float cost_up = __fmul_ru(sd.cost_linf(q_inf, kh), 1.000001f);
                 // steps whose budget stays positive (0.9999 covers the division and keeps the budget after the run > 0)
-                const int nb = (int)fminf(__fdividef(sd.budget * 0.9999f, cost_up), 268435456.0f);
-                int n_clear = max(nb, 0);  // steps this lane can take without a culling check
+                // (fmaxf first: a NaN - 0 / 0 for a ray that does not move - and a negative budget give 0)
+                const int nb = (int)fminf(fmaxf(__fdividef(sd.budget * 0.9999f, cost_up), 0.0f), 268435456.0f);
+                int n_clear = nb;  // steps this lane can take without a culling check
 #if LINON_CULL && !LINON_BVH
                 // the budget is what limits the run (a wall nearby, or a run that just ended): ask how far the straight ray
                 // really is from the geometry along its direction

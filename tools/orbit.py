@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--save-every", type=int, default=0)
     ap.add_argument("--fn", type=int, default=3)
+    ap.add_argument("--quiet-zone", type=int, default=0, choices=[0, 1], help="LINON_OPT_QUIET_ZONE (opt-in)")
     args = ap.parse_args()
 
     import numpy as np
@@ -65,6 +66,8 @@ def main():
     settings = make_settings(overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0)
     mv.update_settings(settings)
     mv.set_shard(rank, world, args.rows_per_block)
+    if args.quiet_zone:
+        mv.set_option(capi.OPT_QUIET_ZONE, 1)
     stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank))
     ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")
     rc = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_RAYCAST_RGBA8), (H, W, 4), "|u1"), device="cuda")
