@@ -321,6 +321,20 @@ def run_ours(args):
     mv.set_shard(rank, world, ROWS_PER_BLOCK)
     if args.quiet_zone:
         mv.set_option(capi.OPT_QUIET_ZONE, 1)
+    peer_stores = bool(args.peer_stores) and world > 1
+    if peer_stores:
+        # no gather: every rank's march stores its rows straight into rank 0's frame buffers over NVLink (CUDA IPC mappings of
+        # rank 0's buffers, include/linon_b200.h: linon_ipc_export / linon_ipc_open / linon_redirect_output)
+        bufs = (capi.BUF_RAYCAST_RGBA8, capi.BUF_ENDPOINT_F32X4, capi.BUF_HIT_ID_I32)
+        handles = torch.zeros(64 * len(bufs), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = b"".join(mv.ipc_export(b) for b in bufs)
+            handles.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        dist.broadcast(handles, 0)
+        if rank != 0:
+            raw = handles.cpu().numpy().tobytes()
+            for k, b in enumerate(bufs):
+                mv.redirect_output(b, mv.ipc_open(raw[64 * k:64 * k + 64]))
     stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank))
 
     ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")
@@ -345,8 +359,11 @@ def run_ours(args):
             mv.sync()
             last["timings"], last["counters"] = mv.timings(), mv.counters()  # of the march render (reset per render)
             last["quiet"] = int(mv.debug_profile()[15]) if args.quiet_zone else 0
-            with torch.cuda.stream(stream):
-                sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, ROWS_PER_BLOCK)
+            if peer_stores:
+                dist.barrier()  # every rank's march has completed (mv.sync above): rank 0's buffers hold the whole frame
+            else:
+                with torch.cuda.stream(stream):
+                    sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, ROWS_PER_BLOCK)
             if rank == 0:
                 mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)  # overlay on the assembled image
                 n += 1
@@ -465,7 +482,7 @@ def run_ours(args):
                     rk4_steps_per_step=acc + rej, field_function="MirageSphericalSigmoid", h_initial=0.001,
                     math_mode="fast (--use_fast_math; whole-step restatement of the predefined mirage body: RK4 stage 1 = identity, scaled coordinates, one reciprocal per stage)",
                     kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass culling checks)", plane_culling=True,
-                    parallelism=f"row-blocks x{world}" if world > 1 else "single GPU",
+                    parallelism=(f"row-blocks x{world}" + (", peer stores into rank 0 over NVLink (no gather)" if peer_stores else ", grouped NCCL send/recv to rank 0")) if world > 1 else "single GPU",
                     l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
         clocks=clocks,
         e2e=dict(value=rays / (e2e_ms / steps * 1e-3) / 1e6, unit="Mrays/s", ms_per_step=e2e_ms / steps,
@@ -527,6 +544,9 @@ def main():
                          "0 (default until the option is validated on the GPU): the default path is measured and the option is "
                          "only probed at the end of the N=1 run (quiet_zone_probe)")
     ap.add_argument("--no-quiet-zone-probe", action="store_true")
+    ap.add_argument("--peer-stores", type=int, default=0, choices=[0, 1],
+                    help="N > 1: 1 = every rank's march stores straight into rank 0's frame buffers (CUDA IPC + NVLink) instead of "
+                         "the NCCL gather after the march (opt-in: not yet run on a multi-GPU box)")
     ap.add_argument("--probe-quiet-zone", action="store_true", help="internal: the child process of the N=1 run")
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()

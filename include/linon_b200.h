@@ -198,6 +198,20 @@ void* linon_stream(linon_view* v);
 /* Row-block sharding for multi-GPU frames: the rows are cut into blocks of rows_per_block; block b belongs to
  * rank b % world.  The march then only renders this rank's rows (buffers stay full-frame; other rows untouched). */
 int linon_set_shard(linon_view* v, uint32_t rank, uint32_t world, uint32_t rows_per_block);
+/* Peer stores - a sharded frame without a gather.  linon_redirect_output makes the march of this view store `buffer`
+ * (LINON_BUF_RAYCAST_RGBA8, LINON_BUF_ENDPOINT_F32X4 or LINON_BUF_HIT_ID_I32) through device_ptr instead of into the
+ * view's own buffer: the frame buffer of the ROOT shard's view, of the same frame size.  A shard writes only its own rows
+ * (linon_set_shard), so the root's buffers hold the assembled frame as soon as every shard's march has completed - the
+ * 24 bytes per ray travel over NVLink while the march runs, and the overlay then runs on the root as before.
+ * NULL restores the view's own buffer; linon_resize drops every redirection.
+ *   same process:     device_ptr = linon_device_ptr(root_view, buffer), with peer access enabled between the devices;
+ *   one process/GPU:  the root exports a 64-byte CUDA IPC handle (linon_ipc_export), ships it to the other ranks (any
+ *                     host channel, e.g. a torch.distributed broadcast), and they map it with linon_ipc_open (the
+ *                     mapping lives until linon_destroy).
+ * The caller orders the root's overlay after the other shards' marches (stream sync on each rank + a barrier). */
+int linon_redirect_output(linon_view* v, int buffer, void* device_ptr);
+int linon_ipc_export(linon_view* v, int buffer, void* handle64);
+int linon_ipc_open(linon_view* v, const void* handle64, void** device_ptr);
 
 int linon_set_option(linon_view* v, int option, int value);
 int linon_get_counters(linon_view* v, linon_counters* out);

@@ -77,6 +77,9 @@ PROTOTYPES = [
     ("linon_device_ptr", _P, [_P, _I]),
     ("linon_stream", _P, [_P]),
     ("linon_set_shard", _I, [_P, _U, _U, _U]),
+    ("linon_redirect_output", _I, [_P, _I, _P]),
+    ("linon_ipc_export", _I, [_P, _I, _P]),
+    ("linon_ipc_open", _I, [_P, _P, C.POINTER(_P)]),
     ("linon_set_option", _I, [_P, _I, _I]),
     ("linon_get_counters", _I, [_P, C.POINTER(Counters)]),
     ("linon_get_timings", _I, [_P, C.POINTER(Timings)]),

@@ -108,6 +108,14 @@
 #undef LINON_QUIET_ZONE
 #define LINON_QUIET_ZONE 0  // the body does not define LinonField<float>::quiet_steps (generic translations never do)
 #endif
+#ifndef LINON_WARP_STATS
+#define LINON_WARP_STATS 0  // 1 (developer aid; tests/emu sets it): warp-level event counts of the fixed-step tile loops in
+#endif                      // counters[5..11]: plans, runs, full steps, quiet single steps, check events, directional bounds, straight warp-steps
+#if LINON_WARP_STATS
+#define LINON_WARP_EVENT(k, n) do { if ((threadIdx.x & 31) == 0) atomicAdd(&P.counters[k], (unsigned long long)(n)); } while (0)
+#else
+#define LINON_WARP_EVENT(k, n) do { } while (0)
+#endif
 #ifndef LINON_STRICT_MATH
 #define LINON_STRICT_MATH 0  // 1: the bit-comparable build (--fmad=false ...): no explicit FMA either
 #endif
@@ -747,6 +755,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             // ONE quiet step through the regular check logic below (velocity = direction), which refreshes the budget.
             bool quiet = false;  // warp-uniform: this step's velocity is the direction
             if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
+                LINON_WARP_EVENT(5, 1);
                 const int nq = LinonField<float>::quiet_steps(r.p, r.dir, h);
                 const float q_inf = fmaxf(fmaxf(fabsf(r.dir.x), fabsf(r.dir.y)), fabsf(r.dir.z));
                 // 1.000001: the run takes n * cost_up from the budget in one rounding instead of n roundings of cost
@@ -759,6 +768,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 // the budget is what limits the run (a wall nearby, or a run that just ended): ask how far the straight ray
                 // really is from the geometry along its direction
                 if (__any_sync(0xffffffffu, n_clear < nq && !has_color)) {
+                    LINON_WARP_EVENT(10, 1);
                     const vec3f d = r.dir * h;
                     const float travel_max = (float)(n_steps - i) * l1_norm(d);
                     if (!has_color) n_clear = max(n_clear, straight_clear_steps(s_tri, r.p, d, travel_max, P.plane_w_max));
@@ -773,6 +783,8 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     // within the budget: take the run from it (+inf stays +inf); beyond it (the directional bound allowed
                     // more): the budget is spent, the next regular step runs a check and refreshes it
                     sd.budget = (n <= nb) ? __fmaf_rd(-(float)n, cost_up, sd.budget) : 0.0f;
+                    LINON_WARP_EVENT(6, 1);
+                    LINON_WARP_EVENT(11, n);
                     cnt.quiet += (unsigned int)n;
                     i += n - 1;  // the loop header adds the last one
                     continue;
@@ -780,6 +792,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 quiet = __all_sync(0xffffffffu, nq > 0);
             }
             if (quiet) ++cnt.quiet;
+            LINON_WARP_EVENT(quiet ? 8 : 7, 1);
             const vec3f v = quiet ? r.dir : rk4_velocity(r, h, st, cam);
 #else
             const vec3f v = rk4_velocity(r, h, st, cam);
@@ -798,6 +811,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             if (__any_sync(0xffffffffu, !(left > 0.0f)))
 #endif
             {
+                LINON_WARP_EVENT(9, 1);
                 if (!has_color) {
                     const float p_l1 = l1_norm(r.p);
                     ++cnt.checks;
@@ -842,8 +856,11 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
 #if LINON_QUIET_ZONE
             // coasting through the quiet zone: the same plan without a budget
             if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
+                LINON_WARP_EVENT(5, 1);
                 const int n = min(__reduce_min_sync(0xffffffffu, LinonField<float>::quiet_steps(r.p, r.dir, h)), n_steps - i);
                 if (n > 0) {
+                    LINON_WARP_EVENT(6, 1);
+                    LINON_WARP_EVENT(11, n);
 #pragma unroll 4
                     for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
                     r.t = __fmaf_rn((float)n, h, r.t);
@@ -853,6 +870,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 }
             }
 #endif
+            LINON_WARP_EVENT(7, 1);
             const vec3f v = rk4_velocity(r, h, st, cam);
 #if LINON_FW_ONE
             r.dir = v;

@@ -360,6 +360,13 @@ struct linon_view {
     uint64_t last_rays = 0;
     std::string error;
 
+    // peer stores (linon_redirect_output): where the march stores colour / endpoint / hit id instead of this view's own
+    // buffers - the frame buffers of the root shard, same process or mapped from another process (linon_ipc_open)
+    uchar4* out_raycast = nullptr;
+    float4* out_endpoint = nullptr;
+    int* out_hit = nullptr;
+    std::vector<void*> ipc_mappings;  // cudaIpcOpenMemHandle results, closed by linon_destroy
+
     int fail(int code, const std::string& msg) {
         error = msg;
         return code;
@@ -547,7 +554,9 @@ void fill_march_params(const linon_view* v, MarchParamsH& P) {
     P.shard_rank = (int)v->shard_rank; P.shard_world = (int)v->shard_world; P.rows_per_block = (int)v->rows_per_block;
     P.tris = v->d_tris;
     P.group_range = v->d_group_range;
-    P.raycast = v->d_raycast; P.endpoint = v->d_endpoint; P.hit_id = v->d_hit;
+    P.raycast = v->out_raycast ? v->out_raycast : v->d_raycast;
+    P.endpoint = v->out_endpoint ? v->out_endpoint : v->d_endpoint;
+    P.hit_id = v->out_hit ? v->out_hit : v->d_hit;
     P.counters = v->d_counters;
     P.work = v->d_work; P.q_pixel = v->d_q_pixel; P.q_state = v->d_q_state;
     P.q_capacity = (unsigned int)v->q_capacity;
@@ -754,6 +763,7 @@ void linon_destroy(linon_view* v) {
     cudaStreamSynchronize(v->stream);
     cudaStreamSynchronize(v->aux);
     for (auto& kv : v->modules) g_drv.ModuleUnload(kv.second.mod);
+    for (void* m : v->ipc_mappings) cudaIpcCloseMemHandle(m);
     free_frame_buffers(v);
     cudaFree(v->d_bvh);
     cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_ray_samples); cudaFree(v->d_pos16); cudaFree(v->d_counters);
@@ -822,6 +832,7 @@ int linon_resize(linon_view* v, uint32_t width, uint32_t height) {
     if (!v || width < 2 || height < 2) return LINON_ERR_INVALID;
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
+    v->out_raycast = nullptr; v->out_endpoint = nullptr; v->out_hit = nullptr;  // a redirection is for one frame size
     return alloc_frame_buffers(v, width, height);
 }
 
@@ -1055,6 +1066,41 @@ void* linon_device_ptr(linon_view* v, int buffer) {
 }
 
 void* linon_stream(linon_view* v) { return v ? (void*)v->stream : nullptr; }
+
+// ---- peer stores: a shard's march writes straight into the root shard's frame buffers (no gather) ------------------
+int linon_redirect_output(linon_view* v, int buffer, void* device_ptr) {
+    if (!v) return LINON_ERR_INVALID;
+    switch (buffer) {
+        case LINON_BUF_RAYCAST_RGBA8: v->out_raycast = (uchar4*)device_ptr; return LINON_OK;
+        case LINON_BUF_ENDPOINT_F32X4: v->out_endpoint = (float4*)device_ptr; return LINON_OK;
+        case LINON_BUF_HIT_ID_I32: v->out_hit = (int*)device_ptr; return LINON_OK;
+    }
+    return v->fail(LINON_ERR_INVALID, "linon_redirect_output: only the march outputs (raycast, endpoint, hit id) can be redirected");
+}
+
+int linon_ipc_export(linon_view* v, int buffer, void* handle64) {
+    if (!v || !handle64) return LINON_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void* p = linon_device_ptr(v, buffer);
+    if (!p) return v->fail(LINON_ERR_INVALID, "linon_ipc_export: unknown buffer");
+    CK(v, cudaSetDevice(v->device));
+    cudaIpcMemHandle_t h;
+    CK(v, cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    return LINON_OK;
+}
+
+int linon_ipc_open(linon_view* v, const void* handle64, void** device_ptr) {
+    if (!v || !handle64 || !device_ptr) return LINON_ERR_INVALID;
+    CK(v, cudaSetDevice(v->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CK(v, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    v->ipc_mappings.push_back(p);
+    *device_ptr = p;
+    return LINON_OK;
+}
 
 int linon_read(linon_view* v, int buffer, void* dst, size_t dst_bytes) {
     if (!v || !dst) return LINON_ERR_INVALID;

@@ -273,6 +273,20 @@ class MainView:
     def set_shard(self, rank: int, world: int, rows_per_block: int = 32):
         self._check_view(capi.lib().linon_set_shard(self._view, rank, world, rows_per_block))
 
+    # ---- peer stores: a shard's march writes straight into the root shard's frame buffers (include/linon_b200.h) --------
+    def redirect_output(self, buffer: int, device_ptr: int | None):
+        self._check_view(capi.lib().linon_redirect_output(self._view, buffer, C.c_void_p(device_ptr or 0)))
+
+    def ipc_export(self, buffer: int) -> bytes:
+        h = C.create_string_buffer(64)
+        self._check_view(capi.lib().linon_ipc_export(self._view, buffer, h))
+        return h.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p(0)
+        self._check_view(capi.lib().linon_ipc_open(self._view, C.c_char_p(handle), C.byref(p)))
+        return int(p.value)
+
     def counters(self) -> Counters:
         c = Counters()
         self._check_view(capi.lib().linon_get_counters(self._view, C.byref(c)))

@@ -101,6 +101,9 @@ extern "C" {
     pub fn linon_device_ptr(v: *mut linon_view, buffer: c_int) -> *mut c_void;
     pub fn linon_stream(v: *mut linon_view) -> *mut c_void;
     pub fn linon_set_shard(v: *mut linon_view, rank: u32, world: u32, rows_per_block: u32) -> c_int;
+    pub fn linon_redirect_output(v: *mut linon_view, buffer: c_int, device_ptr: *mut c_void) -> c_int;
+    pub fn linon_ipc_export(v: *mut linon_view, buffer: c_int, handle64: *mut c_void) -> c_int;
+    pub fn linon_ipc_open(v: *mut linon_view, handle64: *const c_void, device_ptr: *mut *mut c_void) -> c_int;
     pub fn linon_set_option(v: *mut linon_view, option: c_int, value: c_int) -> c_int;
     pub fn linon_get_counters(v: *mut linon_view, out: *mut linon_counters) -> c_int;
     pub fn linon_get_timings(v: *mut linon_view, out: *mut linon_timings) -> c_int;

@@ -64,7 +64,7 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
         defines = [o for o in header.split()[2:] if o.startswith("-D")]
         with open(src, "wb") as f:
             f.write(text)
-        cmd = [_cxx(), opt, "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w",
+        cmd = [_cxx(), opt, "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w", "-DLINON_WARP_STATS=1",
                f'-DLINON_EMU_SOURCE="{src}"', "-I", _HERE, "-I", os.path.join(_ROOT, "linon_b200", "csrc", "host"),
                *defines, os.path.join(_HERE, "emu_driver.cpp"), "-o", so + ".tmp"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -100,3 +100,36 @@ def test_quiet_zone_full_size_c3(product_lib, scene):
         assert q > 0.9 * W * H * 5001
         assert m["hit_group_agree"] >= 0.999 and m["endpoint_within_1e3"] >= 0.999 and m["colour_within_1"] >= 0.999, m
         assert ms[1] < ms[0]
+
+
+@pytest.mark.parametrize("flags", [capi.RENDER_ADAPTIVE_OFF, 0])
+def test_peer_stores_assemble_the_frame_in_the_root_views_buffers(product_lib, scene, flags):
+    """linon_redirect_output: the shards of a frame store their rows straight into the root shard's buffers (what the ranks
+    of a multi-GPU job do through CUDA IPC mappings, bench.py --peer-stores): no gather, and the root's buffers equal the
+    one-view frame bit for bit.  Same process and device here; the IPC calls themselves need two processes."""
+    verts, faces, center = scene
+    W, H, world = 96, 80, 3
+    fn = PredefinedFunction.MirageSphericalSigmoid
+    bufs = (capi.BUF_RAYCAST_RGBA8, capi.BUF_ENDPOINT_F32X4, capi.BUF_HIT_ID_I32)
+    with MainView(verts, faces, center, W, H) as whole:
+        ref = render(whole, fn, flags=flags | capi.RENDER_NO_OVERLAY | capi.RENDER_NO_SAMPLE_RAYS)
+    views = [MainView(verts, faces, center, W, H) for _ in range(world)]
+    try:
+        for rank, mv in enumerate(views):
+            mv.set_shard(rank, world, 16)
+            if rank:
+                for b in bufs:
+                    mv.redirect_output(b, views[0].device_ptr(b))
+        for mv in views:
+            render(mv, fn, flags=flags | capi.RENDER_NO_OVERLAY | capi.RENDER_NO_SAMPLE_RAYS)
+        root = views[0]
+        got = dict(hit_id=root.hit_ids(), rgba8=root.ray_casting_texture(), endpoint=root.mapping_texture())
+        for k in ref:
+            assert np.array_equal(got[k].view(np.uint8), ref[k].view(np.uint8)), k
+        views[1].redirect_output(capi.BUF_HIT_ID_I32, None)  # restored: the shard writes its own buffer again
+        render(views[1], fn, flags=flags | capi.RENDER_NO_OVERLAY | capi.RENDER_NO_SAMPLE_RAYS)
+        own = views[1].hit_ids()
+        assert np.array_equal(own[16:32], ref["hit_id"][16:32])
+    finally:
+        for mv in views:
+            mv.close()
