@@ -325,16 +325,7 @@ def run_ours(args):
     if peer_stores:
         # no gather: every rank's march stores its rows straight into rank 0's frame buffers over NVLink (CUDA IPC mappings of
         # rank 0's buffers, include/linon_b200.h: linon_ipc_export / linon_ipc_open / linon_redirect_output)
-        bufs = (capi.BUF_RAYCAST_RGBA8, capi.BUF_ENDPOINT_F32X4, capi.BUF_HIT_ID_I32)
-        handles = torch.zeros(64 * len(bufs), dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            raw = b"".join(mv.ipc_export(b) for b in bufs)
-            handles.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
-        dist.broadcast(handles, 0)
-        if rank != 0:
-            raw = handles.cpu().numpy().tobytes()
-            for k, b in enumerate(bufs):
-                mv.redirect_output(b, mv.ipc_open(raw[64 * k:64 * k + 64]))
+        sharding.setup_peer_stores(mv, rank, world)
     stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank))
 
     ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")

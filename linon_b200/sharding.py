@@ -62,3 +62,31 @@ def gather_rows_to_root(buffers, height: int, rank: int, world: int, rows_per_bl
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     return moved
+
+
+def setup_peer_stores(mv, rank: int, world: int, root: int = 0):
+    """Multi-GPU frame without a gather (include/linon_b200.h: linon_ipc_export / linon_ipc_open / linon_redirect_output).
+
+    The root rank exports CUDA IPC handles of its colour / endpoint / hit-id frame buffers, the handles travel through one
+    torch.distributed broadcast, and every other rank redirects its march stores into the root's buffers: each shard writes
+    its own row blocks over NVLink while it marches, so after `mv.sync()` on every rank and a barrier the root holds the
+    assembled frame and runs the overlay.  One process per GPU, `torch.distributed` initialised with the nccl backend."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _capi as capi
+
+    if world == 1:
+        return
+    bufs = (capi.BUF_RAYCAST_RGBA8, capi.BUF_ENDPOINT_F32X4, capi.BUF_HIT_ID_I32)
+    # the handles ride on the job's backend: a device tensor under nccl, a host tensor under gloo (CPU tests)
+    device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    handles = torch.zeros(64 * len(bufs), dtype=torch.uint8, device=device)
+    if rank == root:
+        raw = b"".join(mv.ipc_export(b) for b in bufs)
+        handles.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(handles, root)
+    if rank != root:
+        raw = handles.cpu().numpy().tobytes()
+        for k, b in enumerate(bufs):
+            mv.redirect_output(b, mv.ipc_open(raw[64 * k:64 * k + 64]))

@@ -70,3 +70,45 @@ def test_gather_rows_to_root_gloo(tmp_path, world, H, W, rpb):
     out = tmp_path / "ok.txt"
     mp.spawn(_worker, args=(world, _free_port(), H, W, rpb, str(out)), nprocs=world, join=True)
     assert out.read_text() == "ok"
+
+
+class _FakeView:
+    """Stands in for MainView: records what setup_peer_stores asks of the C ABI."""
+
+    def __init__(self, rank):
+        self.rank = rank
+        self.redirected = {}
+
+    def ipc_export(self, buffer):
+        return bytes([(buffer * 7 + k) % 256 for k in range(64)])
+
+    def ipc_open(self, handle):
+        assert len(handle) == 64
+        return 0x1000 + handle[0]
+
+    def redirect_output(self, buffer, ptr):
+        self.redirected[buffer] = ptr
+
+
+def _peer_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from linon_b200 import _capi as capi
+        mv = _FakeView(rank)
+        sharding.setup_peer_stores(mv, rank, world)
+        bufs = (capi.BUF_RAYCAST_RGBA8, capi.BUF_ENDPOINT_F32X4, capi.BUF_HIT_ID_I32)
+        if rank == 0:
+            assert mv.redirected == {}  # the root keeps its own buffers
+        else:  # every other rank maps the ROOT's handle of each buffer and redirects exactly the three march outputs
+            assert mv.redirected == {b: 0x1000 + (b * 7) % 256 for b in bufs}
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_store_handles_reach_every_rank_gloo(tmp_path):
+    world = 3
+    mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == [f"ok{r}" for r in range(world)]

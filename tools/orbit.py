@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--save-every", type=int, default=0)
     ap.add_argument("--fn", type=int, default=3)
     ap.add_argument("--quiet-zone", type=int, default=0, choices=[0, 1], help="LINON_OPT_QUIET_ZONE (opt-in)")
+    ap.add_argument("--peer-stores", type=int, default=0, choices=[0, 1],
+                    help="1: the ranks store their rows straight into rank 0's buffers (CUDA IPC + NVLink), no gather (opt-in)")
     args = ap.parse_args()
 
     import numpy as np
@@ -68,6 +70,8 @@ def main():
     mv.set_shard(rank, world, args.rows_per_block)
     if args.quiet_zone:
         mv.set_option(capi.OPT_QUIET_ZONE, 1)
+    if args.peer_stores and world > 1:
+        sharding.setup_peer_stores(mv, rank, world)
     stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank))
     ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")
     rc = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_RAYCAST_RGBA8), (H, W, 4), "|u1"), device="cuda")
@@ -90,8 +94,12 @@ def main():
         mv.render_flags(march_flags)
         gathered = 0
         if world > 1:
-            with torch.cuda.stream(stream):
-                gathered = sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, args.rows_per_block)
+            if args.peer_stores:
+                mv.sync()
+                dist.barrier()  # every rank's rows are in rank 0's buffers
+            else:
+                with torch.cuda.stream(stream):
+                    gathered = sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, args.rows_per_block)
             if rank == 0:
                 mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
         return cam, gathered
