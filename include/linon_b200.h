@@ -109,6 +109,9 @@ enum {
                                     outside the body's zone of influence, where the reference's own fp32 evaluation returns
                                     eta = 1 exactly and refraction(t, t, v, n) = v up to its rounding noise (csrc/device/
                                     mirage_fused.cuh: quiet_steps).  Every Runge-Kutta step is still executed and counted.
+                                    2: adaptive frames as well - per attempt, velocity = direction when every stage point lies
+                                    outside the zone (diff is exactly 0 there, so the reference's noise-driven rejections
+                                    outside the zone, SURVEY F20, have no counterpart).
                                     Default 0 until measured on the GPU; validated on the host emulation of the device code
                                     (tests/emu) against the oracle. */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the

@@ -657,12 +657,19 @@ __device__ __forceinline__ void flush_counters(const MarchParams& P, StepCounter
 
 // One loop iteration of nonlinear_ray_color up to (not including) the intersection, src/main_view.wgsl:246-258.
 // Returns false when the adaptive test rejects the attempt (h <- 0.001, state unchanged).
+// quiet (LINON_QUIET_ZONE): every stage point of this attempt lies outside the body's zone of influence, where the field is
+// the identity: the velocity is the direction and the field is not evaluated (a real branch: a warp whose lanes are all
+// quiet skips the evaluation, a mixed warp pays for it once either way).
 __device__ __forceinline__ bool rk4_attempt(Ray& r, const WgslSettings& st, const WgslCamera& cam, vec3f& v, float& diff,
-                                            vec3f& step_dir) {
+                                            vec3f& step_dir, bool quiet = false) {
 #if LINON_ADAPTIVE
     const float h = r.h;
 #else
     const float h = LINON_H_INITIAL;
+#endif
+#if LINON_QUIET_ZONE
+    if (quiet) v = r.dir;
+    else
 #endif
     v = rk4_velocity(r, h, st, cam);
 #if LINON_ADAPTIVE
@@ -909,7 +916,17 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         for (; r.t <= 5.0f;) {
             vec3f v, step_dir;
             float diff;
+#if LINON_QUIET_ZONE
+            // Adaptive frames: the same zone argument per attempt (the step size is the lane's own).  Outside the zone v ==
+            // last_v exactly, so diff is 0 there: the reference's rejections and restorations outside the zone are driven by
+            // the rounding noise of its evaluation and have no counterpart; entering the zone raises diff from 0,
+            // which rejects the attempt and drops h to 0.001 like the reference does a little further in.
+            const bool quiet = LinonField<float>::quiet_steps(r.p, r.dir, r.h) > 0;
+            if (quiet) ++cnt.quiet;
+            if (!rk4_attempt(r, st, cam, v, diff, step_dir, quiet)) {
+#else
             if (!rk4_attempt(r, st, cam, v, diff, step_dir)) {
+#endif
                 ++cnt.rejected;
                 continue;
             }

@@ -508,8 +508,10 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.fw_one = (v->opt_math != 0 && v->settings.field_weight == 1.0f) ? 1 : 0;
     var.pairs = (v->opt_kernel == 2 && !v->use_bvh && !v->pair_unfit.count(v->body)) ? 1 : 0;
     var.pair_min_blocks = var.pairs ? v->opt_pair_min_blocks : 0;
-    // only the fixed-step loops of the tile kernel have the quiet-zone path, and only fused mirage bodies define the zone
-    var.quiet = (v->opt_quiet && !var.adaptive && v->opt_math == 2 && v->opt_specialize) ? 1 : 0;
+    // only the tile kernel has the quiet-zone path (runs of straight steps in its fixed-step loops, a per-attempt test in
+    // the adaptive loop), and only fused mirage bodies define the zone
+    // (1: fixed-step variants only, 2: adaptive variants as well)
+    var.quiet = (v->opt_quiet > (var.adaptive ? 1 : 0) && v->opt_math == 2 && v->opt_specialize) ? 1 : 0;
     return var;
 }
 
@@ -1137,7 +1139,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_MAX_REGS: if (value < 0 || value > 255) break; v->opt_max_regs = value; return LINON_OK;
         case LINON_OPT_PROFILE: if (value < 0 || value > 1) break; v->opt_profile = value; return LINON_OK;
         case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
-        case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 1) break; v->opt_quiet = value; return LINON_OK;
+        case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 2) break; v->opt_quiet = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));
 }

@@ -177,6 +177,27 @@ def test_quiet_zone_culling_never_changes_a_result(product_lib, fn, flags, size,
     assert int(a["counters"][4]) < 0.25 * int(b["counters"][4])           # ... and most checks are gone
 
 
+@pytest.mark.parametrize("fn", MIRAGES)
+def test_quiet_zone_adaptive_frames_meet_the_north_star_on_hit_and_colour(product_lib, oracle, fn):
+    """Option level 2: adaptive frames (C1 / C2 as the application renders them).  Graded like the GPU test of the adaptive
+    path: hit id and colour, pixels the oracle itself cannot decide (fp32 vs fp64 vs a one-ulp change of field_weight)
+    excluded and counted - adaptive step sequences are rounding-noise driven."""
+    W, H = 96, 72
+    verts, faces, cam = _frame_inputs(W, H)
+    ref, excl = _oracle_frame(oracle, verts, faces, cam, fn, W, H, 0.1, True)
+    alt64 = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=0.1, adaptive=True, use_fp64=True)
+    st_ulp = dict(SETTINGS, field_weight=float(np.nextafter(np.float32(1.0), np.float32(0))))
+    alt_ulp = oracle.march(verts, faces, cam, st_ulp, int(fn), W, H, h_initial=0.1, adaptive=True)
+    excl = excl | parity.disagreement_mask(alt64, ref) | parity.disagreement_mask(alt_ulp, ref)
+    lib = emu.build(fn.to_code(), 0, capi.MATH_FAST, quiet_zone=2)
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    m = parity.compare_frames(got, ref, exclude=excl)
+    assert m["hit_group_agree"] >= 0.999 and m["colour_within_1"] >= 0.99, m
+    c = got["counters"]
+    assert int(c[15]) > 0.3 * (int(c[0]) + int(c[2])), c  # a good part of the attempts never evaluate the field
+    assert int(c[0]) >= W * H * 51
+
+
 def test_quiet_zone_is_closer_to_the_fp64_reference_run(product_lib, oracle):
     """Outside the zone the reference's fp32 result is `v + rounding noise`; a straight step has none.  Against the oracle's
     fp64 evaluation of the same WGSL the quiet-zone frame must not be farther away than the plain fast build."""

@@ -79,6 +79,17 @@ def test_quiet_zone_enhance_frame_meets_the_north_star(product_lib, oracle, scen
         assert m["hit_group_agree"] >= 0.999 and m["endpoint_within_1e3"] >= 0.999 and m["colour_within_1"] >= 0.999, m
 
 
+@pytest.mark.parametrize("fn", MIRAGES)
+def test_quiet_zone_adaptive_frames_meet_the_north_star_on_hit_and_colour(view, oracle, scene, fn):
+    """Option level 2 (adaptive frames as well), graded like test_adaptive_frames_meet_the_north_star_on_hit_and_colour."""
+    view.set_option(capi.OPT_QUIET_ZONE, 2)
+    ref, excl = oracle_frame(oracle, scene, view, fn, adaptive=True)
+    got = render(view, fn, flags=0)
+    m = parity.compare_frames(got, ref, exclude=excl)
+    assert m["hit_group_agree"] >= 0.999 and m["colour_within_1"] >= 0.99, m
+    assert quiet_steps(view) > 0
+
+
 def test_quiet_zone_full_size_c3(product_lib, scene):
     """The C3 frame itself: step counts, share of straight steps, agreement with the default path, and the time of both."""
     verts, faces, center = scene
