@@ -114,6 +114,10 @@ enum {
                                     outside the zone, SURVEY F20, have no counterpart).
                                     Default 0 until measured on the GPU; validated on the host emulation of the device code
                                     (tests/emu) against the oracle. */
+    LINON_OPT_QUIET_RADIUS = 13, /* radius of the quiet zone of the SIGMOID mirage profiles in permille of their max_dist; 0 (default)
+                                    = 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6).  1250 ... 4000: below
+                                    1886 the reference's eta is 1 +- its rounding noise and the real-number deflection summed over
+                                    the excluded shell is <= 1.85e-4 exp(6 - 12 r): 1e-9 rad at 1500 (mirage_fused.cuh) */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.

@@ -281,9 +281,17 @@ template <class S> struct LinonField {
     // formulation - the same situation as LINON_STAGE1_IDENTITY.  A step whose four stage points are all outside the zone
     // therefore has k1 = k2 = k3 = k4 = dir, v = dir: a straight step.  `radius` carries a margin over those thresholds
     // (0.1 % for the linear profiles, whose value is continuous across the boundary; 1.8 % for the sigmoids).
+    // The sigmoid radius can be lowered (LINON_OPT_QUIET_RADIUS, in permille of max_dist, >= 1250): between 1.25 and 1.8866
+    // max_dist the reference's eta is 1 +- its own rounding noise, the real-number signal being far below fp32 resolution -
+    // per step |eta - 1| ~ 9e-6 E (h / 0.001) with E = exp(6 - 12 dist / max_dist) <= 1.2e-4, and the deflection summed over the
+    // whole shell is (n(t_src) - n(t_env)) E(radius) <= 1.85e-4 E: 2e-8 rad at 1.25, 1e-9 rad (0.02 ulp of a direction
+    // component) at 1.5.  The default stays at the radius where the reference's own arithmetic saturates.
+#ifndef LINON_QUIET_RADIUS_SIGMOID
+#define LINON_QUIET_RADIUS_SIGMOID 1.92f
+#endif
     struct Quiet {
 #if LINON_MIRAGE_KIND >= 3
-        static constexpr float radius = 1.92f * Fused::max_dist;
+        static constexpr float radius = LINON_QUIET_RADIUS_SIGMOID * Fused::max_dist;
 #else
         static constexpr float radius = 1.001f * Fused::max_dist;
 #endif

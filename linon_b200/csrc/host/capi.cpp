@@ -135,6 +135,7 @@ struct Variant {
     int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
     int pair_min_blocks;  // resident CTAs / SM requested for it (0 = kernel default)
     int quiet;            // 1: fixed-step loops take straight steps where a fused mirage body is the identity (LINON_QUIET_ZONE)
+    int quiet_radius;     // sigmoid profiles: zone radius in permille of max_dist (0 = the default of mirage_fused.cuh)
 };
 
 struct Module {
@@ -244,6 +245,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      "-DLINON_BVH=" + std::to_string(var.bvh),
                                      "-DLINON_QUIET_ZONE=" + std::to_string(var.quiet),
+                                     "-DLINON_QUIET_RADIUS_SIGMOID=" + float_literal(var.quiet_radius > 0 ? 0.001f * (float)var.quiet_radius : 1.92f),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
                                      "-DLINON_PACKED_OPS=" + std::to_string((var.math == 0 || getenv("LINON_DEV_UNPACKED")) ? 0 : 1),
                                      "-DLINON_STRICT_MATH=" + std::to_string(var.math == 0 ? 1 : 0)};
@@ -304,8 +306,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
 }
 
 std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
-    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
-               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh, v.quiet) + body;
+    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh, v.quiet, v.quiet_radius) + body;
 }
 
 }  // namespace
@@ -354,7 +356,7 @@ struct linon_view {
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 0;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 0, opt_quiet_radius = 0;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
@@ -512,6 +514,7 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     // the adaptive loop), and only fused mirage bodies define the zone
     // (1: fixed-step variants only, 2: adaptive variants as well)
     var.quiet = (v->opt_quiet > (var.adaptive ? 1 : 0) && v->opt_math == 2 && v->opt_specialize) ? 1 : 0;
+    var.quiet_radius = var.quiet ? v->opt_quiet_radius : 0;
     return var;
 }
 
@@ -1140,6 +1143,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_PROFILE: if (value < 0 || value > 1) break; v->opt_profile = value; return LINON_OK;
         case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
         case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 2) break; v->opt_quiet = value; return LINON_OK;
+        case LINON_OPT_QUIET_RADIUS: if (value != 0 && (value < 1250 || value > 4000)) break; v->opt_quiet_radius = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));
 }
@@ -1221,6 +1225,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (const char* k = getenv("LINON_CHECK_SPECIALIZE")) tmp.opt_specialize = atoi(k);
     if (const char* k = getenv("LINON_CHECK_BVH")) tmp.use_bvh = atoi(k) != 0;
     if (const char* k = getenv("LINON_CHECK_QUIET_ZONE")) tmp.opt_quiet = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_QUIET_RADIUS")) tmp.opt_quiet_radius = atoi(k);
     if (const char* k = getenv("LINON_CHECK_CULL")) tmp.opt_cull = atoi(k);
     Variant var = make_variant(&tmp, flags);
     if (var.n_faces == 0 && !tmp.use_bvh) default_mesh_counts(var);

@@ -33,12 +33,13 @@ def _cxx():
     return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1", pairs: bool = False):
+def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1", pairs: bool = False,
+          quiet_radius: int = 0):
     """-> ctypes library with emu_march for this variant of the march module (pairs: also linon_march_pairs)."""
     from linon_b200.main_view import compile_check
     os.makedirs(_CACHE, exist_ok=True)
     env = {"LINON_CHECK_BLOCK": "32", "LINON_CHECK_QUIET_ZONE": str(quiet_zone), "LINON_CHECK_CULL": str(cull),
-           "LINON_CHECK_KERNEL": "2" if pairs else "0"}
+           "LINON_CHECK_KERNEL": "2" if pairs else "0", "LINON_CHECK_QUIET_RADIUS": str(quiet_radius)}
     old = {k: os.environ.get(k) for k in list(env) + ["LINON_DUMP_SOURCE"]}
     fd, dump = tempfile.mkstemp(suffix=".cu", dir=_CACHE)
     os.close(fd)

@@ -198,6 +198,25 @@ def test_quiet_zone_adaptive_frames_meet_the_north_star_on_hit_and_colour(produc
     assert int(c[0]) >= W * H * 51
 
 
+def test_quiet_zone_radius_option(product_lib, oracle):
+    """LINON_OPT_QUIET_RADIUS: at 1.5 max_dist the sigmoid's real-number deflection over the excluded shell is 1e-9 rad (below
+    fp32 resolution, far below the reference's own rounding noise there): same agreement with the oracle, half the evaluated
+    steps.  At 1.0 max_dist the signal is real - that radius is refused by the option and would fail here."""
+    W, H = 48, 36
+    fn = PredefinedFunction.MirageSphericalSigmoid
+    verts, faces, cam = _frame_inputs(W, H)
+    ref, excl = _oracle_frame(oracle, verts, faces, cam, fn, W, H, 0.001, False)
+    full = {}
+    for radius in (0, 1500):
+        lib = emu.build(fn.to_code(), capi.RENDER_ENHANCE, capi.MATH_FAST, quiet_zone=1, quiet_radius=radius)
+        got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+        m = parity.compare_frames(got, ref, exclude=excl)
+        assert parity.passes_north_star(m), (radius, m)
+        assert m["endpoint_max_rel"] < 1e-3, (radius, m)
+        full[radius] = int(got["counters"][0]) - int(got["counters"][15])
+    assert full[1500] < 0.7 * full[0], full
+
+
 def test_quiet_zone_is_closer_to_the_fp64_reference_run(product_lib, oracle):
     """Outside the zone the reference's fp32 result is `v + rounding noise`; a straight step has none.  Against the oracle's
     fp64 evaluation of the same WGSL the quiet-zone frame must not be farther away than the plain fast build."""
