@@ -802,6 +802,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             LINON_WARP_EVENT(quiet ? 8 : 7, 1);
             const vec3f v = quiet ? r.dir : rk4_velocity(r, h, st, cam);
 #else
+            LINON_WARP_EVENT(7, 1);
             const vec3f v = rk4_velocity(r, h, st, cam);
 #endif
 #if LINON_FW_ONE
