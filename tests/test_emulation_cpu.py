@@ -198,6 +198,30 @@ def test_quiet_zone_adaptive_frames_meet_the_north_star_on_hit_and_colour(produc
     assert int(c[0]) >= W * H * 51
 
 
+@pytest.mark.parametrize("field_weight,orbit_frame", [(0.5, 7), (0.05, 50)])
+def test_quiet_zone_with_partial_field_weight(product_lib, oracle, field_weight, orbit_frame):
+    """field_weight != 1: the direction blend of src/main_view.wgsl:256 stays in the regular steps, straight runs keep the
+    direction (a blend of a vector with itself).  With a partial weight the mirage frames are ill-conditioned in the
+    reference itself - FMA contraction alone moves 4 % of the endpoints by more than 1e-3 (grazing rays at the
+    total-reflection threshold) - so the option is graded against the same build without it, and both on hit id and colour."""
+    W, H = 64, 48
+    fn = PredefinedFunction.MirageSphericalSigmoid
+    st = dict(SETTINGS, field_weight=field_weight)
+    verts, faces, cam = _frame_inputs(W, H, orbit_frame)
+    ref = oracle.march(verts, faces, cam, st, int(fn), W, H, h_initial=0.1, adaptive=False)
+    _, exponents = oracle.overlay(ref["rgba8"], ref["endpoint"], st)
+    excl = parity.high_lyapunov_mask(exponents)
+    m = {}
+    for quiet in (0, 1):
+        lib = emu.build(fn.to_code(), capi.RENDER_ADAPTIVE_OFF, capi.MATH_FAST, quiet_zone=quiet)
+        got = emu.march(lib, verts, faces, cam, st, W, H)
+        m[quiet] = parity.compare_frames(got, ref, exclude=excl)
+        assert (int(got["counters"][15]) > 0) == bool(quiet)
+    assert m[1]["hit_group_agree"] >= 0.999 and m[1]["colour_within_1"] >= 0.99, m[1]
+    for k in ("hit_group_agree", "colour_within_1", "endpoint_within_1e3"):
+        assert m[1][k] >= m[0][k] - 2e-3, (k, m)
+
+
 def test_quiet_zone_radius_option(product_lib, oracle):
     """LINON_OPT_QUIET_RADIUS: at 1.5 max_dist the sigmoid's real-number deflection over the excluded shell is 1e-9 rad (below
     fp32 resolution, far below the reference's own rounding noise there): same agreement with the oracle, half the evaluated
