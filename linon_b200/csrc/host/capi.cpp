@@ -274,6 +274,11 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
             fwrite(src.data(), 1, src.size(), f);
             fclose(f);
         }
+        if (getenv("LINON_DUMP_SOURCE_ONLY")) {  // the caller only wants the text (tests/emu): skip the NVRTC compile
+            nvrtcDestroyProgram(&prog);
+            log = "LINON_DUMP_SOURCE_ONLY: source written, not compiled";
+            return false;
+        }
     }
     const nvrtcResult rc = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
     size_t log_size = 0;
@@ -1232,7 +1237,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     std::vector<char> cubin;
     std::string log;
     bool ok = compile_cubin(wgsl_body, var, tmp.layer, cubin, log);
-    if (!ok && var.pairs) {  // same fallback as linon_render: the body may not instantiate for two rays per thread
+    if (!ok && var.pairs && !getenv("LINON_DUMP_SOURCE_ONLY")) {  // same fallback as linon_render: the body may not instantiate for two rays per thread
         var.pairs = 0;
         std::string log2;
         ok = compile_cubin(wgsl_body, var, tmp.layer, cubin, log2);

@@ -40,13 +40,18 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
     os.makedirs(_CACHE, exist_ok=True)
     env = {"LINON_CHECK_BLOCK": "32", "LINON_CHECK_QUIET_ZONE": str(quiet_zone), "LINON_CHECK_CULL": str(cull),
            "LINON_CHECK_KERNEL": "2" if pairs else "0", "LINON_CHECK_QUIET_RADIUS": str(quiet_radius)}
+    env["LINON_DUMP_SOURCE_ONLY"] = "1"
     old = {k: os.environ.get(k) for k in list(env) + ["LINON_DUMP_SOURCE"]}
     fd, dump = tempfile.mkstemp(suffix=".cu", dir=_CACHE)
     os.close(fd)
     try:
         os.environ.update(env)
         os.environ["LINON_DUMP_SOURCE"] = dump
-        compile_check(body, flags=flags, math_mode=math_mode)
+        try:
+            compile_check(body, flags=flags, math_mode=math_mode)
+        except Exception as e:  # LINON_DUMP_SOURCE_ONLY: the module text is written, the NVRTC compile is skipped
+            if "LINON_DUMP_SOURCE_ONLY" not in str(e):
+                raise
     finally:
         for k, v in old.items():
             if v is None:
