@@ -586,117 +586,30 @@ int launch(linon_view* v, CUfunction f, unsigned grid, unsigned block, cudaStrea
 
 constexpr uint32_t kSharedMeshFaces = 1024;  // 48 B per face + plane groups fit the static shared memory of a CTA
 
-// ---- bounding-volume hierarchy for meshes beyond the shared-memory stage (OBJ models, src/main.rs:139-157) --------
-// Binary tree, median split of the face centroids along the longest axis, <= 4 faces per leaf, the two children of a
-// node in adjacent slots.  Node = 2 x float4: {lo.xyz, int bits: left child (inner) | first face slot (leaf)},
-// {hi.xyz, int bits: 0 (inner) | face count (leaf)}.  Boxes are inflated by a few ulps of the mesh extent and rounded
-// outwards, so a point of a face as the kernel sees it ({v0, e1, e2} in fp32) is always inside its leaf box.
-struct BvhBuild {
-    struct Box { float lo[3], hi[3]; };
-    std::vector<Box> face_box;
-    std::vector<float> centroid;  // 3 per face
-    std::vector<uint32_t> order;  // face slots in hierarchy order -> original face index
-    std::vector<float> nodes;     // 8 floats per node
-    uint32_t depth = 0;
-
-    static void put_int(float* dst, int32_t x) { memcpy(dst, &x, 4); }
-
-    void build(uint32_t node, uint32_t b, uint32_t e, uint32_t level) {
-        depth = std::max(depth, level);
-        Box box = face_box[order[b]];
-        float clo[3], chi[3];
-        for (int k = 0; k < 3; ++k) clo[k] = chi[k] = centroid[3 * order[b] + k];
-        for (uint32_t i = b + 1; i < e; ++i) {
-            const Box& f = face_box[order[i]];
-            for (int k = 0; k < 3; ++k) {
-                box.lo[k] = std::min(box.lo[k], f.lo[k]);
-                box.hi[k] = std::max(box.hi[k], f.hi[k]);
-                clo[k] = std::min(clo[k], centroid[3 * order[i] + k]);
-                chi[k] = std::max(chi[k], centroid[3 * order[i] + k]);
-            }
-        }
-        float* n = nodes.data() + 8 * (size_t)node;
-        for (int k = 0; k < 3; ++k) { n[k] = box.lo[k]; n[4 + k] = box.hi[k]; }
-        if (e - b <= 4) {
-            put_int(n + 3, (int32_t)b);
-            put_int(n + 7, (int32_t)(e - b));
-            return;
-        }
-        int axis = 0;
-        for (int k = 1; k < 3; ++k)
-            if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
-        const uint32_t mid = b + (e - b) / 2;
-        std::nth_element(order.begin() + b, order.begin() + mid, order.begin() + e, [&](uint32_t x, uint32_t y) {
-            const float cx = centroid[3 * x + axis], cy = centroid[3 * y + axis];
-            return cx < cy || (cx == cy && x < y);
-        });
-        const uint32_t left = (uint32_t)(nodes.size() / 8);
-        nodes.resize(nodes.size() + 16);
-        n = nodes.data() + 8 * (size_t)node;  // resize may have moved the storage
-        put_int(n + 3, (int32_t)left);
-        put_int(n + 7, 0);
-        build(left, b, mid, level + 1);
-        build(left + 1, mid, e, level + 1);
-    }
-};
-
+// the bounding-volume hierarchy for meshes beyond the shared-memory stage is built by mesh_tables.hpp: build_bvh_tables
 int set_mesh_bvh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces) {
-    std::vector<float> tris((size_t)n_faces * 12, 0.0f);
-    BvhBuild bb;
-    bb.face_box.resize(n_faces);
-    bb.centroid.resize((size_t)3 * n_faces);
-    bb.order.resize(n_faces);
-    float extent = 0.0f;
-    for (uint32_t i = 0; i < n_faces; ++i) {
-        const uint32_t ia = faces[3 * i], ib = faces[3 * i + 1], ic = faces[3 * i + 2];
-        if (ia >= n_verts || ib >= n_verts || ic >= n_verts) return v->fail(LINON_ERR_INVALID, fmt("face %u indexes past the vertex array", i));
-        const float* a = verts + 3 * ia; const float* b = verts + 3 * ib; const float* c = verts + 3 * ic;
-        float* t = tris.data() + 12 * (size_t)i;
-        for (int k = 0; k < 3; ++k) {  // {v0, e1, e2}: the two subtractions hit_triangle performs (src/main_view.wgsl:152-153)
-            t[k] = a[k];
-            t[4 + k] = b[k] - a[k];
-            t[8 + k] = c[k] - a[k];
-            // the triangle the kernel tests is (v0, v0 + e1, v0 + e2); bound it together with the input vertices
-            const double p1 = (double)t[k] + (double)t[4 + k], p2 = (double)t[k] + (double)t[8 + k];
-            const double lo = std::min({(double)a[k], (double)b[k], (double)c[k], p1, p2});
-            const double hi = std::max({(double)a[k], (double)b[k], (double)c[k], p1, p2});
-            bb.face_box[i].lo[k] = (float)lo;
-            bb.face_box[i].hi[k] = (float)hi;
-            bb.centroid[3 * (size_t)i + k] = (float)((lo + hi) * 0.5);
-            extent = std::max({extent, std::fabs((float)lo), std::fabs((float)hi)});
-        }
-        bb.order[i] = i;
-    }
-    if (!std::isfinite(extent)) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: non-finite vertex coordinates");
-    const float pad = 4e-7f * (1.0f + extent);  // a few ulps of the largest coordinate
-    for (auto& f : bb.face_box)
-        for (int k = 0; k < 3; ++k) {
-            f.lo[k] = std::nextafter(f.lo[k] - pad, -INFINITY);
-            f.hi[k] = std::nextafter(f.hi[k] + pad, INFINITY);
-        }
-    bb.nodes.assign(8, 0.0f);
-    bb.build(0, 0, n_faces, 1);
-    if (bb.depth > 38) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: hierarchy deeper than the traversal stack");
-    // faces in hierarchy order; .w of the first float4 carries the original face index (the hit id and the tie-break)
-    std::vector<float> sorted((size_t)n_faces * 12);
-    for (uint32_t slot = 0; slot < n_faces; ++slot) {
-        memcpy(sorted.data() + 12 * (size_t)slot, tris.data() + 12 * (size_t)bb.order[slot], 48);
-        BvhBuild::put_int(sorted.data() + 12 * (size_t)slot + 3, (int32_t)bb.order[slot]);
+    linon::BvhTables bt;
+    uint32_t bad = 0;
+    switch (linon::build_bvh_tables(verts, n_verts, faces, n_faces, bt, &bad)) {
+        case linon::BVH_BAD_FACE: return v->fail(LINON_ERR_INVALID, fmt("face %u indexes past the vertex array", bad));
+        case linon::BVH_NON_FINITE: return v->fail(LINON_ERR_INVALID, "linon_set_mesh: non-finite vertex coordinates");
+        case linon::BVH_TOO_DEEP: return v->fail(LINON_ERR_INVALID, "linon_set_mesh: hierarchy deeper than the traversal stack");
+        default: break;
     }
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
     cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_bvh);
     v->d_tris = nullptr; v->d_group_range = nullptr; v->d_bvh = nullptr;
-    CK(v, cudaMalloc(&v->d_tris, sorted.size() * sizeof(float)));
-    CK(v, cudaMemcpy(v->d_tris, sorted.data(), sorted.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CK(v, cudaMalloc(&v->d_bvh, bb.nodes.size() * sizeof(float)));
-    CK(v, cudaMemcpy(v->d_bvh, bb.nodes.data(), bb.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(v, cudaMalloc(&v->d_tris, bt.tris.size() * sizeof(float)));
+    CK(v, cudaMemcpy(v->d_tris, bt.tris.data(), bt.tris.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(v, cudaMalloc(&v->d_bvh, bt.nodes.size() * sizeof(float)));
+    CK(v, cudaMemcpy(v->d_bvh, bt.nodes.data(), bt.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
     v->n_faces = n_faces;
     v->n_groups = 0;
     v->use_bvh = true;
-    v->bvh_nodes = (uint32_t)(bb.nodes.size() / 8);
-    v->bvh_depth = bb.depth;
-    v->plane_w_max = extent;
+    v->bvh_nodes = (uint32_t)(bt.nodes.size() / 8);
+    v->bvh_depth = bt.depth;
+    v->plane_w_max = bt.extent;
     return LINON_OK;
 }
 

@@ -34,12 +34,13 @@ def _cxx():
 
 
 def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1", pairs: bool = False,
-          quiet_radius: int = 0):
+          quiet_radius: int = 0, bvh: bool = False, n_faces: int = 36):
     """-> ctypes library with emu_march for this variant of the march module (pairs: also linon_march_pairs)."""
     from linon_b200.main_view import compile_check
     os.makedirs(_CACHE, exist_ok=True)
     env = {"LINON_CHECK_BLOCK": "32", "LINON_CHECK_QUIET_ZONE": str(quiet_zone), "LINON_CHECK_CULL": str(cull),
-           "LINON_CHECK_KERNEL": "2" if pairs else "0", "LINON_CHECK_QUIET_RADIUS": str(quiet_radius)}
+           "LINON_CHECK_KERNEL": "2" if pairs else "0", "LINON_CHECK_QUIET_RADIUS": str(quiet_radius),
+           "LINON_CHECK_BVH": "1" if bvh else "0"}
     env["LINON_DUMP_SOURCE_ONLY"] = "1"
     old = {k: os.environ.get(k) for k in list(env) + ["LINON_DUMP_SOURCE"]}
     fd, dump = tempfile.mkstemp(suffix=".cu", dir=_CACHE)
@@ -48,7 +49,7 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
         os.environ.update(env)
         os.environ["LINON_DUMP_SOURCE"] = dump
         try:
-            compile_check(body, flags=flags, math_mode=math_mode)
+            compile_check(body, flags=flags, math_mode=math_mode, n_faces=n_faces)
         except Exception as e:  # LINON_DUMP_SOURCE_ONLY: the module text is written, the NVRTC compile is skipped
             if "LINON_DUMP_SOURCE_ONLY" not in str(e):
                 raise

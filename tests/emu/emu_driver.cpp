@@ -72,19 +72,26 @@ static int run_grid(void (*entry)(void*), void* arg, int n_blocks, int n_threads
 
 // returns 0 on success, 1 when the mesh tables do not match the variant, 2 when a warp collective was abandoned
 int emu_march(const EmuFrame* f) {
+#if LINON_BVH
+    linon::BvhTables bt;  // large meshes: faces in hierarchy order + the hierarchy, like set_mesh_bvh
+    if (linon::build_bvh_tables(f->verts, (uint32_t)f->n_verts, f->faces, (uint32_t)f->n_faces, bt) != linon::BVH_OK) return 1;
+    const std::vector<float>& tris = bt.tris;
+    std::vector<int> ranges(1, 0);
+    const float plane_w_max = bt.extent;
+#else
     linon::MeshTables mt;
     if (!linon::build_mesh_tables(f->verts, (uint32_t)f->n_verts, f->faces, (uint32_t)f->n_faces, mt)) return 1;
-#if !LINON_BVH
     if ((int)mt.n_groups() != LINON_N_GROUPS || (int)mt.n_p1() != LINON_N_P1 || (int)mt.n_boxes() != LINON_N_BOXES ||
         (int)mt.n_segments() != LINON_N_SEGS || f->n_faces != LINON_N_FACES)
         return 1;
-#endif
     std::vector<float> tris = mt.tris;
     tris.insert(tris.end(), mt.planes.begin(), mt.planes.end());
     tris.insert(tris.end(), mt.p1_planes.begin(), mt.p1_planes.end());
     tris.insert(tris.end(), mt.boxes.begin(), mt.boxes.end());
     std::vector<int> ranges = mt.ranges;
     ranges.insert(ranges.end(), mt.segments.begin(), mt.segments.end());
+    const float plane_w_max = mt.coord_max;
+#endif
 
     MarchParams P;
     memset(&P, 0, sizeof(P));
@@ -106,7 +113,10 @@ int emu_march(const EmuFrame* f) {
     P.counters = (unsigned long long*)f->counters;
     const unsigned int tiles_x = (f->width + 7) / 8, tiles_y = (f->height + 3) / 4;
     P.n_ray_slots = tiles_x * tiles_y * 32u;
-    P.plane_w_max = mt.coord_max;
+    P.plane_w_max = plane_w_max;
+#if LINON_BVH
+    P.bvh = (const float4*)bt.nodes.data();
+#endif
     P.n_fixed_steps = LINON_ADAPTIVE ? 0 : fixed_step_count(LINON_H_INITIAL);
     P.n_pair_slots = (((unsigned int)f->width + 15) / 16) * tiles_y * 32u;
     const int n_threads = f->n_threads > 0 ? f->n_threads : 8;

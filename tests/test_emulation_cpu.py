@@ -96,6 +96,45 @@ def test_emulated_sample_ray_kernel_is_bit_exact_with_the_oracle(product_lib, or
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+def _box_with_sphere(n_lat=12, n_lon=24):
+    """The start-up scene plus a latitude / longitude sphere inside it (shared edges, degenerate pole triangles)."""
+    verts, faces, _ = npo.default_scene()[:3]
+    c, r = np.array([0.0, 0.0, 0.0], np.float32), np.float32(0.4)
+    pts = []
+    for i in range(n_lat + 1):
+        th = np.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2.0 * np.pi * j / n_lon
+            pts.append(c + r * np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)], np.float32))
+    tris = []
+    for i in range(n_lat):
+        for j in range(n_lon):
+            a, b = i * n_lon + j, i * n_lon + (j + 1) % n_lon
+            tris += [(a, b, a + n_lon), (b, b + n_lon, a + n_lon)]
+    v = np.concatenate([np.asarray(verts, np.float32), np.asarray(pts, np.float32)])
+    f = np.concatenate([np.asarray(faces, np.uint32), np.asarray(tris, np.uint32) + len(verts)])
+    return v, f
+
+
+@pytest.mark.parametrize("fn,adaptive", [(PredefinedFunction.TranslationX, False), (PredefinedFunction.MirageSpherical, True)])
+def test_emulated_hierarchy_traversal_matches_the_oracles_loop_over_every_face(product_lib, oracle, fn, adaptive):
+    """LINON_BVH (meshes beyond the shared-memory stage, src/main.rs:139-157): faces in hierarchy order + a bounding-volume
+    hierarchy built by mesh_tables.hpp, exact traversal in intersect_mesh.  612 faces here, forced through that path: hit ids
+    (lowest index wins a shared edge), endpoints and step counters equal the oracle's loop over all faces bit for bit."""
+    W, H = 48, 36
+    verts, faces = _box_with_sphere()
+    _, _, cam = _frame_inputs(W, H)
+    lib = emu.build(fn.to_code(), 0 if adaptive else capi.RENDER_ADAPTIVE_OFF, capi.MATH_STRICT, bvh=True, n_faces=len(faces))
+    got = emu.march(lib, verts, faces, cam, SETTINGS, W, H)
+    ref = oracle.march(verts, faces, cam, SETTINGS, int(fn), W, H, h_initial=0.1, adaptive=adaptive)
+    assert np.array_equal(got["hit_id"], ref["hit_id"])
+    assert np.array_equal(got["rgba8"], ref["rgba8"])
+    assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32))
+    assert (got["hit_id"] >= 36).mean() > 0.03  # the sphere is really hit
+    assert int(got["counters"][0]) == int(ref["accepted"].sum()) and int(got["counters"][1]) == int(ref["prehit"].sum())
+    assert int(got["counters"][3]) < 0.1 * int(ref["prehit"].sum()) * len(faces)  # the traversal prunes
+
+
 PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
 
 
