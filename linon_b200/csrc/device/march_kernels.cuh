@@ -756,10 +756,11 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             // Quiet zone (mirage_fused.cuh): while every lane of the warp is outside the body's zone of influence the field
             // is the identity, a Runge-Kutta step is p += h dir with dir unchanged, and the cost a step takes from the
             // safe-distance budget is a constant.  Plan a run of such steps - as many as the lane with the nearest zone
-            // entry and the lane with the smallest budget allow - and take them back to back: every step is still executed
-            // (one FFMA per component), none needs a field evaluation, a vote or a culling check.  The plan is warp-uniform
-            // (REDUX.MIN); lanes that have hit carry an infinite budget.  A run that the budget cuts short is followed by
-            // ONE quiet step through the regular check logic below (velocity = direction), which refreshes the budget.
+            // entry and the lane nearest to the geometry allow (its budget or, when that is what binds, the directional bound
+            // of straight_clear_steps) - and take them back to back: every step is still executed (one FFMA per component),
+            // none needs a field evaluation, a vote or a culling check.  The plan is warp-uniform (REDUX.MIN); lanes that
+            // have hit carry an infinite budget.  A run that the geometry cuts short is followed by ONE quiet step through
+            // the regular check logic below (velocity = direction), which refreshes the budget.
             bool quiet = false;  // warp-uniform: this step's velocity is the direction
             if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
                 LINON_WARP_EVENT(5, 1);
