@@ -751,6 +751,9 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         const float kh = 1.7321f * 1.003f * h;  // SafeDistance::cost_linf
         int i = 0;
         bool searching = true;  // warp-uniform
+#if LINON_QUIET_ZONE
+        int quiet_ahead = 0;    // warp-uniform: steps from here known to be quiet for every lane (see below)
+#endif
         for (; i < n_steps && searching; ++i) {
 #if LINON_QUIET_ZONE
             // Quiet zone (mirage_fused.cuh): while every lane of the warp is outside the body's zone of influence the field
@@ -762,7 +765,13 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             // have hit carry an infinite budget.  A run that the geometry cuts short is followed by ONE quiet step through
             // the regular check logic below (velocity = direction), which refreshes the budget.
             bool quiet = false;  // warp-uniform: this step's velocity is the direction
-            if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
+            if (quiet_ahead > 0) {
+                // the last plan found no run (some lane is about to reach a face) but at least this many quiet steps for
+                // every lane: take them one by one through the check logic without planning again - on the final approach
+                // to a wall the answer would be "no run" again, and a plan costs as much as a full Runge-Kutta step
+                --quiet_ahead;
+                quiet = true;
+            } else if (!__any_sync(0xffffffffu, !(LinonField<float>::quiet_clearance(r.p) > 0.0f))) {
                 LINON_WARP_EVENT(5, 1);
                 const int nq = LinonField<float>::quiet_steps(r.p, r.dir, h);
                 const float q_inf = fmaxf(fmaxf(fabsf(r.dir.x), fabsf(r.dir.y)), fabsf(r.dir.z));
@@ -797,7 +806,12 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     i += n - 1;  // the loop header adds the last one
                     continue;
                 }
-                quiet = __all_sync(0xffffffffu, nq > 0);
+                const int nq_warp = __reduce_min_sync(0xffffffffu, nq);
+                quiet = nq_warp > 0;
+                // (small steps only: with the default step a ray crosses a tenth of the room per step and the situation
+                // has changed by the next one)
+                constexpr int ahead = LINON_H_INITIAL < 0.01f ? 3 : 1;
+                quiet_ahead = min(nq_warp, ahead) - 1;  // <= 0: the next step plans again
             }
             if (quiet) ++cnt.quiet;
             LINON_WARP_EVENT(quiet ? 8 : 7, 1);
