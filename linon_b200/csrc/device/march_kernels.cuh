@@ -794,7 +794,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 const int n_lane = LINON_CULL ? min(nq, n_clear) : 0;  // without culling every pre-hit step runs the face loop
                 const int n = min(__reduce_min_sync(0xffffffffu, n_lane), n_steps - i);
                 if (n > 0) {
-#pragma unroll 4
+#pragma unroll 8
                     for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
                     r.t = __fmaf_rn((float)n, h, r.t);
                     // within the budget: take the run from it (+inf stays +inf); beyond it (the directional bound allowed
@@ -884,7 +884,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 if (n > 0) {
                     LINON_WARP_EVENT(6, 1);
                     LINON_WARP_EVENT(11, n);
-#pragma unroll 4
+#pragma unroll 8
                     for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
                     r.t = __fmaf_rn((float)n, h, r.t);
                     cnt.quiet += (unsigned int)n;
