@@ -70,6 +70,33 @@ static int run_grid(void (*entry)(void*), void* arg, int n_blocks, int n_threads
     return bad;
 }
 
+#if LINON_QUIET_ZONE
+// the two planning functions of the quiet zone on arrays of rays (property tests): steps outside the body's zone of
+// influence and, for the start-up tables of `verts / faces`, steps of a straight ray that cannot reach a face
+void emu_quiet_plan(int n, const float* p, const float* dir, float h, const float* verts, int n_verts, const uint32_t* faces,
+                    int n_faces, int n_steps_left, int* quiet_steps, int* clear_steps) {
+    linon::MeshTables mt;
+    std::vector<float> tris;
+    if (clear_steps) {
+        linon::build_mesh_tables(verts, (uint32_t)n_verts, faces, (uint32_t)n_faces, mt);
+        tris = mt.tris;
+        tris.insert(tris.end(), mt.planes.begin(), mt.planes.end());
+        tris.insert(tris.end(), mt.p1_planes.begin(), mt.p1_planes.end());
+        tris.insert(tris.end(), mt.boxes.begin(), mt.boxes.end());
+    }
+    for (int i = 0; i < n; ++i) {
+        const vec3f pp(p[3 * i], p[3 * i + 1], p[3 * i + 2]), dd(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        if (quiet_steps) quiet_steps[i] = LinonField<float>::quiet_steps(pp, dd, h);
+#if LINON_CULL && !LINON_BVH
+        if (clear_steps) {
+            const vec3f d = dd * h;
+            clear_steps[i] = straight_clear_steps((const float4*)tris.data(), pp, d, (float)n_steps_left * l1_norm(d), mt.coord_max);
+        }
+#endif
+    }
+}
+#endif
+
 // returns 0 on success, 1 when the mesh tables do not match the variant, 2 when a warp collective was abandoned
 int emu_march(const EmuFrame* f) {
 #if LINON_BVH

@@ -261,6 +261,94 @@ def test_quiet_zone_with_partial_field_weight(product_lib, oracle, field_weight,
         assert m[1][k] >= m[0][k] - 2e-3, (k, m)
 
 
+def _quiet_plan(lib, p, d, h, verts=None, faces=None, n_steps_left=5001):
+    import ctypes as C
+    p = np.ascontiguousarray(p, np.float32)
+    d = np.ascontiguousarray(d, np.float32)
+    n = p.shape[0]
+    nq = np.zeros(n, np.int32)
+    nc = np.zeros(n, np.int32) if verts is not None else None
+    v = np.ascontiguousarray(verts, np.float32) if verts is not None else None
+    f = np.ascontiguousarray(faces, np.uint32) if faces is not None else None
+    lib.emu_quiet_plan(C.c_int(n), C.c_void_p(p.ctypes.data), C.c_void_p(d.ctypes.data), C.c_float(h),
+                       C.c_void_p(v.ctypes.data if v is not None else 0), C.c_int(0 if v is None else v.shape[0]),
+                       C.c_void_p(f.ctypes.data if f is not None else 0), C.c_int(0 if f is None else f.shape[0]),
+                       C.c_int(n_steps_left), C.c_void_p(nq.ctypes.data), C.c_void_p(nc.ctypes.data if nc is not None else 0))
+    return nq, nc
+
+
+@pytest.mark.parametrize("fn,centre_or_height,zone", [(PredefinedFunction.MirageSphericalSigmoid, (-0.5, 0.5, -0.5), 1.8866 * 0.25),
+                                                       (PredefinedFunction.MirageSpherical, (-0.5, 0.5, -0.5), 0.25),
+                                                       (PredefinedFunction.MiragePlaneSigmoid, 0.1, 1.8866 * 0.01),
+                                                       (PredefinedFunction.MiragePlane, 0.1, 0.01)])
+def test_quiet_steps_never_reach_the_zone_of_influence(product_lib, fn, centre_or_height, zone):
+    """quiet_steps (mirage_fused.cuh) on 20 000 random rays: every stage point of the promised steps (the straight line from
+    the start to n h dir) stays outside the region where the reference's own evaluation can differ from the identity -
+    dist < max_dist for the linear profiles, dist < 1.8866 max_dist (fp32 sigmoid saturation) for the sigmoids - and the
+    promise is not needlessly short."""
+    rng = np.random.default_rng(7)
+    n, h = 20000, np.float32(0.001)
+    p = rng.uniform(-1.3, 1.3, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= rng.uniform(0.5, 1.5, (n, 1)).astype(np.float32)       # the direction is not normalised once field_weight != 1
+    lib = emu.build(fn.to_code(), capi.RENDER_ENHANCE, capi.MATH_FAST, quiet_zone=1)
+    nq, _ = _quiet_plan(lib, p, d, h)
+    assert (nq >= 0).all() and (nq > 0).mean() > 0.5
+    p64, d64 = p.astype(np.float64), d.astype(np.float64) * float(h)
+    spherical = not np.isscalar(centre_or_height)
+
+    def dist_min(steps):  # smallest distance to the zone's centre / plane along p + s d, s in [0, steps]
+        if spherical:
+            c = p64 - np.asarray(centre_or_height)
+            s_star = np.clip(-(c * d64).sum(1) / (d64 * d64).sum(1), 0.0, steps)
+            return np.linalg.norm(c + s_star[:, None] * d64, axis=1)
+        y0, y1 = p64[:, 1] - centre_or_height, p64[:, 1] + steps * d64[:, 1] - centre_or_height
+        return np.where(y0 * y1 <= 0.0, 0.0, np.minimum(np.abs(y0), np.abs(y1)))
+
+    capped = np.minimum(nq, 1 << 20).astype(np.float64)
+    assert (dist_min(capped)[nq > 0] >= zone).all()
+    # not needlessly short: a finite promise ends within a few steps (and 0.1 % of its length) of the radius the kernel uses
+    finite = (nq > 0) & (nq < (1 << 20))
+    radius = {1: 1.001 * 0.25, 3: 1.92 * 0.25, 2: 1.001 * 0.01, 4: 1.92 * 0.01}[int(fn)]
+    assert (dist_min(capped * 1.002 + 4.0)[finite] <= radius * 1.0001).all()
+
+
+def test_straight_clear_steps_never_skip_a_face(product_lib, oracle):
+    """straight_clear_steps (march_kernels.cuh) on random straight rays inside the start-up scene: on none of the promised steps
+    can the reference's own hit test (hit_triangle over all 36 faces, t in (eps, max_dist), fp64 here) find a face."""
+    rng = np.random.default_rng(11)
+    verts, faces, _ = npo.default_scene()[:3]
+    verts, faces = np.asarray(verts, np.float64), np.asarray(faces, np.int64)
+    n, h = 4000, np.float32(0.001)
+    p = rng.uniform(-0.98, 0.98, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    lib = emu.build(PredefinedFunction.MirageSphericalSigmoid.to_code(), capi.RENDER_ENHANCE, capi.MATH_FAST, quiet_zone=1)
+    _, nc = _quiet_plan(lib, p, d, h, verts.astype(np.float32), faces.astype(np.uint32))
+    assert (nc >= 0).all() and (nc > 10).mean() > 0.5
+    # the promised stretch p .. p + nc h d as ONE segment against every triangle (Moeller-Trumbore, src/main_view.wgsl:150-175)
+    v0, e1, e2 = verts[faces[:, 0]], verts[faces[:, 1]] - verts[faces[:, 0]], verts[faces[:, 2]] - verts[faces[:, 0]]
+    o = p.astype(np.float64)[:, None, :]
+    length = np.minimum(nc, 20000).astype(np.float64) * float(h)
+    dn = d.astype(np.float64)[:, None, :]
+    hh = np.cross(dn, e2[None])
+    a = (e1[None] * hh).sum(-1)
+    ok = np.abs(a) > 1e-12
+    f = np.where(ok, 1.0 / np.where(ok, a, 1.0), 0.0)
+    s = o - v0[None]
+    u = f * (s * hh).sum(-1)
+    q = np.cross(s, e1[None])
+    v = f * (dn * q).sum(-1)
+    t = f * (e2[None] * q).sum(-1)
+    hit = ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 1e-7) & (t < length[:, None])
+    assert not hit.any(), int(hit.any(axis=1).sum())
+    # ... and the promise is not needlessly short: a few steps later a face is within one step's reach, unless none lies ahead
+    t_first = np.where(ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 1e-7), t, np.inf).min(axis=1)
+    ahead = np.isfinite(t_first) & (nc < 20000)
+    assert np.median((t_first[ahead] / float(h) - nc[ahead])) < 40.0
+
+
 def test_quiet_zone_radius_option(product_lib, oracle):
     """LINON_OPT_QUIET_RADIUS: at 1.5 max_dist the sigmoid's real-number deflection over the excluded shell is 1e-9 rad (below
     fp32 resolution, far below the reference's own rounding noise there): same agreement with the oracle, half the evaluated
