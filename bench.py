@@ -256,26 +256,30 @@ def run_quiet_zone_probe(args):
         c = mv.counters()
         return float(np.mean(frame_ms)), float(np.mean(march_ms)), c, int(mv.debug_profile()[15])
 
+    def agreement(c):
+        same_hit = hid == ref["hid"]
+        use = ~excl
+        matched = use & same_hit
+        n_use, n_matched = int(use.sum()), max(int(matched.sum()), 1)
+        err = torch.linalg.vector_norm(ep[..., :3].double() - ref["ep"][..., :3].double(), dim=-1)
+        rel = err / torch.clamp(torch.linalg.vector_norm(ref["ep"][..., :3].double(), dim=-1), min=1e-12)
+        cdiff = (rc.to(torch.int16) - ref["rc"].to(torch.int16)).abs().amax(dim=-1)
+        agree = dict(pixels=W * H, excluded_high_lyapunov=int(excl.sum()), compared=n_use,
+                     hit_id_equal=float((same_hit & use).sum()) / max(n_use, 1),
+                     colour_within_1=float(((cdiff <= 1) & matched).sum()) / n_matched,
+                     endpoint_within_1e3=float(((rel <= 1e-3) & matched).sum()) / n_matched,
+                     endpoint_max_rel=float(rel[matched].max()) if int(matched.sum()) else 0.0,
+                     hit_id_equal_all_pixels=float(same_hit.sum()) / (W * H))
+        agree["meets_north_star"] = bool(agree["hit_id_equal"] >= 0.999 and agree["colour_within_1"] >= 0.999 and
+                                         agree["endpoint_within_1e3"] >= 0.999 and int(c.accepted_steps) == W * H * 5001)
+        return agree
+
     d_ms, d_march, d_c, _ = measure(0)
     ref = dict(ep=ep.clone(), rc=rc.clone(), hid=hid.clone())
     excl = torch.as_tensor(mv.exponents().reshape(H, W), device="cuda") >= 0.8
     ms, m_ms, c, quiet = measure(1)
-    same_hit = hid == ref["hid"]
-    use = ~excl
-    matched = use & same_hit
-    n_use, n_matched = int(use.sum()), max(int(matched.sum()), 1)
-    err = torch.linalg.vector_norm(ep[..., :3].double() - ref["ep"][..., :3].double(), dim=-1)
-    rel = err / torch.clamp(torch.linalg.vector_norm(ref["ep"][..., :3].double(), dim=-1), min=1e-12)
-    cdiff = (rc.to(torch.int16) - ref["rc"].to(torch.int16)).abs().amax(dim=-1)
     flops = fl.fused_march_flops(c, FN_ID, field_weight_is_one=True, quiet_steps=quiet)
-    agree = dict(pixels=W * H, excluded_high_lyapunov=int(excl.sum()), compared=n_use,
-                 hit_id_equal=float((same_hit & use).sum()) / max(n_use, 1),
-                 colour_within_1=float(((cdiff <= 1) & matched).sum()) / n_matched,
-                 endpoint_within_1e3=float(((rel <= 1e-3) & matched).sum()) / n_matched,
-                 endpoint_max_rel=float(rel[matched].max()) if int(matched.sum()) else 0.0,
-                 hit_id_equal_all_pixels=float(same_hit.sum()) / (W * H))
-    agree["meets_north_star"] = bool(agree["hit_id_equal"] >= 0.999 and agree["colour_within_1"] >= 0.999 and
-                                     agree["endpoint_within_1e3"] >= 0.999 and int(c.accepted_steps) == W * H * 5001)
+    # the main result goes out first: whatever the extra measurements below do, the parent already has this line
     print(json.dumps(dict(
         ms_per_step=ms, march_ms=m_ms, value=W * H / (ms * 1e-3) / 1e6, unit="Mrays/s",
         rk4_gsteps_per_s=c.accepted_steps / (ms * 1e-3) / 1e9, frames=frames,
@@ -283,11 +287,92 @@ def run_quiet_zone_probe(args):
         counters=dict(accepted=int(c.accepted_steps), quiet_steps=quiet, quiet_fraction=quiet / max(int(c.accepted_steps), 1),
                       prehit=int(c.prehit_steps), culling_checks=int(c.culling_checks), face_tests=int(c.face_tests)),
         executed_tflops=flops / (m_ms * 1e-3) / 1e12,
-        vs_default_path=agree,
+        vs_default_path=agreement(c),
         note="LINON_OPT_QUIET_ZONE = 1 (opt-in, off in the headline numbers of this line): fixed-step frames of a predefined mirage "
              "body take straight steps while the whole warp is outside the body's zone of influence, where the reference's own "
-             "fp32 evaluation has eta == 1; every Runge-Kutta step is executed and counted")))
+             "fp32 evaluation has eta == 1; every Runge-Kutta step is executed and counted")), flush=True)
+
+    # Extra measurements of the same opt-in path, each on its own line ({"extra": name, ...}); the parent files them under
+    # quiet_zone_probe[name].  (1) the tighter radius of the sigmoid profiles, same C3 frame against the same default frame.
+    try:
+        mv.set_option(capi.OPT_QUIET_RADIUS, 1500)
+        r_ms, r_march, r_c, r_quiet = measure(1)
+        print(json.dumps(dict(extra="radius_1500", ms_per_step=r_ms, march_ms=r_march, quiet_steps=r_quiet,
+                              quiet_fraction=r_quiet / max(int(r_c.accepted_steps), 1),
+                              culling_checks=int(r_c.culling_checks), vs_default_path=agreement(r_c),
+                              note="LINON_OPT_QUIET_RADIUS = 1500: zone radius 1.5 max_dist instead of where the fp32 sigmoid "
+                                   "saturates (1.92 max_dist)")), flush=True)
+        mv.set_option(capi.OPT_QUIET_RADIUS, 0)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps(dict(extra="radius_1500", error=f"{type(e).__name__}: {e}"[:300])), flush=True)
+    # (2) adaptive default-step frames (C1: 800x600, MirageSpherical) with option level 2 against level 0: march time, the
+    # kernel's own step counters, hit ids and colours (endpoints of adaptive frames are not comparable)
+    try:
+        W1, H1 = 800, 600
+        mv1 = MainView(verts, faces, center, W1, H1, discrete_gpu=True, device=dev)
+        mv1.reload_shader(PredefinedFunction(1).to_code())
+        mv1.update_settings(make_settings())
+        rc1 = torch.as_tensor(_DevBuf(mv1.device_ptr(capi.BUF_RAYCAST_RGBA8), (H1, W1, 4), "|u1"), device="cuda")
+        hid1 = torch.as_tensor(_DevBuf(mv1.device_ptr(capi.BUF_HIT_ID_I32), (H1, W1), "<i4"), device="cuda")
+
+        def c1(level):
+            mv1.set_option(capi.OPT_QUIET_ZONE, level)
+            times = []
+            for i in range(6):
+                mv1.render_flags(0)
+                mv1.sync()
+                if i >= 2:
+                    times.append(mv1.timings().march_ms)
+            k = mv1.counters()
+            return float(np.mean(times)), int(k.accepted_steps), int(k.rejected_steps), rc1.clone(), hid1.clone()
+
+        t0, a0, j0, rc_0, hid_0 = c1(0)
+        t2, a2, j2, rc_2, hid_2 = c1(2)
+        same = hid_0 == hid_2
+        cd = (rc_0.to(torch.int16) - rc_2.to(torch.int16)).abs().amax(dim=-1)
+        print(json.dumps(dict(extra="c1_adaptive_level2", width=W1, height=H1, function="MirageSpherical",
+                              march_ms_level0=t0, march_ms_level2=t2,
+                              steps_per_ray_level0=dict(accepted=a0 / (W1 * H1), rejected=j0 / (W1 * H1)),
+                              steps_per_ray_level2=dict(accepted=a2 / (W1 * H1), rejected=j2 / (W1 * H1)),
+                              hit_id_equal=float(same.sum()) / (W1 * H1),
+                              colour_within_1_where_hit_equal=float(((cd <= 1) & same).sum()) / max(int(same.sum()), 1))),
+              flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps(dict(extra="c1_adaptive_level2", error=f"{type(e).__name__}: {e}"[:300])), flush=True)
     return 0
+
+
+def parse_probe_output(stdout, failure):
+    """First JSON line of the probe child = the main result; later {"extra": name, ...} lines are filed under their name."""
+    probe = None
+    for ln in (stdout or "").splitlines():
+        if not ln.startswith("{"):
+            continue
+        try:
+            obj = json.loads(ln)
+        except ValueError:
+            continue
+        if probe is None and "extra" not in obj:
+            probe = obj
+        elif probe is not None and "extra" in obj:
+            probe[obj.pop("extra")] = obj
+    if probe is None:
+        return dict(error=failure)
+    if failure:
+        probe["incomplete"] = failure
+    return probe
+
+
+def run_probe_child(local_rank, timeout=300):
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-quiet-zone", "--device", str(local_rank)],
+                           capture_output=True, text=True, timeout=timeout)
+        return parse_probe_output(r.stdout, "" if r.returncode == 0 else f"exit {r.returncode}: {r.stderr[-300:]}")
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else e.stdout
+        return parse_probe_output(out, f"time limit of {timeout} s reached")
+    except Exception as e:  # noqa: BLE001
+        return dict(error=f"{type(e).__name__}: {e}"[:400])
 
 
 def run_ours(args):
@@ -513,13 +598,7 @@ def run_ours(args):
         # LAST GPU work of the run: the opt-in quiet-zone path on the same frame, timed and compared with the default path's
         # frame on the device.  A reported probe, not the headline: the option stays off until this has been seen on a B200.
         # In a child process with a time limit, so that nothing the unmeasured path does can take this line down.
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-quiet-zone", "--device", str(local_rank)],
-                               capture_output=True, text=True, timeout=300)
-            out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            line["quiet_zone_probe"] = json.loads(out[-1]) if out else dict(error=f"exit {r.returncode}: {r.stderr[-300:]}")
-        except Exception as e:  # noqa: BLE001
-            line["quiet_zone_probe"] = dict(error=f"{type(e).__name__}: {e}"[:400])
+        line["quiet_zone_probe"] = run_probe_child(local_rank)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
