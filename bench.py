@@ -105,6 +105,18 @@ def ncu_profile():
     return None
 
 
+def overlay_ncu_traffic(W, H):
+    """DRAM bytes per overlay launch from the committed ncu capture (profiles/r1_overlay_c3.json, taken at the C3 size);
+    None for any other frame size."""
+    path = os.path.join(ROOT, "profiles", "r1_overlay_c3.json")
+    if (W, H) != (3840, 2160) or not os.path.exists(path):
+        return None
+    for k in json.load(open(path)):
+        if "overlay_kernel" in str(k.get("kernel", "")) and k.get("dram_traffic_bytes"):
+            return float(k["dram_traffic_bytes"])
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -552,7 +564,8 @@ def run_ours(args):
         ob = fl.OVERLAY_BYTES[1] * W * H
         a = ob / (o_ms * 1e-3) / 1e9
         overlay_roof = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                            traffic=None, kernel="overlay_kernel", algorithmic_bytes_per_launch=ob, peak_source=peak_src)
+                            traffic=overlay_ncu_traffic(W, H), kernel="overlay_kernel", algorithmic_bytes_per_launch=ob,
+                            peak_source=peak_src)
 
     line = dict(
         metric="Mrays/s", value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,

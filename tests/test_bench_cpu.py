@@ -32,3 +32,9 @@ def test_reference_arm_on_other_ranks_exits_without_work():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_overlay_traffic_comes_from_the_committed_capture_of_that_size_only():
+    t = bench.overlay_ncu_traffic(3840, 2160)
+    assert t is not None and 0.8 * 28 * 3840 * 2160 < t < 1.2 * 28 * 3840 * 2160  # no wasted re-reads (28 algorithmic B/px)
+    assert bench.overlay_ncu_traffic(800, 600) is None
