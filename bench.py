@@ -304,6 +304,40 @@ def run_quiet_zone_probe(args):
              "body take straight steps while the whole warp is outside the body's zone of influence, where the reference's own "
              "fp32 evaluation has eta == 1; every Runge-Kutta step is executed and counted")), flush=True)
 
+    # (0) the other opt-in kernel of the path: the direct overlay (LINON_OPT_OVERLAY_KERNEL = 1, no shared-memory stage) against
+    # the measured default on this very frame - time of the overlay launch alone, L2 flushed before each, results compared
+    try:
+        fin = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_FINAL_RGBA8), (H, W, 4), "|u1"), device="cuda")
+        exb = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_EXPONENTS_F32), (H, W), "<f4"), device="cuda")
+
+        def overlay_only(variant, reps=10):
+            mv.set_option(capi.OPT_OVERLAY_KERNEL, variant)
+            t = []
+            for i in range(reps + 3):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+                mv.sync()
+                if i >= 3:
+                    t.append(mv.timings().overlay_ms)
+            return float(np.mean(t)), float(np.min(t)), fin.clone(), exb.clone()
+
+        s_mean, s_min, s_fin, s_ex = overlay_only(0)
+        o_mean, o_min, o_fin, o_ex = overlay_only(1)
+        mv.set_option(capi.OPT_OVERLAY_KERNEL, 0)
+        hbm = measured_peaks()[0]["hbm_gbs"]
+        ob = fl.OVERLAY_BYTES[1] * W * H
+        print(json.dumps(dict(extra="overlay_direct", staged_ms=s_mean, staged_ms_min=s_min, direct_ms=o_mean, direct_ms_min=o_min,
+                              staged_gbs=ob / (s_mean * 1e-3) / 1e9, direct_gbs=ob / (o_mean * 1e-3) / 1e9,
+                              staged_frac_of_hbm_peak=ob / (s_mean * 1e-3) / 1e9 / hbm,
+                              direct_frac_of_hbm_peak=ob / (o_mean * 1e-3) / 1e9 / hbm, algorithmic_bytes_per_launch=ob,
+                              final_equal=bool(torch.equal(s_fin, o_fin)),
+                              exponents_bit_equal=bool(torch.equal(s_ex.view(torch.int32), o_ex.view(torch.int32))),
+                              note="LINON_OPT_OVERLAY_KERNEL = 1 (csrc/device/overlay_direct.cuh): four taps per pixel through the "
+                                   "read-only path instead of a staged tile; opt-in until this line has been seen")), flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps(dict(extra="overlay_direct", error=f"{type(e).__name__}: {e}"[:300])), flush=True)
+
     # Extra measurements of the same opt-in path, each on its own line ({"extra": name, ...}); the parent files them under
     # quiet_zone_probe[name].  (1) the tighter radius of the sigmoid profiles, same C3 frame against the same default frame.
     try:

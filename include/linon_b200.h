@@ -118,6 +118,10 @@ enum {
                                     = 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6).  1250 ... 4000: below
                                     1886 the reference's eta is 1 +- its rounding noise and the real-number deflection summed over
                                     the excluded shell is <= 1.85e-4 exp(6 - 12 r): 1e-9 rad at 1500 (mirage_fused.cuh) */
+    LINON_OPT_OVERLAY_KERNEL = 14, /* overlay stencil (src/overlay.wgsl:99-146).  0 (default, measured): 32x16 tile + halo of the
+                                    endpoints staged in shared memory.  1 (opt-in until measured on the GPU): every pixel
+                                    fetches its four taps through the read-only path, no shared memory, no barrier
+                                    (csrc/device/overlay_direct.cuh).  Bit-identical results */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.

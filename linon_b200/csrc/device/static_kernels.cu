@@ -6,6 +6,7 @@
 //                        out, 4 exponent out), 8 in mode 0.  Endpoints are staged per CTA into shared memory
 //                        (tile + halo of `delta`, three float planes) so every texel is fetched from L2/HBM once
 //                        per tile instead of four times.
+//   overlay_direct_kernel  opt-in variant without the shared-memory stage (overlay_direct.cuh; LINON_OPT_OVERLAY_KERNEL)
 //   outline_search       the eight extreme / first-hit searches over exponents >= 0.8 that pick the "Outline"
 //                        sample rays (src/main_view.wgsl:381-468), restated as ONE parallel arg-reduction with
 //                        the intended stride W instead of eight serial W*H scans.
@@ -108,8 +109,27 @@ overlay_kernel(int W, int H, int overlay_mode, int delta, float scaling, const u
     }
 }
 
+}  // namespace linon
+#include "overlay_direct.cuh"
+namespace linon {
+
+// Direct variant (opt-in, LINON_OPT_OVERLAY_KERNEL = 1): no shared-memory staging, see overlay_direct.cuh
+__global__ void __launch_bounds__(OVD_TX * OVD_WARPS)
+overlay_direct_kernel(int W, int H, int overlay_mode, int delta, float scaling, const unsigned int* __restrict__ raycast,
+                      const float4* __restrict__ endpoint, unsigned int* __restrict__ final_rgba,
+                      float* __restrict__ exponents) {
+    overlay_direct_thread((int)threadIdx.x, (int)threadIdx.y, (int)blockIdx.x, (int)blockIdx.y, W, H, overlay_mode, delta,
+                          scaling, raycast, endpoint, final_rgba, exponents);
+}
+
 void launch_overlay(cudaStream_t stream, int W, int H, int overlay_mode, int delta, float scaling, const void* raycast,
-                    const void* endpoint, void* final_rgba, float* exponents) {
+                    const void* endpoint, void* final_rgba, float* exponents, int variant) {
+    if (variant == 1) {
+        dim3 block(OVD_TX, OVD_WARPS), grid((W + OVD_TX - 1) / OVD_TX, (H + OVD_TY - 1) / OVD_TY);
+        overlay_direct_kernel<<<grid, block, 0, stream>>>(W, H, overlay_mode, delta, scaling, (const unsigned int*)raycast,
+                                                          (const float4*)endpoint, (unsigned int*)final_rgba, exponents);
+        return;
+    }
     dim3 block(OV_TX, 8), grid((W + OV_TX - 1) / OV_TX, (H + OV_TY - 1) / OV_TY);
     overlay_kernel<<<grid, block, 0, stream>>>(W, H, overlay_mode, delta, scaling, (const uchar4*)raycast,
                                                (const float4*)endpoint, (uchar4*)final_rgba, exponents);

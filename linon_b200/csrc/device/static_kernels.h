@@ -5,7 +5,7 @@
 namespace linon {
 
 void launch_overlay(cudaStream_t stream, int W, int H, int overlay_mode, int delta, float scaling, const void* raycast,
-                    const void* endpoint, void* final_rgba, float* exponents);
+                    const void* endpoint, void* final_rgba, float* exponents, int variant);  // variant 1: overlay_direct_kernel
 void launch_outline_search(cudaStream_t stream, int W, int H, const float* exponents, unsigned long long* keys,
                            float* pos16, int n_sm);
 void launch_click_positions(cudaStream_t stream, float mouse_x, float mouse_y, float* pos16);

@@ -361,7 +361,7 @@ struct linon_view {
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 0, opt_quiet_radius = 0;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 0, opt_quiet_radius = 0, opt_overlay_kernel = 0;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
@@ -939,7 +939,8 @@ int linon_render(linon_view* v, uint32_t flags) {
     if (do_overlay) {
         CK(v, cudaEventRecord(v->ev[2], v->stream));
         linon::launch_overlay(v->stream, (int)v->W, (int)v->H, v->settings.overlay_mode, v->settings.central_difference_delta,
-                              v->settings.lyapunov_scaling, v->d_raycast, v->d_endpoint, v->d_final, v->d_exponents);
+                              v->settings.lyapunov_scaling, v->d_raycast, v->d_endpoint, v->d_final, v->d_exponents,
+                              v->opt_overlay_kernel);
         CK(v, cudaGetLastError());
         CK(v, cudaEventRecord(v->ev[3], v->stream));
         v->ran_overlay = true;
@@ -1061,6 +1062,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_PROFILE: if (value < 0 || value > 1) break; v->opt_profile = value; return LINON_OK;
         case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
         case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 2) break; v->opt_quiet = value; return LINON_OK;
+        case LINON_OPT_OVERLAY_KERNEL: if (value < 0 || value > 1) break; v->opt_overlay_kernel = value; return LINON_OK;
         case LINON_OPT_QUIET_RADIUS: if (value != 0 && (value < 1250 || value > 4000)) break; v->opt_quiet_radius = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));

@@ -4,7 +4,9 @@ The option was written in a session without GPU time: its device code is validat
 source (tests/test_emulation_cpu.py: north star against the oracle, culling bit-identity, step counts), and the default
 kernels compile to byte-identical SASS with and without this change.  These tests are its first run on hardware, hence
 xfail(strict=False): a failure here says "keep the option off", never that the default path regressed.  The file sorts
-last among the GPU tests on purpose.
+last among the GPU tests on purpose.  The same holds for the two other opt-in paths tested at the end of the file: peer
+stores (linon_redirect_output) and the direct overlay kernel (LINON_OPT_OVERLAY_KERNEL, validated bit for bit against the
+oracle on the host in tests/test_overlay_emulation_cpu.py).
 """
 import numpy as np
 import pytest
@@ -144,3 +146,39 @@ def test_peer_stores_assemble_the_frame_in_the_root_views_buffers(product_lib, s
     finally:
         for mv in views:
             mv.close()
+
+
+@pytest.mark.parametrize("delta", [1, 2, 5, 10])
+@pytest.mark.parametrize("size", [(200, 150), (1920, 1080)])
+def test_direct_overlay_kernel_equals_the_staged_one_bit_for_bit(product_lib, oracle, scene, delta, size):
+    """LINON_OPT_OVERLAY_KERNEL = 1 (csrc/device/overlay_direct.cuh; opt-in, validated on the host against the oracle in
+    tests/test_overlay_emulation_cpu.py): same final image and same exponents as the measured default on the same frame,
+    and within the oracle's tolerance like test_gpu_units.test_overlay_matches_the_oracle."""
+    verts, faces, center = scene
+    W, H = size
+    with MainView(verts, faces, center, W, H) as mv:
+        mv.reload_shader(PredefinedFunction.MirageSphericalSigmoid.to_code())
+        st = make_settings(overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0)
+        mv.update_settings(st)
+        mv.disable_adaptive_sampling()
+        mv.render()
+        mv.sync()
+        staged_final, staged_ex = mv.texture().copy(), mv.exponents().copy()
+        raycast, ep = mv.ray_casting_texture(), mv.mapping_texture()
+        mv.set_option(capi.OPT_OVERLAY_KERNEL, 1)
+        mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+        mv.sync()
+        final, ex = mv.texture(), mv.exponents()
+        assert np.array_equal(final, staged_final)
+        assert np.array_equal(ex.view(np.uint32), staged_ex.view(np.uint32))
+        assert (ex >= 0.8).any()
+        if W * H <= 200 * 150:
+            ref_final, ref_ex = oracle.overlay(raycast, ep, dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=1,
+                                                                 central_difference_delta=delta, lyapunov_scaling=50.0))
+            assert np.allclose(ex, ref_ex, rtol=1e-5, atol=1e-7)
+            assert np.abs(final.astype(int) - ref_final.astype(int)).max() <= 1
+        # mode 0: exact copy, exponents untouched (src/overlay.wgsl:116-118)
+        mv.update_settings(make_settings(overlay_mode=0, central_difference_delta=delta))
+        mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+        mv.sync()
+        assert np.array_equal(mv.texture(), raycast) and np.array_equal(mv.exponents(), ex)
