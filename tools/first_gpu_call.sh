@@ -6,7 +6,7 @@ set -u
 OUT=gpurun_out/first
 mkdir -p "$OUT"
 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
-# 1. the opt-in paths on hardware, with the reasons of every xfail / xpass
+# 1. the opt-in paths on hardware (quiet zone, peer stores in one process, direct overlay kernel), with the reasons of every xfail / xpass
 timeout 900 python -m pytest tests/test_gpu_zz_quiet_zone.py -q -m gpu -rxXs -p no:cacheprovider --runxfail > "$OUT/quiet_zone_tests.log" 2>&1
 # 2. C3: default path (with the probe), quiet zone, quiet zone with the tighter sigmoid radius
 timeout 600 python bench.py --steps 5 --warmup 3 > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
