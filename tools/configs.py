@@ -1,6 +1,6 @@
 """BASELINE.json configs C1, C2 and C4 on one B200 (developer / evidence tool, run under gpurun).
 
-    python tools/configs.py [--out gpurun_out/configs.json] [--reps 3] [--quiet-zone 0|1|2]
+    python tools/configs.py [--out gpurun_out/configs.json] [--reps 3] [--quiet-zone 0|1|2] [--overlay-kernel 0|1]
 
   C1  800x600, MirageSpherical (first predefined function), default step size (h = 0.1, adaptive sampling on)
   C2  1920x1080, every predefined function of src/functions.rs, default step size
@@ -20,6 +20,7 @@ from linon_b200.main_view import MainView, PredefinedFunction, default_scene, ma
 out_path = "gpurun_out/configs.json"
 reps = 3
 quiet_zone = 0
+overlay_kernel = 0
 args = sys.argv[1:]
 for i, a in enumerate(args):
     if a == "--out":
@@ -28,6 +29,8 @@ for i, a in enumerate(args):
         reps = int(args[i + 1])
     if a == "--quiet-zone":  # LINON_OPT_QUIET_ZONE (opt-in): 1 fixed-step variants, 2 adaptive variants as well
         quiet_zone = int(args[i + 1])
+    if a == "--overlay-kernel":  # LINON_OPT_OVERLAY_KERNEL (opt-in): 1 = direct kernel without the shared-memory stage
+        overlay_kernel = int(args[i + 1])
 
 verts, faces, center = default_scene()
 PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
@@ -55,10 +58,11 @@ def frame(mv, flags):
                 culling_checks_per_prehit_step=round(c.culling_checks / max(c.prehit_steps, 1), 4))
 
 
-result = dict(configs=[], quiet_zone=quiet_zone)
+result = dict(configs=[], quiet_zone=quiet_zone, overlay_kernel=overlay_kernel)
 # ---- C1 -----------------------------------------------------------------------------------------------------------
 with MainView(verts, faces, center, 800, 600) as mv:
     mv.set_option(capi.OPT_QUIET_ZONE, quiet_zone)
+    mv.set_option(capi.OPT_OVERLAY_KERNEL, overlay_kernel)
     mv.reload_shader(PredefinedFunction.MirageSpherical.to_code())
     for name, flags in (("adaptive on (as the application renders)", 0), ("adaptive off (51 steps)", capi.RENDER_ADAPTIVE_OFF)):
         r = frame(mv, flags)
@@ -69,6 +73,7 @@ with MainView(verts, faces, center, 800, 600) as mv:
 # ---- C2 -----------------------------------------------------------------------------------------------------------
 with MainView(verts, faces, center, 1920, 1080) as mv:
     mv.set_option(capi.OPT_QUIET_ZONE, quiet_zone)
+    mv.set_option(capi.OPT_OVERLAY_KERNEL, overlay_kernel)
     for fn in PREDEFINED:
         mv.reload_shader(fn.to_code())
         for name, flags in (("adaptive on", 0), ("adaptive off", capi.RENDER_ADAPTIVE_OFF)):

@@ -14,9 +14,13 @@ timeout 300 python bench.py --steps 5 --warmup 3 --quiet-zone 1 --no-cpu-baselin
 # 3. C1 / C2 / C4 with the option at level 2 (adaptive frames) next to the default
 timeout 300 python tools/configs.py --out "$OUT/configs_default.json" > "$OUT/configs_default.log" 2>&1
 timeout 300 python tools/configs.py --quiet-zone 2 --out "$OUT/configs_quiet2.json" > "$OUT/configs_quiet2.log" 2>&1
+timeout 300 python tools/configs.py --overlay-kernel 1 --out "$OUT/configs_overlay1.json" > "$OUT/configs_overlay1.log" 2>&1
 # 4. launch list + one full capture of the quiet-zone march (never a bench value)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches_quiet.csv" \
     python bench.py --steps 2 --warmup 1 --quiet-zone 1 --no-cpu-baseline > "$OUT/ncu_launches.log" 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:linon_march_tiles -s 2 -c 1 -o "$OUT/march_quiet" -f \
     python bench.py --steps 1 --warmup 1 --quiet-zone 1 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
+# 5. the direct overlay kernel under ncu: one full capture (bench.py's probe child runs it on the C3 frame)
+timeout 600 ncu --set full --clock-control none --import-source on --target-processes all -k regex:overlay_direct_kernel -s 3 -c 1 \
+    -o "$OUT/overlay_direct" -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > "$OUT/ncu_overlay_direct.log" 2>&1
 ls -la "$OUT"
