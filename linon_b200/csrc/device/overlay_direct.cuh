@@ -55,7 +55,8 @@ LINON_OV_HD void overlay_direct_thread(int tx, int ty, int bx, int by, int W, in
     const int padding = 2 * delta;
     const bool stencil = overlay_mode == 1;
     const bool inner_x = !(x < padding || x >= W - padding);
-    const long long row_step = (long long)delta * W;
+    const long long tap_x = (long long)delta * (long long)sizeof(float4);
+    const long long tap_y = tap_x * W;
 #pragma unroll
     for (int r = 0; r < OVD_TY / OVD_WARPS; ++r) {
         const int y = by * OVD_TY + ty + OVD_WARPS * r;
@@ -64,9 +65,10 @@ LINON_OV_HD void overlay_direct_thread(int tx, int ty, int bx, int by, int W, in
         unsigned int c = raycast[idx];
         if (stencil && inner_x && !(y < padding || y >= H - padding)) {
             // lyapunov_exponent, src/overlay.wgsl:99-112
-            const float4* __restrict__ e = endpoint + idx;
-            const float4 xp = __ldg(e + delta), xm = __ldg(e - delta);
-            const float4 yp = __ldg(e + row_step), ym = __ldg(e - row_step);
+            // one 64-bit address for the pixel, four warp-uniform byte offsets from it
+            const char* e = (const char*)(endpoint + idx);
+            const float4 xp = __ldg((const float4*)(e + tap_x)), xm = __ldg((const float4*)(e - tap_x));
+            const float4 yp = __ldg((const float4*)(e + tap_y)), ym = __ldg((const float4*)(e - tap_y));
             const float gxx = 0.5f * (xp.x - xm.x);
             const float gxy = 0.5f * (xp.y - xm.y);
             const float gxz = 0.5f * (xp.z - xm.z);

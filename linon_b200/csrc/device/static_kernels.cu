@@ -114,7 +114,7 @@ overlay_kernel(int W, int H, int overlay_mode, int delta, float scaling, const u
 namespace linon {
 
 // Direct variant (opt-in, LINON_OPT_OVERLAY_KERNEL = 1): no shared-memory staging, see overlay_direct.cuh
-__global__ void __launch_bounds__(OVD_TX * OVD_WARPS)
+__global__ void __launch_bounds__(OVD_TX * OVD_WARPS, 8)  // 32 registers: 64 resident warps per SM
 overlay_direct_kernel(int W, int H, int overlay_mode, int delta, float scaling, const unsigned int* __restrict__ raycast,
                       const float4* __restrict__ endpoint, unsigned int* __restrict__ final_rgba,
                       float* __restrict__ exponents) {
