@@ -140,11 +140,9 @@ void launch_overlay(cudaStream_t stream, int W, int H, int overlay_mode, int del
 //   "max sum, last in scan order (x outer, y inner)"  -> (sum, x, y) lexicographic maximum
 //   "first found in scan order (a outer, b inner)"    -> (a, b) lexicographic minimum, stored inverted
 // ------------------------------------------------------------------------------------------------------------
-constexpr unsigned long long KEY_VALID = 1ull << 63;
-__device__ __forceinline__ unsigned long long key3(unsigned int a, unsigned int b, unsigned int c) {
-    return KEY_VALID | ((unsigned long long)a << 42) | ((unsigned long long)b << 21) | (unsigned long long)c;
-}
-constexpr unsigned int M21 = (1u << 21) - 1u;
+}  // namespace linon
+#include "outline_keys.cuh"
+namespace linon {
 
 __global__ void __launch_bounds__(256) outline_search_kernel(int W, int H, const float* __restrict__ exponents,
                                                              unsigned long long* __restrict__ keys) {
@@ -155,14 +153,7 @@ __global__ void __launch_bounds__(256) outline_search_kernel(int W, int H, const
         const unsigned int y = (unsigned int)(i / W), x = (unsigned int)(i - (size_t)y * W);
         const unsigned int uw = (unsigned int)W, uh = (unsigned int)H;
         unsigned long long k[8];
-        k[0] = key3((uw - x) + y, x, y);                   // bottom left   :385-394
-        k[1] = key3(0, M21 - (uh - 1 - y), M21 - x);       // bottom middle :395-404 (rows from the bottom)
-        k[2] = key3(x + y, x, y);                          // bottom right  :405-414
-        k[3] = key3(0, M21 - (uw - 1 - x), M21 - y);       // middle right  :415-424
-        k[4] = key3(x + (uh - y), x, y);                   // top right     :425-434
-        k[5] = key3(0, M21 - y, M21 - x);                  // top middle    :435-444
-        k[6] = key3((uw - x) + (uh - y), x, y);            // top left      :445-454
-        k[7] = key3(0, M21 - x, M21 - y);                  // middle left   :455-464
+        outline_keys(x, y, uw, uh, k);
 #pragma unroll
         for (int j = 0; j < 8; ++j) best[j] = best[j] > k[j] ? best[j] : k[j];
     }
@@ -192,18 +183,7 @@ __global__ void outline_finalize_kernel(int W, int H, const unsigned long long* 
     if (j >= 8) return;
     const unsigned long long k = keys[j];
     float px = 0.0f, py = 0.0f;
-    if (k & KEY_VALID) {
-        const unsigned int b = (unsigned int)(k >> 21) & M21, c = (unsigned int)k & M21;
-        unsigned int x, y;
-        switch (j) {
-            case 1: y = (unsigned int)H - 1 - (M21 - b); x = M21 - c; break;
-            case 3: x = (unsigned int)W - 1 - (M21 - b); y = M21 - c; break;
-            case 5: y = M21 - b; x = M21 - c; break;
-            case 7: x = M21 - b; y = M21 - c; break;
-            default: x = b; y = c; break;
-        }
-        px = (float)x; py = (float)y;
-    }
+    outline_decode(j, k, W, H, px, py);
     const float width = (float)W, height = (float)H;
     pos16[2 * j] = px / (width - 1.0f);
     pos16[2 * j + 1] = (height - 1.0f - py) / (height - 1.0f);
