@@ -124,3 +124,20 @@ def test_obj_loader_follows_the_drop_path(product_lib):
         load_obj("v 0 0 0\nf 1 2 3\n")                                  # index past the vertex list
     with pytest.raises(LinonError):
         load_obj("v 0 0 0\nv 1 0 0\n")                                  # no faces
+
+
+def test_python_constants_equal_the_headers_enumerators():
+    """Every LINON_OPT_* / LINON_RENDER_* / LINON_BUF_* enumerator of include/linon_b200.h that the ctypes binding names has
+    the header's value (the binding is written by hand)."""
+    _capi = capi
+    text = open(os.path.join(ROOT, "include", "linon_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    header = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"\bLINON_([A-Z0-9_]+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", text)}
+    checked = 0
+    for name, value in vars(_capi).items():
+        if name.startswith(("OPT_", "RENDER_", "BUF_")) and isinstance(value, int):
+            assert name in header, f"{name} is not an enumerator of the header"
+            assert header[name] == value, (name, header[name], value)
+            checked += 1
+    assert checked >= 25
+    assert {k for k in header if k.startswith("OPT_")} <= {k for k in vars(_capi)}, "an option of the header has no binding"
