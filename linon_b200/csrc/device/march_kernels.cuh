@@ -1501,8 +1501,26 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
     r.h = 0.001f;
     const float h = 0.001f;
     const float4 colour = make_float4(c_sample_colors[k][0], c_sample_colors[k][1], c_sample_colors[k][2], 0.5f);
+#if LINON_QUIET_ZONE && LINON_FW_ONE
+    // LINON_QUIET_ZONE (opt-in): outside the body's zone of influence the Runge-Kutta velocity is the direction itself, so the
+    // ray asks once how many steps it stays outside (quiet_steps: exact entry of the straight line into the zone) and takes
+    // them as straight steps - every one of the 5000 steps is still executed and every 50th still sampled.  Per lane, no
+    // collective: only lanes 0..7 are alive here.  The serial chain of a sample ray is what a small frame waits for.
+    int quiet_left = 0;
+#endif
     for (int i = 0; i < 5000; ++i) {
+#if LINON_QUIET_ZONE && LINON_FW_ONE
+        if (quiet_left == 0) quiet_left = min(LinonField<float>::quiet_steps(r.p, r.dir, h), 5000);
+        vec3f v;
+        if (quiet_left > 0) {
+            v = r.dir;
+            --quiet_left;
+        } else {
+            v = rk4_velocity(r, h, st, cam);
+        }
+#else
         const vec3f v = rk4_velocity(r, h, st, cam);
+#endif
 #if LINON_FW_ONE
         r.dir = v;
 #else

@@ -416,3 +416,27 @@ def test_quiet_zone_needs_a_fused_mirage_body(product_lib):
     # a user-edited body runs the generic translation, which has no quiet_steps: the macro is switched off in the module
     generic = module_text(sig + " ", capi.RENDER_ENHANCE, capi.MATH_FAST, 1)
     assert "LINON_HAS_QUIET_ZONE" not in generic.split("march_kernels.cuh", 1)[0].replace("defined(LINON_HAS_QUIET_ZONE)", "")
+
+
+@pytest.mark.parametrize("fn", [PredefinedFunction.MirageSpherical, PredefinedFunction.MiragePlane,
+                                PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.MiragePlaneSigmoid])
+def test_emulated_sample_rays_with_the_quiet_zone(product_lib, oracle, fn):
+    """linon_sample_rays with LINON_OPT_QUIET_ZONE: the eight rays take straight steps outside the body's zone of influence.
+    Same 800 samples as the oracle within the spread of the production build, and no farther from the oracle than twice
+    what the same build without the option is (max over the eight rays)."""
+    W, H = 64, 48
+    verts, faces, cam = _frame_inputs(W, H)
+    for mouse in ((0.5, 0.6), (0.36, 0.55), (0.05, 0.95)):  # start-up click, the mirage rim, a corner far from the body
+        st = dict(SETTINGS, mouse_x=mouse[0], mouse_y=mouse[1])
+        pos = oracle.sample_positions(cam, st, W, H)
+        ref = np.asarray(oracle.sample_rays(cam, st, int(fn), W, H, pos), np.float32).reshape(800, 8)
+        plain = emu.march(emu.build(fn.to_code(), capi.RENDER_ADAPTIVE_OFF, capi.MATH_FAST), verts, faces, cam, st, W, H,
+                          sample_pos=pos)["ray_samples"]
+        quiet = emu.march(emu.build(fn.to_code(), capi.RENDER_ADAPTIVE_OFF, capi.MATH_FAST, quiet_zone=1), verts, faces, cam, st,
+                          W, H, sample_pos=pos)["ray_samples"]
+        # rays through the body amplify rounding differences (the plain production build is up to 3e-3 from the oracle here)
+        assert np.allclose(quiet, ref, rtol=0, atol=5e-3)
+        assert np.array_equal(quiet[:, 3:], ref[:, 3:])  # colours and the 0.5 alpha
+        err_q = np.abs(quiet[:, :3].astype(np.float64) - ref[:, :3]).max()
+        err_p = np.abs(plain[:, :3].astype(np.float64) - ref[:, :3]).max()
+        assert err_q <= max(2.0 * err_p, 2e-5), (err_q, err_p)
