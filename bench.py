@@ -248,12 +248,14 @@ def run_quiet_zone_probe(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     frames = 3
 
+    sample_rays_ms = {}  # the sample-ray kernel (second stream) takes the same option
+
     def measure(quiet):
         mv.set_option(capi.OPT_QUIET_ZONE, quiet)
         for _ in range(2):
             mv.render_flags(capi.RENDER_ENHANCE)
             mv.sync()
-        frame_ms, march_ms = [], []
+        frame_ms, march_ms, sample_ms = [], [], []
         for _ in range(frames):
             flush.fill_(1)
             torch.cuda.synchronize()
@@ -265,7 +267,9 @@ def run_quiet_zone_probe(args):
             torch.cuda.synchronize()
             frame_ms.append(e0.elapsed_time(e1))
             march_ms.append(mv.timings().march_ms)
+            sample_ms.append(mv.timings().sample_rays_ms)
         c = mv.counters()
+        sample_rays_ms[quiet] = float(np.mean(sample_ms))
         return float(np.mean(frame_ms)), float(np.mean(march_ms)), c, int(mv.debug_profile()[15])
 
     def agreement(c):
@@ -299,6 +303,7 @@ def run_quiet_zone_probe(args):
         counters=dict(accepted=int(c.accepted_steps), quiet_steps=quiet, quiet_fraction=quiet / max(int(c.accepted_steps), 1),
                       prehit=int(c.prehit_steps), culling_checks=int(c.culling_checks), face_tests=int(c.face_tests)),
         executed_tflops=flops / (m_ms * 1e-3) / 1e12,
+        sample_rays_ms=dict(default=sample_rays_ms.get(0), quiet_zone=sample_rays_ms.get(1)),
         vs_default_path=agreement(c),
         note="LINON_OPT_QUIET_ZONE = 1 (opt-in, off in the headline numbers of this line): fixed-step frames of a predefined mirage "
              "body take straight steps while the whole warp is outside the body's zone of influence, where the reference's own "

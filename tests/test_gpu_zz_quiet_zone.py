@@ -182,3 +182,23 @@ def test_direct_overlay_kernel_equals_the_staged_one_bit_for_bit(product_lib, or
         mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
         mv.sync()
         assert np.array_equal(mv.texture(), raycast) and np.array_equal(mv.exponents(), ex)
+
+
+@pytest.mark.parametrize("fn", MIRAGES)
+def test_quiet_zone_sample_rays_stay_on_the_default_paths(view, scene, fn):
+    """linon_sample_rays takes the same option (per-lane straight steps outside the zone): the 800 samples of a fixed-step
+    frame stay on the default build's paths (rays through the body amplify rounding differences: 5e-3 absolute, the spread
+    the emulation shows between production builds and the oracle), colours and alphas are identical, and it is not slower."""
+    verts, faces, center = scene
+    view.reload_shader(fn.to_code())
+    view.update_settings(make_settings(overlay_mode=0))
+    view.render_flags(capi.RENDER_ADAPTIVE_OFF)
+    view.sync()
+    quiet, quiet_ms = view.ray_samples().copy(), view.timings().sample_rays_ms
+    view.set_option(capi.OPT_QUIET_ZONE, 0)
+    view.render_flags(capi.RENDER_ADAPTIVE_OFF)
+    view.sync()
+    plain, plain_ms = view.ray_samples().copy(), view.timings().sample_rays_ms
+    assert np.allclose(quiet[:, :3], plain[:, :3], rtol=0, atol=5e-3)
+    assert np.array_equal(quiet[:, 3:], plain[:, 3:])
+    assert quiet_ms <= plain_ms * 1.05
