@@ -112,3 +112,14 @@ def test_direct_overlay_mode_0_copies_and_leaves_the_exponents_alone(emu_overlay
     st = dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=0, central_difference_delta=2, lyapunov_scaling=50.0)
     ref_final, ref_ex = oracle.overlay(raycast, ep, st, exponents=before)
     assert np.array_equal(final, ref_final) and _same_bits(ex, ref_ex)
+
+
+def test_direct_overlay_at_the_c3_frame_size(emu_overlay, oracle):
+    """BASELINE config 3's frame size (3840x2160, delta 1, scaling 50): 16 200 CTAs of the launcher's grid, bit-identical."""
+    W, H = 3840, 2160
+    raycast, ep = _field(W, H, seed=42)
+    st = dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0)
+    ref_final, ref_ex = oracle.overlay(raycast, ep, st)
+    final, ex = emu_overlay(raycast, ep, 1, 1, 50.0)
+    assert np.array_equal(final, ref_final) and _same_bits(ex, ref_ex)
+    assert (ref_ex >= 0.8).mean() > 0.01
