@@ -1,6 +1,7 @@
-"""The direct overlay kernel (LINON_OPT_OVERLAY_KERNEL = 1, csrc/device/overlay_direct.cuh) on the host: its per-thread body
-is compiled by g++ (tests/emu/overlay_driver.cpp) and run over the launcher's grid, then compared BIT FOR BIT with the
-oracle's overlay (src/overlay.wgsl:99-146) - final colours, exponents, untouched border, mode 0 copy - on ragged frame
+"""Both overlay kernels on the host - the measured default (overlay_kernel, static_kernels.cu: shared-memory stage, one
+barrier) and the opt-in direct variant (LINON_OPT_OVERLAY_KERNEL = 1, csrc/device/overlay_direct.cuh): the device text is
+compiled by g++ (tests/emu/overlay_staged_driver.cpp, overlay_driver.cpp) and run over the launcher's grid, then compared BIT
+FOR BIT with the oracle's overlay (src/overlay.wgsl:99-146) - final colours, exponents, untouched border, mode 0 copy - on ragged frame
 sizes, every delta of the GUI slider, and endpoint fields with smooth, chaotic, constant, NaN and infinite regions."""
 import ctypes as C
 import hashlib
@@ -13,22 +14,49 @@ import pytest
 
 from conftest import ROOT
 
-_SRC = [os.path.join(ROOT, "tests", "emu", "overlay_driver.cpp"),
-        os.path.join(ROOT, "linon_b200", "csrc", "device", "overlay_direct.cuh")]
+_DEVICE = os.path.join(ROOT, "linon_b200", "csrc", "device")
+_EMU = os.path.join(ROOT, "tests", "emu")
 
 
-@pytest.fixture(scope="module")
-def emu_overlay():
-    key = hashlib.sha1(b"".join(open(p, "rb").read() for p in _SRC)).hexdigest()[:16]
+def _staged_kernel_text():
+    """overlay_kernel as static_kernels.cu has it: from its tile constants to the end of the kernel."""
+    s = open(os.path.join(_DEVICE, "static_kernels.cu")).read()
+    a, b = s.index("constexpr int OV_TX = 32;"), s.index('}  // namespace linon\n#include "overlay_direct.cuh"')
+    text = s[a:b]
+    assert "__global__" in text and "overlay_kernel(" in text and text.count("__syncthreads()") == 1
+    return text
+
+
+def _build(kind):
     cache = os.path.join(tempfile.gettempdir(), "linon_emu_cache")
     os.makedirs(cache, exist_ok=True)
-    so = os.path.join(cache, f"libovd_{key}.so")
+    if kind == "direct":
+        driver, extra = os.path.join(_EMU, "overlay_driver.cpp"), open(os.path.join(_DEVICE, "overlay_direct.cuh"), "rb").read()
+        flags = ["-fopenmp", "-I", _DEVICE]
+    else:
+        driver, extra = os.path.join(_EMU, "overlay_staged_driver.cpp"), _staged_kernel_text().encode()
+        flags = []
+    key = hashlib.sha1(open(driver, "rb").read() + extra).hexdigest()[:16]
+    so = os.path.join(cache, f"libov_{kind}_{key}.so")
     if not os.path.exists(so):
+        if kind == "staged":
+            inc = os.path.join(cache, f"ov_staged_{key}.inc")
+            with open(inc, "wb") as f:
+                f.write(extra)
+            flags = [f'-DLINON_OV_TEXT="{inc}"']
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w",
-                        "-I", os.path.dirname(_SRC[1]), _SRC[0], "-o", so + ".tmp"], check=True)
+        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", *flags, driver, "-o", so + ".tmp"],
+                       check=True)
         os.replace(so + ".tmp", so)
-    lib = C.CDLL(so)
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module", params=["direct", "staged"])
+def emu_overlay(request):
+    """direct: overlay_direct_kernel's per-thread body (opt-in variant).  staged: the measured default overlay_kernel, its text
+    cut out of static_kernels.cu and run CTA by CTA in two passes around its single barrier (tests/emu/overlay_staged_driver.cpp)."""
+    lib = _build(request.param)
+    entry = lib.emu_overlay_direct if request.param == "direct" else lib.emu_overlay_staged
 
     def run(raycast, endpoint, mode, delta, scaling, exponents=None):
         H, W = raycast.shape[:2]
@@ -36,8 +64,8 @@ def emu_overlay():
         endpoint = np.ascontiguousarray(endpoint, np.float32)
         final = np.full_like(raycast, 0xAB)  # every pixel must be written
         ex = np.zeros((H, W), np.float32) if exponents is None else np.array(exponents, np.float32, copy=True)
-        lib.emu_overlay_direct(W, H, int(mode), int(delta), C.c_float(scaling), C.c_void_p(raycast.ctypes.data),
-                               C.c_void_p(endpoint.ctypes.data), C.c_void_p(final.ctypes.data), C.c_void_p(ex.ctypes.data))
+        entry(W, H, int(mode), int(delta), C.c_float(scaling), C.c_void_p(raycast.ctypes.data),
+              C.c_void_p(endpoint.ctypes.data), C.c_void_p(final.ctypes.data), C.c_void_p(ex.ctypes.data))
         return final, ex
 
     return run
@@ -62,12 +90,15 @@ def _field(W, H, seed):
 
 
 def _same_bits(a, b):
-    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+    """Same 32-bit words; two NaNs count as equal whatever their sign / payload (x86 keeps the first operand's, the device
+    writes its canonical NaN - neither is part of the reference's definition)."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
 
 
 @pytest.mark.parametrize("delta", [1, 2, 3, 5, 10])
 @pytest.mark.parametrize("size", [(200, 150), (97, 33), (64, 48)])
-def test_direct_overlay_is_the_oracles_overlay_bit_for_bit(emu_overlay, oracle, delta, size):
+def test_overlay_kernels_are_the_oracles_overlay_bit_for_bit(emu_overlay, oracle, delta, size):
     W, H = size
     raycast, ep = _field(W, H, seed=delta * 1000 + W)
     st = dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0)
@@ -82,7 +113,7 @@ def test_direct_overlay_is_the_oracles_overlay_bit_for_bit(emu_overlay, oracle, 
 
 
 @pytest.mark.parametrize("scaling", [0.0, 7.5, 500.0])
-def test_direct_overlay_scaling_values(emu_overlay, oracle, scaling):
+def test_overlay_kernels_scaling_values(emu_overlay, oracle, scaling):
     raycast, ep = _field(120, 90, seed=3)
     st = dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=1, central_difference_delta=1, lyapunov_scaling=scaling)
     ref_final, ref_ex = oracle.overlay(raycast, ep, st)
@@ -91,7 +122,7 @@ def test_direct_overlay_scaling_values(emu_overlay, oracle, scaling):
 
 
 @pytest.mark.parametrize("size", [(1, 1), (3, 2), (4, 4), (5, 5), (33, 17), (40, 41)])
-def test_direct_overlay_frames_smaller_than_the_border(emu_overlay, oracle, size):
+def test_overlay_kernels_frames_smaller_than_the_border(emu_overlay, oracle, size):
     """Frames in which no or few pixels are inner (W, H <= 4 delta): every tap stays inside the image."""
     W, H = size
     rng = np.random.default_rng(W * 100 + H)
@@ -104,7 +135,7 @@ def test_direct_overlay_frames_smaller_than_the_border(emu_overlay, oracle, size
         assert np.array_equal(final, ref_final) and _same_bits(ex, ref_ex)
 
 
-def test_direct_overlay_mode_0_copies_and_leaves_the_exponents_alone(emu_overlay, oracle):
+def test_overlay_kernels_mode_0_copies_and_leaves_the_exponents_alone(emu_overlay, oracle):
     raycast, ep = _field(130, 70, seed=9)
     before = np.random.default_rng(1).random((70, 130)).astype(np.float32)
     final, ex = emu_overlay(raycast, ep, 0, 2, 50.0, exponents=before)
@@ -114,7 +145,7 @@ def test_direct_overlay_mode_0_copies_and_leaves_the_exponents_alone(emu_overlay
     assert np.array_equal(final, ref_final) and _same_bits(ex, ref_ex)
 
 
-def test_direct_overlay_at_the_c3_frame_size(emu_overlay, oracle):
+def test_overlay_kernels_at_the_c3_frame_size(emu_overlay, oracle):
     """BASELINE config 3's frame size (3840x2160, delta 1, scaling 50): 16 200 CTAs of the launcher's grid, bit-identical."""
     W, H = 3840, 2160
     raycast, ep = _field(W, H, seed=42)
