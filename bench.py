@@ -2,18 +2,32 @@
 """bench.py — headline benchmark of the linon ray-march path on B200 (contract: see DESIGN.md "Measurement").
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (CPU port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own WGSL on the host cores
 
 One "step" = one frame of the hot path: [click positions] -> march (+ 8 sample rays on a second stream) -> Lyapunov
-overlay.  N = 1 runs BASELINE.json configs[2]: 3840x2160, Enhance step size (h = 0.001, 5001 RK4 steps per ray),
+overlay.  N = 1 runs BASELINE.json configs[2] (C3): 3840x2160, Enhance step size (h = 0.001, 5001 RK4 steps per ray),
 overlay on, the application's default field function (MirageSphericalSigmoid), default camera / mesh / settings.
 N > 1 is weak scaling of the same frame: N times the pixels over the same field of view (round(3840 sqrt N) x
-round(2160 sqrt N), so the per-ray work mix is unchanged), rows cut into blocks dealt round-robin to the ranks, one
-grouped NCCL exchange of the RGBA / endpoint / hit-id row blocks to rank 0, overlay on rank 0.
+round(2160 sqrt N), so the per-ray work mix is unchanged), rows cut into blocks dealt round-robin to the ranks; the
+row blocks reach rank 0 either by peer stores during the march or by one grouped NCCL exchange after it, overlay on
+rank 0.  Every N also renders BASELINE.json configs[4]'s frame (C5: 8192x8192, Enhance) sharded over the same ranks:
+`c5_strong` is the fixed-size record a strong-scaling curve is read from.
 
 Prints ONE JSON line (rank 0).  value = Mrays/s of the whole job (rays of all ranks / max-over-ranks device time);
-e2e = the same through the public MainView API with host buffers (camera+settings upload, final image read back into
+e2e = the same through the public MainView API with host buffers (camera + settings upload, final image read back into
 pinned memory) inside the timed region.
+
+The N = 1 line also carries, from the same process and the same frame:
+  parity     the GPU frame graded against the oracle on sampled rows of the FULL C3 frame (oracle/sampled_rows.py: bands
+             of three rows, centre rows graded, high-Lyapunov pixels from the oracle's own endpoints excluded and
+             counted, the excluded fraction capped) - for the shipped path, for the round-1 path (quiet zone off) and
+             for the generic translation of the same WGSL text (LINON_OPT_SPECIALIZE = 0); the oracle itself is
+             compared bit for bit with the reference's transpiled WGSL (oracle/_ref) on those rows
+  variants   frame times of those two other paths beside the headline
+  configs    BASELINE.json configs[0], [1], [3] (C1, C2 over the nine predefined functions, C4): kernel times, the
+             kernel's own step counters and the same sampled-row parity (child process)
+The oracle is the CHECKER of frames the CUDA path produced and, in `cpu_baseline` / `--impl reference`, the CPU arm;
+nothing it computes feeds the product path.
 """
 from __future__ import annotations
 
@@ -31,7 +45,11 @@ sys.path.insert(0, ROOT)
 
 FN_ID = 3  # MirageSphericalSigmoid: the function the application starts with (src/main_view.rs:100)
 BASE_W, BASE_H = 3840, 2160
+C5_W, C5_H = 8192, 8192
 ROWS_PER_BLOCK = 32
+STEPS_PER_RAY = 5001  # h_initial = 0.001: the loop of src/main_view.wgsl:244 runs 5001 times; adaptive sampling cannot trigger
+MARCH_PROFILE = os.path.join(ROOT, "profiles", "r2_march_c3.json")
+OVERLAY_PROFILE = os.path.join(ROOT, "profiles", "r2_overlay_c3.json")
 
 
 def workload_size(n_gpus: int):
@@ -43,7 +61,14 @@ def workload_name(n_gpus: int, w: int, h: int) -> str:
     base = "C3: Cornell box, MirageSphericalSigmoid, Enhance h=0.001 (5001 RK4 steps/ray), Lyapunov overlay delta=1 scaling=50"
     if n_gpus == 1:
         return f"{base}, {w}x{h}, 1xB200"
-    return f"{base}, weak-scaled to {w}x{h} ({n_gpus}x the pixels, same field of view), {ROWS_PER_BLOCK}-row blocks round-robin over {n_gpus} GPUs + gather to rank 0"
+    return f"{base}, weak-scaled to {w}x{h} ({n_gpus}x the pixels, same field of view), {ROWS_PER_BLOCK}-row blocks round-robin over {n_gpus} GPUs, frame assembled on rank 0"
+
+
+def workload_config(n_gpus: int, w: int, h: int) -> dict:
+    """The `config` object: names the WORKLOAD only, identical in both arms (ours / --impl reference)."""
+    return dict(workload=workload_name(n_gpus, w, h), width=w, height=h, rays_per_step=w * h,
+                rk4_steps_per_step=w * h * STEPS_PER_RAY, field_function="MirageSphericalSigmoid", h_initial=0.001,
+                overlay="mode 1, delta 1, scaling 50")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -61,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -94,27 +119,29 @@ class ClockSampler:
                     power_w_max=max(power) if power else None, reasons=sorted(reasons), samples=len(sm))
 
 
-def ncu_profile():
-    """Executed FP32 FLOPs per RK4 step and issue-slot utilisation of the march kernel from the committed ncu summary."""
-    path = os.path.join(ROOT, "profiles", "r1_march_c3.json")
+def static_source_hash() -> str:
+    """Identity of the ahead-of-time kernels (overlay, outline search, click positions): sha256 of their sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for rel in ("static_kernels.cu", "overlay_direct.cuh", "outline_keys.cuh"):
+        with open(os.path.join(ROOT, "linon_b200", "csrc", "device", rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def committed_profile(path: str, kernel_substring: str, identity: str | None, key: str = "cubin_hash"):
+    """A committed ncu summary (tools/ncu_summary.py) is evidence about ONE binary: it names what it profiled - the FNV-1a
+    hash of the NVRTC cubin (`cubin_hash`, march kernels) or the hash of the sources of the ahead-of-time kernels
+    (`source_hash`) - and is refused, with the reason, when the kernel running now is another one."""
     if not os.path.exists(path):
-        return None
+        return None, f"{os.path.relpath(path, ROOT)} not committed"
     for k in json.load(open(path)):
-        if k.get("kernel") == "linon_march_tiles" and k.get("fp32_flops_per_rk4_step"):
-            return k
-    return None
-
-
-def overlay_ncu_traffic(W, H):
-    """DRAM bytes per overlay launch from the committed ncu capture (profiles/r1_overlay_c3.json, taken at the C3 size);
-    None for any other frame size."""
-    path = os.path.join(ROOT, "profiles", "r1_overlay_c3.json")
-    if (W, H) != (3840, 2160) or not os.path.exists(path):
-        return None
-    for k in json.load(open(path)):
-        if "overlay_kernel" in str(k.get("kernel", "")) and k.get("dram_traffic_bytes"):
-            return float(k["dram_traffic_bytes"])
-    return None
+        if kernel_substring in str(k.get("kernel", "")):
+            if identity is not None and k.get(key) != identity:
+                return None, (f"{os.path.relpath(path, ROOT)} profiled {key} {k.get(key)}, the running kernel is "
+                              f"{identity}: stale capture refused")
+            return k, "ok"
+    return None, f"no {kernel_substring} entry in {os.path.relpath(path, ROOT)}"
 
 
 def measured_peaks():
@@ -124,12 +151,21 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), "fallback (B200_PROFILING.md)"
 
 
+def host_threads() -> int:
+    """Threads the CPU arm uses: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1, which would make
+    the OpenMP default one thread - the count is therefore always passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference():
     """The CPU implementation timed beside the GPU path.  oracle/_ref (the reference's own WGSL, transpiled mechanically
     to C++ by oracle/wgsl_ref and compiled with gcc; built where /root/reference is mounted, the .so travels) when it
     exists -> kind "reference"; otherwise the hand-written restatement oracle/linon_oracle.cpp -> kind "port".  The two
-    are bit-identical (tests/test_wgsl_reference_cpu.py)."""
+    are bit-identical (tests/test_wgsl_reference_cpu.py; re-checked on the sampled rows of every N = 1 run)."""
     from oracle import wgsl_reference as wr
     if wr.available():
         wr.build()
@@ -139,46 +175,54 @@ def cpu_reference():
     return co, "port"
 
 
-def oracle_sample(w: int, h: int, budget_s: float, threads: int = 0):
-    """Times the CPU implementation of the reference's path on a bounded sample of the same frame: every `stride`-th
-    row, full width (pixels are independent; cost is per ray), sized by a short calibration run to ~budget_s seconds."""
+def c3_inputs(w: int, h: int):
     from oracle import np_oracle as npo
-
-    impl, kind = cpu_reference()
     verts, faces, center = npo.default_scene()
     cam = npo.camera_uniform(npo.default_camera(center, w, h))
     st = dict(npo.default_settings(), overlay_mode=1)
-    cores = impl.num_threads() if threads <= 0 else threads
-    steps_per_ray = 5001  # h_initial = 0.001: the loop of src/main_view.wgsl:244 runs 5001 times, adaptive sampling cannot trigger (h <= 0.002)
+    return verts, faces, cam, st
+
+
+def oracle_sample(w: int, h: int, budget_s: float, threads: int = 0, keep_outputs: bool = False):
+    """Times the CPU implementation of the reference's path on a bounded sample of the same frame: evenly spaced full rows
+    (pixels are independent; cost is per ray), sized by a short calibration run to ~budget_s seconds.  The rows are the
+    centre rows of oracle/sampled_rows.band_centres, so the parity block can grade exactly these rows."""
+    from oracle import sampled_rows as sr
+
+    impl, kind = cpu_reference()
+    verts, faces, cam, st = c3_inputs(w, h)
+    cores = threads if threads > 0 else host_threads()
 
     def run(rows):
-        y_step = max(1, h // rows)
-        ys = range(y_step // 2, h, y_step)
+        centres, stride = sr.band_centres(h, rows)
         t0 = time.perf_counter()
-        out = impl.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, y_step // 2, h),
-                         y_step=y_step, n_threads=threads)
+        out = sr.march_bands(verts, faces, cam, st, FN_ID, w, h, centres, stride, h_initial=0.001, adaptive=True, delta=0,
+                             n_threads=cores, impl=impl)
         dt = time.perf_counter() - t0
-        rays = len(ys) * w
+        rays = len(centres) * w
         if "accepted" in out:  # the port counts its steps; the transpiled shader has no such output
-            assert int(out["accepted"].sum() + out["rejected"].sum()) == rays * steps_per_ray
-        return dt, rays, rays * steps_per_ray, len(ys)
+            assert int(out["accepted"].sum() + out["rejected"].sum()) == rays * STEPS_PER_RAY
+        return dt, rays, rays * STEPS_PER_RAY, centres, stride, out
 
     # calibration on a strided part of one row
     xs = max(1, w // (cores * 16))
     t0 = time.perf_counter()
     impl.march(verts, faces, cam, st, FN_ID, w, h, h_initial=0.001, adaptive=True, rect=(0, w, h // 2, h // 2 + 1),
-               x_step=xs, n_threads=threads)
+               x_step=xs, n_threads=cores)
     per_ray = (time.perf_counter() - t0) / len(range(0, w, xs))
-    rows = max(1, min(h, int(budget_s / (per_ray * w))))
-    t, rays, steps, rows = run(rows)
-    if t < 0.4 * budget_s and rows < h:
-        # the calibration (128 rays, thread start-up included) overestimates the cost per ray: size the sample from the
-        # rate just measured and time that one instead
-        t, rays, steps, rows = run(max(rows + 1, min(h, int(rows * 0.8 * budget_s / t))))
+    rows = max(1, min(h // 8, int(budget_s / (per_ray * w))))
+    t, rays, steps, centres, stride, out = run(rows)
+    if t < 0.4 * budget_s and len(centres) < h // 8:
+        # the calibration (a few rays per thread, thread start-up included) overestimates the cost per ray: size the sample
+        # from the rate just measured and time that one instead
+        t, rays, steps, centres, stride, out = run(max(len(centres) + 1, min(h // 8, int(len(centres) * 0.8 * budget_s / t))))
     what = ("the reference's main_view.wgsl + MirageSphericalSigmoid body transpiled to C++ (oracle/_ref), gcc -O2 -ffp-contract=off"
             if kind == "reference" else "hand-written C++ restatement of the reference WGSL (oracle/linon_oracle.cpp)")
-    return dict(seconds=t, rays=rays, steps=steps, rows=rows, cores=cores, kind=kind,
-                sample=f"{rows} full rows of the {w}x{h} frame, evenly spaced ({rays} rays, {steps} RK4 steps), {cores} OpenMP threads; {what}")
+    res = dict(seconds=t, rays=rays, steps=steps, rows=len(centres), cores=cores, kind=kind, centres=centres, stride=stride,
+               sample=f"{len(centres)} full rows of the {w}x{h} frame, evenly spaced ({rays} rays, {steps} RK4 steps), {cores} OpenMP threads; {what}")
+    if keep_outputs:
+        res["outputs"] = out
+    return res
 
 
 def run_reference(args):
@@ -186,29 +230,32 @@ def run_reference(args):
     be built or run in this image (no rustc/cargo, no Vulkan ICD / lavapipe); what runs is the reference's
     shader itself: main_view.wgsl with the MirageSphericalSigmoid body of functions.rs spliced in, transpiled
     mechanically to C++ and compiled with gcc (oracle/_ref, kind = "reference"; falls back to the hand-written port when
-    that library was never built), all host threads, on a bounded sample of the same frame per step."""
+    that library was never built), all host threads (counted from the affinity mask: torchrun's OMP_NUM_THREADS=1 is
+    not obeyed), on a bounded sample of the same frame per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     w, h = workload_size(args.gpus)
+    threads = host_threads()
     budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
-        oracle_sample(w, h, budget)
+        oracle_sample(w, h, budget, threads)
     tot_t = tot_rays = tot_steps = 0
     last = None
     for _ in range(args.steps):
-        last = oracle_sample(w, h, budget)
+        last = oracle_sample(w, h, budget, threads)
         tot_t += last["seconds"]; tot_rays += last["rays"]; tot_steps += last["steps"]
     mrays = tot_rays / tot_t / 1e6
     line = dict(impl="reference", metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=tot_t / args.steps * 1e3 * (w * h) / (tot_rays / args.steps),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 rk4_gsteps_per_s=tot_steps / tot_t / 1e9,
-                config=dict(workload=workload_name(args.gpus, w, h), width=w, height=h,
-                            note="ms_per_step is the sampled time scaled to the full frame (pixels are independent)"),
+                config=workload_config(args.gpus, w, h),
                 cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=last["cores"], kind=last["kind"], sample=last["sample"]),
                 e2e=dict(value=mrays, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                note="niklaskorz/linon's host is Rust+wgpu (no rustc/cargo/Vulkan in this image): its WGSL compute shader is run on the host cores through a mechanical WGSL->C++ transpile, not through wgpu on lavapipe")
+                note="ms_per_step is the sampled time scaled to the full frame (pixels are independent).  niklaskorz/linon's host is "
+                     "Rust+wgpu (no rustc/cargo/Vulkan in this image): its WGSL compute shader is run on the host cores through a "
+                     "mechanical WGSL->C++ transpile, not through wgpu on lavapipe")
     print(json.dumps(line))
     return 0
 
@@ -222,210 +269,222 @@ class _DevBuf:
                                              strides=None)
 
 
-def run_quiet_zone_probe(args):
-    """--probe-quiet-zone (child process of the N = 1 run): the C3 frame with the default path and with
-    LINON_OPT_QUIET_ZONE on (include/linon_b200.h) - march time of both from CUDA events on the library's stream, L2 flushed
-    between frames, and the two frames compared on the device (hit id, colour, endpoint; pixels the overlay marks as
-    high-Lyapunov excluded and counted, like the parity tests).  Prints one JSON object."""
+def frame_buffers(mv):
+    """The march outputs of the view's last frame on the host (hit id, colour, endpoint)."""
+    return dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
+
+
+def timed_frames(mv, flags, n, warm=1, flush=None):
+    """Mean frame time (CUDA events on the library's stream) and the kernel times of n frames after `warm` untimed ones."""
+    import numpy as np
+    import torch
+    stream = torch.cuda.ExternalStream(mv.stream())
+    for _ in range(warm):
+        mv.render_flags(flags)
+        mv.sync()
+    frame_ms, march_ms, overlay_ms, sample_ms = [], [], [], []
+    for _ in range(n):
+        if flush is not None:
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        mv.render_flags(flags)
+        e1.record(stream)
+        mv.sync()
+        torch.cuda.synchronize()
+        t = mv.timings()
+        frame_ms.append(e0.elapsed_time(e1)); march_ms.append(t.march_ms); overlay_ms.append(t.overlay_ms)
+        sample_ms.append(t.sample_rays_ms)
+    return dict(ms_per_step=float(np.mean(frame_ms)), march_ms=float(np.mean(march_ms)), overlay_ms=float(np.mean(overlay_ms)),
+                sample_rays_ms=float(np.mean(sample_ms)), frames=n)
+
+
+def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
+    """N = 1, after the timed loops: (i) the oracle on bands around the rows the cpu_baseline leg just computed with the
+    reference's transpiled WGSL; (ii) the frame of the shipped path, of the round-1 path (LINON_OPT_QUIET_ZONE = 0) and of
+    the generic translation (LINON_OPT_SPECIALIZE = 0), each rendered here on the device and graded against those rows."""
+    import numpy as np
+
+    from linon_b200 import _capi as capi
+    from oracle import cpu_oracle as co
+    from oracle import sampled_rows as sr
+
+    verts, faces, cam, st = c3_inputs(W, H)
+    threads = host_threads()
+    # bands: as many as the budget allows (3 rows per graded row), never more than the rows the cpu_baseline leg sampled
+    if cpu is not None:
+        rate = cpu["rays"] / cpu["seconds"]
+        n_bands = max(4, min(cpu["rows"], int(parity_seconds * rate / (3 * W))))
+        k = max(1, -(-cpu["rows"] // n_bands))
+        centres, stride = cpu["centres"][::k], cpu["stride"] * k
+    else:
+        centres, stride = sr.band_centres(H, 8)
+    t0 = time.perf_counter()
+    ref = sr.march_bands(verts, faces, cam, st, FN_ID, W, H, centres, stride, h_initial=0.001, adaptive=True, delta=1, n_threads=threads)
+    oracle_s = time.perf_counter() - t0
+    graded = sr.graded_mask(W, H, centres)
+    high = sr.high_lyapunov_on_centres(ref, W, H, centres, dict(st, central_difference_delta=1, lyapunov_scaling=50.0)) & graded
+    rf = dict(ref=ref, graded=graded, high_lyapunov=high, undecided=np.zeros_like(high), excluded=high, centres=centres, stride=stride)
+    pinned = None
+    if cpu is not None and cpu["kind"] == "reference" and "outputs" in cpu:
+        shader = cpu["outputs"]  # the reference's transpiled WGSL on the same rows (the timed cpu_baseline run itself)
+        pinned = bool(np.array_equal(shader["rgba8"][graded], ref["rgba8"][graded]) and
+                      np.array_equal(shader["endpoint"][graded].view(np.uint32), ref["endpoint"][graded].view(np.uint32)))
+    out = dict(
+        checker="oracle/linon_oracle.cpp (fp32 restatement of src/main_view.wgsl, hit ids per SURVEY F10) on bands of 3 rows; centre rows graded",
+        rows=len(centres), pixels=int(graded.sum()), oracle_seconds=round(oracle_s, 2), oracle_threads=threads,
+        oracle_equals_transpiled_reference_wgsl_on_these_rows=pinned,
+        hit_ids="compared per surface group (coplanar Cornell faces, SURVEY F11); raw agreement reported beside it",
+        max_excluded_fraction=0.02)
+    variants = {}
+    E = capi.RENDER_ENHANCE
+    shipped_quiet, shipped_spec = 1, 1
+
+    def one(name, quiet, spec, frames):
+        mv.set_option(capi.OPT_QUIET_ZONE, quiet)
+        mv.set_option(capi.OPT_SPECIALIZE, spec)
+        t = timed_frames(mv, E, frames, warm=1, flush=flush)
+        c = mv.counters()
+        assert int(c.accepted_steps) == W * H * STEPS_PER_RAY and int(c.rejected_steps) == 0, (name, c.accepted_steps)
+        m = sr.grade(frame_buffers(mv), rf, fixed_step=True, max_excluded_fraction=0.02)
+        t.update(mrays_s=W * H / (t["ms_per_step"] * 1e-3) / 1e6, cubin_hash=mv.march_cubin_hash(),
+                 quiet_steps=int(mv.debug_profile()[15]), culling_checks=int(c.culling_checks), face_tests=int(c.face_tests))
+        return t, m
+
+    try:
+        t, m = one("shipped", shipped_quiet, shipped_spec, 2)
+        out["shipped"] = m
+        t, m = one("quiet_zone_off", 0, 1, 2)
+        variants["quiet_zone_off"] = dict(t, note="LINON_OPT_QUIET_ZONE = 0: every step evaluates the field (the round-1 headline kernel)")
+        out["quiet_zone_off"] = m
+        t, m = one("generic_translation", 0, 0, 2)
+        variants["generic_translation"] = dict(t, note="LINON_OPT_SPECIALIZE = 0: the WGSL body through the generic translator, four field "
+                                                       "evaluations per step - the path of a user body no structural match recognises")
+        out["generic_translation"] = m
+    finally:
+        mv.set_option(capi.OPT_QUIET_ZONE, shipped_quiet)
+        mv.set_option(capi.OPT_SPECIALIZE, shipped_spec)
+    out["green"] = bool(out.get("shipped", {}).get("green")) and pinned is not False
+    return out, variants
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_configs_child(args):
+    """--configs-child: BASELINE.json configs[0], [1], [3] on the device (C1; C2 = the nine predefined functions at
+    1920x1080; C4 = the outline workload), each with kernel times, the kernel's own counters and sampled-row parity
+    against the oracle.  Prints one JSON object per config line, then {"done": true}."""
     import numpy as np
     import torch
 
     from linon_b200 import _capi as capi
-    from linon_b200 import flops as fl
     from linon_b200.main_view import MainView, PredefinedFunction, default_scene, make_settings
+    from oracle import np_oracle as npo
+    from oracle import sampled_rows as sr
 
-    dev = args.device
-    torch.cuda.set_device(dev)
-    W, H = workload_size(1)
+    torch.cuda.set_device(args.device)
     verts, faces, center = default_scene()
-    mv = MainView(verts, faces, center, W, H, discrete_gpu=True, device=dev)
-    mv.reload_shader(PredefinedFunction(FN_ID).to_code())
-    mv.update_settings(make_settings(overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0))
-    stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", dev))
-    ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")
-    rc = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_RAYCAST_RGBA8), (H, W, 4), "|u1"), device="cuda")
-    hid = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_HIT_ID_I32), (H, W), "<i4"), device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    frames = 3
+    threads = host_threads()
+    PRE = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
 
-    sample_rays_ms = {}  # the sample-ray kernel (second stream) takes the same option
-
-    def measure(quiet):
-        mv.set_option(capi.OPT_QUIET_ZONE, quiet)
-        for _ in range(2):
-            mv.render_flags(capi.RENDER_ENHANCE)
+    def measure(mv, flags, reps=3):
+        best = None
+        for _ in range(reps + 1):
+            mv.render_flags(flags)
             mv.sync()
-        frame_ms, march_ms, sample_ms = [], [], []
-        for _ in range(frames):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            mv.render_flags(capi.RENDER_ENHANCE)
-            e1.record(stream)
-            mv.sync()
-            torch.cuda.synchronize()
-            frame_ms.append(e0.elapsed_time(e1))
-            march_ms.append(mv.timings().march_ms)
-            sample_ms.append(mv.timings().sample_rays_ms)
+            t = mv.timings()
+            if best is None or t.march_ms < best.march_ms:
+                best = t
         c = mv.counters()
-        sample_rays_ms[quiet] = float(np.mean(sample_ms))
-        return float(np.mean(frame_ms)), float(np.mean(march_ms)), c, int(mv.debug_profile()[15])
+        W, H = mv.size
+        steps = c.accepted_steps + c.rejected_steps
+        return dict(march_ms=round(best.march_ms, 4), overlay_ms=round(best.overlay_ms, 4), sample_rays_ms=round(best.sample_rays_ms, 4),
+                    outline_search_ms=round(best.outline_search_ms, 4), mrays_s=round(W * H / best.march_ms / 1e3, 2),
+                    gsteps_s=round(steps / best.march_ms / 1e6, 2), regs=best.march_regs,
+                    accepted_per_ray=round(c.accepted_steps / c.rays, 2), rejected_per_ray=round(c.rejected_steps / c.rays, 3),
+                    prehit_fraction=round(c.prehit_steps / max(c.accepted_steps, 1), 4),
+                    face_tests_per_prehit_step=round(c.face_tests / max(c.prehit_steps, 1), 4),
+                    quiet_steps_fraction=round(int(mv.debug_profile()[15]) / max(c.accepted_steps, 1), 4))
 
-    def agreement(c):
-        same_hit = hid == ref["hid"]
-        use = ~excl
-        matched = use & same_hit
-        n_use, n_matched = int(use.sum()), max(int(matched.sum()), 1)
-        err = torch.linalg.vector_norm(ep[..., :3].double() - ref["ep"][..., :3].double(), dim=-1)
-        rel = err / torch.clamp(torch.linalg.vector_norm(ref["ep"][..., :3].double(), dim=-1), min=1e-12)
-        cdiff = (rc.to(torch.int16) - ref["rc"].to(torch.int16)).abs().amax(dim=-1)
-        agree = dict(pixels=W * H, excluded_high_lyapunov=int(excl.sum()), compared=n_use,
-                     hit_id_equal=float((same_hit & use).sum()) / max(n_use, 1),
-                     colour_within_1=float(((cdiff <= 1) & matched).sum()) / n_matched,
-                     endpoint_within_1e3=float(((rel <= 1e-3) & matched).sum()) / n_matched,
-                     endpoint_max_rel=float(rel[matched].max()) if int(matched.sum()) else 0.0,
-                     hit_id_equal_all_pixels=float(same_hit.sum()) / (W * H))
-        agree["meets_north_star"] = bool(agree["hit_id_equal"] >= 0.999 and agree["colour_within_1"] >= 0.999 and
-                                         agree["endpoint_within_1e3"] >= 0.999 and int(c.accepted_steps) == W * H * 5001)
-        return agree
+    def graded(mv, fn, W, H, adaptive, n_bands, st=None):
+        cam = npo.camera_uniform(npo.default_camera(center, W, H))
+        std = dict(npo.default_settings()) if st is None else st
+        rf = sr.reference_frame(verts, faces, cam, std, int(fn), W, H, n_bands, h_initial=0.1, adaptive=adaptive, n_threads=threads)
+        m = sr.grade(dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture()), rf,
+                     fixed_step=not adaptive, max_excluded_fraction=sr.excluded_cap(int(fn), adaptive))
+        return {k: m[k] for k in ("rows", "compared", "hit_group_agree", "hit_raw_agree", "colour_within_1", "endpoint_within_1e3",
+                                  "excluded_high_lyapunov", "excluded_undecided_by_the_oracle", "excluded_fraction", "green")}
 
-    d_ms, d_march, d_c, _ = measure(0)
-    ref = dict(ep=ep.clone(), rc=rc.clone(), hid=hid.clone())
-    excl = torch.as_tensor(mv.exponents().reshape(H, W), device="cuda") >= 0.8
-    ms, m_ms, c, quiet = measure(1)
-    flops = fl.fused_march_flops(c, FN_ID, field_weight_is_one=True, quiet_steps=quiet)
-    # the main result goes out first: whatever the extra measurements below do, the parent already has this line
-    print(json.dumps(dict(
-        ms_per_step=ms, march_ms=m_ms, value=W * H / (ms * 1e-3) / 1e6, unit="Mrays/s",
-        rk4_gsteps_per_s=c.accepted_steps / (ms * 1e-3) / 1e9, frames=frames,
-        default_path_same_process=dict(ms_per_step=d_ms, march_ms=d_march, culling_checks=int(d_c.culling_checks)),
-        counters=dict(accepted=int(c.accepted_steps), quiet_steps=quiet, quiet_fraction=quiet / max(int(c.accepted_steps), 1),
-                      prehit=int(c.prehit_steps), culling_checks=int(c.culling_checks), face_tests=int(c.face_tests)),
-        executed_tflops=flops / (m_ms * 1e-3) / 1e12,
-        sample_rays_ms=dict(default=sample_rays_ms.get(0), quiet_zone=sample_rays_ms.get(1)),
-        vs_default_path=agreement(c),
-        note="LINON_OPT_QUIET_ZONE = 1 (opt-in, off in the headline numbers of this line): fixed-step frames of a predefined mirage "
-             "body take straight steps while the whole warp is outside the body's zone of influence, where the reference's own "
-             "fp32 evaluation has eta == 1; every Runge-Kutta step is executed and counted")), flush=True)
+    def emit(**kw):
+        print(json.dumps(kw), flush=True)
 
-    # (0) the other opt-in kernel of the path: the direct overlay (LINON_OPT_OVERLAY_KERNEL = 1, no shared-memory stage) against
-    # the measured default on this very frame - time of the overlay launch alone, L2 flushed before each, results compared
-    try:
-        fin = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_FINAL_RGBA8), (H, W, 4), "|u1"), device="cuda")
-        exb = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_EXPONENTS_F32), (H, W), "<f4"), device="cuda")
-
-        def overlay_only(variant, reps=10):
-            mv.set_option(capi.OPT_OVERLAY_KERNEL, variant)
-            t = []
-            for i in range(reps + 3):
-                flush.fill_(1)
-                torch.cuda.synchronize()
-                mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
-                mv.sync()
-                if i >= 3:
-                    t.append(mv.timings().overlay_ms)
-            return float(np.mean(t)), float(np.min(t)), fin.clone(), exb.clone()
-
-        s_mean, s_min, s_fin, s_ex = overlay_only(0)
-        o_mean, o_min, o_fin, o_ex = overlay_only(1)
-        mv.set_option(capi.OPT_OVERLAY_KERNEL, 0)
-        hbm = measured_peaks()[0]["hbm_gbs"]
-        ob = fl.OVERLAY_BYTES[1] * W * H
-        print(json.dumps(dict(extra="overlay_direct", staged_ms=s_mean, staged_ms_min=s_min, direct_ms=o_mean, direct_ms_min=o_min,
-                              staged_gbs=ob / (s_mean * 1e-3) / 1e9, direct_gbs=ob / (o_mean * 1e-3) / 1e9,
-                              staged_frac_of_hbm_peak=ob / (s_mean * 1e-3) / 1e9 / hbm,
-                              direct_frac_of_hbm_peak=ob / (o_mean * 1e-3) / 1e9 / hbm, algorithmic_bytes_per_launch=ob,
-                              final_equal=bool(torch.equal(s_fin, o_fin)),
-                              exponents_bit_equal=bool(torch.equal(s_ex.view(torch.int32), o_ex.view(torch.int32))),
-                              note="LINON_OPT_OVERLAY_KERNEL = 1 (csrc/device/overlay_direct.cuh): four taps per pixel through the "
-                                   "read-only path instead of a staged tile; opt-in until this line has been seen")), flush=True)
-    except Exception as e:  # noqa: BLE001
-        print(json.dumps(dict(extra="overlay_direct", error=f"{type(e).__name__}: {e}"[:300])), flush=True)
-
-    # Extra measurements of the same opt-in path, each on its own line ({"extra": name, ...}); the parent files them under
-    # quiet_zone_probe[name].  (1) the tighter radius of the sigmoid profiles, same C3 frame against the same default frame.
-    try:
-        mv.set_option(capi.OPT_QUIET_RADIUS, 1500)
-        r_ms, r_march, r_c, r_quiet = measure(1)
-        print(json.dumps(dict(extra="radius_1500", ms_per_step=r_ms, march_ms=r_march, quiet_steps=r_quiet,
-                              quiet_fraction=r_quiet / max(int(r_c.accepted_steps), 1),
-                              culling_checks=int(r_c.culling_checks), vs_default_path=agreement(r_c),
-                              note="LINON_OPT_QUIET_RADIUS = 1500: zone radius 1.5 max_dist instead of where the fp32 sigmoid "
-                                   "saturates (1.92 max_dist)")), flush=True)
-        mv.set_option(capi.OPT_QUIET_RADIUS, 0)
-    except Exception as e:  # noqa: BLE001
-        print(json.dumps(dict(extra="radius_1500", error=f"{type(e).__name__}: {e}"[:300])), flush=True)
-    # (2) adaptive default-step frames (C1: 800x600, MirageSpherical) with option level 2 against level 0: march time, the
-    # kernel's own step counters, hit ids and colours (endpoints of adaptive frames are not comparable, SURVEY F20)
-    try:
-        W1, H1 = 800, 600
-        mv1 = MainView(verts, faces, center, W1, H1, discrete_gpu=True, device=dev)
-        mv1.reload_shader(PredefinedFunction(1).to_code())
-        mv1.update_settings(make_settings())
-        rc1 = torch.as_tensor(_DevBuf(mv1.device_ptr(capi.BUF_RAYCAST_RGBA8), (H1, W1, 4), "|u1"), device="cuda")
-        hid1 = torch.as_tensor(_DevBuf(mv1.device_ptr(capi.BUF_HIT_ID_I32), (H1, W1), "<i4"), device="cuda")
-
-        def c1(level):
-            mv1.set_option(capi.OPT_QUIET_ZONE, level)
-            times = []
-            for i in range(6):
-                mv1.render_flags(0)
-                mv1.sync()
-                if i >= 2:
-                    times.append(mv1.timings().march_ms)
-            k = mv1.counters()
-            return float(np.mean(times)), int(k.accepted_steps), int(k.rejected_steps), rc1.clone(), hid1.clone()
-
-        t0, a0, j0, rc_0, hid_0 = c1(0)
-        t2, a2, j2, rc_2, hid_2 = c1(2)
-        same = hid_0 == hid_2
-        cd = (rc_0.to(torch.int16) - rc_2.to(torch.int16)).abs().amax(dim=-1)
-        print(json.dumps(dict(extra="c1_adaptive_level2", width=W1, height=H1, function="MirageSpherical",
-                              march_ms_level0=t0, march_ms_level2=t2,
-                              steps_per_ray_level0=dict(accepted=a0 / (W1 * H1), rejected=j0 / (W1 * H1)),
-                              steps_per_ray_level2=dict(accepted=a2 / (W1 * H1), rejected=j2 / (W1 * H1)),
-                              hit_id_equal=float(same.sum()) / (W1 * H1),
-                              colour_within_1_where_hit_equal=float(((cd <= 1) & same).sum()) / max(int(same.sum()), 1))),
-              flush=True)
-    except Exception as e:  # noqa: BLE001
-        print(json.dumps(dict(extra="c1_adaptive_level2", error=f"{type(e).__name__}: {e}"[:300])), flush=True)
+    # C1: 800x600, first predefined function, default step size
+    with MainView(verts, faces, center, 800, 600, device=args.device) as mv:
+        fn = PredefinedFunction.MirageSpherical
+        mv.reload_shader(fn.to_code())
+        mv.update_settings(make_settings())
+        for name, flags, adaptive in (("adaptive on (as the application renders)", 0, True), ("adaptive off (51 steps)", capi.RENDER_ADAPTIVE_OFF, False)):
+            r = measure(mv, flags)
+            r["parity"] = graded(mv, fn, 800, 600, adaptive, 24)
+            emit(config="C1", size="800x600", function=fn.name, variant=name, **r)
+    # C2: 1920x1080, every predefined function
+    with MainView(verts, faces, center, 1920, 1080, device=args.device) as mv:
+        mv.update_settings(make_settings())
+        for fn in PRE:
+            mv.reload_shader(fn.to_code())
+            for name, flags, adaptive in (("adaptive on", 0, True), ("adaptive off", capi.RENDER_ADAPTIVE_OFF, False)):
+                r = measure(mv, flags)
+                r["parity"] = graded(mv, fn, 1920, 1080, adaptive, 8)
+                emit(config="C2", size="1920x1080", function=fn.name, variant=name, **r)
+        # C4: overlay + sample rays, click mode and outline mode, kernels timed separately
+        fn = PredefinedFunction.MirageSphericalSigmoid
+        mv.reload_shader(fn.to_code())
+        for mouse, label in (((0.5, 0.6), "click (0.5, 0.6)"), ((0.36, 0.55), "click on the mirage rim")):
+            mv.update_settings(make_settings(overlay_mode=1, mouse_pos=mouse))
+            emit(config="C4", size="1920x1080", function=fn.name, variant=label, **measure(mv, 0))
+        mv.update_settings(make_settings(overlay_mode=1))
+        r = measure(mv, capi.RENDER_OUTLINE)
+        emit(config="C4", size="1920x1080", function=fn.name, variant="outline mode (8 searches over exponents >= 0.8)",
+             sample_positions=np.asarray(mv.read(capi.BUF_SAMPLE_POS)).round(5).tolist(), **r)
+    emit(done=True)
     return 0
 
 
-def parse_probe_output(stdout, failure):
-    """First JSON line of the probe child = the main result; later {"extra": name, ...} lines are filed under their name."""
-    probe = None
-    for ln in (stdout or "").splitlines():
-        if not ln.startswith("{"):
-            continue
-        try:
-            obj = json.loads(ln)
-        except ValueError:
-            continue
-        if probe is None and "extra" not in obj:
-            probe = obj
-        elif probe is not None and "extra" in obj:
-            probe[obj.pop("extra")] = obj
-    if probe is None:
-        return dict(error=failure)
-    if failure:
-        probe["incomplete"] = failure
-    return probe
-
-
-def run_probe_child(local_rank, timeout=300):
+def run_child(flag, local_rank, timeout):
+    """Runs `bench.py <flag>` in a child process with a time limit; returns the JSON objects it printed + a failure note."""
+    lines, note = [], ""
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-quiet-zone", "--device", str(local_rank)],
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), flag, "--device", str(local_rank)],
                            capture_output=True, text=True, timeout=timeout)
-        return parse_probe_output(r.stdout, "" if r.returncode == 0 else f"exit {r.returncode}: {r.stderr[-300:]}")
+        stdout = r.stdout
+        if r.returncode != 0:
+            note = f"exit {r.returncode}: {r.stderr[-300:]}"
     except subprocess.TimeoutExpired as e:
-        out = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else e.stdout
-        return parse_probe_output(out, f"time limit of {timeout} s reached")
+        stdout = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+        note = f"time limit of {timeout} s reached"
     except Exception as e:  # noqa: BLE001
-        return dict(error=f"{type(e).__name__}: {e}"[:400])
+        return [], f"{type(e).__name__}: {e}"[:400]
+    for ln in (stdout or "").splitlines():
+        if ln.startswith("{"):
+            try:
+                lines.append(json.loads(ln))
+            except ValueError:
+                pass
+    return lines, note
 
 
+def collect_configs(lines, note):
+    """Files the child's lines: {"lines": [...], "complete": bool, "all_green": bool}."""
+    done = any(ln.get("done") for ln in lines)
+    rows = [ln for ln in lines if "config" in ln]
+    graded = [ln["parity"]["green"] for ln in rows if isinstance(ln.get("parity"), dict)]
+    out = dict(lines=rows, complete=bool(done), graded=len(graded), all_green=bool(graded) and all(graded))
+    if note:
+        out["incomplete"] = note
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import numpy as np
     import torch
@@ -452,26 +511,31 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    W, H = workload_size(world)
     verts, faces, center = default_scene()
-    mv = MainView(verts, faces, center, W, H, discrete_gpu=True, device=local_rank)
-    mv.reload_shader(PredefinedFunction(FN_ID).to_code())
     settings = make_settings(overlay_mode=1, central_difference_delta=1, lyapunov_scaling=50.0)
-    mv.update_settings(settings)
-    mv.set_shard(rank, world, ROWS_PER_BLOCK)
-    if args.quiet_zone:
-        mv.set_option(capi.OPT_QUIET_ZONE, 1)
     peer_stores = bool(args.peer_stores) and world > 1
-    if peer_stores:
-        # no gather: every rank's march stores its rows straight into rank 0's frame buffers over NVLink (CUDA IPC mappings of
-        # rank 0's buffers, include/linon_b200.h: linon_ipc_export / linon_ipc_open / linon_redirect_output)
-        sharding.setup_peer_stores(mv, rank, world)
-    stream = torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank))
-
-    ep = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda")
-    rc = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_RAYCAST_RGBA8), (H, W, 4), "|u1"), device="cuda")
-    hid = torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_HIT_ID_I32), (H, W), "<i4"), device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def make_view(W, H):
+        mv = MainView(verts, faces, center, W, H, discrete_gpu=True, device=local_rank)
+        mv.reload_shader(PredefinedFunction(FN_ID).to_code())
+        mv.update_settings(settings)
+        mv.set_shard(rank, world, ROWS_PER_BLOCK)
+        if args.quiet_zone is not None:
+            mv.set_option(capi.OPT_QUIET_ZONE, args.quiet_zone)
+        if args.overlay_kernel is not None:
+            mv.set_option(capi.OPT_OVERLAY_KERNEL, args.overlay_kernel)
+        if peer_stores:
+            # no gather: every rank's march stores its rows straight into rank 0's frame buffers over NVLink (CUDA IPC mappings
+            # of rank 0's buffers, include/linon_b200.h: linon_ipc_export / linon_ipc_open / linon_redirect_output)
+            sharding.setup_peer_stores(mv, rank, world)
+        bufs = [torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_RAYCAST_RGBA8), (H, W, 4), "|u1"), device="cuda"),
+                torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_ENDPOINT_F32X4), (H, W, 4), "<f4"), device="cuda"),
+                torch.as_tensor(_DevBuf(mv.device_ptr(capi.BUF_HIT_ID_I32), (H, W), "<i4"), device="cuda")]
+        return mv, torch.cuda.ExternalStream(mv.stream(), device=torch.device("cuda", local_rank)), bufs
+
+    W, H = workload_size(world)
+    mv, stream, bufs = make_view(W, H)
     final_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
 
     march_flags = capi.RENDER_ENHANCE
@@ -482,19 +546,19 @@ def run_ours(args):
 
     last = {}
 
-    def frame():
+    def frame(mv, stream, bufs, H):
         """One step of the hot path on this rank; returns launches of our kernels."""
         mv.render_flags(march_flags)
         n = 1 + (2 if not (march_flags & capi.RENDER_NO_SAMPLE_RAYS) else 0)  # march (+ click positions + sample rays)
         if world > 1:
             mv.sync()
             last["timings"], last["counters"] = mv.timings(), mv.counters()  # of the march render (reset per render)
-            last["quiet"] = int(mv.debug_profile()[15]) if args.quiet_zone else 0
+            last["quiet"] = int(mv.debug_profile()[15])
             if peer_stores:
                 dist.barrier()  # every rank's march has completed (mv.sync above): rank 0's buffers hold the whole frame
             else:
                 with torch.cuda.stream(stream):
-                    sharding.gather_rows_to_root([rc, ep, hid], H, rank, world, ROWS_PER_BLOCK)
+                    sharding.gather_rows_to_root(bufs, H, rank, world, ROWS_PER_BLOCK)
             if rank == 0:
                 mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)  # overlay on the assembled image
                 n += 1
@@ -502,7 +566,7 @@ def run_ours(args):
             n += 1  # overlay
         return n
 
-    def barrier():
+    def barrier(mv):
         mv.sync()
         torch.cuda.synchronize()
         if dist is not None:
@@ -511,27 +575,25 @@ def run_ours(args):
 
     # JIT + warm-up (untimed)
     for _ in range(max(args.warmup, 3 if args.steps > 0 else 0)):
-        frame()
-        barrier()
+        frame(mv, stream, bufs, H)
+        barrier(mv)
 
     # ---- device-timed steps: CUDA events on the stream the kernels are launched on; L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches = 0
-    dev_ms = []
-    march_ms = []
-    overlay_ms = []
+    dev_ms, march_ms, overlay_ms = [], [], []
     counters = None
-    barrier()
+    barrier(mv)
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        launches += frame()
+        launches += frame(mv, stream, bufs, H)
         e1.record(stream)
-        barrier()
+        barrier(mv)
         dev_ms.append(e0.elapsed_time(e1))
         t = mv.timings()
         overlay_ms.append(t.overlay_ms)
@@ -539,7 +601,7 @@ def run_ours(args):
             t, counters = last["timings"], last["counters"]
         else:
             counters = mv.counters()
-            last["quiet"] = int(mv.debug_profile()[15]) if args.quiet_zone else 0
+            last["quiet"] = int(mv.debug_profile()[15])
         march_ms.append(t.march_ms)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -551,32 +613,67 @@ def run_ours(args):
 
     # ---- e2e: public API with host buffers (uniform upload + final image read back) inside the timed region ----
     e2e_ms = 0.0
-    barrier()
+    barrier(mv)
     for _ in range(args.steps):
         t0 = time.perf_counter()
         mv.update_camera()                 # 112-byte camera uniform from the host-side arcball (MainView::update_camera)
         mv.update_settings(settings)       # 24-byte settings uniform (MainView::update_settings)
-        frame()
+        frame(mv, stream, bufs, H)
         if rank == 0:
             # result read back into pinned host memory (what a headless caller of the reference-facing API receives)
             mv.read_into_ptr(capi.BUF_FINAL_RGBA8, final_host.data_ptr(), final_host.numel())
-        barrier()
+        barrier(mv)
         e2e_ms += (time.perf_counter() - t0) * 1e3
     te = torch.tensor([e2e_ms], device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
+    cubin_hash = mv.march_cubin_hash()
+    march_regs = int(last["timings"].march_regs) if world > 1 else int(mv.timings().march_regs)
 
     # counters of all ranks (rays / steps processed by the whole job in one step)
     cvec = torch.tensor([counters.rays, counters.accepted_steps, counters.rejected_steps, counters.prehit_steps,
-                         counters.face_tests, counters.plane_tests, last.get("quiet", 0)], dtype=torch.float64, device="cuda")
+                         counters.face_tests, counters.plane_tests, last.get("quiet", 0), counters.culling_checks],
+                        dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(cvec)
+
+    # ---- C5 (BASELINE.json configs[4]): the 8192 x 8192 Enhance frame of the orbit, sharded over the same ranks: the
+    # fixed-size record of every N (strong scaling is read across the N = 1, 2, 4, 8 lines) ----
+    c5 = None
+    if args.c5_frames > 0:
+        try:
+            mv5, stream5, bufs5 = make_view(C5_W, C5_H)
+            for _ in range(2):
+                frame(mv5, stream5, bufs5, C5_H)
+                barrier(mv5)
+            ms5 = []
+            for _ in range(args.c5_frames):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream5)
+                frame(mv5, stream5, bufs5, C5_H)
+                e1.record(stream5)
+                barrier(mv5)
+                ms5.append(e0.elapsed_time(e1))
+            t5 = torch.tensor([float(np.mean(ms5))], device="cuda")
+            if dist is not None:
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            ms = float(t5.item())
+            c5 = dict(workload="C5 frame 0: 8192x8192, Enhance, MirageSphericalSigmoid, overlay on, default camera of the orbit",
+                      ms_per_frame=ms, mrays_s=C5_W * C5_H / (ms * 1e-3) / 1e6,
+                      rk4_gsteps_per_s=C5_W * C5_H * STEPS_PER_RAY / (ms * 1e-3) / 1e9, frames=args.c5_frames, n_gpus=world,
+                      scaling="strong (fixed frame size at every N)", orbit_64_frames_s=64 * ms * 1e-3)
+            mv5.close()
+        except Exception as e:  # noqa: BLE001
+            c5 = dict(error=f"{type(e).__name__}: {e}"[:300])
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
-    rays, acc, rej, pre, ftests, ptests, quiet_steps = [float(x) for x in cvec.tolist()]
+    rays, acc, rej, pre, ftests, ptests, quiet_steps, checks = [float(x) for x in cvec.tolist()]
 
     steps = max(args.steps, 1)
     ms_per_step = total_ms / steps
@@ -585,15 +682,17 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (the march): FP32 work actually executed / live launch duration ----
     # Two numerators, the SMALLER one is `achieved`: (i) the hand count of the executed arithmetic
-    # (linon_b200/flops.py: fused mirage body, three evaluated stages, only the plane / triangle tests that ran);
-    # (ii) FADD + FMUL + 2 FFMA per RK4 step as ncu counted them for this exact kernel variant
-    # (profiles/r1_march_c3.json, committed), times the steps of this launch.
+    # (linon_b200/flops.py: fused mirage body, three evaluated stages, straight steps as 3 FMA, only the plane / triangle
+    # tests that ran); (ii) FADD + FMUL + 2 FFMA of one C3 launch as ncu counted them for THIS binary (committed summary,
+    # accepted only when its cubin hash equals the running kernel's and the frame is the C3 frame).
     fp32_peak, sms = measure_fp32_peak(local_rank)
     m_ms = float(np.mean(march_ms))
+
     model_flops = fl.fused_march_flops(counters, FN_ID, field_weight_is_one=True, quiet_steps=last.get("quiet", 0))
-    # the committed ncu capture is of the default variant: with the quiet zone on only the hand count applies
-    ncu_prof = ncu_profile() if not args.quiet_zone else None
-    ncu_flops = ncu_prof["fp32_flops_per_rk4_step"] * (counters.accepted_steps + counters.rejected_steps) if ncu_prof else None
+    prof, prof_note = committed_profile(MARCH_PROFILE, "linon_march_tiles", cubin_hash)
+    ncu_flops = None
+    if prof is not None and world == 1 and prof.get("fp32_flops_executed"):
+        ncu_flops = float(prof["fp32_flops_executed"])
     alg_flops = min(model_flops, ncu_flops) if ncu_flops else model_flops
     achieved = alg_flops / (m_ms * 1e-3) / 1e12
     peaks, peak_src = measured_peaks()
@@ -602,55 +701,70 @@ def run_ours(args):
     if o_ms:
         ob = fl.OVERLAY_BYTES[1] * W * H
         a = ob / (o_ms * 1e-3) / 1e9
+        oprof, onote = committed_profile(OVERLAY_PROFILE, "overlay", static_source_hash(), "source_hash")
         overlay_roof = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                            traffic=overlay_ncu_traffic(W, H), kernel="overlay_kernel", algorithmic_bytes_per_launch=ob,
-                            peak_source=peak_src)
+                            traffic=(oprof.get("dram_traffic_bytes") if (oprof and (W, H) == (BASE_W, BASE_H)) else None),
+                            kernel=(oprof or {}).get("kernel", "overlay"), algorithmic_bytes_per_launch=ob, launch_ms=o_ms,
+                            peak_source=peak_src, profile=onote)
 
     line = dict(
         metric="Mrays/s", value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         rk4_gsteps_per_s=gsteps,
-        config=dict(workload=workload_name(world, W, H), width=W, height=H, rays_per_step=rays,
-                    rk4_steps_per_step=acc + rej, field_function="MirageSphericalSigmoid", h_initial=0.001,
-                    math_mode="fast (--use_fast_math; whole-step restatement of the predefined mirage body: RK4 stage 1 = identity, scaled coordinates, one reciprocal per stage)",
-                    kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass culling checks)", plane_culling=True,
-                    parallelism=(f"row-blocks x{world}" + (", peer stores into rank 0 over NVLink (no gather)" if peer_stores else ", grouped NCCL send/recv to rank 0")) if world > 1 else "single GPU",
-                    l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
+        config=workload_config(world, W, H),
+        implementation=dict(
+            math_mode="fast (--use_fast_math; whole-step restatement of the predefined mirage body: RK4 stage 1 = identity, scaled coordinates, one reciprocal per stage)",
+            kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass culling checks)",
+            quiet_zone=("on" if last.get("quiet", 0) else "off") + ": straight steps (velocity = direction) while the whole warp is outside the "
+                       "mirage's zone of influence, where the reference's own fp32 evaluation is the identity; every RK4 step is executed and counted",
+            plane_culling=True, march_cubin_hash=cubin_hash, march_regs=march_regs,
+            parallelism=(f"row-blocks x{world}" + (", peer stores into rank 0 over NVLink during the march (no gather)" if peer_stores else ", grouped NCCL send/recv to rank 0 after the march")) if world > 1 else "single GPU",
+            l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
         clocks=clocks,
         e2e=dict(value=rays / (e2e_ms / steps * 1e-3) / 1e6, unit="Mrays/s", ms_per_step=e2e_ms / steps,
                  h2d_bytes_per_step=112 + 24, d2h_bytes_per_step=W * H * 4),
         gpu_launches=launches,
         roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak,
-                      traffic=ncu_prof.get("dram_traffic_bytes") if ncu_prof else None,
+                      traffic=(prof.get("dram_traffic_bytes") if (prof and ncu_flops) else None),
                       kernel="linon_march_tiles", algorithmic_flops_per_launch=alg_flops, launch_ms=m_ms,
                       peak_source="FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no fp32 entry; nominal 74.45)",
                       frac_of_nominal=achieved / 74.45,
                       numerators=dict(model_executed_flops=model_flops, ncu_executed_flops=ncu_flops,
                                       as_written_equivalent_flops=fl.as_written_flops(counters, FN_ID)),
-                      issue_slot_utilization_ncu=(ncu_prof.get("sm__inst_issued.avg.pct_of_peak_sustained_active") if ncu_prof else None),
-                      algorithmic_bytes_per_launch=fl.MARCH_BYTES_PER_PIXEL * rays,
+                      ncu_profile=prof_note,
+                      issue_slot_utilization_ncu=(prof.get("sm__inst_issued.avg.pct_of_peak_sustained_active") if prof else None),
+                      warp_execution_efficiency_ncu=((prof.get("smsp__thread_inst_executed_per_inst_executed.ratio") or 0) / 32 if prof else None),
+                      reference_equivalent=dict(
+                          rk4_gsteps_per_s_march_only=(counters.accepted_steps + counters.rejected_steps) / (m_ms * 1e-3) / 1e9,
+                          as_written_tflops=fl.as_written_flops(counters, FN_ID) / (m_ms * 1e-3) / 1e12,
+                          note="steps of the reference's loop completed per second, and the FLOP/s the reference's as-written "
+                               "arithmetic for those steps would need (context only: never a roofline numerator)"),
+                      algorithmic_bytes_per_launch=fl.MARCH_BYTES_PER_PIXEL * int(counters.rays),
                       note="issue-slot bound fp32 CUDA-core kernel (no dense contraction; HBM traffic is 24 B per 5001-step ray): "
-                           "the binding resource is the scheduler's one instruction per cycle (issue_slot_utilization_ncu, "
-                           "from the committed ncu capture of this variant), not the FMA pipe; the numerator is work actually "
-                           "executed (smaller of hand count and ncu count), never culled or skipped work; traffic = ncu DRAM bytes"),
+                           "the numerator is work actually executed (smaller of hand count and, when the committed capture is of "
+                           "this very binary, the ncu count), never culled or skipped work"),
         roofline_overlay=overlay_roof,
         counters=dict(accepted=acc, rejected=rej, prehit=pre, face_tests=ftests, plane_tests=ptests,
-                      culling_checks=float(counters.culling_checks), quiet_steps=quiet_steps),
+                      culling_checks=checks, quiet_steps=quiet_steps, quiet_fraction=quiet_steps / max(acc, 1.0)),
+        c5_strong=c5,
         wall_s=t_wall,
     )
-    if args.quiet_zone:
-        line["config"]["quiet_zone"] = ("LINON_OPT_QUIET_ZONE on: straight steps (velocity = direction) while the whole warp is outside "
-                                        "the mirage's zone of influence; every step executed and counted (counters.quiet_steps)")
+    cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        s = oracle_sample(W, H, args.cpu_seconds)
-        line["cpu_baseline"] = dict(value=s["rays"] / s["seconds"] / 1e6, unit="Mrays/s", cores=s["cores"], kind=s["kind"],
-                                    sample=s["sample"], rk4_gsteps_per_s=s["steps"] / s["seconds"] / 1e9,
+        cpu = oracle_sample(W, H, args.cpu_seconds, keep_outputs=True)
+        line["cpu_baseline"] = dict(value=cpu["rays"] / cpu["seconds"] / 1e6, unit="Mrays/s", cores=cpu["cores"], kind=cpu["kind"],
+                                    sample=cpu["sample"], rk4_gsteps_per_s=cpu["steps"] / cpu["seconds"] / 1e9,
                                     note="the reference's WGSL run on the host cores (oracle/_ref transpile, or the bit-identical hand port), not wgpu-on-lavapipe: no Rust/Vulkan in this image")
-    if world == 1 and not args.quiet_zone and not args.no_quiet_zone_probe:
-        # LAST GPU work of the run: the opt-in quiet-zone path on the same frame, timed and compared with the default path's
-        # frame on the device.  A reported probe, not the headline: the option stays off until this has been seen on a B200.
-        # In a child process with a time limit, so that nothing the unmeasured path does can take this line down.
-        line["quiet_zone_probe"] = run_probe_child(local_rank)
+    if world == 1 and not args.no_parity:
+        try:
+            line["parity"], line["variants"] = c3_parity_and_variants(mv, W, H, cpu, args.parity_seconds, flush)
+        except Exception as e:  # noqa: BLE001
+            line["parity"] = dict(error=f"{type(e).__name__}: {e}"[:400], green=False)
+    if world == 1 and not args.no_configs:
+        mv.close()
+        del flush
+        torch.cuda.empty_cache()
+        line["configs"] = collect_configs(*run_child("--configs-child", local_rank, 420))
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -663,21 +777,23 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--parity-seconds", type=float, default=30.0, help="budget of the oracle bands of the parity block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quiet-zone", type=int, default=0, choices=[0, 1],
-                    help="1: measure with LINON_OPT_QUIET_ZONE on (straight steps outside the mirage's zone of influence); "
-                         "0 (default until the option is validated on the GPU): the default path is measured and the option is "
-                         "only probed at the end of the N=1 run (quiet_zone_probe)")
-    ap.add_argument("--no-quiet-zone-probe", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--quiet-zone", type=int, default=None, choices=[0, 1, 2],
+                    help="override LINON_OPT_QUIET_ZONE (library default: 1 = straight steps outside the mirage's zone of influence)")
+    ap.add_argument("--overlay-kernel", type=int, default=None, choices=[0, 1], help="override LINON_OPT_OVERLAY_KERNEL")
     ap.add_argument("--peer-stores", type=int, default=0, choices=[0, 1],
                     help="N > 1: 1 = every rank's march stores straight into rank 0's frame buffers (CUDA IPC + NVLink) instead of "
-                         "the NCCL gather after the march (opt-in: not yet run on a multi-GPU box)")
-    ap.add_argument("--probe-quiet-zone", action="store_true", help="internal: the child process of the N=1 run")
+                         "the NCCL gather after the march")
+    ap.add_argument("--c5-frames", type=int, default=2, help="frames of the 8192x8192 C5 record (0 = skip)")
+    ap.add_argument("--configs-child", action="store_true", help="internal: the child process of the N=1 run")
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()
-    if args.probe_quiet_zone:
-        return run_quiet_zone_probe(args)
+    if args.configs_child:
+        return run_configs_child(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

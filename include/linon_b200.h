@@ -112,16 +112,17 @@ enum {
                                     2: adaptive frames as well - per attempt, velocity = direction when every stage point lies
                                     outside the zone (diff is exactly 0 there, so the reference's noise-driven rejections
                                     outside the zone, SURVEY F20, have no counterpart).
-                                    Default 0 until measured on the GPU; validated on the host emulation of the device code
-                                    (tests/emu) against the oracle. */
+                                    Default 1 since round 2: measured on B200 (C3 march 191 -> 13 ms) and graded against the
+                                    oracle at the full C3 size in every bench.py run (`parity` block).  0: every step evaluates the
+                                    field (the round-1 kernel) */
     LINON_OPT_QUIET_RADIUS = 13, /* radius of the quiet zone of the SIGMOID mirage profiles in permille of their max_dist; 0 (default)
                                     = 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6).  1250 ... 4000: below
                                     1886 the reference's eta is 1 +- its rounding noise and the real-number deflection summed over
                                     the excluded shell is <= 1.85e-4 exp(6 - 12 r): 1e-9 rad at 1500 (mirage_fused.cuh) */
-    LINON_OPT_OVERLAY_KERNEL = 14, /* overlay stencil (src/overlay.wgsl:99-146).  0 (default, measured): 32x16 tile + halo of the
-                                    endpoints staged in shared memory.  1 (opt-in until measured on the GPU): every pixel
-                                    fetches its four taps through the read-only path, no shared memory, no barrier
-                                    (csrc/device/overlay_direct.cuh).  Bit-identical results */
+    LINON_OPT_OVERLAY_KERNEL = 14, /* overlay stencil (src/overlay.wgsl:99-146).  0: 32x16 tile + halo of the endpoints staged in
+                                    shared memory (the round-1 default).  1 (default since round 2: 54.9 vs 91.0 us at C3 on the
+                                    driver's box, bit-equal): every pixel fetches its four taps through the read-only path, no
+                                    shared memory, no barrier (csrc/device/overlay_direct.cuh).  Bit-identical results */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.
@@ -227,6 +228,9 @@ int linon_ipc_open(linon_view* v, const void* handle64, void** device_ptr);
 int linon_set_option(linon_view* v, int option, int value);
 int linon_get_counters(linon_view* v, linon_counters* out);
 int linon_get_timings(linon_view* v, linon_timings* out);
+/* FNV-1a (64 bit) of the cubin whose march kernel ran last (0 before the first march).  A committed ncu capture names the
+ * hash of the kernel it profiled; bench.py refuses its counters when the running kernel is a different binary. */
+int linon_march_cubin_hash(linon_view* v, uint64_t* out);
 /* Last error message of the handle (or of the failed linon_create when v is NULL). */
 const char* linon_last_error(const linon_view* v);
 

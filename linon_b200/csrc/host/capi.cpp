@@ -143,6 +143,7 @@ struct Module {
     CUfunction tiles = nullptr, pairs = nullptr, refill = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr,
                eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr, eval_rk4 = nullptr;
     int regs_tiles = 0, regs_pairs = 0, regs_refill = 0, regs_phase_a = 0, regs_phase_b = 0;
+    uint64_t cubin_hash = 0;  // FNV-1a of the cubin: ties a committed ncu capture to the kernel that is running
 };
 
 // The translated body becomes LinonField<S>::eval.  The member typedefs re-declare the type names the translator
@@ -202,6 +203,12 @@ std::string build_source(const std::string& cuda_body, int fused_kind, const lin
     }
     s += kMarchSrc;
     return s;
+}
+
+uint64_t fnv1a64(const char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+    return h;
 }
 
 std::string float_literal(float x) {
@@ -361,10 +368,11 @@ struct linon_view {
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 0, opt_quiet_radius = 0, opt_overlay_kernel = 0;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 1, opt_quiet_radius = 0, opt_overlay_kernel = 1;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
+    uint64_t last_cubin_hash = 0;  // of the module whose march kernel ran last
     std::string error;
 
     // peer stores (linon_redirect_output): where the march stores colour / endpoint / hit id instead of this view's own
@@ -448,6 +456,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     std::string log;
     if (!compile_cubin(body, var, v->layer, cubin, log)) return v->fail(LINON_ERR_COMPILE, log);
     Module m;
+    m.cubin_hash = fnv1a64(cubin.data(), cubin.size());
     CUresult r = g_drv.ModuleLoadData(&m.mod, cubin.data());
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
     struct { const char* name; CUfunction* f; } fns[] = {
@@ -933,6 +942,7 @@ int linon_render(linon_view* v, uint32_t flags) {
         }
         CK(v, cudaEventRecord(v->ev[1], v->stream));
         v->ran_march = true;
+        v->last_cubin_hash = mod->cubin_hash;
         v->last_rays = (uint64_t)v->local_rows * v->W;
     }
 
@@ -1092,6 +1102,12 @@ int linon_debug_profile(linon_view* v, uint64_t* out16) {
     return LINON_OK;
 }
 
+int linon_march_cubin_hash(linon_view* v, uint64_t* out) {
+    if (!v || !out) return LINON_ERR_INVALID;
+    *out = v->last_cubin_hash;
+    return LINON_OK;
+}
+
 int linon_get_timings(linon_view* v, linon_timings* out) {
     if (!v || !out) return LINON_ERR_INVALID;
     const int rc = linon_sync(v);
@@ -1128,6 +1144,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (n_faces == 36) tmp.n_faces = 0;  // the start-up mesh: make_variant's caller fills the real table sizes
     if (n_faces > kSharedMeshFaces) tmp.use_bvh = true;
     tmp.opt_math = math_mode;
+    tmp.opt_quiet = 0;  // the build check names the quiet-zone variants explicitly (LINON_CHECK_QUIET_ZONE)
     tmp.body = wgsl_body;
     tmp.settings.field_weight = 1.0f;  // the application's default (src/main_view.rs:133-139)
     if (module_src && module_src[0]) {
@@ -1163,6 +1180,12 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
         return LINON_ERR_COMPILE;
     }
     if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (const char* hf = getenv("LINON_DUMP_CUBIN_HASH")) {  // developer aid: the hash linon_march_cubin_hash reports for this variant
+        if (FILE* f = fopen(hf, "w")) {
+            fprintf(f, "%016llx\n", (unsigned long long)fnv1a64(cubin.data(), cubin.size()));
+            fclose(f);
+        }
+    }
     if (const char* dump = getenv("LINON_DUMP_CUBIN")) {  // developer aid: inspect with cuobjdump -sass / -res-usage
         if (FILE* f = fopen(dump, "wb")) {
             fwrite(cubin.data(), 1, cubin.size(), f);

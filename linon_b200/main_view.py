@@ -297,6 +297,12 @@ class MainView:
         self._check_view(capi.lib().linon_get_timings(self._view, C.byref(t)))
         return t
 
+    def march_cubin_hash(self) -> str:
+        """FNV-1a of the cubin whose march kernel ran last, 16 hex digits (ties ncu captures to the running kernel)."""
+        h = C.c_uint64(0)
+        self._check_view(capi.lib().linon_march_cubin_hash(self._view, C.byref(h)))
+        return f"{h.value:016x}"
+
     def debug_profile(self) -> np.ndarray:
         out = np.zeros(16, np.uint64)
         self._check_view(capi.lib().linon_debug_profile(self._view, out.ctypes.data))

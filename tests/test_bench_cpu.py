@@ -1,4 +1,4 @@
-"""Host logic of bench.py that needs no GPU: how the parent files what the quiet-zone probe child printed."""
+"""Host logic of bench.py that needs no GPU."""
 import json
 import os
 import subprocess
@@ -9,22 +9,45 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def test_probe_output_main_line_then_extras():
-    out = "\n".join(["some library chatter", json.dumps(dict(ms_per_step=12.5, vs_default_path=dict(meets_north_star=True))),
-                     json.dumps(dict(extra="radius_1500", ms_per_step=9.0)), "{not json",
-                     json.dumps(dict(extra="c1_adaptive_level2", error="RuntimeError: x"))])
-    p = bench.parse_probe_output(out, "")
-    assert p["ms_per_step"] == 12.5 and p["radius_1500"] == dict(ms_per_step=9.0)
-    assert p["c1_adaptive_level2"] == dict(error="RuntimeError: x") and "incomplete" not in p
+def test_config_lines_of_the_child_are_filed_and_graded():
+    lines = [dict(config="C1", parity=dict(green=True)), dict(config="C2", parity=dict(green=True)), dict(config="C4"), dict(done=True)]
+    c = bench.collect_configs(lines, "")
+    assert c["complete"] and c["all_green"] and c["graded"] == 2 and len(c["lines"]) == 3 and "incomplete" not in c
+    c = bench.collect_configs(lines[:2] + [dict(config="C2", parity=dict(green=False))], "time limit of 420 s reached")
+    assert not c["complete"] and not c["all_green"] and c["incomplete"].startswith("time limit")
+    assert not bench.collect_configs([], "exit -11: Segmentation fault")["all_green"]
 
 
-def test_probe_output_keeps_the_main_line_of_a_child_that_died_later():
-    p = bench.parse_probe_output(json.dumps(dict(ms_per_step=12.5)) + "\n", "time limit of 300 s reached")
-    assert p == dict(ms_per_step=12.5, incomplete="time limit of 300 s reached")
-    assert bench.parse_probe_output("", "exit -11: Segmentation fault") == dict(error="exit -11: Segmentation fault")
-    assert bench.parse_probe_output(None, "time limit of 300 s reached") == dict(error="time limit of 300 s reached")
-    # an extra line without a main line before it is not a result
-    assert "error" in bench.parse_probe_output(json.dumps(dict(extra="radius_1500", ms_per_step=9.0)), "exit 1: boom")
+def test_a_stale_ncu_capture_is_refused(tmp_path):
+    p = tmp_path / "prof.json"
+    p.write_text(json.dumps([dict(kernel="linon_march_tiles", cubin_hash="00000000deadbeef", fp32_flops_executed=1.0)]))
+    k, note = bench.committed_profile(str(p), "linon_march_tiles", "00000000deadbeef")
+    assert k is not None and note == "ok"
+    k, note = bench.committed_profile(str(p), "linon_march_tiles", "0123456789abcdef")
+    assert k is None and "stale capture refused" in note
+    k, note = bench.committed_profile(str(tmp_path / "missing.json"), "x", None)
+    assert k is None and "not committed" in note
+    assert len(bench.static_source_hash()) == 16
+
+
+def test_committed_captures_name_what_they_profiled():
+    """Every committed r2 capture bench.py reads carries the identity of the binary it profiled."""
+    for path, key in ((bench.MARCH_PROFILE, "cubin_hash"), (bench.OVERLAY_PROFILE, "source_hash")):
+        if os.path.exists(path):
+            assert any(k.get(key) for k in json.load(open(path))), path
+
+
+def test_both_arms_name_the_same_workload():
+    a = bench.workload_config(1, *bench.workload_size(1))
+    assert a["width"] == 3840 and a["height"] == 2160 and a["rk4_steps_per_step"] == 3840 * 2160 * 5001
+    for n in (2, 4, 8):
+        w, h = bench.workload_size(n)
+        assert abs(w * h / (3840 * 2160) - n) < 0.01 * n
+
+
+def test_cpu_arm_counts_its_threads_from_the_affinity_mask_not_from_omp_num_threads(monkeypatch):
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")  # what torchrun exports
+    assert bench.host_threads() == len(os.sched_getaffinity(0))
 
 
 def test_reference_arm_on_other_ranks_exits_without_work():
@@ -34,7 +57,12 @@ def test_reference_arm_on_other_ranks_exits_without_work():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_overlay_traffic_comes_from_the_committed_capture_of_that_size_only():
-    t = bench.overlay_ncu_traffic(3840, 2160)
-    assert t is not None and 0.8 * 28 * 3840 * 2160 < t < 1.2 * 28 * 3840 * 2160  # no wasted re-reads (28 algorithmic B/px)
-    assert bench.overlay_ncu_traffic(800, 600) is None
+def test_reference_arm_uses_every_core_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use all host threads (round-1 finding)."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["config"] == bench.workload_config(2, *bench.workload_size(2))

@@ -48,6 +48,14 @@ def render(mv, fn, flags=0, math=capi.MATH_FAST, kernel=capi.KERNEL_TILES, cull=
     return dict(hit_id=mv.hit_ids(), rgba8=mv.ray_casting_texture(), endpoint=mv.mapping_texture())
 
 
+# Cap on the fraction of pixels a frame test may leave ungraded (VERDICT r1 "what's weak" 2): the oracle's own numbers at
+# the sizes used here (64x48 ... 160x120, where one pixel spans much more of the scene than at full size and the
+# reference's un-normalised central difference marks more of it as diverging) are <= 13.4 % high-Lyapunov pixels on
+# fixed-step frames and <= 21.7 % (high Lyapunov + undecided) on adaptive frames, both for MiragePlaneSigmoid; the
+# full-size caps are in tests/test_gpu_fullsize.py.
+MAX_EXCLUDED = {False: 0.15, True: 0.25}
+
+
 def oracle_frame(oracle, scene, mv, fn, h_initial=0.1, adaptive=True, settings=None, **kw):
     verts, faces, _ = scene
     W, H = mv.size
@@ -65,6 +73,8 @@ def oracle_frame(oracle, scene, mv, fn, h_initial=0.1, adaptive=True, settings=N
         st_ulp = dict(st, field_weight=float(np.nextafter(np.float32(st["field_weight"]), np.float32(0))))
         alt_ulp = oracle.march(verts, faces, cam, st_ulp, int(fn), W, H, h_initial=h_initial, adaptive=True, **kw)
         excl = excl | parity.disagreement_mask(alt64, ref) | parity.disagreement_mask(alt_ulp, ref)
+    cap = MAX_EXCLUDED[bool(adaptive and h_initial > 0.002)]
+    assert excl.mean() <= cap, f"{excl.mean():.3f} of the pixels excluded from grading (cap {cap}): the checker must not declare the frame undecided"
     return ref, excl
 
 
@@ -230,7 +240,9 @@ def test_rotated_cameras_and_partial_field_weight(product_lib, oracle, scene):
             cam = camera_dict(orbit_camera(center, W, H, frame).uniform())
             ref = oracle.march(verts, faces, cam, settings_dict(st), int(fn), W, H, h_initial=0.1, adaptive=False)
             _, exps = oracle.overlay(ref["rgba8"], ref["endpoint"], dict(settings_dict(st), overlay_mode=1))
-            m = parity.compare_frames(got, ref, exclude=parity.high_lyapunov_mask(exps))
+            excl = parity.high_lyapunov_mask(exps)
+            assert excl.mean() <= MAX_EXCLUDED[False], (frame, fn, excl.mean())
+            m = parity.compare_frames(got, ref, exclude=excl)
             assert parity.passes_north_star(m), (frame, fn, m)
 
 
@@ -246,7 +258,9 @@ def test_golden_fixtures(product_lib, scene):
             flags = 0 if entry["adaptive"] else capi.RENDER_ADAPTIVE_OFF
             got = render(mv, fn, flags=flags, math=capi.MATH_FAST)
             ref = dict(hit_id=z["hit_id"].astype(np.int32), rgba8=z["rgba8"], endpoint=z["endpoint"])
-            m = parity.compare_frames(got, ref, exclude=z["high_lyapunov"] | z["undecided"])
+            excl = z["high_lyapunov"] | z["undecided"]
+            assert excl.mean() <= MAX_EXCLUDED[bool(entry["adaptive"])], (entry, excl.mean())
+            m = parity.compare_frames(got, ref, exclude=excl)
             if entry["adaptive"]:
                 assert m["hit_group_agree"] >= 0.999 and m["colour_within_1"] >= 0.99, (entry, m)
             else:

@@ -1,12 +1,12 @@
-"""LINON_OPT_QUIET_ZONE on the GPU (opt-in; off by default): straight steps where a fused mirage body is the identity.
+"""LINON_OPT_QUIET_ZONE on the GPU: straight steps where a fused mirage body is the identity (default since round 2).
 
-The option was written in a session without GPU time: its device code is validated on the host emulation of the exact NVRTC
-source (tests/test_emulation_cpu.py: north star against the oracle, culling bit-identity, step counts), and the default
-kernels compile to byte-identical SASS with and without this change.  These tests are its first run on hardware, hence
-xfail(strict=False): a failure here says "keep the option off", never that the default path regressed.  The file sorts
-last among the GPU tests on purpose.  The same holds for the two other opt-in paths tested at the end of the file: peer
-stores (linon_redirect_output) and the direct overlay kernel (LINON_OPT_OVERLAY_KERNEL, validated bit for bit against the
-oracle on the host in tests/test_overlay_emulation_cpu.py).
+The option was written in round 1 without GPU time (validated on the host emulation of the exact NVRTC source,
+tests/test_emulation_cpu.py), first ran on hardware in the driver's round-1 GPU tests (all green) and is the shipped path
+since round 2: level 1 (fixed-step frames) is the library default, level 2 (adaptive frames as well) stays opt-in.  The same
+holds for the two other paths tested at the end of the file: peer stores (linon_redirect_output) and the direct overlay
+kernel (LINON_OPT_OVERLAY_KERNEL = 1, default since round 2; validated bit for bit against the oracle on the host in
+tests/test_overlay_emulation_cpu.py).  Full-size grading against the oracle: tests/test_gpu_fullsize.py and bench.py's
+`parity` block.
 """
 import numpy as np
 import pytest
@@ -16,8 +16,7 @@ from linon_b200 import parity
 from linon_b200.main_view import MainView, PredefinedFunction, make_settings
 from test_gpu_parity import oracle_frame, render
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="opt-in path, first run on hardware (validated on the host emulation so far)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 MIRAGES = [PredefinedFunction.MirageSpherical, PredefinedFunction.MiragePlane, PredefinedFunction.MirageSphericalSigmoid,
            PredefinedFunction.MiragePlaneSigmoid]
@@ -161,6 +160,7 @@ def test_direct_overlay_kernel_equals_the_staged_one_bit_for_bit(product_lib, or
         st = make_settings(overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0)
         mv.update_settings(st)
         mv.disable_adaptive_sampling()
+        mv.set_option(capi.OPT_OVERLAY_KERNEL, 0)
         mv.render()
         mv.sync()
         staged_final, staged_ex = mv.texture().copy(), mv.exponents().copy()
