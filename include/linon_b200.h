@@ -61,7 +61,9 @@ enum {
     LINON_RENDER_ADAPTIVE_OFF = 4,    /* disable_adaptive_sampling (while dragging), :765-776 */
     LINON_RENDER_NO_OVERLAY = 8,      /* skip the overlay dispatch (sharded march; overlay runs after the gather) */
     LINON_RENDER_NO_MARCH = 16,       /* overlay (+ sample rays) only, on buffers already in place */
-    LINON_RENDER_NO_SAMPLE_RAYS = 32  /* skip the 8 reference-view rays */
+    LINON_RENDER_NO_SAMPLE_RAYS = 32, /* skip the 8 reference-view rays */
+    LINON_RENDER_KEEP_TIMINGS = 64    /* linon_get_timings keeps the passes of the previous linon_render call (a frame rendered
+                                         by two calls: march, then overlay on the assembled frame) */
 };
 
 /* buffers (linon_read / linon_device_ptr).  Element sizes in bytes per pixel unless noted. */
@@ -99,10 +101,13 @@ enum {
     LINON_OPT_PROFILE = 7,       /* 1: persistent kernel accumulates clock64 section timers (linon_debug_profile) */
     LINON_OPT_FORCE_BVH = 11,    /* 1: stage the mesh as faces + bounding-volume hierarchy in global memory even when it would fit
                                     shared memory (meshes above 1024 faces always do).  Results are identical; for tests */
-    LINON_OPT_SPECIALIZE = 10,   /* 1 (default): in fast math mode a body that is byte-identical with one of the four predefined
-                                    mirage functions (src/functions.rs:36-94) runs its hand-fused restatement
-                                    (csrc/device/mirage_fused.cuh: one reciprocal for eta, no sigmoid reciprocal, shared
-                                    inverse square root, Runge-Kutta stage 1 = identity).  0: always the generic translation */
+    LINON_OPT_SPECIALIZE = 10,   /* 1 (default): in fast math mode a body of the MIRAGE FAMILY - one of the four predefined mirage
+                                    functions (src/functions.rs:36-94) up to comments, white space and the values of its
+                                    literals (t_env, t_src, max_dist, centre / plane_p0, the sigmoid's constants; matched
+                                    token by token, csrc/host/mirage_match.hpp) - runs the hand-fused restatement with those
+                                    constants (csrc/device/mirage_fused.cuh: one reciprocal for eta, no sigmoid reciprocal,
+                                    shared inverse square root, Runge-Kutta stage 1 = identity).  0: always the generic
+                                    translation */
     LINON_OPT_PAIR_MIN_BLOCKS = 9, /* resident CTAs / SM requested for the pair kernel (register cap); 0 = default (512/block) */
     LINON_OPT_QUIET_ZONE = 12,   /* 1: fixed-step frames (Enhance, adaptive off) of a predefined mirage body in fast math mode take
                                     straight steps - velocity = direction, no field evaluation - while every lane of the warp is
@@ -225,6 +230,43 @@ int linon_redirect_output(linon_view* v, int buffer, void* device_ptr);
 int linon_ipc_export(linon_view* v, int buffer, void* handle64);
 int linon_ipc_open(linon_view* v, const void* handle64, void** device_ptr);
 
+/* ---- one frame on several B200s of a node, driven by ONE host thread (create_sharded + render_sharded) --------
+ * The reference renders on one device (src/application.rs:67-89); this is the north star's "image shards naturally by row
+ * tiles across the 8 B200s".  A linon_sharded owns one linon_view per device; rows are cut into blocks of rows_per_block and
+ * dealt round-robin (block b -> shard b % n); shard 0 is the ROOT: its buffers hold the assembled frame, it runs the sample
+ * rays and the overlay, and every reader (linon_read, linon_device_ptr, linon_get_counters ...) is used on
+ * linon_sharded_view(s, 0).  The setters below are MainView's (update_model, update_camera, update_settings, reload_shader),
+ * applied to every shard.  How the rows reach the root: */
+enum {
+    LINON_SHARD_PEER_STORES = 0, /* default: every shard's march stores its rows straight into the root's buffers over NVLink
+                                    (peer access between the devices, linon_redirect_output); the root's overlay is ordered
+                                    behind the other shards' marches by CUDA events.  No copy, no collective, no host sync */
+    LINON_SHARD_NCCL_GATHER = 1  /* every shard marches into its own buffers, then ONE grouped ncclSend / ncclRecv exchange
+                                    moves each non-root row block to the same rows of the root's buffers (libnccl.so.2,
+                                    single-process communicators; needs distinct devices) */
+};
+typedef struct linon_sharded linon_sharded;
+/* devices: CUDA ordinals, devices[0] is the root.  The same ordinal may appear more than once (several shards on one
+ * device: peer-store mode only; how the multi-shard logic is tested on a single-GPU box). */
+int linon_sharded_create(const int* devices, uint32_t n_devices, uint32_t width, uint32_t height, uint32_t rows_per_block,
+                         int mode, linon_sharded** out);
+void linon_sharded_destroy(linon_sharded* s);
+uint32_t linon_sharded_world(const linon_sharded* s);
+linon_view* linon_sharded_view(linon_sharded* s, uint32_t rank);
+int linon_sharded_set_mesh(linon_sharded* s, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces);
+int linon_sharded_set_camera(linon_sharded* s, const linon_camera* camera);
+int linon_sharded_set_settings(linon_sharded* s, const linon_settings* settings);
+/* On a compile error no shard changes its function (the body is validated on the root first). */
+int linon_sharded_set_field_function(linon_sharded* s, const char* wgsl_body, char* err, size_t err_len);
+int linon_sharded_set_option(linon_sharded* s, int option, int value);
+int linon_sharded_resize(linon_sharded* s, uint32_t width, uint32_t height);
+/* MainView::render for the whole frame: every shard marches its rows, the rows are assembled on the root (see the modes),
+ * the root runs the overlay.  Asynchronous like linon_render; flags as for linon_render. */
+int linon_sharded_render(linon_sharded* s, uint32_t flags);
+int linon_sharded_sync(linon_sharded* s);
+/* Last error of the handle (or of the failed linon_sharded_create when s is NULL). */
+const char* linon_sharded_last_error(const linon_sharded* s);
+
 int linon_set_option(linon_view* v, int option, int value);
 int linon_get_counters(linon_view* v, linon_counters* out);
 int linon_get_timings(linon_view* v, linon_timings* out);
@@ -270,6 +312,12 @@ int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const
  * kernels when LINON_OPT_PROFILE = 1: [5..9] phase A, [10..14] phase B = refill cycles, step cycles, warp iterations,
  * live lanes summed over iterations, warp lifetime cycles. */
 int linon_debug_profile(linon_view* v, uint64_t* out16);
+
+/* The structural match that selects the hand-fused restatement of the mirage family (csrc/host/mirage_match.hpp): *kind = 1..4
+ * (MirageSpherical, MiragePlane, MirageSphericalSigmoid, MiragePlaneSigmoid) when wgsl_body is one of the predefined mirage
+ * bodies of src/functions.rs:36-94 up to comments, white space and the values of its literals, 0 otherwise; params8 (optional)
+ * receives t_env, t_src, max_dist, centre / plane_p0 x y z, and the sigmoid's K and C as found in the text.  No device needed. */
+int linon_debug_match_mirage(const char* wgsl_body, int* kind, double* params8);
 
 /* FFMA-chain microbenchmark on `device`: the measured FP32 peak used as the roofline denominator. */
 int linon_measure_fp32_peak(int device, double* tflops, int* sm_count);

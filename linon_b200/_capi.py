@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "liblinon_b200.so")
 # --- enums of include/linon_b200.h ---------------------------------------------------------------
 OK, ERR_INVALID, ERR_CUDA, ERR_COMPILE, ERR_NO_DRIVER, ERR_SIZE, ERR_UNSUPPORTED = range(7)
 RENDER_DEFAULT, RENDER_ENHANCE, RENDER_OUTLINE, RENDER_ADAPTIVE_OFF = 0, 1, 2, 4
-RENDER_NO_OVERLAY, RENDER_NO_MARCH, RENDER_NO_SAMPLE_RAYS = 8, 16, 32
+RENDER_NO_OVERLAY, RENDER_NO_MARCH, RENDER_NO_SAMPLE_RAYS, RENDER_KEEP_TIMINGS = 8, 16, 32, 64
+SHARD_PEER_STORES, SHARD_NCCL_GATHER = 0, 1
 BUF_FINAL_RGBA8, BUF_RAYCAST_RGBA8, BUF_ENDPOINT_F32X4, BUF_EXPONENTS_F32, BUF_HIT_ID_I32 = range(5)
 BUF_RAY_SAMPLES, BUF_SAMPLE_POS = 5, 6
 OPT_MATH, OPT_KERNEL, OPT_BLOCK, OPT_CTAS_PER_SM, OPT_REFILL_MIN, OPT_FACE_UNROLL, OPT_MAX_REGS, OPT_PROFILE, OPT_CULL = range(9)
@@ -81,6 +82,19 @@ PROTOTYPES = [
     ("linon_redirect_output", _I, [_P, _I, _P]),
     ("linon_ipc_export", _I, [_P, _I, _P]),
     ("linon_ipc_open", _I, [_P, _P, C.POINTER(_P)]),
+    ("linon_sharded_create", _I, [_P, _U, _U, _U, _U, _I, C.POINTER(_P)]),
+    ("linon_sharded_destroy", None, [_P]),
+    ("linon_sharded_world", _U, [_P]),
+    ("linon_sharded_view", _P, [_P, _U]),
+    ("linon_sharded_set_mesh", _I, [_P, _P, _U, _P, _U]),
+    ("linon_sharded_set_camera", _I, [_P, C.POINTER(Camera)]),
+    ("linon_sharded_set_settings", _I, [_P, C.POINTER(Settings)]),
+    ("linon_sharded_set_field_function", _I, [_P, _CP, _P, _S]),
+    ("linon_sharded_set_option", _I, [_P, _I, _I]),
+    ("linon_sharded_resize", _I, [_P, _U, _U]),
+    ("linon_sharded_render", _I, [_P, _U]),
+    ("linon_sharded_sync", _I, [_P]),
+    ("linon_sharded_last_error", _CP, [_P]),
     ("linon_set_option", _I, [_P, _I, _I]),
     ("linon_get_counters", _I, [_P, C.POINTER(Counters)]),
     ("linon_get_timings", _I, [_P, C.POINTER(Timings)]),
@@ -96,6 +110,7 @@ PROTOTYPES = [
     ("linon_debug_eval_helper", _I, [_P, _I, _U, _P, _P, _P, _P, _P, _P, _P]),
     ("linon_debug_hit_triangle", _I, [_P, _U, _P, _P, _P, _P]),
     ("linon_debug_profile", _I, [_P, _P]),
+    ("linon_debug_match_mirage", _I, [_CP, C.POINTER(_I), _P]),
     ("linon_measure_fp32_peak", _I, [_I, C.POINTER(C.c_double), C.POINTER(_I)]),
     # include/linon_b200_host.h
     ("linon_host_default_scene", None, [_P, _P, _P, _I]),

@@ -34,10 +34,11 @@
 //       - the distance profile runs in scaled coordinates c' = s (p - centre) with s = 12 log2(e) / max_dist (sigmoid)
 //         or 1 / max_dist (linear), so E = exp2(k0 - |c'|) is one FFMA + MUFU.EX2 on (q, rsqrt q), every stage point is
 //         ONE FFMA per component from the step's scaled origin (s h k + c'_prev), and the normal c' / |c'| is unchanged;
-//       - A and B are divided by their slopes: a~ = u + A1/A2, b~ = u + B1/B2 (u = E or min(1, |c'|)); the slopes cancel
-//         in eta = a~(in) b~(out) / (a~(out) b~(in)), so two FFMAs with register constants become two FADDs with immediates;
-//         a~(in) / b~(in) is formed once per step, and for the sigmoid profiles b~ / a~ = 1 + D / a~ is one FFMA on the
-//         reciprocal (the linear profiles have A1/A2 ~ 550, where that form would cancel: they multiply b~ by 1 / a~);
+//       - A and B are normalised: sigmoid profiles divide by the slopes, a~ = E + A1/A2, b~ = E + B1/B2; linear profiles by
+//         the constant terms, a~ = 1 + (A2/A1) u, b~ = 1 + (B2/B1) u (A1/A2 ~ 1e5 / (t_src - t_env) would swamp u in [0, 1]);
+//         the factors cancel in eta = a~(in) b~(out) / (a~(out) b~(in)), which is evaluated as 1 + (eta - 1) with the
+//         difference of the two products collapsed by hand (see stage()): one reciprocal per stage, one per step, and
+//         eta == 1 exactly wherever the profile is flat;
 //       - the normal is never materialised: d = (v . c') rq and the refracted direction is eta v + (cs rq) c';
 //       - stage 4 is accumulated straight into k1 + 2 k2 + 2 k3 (two FFMAs per component, no k4);
 //       - total reflection (k < 0, a thin band of grazing rays) is detected once per step on min(k2, k3, k4); such a step
@@ -46,6 +47,40 @@
 
 #ifndef LINON_MIRAGE_KIND
 #error "mirage_fused.cuh needs -DLINON_MIRAGE_KIND=1..4"
+#endif
+// The constants of the body (csrc/host/mirage_match.hpp fills them from the user's text; the defaults are the predefined
+// bodies of src/functions.rs:36-94).  CX, CY, CZ: the sphere's centre, or plane_p0 (plane_n is (0, 1, 0): only CY counts).
+#ifndef LINON_MIRAGE_T_ENV
+#define LINON_MIRAGE_T_ENV (15.0f)
+#endif
+#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
+#ifndef LINON_MIRAGE_T_SRC
+#define LINON_MIRAGE_T_SRC (200.0f)
+#endif
+#ifndef LINON_MIRAGE_MAX_DIST
+#define LINON_MIRAGE_MAX_DIST (0.25f)
+#endif
+#ifndef LINON_MIRAGE_CX
+#define LINON_MIRAGE_CX (-0.5f)
+#define LINON_MIRAGE_CY (0.5f)
+#define LINON_MIRAGE_CZ (-0.5f)
+#endif
+#else
+#ifndef LINON_MIRAGE_T_SRC
+#define LINON_MIRAGE_T_SRC (30.0f)
+#endif
+#ifndef LINON_MIRAGE_MAX_DIST
+#define LINON_MIRAGE_MAX_DIST (0.01f)
+#endif
+#ifndef LINON_MIRAGE_CX
+#define LINON_MIRAGE_CX (0.0f)
+#define LINON_MIRAGE_CY (0.1f)
+#define LINON_MIRAGE_CZ (0.0f)
+#endif
+#endif
+#ifndef LINON_MIRAGE_SIG_K  // sigmoid(dist / max_dist * K - C)
+#define LINON_MIRAGE_SIG_K (12.0f)
+#define LINON_MIRAGE_SIG_C (6.0f)
 #endif
 #define LINON_STAGE1_IDENTITY 1
 #define LINON_FUSED_RK4 1
@@ -67,12 +102,7 @@ template <class S> struct LinonField {
     static __device__ __forceinline__ vec3t<S> eval(const vec3t<S> p_prev, const vec3t<S> p, const vec3t<S> v0,
                                                     const vec3t<S> v, const S t, const WgslSettings& settings,
                                                     const WgslCamera& camera) {
-        const float t_env = 15.0f;
-#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
-        const float t_src = 200.0f, max_dist = 0.25f;
-#else
-        const float t_src = 30.0f, max_dist = 0.01f;
-#endif
+        const float t_env = LINON_MIRAGE_T_ENV, t_src = LINON_MIRAGE_T_SRC, max_dist = LINON_MIRAGE_MAX_DIST;
         // n(t) = A(t) / B(t)
         const float c1p = 0.0000104f * 101325.0f;
         const float a0 = c1p * (1.0f + 101325.0f * 1e-10f * 60.1f);
@@ -80,7 +110,7 @@ template <class S> struct LinonField {
         const float c2 = 0.00366f;
 
 #if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
-        const vec3f center(-0.5f, 0.5f, -0.5f);
+        const vec3f center(LINON_MIRAGE_CX, LINON_MIRAGE_CY, LINON_MIRAGE_CZ);
         const vec3t<S> c_out = p - center;
         const S q_out = w_dot(c_out, c_out);
         const S r_out = w_inverseSqrt(q_out);
@@ -91,15 +121,15 @@ template <class S> struct LinonField {
         const S dist_in = q_in * w_inverseSqrt(q_in);
         const S d = w_dot(v, normal);
 #else
-        const S dist_out = w_abs(p.y - 0.1f);
-        const S dist_in = w_abs(p_prev.y - 0.1f);
+        const S dist_out = w_abs(p.y - LINON_MIRAGE_CY);
+        const S dist_in = w_abs(p_prev.y - LINON_MIRAGE_CY);
         const S d = v.y;
 #endif
 
 #if LINON_MIRAGE_KIND >= 3
-        // E = exp(-(dist / max_dist * 12 - 6)) = exp2(dist * ks + k0)
+        // E = exp(-(dist / max_dist * K - C)) = exp2(dist * ks + k0)
         const float log2e = 1.4426950408889634f;
-        const float ks = -12.0f / max_dist * log2e, k0 = 6.0f * log2e;
+        const float ks = -LINON_MIRAGE_SIG_K / max_dist * log2e, k0 = LINON_MIRAGE_SIG_C * log2e;
         const S e_in = w_exp2(dist_in * ks + k0);
         const S e_out = w_exp2(dist_out * ks + k0);
         const float A1 = a0 - t_env * a1, A2 = a0 - t_src * a1;
@@ -135,26 +165,25 @@ template <class S> struct LinonField {
     // ---- LINON_FUSED_RK4 -------------------------------------------------------------------------------------------
     // profile constants in slope-normalised form (see the header): u + RA, u + RB
     struct Fused {
-        static constexpr float t_env = 15.0f;
-#if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
-        static constexpr float t_src = 200.0f, max_dist = 0.25f;
-#else
-        static constexpr float t_src = 30.0f, max_dist = 0.01f;
-#endif
+        static constexpr float t_env = LINON_MIRAGE_T_ENV, t_src = LINON_MIRAGE_T_SRC, max_dist = LINON_MIRAGE_MAX_DIST;
         static constexpr float c1p = 0.0000104f * 101325.0f;
         static constexpr float a0 = c1p * (1.0f + 101325.0f * 1e-10f * 60.1f);
         static constexpr float a1 = c1p * 101325.0f * 1e-10f * 0.972f;
         static constexpr float c2 = 0.00366f;
 #if LINON_MIRAGE_KIND >= 3
         static constexpr float log2e = 1.4426950408889634f;
-        static constexpr float scale = 12.0f / max_dist * log2e;  // E = exp2(k0 - scale dist)
-        static constexpr float k0 = 6.0f * log2e;
+        static constexpr float scale = LINON_MIRAGE_SIG_K / max_dist * log2e;  // E = exp2(k0 - scale dist)
+        static constexpr float k0 = LINON_MIRAGE_SIG_C * log2e;
         static constexpr float RA = (a0 - t_env * a1) / (a0 - t_src * a1);
         static constexpr float RB = (1.0f + t_env * c2) / (1.0f + t_src * c2);
 #else
         static constexpr float scale = 1.0f / max_dist;           // part = min(1, scale dist)
-        static constexpr float RA = (a0 - a1 * t_src) / (a1 * (t_src - t_env));
-        static constexpr float RB = (1.0f + c2 * t_src) / (-c2 * (t_src - t_env));
+        // linear profiles: A(u) = A1 (1 + EA u), B(u) = B1 (1 + EB u) - the leading factors cancel in eta.  (Round 1 divided by
+        // the slopes instead, a~ = u + A1/A2 with A1/A2 ~ 1e5 / (t_src - t_env): fine for the predefined 185 K, but u in [0, 1]
+        // loses 10 bits against 1.1e4 once a user narrows the temperature gap to 9 K.  This form is exact in the limit dt -> 0.)
+        static constexpr float EA = (a1 * (t_src - t_env)) / (a0 - a1 * t_src);
+        static constexpr float EB = (-c2 * (t_src - t_env)) / (1.0f + c2 * t_src);
+        static constexpr float RA = 0.0f, RB = 0.0f;              // sigmoid profiles only
 #endif
         static constexpr float D = RB - RA;  // b~ / a~ = 1 + D / (u + RA)
     };
@@ -183,8 +212,8 @@ template <class S> struct LinonField {
 #if LINON_MIRAGE_KIND == 1 || LINON_MIRAGE_KIND == 3
     typedef vec3t<S> Pos;  // scaled offset from the sphere centre
     static __device__ __forceinline__ Pos scaled_origin(const vec3t<S> p) {
-        return vec3t<S>(p.x * Fused::scale + 0.5f * Fused::scale, p.y * Fused::scale - 0.5f * Fused::scale,
-                        p.z * Fused::scale + 0.5f * Fused::scale);  // scale (p - (-0.5, 0.5, -0.5))
+        return vec3t<S>(p.x * Fused::scale - LINON_MIRAGE_CX * Fused::scale, p.y * Fused::scale - LINON_MIRAGE_CY * Fused::scale,
+                        p.z * Fused::scale - LINON_MIRAGE_CZ * Fused::scale);  // scale (p - centre)
     }
     // u(|c'|) from q = c'.c' and rq = rsqrt(q)
     static __device__ __forceinline__ S profile(S q, S rq) {
@@ -196,7 +225,7 @@ template <class S> struct LinonField {
     }
 #else
     typedef S Pos;         // scaled signed height above the plane y = 0.1
-    static __device__ __forceinline__ Pos scaled_origin(const vec3t<S> p) { return p.y * Fused::scale - 0.1f * Fused::scale; }
+    static __device__ __forceinline__ Pos scaled_origin(const vec3t<S> p) { return p.y * Fused::scale - LINON_MIRAGE_CY * Fused::scale; }
     static __device__ __forceinline__ S profile(S y) {
 #if LINON_MIRAGE_KIND == 4
         return w_exp2(Fused::k0 - w_abs(y));
@@ -224,12 +253,17 @@ template <class S> struct LinonField {
         const S u = profile(y);
         const S d = kp.y;
 #endif
+        // eta - 1 in its cancellation-free form.  eta = a~(in) b~(out) / (a~(out) b~(in)), and the numerator minus the
+        // denominator collapses: sigmoid profiles (a~ = u + RA, b~ = u + RB)   eta = 1 + D (u_in - u) / ((u + RA)(u_in + RB)),
+        // linear profiles (a~ = 1 + EA u, b~ = 1 + EB u)   eta = 1 + (EB - EA)(u - u_in) / ((1 + EA u)(1 + EB u_in)).
+        // g_in = (D or EB - EA) / b~(in) and gd_in = u_in g_in are formed once per step.  Where the profile is flat
+        // (u == u_in: the whole room outside the mirage) eta is EXACTLY 1, like the reference's n(t_env) / n(t_env) - round 1
+        // multiplied two ratios there and got 1 +- 1 ulp, a constant bias of (eta - 1) / cos(incidence) per stage that grazing
+        // rays accumulated coherently (found with a 9 K plane mirage: 0.35 % of the endpoints off by more than 1e-3).
 #if LINON_MIRAGE_KIND >= 3
-        // eta = g(u) / g(u_in) with g = b~ / a~ = 1 + D / (u + RA):  g_in = 1 / g(u_in), gd_in = D g_in.  Sigmoid profiles
-        // only: there RA ~ 1 and g lies in [0.6, 1]; with the linear profile RA ~ 550 and 1 + D / (u + RA) would cancel.
-        const S eta = g_in + gd_in * (1.0f / (u + Fused::RA));
+        const S eta = 1.0f + (gd_in - u * g_in) * (1.0f / (u + Fused::RA));
 #else
-        const S eta = ((u + Fused::RB) * (1.0f / (u + Fused::RA))) * g_in;  // g_in = a~(in) / b~(in)
+        const S eta = 1.0f + (u * g_in - gd_in) * (1.0f / (1.0f + Fused::EA * u));
 #endif
         const S cr = w_min(1.0f, d);  // clamp(-1, 1, d) with its misordered arguments
         kk = 1.0f - eta * eta * (1.0f - cr * cr);
@@ -286,8 +320,9 @@ template <class S> struct LinonField {
     // per step |eta - 1| ~ 9e-6 E (h / 0.001) with E = exp(6 - 12 dist / max_dist) <= 1.2e-4, and the deflection summed over the
     // whole shell is (n(t_src) - n(t_env)) E(radius) <= 1.85e-4 E: 2e-8 rad at 1.25, 1e-9 rad (0.02 ulp of a direction
     // component) at 1.5.  The default stays at the radius where the reference's own arithmetic saturates.
+    // With other sigmoid constants the saturation point moves: K dist / max_dist - C >= 16.64, same 1.77 % margin.
 #ifndef LINON_QUIET_RADIUS_SIGMOID
-#define LINON_QUIET_RADIUS_SIGMOID 1.92f
+#define LINON_QUIET_RADIUS_SIGMOID ((LINON_MIRAGE_SIG_K == 12.0f && LINON_MIRAGE_SIG_C == 6.0f) ? 1.92f : 1.0177f * (16.64f + LINON_MIRAGE_SIG_C) / LINON_MIRAGE_SIG_K)
 #endif
     struct Quiet {
 #if LINON_MIRAGE_KIND >= 3
@@ -349,11 +384,11 @@ template <class S> struct LinonField {
         const S u_in = profile(pc);
 #endif
 #if LINON_MIRAGE_KIND >= 3
-        const S g_in = 1.0f - Fused::D * (1.0f / (u_in + Fused::RB));  // a~ / b~ at the step's origin
-        const S gd_in = Fused::D * g_in;
+        const S g_in = Fused::D * (1.0f / (u_in + Fused::RB));  // D / b~ at the step's origin
+        const S gd_in = u_in * g_in;
 #else
-        const S g_in = (u_in + Fused::RA) * (1.0f / (u_in + Fused::RB));
-        const S gd_in = g_in;  // unused by the linear profile
+        const S g_in = (Fused::EB - Fused::EA) * (1.0f / (1.0f + Fused::EB * u_in));  // (EB - EA) / b~ at the step's origin
+        const S gd_in = u_in * g_in;
 #endif
         S kk_min;
         vec3t<S> sum = rk4_sum<false>(pc, g_in, gd_in, dir, h, kk_min);

@@ -30,6 +30,7 @@
 #include "../device/static_kernels.h"
 #include "functions.hpp"
 #include "mesh_tables.hpp"
+#include "mirage_match.hpp"
 #include "scene.hpp"
 #include "wgsl_translate.h"
 
@@ -160,24 +161,19 @@ const char kFieldHead[] =
     "#line 1 \"field_function.wgsl\"\n";
 const char kFieldTail[] = "\n    }\n};\n#line 1 \"march_kernels.cuh\"\n";
 
-// 1..4 when `wgsl_body` is byte-identical with one of the predefined mirage bodies (src/functions.rs:36-94), else 0
-int mirage_kind(const std::string& wgsl_body) {
-    using linon::PredefinedFunction;
-    const PredefinedFunction kinds[4] = {PredefinedFunction::MirageSpherical, PredefinedFunction::MiragePlane,
-                                         PredefinedFunction::MirageSphericalSigmoid, PredefinedFunction::MiragePlaneSigmoid};
-    for (int k = 0; k < 4; ++k)
-        if (wgsl_body == linon::to_code(kinds[k])) return k + 1;
-    return 0;
-}
+// The mirage family, recognised structurally (mirage_match.hpp): kind 1..4 and the constants of the user's text, so that a
+// body with edited constants (src/main_view.rs:852-861: the body is editable text) still runs the hand-fused restatement.
+linon::MirageParams mirage_params(const std::string& wgsl_body) { return linon::match_mirage(wgsl_body); }
 
-std::string build_source(const std::string& cuda_body, int fused_kind, const linon::ModuleLayer& layer) {
+std::string build_source(const std::string& cuda_body, const linon::MirageParams& mirage, const linon::ModuleLayer& layer) {
+    const int fused_kind = mirage.kind;
     std::string s;
     s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + sizeof(kMirageFusedSrc) + cuda_body.size() + layer.members.size() + 512);
     s += "#line 1 \"wgsl_prelude.cuh\"\n";
     s += kPreludeSrc;
     s += "\n";
     if (fused_kind > 0) {  // hand-fused restatement of a predefined mirage body (fast math only)
-        s += "#define LINON_MIRAGE_KIND " + std::to_string(fused_kind) + "\n#line 1 \"mirage_fused.cuh\"\n";
+        s += linon::mirage_defines(mirage) + "#line 1 \"mirage_fused.cuh\"\n";
         s += kMirageFusedSrc;
         s += "\n#line 1 \"march_kernels.cuh\"\n";
     } else {
@@ -228,8 +224,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
         return false;
     }
     // an edited helper layer may redefine what the predefined bodies call: they then run the generic translation
-    const int fused_kind = (var.math == 2 && var.specialize && layer.empty()) ? mirage_kind(wgsl_body) : 0;
-    const std::string src = build_source(cuda_body, fused_kind, layer);
+    const linon::MirageParams mirage = (var.math == 2 && var.specialize && layer.empty()) ? mirage_params(wgsl_body) : linon::MirageParams();
+    const std::string src = build_source(cuda_body, mirage, layer);
     nvrtcProgram prog = nullptr;
     if (nvrtcCreateProgram(&prog, src.c_str(), "linon_march.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
         log = "nvrtcCreateProgram failed";
@@ -252,11 +248,11 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      "-DLINON_BVH=" + std::to_string(var.bvh),
                                      "-DLINON_QUIET_ZONE=" + std::to_string(var.quiet),
-                                     "-DLINON_QUIET_RADIUS_SIGMOID=" + float_literal(var.quiet_radius > 0 ? 0.001f * (float)var.quiet_radius : 1.92f),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
                                      "-DLINON_PACKED_OPS=" + std::to_string((var.math == 0 || getenv("LINON_DEV_UNPACKED")) ? 0 : 1),
                                      "-DLINON_STRICT_MATH=" + std::to_string(var.math == 0 ? 1 : 0)};
     if (var.pair_min_blocks > 0) opts.push_back("-DLINON_PAIR_MIN_BLOCKS=" + std::to_string(var.pair_min_blocks));
+    if (var.quiet_radius > 0) opts.push_back("-DLINON_QUIET_RADIUS_SIGMOID=" + float_literal(0.001f * (float)var.quiet_radius));
     if (var.math == 0) {
         opts.insert(opts.end(), {"--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
     } else if (var.math == 1) {
@@ -841,8 +837,10 @@ int linon_render(linon_view* v, uint32_t flags) {
     if ((do_march || do_sample) && (!v->d_tris || !v->has_camera))
         return v->fail(LINON_ERR_INVALID, "linon_render: set a mesh and a camera first");
     CK(v, cudaSetDevice(v->device));
-    v->timings = linon_timings{};
-    v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = v->ran_phases = false;
+    if (!(flags & LINON_RENDER_KEEP_TIMINGS)) {
+        v->timings = linon_timings{};
+        v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = v->ran_phases = false;
+    }
 
     if (do_march && v->opt_kernel == 1 && !v->use_bvh) {
         const int rc = alloc_queue(v, true);
@@ -1333,6 +1331,17 @@ int linon_debug_hit_triangle(linon_view* v, uint32_t n, const float* tri9, const
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuLaunchKernel(eval_hit): " + g_drv.err_str(r));
     CK(v, cudaStreamSynchronize(v->stream));
     CK(v, cudaMemcpy(t_out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return LINON_OK;
+}
+
+int linon_debug_match_mirage(const char* wgsl_body, int* kind, double* params8) {
+    if (!wgsl_body || !kind) return LINON_ERR_INVALID;
+    const linon::MirageParams m = linon::match_mirage(wgsl_body);
+    *kind = m.kind;
+    if (params8) {
+        const double v[8] = {m.t_env, m.t_src, m.max_dist, m.c[0], m.c[1], m.c[2], m.sig_k, m.sig_c};
+        memcpy(params8, v, sizeof(v));
+    }
     return LINON_OK;
 }
 

@@ -392,6 +392,16 @@ class MainView:
         return out
 
 
+def match_mirage(body: str):
+    """(kind, dict of constants) of the structural mirage-family match (csrc/host/mirage_match.hpp); kind 0 = no match."""
+    kind = C.c_int(0)
+    p = np.zeros(8, np.float64)
+    rc = capi.lib().linon_debug_match_mirage(body.encode("utf-8"), C.byref(kind), p.ctypes.data)
+    if rc != capi.OK:
+        raise LinonError(rc, "linon_debug_match_mirage")
+    return kind.value, dict(t_env=p[0], t_src=p[1], max_dist=p[2], c=(p[3], p[4], p[5]), sig_k=p[6], sig_c=p[7])
+
+
 def translate_wgsl(body: str) -> str:
     out = C.create_string_buffer(1 << 16)
     err = C.create_string_buffer(4096)
@@ -447,3 +457,98 @@ def measure_fp32_peak(device: int = 0):
     if rc != capi.OK:
         raise LinonError(rc, capi.lib().linon_last_error(None).decode())
     return t.value, sms.value
+
+
+class ShardedFrame:
+    """linon_sharded_* (include/linon_b200.h): one frame on several devices of a node, driven by one host thread.
+
+    devices[0] is the root: read_root() reads the assembled frame from it."""
+
+    def __init__(self, devices, vertices, faces, width, height, rows_per_block=32, mode=capi.SHARD_PEER_STORES):
+        L = capi.lib()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p(0)
+        rc = L.linon_sharded_create(devs, len(devices), width, height, rows_per_block, mode, C.byref(h))
+        if rc != capi.OK:
+            raise LinonError(rc, L.linon_sharded_last_error(None).decode())
+        self._s = h
+        self.width, self.height = width, height
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        f = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        self._check(L.linon_sharded_set_mesh(self._s, v.ctypes.data, v.shape[0], f.ctypes.data, f.shape[0]))
+
+    def _check(self, rc):
+        if rc != capi.OK:
+            raise LinonError(rc, capi.lib().linon_sharded_last_error(self._s).decode())
+
+    def close(self):
+        if getattr(self, "_s", None):
+            capi.lib().linon_sharded_destroy(self._s)
+            self._s = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def world(self):
+        return capi.lib().linon_sharded_world(self._s)
+
+    def view(self, rank: int) -> int:
+        return capi.lib().linon_sharded_view(self._s, rank)
+
+    def set_camera_uniform(self, camera: Camera):
+        self._check(capi.lib().linon_sharded_set_camera(self._s, C.byref(camera)))
+
+    def update_settings(self, settings: Settings):
+        self._check(capi.lib().linon_sharded_set_settings(self._s, C.byref(settings)))
+
+    def reload_shader(self, field_function: str):
+        err = C.create_string_buffer(16384)
+        rc = capi.lib().linon_sharded_set_field_function(self._s, field_function.encode("utf-8"), err, len(err))
+        if rc != capi.OK:
+            raise LinonError(rc, err.value.decode("utf-8", "replace") or capi.lib().linon_sharded_last_error(self._s).decode())
+
+    def set_option(self, option: int, value: int):
+        self._check(capi.lib().linon_sharded_set_option(self._s, option, value))
+
+    def resize_texture(self, width: int, height: int):
+        self._check(capi.lib().linon_sharded_resize(self._s, width, height))
+        self.width, self.height = width, height
+
+    def render_flags(self, flags: int):
+        self._check(capi.lib().linon_sharded_render(self._s, flags))
+
+    def sync(self):
+        self._check(capi.lib().linon_sharded_sync(self._s))
+
+    def read_root(self, buffer: int) -> np.ndarray:
+        w, h = self.width, self.height
+        shape, dtype = {capi.BUF_FINAL_RGBA8: ((h, w, 4), np.uint8), capi.BUF_RAYCAST_RGBA8: ((h, w, 4), np.uint8),
+                        capi.BUF_ENDPOINT_F32X4: ((h, w, 4), np.float32), capi.BUF_EXPONENTS_F32: ((h, w), np.float32),
+                        capi.BUF_HIT_ID_I32: ((h, w), np.int32), capi.BUF_RAY_SAMPLES: ((800, 8), np.float32),
+                        capi.BUF_SAMPLE_POS: ((8, 2), np.float32)}[buffer]
+        out = np.empty(shape, dtype)
+        rc = capi.lib().linon_read(self.view(0), buffer, out.ctypes.data, out.nbytes)
+        if rc != capi.OK:
+            raise LinonError(rc, capi.lib().linon_last_error(self.view(0)).decode())
+        return out
+
+    def counters(self, rank: int) -> Counters:
+        c = Counters()
+        rc = capi.lib().linon_get_counters(self.view(rank), C.byref(c))
+        if rc != capi.OK:
+            raise LinonError(rc, capi.lib().linon_last_error(self.view(rank)).decode())
+        return c
+
+    def timings(self, rank: int) -> Timings:
+        t = Timings()
+        rc = capi.lib().linon_get_timings(self.view(rank), C.byref(t))
+        if rc != capi.OK:
+            raise LinonError(rc, capi.lib().linon_last_error(self.view(rank)).decode())
+        return t

@@ -156,12 +156,17 @@ def generate():
     return sources + [os.path.join(HERE, "ref_api.cpp")]
 
 
-def build_custom(body: str, workdir: str, name: str = "custom") -> str:
-    """One module with a user-edited field-function body spliced in (as shipped: h_initial 0.1, adaptive sampling),
-    compiled into `workdir`; exports `wgslref_custom_field(settings, n, p_prev, p, v0, v, t, out)` and
-    `wgslref_custom_main_view(frame, outputs)`.  For differential tests of the product's own WGSL translator."""
+def build_custom(body: str, workdir: str, name: str = "custom", variant: str = "default", module_edits=()) -> str:
+    """One module with a user-edited field-function body spliced in, compiled into `workdir`; exports
+    `wgslref_custom_field(settings, n, p_prev, p, v0, v, t, out)` and `wgslref_custom_main_view(frame, outputs)`.
+    variant: one of VARIANTS' names (the reference's own string replacements, src/main_view.rs:752-829);
+    module_edits: (old, new) pairs applied to the text of main_view.wgsl first - what a user who edits the shader file
+    does (src/main.rs:206-222); every `old` must occur.  For differential tests of the product's translator and hot reload."""
     main_view = open(os.path.join(REFERENCE, "src", "main_view.wgsl"), encoding="utf-8").read()
-    text = with_field_function(main_view, body)
+    for old, new in module_edits:
+        assert old in main_view, f"module edit does not apply: {old!r}"
+        main_view = main_view.replace(old, new)
+    text = make_variant(with_field_function(main_view, body), dict(VARIANTS)[variant], [])
     src = os.path.join(workdir, name + ".cpp")
     lib = os.path.join(workdir, name + ".so")
     open(src, "w").write(

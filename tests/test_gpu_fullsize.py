@@ -20,6 +20,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
 CAP_ENHANCE = 0.01
+DEFAULT_QUIET = 1  # the library's default level of LINON_OPT_QUIET_ZONE (include/linon_b200.h)
 
 
 def gpu_frame(mv):
@@ -35,13 +36,17 @@ def view_1080p(product_lib, scene):
 
 
 @pytest.mark.parametrize("fn", PREDEFINED)
-@pytest.mark.parametrize("adaptive", [False, True])
-def test_c2_full_size_sampled_rows(view_1080p, scene, fn, adaptive):
+@pytest.mark.parametrize("adaptive,quiet", [(False, None), (True, None), (True, 0), (True, 2)])
+def test_c2_full_size_sampled_rows(view_1080p, scene, fn, adaptive, quiet):
     """C2: 1920x1080, every predefined function, default step size - as the application renders it (adaptive on) and with
-    adaptive sampling off (the variant whose endpoints are comparable)."""
+    adaptive sampling off (the variant whose endpoints are comparable).  quiet: LINON_OPT_QUIET_ZONE (None = the
+    library default; 0 = every attempt evaluates the field; 2 = identity steps outside the mirage's zone in adaptive frames too)."""
     verts, faces, _ = scene
     mv = view_1080p
     W, H = mv.size
+    if quiet is not None and int(fn) > 4:
+        pytest.skip("the quiet zone is defined by the mirage bodies only")
+    mv.set_option(capi.OPT_QUIET_ZONE, DEFAULT_QUIET if quiet is None else quiet)
     mv.reload_shader(fn.to_code())
     st = make_settings()
     mv.update_settings(st)
@@ -98,6 +103,7 @@ def test_c4_full_size_sampled_rows(view_1080p, scene):
     mv = view_1080p
     W, H = mv.size
     fn = PredefinedFunction.MirageSphericalSigmoid
+    mv.set_option(capi.OPT_QUIET_ZONE, DEFAULT_QUIET)
     mv.reload_shader(fn.to_code())
     st = make_settings(overlay_mode=1)
     mv.update_settings(st)

@@ -1,6 +1,10 @@
 """Summarises an .ncu-rep (read here on the CPU box with `ncu -i`) into profiles/<name>.md + .json.
 
 usage: python tools/ncu_summary.py gpurun_out/march_c3_r1.ncu-rep profiles/r1_march_c3 [rk4_steps_per_launch]
+                                   [--cubin-hash H] [--source-hash H] [--note TEXT]
+--cubin-hash: FNV-1a of the NVRTC cubin the capture profiled (tools/render_once.py prints it; linon_march_cubin_hash);
+--source-hash: bench.static_source_hash() of the ahead-of-time kernels.  bench.py refuses a summary whose identity is not
+the running kernel's.
 """
 import csv
 import io
@@ -36,15 +40,41 @@ KEYS = [
 UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 
 
+KEYS += [
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_drain_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio",
+    "smsp__average_warp_latency_per_inst_issued.ratio",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__t_bytes.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.per_cycle_active", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+    "smsp__warps_eligible.avg.per_cycle_active", "smsp__issue_active.avg.per_cycle_active",
+    "smsp__thread_inst_executed.sum", "smsp__inst_executed_op_branch.sum",
+]
+
+
 def main():
-    rep, out = sys.argv[1], sys.argv[2]
-    steps = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    args = sys.argv[1:]
+    extra = {}
+    for flag, key in (("--cubin-hash", "cubin_hash"), ("--source-hash", "source_hash"), ("--note", "note")):
+        if flag in args:
+            i = args.index(flag)
+            extra[key] = args[i + 1]
+            del args[i:i + 2]
+    rep, out = args[0], args[1]
+    steps = float(args[2]) if len(args) > 2 else None
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     results = []
     for r in rows[2:]:
-        d = {"kernel": r[hdr.index("Kernel Name")]}
+        d = {"kernel": r[hdr.index("Kernel Name")], **extra}
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)
@@ -77,7 +107,7 @@ def main():
             for k, v in d.items():
                 if k.startswith("_") or k == "kernel":
                     continue
-                f.write(f"| {k} | {v:,.6g} {d.get('_units', {}).get(k, '')} |\n")
+                f.write(f"| {k} | {v:,.6g} {d.get('_units', {}).get(k, '')} |\n" if isinstance(v, (int, float)) else f"| {k} | {v} |\n")
             f.write("\n")
     print(json.dumps([{k: v for k, v in d.items() if not k.startswith('_')} for d in results], indent=1)[:3000])
 
