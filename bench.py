@@ -47,7 +47,7 @@ FN_ID = 3  # MirageSphericalSigmoid: the function the application starts with (s
 BASE_W, BASE_H = 3840, 2160
 C5_W, C5_H = 8192, 8192
 ROWS_PER_BLOCK = 32
-DEFAULT_QUIET = 1     # the library's default level of LINON_OPT_QUIET_ZONE (include/linon_b200.h)
+DEFAULT_QUIET = 2     # the library's default level of LINON_OPT_QUIET_ZONE (include/linon_b200.h)
 STEPS_PER_RAY = 5001  # h_initial = 0.001: the loop of src/main_view.wgsl:244 runs 5001 times; adaptive sampling cannot trigger
 MARCH_PROFILE = os.path.join(ROOT, "profiles", "r2_march_c3.json")
 OVERLAY_PROFILE = os.path.join(ROOT, "profiles", "r2_overlay_c3.json")
@@ -340,7 +340,7 @@ def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
         max_excluded_fraction=0.02)
     variants = {}
     E = capi.RENDER_ENHANCE
-    shipped_quiet, shipped_spec = 1, 1
+    shipped_quiet, shipped_spec = DEFAULT_QUIET, 1
 
     def one(name, quiet, spec, frames):
         mv.set_option(capi.OPT_QUIET_ZONE, quiet)
@@ -434,8 +434,8 @@ def run_configs_child(args):
         for fn in PRE:
             mv.reload_shader(fn.to_code())
             variants = [("adaptive on", 0, True, None), ("adaptive off", capi.RENDER_ADAPTIVE_OFF, False, None)]
-            if int(fn) <= 4:  # the mirage family defines a quiet zone: the other level of LINON_OPT_QUIET_ZONE beside the default
-                variants.insert(1, ("adaptive on, LINON_OPT_QUIET_ZONE = %d" % (2 if DEFAULT_QUIET != 2 else 1), 0, True, 2 if DEFAULT_QUIET != 2 else 1))
+            if int(fn) <= 4:  # the mirage family defines a quiet zone: the same frame without it beside the default
+                variants.insert(1, ("adaptive on, LINON_OPT_QUIET_ZONE = 0 (every attempt evaluates the field)", 0, True, 0))
             for name, flags, adaptive, quiet in variants:
                 mv.set_option(capi.OPT_QUIET_ZONE, DEFAULT_QUIET if quiet is None else quiet)
                 r = measure(mv, flags)
@@ -795,7 +795,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--quiet-zone", type=int, default=None, choices=[0, 1, 2],
-                    help="override LINON_OPT_QUIET_ZONE (library default: 1 = straight steps outside the mirage's zone of influence)")
+                    help="override LINON_OPT_QUIET_ZONE (library default: 2 = straight / identity steps outside the mirage's zone of influence)")
     ap.add_argument("--overlay-kernel", type=int, default=None, choices=[0, 1], help="override LINON_OPT_OVERLAY_KERNEL")
     ap.add_argument("--peer-stores", type=int, default=0, choices=[0, 1],
                     help="N > 1: 1 = every rank's march stores straight into rank 0's frame buffers (CUDA IPC + NVLink) instead of "

@@ -117,9 +117,10 @@ enum {
                                     2: adaptive frames as well - per attempt, velocity = direction when every stage point lies
                                     outside the zone (diff is exactly 0 there, so the reference's noise-driven rejections
                                     outside the zone, SURVEY F20, have no counterpart).
-                                    Default 1 since round 2: measured on B200 (C3 march 191 -> 13 ms) and graded against the
-                                    oracle at the full C3 size in every bench.py run (`parity` block).  0: every step evaluates the
-                                    field (the round-1 kernel) */
+                                    Default 2 since round 2: measured on B200 (C3 march 191 -> 13 ms at level 1; C2 adaptive
+                                    frames 7.4 -> 1.3 ms MirageSpherical, 9.1 -> 5.2 ms MirageSphericalSigmoid at level 2) and
+                                    graded against the oracle at full size (tests/test_gpu_fullsize.py, bench.py `parity` and
+                                    `configs`).  0: every step evaluates the field (the round-1 kernel) */
     LINON_OPT_QUIET_RADIUS = 13, /* radius of the quiet zone of the SIGMOID mirage profiles in permille of their max_dist; 0 (default)
                                     = 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6).  1250 ... 4000: below
                                     1886 the reference's eta is 1 +- its rounding noise and the real-number deflection summed over
@@ -270,8 +271,9 @@ const char* linon_sharded_last_error(const linon_sharded* s);
 int linon_set_option(linon_view* v, int option, int value);
 int linon_get_counters(linon_view* v, linon_counters* out);
 int linon_get_timings(linon_view* v, linon_timings* out);
-/* FNV-1a (64 bit) of the cubin whose march kernel ran last (0 before the first march).  A committed ncu capture names the
- * hash of the kernel it profiled; bench.py refuses its counters when the running kernel is a different binary. */
+/* FNV-1a (64 bit) over the machine code (.text.* sections) of the cubin whose march kernel ran last (0 before the first march;
+ * line tables are left out, so an edit that only moves lines keeps the identity).  A committed ncu capture names the hash of
+ * the kernel it profiled; bench.py refuses its counters when the running kernel is a different binary. */
 int linon_march_cubin_hash(linon_view* v, uint64_t* out);
 /* Last error message of the handle (or of the failed linon_create when v is NULL). */
 const char* linon_last_error(const linon_view* v);

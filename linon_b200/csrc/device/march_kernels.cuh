@@ -124,6 +124,7 @@
 #endif
 
 #define LINON_EPS 0.0000001f  // const eps, src/main_view.wgsl:74
+#define LINON_DIFF_FLOOR 1e-7f  // resolution of the reference's own velocity evaluation (its rounding noise)
 
 struct MarchParams {
     float cam_origin[4];          // Camera.origin          (src/main_view.wgsl:7-12)
@@ -674,6 +675,17 @@ __device__ __forceinline__ bool rk4_attempt(Ray& r, const WgslSettings& st, cons
     v = rk4_velocity(r, h, st, cam);
 #if LINON_ADAPTIVE
     diff = w_length(v - r.last_v);
+#if LINON_FUSED_RK4
+    // The fused restatements are exact where the reference is noisy: outside a mirage's zone they return the direction
+    // unchanged (diff == 0) and in the tail of a profile they resolve changes of 1e-10, where the reference's evaluation adds
+    // ~1e-7 of rounding noise to every velocity.  The reference's step control is relative (diff > 10 last_diff
+    // rejects, 2 diff < last_diff restores), so that noise is what it compares in calm regions - and what restores its step
+    // there, on about every other step.  With exact values the restore test never holds again (0 < 0) and a ray leaving a
+    // plane mirage crawled at h = 0.001 to the end of the frame: 795 instead of 128 accepted steps per ray for
+    // MiragePlaneSigmoid at 1080p, measured.  The same resolution is therefore applied here: a difference below the noise
+    // floor counts as the floor (never rejects on its own) and as calm (restores the step, rk4_advance).
+    diff = fmaxf(diff, LINON_DIFF_FLOOR);
+#endif
     if (r.last_diff >= 0.0f && diff > 10.0f * r.last_diff && h > 0.002f) {
         r.h = 0.001f;
         return false;
@@ -696,7 +708,11 @@ __device__ __forceinline__ void rk4_advance(Ray& r, vec3f v, float diff, vec3f s
 #if LINON_ADAPTIVE
     r.t = r.t + r.h;
     r.last_v = v;
+#if LINON_FUSED_RK4
+    if ((2.0f * diff < r.last_diff || diff <= LINON_DIFF_FLOOR) && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
+#else
     if (2.0f * diff < r.last_diff && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
+#endif
     r.last_diff = diff;
 #else
     r.t = r.t + LINON_H_INITIAL;
@@ -1084,7 +1100,11 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS)
         while (act0 || act1) {
             const f32x2 h = r.h;
             const vec3t<f32x2> v = rk4_velocity(r, h, st, cam);
+#if LINON_FUSED_RK4
+            const f32x2 diff = w_max(w_length(v - r.last_v), f32x2(LINON_DIFF_FLOOR));  // the noise floor of rk4_attempt
+#else
             const f32x2 diff = w_length(v - r.last_v);
+#endif
             const bool2 rej = (r.last_diff >= 0.0f) && (diff > 10.0f * r.last_diff) && (h > 0.002f);
             const bool2 rejected(act0 && rej.lo, act1 && rej.hi);
             const bool2 accepted(act0 && !rej.lo, act1 && !rej.hi);
@@ -1102,7 +1122,11 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS)
             r.p = w_select(r.p, r.p + step_dir, accepted);
             r.t = s_sel(accepted, r.t + h, r.t);
             r.last_v = w_select(r.last_v, v, accepted);
+#if LINON_FUSED_RK4
+            const bool2 restore = accepted && ((2.0f * diff < r.last_diff) || (diff <= LINON_DIFF_FLOOR)) && (r.h < LINON_H_INITIAL);
+#else
             const bool2 restore = accepted && (2.0f * diff < r.last_diff) && (r.h < LINON_H_INITIAL);
+#endif
             r.h = s_sel(restore, f32x2(LINON_H_INITIAL), r.h);
             r.last_diff = s_sel(accepted, diff, r.last_diff);
             acc0 += accepted.lo ? 1u : 0u;

@@ -400,7 +400,19 @@ template <class A, class B> LINON_HD vec3t<f32x2> w_select(vec3t<A> f, vec3t<B> 
     return vec3t<f32x2>(w_select(f.x, t.x, c), w_select(f.y, t.y, c), w_select(f.z, t.z, c)); }
 template <class A, class B> LINON_HD vec4t<f32x2> w_select(vec4t<A> f, vec4t<B> t, bool2 c) {
     return vec4t<f32x2>(w_select(f.x, t.x, c), w_select(f.y, t.y, c), w_select(f.z, t.z, c), w_select(f.w, t.w, c)); }
+// WGSL's % on floats (the translator rewrites `a % b` to w_mod(a, b): C++ has no float %): x - y * trunc(x / y), lifted like
+// every two-operand builtin; vector % scalar and scalar % vector mix like the arithmetic operators
+template <class S> LINON_HD S s_mod(S x, S y) { return x - y * s_trunc(x / y); }
+LINON_W2(mod)
+template <class A, class B, LINON_REQ(B)> LINON_HD vec2t<P<A, B>> w_mod(vec2t<A> a, B s) { typedef P<A, B> S; return w_mod(vec2t<S>(a), vec2t<S>(S(s))); }
+template <class A, class B, LINON_REQ(B)> LINON_HD vec3t<P<A, B>> w_mod(vec3t<A> a, B s) { typedef P<A, B> S; return w_mod(vec3t<S>(a), vec3t<S>(S(s))); }
+template <class A, class B, LINON_REQ(B)> LINON_HD vec4t<P<A, B>> w_mod(vec4t<A> a, B s) { typedef P<A, B> S; return w_mod(vec4t<S>(a), vec4t<S>(S(s))); }
+template <class A, class B, LINON_REQ(A)> LINON_HD vec2t<P<A, B>> w_mod(A s, vec2t<B> b) { typedef P<A, B> S; return w_mod(vec2t<S>(S(s)), vec2t<S>(b)); }
+template <class A, class B, LINON_REQ(A)> LINON_HD vec3t<P<A, B>> w_mod(A s, vec3t<B> b) { typedef P<A, B> S; return w_mod(vec3t<S>(S(s)), vec3t<S>(b)); }
+template <class A, class B, LINON_REQ(A)> LINON_HD vec4t<P<A, B>> w_mod(A s, vec4t<B> b) { typedef P<A, B> S; return w_mod(vec4t<S>(S(s)), vec4t<S>(b)); }
 // integer builtins keep integer results (non-templates win overload resolution)
+LINON_HD int w_mod(int a, int b) { return a % b; }
+LINON_HD unsigned w_mod(unsigned a, unsigned b) { return a % b; }
 LINON_HD int w_select(int f, int t, bool c) { return c ? t : f; }
 LINON_HD int w_abs(int x) { return x < 0 ? -x : x; }
 LINON_HD int w_min(int a, int b) { return a < b ? a : b; }

@@ -201,9 +201,39 @@ std::string build_source(const std::string& cuda_body, const linon::MirageParams
     return s;
 }
 
-uint64_t fnv1a64(const char* p, size_t n) {
-    uint64_t h = 1469598103934665603ull;
+uint64_t fnv1a64(const char* p, size_t n, uint64_t h = 1469598103934665603ull) {
     for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+    return h;
+}
+
+// Identity of a module's MACHINE CODE: FNV-1a over the names and contents of the .text.* sections of the cubin (an ELF64
+// image), in section order.  The -lineinfo tables are left out on purpose: an edit that only moves lines in a source file
+// changes them, not the kernel - and a committed ncu capture is evidence about the kernel.
+uint64_t cubin_code_hash(const std::vector<char>& cubin) {
+    const size_t n = cubin.size();
+    const unsigned char* b = (const unsigned char*)cubin.data();
+    auto rd = [&](size_t off, int bytes) -> uint64_t {
+        uint64_t v = 0;
+        if (off + bytes > n) return 0;
+        for (int i = 0; i < bytes; ++i) v |= (uint64_t)b[off + i] << (8 * i);
+        return v;
+    };
+    if (n < 64 || memcmp(b, "\x7f" "ELF", 4) != 0 || b[4] != 2) return fnv1a64(cubin.data(), n);  // not ELF64: hash everything
+    const uint64_t shoff = rd(0x28, 8);
+    const uint64_t shentsize = rd(0x3a, 2), shnum = rd(0x3c, 2), shstrndx = rd(0x3e, 2);
+    if (!shoff || shentsize < 64 || shstrndx >= shnum || shoff + shnum * shentsize > n) return fnv1a64(cubin.data(), n);
+    const uint64_t str_off = rd(shoff + shstrndx * shentsize + 0x18, 8), str_size = rd(shoff + shstrndx * shentsize + 0x20, 8);
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t k = 0; k < shnum; ++k) {
+        const uint64_t sh = shoff + k * shentsize;
+        const uint64_t name = rd(sh, 4), off = rd(sh + 0x18, 8), size = rd(sh + 0x20, 8);
+        if (name >= str_size || str_off + name >= n) continue;
+        const char* nm = cubin.data() + str_off + name;
+        const size_t nlen = strnlen(nm, n - (str_off + name));
+        if (nlen < 5 || memcmp(nm, ".text", 5) != 0 || off + size > n) continue;
+        h = fnv1a64(nm, nlen, h);
+        h = fnv1a64(cubin.data() + off, size, h);
+    }
     return h;
 }
 
@@ -219,7 +249,7 @@ std::string float_literal(float x) {
 bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon::ModuleLayer& layer, std::vector<char>& cubin,
                    std::string& log) {
     std::string cuda_body, terr;
-    if (!linon::translate_wgsl_body(wgsl_body, cuda_body, terr)) {
+    if (!linon::translate_wgsl_body(wgsl_body, layer.names, cuda_body, terr)) {
         log = terr;
         return false;
     }
@@ -299,8 +329,15 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
             if (line.find("field_function.wgsl") != std::string::npos || line.find("main_view.wgsl") != std::string::npos) mine += line + "\n";
             pos = e + 1;
         }
-        log = mine.empty() ? full_log : mine;
-        if (log.empty()) log = nvrtcGetErrorString(rc);
+        // Only diagnostics that point into the user's own text go back across the ABI.  Anything else (the translated body
+        // broke a line of the kernel template) is reported by its message alone, without the module's paths and code.
+        if (mine.empty()) {
+            const size_t e = full_log.find("error");
+            size_t eol = e == std::string::npos ? std::string::npos : full_log.find('\n', e);
+            mine = "the field function does not fit the kernel template (" +
+                   (e == std::string::npos ? std::string(nvrtcGetErrorString(rc)) : full_log.substr(e, eol == std::string::npos ? std::string::npos : eol - e)) + ")";
+        }
+        log = mine;
         nvrtcDestroyProgram(&prog);
         return false;
     }
@@ -364,7 +401,7 @@ struct linon_view {
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 1, opt_quiet_radius = 0, opt_overlay_kernel = 1;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 0, opt_overlay_kernel = 1;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
@@ -452,7 +489,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     std::string log;
     if (!compile_cubin(body, var, v->layer, cubin, log)) return v->fail(LINON_ERR_COMPILE, log);
     Module m;
-    m.cubin_hash = fnv1a64(cubin.data(), cubin.size());
+    m.cubin_hash = cubin_code_hash(cubin);
     CUresult r = g_drv.ModuleLoadData(&m.mod, cubin.data());
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
     struct { const char* name; CUfunction* f; } fns[] = {
@@ -1180,7 +1217,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (cubin_bytes) *cubin_bytes = cubin.size();
     if (const char* hf = getenv("LINON_DUMP_CUBIN_HASH")) {  // developer aid: the hash linon_march_cubin_hash reports for this variant
         if (FILE* f = fopen(hf, "w")) {
-            fprintf(f, "%016llx\n", (unsigned long long)fnv1a64(cubin.data(), cubin.size()));
+            fprintf(f, "%016llx\n", (unsigned long long)cubin_code_hash(cubin));
             fclose(f);
         }
     }

@@ -250,6 +250,323 @@ struct Rewriter {
         return false;
     }
 
+    int line_of(int i) const {  // 1-based line of token i
+        int line = 1;
+        for (int j = 0; j < i && j < (int)t.size(); ++j)
+            if (t[j].kind == NL) ++line;
+        return line;
+    }
+    std::string at(int i) const { return "line " + std::to_string(line_of(i)) + ": "; }
+
+    // ---- pass 0: the text must be WGSL, nothing else ---------------------------------------------------------------
+    // The reference hands the body to naga, which sandboxes it; here the translated text becomes CUDA C++ that NVRTC
+    // compiles, so whatever is not WGSL must not reach the compiler: preprocessor directives (`#include "/etc/hostname"` made
+    // NVRTC read a host file), string literals, scope resolution, reserved `__` names, brackets that close the enclosing
+    // function, and EVERY identifier that is not a WGSL keyword / type / builtin, a helper of main_view.wgsl, a parameter or
+    // module-scope name, or declared in this text.  `extra` = names the module provides (helper functions, constants),
+    // `params` = the parameters of the enclosing function.
+    bool pass_sanitize(const std::set<std::string>& extra, const std::vector<std::string>& params) {
+        static const char* const kw[] = {"let", "var", "const", "if", "else", "for", "while", "loop", "break", "continue",
+                                         "continuing", "return", "switch", "case", "default", "true", "false", "fn", "discard",
+                                         "function", "private"};
+        static const char* const types[] = {"f32", "i32", "u32", "bool", "vec2", "vec3", "vec4", "vec2f", "vec3f", "vec4f",
+                                            "mat2x2", "mat3x3", "mat2x2f", "mat3x3f", "array", "ptr", "atomic", "mat4x4",
+                                            "mat4x4f", "bitcast", "f16", "vec2i", "vec3i", "vec4i", "vec2u", "vec3u", "vec4u"};
+        static const char* const helpers[] = {"rotateX", "rotateY", "rotateZ", "translate", "refraction_index", "refraction",
+                                              "point_plane_distance", "sigmoid"};
+        static const char* const module_names[] = {"PI", "settings", "camera"};
+        static const char* const members[] = {"field_weight", "mouse_pos", "overlay_mode", "central_difference_delta",
+                                              "lyapunov_scaling", "origin", "view_direction", "up", "view_matrix"};
+        std::set<std::string> known(extra);
+        for (const char* k : kw) known.insert(k);
+        for (const char* k : types) known.insert(k);
+        for (const char* k : helpers) known.insert(k);
+        for (const char* k : module_names) known.insert(k);
+        for (const std::string& k : params) known.insert(k);
+        for (const std::string& b : builtins) known.insert(b);
+        // declarations of this text (flat: WGSL scoping is checked by the C++ compiler afterwards)
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT || (t[i].text != "let" && t[i].text != "var" && t[i].text != "const")) continue;
+            int n = next_sig(i);
+            if (is_p(n, "<")) {
+                while (n >= 0 && !is_p(n, ">")) n = next_sig(n);
+                n = n >= 0 ? next_sig(n) : -1;
+            }
+            if (n >= 0 && t[n].kind == IDENT) known.insert(t[n].text);
+        }
+        std::vector<char> stack;
+        for (int i = 0; i < (int)t.size(); ++i) {
+            const Tok& k = t[i];
+            if (k.kind == PUNCT) {
+                const std::string& c = k.text;
+                if (c == "#" || c == "\"" || c == "'" || c == "\\" || c == "@" || c == "$" || c == "`" || c == "?") {
+                    err = at(i) + "'" + c + "' is not WGSL";
+                    return false;
+                }
+                if (c == ":" && is_p(next_sig(i), ":") ) {
+                    err = at(i) + "'::' is not WGSL";
+                    return false;
+                }
+                if (c == "(" || c == "{" || c == "[") stack.push_back(c[0]);
+                if (c == ")" || c == "}" || c == "]") {
+                    const char open = c == ")" ? '(' : (c == "}" ? '{' : '[');
+                    if (stack.empty() || stack.back() != open) {
+                        err = at(i) + "unbalanced '" + c + "'";
+                        return false;
+                    }
+                    stack.pop_back();
+                }
+                continue;
+            }
+            if (k.kind != IDENT) continue;
+            if (k.text.compare(0, 2, "__") == 0) {
+                err = at(i) + "'" + k.text + "': identifiers must not start with two underscores";
+                return false;
+            }
+            if (is_p(prev_sig(i), ".")) {
+                const bool swz = k.text.size() <= 4 && (k.text.find_first_not_of("xyzw") == std::string::npos ||
+                                                        k.text.find_first_not_of("rgba") == std::string::npos);
+                bool ok = swz;
+                for (const char* m : members) ok = ok || k.text == m;
+                if (!ok) {
+                    err = at(i) + "unknown member '." + k.text + "'";
+                    return false;
+                }
+                continue;
+            }
+            if (!known.count(k.text)) {
+                err = at(i) + "unknown identifier '" + k.text + "' (not a WGSL builtin, a helper of main_view.wgsl, a parameter or a declaration of this text)";
+                return false;
+            }
+        }
+        if (!stack.empty()) {
+            err = std::string("unbalanced '") + stack.back() + "'";
+            return false;
+        }
+        // loop { body continuing { ... } }: pass_control moves the continuing block to the top of the next iteration, where
+        // the declarations of the loop body are out of scope (WGSL lets a continuing block see them)
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT || t[i].text != "loop" || is_p(prev_sig(i), ".")) continue;
+            const int open = next_sig(i);
+            const int close = is_p(open, "{") ? match_fwd(open) : -1;
+            if (close < 0) continue;
+            std::set<std::string> body_decls;
+            for (int j = open + 1, depth = 0; j < close; ++j) {
+                if (is_p(j, "{")) ++depth;
+                if (is_p(j, "}")) --depth;
+                if (t[j].kind != IDENT) continue;
+                if (t[j].text == "let" || t[j].text == "var" || t[j].text == "const") {
+                    const int n = next_sig(j);
+                    if (n >= 0 && t[n].kind == IDENT) body_decls.insert(t[n].text);
+                }
+                if (depth == 0 && t[j].text == "continuing") {
+                    const int co = next_sig(j), cc = is_p(co, "{") ? match_fwd(co) : -1;
+                    for (int q = co + 1; q < cc; ++q)
+                        if (t[q].kind == IDENT && body_decls.count(t[q].text) && !is_p(prev_sig(q), ".")) {
+                            err = at(q) + "a 'continuing' block that uses '" + t[q].text + "', declared in the loop body, is not supported";
+                            return false;
+                        }
+                    break;
+                }
+            }
+        }
+        return true;
+    }
+
+    // index of the token that opens the bracket closed at `close` (same kind), -1 if none
+    int match_back(int close) const {
+        const std::string c = t[close].text, o = c == ")" ? "(" : (c == "]" ? "[" : "{");
+        int depth = 0;
+        for (int j = close; j >= 0; --j) {
+            if (is_p(j, c.c_str())) ++depth;
+            if (is_p(j, o.c_str()) && --depth == 0) return j;
+        }
+        return -1;
+    }
+    int match_fwd(int open) const {
+        const std::string o = t[open].text, c = o == "(" ? ")" : (o == "[" ? "]" : "}");
+        int depth = 0;
+        for (int j = open; j < (int)t.size(); ++j) {
+            if (is_p(j, o.c_str())) ++depth;
+            if (is_p(j, c.c_str()) && --depth == 0) return j;
+        }
+        return -1;
+    }
+    // first token of the postfix expression (primary with calls, members, indices) whose last token is `end`
+    int postfix_start(int end) const {
+        int k = end;
+        for (;;) {
+            int start;
+            if (k < 0) return -1;
+            if (is_p(k, ")") || is_p(k, "]")) {
+                const int o = match_back(k);
+                if (o < 0) return -1;
+                const int before = prev_sig(o);
+                if (is_p(k, "]")) {  // indexing: the indexed expression continues to the left
+                    k = before;
+                    continue;
+                }
+                start = (before >= 0 && t[before].kind == IDENT && !is_keyword_token(before)) ? before : o;
+            } else if (t[k].kind == IDENT || t[k].kind == NUMBER) {
+                start = k;
+            } else {
+                return -1;
+            }
+            const int dot = prev_sig(start);
+            if (is_p(dot, ".")) {  // member of something further left
+                k = prev_sig(dot);
+                continue;
+            }
+            return start;
+        }
+    }
+    bool is_keyword_token(int i) const {
+        const std::string& s = t[i].text;
+        return s == "return" || s == "if" || s == "while" || s == "for" || s == "else" || s == "switch" || s == "case";
+    }
+    // last token of the unary-prefixed postfix expression that starts at `first`
+    int unary_end(int first) const {
+        int k = first;
+        while (is_p(k, "-") || is_p(k, "!") || is_p(k, "~") || is_p(k, "+")) k = next_sig(k);
+        if (k < 0) return -1;
+        int end;
+        if (is_p(k, "(")) end = match_fwd(k);
+        else if (t[k].kind == IDENT || t[k].kind == NUMBER) end = k;
+        else return -1;
+        for (;;) {  // postfix: call, index, member
+            if (end < 0) return -1;
+            const int n = next_sig(end);
+            if (is_p(n, "(") && t[end].kind == IDENT) { end = match_fwd(n); continue; }
+            if (is_p(n, "[")) { end = match_fwd(n); continue; }
+            if (is_p(n, ".")) { end = next_sig(n); continue; }
+            return end;
+        }
+    }
+    bool unary_position(int i) const {  // is the + or - at i a sign rather than a binary operator?
+        const int p = prev_sig(i);
+        if (p < 0) return true;
+        if (t[p].kind == NUMBER) return false;
+        if (t[p].kind == IDENT) return is_keyword_token(p);
+        return !(is_p(p, ")") || is_p(p, "]"));
+    }
+
+    // ---- pass: WGSL's % works on floats, C++'s does not: a % b -> w_mod(a, b), a %= b -> a = w_mod(a, b) ----------------
+    bool pass_mod() {
+        // rewrites insert TOKENS (never edit a bracket's text): later scans must still recognise every ( ) [ ]
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != PUNCT || (t[i].text != "%" && t[i].text != "%=")) continue;
+            const int left_end = prev_sig(i), right_first = next_sig(i);
+            int start = left_end >= 0 ? postfix_start(left_end) : -1;
+            if (start < 0 || right_first < 0) {
+                err = at(i) + "cannot find the operands of '" + t[i].text + "'";
+                return false;
+            }
+            if (t[i].text == "%=") {
+                int semi = -1, depth = 0;
+                for (int j = i + 1; j < (int)t.size(); ++j) {
+                    if (is_p(j, "(") || is_p(j, "[")) ++depth;
+                    if (is_p(j, ")") || is_p(j, "]")) --depth;
+                    if (depth == 0 && is_p(j, ";")) { semi = j; break; }
+                }
+                if (semi < 0) { err = at(i) + "'%=' without a terminating ';'"; return false; }
+                std::vector<Tok> head = {{PUNCT, "="}, {WS, " "}, {IDENT, "w_mod"}, {PUNCT, "("}};
+                for (int j = start; j <= left_end; ++j) head.push_back(t[j]);
+                head.push_back({PUNCT, ","});
+                head.push_back({PUNCT, "("});
+                const std::vector<Tok> tail = {{PUNCT, ")"}, {PUNCT, ")"}};
+                t.insert(t.begin() + semi, tail.begin(), tail.end());
+                t.erase(t.begin() + i);
+                t.insert(t.begin() + i, head.begin(), head.end());
+                continue;
+            }
+            // the left operand is the whole multiplicative chain that precedes (left-associative with * and /)
+            for (;;) {
+                int sgn = prev_sig(start);
+                while ((is_p(sgn, "-") || is_p(sgn, "+") || is_p(sgn, "!")) && unary_position(sgn)) {
+                    start = sgn;
+                    sgn = prev_sig(start);
+                }
+                const int op = prev_sig(start);
+                if (!(is_p(op, "*") || is_p(op, "/"))) break;
+                const int s2 = postfix_start(prev_sig(op));
+                if (s2 < 0) { err = at(i) + "cannot find the left operand of '%'"; return false; }
+                start = s2;
+            }
+            const int end = unary_end(right_first);
+            if (end < 0) { err = at(i) + "cannot find the right operand of '%'"; return false; }
+            t[i] = {PUNCT, ","};
+            t.insert(t.begin() + end + 1, Tok{PUNCT, ")"});
+            const std::vector<Tok> head = {{IDENT, "w_mod"}, {PUNCT, "("}};
+            t.insert(t.begin() + start, head.begin(), head.end());
+            i += 2;  // the comma that replaced this %
+        }
+        return true;
+    }
+
+    // ---- pass: WGSL never converts i32 / u32 to f32 implicitly, C++ does ------------------------------------------------
+    // `let a = 1; return v * a;` is a type error in the reference (naga) and would compile here.  A conservative token-level
+    // check: a name declared as an integer (typed i32 / u32, or initialised by an integer literal) must not be a direct
+    // operand of + - * / whose other operand is a float literal, a float parameter (p_prev p v0 v t, possibly swizzled) or a
+    // name declared from a float literal / a vector constructor / with a float type.  Anything this cannot decide is left to
+    // the C++ compiler (which accepts it).
+    bool pass_intmix(const std::vector<std::string>& float_params) {
+        std::set<std::string> ints, floats(float_params.begin(), float_params.end());
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT || (t[i].text != "let" && t[i].text != "var" && t[i].text != "const")) continue;
+            int n = next_sig(i);
+            if (is_p(n, "<")) {
+                while (n >= 0 && !is_p(n, ">")) n = next_sig(n);
+                n = n >= 0 ? next_sig(n) : -1;
+            }
+            if (n < 0 || t[n].kind != IDENT) continue;
+            const std::string name = t[n].text;
+            int a = next_sig(n);
+            if (is_p(a, ":")) {
+                const int ty = next_sig(a);
+                if (ty >= 0 && (t[ty].text == "i32" || t[ty].text == "u32")) ints.insert(name);
+                else if (ty >= 0 && (t[ty].text == "f32" || t[ty].text.compare(0, 3, "vec") == 0)) floats.insert(name);
+                continue;
+            }
+            if (!is_p(a, "=")) continue;
+            const int v = next_sig(a), after = v >= 0 ? next_sig(v) : -1;
+            if (v < 0) continue;
+            if (t[v].kind == NUMBER && is_p(after, ";")) {
+                const std::string& lit = t[v].text;
+                (lit.back() == 'f' && lit.find_first_of("xX") == std::string::npos ? floats : ints).insert(name);
+            } else if (t[v].kind == IDENT && t[v].text.compare(0, 3, "vec") == 0) {
+                floats.insert(name);
+            }
+        }
+        if (ints.empty()) return true;
+        auto is_float_operand_end = [&](int k) {  // token k ends a float operand (literal, float name, or a swizzle of one)
+            if (k < 0) return false;
+            if (t[k].kind == NUMBER) return t[k].text.back() == 'f' && t[k].text.find_first_of("xX") == std::string::npos;
+            if (t[k].kind != IDENT) return false;
+            if (is_p(prev_sig(k), ".")) {
+                const int base = prev_sig(prev_sig(k));
+                return base >= 0 && t[base].kind == IDENT && floats.count(t[base].text) > 0;
+            }
+            return floats.count(t[k].text) > 0 && !is_p(next_sig(k), "(");
+        };
+        auto is_float_operand_start = [&](int k) {
+            if (k < 0) return false;
+            if (t[k].kind == NUMBER) return t[k].text.back() == 'f' && t[k].text.find_first_of("xX") == std::string::npos;
+            return t[k].kind == IDENT && floats.count(t[k].text) > 0 && !is_p(next_sig(k), "(");
+        };
+        for (int i = 0; i < (int)t.size(); ++i) {
+            if (t[i].kind != IDENT || !ints.count(t[i].text) || is_p(prev_sig(i), ".")) continue;
+            const int p = prev_sig(i), n = next_sig(i);
+            auto arith = [&](int k) { return is_p(k, "*") || is_p(k, "/") || is_p(k, "+") || is_p(k, "-"); };
+            const bool left = arith(p) && !unary_position(p) && is_float_operand_end(prev_sig(p));
+            const bool right = arith(n) && is_float_operand_start(next_sig(n));
+            if (left || right) {
+                err = at(i) + "'" + t[i].text + "' is an integer: WGSL does not convert i32 / u32 to f32 implicitly (write f32(" + t[i].text + "))";
+                return false;
+            }
+        }
+        return true;
+    }
+
     // ---- pass 1: types (vec3<f32> -> vec3f, f32( -> float( ...) --------------------------------------
     bool pass_types() {
         for (int i = 0; i < (int)t.size(); ++i) {
@@ -374,16 +691,121 @@ struct Rewriter {
         return true;
     }
 
-    // ---- pass 3: control flow parentheses --------------------------------------------------------------------
+    // ---- pass 3: control flow ----------------------------------------------------------------------------------------
+    // if / while get their parentheses; `loop { ... continuing { ... } }` and `switch e { case a, b: { ... } default: { ... } }`
+    // become their C++ forms.
     bool pass_control() {
         for (int i = 0; i < (int)t.size(); ++i) {
             if (t[i].kind != IDENT) continue;
-            const std::string& kw = t[i].text;
-            if (kw == "loop" || kw == "continuing" || kw == "switch" || kw == "fn" || kw == "discard") {
-                if (!is_p(prev_sig(i), ".")) {
-                    err = "'" + kw + "' is not supported in a field function body (use if / for / while)";
-                    return false;
+            const std::string kw = t[i].text;
+            if (is_p(prev_sig(i), ".")) continue;
+            if (kw == "fn" || kw == "discard") {
+                err = "'" + kw + "' is not supported in a field function body";
+                return false;
+            }
+            if (kw == "loop") {
+                // loop { body continuing { c; break if e; } }  ->  for (bool first_ = true;; first_ = false) { if (!first_) { c;
+                // if (e) break; } body }: the continuing block runs between iterations, also after a `continue`.  It moves to
+                // the top of the NEXT iteration, so it cannot see declarations of the loop body (rejected below).
+                const int open = next_sig(i);
+                if (!is_p(open, "{")) { err = at(i) + "expected '{' after 'loop'"; return false; }
+                const int close = match_fwd(open);
+                if (close < 0) { err = at(i) + "unbalanced '{' after 'loop'"; return false; }
+                int cont = -1;
+                for (int j = open + 1, depth = 0; j < close; ++j) {
+                    if (is_p(j, "{")) ++depth;
+                    if (is_p(j, "}")) --depth;
+                    if (depth == 0 && t[j].kind == IDENT && t[j].text == "continuing") cont = j;
                 }
+                if (cont < 0) {
+                    t[i].text = "for (;;)";
+                    continue;
+                }
+                const int copen = next_sig(cont), cclose = is_p(copen, "{") ? match_fwd(copen) : -1;
+                if (cclose < 0 || next_sig(cclose) != close) { err = at(cont) + "'continuing' must be the last statement of its loop"; return false; }
+                std::set<std::string> body_decls;
+                for (int j = open + 1; j < cont; ++j)
+                    if (t[j].kind == IDENT && (t[j].text == "let" || t[j].text == "var" || t[j].text == "const")) {
+                        const int n = next_sig(j);
+                        if (n >= 0 && t[n].kind == IDENT) body_decls.insert(t[n].text);
+                    }
+                std::string c_text;
+                for (int j = copen + 1; j < cclose; ++j) {
+                    if (t[j].kind == IDENT && body_decls.count(t[j].text) && !is_p(prev_sig(j), ".")) {
+                        err = at(j) + "a 'continuing' block that uses '" + t[j].text + "', declared in the loop body, is not supported";
+                        return false;
+                    }
+                    if (t[j].kind == IDENT && t[j].text == "break" && t[next_sig(j)].kind == IDENT && t[next_sig(j)].text == "if") {
+                        // break if e;  ->  if (e) break;
+                        const int iff = next_sig(j);
+                        int semi = -1;
+                        for (int q = iff + 1; q < cclose; ++q)
+                            if (is_p(q, ";")) { semi = q; break; }
+                        if (semi < 0) { err = at(j) + "'break if' without ';'"; return false; }
+                        std::string cond;
+                        for (int q = iff + 1; q < semi; ++q) cond += t[q].kind == NL ? " " : t[q].text;
+                        c_text += "if (" + cond + ") break;";
+                        j = semi;
+                        continue;
+                    }
+                    c_text += t[j].kind == NL ? " " : t[j].text;
+                }
+                for (int j = cont; j <= cclose; ++j)
+                    if (t[j].kind != NL) blank(j);
+                const std::string flag = "linon_first_" + std::to_string(i) + "_";
+                t[i].text = "for (bool " + flag + " = true;; " + flag + " = false)";
+                t[open].text = "{ if (!" + flag + ") { " + c_text + " }";
+                continue;
+            }
+            if (kw == "continuing") {
+                err = at(i) + "'continuing' outside a loop";
+                return false;
+            }
+            if (kw == "switch") {
+                const int first = next_sig(i);
+                int open = -1;
+                for (int j = first, depth = 0; j >= 0 && j < (int)t.size(); ++j) {
+                    if (is_p(j, "(")) ++depth;
+                    if (is_p(j, ")")) --depth;
+                    if (depth == 0 && is_p(j, "{")) { open = j; break; }
+                }
+                const int close = open >= 0 ? match_fwd(open) : -1;
+                if (first < 0 || close < 0) { err = at(i) + "malformed 'switch'"; return false; }
+                const int last = prev_sig(open);
+                t[first].text = "(" + t[first].text;
+                t[last].text += ")";
+                // clauses: `case a, b: {` / `case a {` / `default: {` / `default {`; WGSL never falls through: `break;` is appended
+                for (int j = open + 1; j < close; ++j) {
+                    if (t[j].kind != IDENT || (t[j].text != "case" && t[j].text != "default") || is_p(prev_sig(j), ".")) {
+                        if (is_p(j, "{")) j = match_fwd(j);  // a nested block that is not a clause cannot occur here, be safe
+                        continue;
+                    }
+                    int body = -1;
+                    for (int q = j + 1; q < close; ++q)
+                        if (is_p(q, "{")) { body = q; break; }
+                    const int bclose = body >= 0 ? match_fwd(body) : -1;
+                    if (bclose < 0 || bclose > close) { err = at(j) + "malformed switch clause"; return false; }
+                    bool colon = false;
+                    if (t[j].text == "case") {
+                        // selectors separated by commas: each becomes its own label; `default` may appear among them
+                        for (int q = j + 1; q < body; ++q) {
+                            if (is_p(q, ",")) {
+                                const int nq = next_sig(q);
+                                if (nq >= body || is_p(nq, ":")) { blank(q); continue; }  // trailing comma
+                                const bool dflt = t[nq].kind == IDENT && t[nq].text == "default";
+                                t[q].text = dflt ? ":" : ": case";
+                            }
+                            if (is_p(q, ":")) colon = true;
+                        }
+                    } else {
+                        for (int q = j + 1; q < body; ++q)
+                            if (is_p(q, ":")) colon = true;
+                    }
+                    if (!colon) t[body].text = ": {";
+                    t[bclose].text = "} break;";
+                    j = bclose;
+                }
+                continue;
             }
             if (kw != "if" && kw != "while") continue;
             const int first = next_sig(i);
@@ -596,7 +1018,27 @@ struct Rewriter {
 
 }  // namespace
 
+namespace {
+const std::vector<std::string> kFieldParams = {"p_prev", "p", "v0", "v", "t"};  // src/main_view.rs:853-855
+std::set<std::string> split_names(const std::string& csv) {
+    std::set<std::string> out;
+    size_t b = 0;
+    while (b <= csv.size()) {
+        const size_t e = csv.find(',', b);
+        const std::string n = csv.substr(b, e == std::string::npos ? std::string::npos : e - b);
+        if (!n.empty()) out.insert(n);
+        if (e == std::string::npos) break;
+        b = e + 1;
+    }
+    return out;
+}
+}  // namespace
+
 bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string& error) {
+    return translate_wgsl_body(body, "", cuda, error);
+}
+
+bool translate_wgsl_body(const std::string& body, const std::string& module_names, std::string& cuda, std::string& error) {
     Lexer lx(body);
     if (!lx.run()) {
         error = "WGSL translation error: " + lx.err;
@@ -605,8 +1047,15 @@ bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string
     Rewriter rw;
     rw.t = std::move(lx.out);
     // keyword-clash renaming must see the user's identifiers before passes introduce C++ keywords
-    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_fold()) {
-        error = "WGSL translation error: " + rw.err;
+    if (!rw.pass_sanitize(split_names(module_names), kFieldParams) || !rw.pass_intmix(kFieldParams) || !rw.pass_names() ||
+        !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_mod() || !rw.pass_fold()) {
+        // "line N: what" -> the format of the compiler's own diagnostics for the body, so callers parse one shape
+        if (rw.err.compare(0, 5, "line ") == 0 && rw.err.find(": ") != std::string::npos) {
+            const size_t c = rw.err.find(": ");
+            error = "field_function.wgsl(" + rw.err.substr(5, c - 5) + "): error: " + rw.err.substr(c + 2);
+        } else {
+            error = "WGSL translation error: " + rw.err;
+        }
         return false;
     }
     cuda.clear();
@@ -772,10 +1221,12 @@ template <size_t N> bool in_list(const char* const (&list)[N], const std::string
 }
 
 // translate tokens [b, e) with the statement passes; newlines are kept (keep_nl) or dropped
-bool translate_range(const std::vector<Tok>& t, int b, int e, bool keep_nl, std::string& out, std::string& err) {
+bool translate_range(const std::vector<Tok>& t, int b, int e, bool keep_nl, const std::set<std::string>& module_names,
+                     std::string& out, std::string& err) {
     Rewriter rw;
     rw.t.assign(t.begin() + b, t.begin() + e);
-    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_fold()) {
+    if (!rw.pass_sanitize(module_names, {}) || !rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() ||
+        !rw.pass_mod() || !rw.pass_fold()) {
         err = rw.err;
         return false;
     }
@@ -788,13 +1239,34 @@ bool translate_range(const std::vector<Tok>& t, int b, int e, bool keep_nl, std:
 }
 
 // `fn name(a: T, b: U) -> R { body }` -> `static __device__ __forceinline__ R name(const T a, const U b) { preamble body }`
-bool emit_function(const std::vector<Tok>& t, const RawItem& it, const std::string& preamble, std::string& out, std::string& err) {
+bool emit_function(const std::vector<Tok>& t, const RawItem& it, const std::string& preamble, const std::set<std::string>& module_names,
+                   std::string& out, std::string& err) {
     Rewriter rw;
     rw.t.assign(t.begin() + it.paren_open, t.begin() + it.end);
     const int off = it.paren_open;
     const int pc = it.paren_close - off, bo = it.brace_open - off;
-    if (!rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() || !rw.pass_fold()) {
-        err = "function '" + it.info.name + "': " + rw.err;
+    std::vector<std::string> params;  // `name : type` inside the parameter list
+    for (int i = 1; i < pc; ++i)
+        if (rw.is_p(i, ":") && rw.prev_sig(i) >= 1 && rw.t[rw.prev_sig(i)].kind == IDENT) params.push_back(rw.t[rw.prev_sig(i)].text);
+    for (int i = 1; i < pc; ++i)
+        if (rw.is_p(i, "@")) {
+            err = "function '" + it.info.name + "': parameter attributes are not supported in a helper function";
+            return false;
+        }
+    if (!rw.pass_sanitize(module_names, params) || !rw.pass_names() || !rw.pass_types() || !rw.pass_decls() || !rw.pass_control() ||
+        !rw.pass_mod() || !rw.pass_fold()) {
+        // "line N: what" counts from the function's first line: cite the module's own line like the compiler would
+        if (rw.err.compare(0, 5, "line ") == 0 && rw.err.find(": ") != std::string::npos) {
+            const size_t c = rw.err.find(": ");
+            const int rel = std::atoi(rw.err.substr(5, c - 5).c_str());
+            // the token range starts at the '(' of the parameter list, which sits on the line of `fn name`
+            int fn_line = it.info.line;
+            for (int j = it.begin; j < it.paren_open; ++j)
+                if (t[j].kind == NL) ++fn_line;
+            err = "main_view.wgsl(" + std::to_string(fn_line + rel - 1) + "): error: function '" + it.info.name + "': " + rw.err.substr(c + 2);
+        } else {
+            err = "function '" + it.info.name + "': " + rw.err;
+        }
         return false;
     }
     // parameters: name : TYPE  ->  const TYPE name   (WGSL parameters are immutable)
@@ -933,10 +1405,14 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
             }
         }
     }
+    // names a helper may use: every function and constant of the module text (the reference's own and the user's)
+    std::set<std::string> module_names;
+    for (const RawItem& it : items)
+        if (it.info.kind == "fn" || it.info.kind == "const") module_names.insert(it.info.name);
     // ---- constants: one line, re-declared at the top of every emitted function and of the field-function body ----
     for (int k : emit_const) {
         std::string text;
-        if (!translate_range(t, items[k].begin, items[k].end, false, text, err)) {
+        if (!translate_range(t, items[k].begin, items[k].end, false, module_names, text, err)) {
             error = "WGSL module error: constant '" + items[k].info.name + "': " + err;
             return false;
         }
@@ -944,7 +1420,7 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
         layer.names += (layer.names.empty() ? "" : ",") + items[k].info.name;
     }
     for (int k : emit_fn) {
-        if (!emit_function(t, items[k], layer.preamble, layer.members, err)) {
+        if (!emit_function(t, items[k], layer.preamble, module_names, layer.members, err)) {
             error = "WGSL module error: " + err;
             return false;
         }

@@ -10,6 +10,10 @@ namespace linon {
 // (src/main_view.rs:852-861).  Returns false and fills `error` when the body uses WGSL outside the
 // supported subset; line structure is preserved so compiler diagnostics map to the user's lines.
 bool translate_wgsl_body(const std::string& body, std::string& cuda, std::string& error);
+// The same with the names an installed helper layer provides (ModuleLayer::names, comma-separated): the body may call them.
+// Every other identifier must be a WGSL keyword / type / builtin, a helper of main_view.wgsl, a parameter of field_function,
+// PI / settings / camera, or declared in the body - nothing else reaches the CUDA compiler (see pass_sanitize).
+bool translate_wgsl_body(const std::string& body, const std::string& module_names, std::string& cuda, std::string& error);
 
 // ---- whole-shader hot reload (src/main.rs:206-222 -> Application::reload_compute_shader, src/application.rs:228-232
 //      -> MainView::reload_shader(device, Some(new_src), field_function), src/main_view.rs:649-690) ------------------

@@ -371,12 +371,56 @@ class Parser:
                 cond = self.expr()
                 return ("while", cond, self.block())
             if t.text == "loop":
+                # loop { statements [continuing { statements [break if e;] }] }   (WGSL spec 9.4.2, 9.4.5)
                 self.i += 1
-                body = self.block()
-                if any(s[0] == "continuing" for s in body[1]):
-                    raise WgslError(f"line {t.line}: loop/continuing is not supported")
-                return ("while", ("bool", "true"), body)
-            if t.text in ("switch", "continuing", "discard"):
+                self.expect("{")
+                body, cont, break_if = [], None, None
+                while not self.at("}"):
+                    if self.t.kind == "id" and self.t.text == "continuing":
+                        self.i += 1
+                        self.expect("{")
+                        cont = []
+                        while not self.at("}"):
+                            if self.t.kind == "id" and self.t.text == "break" and self.peek().text == "if":
+                                self.i += 2
+                                break_if = self.expr()
+                                self.expect(";")
+                                if not self.at("}"):
+                                    raise WgslError(f"line {self.t.line}: 'break if' must end the continuing block")
+                                break
+                            cont.append(self.statement())
+                        self.expect("}")
+                        if not self.at("}"):
+                            raise WgslError(f"line {self.t.line}: 'continuing' must be the last statement of its loop")
+                        break
+                    body.append(self.statement())
+                self.expect("}")
+                if cont is None:
+                    return ("while", ("bool", "true"), ("block", body))
+                return ("loop", ("block", body), ("block", cont), break_if, t.line)
+            if t.text == "switch":
+                # switch e { case s, s [:] { } default [:] { } }   (WGSL spec 9.4.1: no fall-through)
+                self.i += 1
+                sel = self.expr()
+                self.expect("{")
+                clauses = []
+                while not self.at("}"):
+                    labels = []
+                    if self.accept("default"):
+                        labels.append(None)
+                    else:
+                        self.expect("case")
+                        while True:
+                            labels.append(None if self.accept("default") else self.expr())
+                            if not self.accept(","):
+                                break
+                            if self.at(":") or self.at("{"):
+                                break
+                    self.accept(":")
+                    clauses.append((labels, self.block()))
+                self.expect("}")
+                return ("switch", sel, clauses)
+            if t.text in ("continuing", "discard"):
                 raise WgslError(f"line {t.line}: '{t.text}' is not supported by the reference transpiler")
             if t.text == "return":
                 self.i += 1
@@ -515,11 +559,15 @@ class Emitter:
                 if kind == AF:  # abstract-int operand of an abstract-float operation
                     lt = f"double({lt})" if lk == AI else lt
                     rt = f"double({rt})" if rk == AI else rt
+                if op == "%":
+                    return f"wgsl::mod({lt}, {rt})", kind
                 return f"({lt} {op} {rt})", kind
             if lk == AF:
                 lt = f"float({lt})"
             if rk == AF:
                 rt = f"float({rt})"
+            if op == "%":  # C++ has no % on floats: wgsl::mod dispatches on the operand types
+                return f"wgsl::mod({lt}, {rt})", CC
             return f"({lt} {op} {rt})", CC
         if k == "member":
             text, _ = self.expr(e[1])
@@ -664,8 +712,45 @@ class Emitter:
             out.append(pad + ("return;" if s[1] is None else f"return {self.conc(s[1])};"))
         elif k in ("break", "continue"):
             out.append(pad + k + ";")
+        elif k == "loop_break":  # a `break` of a loop whose body is wrapped for its continuing block (see "loop")
+            out.append(f"{pad}{{ {s[1]} = true; break; }}")
+        elif k == "loop":
+            # for (;;) { bool brk = false; do { body } while (false); if (brk) break; continuing; if (break_if) break; }
+            # `continue` inside the do-while leaves it and so reaches the continuing block; a `break` of THIS loop sets brk.
+            flag = f"wgsl_loop_break_{s[4]}_{len(out)}"
+            out.append(f"{pad}for (;;)")
+            out.append(pad + "{")
+            out.append(f"{pad}    bool {flag} = false;")
+            out.append(f"{pad}    do")
+            self.stmt(self.rebind_breaks(s[1], flag), out, ind + 1)
+            out.append(f"{pad}    while (false);")
+            out.append(f"{pad}    if ({flag}) break;")
+            self.stmt(s[2], out, ind + 1)
+            if s[3] is not None:
+                out.append(f"{pad}    if ({self.conc(s[3])}) break;")
+            out.append(pad + "}")
+        elif k == "switch":
+            out.append(f"{pad}switch ({self.conc(s[1])})")
+            out.append(pad + "{")
+            for labels, body in s[2]:
+                for lab in labels:
+                    out.append(f"{pad}    " + ("default:" if lab is None else f"case {self.conc(lab)}:"))
+                self.stmt(body, out, ind + 2)
+                out.append(f"{pad}        break;")
+            out.append(pad + "}")
         else:
             raise WgslError(f"unhandled statement {k}")
+
+    def rebind_breaks(self, s, flag):
+        """`break` statements that belong to the enclosing loop (not to a nested loop or switch) -> ("loop_break", flag)."""
+        k = s[0]
+        if k == "break":
+            return ("loop_break", flag)
+        if k == "block":
+            return ("block", [self.rebind_breaks(x, flag) for x in s[1]])
+        if k == "if":
+            return ("if", s[1], self.rebind_breaks(s[2], flag), None if s[3] is None else self.rebind_breaks(s[3], flag))
+        return s  # for / while / loop / switch bind their own breaks; everything else has none
 
     # ---- module ------------------------------------------------------------------------------------------------------------
     def signature(self, d):

@@ -224,6 +224,20 @@ template <int N> inline bool all(const vec<bool, N>& a) {
 }
 
 // ---- geometric builtins ----------------------------------------------------------------------------------------------
+// e1 % e2 (WGSL spec 8.7): integers truncate like C++; floats are e1 - e2 * trunc(e1 / e2); vectors component-wise, a scalar
+// operand is splatted.  C++ has no % on floats, so the transpiler emits wgsl::mod for every %.
+inline i32 mod(i32 a, i32 b) { return a % b; }
+inline u32 mod(u32 a, u32 b) { return a % b; }
+inline long long mod(long long a, long long b) { return a % b; }  // AbstractInt constant evaluation
+inline float mod(float a, float b) { return a - b * truncf(a / b); }
+inline double mod(double a, double b) { return a - b * std::trunc(a / b); }  // AbstractFloat constant evaluation
+template <class T, int N> inline vec<T, N> mod(const vec<T, N>& a, const vec<T, N>& b) {
+    vec<T, N> r;
+    for (int i = 0; i < N; ++i) r[i] = mod(a[i], b[i]);
+    return r;
+}
+template <class T, int N> inline vec<T, N> mod(const vec<T, N>& a, identity_t<T> s) { return mod(a, vec<T, N>(s)); }
+template <class T, int N> inline vec<T, N> mod(identity_t<T> s, const vec<T, N>& b) { return mod(vec<T, N>(s), b); }
 template <class T, int N> inline T dot(const vec<T, N>& a, const vec<T, N>& b) {
     T s = a[0] * b[0];
     for (int i = 1; i < N; ++i) s = s + a[i] * b[i];

@@ -14,6 +14,6 @@ def bodies():
             (2, pla.replace("30.0", "24.0").replace("0.01;", "0.015;").replace("0.0, 0.1, 0.0", "0.0, 0.18, 0.0")),
         "spherical sigmoid: retuned sigmoid, colder environment":
             (3, sphs.replace("15.0", "5.0").replace("12.0", "9.0").replace("6.0", "4.5").replace("-0.5, 0.5, -0.5", "-0.55, 0.6, -0.4")),
-        "plane sigmoid: inverted gradient (cold source)":
-            (4, plas.replace("30.0", "-10.0").replace("0.01;", "0.02;").replace("12.0", "14.0")),
+        "plane sigmoid: hotter source, higher plane, retuned sigmoid":
+            (4, plas.replace("30.0", "45.0").replace("0.0, 0.1, 0.0", "0.0, 0.14, 0.0").replace("12.0", "10.0").replace("6.0", "5.5")),
     }

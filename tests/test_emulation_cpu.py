@@ -233,7 +233,9 @@ def test_quiet_zone_adaptive_frames_meet_the_north_star_on_hit_and_colour(produc
     m = parity.compare_frames(got, ref, exclude=excl)
     assert m["hit_group_agree"] >= 0.999 and m["colour_within_1"] >= 0.99, m
     c = got["counters"]
-    assert int(c[15]) > 0.3 * (int(c[0]) + int(c[2])), c  # a good part of the attempts never evaluate the field
+    # a good part of the attempts never evaluate the field (30 % for the spherical sigmoid since the step control has the
+    # reference's noise floor: rays no longer crawl at h = 0.001 through the calm tail of the profile, see rk4_attempt)
+    assert int(c[15]) > 0.25 * (int(c[0]) + int(c[2])), c
     assert int(c[0]) >= W * H * 51
 
 

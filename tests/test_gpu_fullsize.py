@@ -20,7 +20,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 PREDEFINED = [f for f in PredefinedFunction if f != PredefinedFunction.Custom]
 CAP_ENHANCE = 0.01
-DEFAULT_QUIET = 1  # the library's default level of LINON_OPT_QUIET_ZONE (include/linon_b200.h)
+DEFAULT_QUIET = 2  # the library's default level of LINON_OPT_QUIET_ZONE (include/linon_b200.h)
 
 
 def gpu_frame(mv):
@@ -36,11 +36,12 @@ def view_1080p(product_lib, scene):
 
 
 @pytest.mark.parametrize("fn", PREDEFINED)
-@pytest.mark.parametrize("adaptive,quiet", [(False, None), (True, None), (True, 0), (True, 2)])
+@pytest.mark.parametrize("adaptive,quiet", [(False, None), (True, None), (True, 0), (True, 1)])
 def test_c2_full_size_sampled_rows(view_1080p, scene, fn, adaptive, quiet):
     """C2: 1920x1080, every predefined function, default step size - as the application renders it (adaptive on) and with
     adaptive sampling off (the variant whose endpoints are comparable).  quiet: LINON_OPT_QUIET_ZONE (None = the
-    library default; 0 = every attempt evaluates the field; 2 = identity steps outside the mirage's zone in adaptive frames too)."""
+    library default, 2 = identity steps outside the mirage's zone in adaptive frames too; 0 = every attempt evaluates the
+    field; 1 = the zone in fixed-step frames only)."""
     verts, faces, _ = scene
     mv = view_1080p
     W, H = mv.size

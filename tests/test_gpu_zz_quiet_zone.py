@@ -2,7 +2,7 @@
 
 The option was written in round 1 without GPU time (validated on the host emulation of the exact NVRTC source,
 tests/test_emulation_cpu.py), first ran on hardware in the driver's round-1 GPU tests (all green) and is the shipped path
-since round 2: level 1 (fixed-step frames) is the library default, level 2 (adaptive frames as well) stays opt-in.  The same
+since round 2: level 2 (fixed-step and adaptive frames) is the library default.  The same
 holds for the two other paths tested at the end of the file: peer stores (linon_redirect_output) and the direct overlay
 kernel (LINON_OPT_OVERLAY_KERNEL = 1, default since round 2; validated bit for bit against the oracle on the host in
 tests/test_overlay_emulation_cpu.py).  Full-size grading against the oracle: tests/test_gpu_fullsize.py and bench.py's

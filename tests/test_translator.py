@@ -99,7 +99,7 @@ def test_compile_errors_cite_the_users_line(product_lib):
 
 
 @pytest.mark.parametrize("body,needle", [
-    ("loop { break; }\nreturn v;", "loop"),
+    ("loop { var q = 1.0; continuing { q = q + 1.0; } }\nreturn v;", "continuing"),
     ("let x = 1.0h;\nreturn v;", "f16"),
     ("let a: array<f32, 3> = array<f32, 3>(1.0, 2.0, 3.0);\nreturn v;", "array"),
     ("let x = vec3<i32>(1, 2, 3);\nreturn v;", "vec3<i32>"),
@@ -167,3 +167,73 @@ def test_translated_bodies_equal_the_oracles_transcriptions(product_lib, oracle,
             oracle.lib().oracle_set_custom_field(None)
     # same compiler, same libm, no contraction: the translated text must reproduce the transcription bit for bit
     assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
+
+
+# ---- the body must be WGSL and nothing else (round-1 advisor finding: the lexer passed unknown text on to NVRTC) ----------
+@pytest.mark.parametrize("body,needle", [
+    ('#include "/etc/hostname"\nreturn v;', "'#' is not WGSL"),
+    ("#define X 1\nreturn v;", "'#' is not WGSL"),
+    ('let s = "text";\nreturn v;', "is not WGSL"),
+    ("return v; }\n__device__ void evil() {", "unbalanced '}'"),
+    ("return v * f32(threadIdx.x);", "unknown identifier 'threadIdx'"),
+    ("let q = __ldg(0);\nreturn v;", "two underscores"),
+    ("return std::sqrt(v);", "unknown identifier 'std'"),
+    ("return v * settings::x;", "'::' is not WGSL"),
+    ("asm(\"trap;\");\nreturn v;", "'asm'"),
+    ("let a = p.x ? 1.0 : 2.0;\nreturn v;", "'?' is not WGSL"),
+    ("return v * blockDim.x;", "unknown identifier 'blockDim'"),
+    ("printf(1.0);\nreturn v;", "unknown identifier 'printf'"),
+    ("return v + undefined_helper(p);", "unknown identifier 'undefined_helper'"),
+    ("return v.foo;", "unknown member '.foo'"),
+    ("return vec3<f32>(settings.secret, 0.0, 0.0);", "unknown member '.secret'"),
+    ("return (v;", "unbalanced"),
+    ("let a = vec3<f32>(1.0, 2.0, 3.0)];\nreturn a;", "unbalanced ']'"),
+    ("@compute fn f() {}\nreturn v;", "'@' is not WGSL"),
+])
+def test_text_that_is_not_wgsl_never_reaches_the_cuda_compiler(product_lib, body, needle):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl(body)
+    assert e.value.code == capi.ERR_COMPILE and needle in e.value.message, e.value.message
+    with pytest.raises(LinonError) as e:
+        compile_check(body)
+    assert e.value.code == capi.ERR_COMPILE and "field_function.wgsl(" in e.value.message or needle in e.value.message
+    assert "/tmp" not in e.value.message and "wgsl_prelude" not in e.value.message  # no module text or paths leak out
+
+
+def test_diagnostics_cite_only_the_users_own_lines(product_lib):
+    """A body that translates but does not compile: the message names field_function.wgsl lines, never the kernel template."""
+    with pytest.raises(LinonError) as e:
+        compile_check("let a = vec3<f32>(1.0, 2.0, 3.0);\nlet b = a * mat3x3<f32>(a, a);\nreturn b;")
+    assert "field_function.wgsl(2)" in e.value.message
+    for leak in ("march_kernels.cuh", "wgsl_prelude.cuh", "mirage_fused.cuh"):
+        assert leak not in e.value.message
+
+
+@pytest.mark.parametrize("body", [
+    "let a = 1;\nreturn v * a;",                                 # i32 * vec3<f32>
+    "var n: i32 = 3;\nreturn vec3<f32>(p.x * n, 0.0, 0.0);",     # f32 * i32
+    "let k = 2u;\nlet s = 0.5;\nreturn v * (s + k);",            # f32 + u32
+    "var i = 0;\nreturn v / i;",
+])
+def test_implicit_integer_to_float_mixing_is_rejected_like_naga_does(product_lib, body):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl(body)
+    assert "does not convert i32 / u32 to f32 implicitly" in e.value.message
+
+
+def test_valid_integer_code_is_not_mistaken_for_mixing(product_lib):
+    for body in ("let k = 7 / 2;\nreturn v * f32(k);", "var i = 0;\nfor (var j = 0; j < 3; j++) { i = i + j * 2; }\nreturn v * f32(i);",
+                 "let n = 3;\nlet m = n * 2 + 1;\nreturn v * 2.0 + vec3<f32>(f32(m));", "return v * 2;"):
+        assert compile_check(body) > 0
+
+
+def test_loop_switch_and_remainder_translate(product_lib):
+    out = translate_wgsl("var i = 0;\nloop {\n  if (i > 3) { break; }\n  continuing { i = i + 1; break if i > 9; }\n}\nreturn v;")
+    assert "for (bool linon_first_" in out and "if ( i > 9) break;" in out and "continuing" not in out
+    out = translate_wgsl("var a = 0.0;\nswitch i32(t) {\n  case 1, 2: { a = 1.0; }\n  default { a = 2.0; }\n}\nreturn v * a;")
+    assert "switch (int(t))" in out and "case 1: case 2: {" in out and "default : {" in out and out.count("} break;") == 2
+    out = translate_wgsl("return v * (t % 0.5) + p % 2.0;")
+    assert "w_mod(t , 0.5f)" in out and "w_mod(p , 2.0f)" in out and "%" not in out
+    for body in ("var i = 0;\nloop { i = i + 1; if (i > 4) { break; } }\nreturn v * f32(i);",
+                 "var a = 0.0;\nswitch i32(t) { case 0: { a = 1.0; } case 1, 2, default: { a = t % 0.5; } }\nreturn v * a;"):
+        assert compile_check(body) > 0

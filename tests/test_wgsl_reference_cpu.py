@@ -86,10 +86,30 @@ fn g(v: vec4<f32>, s: S, m: mat2x2<f32>) -> f32 {
 
 
 def test_unsupported_constructs_are_refused_not_guessed():
-    for src in ("fn f() { switch (1) { default: {} } }", "fn f() { loop { continuing { } } }", "alias T = f32;",
-                "fn f() -> f32 { return unknown_fn(1.0); }"):
+    for src in ("fn f() { discard; }", "fn f() { loop { continuing { } var x = 1; } }", "alias T = f32;",
+                "fn f() -> f32 { return unknown_fn(1.0); }", "fn f() { continuing { } }"):
         with pytest.raises(wgsl2cpp.WgslError):
             wgsl2cpp.transpile(src)
+
+
+def test_loop_continuing_and_switch_keep_wgsl_semantics():
+    """Round 2: the transpiler follows WGSL 9.4 for `loop { ... continuing { ... break if e; } }` (a `continue` reaches the
+    continuing block, a `break` of the loop does not) and `switch` (several selectors per clause, no fall-through)."""
+    cpp = wgsl2cpp.transpile("""
+fn f(n: i32) -> i32 {
+    var i = 0; var s = 0;
+    loop {
+        if (i == 2) { continue; }
+        if (i > n) { break; }
+        s = s + i;
+        continuing { i = i + 1; break if i > 100; }
+    }
+    switch (s % 3) { case 0, 1: { s = s + 10; } default: { s = s - 1; } }
+    return s;
+}""")
+    assert "do" in cpp and "while (false);" in cpp and "wgsl_loop_break_" in cpp and "if ((i > 100)) break;" in cpp
+    assert "case 0:" in cpp and "case 1:" in cpp and "default:" in cpp and cpp.count("break;") >= 4
+    assert "wgsl::mod(s, 3)" in cpp
 
 
 def test_a_transpiled_snippet_computes_what_wgsl_says(tmp_path):

@@ -76,11 +76,57 @@ BODIES.update({
         let w = settings.field_weight * 0.5 + f32(settings.overlay_mode) + settings.lyapunov_scaling * 1e-2;
         let o = camera.origin.xyz - p;
         return normalize(o) * w + camera.up.xyz * (t * 0.1) - camera.view_direction.xyz / (1.0 + length(o));""",
+    "loop, continuing and break if": """
+        var acc = vec3<f32>(0.0);
+        var i = 0;
+        var w = 1.0;
+        loop {
+            if (i >= 6) { break; }
+            if (i == 2) { continue; }
+            acc = acc + v * w + p * f32(i);
+            continuing {
+                i = i + 1;
+                w = w * 0.5;
+                break if w < 0.05;
+            }
+        }
+        var n = 0u;
+        loop {
+            n = n + 1u;
+            if (n > 3u) { break; }
+        }
+        return acc + vec3<f32>(f32(n), w, f32(i));""",
+    "switch with several selectors and default": """
+        let k = i32(floor(p.x * 3.0)) + 3;
+        var out = v;
+        switch k {
+            case 0, 1: { out = out * 2.0; }
+            case 2 { out = -out; }
+            case 3, default: { out = out + p; }
+            case 5: {
+                if (p.y > 0.0) { break; }
+                out = vec3<f32>(p.y);
+            }
+        }
+        switch (k % 2) {
+            case 0: { out.x = out.x + 1.0; }
+            default { out.y = out.y - 1.0; }
+        }
+        return out;""",
+    "float and integer remainder": """
+        let a = p.x * 7.0 % 0.75;
+        let b = v % 0.3 + p % vec3<f32>(0.5, 0.25, 0.125) + 2.5 % p.yzx;
+        var c = t;
+        c %= 0.7;
+        var m = i32(p.y * 10.0) * 3 % 5 - 7 % 3;
+        m %= 4;
+        let d = -p.z % 0.4 * 2.0 + (p.x + 1.0) % (0.1 + 0.2) - length(v) % 0.33;
+        return b + vec3<f32>(a, c + f32(m), d + 5.5 % 2.0);""",
 })
 
 # bodies whose arithmetic is + - * / sqrt, comparisons and integer work only: bit-exact on the device in strict mode
 EXACT = ["for loop, i32, swizzles", "integers, casts and wrap-around", "shadowing and nested control flow",
-         "settings, camera and the loop variable t"]
+         "settings, camera and the loop variable t", "loop, continuing and break if", "switch with several selectors and default"]
 
 
 def inputs(n=4096, seed=11):
