@@ -194,8 +194,17 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
  * main_view, their constants, structs or bindings - recognised by token hashes of the reference's declarations)
  * returns LINON_ERR_UNSUPPORTED naming the declaration; a syntax or compile error returns LINON_ERR_COMPILE with
  * diagnostics that cite main_view.wgsl line numbers.  In both cases the previous module and kernel stay live (:677-679).
- * While a helper layer is installed the predefined mirage bodies run their generic translation. */
+ * While a helper layer is installed the predefined mirage bodies run their generic translation.
+ * Also hot-reloaded: the march-level CONSTANTS of the module - eps, backface_culling, use_lighting, linear_mode, light_color,
+ * ambient_strength, shininess (src/main_view.wgsl:65-76), adaptive_sampling and sample_outline_rays (:227, :337) and the VALUES
+ * of the step size, horizon and step-control literals of nonlinear_ray_color / sample_rays (:241-267, :287-288) - which
+ * become macros of the kernel template (a changed h_initial disables Enhance's text replacement, like in the reference). */
 int linon_reload_shader_source(linon_view* v, const char* wgsl_module_source, char* err, size_t err_len);
+/* MainView::reload_shader(device, Some(new_src), field_function) as ONE step (:649-690 compiles new_src with the new field
+ * function spliced in): the module and the body are validated together and committed together, or neither is - a helper
+ * renamed in both at once is accepted although neither half would compile against the other's old state.
+ * wgsl_module_source NULL or "" = the stock module. */
+int linon_reload_shader(linon_view* v, const char* wgsl_module_source, const char* wgsl_body, char* err, size_t err_len);
 /* Comma-separated names of the declarations the installed helper layer overrides or adds ("" = stock module). */
 int linon_module_overrides(linon_view* v, char* names, size_t names_len);
 /* MainView::render (:831-849), render_high_accuracy (:778-802), render_outline_rays (:804-829) by flags.
@@ -228,6 +237,24 @@ int linon_set_shard(linon_view* v, uint32_t rank, uint32_t world, uint32_t rows_
  *                     mapping lives until linon_destroy).
  * The caller orders the root's overlay after the other shards' marches (stream sync on each rank + a barrier). */
 int linon_redirect_output(linon_view* v, int buffer, void* device_ptr);
+/* ---- display hand-off without a copy ---------------------------------------------------------------------
+ * The reference SHOWS two of the path's outputs: `texture` is registered with egui as a native texture
+ * (src/main_view.rs:114-115, re-registered on resize :569-570) and `ray_samples_buffer` is the vertex buffer of the reference
+ * view's second draw (src/reference_view.rs:381-388, src/application.rs:514-518).  linon_export_buffer_fd moves
+ * LINON_BUF_FINAL_RGBA8 or LINON_BUF_RAY_SAMPLES into an exportable device allocation (CUDA virtual memory management, POSIX
+ * file descriptor; the contents are kept) and returns a NEW file descriptor for it each call (the caller closes it) together
+ * with the size of the allocation (>= linon_buffer_bytes, rounded up to the allocation granularity).  A Vulkan / wgpu-hal host
+ * imports the descriptor as VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT memory and binds a linear buffer (ray samples: vertex
+ * buffer, stride 32) or copies buffer-to-image on its own queue (final image: tightly packed rgba8, row 0 = top); the frames
+ * then never cross PCIe.  The buffer keeps its place across renders; linon_resize reallocates the frame buffers, after which
+ * the final image must be exported again (as the reference re-registers its texture).  Synchronisation: linon_sync (or a CUDA
+ * external semaphore of the host's own) before the graphics queue reads. */
+int linon_export_buffer_fd(linon_view* v, int buffer, int* fd, size_t* allocation_bytes);
+/* The consumer side for a CUDA host (and the tests): maps an exported descriptor in the calling process / context and returns the
+ * device pointer; the descriptor can be closed afterwards.  linon_release_import unmaps.  linon_copy_to_host reads through it. */
+int linon_import_buffer_fd(int device, int fd, size_t allocation_bytes, void** device_ptr, void** import_handle);
+int linon_release_import(void* import_handle);
+int linon_copy_to_host(int device, const void* device_ptr, void* dst, size_t bytes);
 int linon_ipc_export(linon_view* v, int buffer, void* handle64);
 int linon_ipc_open(linon_view* v, const void* handle64, void** device_ptr);
 
@@ -290,8 +317,9 @@ int linon_compile_check_module(const char* wgsl_module_source, const char* wgsl_
 /* Module translator alone: the CUDA member functions generated for the helper layer (out) and the names emitted. */
 int linon_translate_wgsl_module(const char* wgsl_module_source, char* out, size_t out_len, char* names, size_t names_len,
                                 char* err, size_t err_len);
-/* Top-level declarations of a WGSL module, one per line: "<kind> <name> <token hash> <line>" (used to generate the
- * table of the reference's own declarations, tools/gen_module_hashes.py). */
+/* Top-level declarations of a WGSL module, one per line: "<kind> <name> <token hash> <line> <hash with the numeric literals
+ * masked> <n> <the n numeric literals>" (used to generate the tables of the reference's own declarations,
+ * tools/gen_module_hashes.py). */
 int linon_scan_wgsl_module(const char* wgsl_module_source, char* out, size_t out_len, char* err, size_t err_len);
 
 /* Parity/debug entry points: evaluate the CURRENT field function / helper library / hit_triangle on arrays

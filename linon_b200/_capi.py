@@ -71,6 +71,7 @@ PROTOTYPES = [
     ("linon_resize", _I, [_P, _U, _U]),
     ("linon_set_field_function", _I, [_P, _CP, _P, _S]),
     ("linon_reload_shader_source", _I, [_P, _CP, _P, _S]),
+    ("linon_reload_shader", _I, [_P, _CP, _CP, _P, _S]),
     ("linon_module_overrides", _I, [_P, _P, _S]),
     ("linon_render", _I, [_P, _U]),
     ("linon_sync", _I, [_P]),
@@ -80,6 +81,10 @@ PROTOTYPES = [
     ("linon_stream", _P, [_P]),
     ("linon_set_shard", _I, [_P, _U, _U, _U]),
     ("linon_redirect_output", _I, [_P, _I, _P]),
+    ("linon_export_buffer_fd", _I, [_P, _I, C.POINTER(_I), C.POINTER(_S)]),
+    ("linon_import_buffer_fd", _I, [_I, _I, _S, C.POINTER(_P), C.POINTER(_P)]),
+    ("linon_release_import", _I, [_P]),
+    ("linon_copy_to_host", _I, [_I, _P, _P, _S]),
     ("linon_ipc_export", _I, [_P, _I, _P]),
     ("linon_ipc_open", _I, [_P, _P, C.POINTER(_P)]),
     ("linon_sharded_create", _I, [_P, _U, _U, _U, _U, _I, C.POINTER(_P)]),

@@ -123,7 +123,54 @@
 #define LINON_PAIR_MIN_BLOCKS (512 / LINON_BLOCK)  // 16 resident warps / SM = 32 rays per scheduler slot pair: <= 128 registers
 #endif
 
-#define LINON_EPS 0.0000001f  // const eps, src/main_view.wgsl:74
+// ---- the march-level constants of the reference's module (src/main_view.wgsl:65-76, :227, :241-267, :281-313) -------------
+// A user who edits main_view.wgsl (the file watcher of src/main.rs:206-222 recompiles the whole shader) can change these;
+// linon_reload_shader_source maps such edits to the macros below (csrc/host/wgsl_translate.cpp: march_edits) instead of
+// refusing the module.  The defaults are the reference's literals.
+#ifndef LINON_EPS
+#define LINON_EPS 0.0000001f           // const eps, src/main_view.wgsl:74
+#endif
+#ifndef LINON_BACKFACE_CULLING
+#define LINON_BACKFACE_CULLING 0       // const backface_culling, :65 (hit_triangle rejects a < eps instead of |a| < eps)
+#endif
+#ifndef LINON_USE_LIGHTING
+#define LINON_USE_LIGHTING 1           // const use_lighting, :73 (0: colour = abs(normal), alpha 1)
+#endif
+#ifndef LINON_LINEAR_MODE
+#define LINON_LINEAR_MODE 0            // const linear_mode, :72 (1: one straight ray_color(origin, dir, 100.0) per pixel, no march)
+#endif
+#ifndef LINON_AMBIENT
+#define LINON_AMBIENT 0.01f            // const ambient_strength, :68
+#endif
+#ifndef LINON_SHININESS
+#define LINON_SHININESS 64.0f          // const shininess, :69
+#endif
+#ifndef LINON_LIGHT_R
+#define LINON_LIGHT_R 1.0f             // const light_color, :67
+#define LINON_LIGHT_G 1.0f
+#define LINON_LIGHT_B 1.0f
+#endif
+#ifndef LINON_T_MAX
+#define LINON_T_MAX 5.0f               // the horizon of `for (; t <= 5.0;)`, :244
+#endif
+#ifndef LINON_REJECT_FACTOR
+#define LINON_REJECT_FACTOR 10.0f      // diff > 10.0 * last_diff, :252
+#endif
+#ifndef LINON_REJECT_MIN_H
+#define LINON_REJECT_MIN_H 0.002f      // ... && h > 0.002, :252
+#endif
+#ifndef LINON_SMALL_H
+#define LINON_SMALL_H 0.001f           // h = 0.001 after a rejection, :253
+#endif
+#ifndef LINON_RESTORE_FACTOR
+#define LINON_RESTORE_FACTOR 2.0f      // 2.0 * diff < last_diff, :267
+#endif
+#ifndef LINON_SAMPLE_H
+#define LINON_SAMPLE_H 0.001f          // sample_rays: let h = 0.001, :287
+#endif
+#ifndef LINON_SAMPLE_STEPS
+#define LINON_SAMPLE_STEPS 5000        // sample_rays: let steps: i32 = 5000, :288 (a multiple of the 100 samples per ray)
+#endif
 #define LINON_DIFF_FLOOR 1e-7f  // resolution of the reference's own velocity evaluation (its rounding noise)
 
 struct MarchParams {
@@ -253,7 +300,8 @@ __device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int 
     const vec3f q = w_cross(s, edge1);
     const float v = f * w_dot(direction, q);
     const float t = f * w_dot(edge2, q);
-    const bool ok = !(det > -LINON_EPS && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) &&
+    // `if ((backface_culling || a > -eps) && a < eps) { return -1.0; }`, src/main_view.wgsl:156
+    const bool ok = !((LINON_BACKFACE_CULLING || det > -LINON_EPS) && det < LINON_EPS) && !(u < 0.0f || u > 1.0f) &&
                     !(v < 0.0f || u + v > 1.0f) && (t > LINON_EPS);
     const float t_new = ok ? t : -1.0f;
 #if LINON_BVH
@@ -568,13 +616,17 @@ __device__ __forceinline__ int straight_clear_steps(const float4* __restrict__ s
 __device__ __forceinline__ vec3f shade(const float4* __restrict__ s_tri, int id, vec3f direction) {
     const float4 b = s_tri[3 * id + 1], c = s_tri[3 * id + 2];
     const vec3f normal = w_normalize(w_cross(vec3f(b.x, b.y, b.z), vec3f(c.x, c.y, c.z)));
-    const vec3f light_color(1.0f, 1.0f, 1.0f);
-    const vec3f ambient = 0.01f * light_color;
+#if !LINON_USE_LIGHTING
+    return w_abs(normal);  // `if (!use_lighting) { return vec4<f32>(abs(normal), 1.0); }`, src/main_view.wgsl:201-204
+#else
+    const vec3f light_color(LINON_LIGHT_R, LINON_LIGHT_G, LINON_LIGHT_B);
+    const vec3f ambient = LINON_AMBIENT * light_color;
     float intensity = w_max(w_dot(normal, -direction), 0.0f);
     if (intensity == 0.0f) intensity = w_max(w_dot(-normal, -direction), 0.0f);
     const vec3f diffuse = intensity * light_color;
-    const vec3f specular = w_pow(intensity, 64.0f) * light_color;
+    const vec3f specular = w_pow(intensity, LINON_SHININESS) * light_color;
     return (ambient + diffuse + specular) * w_abs(normal);
+#endif
 }
 
 // rgba8unorm store conversion: clamp to [0,1], x255, round to nearest even; NaN -> 0.
@@ -686,8 +738,8 @@ __device__ __forceinline__ bool rk4_attempt(Ray& r, const WgslSettings& st, cons
     // floor counts as the floor (never rejects on its own) and as calm (restores the step, rk4_advance).
     diff = fmaxf(diff, LINON_DIFF_FLOOR);
 #endif
-    if (r.last_diff >= 0.0f && diff > 10.0f * r.last_diff && h > 0.002f) {
-        r.h = 0.001f;
+    if (r.last_diff >= 0.0f && diff > LINON_REJECT_FACTOR * r.last_diff && h > LINON_REJECT_MIN_H) {
+        r.h = LINON_SMALL_H;
         return false;
     }
 #else
@@ -709,9 +761,9 @@ __device__ __forceinline__ void rk4_advance(Ray& r, vec3f v, float diff, vec3f s
     r.t = r.t + r.h;
     r.last_v = v;
 #if LINON_FUSED_RK4
-    if ((2.0f * diff < r.last_diff || diff <= LINON_DIFF_FLOOR) && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
+    if ((LINON_RESTORE_FACTOR * diff < r.last_diff || diff <= LINON_DIFF_FLOOR) && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
 #else
-    if (2.0f * diff < r.last_diff && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
+    if (LINON_RESTORE_FACTOR * diff < r.last_diff && r.h < LINON_H_INITIAL) r.h = LINON_H_INITIAL;
 #endif
     r.last_diff = diff;
 #else
@@ -738,6 +790,33 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
     const unsigned int slot = blockIdx.x * LINON_BLOCK + threadIdx.x;
     int x, local_row;
     StepCounters cnt = {0u, 0u, 0u, 0u, 0u};
+#if LINON_LINEAR_MODE
+    // `const linear_mode: bool = true` (src/main_view.wgsl:72, :368-370): one straight ray per pixel,
+    // textureStore(ttarget, coords, ray_color(origin, dir, 100.0)) - the colour's alpha is the hit distance t (0 and a black
+    // pixel on a miss), and `mapping` is NOT written: endpoints keep whatever the previous frame left there.
+    if (slot < P.n_ray_slots && slot_to_pixel(P, slot, x, local_row)) {
+        Ray r;
+        init_ray(P, x, local_row, r);
+        float t_hit, nearest;
+        int id;
+        intersect_mesh(s_tri, s_range, P.bvh, r.p, r.dir, 100.0f, l1_norm(r.p), t_hit, id, nearest, cnt.face_tests);
+        const size_t pix = (size_t)texture_row(P, local_row) * P.width + x;
+        uchar4 c = make_uchar4(0, 0, 0, 0);
+        int hit = -1;
+        if (t_hit > 0.0f && t_hit < 100.0f) {
+            const vec3f rgb = shade(s_tri, id, r.dir);
+            c = pack_color(rgb);
+#if LINON_USE_LIGHTING
+            c.w = unorm8(t_hit);  // vec4<f32>(result, t), src/main_view.wgsl:217
+#endif
+            hit = LINON_FACE_ID(s_tri, id);
+        }
+        P.raycast[pix] = c;
+        P.hit_id[pix] = hit;
+    }
+    flush_counters(P, cnt);
+    return;
+#endif
 #if !LINON_ADAPTIVE
     // Fixed step (Enhance, or adaptive sampling switched off): every ray runs the same P.n_fixed_steps iterations, so
     // the whole warp stays converged from the first step to the last.  Padding lanes outside the frame repeat the nearest
@@ -945,7 +1024,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         sd.reset();
         vec3f color(0.0f, 0.0f, 0.0f);
         int hit = -1;
-        for (; r.t <= 5.0f;) {
+        for (; r.t <= LINON_T_MAX;) {
             vec3f v, step_dir;
             float diff;
 #if LINON_QUIET_ZONE
@@ -1105,11 +1184,11 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS)
 #else
             const f32x2 diff = w_length(v - r.last_v);
 #endif
-            const bool2 rej = (r.last_diff >= 0.0f) && (diff > 10.0f * r.last_diff) && (h > 0.002f);
+            const bool2 rej = (r.last_diff >= 0.0f) && (diff > LINON_REJECT_FACTOR * r.last_diff) && (h > LINON_REJECT_MIN_H);
             const bool2 rejected(act0 && rej.lo, act1 && rej.hi);
             const bool2 accepted(act0 && !rej.lo, act1 && !rej.hi);
             cnt.rejected += (rejected.lo ? 1u : 0u) + (rejected.hi ? 1u : 0u);
-            r.h = s_sel(rejected, f32x2(0.001f), r.h);
+            r.h = s_sel(rejected, f32x2(LINON_SMALL_H), r.h);
 #if LINON_FW_ONE
             const vec3t<f32x2> new_dir = v;
 #else
@@ -1123,20 +1202,20 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_PAIR_MIN_BLOCKS)
             r.t = s_sel(accepted, r.t + h, r.t);
             r.last_v = w_select(r.last_v, v, accepted);
 #if LINON_FUSED_RK4
-            const bool2 restore = accepted && ((2.0f * diff < r.last_diff) || (diff <= LINON_DIFF_FLOOR)) && (r.h < LINON_H_INITIAL);
+            const bool2 restore = accepted && ((LINON_RESTORE_FACTOR * diff < r.last_diff) || (diff <= LINON_DIFF_FLOOR)) && (r.h < LINON_H_INITIAL);
 #else
-            const bool2 restore = accepted && (2.0f * diff < r.last_diff) && (r.h < LINON_H_INITIAL);
+            const bool2 restore = accepted && (LINON_RESTORE_FACTOR * diff < r.last_diff) && (r.h < LINON_H_INITIAL);
 #endif
             r.h = s_sel(restore, f32x2(LINON_H_INITIAL), r.h);
             r.last_diff = s_sel(accepted, diff, r.last_diff);
             acc0 += accepted.lo ? 1u : 0u;
             acc1 += accepted.hi ? 1u : 0u;
-            act0 = act0 && (r.t.lo <= 5.0f);
-            act1 = act1 && (r.t.hi <= 5.0f);
+            act0 = act0 && (r.t.lo <= LINON_T_MAX);
+            act1 = act1 && (r.t.hi <= LINON_T_MAX);
         }
 #else
         // fixed step: both rays are in lockstep (same t), every attempt is accepted
-        for (; r.t.lo <= 5.0f;) {
+        for (; r.t.lo <= LINON_T_MAX;) {
             const vec3t<f32x2> v = rk4_velocity(r, LINON_H_INITIAL, st, cam);
 #if LINON_FW_ONE
             r.dir = v;
@@ -1298,7 +1377,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 rk4_advance(r, v, diff, step_dir);
                 ++steps;
                 ++cnt.accepted;
-                if (!(r.t <= 5.0f)) {
+                if (!(r.t <= LINON_T_MAX)) {
                     if (!has_color) cnt.prehit += steps;
                     P.raycast[pix] = pack_color(color);
                     P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
@@ -1391,7 +1470,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 ++cnt.prehit;
                 rk4_advance(r, v, diff, step_dir);
                 ++cnt.accepted;
-                const bool finished = !(r.t <= 5.0f);
+                const bool finished = !(r.t <= LINON_T_MAX);
                 if (finished) {
                     P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
                     if (!hit_now) {  // never hit: black, alpha 1 (src/main_view.wgsl:275-277)
@@ -1481,7 +1560,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
             if (rk4_attempt(r, st, cam, v, diff, step_dir)) {
                 rk4_advance(r, v, diff, step_dir);
                 ++cnt.accepted;
-                if (!(r.t <= 5.0f)) {
+                if (!(r.t <= LINON_T_MAX)) {
                     P.endpoint[pix] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
                     alive = false;
                 }
@@ -1522,8 +1601,8 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
     r.t = 0.0f;
     r.last_v = vec3f(0.0f, 0.0f, 0.0f);
     r.last_diff = -1.0f;
-    r.h = 0.001f;
-    const float h = 0.001f;
+    r.h = LINON_SAMPLE_H;
+    const float h = LINON_SAMPLE_H;
     const float4 colour = make_float4(c_sample_colors[k][0], c_sample_colors[k][1], c_sample_colors[k][2], 0.5f);
 #if LINON_QUIET_ZONE && LINON_FW_ONE
     // LINON_QUIET_ZONE (opt-in): outside the body's zone of influence the Runge-Kutta velocity is the direction itself, so the
@@ -1532,9 +1611,10 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
     // collective: only lanes 0..7 are alive here.  The serial chain of a sample ray is what a small frame waits for.
     int quiet_left = 0;
 #endif
-    for (int i = 0; i < 5000; ++i) {
+    constexpr int sample_step_size = LINON_SAMPLE_STEPS / 100;  // steps / sample_steps, src/main_view.wgsl:292-293
+    for (int i = 0; i < LINON_SAMPLE_STEPS; ++i) {
 #if LINON_QUIET_ZONE && LINON_FW_ONE
-        if (quiet_left == 0) quiet_left = min(LinonField<float>::quiet_steps(r.p, r.dir, h), 5000);
+        if (quiet_left == 0) quiet_left = min(LinonField<float>::quiet_steps(r.p, r.dir, h), LINON_SAMPLE_STEPS);
         vec3f v;
         if (quiet_left > 0) {
             v = r.dir;
@@ -1551,8 +1631,8 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
         r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
 #endif
         const vec3f step_dir = r.dir * h;
-        if (i % 50 == 0) {
-            const int index = k * 100 + i / 50;
+        if (i % sample_step_size == 0) {
+            const int index = k * 100 + i / sample_step_size;
             S.ray_samples[2 * index] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
             S.ray_samples[2 * index + 1] = colour;
         }

@@ -60,6 +60,18 @@ struct Driver {
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    // virtual memory management: exportable allocations for the display hand-off (linon_export_buffer_fd)
+    CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    bool has_vmm = false;
     std::string error;
 
     bool load() {
@@ -78,6 +90,18 @@ struct Driver {
         FuncGetAttribute = (decltype(FuncGetAttribute))sym("cuFuncGetAttribute");
         OccupancyMaxActiveBlocksPerMultiprocessor =
             (decltype(OccupancyMaxActiveBlocksPerMultiprocessor))sym("cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        MemGetAllocationGranularity = (decltype(MemGetAllocationGranularity))sym("cuMemGetAllocationGranularity");
+        MemCreate = (decltype(MemCreate))sym("cuMemCreate");
+        MemRelease = (decltype(MemRelease))sym("cuMemRelease");
+        MemAddressReserve = (decltype(MemAddressReserve))sym("cuMemAddressReserve");
+        MemAddressFree = (decltype(MemAddressFree))sym("cuMemAddressFree");
+        MemMap = (decltype(MemMap))sym("cuMemMap");
+        MemUnmap = (decltype(MemUnmap))sym("cuMemUnmap");
+        MemSetAccess = (decltype(MemSetAccess))sym("cuMemSetAccess");
+        MemExportToShareableHandle = (decltype(MemExportToShareableHandle))sym("cuMemExportToShareableHandle");
+        MemImportFromShareableHandle = (decltype(MemImportFromShareableHandle))sym("cuMemImportFromShareableHandle");
+        has_vmm = MemGetAllocationGranularity && MemCreate && MemRelease && MemAddressReserve && MemAddressFree && MemMap &&
+                  MemUnmap && MemSetAccess && MemExportToShareableHandle && MemImportFromShareableHandle;
         if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString ||
             !FuncGetAttribute || !OccupancyMaxActiveBlocksPerMultiprocessor) {
             error = "libcuda.so.1 lacks a required entry point";
@@ -144,6 +168,7 @@ struct Module {
     CUfunction tiles = nullptr, pairs = nullptr, refill = nullptr, phase_a = nullptr, phase_b = nullptr, sample = nullptr,
                eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr, eval_rk4 = nullptr;
     int regs_tiles = 0, regs_pairs = 0, regs_refill = 0, regs_phase_a = 0, regs_phase_b = 0;
+    uint64_t last_use = 0;  // linon_view::module_clock at the last get_module
     uint64_t cubin_hash = 0;  // FNV-1a of the cubin: ties a committed ncu capture to the kernel that is running
 };
 
@@ -169,6 +194,7 @@ std::string build_source(const std::string& cuda_body, const linon::MirageParams
     const int fused_kind = mirage.kind;
     std::string s;
     s.reserve(sizeof(kPreludeSrc) + sizeof(kMarchSrc) + sizeof(kMirageFusedSrc) + cuda_body.size() + layer.members.size() + 512);
+    s += layer.march_defines;  // march-level constants of an edited main_view.wgsl (macros of march_kernels.cuh)
     s += "#line 1 \"wgsl_prelude.cuh\"\n";
     s += kPreludeSrc;
     s += "\n";
@@ -351,7 +377,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
 }
 
 std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
-    return layer.members + "\x01" + layer.preamble + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
+    return layer.members + "\x01" + layer.preamble + "\x01" + layer.march_defines + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
                v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh, v.quiet, v.quiet_radius) + body;
 }
 
@@ -399,6 +425,8 @@ struct linon_view {
     std::string body;  // current WGSL body
     std::map<std::string, Module> modules;
     std::map<std::string, bool> pair_unfit;  // bodies whose LinonField<f32x2> instantiation failed to compile
+    mutable std::map<std::string, bool> mirage_cache;  // body -> member of the mirage family (csrc/host/mirage_match.hpp)
+    uint64_t module_clock = 0;  // use counter for the LRU eviction of `modules`
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
         opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 0, opt_overlay_kernel = 1;
@@ -414,6 +442,13 @@ struct linon_view {
     float4* out_endpoint = nullptr;
     int* out_hit = nullptr;
     std::vector<void*> ipc_mappings;  // cudaIpcOpenMemHandle results, closed by linon_destroy
+    // display hand-off (linon_export_buffer_fd): buffers that live in an exportable allocation instead of cudaMalloc memory
+    struct VmmAlloc {
+        CUmemGenericAllocationHandle handle = 0;
+        CUdeviceptr ptr = 0;
+        size_t size = 0;
+    };
+    std::map<int, VmmAlloc> exported;  // LINON_BUF_* -> the allocation that backs it now
 
     int fail(int code, const std::string& msg) {
         error = msg;
@@ -430,6 +465,13 @@ namespace {
             return (v)->fail(LINON_ERR_CUDA, fmt("%s failed: %s", #call, cudaGetErrorString(e__)));     \
     } while (0)
 
+// Pixel indices are 32-bit ints in the kernels (texture_row * width + x, ray slots) and the outline search packs x and y into
+// 21-bit key fields (csrc/device/outline_keys.cuh): larger frames are refused instead of overflowing (cudaMalloc would succeed
+// on a 180 GB part).
+bool frame_size_ok(uint32_t W, uint32_t H) {
+    return W >= 2 && H >= 2 && W <= 65536u && H <= 65536u && (uint64_t)W * H < (1ull << 31);
+}
+
 uint32_t count_local_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t rpb) {
     uint32_t n = 0;
     for (uint32_t b = 0, y = 0; y < H; ++b, y += rpb)
@@ -437,7 +479,22 @@ uint32_t count_local_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t rp
     return n;
 }
 
+// frees a buffer whichever way it was allocated (cudaMalloc, or an exportable allocation mapped by linon_export_buffer_fd)
+void release_buffer(linon_view* v, int buffer, void* ptr) {
+    auto it = v->exported.find(buffer);
+    if (it == v->exported.end()) {
+        cudaFree(ptr);
+        return;
+    }
+    g_drv.MemUnmap(it->second.ptr, it->second.size);
+    g_drv.MemRelease(it->second.handle);
+    g_drv.MemAddressFree(it->second.ptr, it->second.size);
+    v->exported.erase(it);
+}
+
 void free_frame_buffers(linon_view* v) {
+    release_buffer(v, LINON_BUF_FINAL_RGBA8, v->d_final);
+    v->d_final = nullptr;
     cudaFree(v->d_final); cudaFree(v->d_raycast); cudaFree(v->d_endpoint); cudaFree(v->d_exponents);
     cudaFree(v->d_hit); cudaFree(v->d_q_pixel); cudaFree(v->d_q_state);
     v->d_final = v->d_raycast = v->d_endpoint = nullptr;
@@ -481,9 +538,25 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     const std::string key = variant_key(body, var, v->layer);
     auto it = v->modules.find(key);
     if (it != v->modules.end()) {
+        it->second.last_use = ++v->module_clock;
         *out = &it->second;
         return LINON_OK;
     }
+    // A long editing session compiles a module per distinct body / variant / helper layer: keep the most recently used ones
+    // (an evicted variant is rebuilt on demand, ~1 s).  Kernels of an evicted module may still be in flight: wait first.
+    constexpr size_t kMaxModules = 48;
+    if (v->modules.size() >= kMaxModules) {
+        cudaStreamSynchronize(v->stream);
+        cudaStreamSynchronize(v->aux);
+        while (v->modules.size() >= kMaxModules) {
+            auto oldest = v->modules.begin();
+            for (auto m = v->modules.begin(); m != v->modules.end(); ++m)
+                if (m->second.last_use < oldest->second.last_use) oldest = m;
+            g_drv.ModuleUnload(oldest->second.mod);
+            v->modules.erase(oldest);
+        }
+    }
+    if (v->pair_unfit.size() > 256) v->pair_unfit.clear();
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<char> cubin;
     std::string log;
@@ -513,6 +586,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     g_drv.FuncGetAttribute(&m.regs_phase_b, CU_FUNC_ATTRIBUTE_NUM_REGS, m.phase_b);
     const auto t1 = std::chrono::steady_clock::now();
     if (jit_ms) *jit_ms += std::chrono::duration<float, std::milli>(t1 - t0).count();
+    m.last_use = ++v->module_clock;
     auto ins = v->modules.emplace(key, m);
     *out = &ins.first->second;
     return LINON_OK;
@@ -534,11 +608,26 @@ void default_mesh_counts(Variant& var) {
     var.n_segs = (int)t.n_segments();
 }
 
+bool body_is_mirage(const linon_view* v) {
+    auto it = v->mirage_cache.find(v->body);
+    if (it != v->mirage_cache.end()) return it->second;
+    if (v->mirage_cache.size() > 256) v->mirage_cache.clear();
+    const bool m = linon::match_mirage(v->body).kind > 0;
+    v->mirage_cache[v->body] = m;
+    return m;
+}
+
 Variant make_variant(const linon_view* v, uint32_t flags) {
     Variant var;
-    var.h_initial = (flags & LINON_RENDER_ENHANCE) ? 0.001f : 0.1f;  // src/main_view.rs:785-787
-    // adaptive sampling can only act while h_initial > 0.002 (src/main_view.wgsl:252,267)
-    var.adaptive = (!(flags & LINON_RENDER_ADAPTIVE_OFF) && var.h_initial > 0.002f) ? 1 : 0;
+    const linon::ModuleLayer& L = v->layer;
+    // Enhance replaces the TEXT `let h_initial = 0.1;` (src/main_view.rs:785-787): with an edited literal the replacement no
+    // longer matches and the frame keeps the module's own step size, like in the reference
+    const float h_module = L.h_initial > 0.0 ? (float)L.h_initial : 0.1f;
+    var.h_initial = ((flags & LINON_RENDER_ENHANCE) && !(L.h_initial > 0.0)) ? 0.001f : h_module;
+    // adaptive sampling can only act while h_initial > 0.002 (src/main_view.wgsl:252,267); `const adaptive_sampling` of an
+    // edited module (:227) is the default the ADAPTIVE_OFF flag overrides
+    const float min_h = L.reject_min_h >= 0.0 ? (float)L.reject_min_h : 0.002f;
+    var.adaptive = (!(flags & LINON_RENDER_ADAPTIVE_OFF) && L.adaptive_sampling != 0 && var.h_initial > min_h) ? 1 : 0;
     var.bvh = v->use_bvh ? 1 : 0;
     var.n_faces = v->use_bvh ? 1 : (int)v->n_faces;   // the hierarchy kernels do not depend on the face count
     var.n_groups = v->use_bvh ? 1 : (int)v->n_groups;
@@ -554,7 +643,11 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     var.profile = v->opt_profile;
     var.specialize = v->opt_specialize;
     // production math modes only: strict mode keeps the blend as written (0 * dir + 1 * v differs from v in the sign of a zero)
-    var.fw_one = (v->opt_math != 0 && v->settings.field_weight == 1.0f) ? 1 : 0;
+    // cur_dir = v instead of (1 - 1) * cur_dir + 1 * v: only where the velocity is known to be finite, i.e. for the fused mirage
+    // restatements (bounded by construction).  A generic body may overflow, and 0 * inf + v is NaN in the reference while the
+    // shortcut would keep v (round-1 advisor finding): those keep the blend as written in every math mode.
+    var.fw_one = (v->opt_math == 2 && v->opt_specialize && v->layer.empty() && v->settings.field_weight == 1.0f &&
+                  body_is_mirage(v)) ? 1 : 0;
     var.pairs = (v->opt_kernel == 2 && !v->use_bvh && !v->pair_unfit.count(v->body)) ? 1 : 0;
     var.pair_min_blocks = var.pairs ? v->opt_pair_min_blocks : 0;
     // only the tile kernel has the quiet-zone path (runs of straight steps in its fixed-step loops, a per-attempt test in
@@ -584,11 +677,11 @@ int get_module_for_body(linon_view* v, const std::string& body, Variant& var, Mo
 // Iterations of `loop { if (t > 5.0) { break; } ...; t = t + h; }` (src/main_view.wgsl:244-266) when h never changes: the
 // same fp32 recurrence, evaluated once on the host (g++ -ffp-contract=off, IEEE binary32 additions), so fixed-step
 // kernels count to an integer instead of comparing a per-lane float.  5001 for h = 0.001, 51 for h = 0.1.
-int fixed_step_count(float h) {
+int fixed_step_count(float h, float t_max = 5.0f) {
     if (!(h > 0.0f)) return 0;
     volatile float t = 0.0f;
     int n = 0;
-    while (t <= 5.0f && n < (1 << 24)) {
+    while (t <= t_max && n < (1 << 24)) {
         t = t + h;
         ++n;
     }
@@ -663,8 +756,8 @@ extern "C" {
 const char* linon_last_error(const linon_view* v) { return v ? v->error.c_str() : g_create_error.c_str(); }
 
 int linon_create(int device, uint32_t width, uint32_t height, linon_view** out) {
-    if (!out || width < 2 || height < 2) {
-        g_create_error = "linon_create: need out != NULL and width, height >= 2";
+    if (!out || !frame_size_ok(width, height)) {
+        g_create_error = "linon_create: need out != NULL, 2 <= width, height <= 65536 and width * height < 2^31";
         return LINON_ERR_INVALID;
     }
     *out = nullptr;
@@ -731,7 +824,8 @@ void linon_destroy(linon_view* v) {
     for (void* m : v->ipc_mappings) cudaIpcCloseMemHandle(m);
     free_frame_buffers(v);
     cudaFree(v->d_bvh);
-    cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_ray_samples); cudaFree(v->d_pos16); cudaFree(v->d_counters);
+    release_buffer(v, LINON_BUF_RAY_SAMPLES, v->d_ray_samples);
+    cudaFree(v->d_tris); cudaFree(v->d_group_range); cudaFree(v->d_pos16); cudaFree(v->d_counters);
     cudaFree(v->d_outline_keys); cudaFree(v->d_work);
     for (auto& ev : v->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(v->stream);
@@ -742,6 +836,12 @@ void linon_destroy(linon_view* v) {
 int linon_set_mesh(linon_view* v, const float* verts, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces) {
     if (!v || !verts || !faces || n_faces == 0) return v ? v->fail(LINON_ERR_INVALID, "linon_set_mesh: null/empty mesh") : LINON_ERR_INVALID;
     if (n_faces > (1u << 24)) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: more than 2^24 faces");
+    // validate BEFORE anything of the current mesh is replaced: a rejected mesh must not be re-staged later by the
+    // LINON_OPT_FORCE_BVH toggle (which works from the host copies)
+    for (size_t k = 0; k < (size_t)3 * n_faces; ++k)
+        if (faces[k] >= n_verts) return v->fail(LINON_ERR_INVALID, fmt("face %zu indexes past the vertex array", k / 3));
+    for (size_t k = 0; k < (size_t)3 * n_verts; ++k)
+        if (!std::isfinite(verts[k])) return v->fail(LINON_ERR_INVALID, "linon_set_mesh: non-finite vertex coordinates");
     if (verts != v->host_verts.data()) v->host_verts.assign(verts, verts + (size_t)3 * n_verts);
     if (faces != v->host_faces.data()) v->host_faces.assign(faces, faces + (size_t)3 * n_faces);
     verts = v->host_verts.data();
@@ -794,7 +894,8 @@ int linon_set_settings(linon_view* v, const linon_settings* settings) {
 }
 
 int linon_resize(linon_view* v, uint32_t width, uint32_t height) {
-    if (!v || width < 2 || height < 2) return LINON_ERR_INVALID;
+    if (!v) return LINON_ERR_INVALID;
+    if (!frame_size_ok(width, height)) return v->fail(LINON_ERR_INVALID, "linon_resize: need 2 <= width, height <= 65536 and width * height < 2^31");
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaStreamSynchronize(v->stream));
     v->out_raycast = nullptr; v->out_endpoint = nullptr; v->out_hit = nullptr;  // a redirection is for one frame size
@@ -859,6 +960,39 @@ int linon_reload_shader_source(linon_view* v, const char* wgsl_module_source, ch
     return LINON_OK;
 }
 
+int linon_reload_shader(linon_view* v, const char* wgsl_module_source, const char* wgsl_body, char* err, size_t err_len) {
+    if (!v || !wgsl_body) return LINON_ERR_INVALID;
+    if (err && err_len) err[0] = '\0';
+    CK(v, cudaSetDevice(v->device));
+    linon::ModuleLayer layer;  // NULL / "" = the stock module
+    if (wgsl_module_source && wgsl_module_source[0]) {
+        std::string merr;
+        bool unsupported = false;
+        if (!linon::translate_wgsl_module(wgsl_module_source, layer, merr, unsupported)) {
+            if (err && err_len) snprintf(err, err_len, "%s", merr.c_str());
+            return v->fail(unsupported ? LINON_ERR_UNSUPPORTED : LINON_ERR_COMPILE, merr);
+        }
+    }
+    // the PAIR is validated once, like the reference compiles new_src with the new field function spliced in
+    // (src/main_view.rs:649-690); both are committed or neither
+    const linon::ModuleLayer old_layer = v->layer;
+    const std::string old_body = v->body;
+    v->layer = layer;
+    v->body = wgsl_body;
+    Variant var = make_variant(v, LINON_RENDER_DEFAULT);
+    if (var.n_faces == 0) default_mesh_counts(var);
+    Module* m = nullptr;
+    float jit = 0.0f;
+    const int rc = get_module_for_body(v, v->body, var, &m, &jit);
+    if (rc != LINON_OK) {
+        v->layer = old_layer;
+        v->body = old_body;
+        if (err && err_len) snprintf(err, err_len, "%s", v->error.c_str());
+        return rc;
+    }
+    return LINON_OK;
+}
+
 int linon_module_overrides(linon_view* v, char* names, size_t names_len) {
     if (!v || !names || !names_len) return LINON_ERR_INVALID;
     if (v->layer.names.size() + 1 > names_len) return LINON_ERR_SIZE;
@@ -879,7 +1013,7 @@ int linon_render(linon_view* v, uint32_t flags) {
         v->ran_march = v->ran_overlay = v->ran_sample = v->ran_outline = v->ran_phases = false;
     }
 
-    if (do_march && v->opt_kernel == 1 && !v->use_bvh) {
+    if (do_march && v->opt_kernel == 1 && !v->use_bvh && !v->layer.linear_mode) {
         const int rc = alloc_queue(v, true);
         if (rc != LINON_OK) return rc;
     }
@@ -890,13 +1024,13 @@ int linon_render(linon_view* v, uint32_t flags) {
         Variant var = make_variant(v, flags);
         const int rc = get_module_for_body(v, v->body, var, &mod, &v->timings.jit_ms);
         if (rc != LINON_OK) return rc;
-        P.n_fixed_steps = var.adaptive ? 0 : fixed_step_count(var.h_initial);
+        P.n_fixed_steps = var.adaptive ? 0 : fixed_step_count(var.h_initial, v->layer.t_max > 0.0 ? (float)v->layer.t_max : 5.0f);
     }
 
     if (do_sample) {
         // sample-ray start positions: outline search over the exponents of the PREVIOUS overlay pass (the march
         // dispatch runs before the overlay dispatch in the reference, src/main_view.rs:838-846) or the click ring
-        if (flags & LINON_RENDER_OUTLINE) {
+        if ((flags & LINON_RENDER_OUTLINE) || v->layer.sample_outline_rays == 1) {  // `const sample_outline_rays`, :337
             CK(v, cudaEventRecord(v->ev[6], v->stream));
             linon::launch_outline_search(v->stream, (int)v->W, (int)v->H, v->d_exponents, v->d_outline_keys, v->d_pos16,
                                          v->sm_count);
@@ -922,13 +1056,14 @@ int linon_render(linon_view* v, uint32_t flags) {
     if (do_march && v->local_rows > 0) {
         CK(v, cudaMemsetAsync(v->d_counters, 0, 128, v->stream));
         const unsigned block = (unsigned)v->opt_block;
-        const bool use_pairs = v->opt_kernel == 2 && mod->pairs != nullptr;
+        const int kernel_opt = v->layer.linear_mode ? 0 : v->opt_kernel;  // linear_mode: one straight ray per pixel (tile kernel)
+        const bool use_pairs = kernel_opt == 2 && mod->pairs != nullptr;
         const unsigned needed = ((use_pairs ? P.n_pair_slots : P.n_ray_slots) + block - 1) / block;
-        const bool use_refill = v->opt_kernel == 3;
-        v->timings.march_kernel = use_pairs ? 2 : ((v->opt_kernel == 1 && !v->use_bvh) ? 1 : (use_refill ? 3 : 0));
+        const bool use_refill = kernel_opt == 3;
+        v->timings.march_kernel = use_pairs ? 2 : ((kernel_opt == 1 && !v->use_bvh) ? 1 : (use_refill ? 3 : 0));
         v->timings.march_block = (int)block;
         CK(v, cudaEventRecord(v->ev[0], v->stream));
-        if (v->opt_kernel == 1 && !v->use_bvh) {
+        if (kernel_opt == 1 && !v->use_bvh) {
             // persistent warps: phase A (pre-hit rays, lane refill from the fresh cursor) then phase B (queued post-hit
             // rays) as two launches on the same stream, so phase B sees a complete, immutable queue
             CK(v, cudaMemsetAsync(v->d_work, 0, 64, v->stream));
@@ -1069,6 +1204,135 @@ int linon_ipc_open(linon_view* v, const void* handle64, void** device_ptr) {
     v->ipc_mappings.push_back(p);
     *device_ptr = p;
     return LINON_OK;
+}
+
+// ---- display hand-off: the buffers the application SHOWS, shared with its graphics API without a copy -----------------------
+namespace {
+struct ImportedBuffer {
+    CUmemGenericAllocationHandle handle = 0;
+    CUdeviceptr ptr = 0;
+    size_t size = 0;
+    int device = 0;
+};
+CUmemAllocationProp exportable_prop(int device) {
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+}  // namespace
+
+int linon_export_buffer_fd(linon_view* v, int buffer, int* fd, size_t* allocation_bytes) {
+    if (!v || !fd) return LINON_ERR_INVALID;
+    if (buffer != LINON_BUF_FINAL_RGBA8 && buffer != LINON_BUF_RAY_SAMPLES)
+        return v->fail(LINON_ERR_INVALID, "linon_export_buffer_fd: only the buffers the application displays (final image, ray samples) are exported");
+    if (!g_drv.has_vmm) return v->fail(LINON_ERR_NO_DRIVER, "this CUDA driver lacks the virtual memory management API (cuMemCreate ...)");
+    CK(v, cudaSetDevice(v->device));
+    CK(v, cudaStreamSynchronize(v->stream));
+    CK(v, cudaStreamSynchronize(v->aux));
+    const size_t bytes = linon_buffer_bytes(v, buffer);
+    void** slot = buffer == LINON_BUF_FINAL_RGBA8 ? &v->d_final : &v->d_ray_samples;
+    auto it = v->exported.find(buffer);
+    if (it == v->exported.end()) {
+        // move the buffer into an exportable allocation (once; linon_resize reallocates frame buffers plainly again)
+        const CUmemAllocationProp prop = exportable_prop(v->device);
+        size_t gran = 0;
+        CUresult r = g_drv.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM);
+        if (r != CUDA_SUCCESS || gran == 0) return v->fail(LINON_ERR_CUDA, "cuMemGetAllocationGranularity: " + g_drv.err_str(r));
+        linon_view::VmmAlloc a;
+        a.size = (bytes + gran - 1) / gran * gran;
+        if ((r = g_drv.MemCreate(&a.handle, a.size, &prop, 0)) != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuMemCreate: " + g_drv.err_str(r));
+        if ((r = g_drv.MemAddressReserve(&a.ptr, a.size, 0, 0, 0)) != CUDA_SUCCESS) {
+            g_drv.MemRelease(a.handle);
+            return v->fail(LINON_ERR_CUDA, "cuMemAddressReserve: " + g_drv.err_str(r));
+        }
+        CUmemAccessDesc access;
+        memset(&access, 0, sizeof(access));
+        access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        access.location.id = v->device;
+        access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if ((r = g_drv.MemMap(a.ptr, a.size, 0, a.handle, 0)) != CUDA_SUCCESS || (r = g_drv.MemSetAccess(a.ptr, a.size, &access, 1)) != CUDA_SUCCESS) {
+            g_drv.MemAddressFree(a.ptr, a.size);
+            g_drv.MemRelease(a.handle);
+            return v->fail(LINON_ERR_CUDA, "cuMemMap / cuMemSetAccess: " + g_drv.err_str(r));
+        }
+        cudaError_t e = cudaMemset((void*)a.ptr, 0, a.size);
+        if (e == cudaSuccess) e = cudaMemcpy((void*)a.ptr, *slot, bytes, cudaMemcpyDeviceToDevice);  // keep what is on screen
+        if (e != cudaSuccess) {
+            g_drv.MemUnmap(a.ptr, a.size);
+            g_drv.MemAddressFree(a.ptr, a.size);
+            g_drv.MemRelease(a.handle);
+            return v->fail(LINON_ERR_CUDA, std::string("copy into the exportable allocation: ") + cudaGetErrorString(e));
+        }
+        cudaFree(*slot);
+        *slot = (void*)a.ptr;
+        it = v->exported.emplace(buffer, a).first;
+    }
+    int out = -1;
+    const CUresult r = g_drv.MemExportToShareableHandle(&out, it->second.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuMemExportToShareableHandle: " + g_drv.err_str(r));
+    *fd = out;
+    if (allocation_bytes) *allocation_bytes = it->second.size;
+    return LINON_OK;
+}
+
+int linon_import_buffer_fd(int device, int fd, size_t allocation_bytes, void** device_ptr, void** import_handle) {
+    if (fd < 0 || !allocation_bytes || !device_ptr || !import_handle) return LINON_ERR_INVALID;
+    {
+        std::lock_guard<std::mutex> lock(g_drv_mutex);
+        if (!g_drv.load()) {
+            g_create_error = g_drv.error;
+            return LINON_ERR_NO_DRIVER;
+        }
+    }
+    if (!g_drv.has_vmm) { g_create_error = "this CUDA driver lacks the virtual memory management API"; return LINON_ERR_NO_DRIVER; }
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { g_create_error = "no CUDA device (no CPU fallback)"; return LINON_ERR_NO_DRIVER; }
+    ImportedBuffer* b = new ImportedBuffer;
+    b->size = allocation_bytes;
+    b->device = device;
+    CUresult r = g_drv.MemImportFromShareableHandle(&b->handle, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (r == CUDA_SUCCESS) r = g_drv.MemAddressReserve(&b->ptr, b->size, 0, 0, 0);
+    if (r == CUDA_SUCCESS) r = g_drv.MemMap(b->ptr, b->size, 0, b->handle, 0);
+    if (r == CUDA_SUCCESS) {
+        CUmemAccessDesc access;
+        memset(&access, 0, sizeof(access));
+        access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        access.location.id = device;
+        access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = g_drv.MemSetAccess(b->ptr, b->size, &access, 1);
+    }
+    if (r != CUDA_SUCCESS) {
+        g_create_error = "importing the shared allocation: " + g_drv.err_str(r);
+        if (b->ptr) g_drv.MemAddressFree(b->ptr, b->size);
+        if (b->handle) g_drv.MemRelease(b->handle);
+        delete b;
+        return LINON_ERR_CUDA;
+    }
+    *device_ptr = (void*)b->ptr;
+    *import_handle = b;
+    return LINON_OK;
+}
+
+int linon_release_import(void* import_handle) {
+    if (!import_handle) return LINON_ERR_INVALID;
+    ImportedBuffer* b = (ImportedBuffer*)import_handle;
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    g_drv.MemUnmap(b->ptr, b->size);
+    g_drv.MemAddressFree(b->ptr, b->size);
+    g_drv.MemRelease(b->handle);
+    delete b;
+    return LINON_OK;
+}
+
+int linon_copy_to_host(int device, const void* device_ptr, void* dst, size_t bytes) {
+    if (!device_ptr || !dst) return LINON_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return LINON_ERR_NO_DRIVER;
+    if (cudaDeviceSynchronize() != cudaSuccess) return LINON_ERR_CUDA;
+    return cudaMemcpy(dst, device_ptr, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? LINON_OK : LINON_ERR_CUDA;
 }
 
 int linon_read(linon_view* v, int buffer, void* dst, size_t dst_bytes) {
@@ -1252,7 +1516,11 @@ int linon_translate_wgsl_module(const char* wgsl_module_source, char* out, size_
         if (err && err_len) snprintf(err, err_len, "%s", merr.c_str());
         return unsupported ? LINON_ERR_UNSUPPORTED : LINON_ERR_COMPILE;
     }
-    const std::string text = layer.preamble.empty() ? layer.members : "// module constants: " + layer.preamble + "\n" + layer.members;
+    std::string text = layer.preamble.empty() ? layer.members : "// module constants: " + layer.preamble + "\n" + layer.members;
+    if (!layer.march_defines.empty()) text = "// march-level constants (macros of the kernel template):\n" + layer.march_defines + text;
+    if (layer.adaptive_sampling >= 0) text = fmt("// adaptive_sampling = %d\n", layer.adaptive_sampling) + text;
+    if (layer.sample_outline_rays >= 0) text = fmt("// sample_outline_rays = %d\n", layer.sample_outline_rays) + text;
+    if (layer.h_initial > 0.0) text = fmt("// h_initial = %.9g\n", layer.h_initial) + text;
     if (out && out_len) {
         if (text.size() + 1 > out_len) return LINON_ERR_SIZE;
         memcpy(out, text.c_str(), text.size() + 1);
@@ -1270,7 +1538,12 @@ int linon_scan_wgsl_module(const char* wgsl_module_source, char* out, size_t out
         return LINON_ERR_COMPILE;
     }
     std::string text;
-    for (const auto& it : items) text += fmt("%s %s 0x%016llx %d\n", it.kind.c_str(), it.name.c_str(), (unsigned long long)it.hash, it.line);
+    for (const auto& it : items) {
+        text += fmt("%s %s 0x%016llx %d 0x%016llx %zu", it.kind.c_str(), it.name.c_str(), (unsigned long long)it.hash, it.line,
+                    (unsigned long long)it.masked_hash, it.literals.size());
+        for (double x : it.literals) text += fmt(" %.17g", x);
+        text += "\n";
+    }
     if (text.size() + 1 > out_len) return LINON_ERR_SIZE;
     memcpy(out, text.c_str(), text.size() + 1);
     return LINON_OK;

@@ -46,10 +46,16 @@ public:
           field_function_(to_code(PredefinedFunction::MirageSphericalSigmoid)),
           camera_(center, 1.0f, (float)width_, (float)height_) {
         check(linon_create(device, width_, height_, &view_), "linon_create");
-        check(linon_set_mesh(view_, vertices.data(), (uint32_t)(vertices.size() / 3), faces.data(),
-                             (uint32_t)(faces.size() / 3)), "linon_set_mesh");
-        camera_.zoom(-1.0f, 1.0f);  // :153-155
-        update_camera();
+        try {
+            check(linon_set_mesh(view_, vertices.data(), (uint32_t)(vertices.size() / 3), faces.data(),
+                                 (uint32_t)(faces.size() / 3)), "linon_set_mesh");
+            camera_.zoom(-1.0f, 1.0f);  // :153-155
+            update_camera();
+        } catch (...) {  // the destructor does not run for a half-constructed object
+            linon_destroy(view_);
+            view_ = nullptr;
+            throw;
+        }
     }
     ~MainView() { linon_destroy(view_); }
     MainView(const MainView&) = delete;
@@ -123,15 +129,11 @@ public:
     }
     // src/main_view.rs:649-690 with new_src = Some(..): the whole-shader hot reload (file watcher on src/main_view.wgsl,
     // src/main.rs:206-222 -> Application::reload_compute_shader, src/application.rs:228-232).  The helper layer of the
-    // edited module is installed first, then the field function is rebuilt against it; on an error nothing changes
+    // edited module and the field function are validated as a pair and committed together; on an error nothing changes
     // (:677-679 returns before `self.shader_src = new_src`).
     bool reload_shader(const std::string& new_src, const std::string& field_function, std::string* error) {
         char buf[8192];
-        int rc = linon_reload_shader_source(view_, new_src.c_str(), buf, sizeof(buf));
-        if (rc == LINON_OK && field_function != field_function_) {
-            rc = linon_set_field_function(view_, field_function.c_str(), buf, sizeof(buf));
-            if (rc != LINON_OK) linon_reload_shader_source(view_, shader_src_.c_str(), nullptr, 0);  // back to the old module
-        }
+        const int rc = linon_reload_shader(view_, new_src.c_str(), field_function.c_str(), buf, sizeof(buf));  // both or neither
         if (rc != LINON_OK) {
             if (error) *error = buf;
             return false;

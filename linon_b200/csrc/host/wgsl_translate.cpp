@@ -1076,10 +1076,13 @@ struct Pristine {
     const char* kind;
     const char* name;
     uint64_t hash;
+    uint64_t masked_hash;
 };
 const Pristine kPristine[] = {
 #include "module_items.inc"
-    {"", "", 0}};
+    {"", "", 0, 0}};
+// the numeric literals of the reference's nonlinear_ray_color and sample_rays in order of appearance (values only)
+#include "module_literals.inc"
 
 // library helpers a field function may call (README.md:37-44): an edited version overrides the prelude's
 const char* const kLibraryHelpers[] = {"rotateX", "rotateY", "rotateZ", "translate", "refraction_index", "refraction",
@@ -1199,10 +1202,21 @@ bool split_module(const std::vector<Tok>& t, std::vector<RawItem>& items, std::s
             it.end = semi + 1;
         }
         it.info.name = t[it.name_tok].text;
-        uint64_t h = 1469598103934665603ull;
-        for (int j = it.begin; j < it.end; ++j)
-            if (t[j].kind != WS && t[j].kind != NL) h = fnv1a(h, t[j].text);
+        uint64_t h = 1469598103934665603ull, hm = 1469598103934665603ull;
+        for (int j = it.begin; j < it.end; ++j) {
+            if (t[j].kind == WS || t[j].kind == NL) continue;
+            h = fnv1a(h, t[j].text);
+            if (t[j].kind == NUMBER) {
+                hm = fnv1a(hm, "#");
+                std::string num = t[j].text;
+                while (!num.empty() && (num.back() == 'f' || num.back() == 'u')) num.pop_back();
+                it.info.literals.push_back(std::strtod(num.c_str(), nullptr));
+            } else {
+                hm = fnv1a(hm, t[j].text);
+            }
+        }
         it.info.hash = h;
+        it.info.masked_hash = hm;
         items.push_back(it);
         i = sig(it.end);
     }
@@ -1315,6 +1329,165 @@ bool emit_function(const std::vector<Tok>& t, const RawItem& it, const std::stri
     return true;
 }
 
+// ---- march-level edits ------------------------------------------------------------------------------------------------
+std::string f32_literal(double x) {
+    char b[64];
+    std::snprintf(b, sizeof b, "%.9g", (double)(float)x);
+    std::string s = b;
+    if (s.find_first_of(".en") == std::string::npos) s += ".0";
+    return "(" + s + "f)";
+}
+
+// value tokens of `const NAME [: TYPE] = VALUE ;` -> numbers (with their signs) and identifiers
+bool const_value(const std::vector<Tok>& t, const RawItem& it, std::vector<double>& nums, std::vector<std::string>& idents) {
+    int eq = -1;
+    for (int j = it.begin; j < it.end; ++j)
+        if (t[j].kind == PUNCT && t[j].text == "=") { eq = j; break; }
+    if (eq < 0) return false;
+    double sign = 1.0;
+    for (int j = eq + 1; j < it.end; ++j) {
+        const Tok& k = t[j];
+        if (k.kind == WS || k.kind == NL) continue;
+        if (k.kind == NUMBER) {
+            std::string num = k.text;
+            while (!num.empty() && (num.back() == 'f' || num.back() == 'u')) num.pop_back();
+            nums.push_back(sign * std::strtod(num.c_str(), nullptr));
+            sign = 1.0;
+        } else if (k.kind == IDENT) {
+            idents.push_back(k.text);
+        } else if (k.text == "-") {
+            sign = -sign;
+        } else if (k.text != "(" && k.text != ")" && k.text != "," && k.text != "<" && k.text != ">" && k.text != ";" && k.text != "+") {
+            return false;  // an expression, not a literal value
+        }
+    }
+    return true;
+}
+
+// A pristine-named module constant with another value: true = mapped to the kernel template (layer updated); false with
+// err empty = not a constant this path knows; false with err set = known but outside the supported range.
+bool apply_march_const(const std::vector<Tok>& t, const RawItem& it, ModuleLayer& layer, std::string& err) {
+    const std::string& name = it.info.name;
+    std::vector<double> n;
+    std::vector<std::string> id;
+    if (!const_value(t, it, n, id)) return false;
+    auto is_bool = [&](bool& v) {
+        if (!n.empty()) return false;
+        int seen = 0;
+        for (const std::string& s : id) {
+            if (s == "true") { v = true; ++seen; }
+            if (s == "false") { v = false; ++seen; }
+        }
+        return seen == 1;
+    };
+    auto out_of_range = [&](const char* what) {
+        err = "the constant '" + name + "' is outside the range the CUDA path supports (" + what + ")";
+        return false;
+    };
+    bool b = false;
+    if (name == "backface_culling" || name == "use_lighting" || name == "linear_mode" || name == "adaptive_sampling" ||
+        name == "sample_outline_rays") {
+        if (!is_bool(b)) return false;
+        if (name == "backface_culling") layer.march_defines += std::string("#define LINON_BACKFACE_CULLING ") + (b ? "1" : "0") + "\n";
+        if (name == "use_lighting") layer.march_defines += std::string("#define LINON_USE_LIGHTING ") + (b ? "1" : "0") + "\n";
+        if (name == "linear_mode") {
+            layer.march_defines += std::string("#define LINON_LINEAR_MODE ") + (b ? "1" : "0") + "\n";
+            layer.linear_mode = b;
+        }
+        if (name == "adaptive_sampling") layer.adaptive_sampling = b ? 1 : 0;
+        if (name == "sample_outline_rays") layer.sample_outline_rays = b ? 1 : 0;
+    } else if (name == "eps" || name == "ambient_strength" || name == "shininess") {
+        if (n.size() != 1 || !std::isfinite(n[0])) return false;
+        if (name == "eps") {
+            if (!(n[0] >= 0.0 && n[0] <= 1e-2)) return out_of_range("0 <= eps <= 0.01");
+            layer.march_defines += "#define LINON_EPS " + f32_literal(n[0]) + "\n";
+        } else if (name == "ambient_strength") {
+            if (!(n[0] >= 0.0 && n[0] <= 100.0)) return out_of_range("0 <= ambient_strength <= 100");
+            layer.march_defines += "#define LINON_AMBIENT " + f32_literal(n[0]) + "\n";
+        } else {
+            if (!(n[0] >= 0.0 && n[0] <= 1e4)) return out_of_range("0 <= shininess <= 10000");
+            layer.march_defines += "#define LINON_SHININESS " + f32_literal(n[0]) + "\n";
+        }
+    } else if (name == "light_color" || name == "object_color") {
+        if (n.size() != 3 && n.size() != 1) return false;
+        if (n.size() == 1) n = {n[0], n[0], n[0]};  // vec3<f32>(x) splats
+        for (double x : n)
+            if (!std::isfinite(x) || std::fabs(x) > 1e3) return out_of_range("|component| <= 1000");
+        if (name == "light_color")
+            layer.march_defines += "#define LINON_LIGHT_R " + f32_literal(n[0]) + "\n#define LINON_LIGHT_G " + f32_literal(n[1]) +
+                                   "\n#define LINON_LIGHT_B " + f32_literal(n[2]) + "\n";
+        // object_color is declared and never used by the reference's shader: any value renders the same frame
+    } else {
+        return false;
+    }
+    layer.names += (layer.names.empty() ? "" : ",") + name;
+    return true;
+}
+
+// nonlinear_ray_color / sample_rays whose tokens equal the reference's except for the VALUES of numeric literals
+bool apply_march_literals(const RawItem& it, ModuleLayer& layer, std::string& err) {
+    const std::string& name = it.info.name;
+    const double* pristine = nullptr;
+    size_t n_pristine = 0;
+    if (name == "nonlinear_ray_color") { pristine = kLit_nonlinear_ray_color; n_pristine = sizeof(kLit_nonlinear_ray_color) / sizeof(double); }
+    if (name == "sample_rays") { pristine = kLit_sample_rays; n_pristine = sizeof(kLit_sample_rays) / sizeof(double); }
+    if (!pristine || it.info.literals.size() != n_pristine) return false;
+    struct Hole { int ordinal; const char* what; };
+    // ordinals verified against the reference's text by tools/gen_module_hashes.py (kLitHoles_* in module_literals.inc)
+    for (size_t k = 0; k < n_pristine; ++k) {
+        const double v = it.info.literals[k];
+        if (v == pristine[k]) continue;
+        const char* what = nullptr;
+        const int* holes = name == "nonlinear_ray_color" ? kLitHoles_nonlinear_ray_color : kLitHoles_sample_rays;
+        static const char* const names_nl[] = {"h_initial", "t_max", "reject_factor", "reject_min_h", "small_h", "restore_factor"};
+        static const char* const names_sr[] = {"sample_h", "sample_steps"};
+        const int n_holes = name == "nonlinear_ray_color" ? 6 : 2;
+        for (int q = 0; q < n_holes; ++q)
+            if (holes[q] == (int)k) what = (name == "nonlinear_ray_color" ? names_nl : names_sr)[q];
+        if (!what) {
+            err = "the function '" + name + "' was edited (literal " + std::to_string(k + 1) + " of " + std::to_string(n_pristine) +
+                  "); the CUDA path maps its step size, horizon and step-control constants to the kernel template, nothing else of it";
+            return false;
+        }
+        auto bad = [&](const char* range) {
+            err = std::string("'") + what + "' of '" + name + "' is outside the range the CUDA path supports (" + range + ")";
+            return false;
+        };
+        const std::string w = what;
+        if (!std::isfinite(v)) return bad("finite");
+        if (w == "h_initial") {
+            if (!(v >= 1e-5 && v <= 1.0)) return bad("1e-5 <= h_initial <= 1");
+            layer.h_initial = v;
+        } else if (w == "t_max") {
+            if (!(v > 0.0 && v <= 100.0)) return bad("0 < horizon <= 100");
+            layer.t_max = v;
+            layer.march_defines += "#define LINON_T_MAX " + f32_literal(v) + "\n";
+        } else if (w == "reject_factor") {
+            if (!(v >= 1.0 && v <= 1e6)) return bad("1 <= factor <= 1e6");
+            layer.march_defines += "#define LINON_REJECT_FACTOR " + f32_literal(v) + "\n";
+        } else if (w == "reject_min_h") {
+            if (!(v >= 0.0 && v <= 1.0)) return bad("0 <= threshold <= 1");
+            layer.reject_min_h = v;
+            layer.march_defines += "#define LINON_REJECT_MIN_H " + f32_literal(v) + "\n";
+        } else if (w == "small_h") {
+            if (!(v >= 1e-5 && v <= 1.0)) return bad("1e-5 <= h <= 1");
+            layer.march_defines += "#define LINON_SMALL_H " + f32_literal(v) + "\n";
+        } else if (w == "restore_factor") {
+            if (!(v >= 0.0 && v <= 1e6)) return bad("0 <= factor <= 1e6");
+            layer.march_defines += "#define LINON_RESTORE_FACTOR " + f32_literal(v) + "\n";
+        } else if (w == "sample_h") {
+            if (!(v >= 1e-5 && v <= 1.0)) return bad("1e-5 <= h <= 1");
+            layer.march_defines += "#define LINON_SAMPLE_H " + f32_literal(v) + "\n";
+        } else if (w == "sample_steps") {
+            const long steps = (long)v;
+            if ((double)steps != v || steps < 100 || steps > 1000000 || steps % 100 != 0) return bad("a multiple of 100 in 100 ... 1 000 000: 100 samples per ray");
+            layer.march_defines += "#define LINON_SAMPLE_STEPS " + std::to_string(steps) + "\n";
+        }
+    }
+    layer.names += (layer.names.empty() ? "" : ",") + name;
+    return true;
+}
+
 }  // namespace
 
 bool scan_wgsl_module(const std::string& src, std::vector<ModuleItem>& items, std::string& error) {
@@ -1376,6 +1549,17 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
         if (kind == "const" && (!p || name == "PI")) {
             emit_const.push_back(k);
             continue;
+        }
+        // march-level constants and literals: mapped to macros of the kernel template (march_kernels.cuh)
+        {
+            std::string merr;
+            if (kind == "const" && p && apply_march_const(t, it, layer, merr)) continue;
+            if (kind == "fn" && p && p->masked_hash == it.info.masked_hash && apply_march_literals(it, layer, merr)) continue;
+            if (!merr.empty()) {
+                unsupported = true;
+                error = "main_view.wgsl line " + std::to_string(it.info.line) + ": " + merr;
+                return false;
+            }
         }
         unsupported = true;
         error = "main_view.wgsl line " + std::to_string(it.info.line) + ": " + (p ? "the " : "a new ") + kind + " '" + name + "' " +

@@ -287,6 +287,12 @@ class MainView:
         self._check_view(capi.lib().linon_ipc_open(self._view, C.c_char_p(handle), C.byref(p)))
         return int(p.value)
 
+    def export_buffer_fd(self, buffer: int):
+        """(fd, allocation bytes) of LINON_BUF_FINAL_RGBA8 / LINON_BUF_RAY_SAMPLES in an exportable allocation; the caller closes fd."""
+        fd, n = C.c_int(-1), C.c_size_t(0)
+        self._check_view(capi.lib().linon_export_buffer_fd(self._view, buffer, C.byref(fd), C.byref(n)))
+        return fd.value, n.value
+
     def counters(self) -> Counters:
         c = Counters()
         self._check_view(capi.lib().linon_get_counters(self._view, C.byref(c)))
@@ -402,6 +408,23 @@ def match_mirage(body: str):
     return kind.value, dict(t_env=p[0], t_src=p[1], max_dist=p[2], c=(p[3], p[4], p[5]), sig_k=p[6], sig_c=p[7])
 
 
+def read_exported_buffer(device: int, fd: int, allocation_bytes: int, nbytes: int) -> np.ndarray:
+    """Consumer side of the display hand-off: maps the descriptor in THIS process, copies nbytes to the host, unmaps."""
+    L = capi.lib()
+    ptr, handle = C.c_void_p(0), C.c_void_p(0)
+    rc = L.linon_import_buffer_fd(device, fd, allocation_bytes, C.byref(ptr), C.byref(handle))
+    if rc != capi.OK:
+        raise LinonError(rc, L.linon_last_error(None).decode())
+    try:
+        out = np.empty(nbytes, np.uint8)
+        rc = L.linon_copy_to_host(device, ptr, out.ctypes.data, nbytes)
+        if rc != capi.OK:
+            raise LinonError(rc, "linon_copy_to_host")
+        return out
+    finally:
+        L.linon_release_import(handle)
+
+
 def translate_wgsl(body: str) -> str:
     out = C.create_string_buffer(1 << 16)
     err = C.create_string_buffer(4096)
@@ -422,17 +445,22 @@ def translate_wgsl_module(module_src: str):
     return out.value.decode("utf-8"), [n for n in names.value.decode().split(",") if n]
 
 
-def scan_wgsl_module(module_src: str):
-    """Top-level declarations of a WGSL module: list of (kind, name, hash, line)."""
-    out = C.create_string_buffer(1 << 16)
+def scan_wgsl_module(module_src: str, full: bool = False):
+    """Top-level declarations of a WGSL module: list of (kind, name, hash, line); full: + (hash with the numeric literals
+    masked, the literals in order of appearance)."""
+    out = C.create_string_buffer(1 << 18)
     err = C.create_string_buffer(4096)
     rc = capi.lib().linon_scan_wgsl_module(module_src.encode("utf-8"), out, len(out), err, len(err))
     if rc != capi.OK:
         raise LinonError(rc, err.value.decode("utf-8", "replace"))
     items = []
     for line in out.value.decode().splitlines():
-        kind, name, h, ln = line.split()
-        items.append((kind, name, int(h, 16), int(ln)))
+        f = line.split()
+        kind, name, h, ln = f[:4]
+        if full:
+            items.append((kind, name, int(h, 16), int(ln), int(f[4], 16), [float(x) for x in f[6:6 + int(f[5])]]))
+        else:
+            items.append((kind, name, int(h, 16), int(ln)))
     return items
 
 

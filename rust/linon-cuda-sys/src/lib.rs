@@ -74,6 +74,15 @@ pub const LINON_RENDER_ADAPTIVE_OFF: u32 = 4; // disable_adaptive_sampling, :765
 pub const LINON_RENDER_NO_OVERLAY: u32 = 8;
 pub const LINON_RENDER_NO_MARCH: u32 = 16;
 pub const LINON_RENDER_NO_SAMPLE_RAYS: u32 = 32;
+pub const LINON_RENDER_KEEP_TIMINGS: u32 = 64;
+
+pub const LINON_SHARD_PEER_STORES: c_int = 0; // every shard's march stores into the root's buffers over NVLink
+pub const LINON_SHARD_NCCL_GATHER: c_int = 1; // one grouped ncclSend / ncclRecv to the root after the march
+
+#[repr(C)]
+pub struct linon_sharded {
+    _private: [u8; 0],
+}
 
 pub const LINON_BUF_FINAL_RGBA8: c_int = 0; // `texture`
 pub const LINON_BUF_RAYCAST_RGBA8: c_int = 1; // `ray_casting_texture`
@@ -112,4 +121,29 @@ extern "C" {
     pub fn linon_compile_check(wgsl_body: *const c_char, flags: u32, math_mode: c_int, n_faces: u32, cubin_bytes: *mut usize,
                                err: *mut c_char, err_len: usize) -> c_int;
     pub fn linon_measure_fp32_peak(device: c_int, tflops: *mut f64, sm_count: *mut c_int) -> c_int;
+    pub fn linon_march_cubin_hash(v: *mut linon_view, out: *mut u64) -> c_int;
+
+    // one frame on several B200s of a node, from one host thread (devices[0] is the root)
+    pub fn linon_sharded_create(devices: *const c_int, n_devices: u32, width: u32, height: u32, rows_per_block: u32, mode: c_int,
+                                out: *mut *mut linon_sharded) -> c_int;
+    pub fn linon_sharded_destroy(s: *mut linon_sharded);
+    pub fn linon_sharded_world(s: *const linon_sharded) -> u32;
+    pub fn linon_sharded_view(s: *mut linon_sharded, rank: u32) -> *mut linon_view;
+    pub fn linon_sharded_set_mesh(s: *mut linon_sharded, verts: *const f32, n_verts: u32, faces: *const u32, n_faces: u32) -> c_int;
+    pub fn linon_sharded_set_camera(s: *mut linon_sharded, camera: *const linon_camera) -> c_int;
+    pub fn linon_sharded_set_settings(s: *mut linon_sharded, settings: *const linon_settings) -> c_int;
+    pub fn linon_sharded_set_field_function(s: *mut linon_sharded, wgsl_body: *const c_char, err: *mut c_char, err_len: usize) -> c_int;
+    pub fn linon_sharded_set_option(s: *mut linon_sharded, option: c_int, value: c_int) -> c_int;
+    pub fn linon_sharded_resize(s: *mut linon_sharded, width: u32, height: u32) -> c_int;
+    pub fn linon_sharded_render(s: *mut linon_sharded, flags: u32) -> c_int;
+    pub fn linon_sharded_sync(s: *mut linon_sharded) -> c_int;
+    pub fn linon_sharded_last_error(s: *const linon_sharded) -> *const c_char;
+
+    // display hand-off without a copy: LINON_BUF_FINAL_RGBA8 / LINON_BUF_RAY_SAMPLES as an exportable allocation (POSIX fd,
+    // importable as VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT); the caller closes the descriptor
+    pub fn linon_export_buffer_fd(v: *mut linon_view, buffer: c_int, fd: *mut c_int, allocation_bytes: *mut usize) -> c_int;
+    pub fn linon_import_buffer_fd(device: c_int, fd: c_int, allocation_bytes: usize, device_ptr: *mut *mut c_void,
+                                  import_handle: *mut *mut c_void) -> c_int;
+    pub fn linon_release_import(import_handle: *mut c_void) -> c_int;
+    pub fn linon_copy_to_host(device: c_int, device_ptr: *const c_void, dst: *mut c_void, bytes: usize) -> c_int;
 }

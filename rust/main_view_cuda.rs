@@ -107,8 +107,10 @@ impl MainView {
 
     /// reload_shader(device, Some(new_src), field_function), :649-690, as Application::reload_compute_shader calls it
     /// (src/application.rs:228-232) when the watcher on src/main_view.wgsl fires (src/main.rs:206-222): the CUDA path
-    /// installs the module's helper layer (new / edited helper functions and constants); an edit to the march itself is
-    /// an Err naming the declaration, and nothing changes on any Err (:677-679).
+    /// installs the module's helper layer (new / edited helper functions and constants) and its march-level constants (eps,
+    /// backface_culling, use_lighting, linear_mode, the light constants, adaptive_sampling, sample_outline_rays, the step /
+    /// horizon / step-control literals); any other edit to the march is an Err naming the declaration, and nothing changes
+    /// on any Err (:677-679).
     pub fn reload_compute_shader(&mut self, new_src: &str) -> Result<(), String> {
         let src = CString::new(new_src).map_err(|e| e.to_string())?;
         let mut err = vec![0u8; 16384];
@@ -165,6 +167,29 @@ impl MainView {
         self.check(unsafe { sys::linon_read(self.view, sys::LINON_BUF_RAY_SAMPLES, samples.as_mut_ptr() as *mut _, samples.len()) })?;
         queue.write_buffer(ray_samples_buffer, 0, &samples);
         Ok(())
+    }
+}
+
+/// File descriptors of the two buffers the application shows, for a host that imports them into its graphics API instead of
+/// staging them through `upload_to_wgpu`: the final image (re-export after every resize_texture,
+/// like the reference re-registers its texture, :569-570) and the ray samples (once).  The caller owns the descriptors.
+/// With wgpu 22's Vulkan backend: `vkAllocateMemory` with `VkImportMemoryFdInfoKHR { handleType: OPAQUE_FD, fd }` of
+/// `allocation_bytes`, `vkBindBufferMemory` on a linear `VkBuffer`, `wgpu_hal::vulkan::Device::buffer_from_raw`, then
+/// `wgpu::Device::create_buffer_from_hal`.  UNVERIFIED source like the rest of this file (no Rust toolchain in the image);
+/// the C entry point itself is GPU-tested from a second process (tests/test_gpu_handoff.py).
+pub struct SharedBuffers {
+    pub final_rgba8_fd: i32,
+    pub final_rgba8_bytes: usize,
+    pub ray_samples_fd: i32,
+    pub ray_samples_bytes: usize,
+}
+
+impl MainView {
+    pub fn import_shared(&mut self) -> Result<SharedBuffers, String> {
+        let (mut fd_a, mut n_a, mut fd_b, mut n_b) = (-1i32, 0usize, -1i32, 0usize);
+        self.check(unsafe { sys::linon_export_buffer_fd(self.view, sys::LINON_BUF_FINAL_RGBA8, &mut fd_a, &mut n_a) })?;
+        self.check(unsafe { sys::linon_export_buffer_fd(self.view, sys::LINON_BUF_RAY_SAMPLES, &mut fd_b, &mut n_b) })?;
+        Ok(SharedBuffers { final_rgba8_fd: fd_a, final_rgba8_bytes: n_a, ray_samples_fd: fd_b, ray_samples_bytes: n_b })
     }
 }
 

@@ -34,7 +34,7 @@ def _cxx():
 
 
 def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1", pairs: bool = False,
-          quiet_radius: int = 0, bvh: bool = False, n_faces: int = 36):
+          quiet_radius: int = 0, bvh: bool = False, n_faces: int = 36, module_src: str | None = None):
     """-> ctypes library with emu_march for this variant of the march module (pairs: also linon_march_pairs)."""
     from linon_b200.main_view import compile_check
     os.makedirs(_CACHE, exist_ok=True)
@@ -49,7 +49,7 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
         os.environ.update(env)
         os.environ["LINON_DUMP_SOURCE"] = dump
         try:
-            compile_check(body, flags=flags, math_mode=math_mode, n_faces=n_faces)
+            compile_check(body, flags=flags, math_mode=math_mode, n_faces=n_faces, module_src=module_src)
         except Exception as e:  # LINON_DUMP_SOURCE_ONLY: the module text is written, the NVRTC compile is skipped
             if "LINON_DUMP_SOURCE_ONLY" not in str(e):
                 raise

@@ -40,7 +40,7 @@ static int fixed_step_count(float h) {  // capi.cpp: fixed_step_count
     if (!(h > 0.0f)) return 0;
     volatile float t = 0.0f;
     int n = 0;
-    while (t <= 5.0f && n < (1 << 24)) {
+    while (t <= LINON_T_MAX && n < (1 << 24)) {  // the module's horizon (march_kernels.cuh; 5.0 as shipped)
         t = t + h;
         ++n;
     }

@@ -141,3 +141,15 @@ def test_python_constants_equal_the_headers_enumerators():
             checked += 1
     assert checked >= 25
     assert {k for k in header if k.startswith("OPT_")} <= {k for k in vars(_capi)}, "an option of the header has no binding"
+
+
+def test_frame_sizes_that_would_overflow_the_kernels_indices_are_refused(product_lib):
+    """Pixel indices are 32-bit in the kernels and the outline keys hold 21 bits per coordinate (round-1 advisor finding):
+    the size check comes before anything touches a device, so it is visible here."""
+    import ctypes as C
+    from linon_b200 import _capi as capi
+    L = capi.lib()
+    for w, h in ((1, 100), (100, 1), (65537, 16), (16, 70000), (65536, 32768), (50000, 50000)):
+        out = C.c_void_p(0)
+        assert L.linon_create(0, w, h, C.byref(out)) == capi.ERR_INVALID, (w, h)
+        assert b"width * height < 2^31" in L.linon_last_error(None)

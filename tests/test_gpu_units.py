@@ -1,5 +1,7 @@
 """Unit-level parity on the GPU: helper library, hit_triangle, field functions, overlay stencil, outline search, sample
 rays, error behaviour of reload_shader, row-block shards.  Needs a B200: -m gpu."""
+import os
+
 import numpy as np
 import pytest
 
@@ -266,9 +268,9 @@ def test_reloaded_module_helpers_run_on_the_device(view):
         with pytest.raises(LinonError) as e:
             view.reload_compute_shader(HELPER_MODULE.replace("cross(up_axis, p)", "crossx(up_axis, p)"))
         assert e.value.code == capi.ERR_COMPILE and "main_view.wgsl(5)" in e.value.message
-        with pytest.raises(LinonError) as e:
-            view.reload_compute_shader(HELPER_MODULE + "const eps: f32 = 0.01;")
-        assert e.value.code == capi.ERR_UNSUPPORTED and "'eps'" in e.value.message
+        with pytest.raises(LinonError) as e:  # an edit to the march itself that the kernel template has no switch for
+            view.reload_compute_shader(HELPER_MODULE + "fn hit_triangle(a: f32) -> f32 { return a; }")
+        assert e.value.code == capi.ERR_UNSUPPORTED and "'hit_triangle'" in e.value.message
         assert view.module_overrides() == ["swirl_gain", "up_axis", "swirl", "rotateZ"]
         assert np.array_equal(view.debug_eval_field(z, p, z, v, t), v)
         # frames render through every march kernel with the helper layer installed
@@ -526,3 +528,127 @@ def test_main_view_mirror_follows_the_reference(product_lib, scene):
         mv.render()
         mv.sync()
         assert (mv.hit_ids() >= 0).any()
+
+
+@pytest.mark.parametrize("name", ["eps", "backface_culling", "use_lighting", "light", "linear_mode", "adaptive_sampling"])
+def test_march_level_constants_hot_reload_against_the_edited_reference_shader(product_lib, scene, name):
+    """The file watcher path (src/main.rs:206-222) with an edit to a march-level constant of main_view.wgsl
+    (src/main_view.wgsl:65-76, :227): the module is accepted, the kernel template is rebuilt with the constant, and the frame
+    equals tests/golden/march_edits.npz - the REFERENCE's shader with the same edit in its text (transpiled and run on the CPU
+    by tests/golden/make_march_edits.py) - endpoints bit for bit in strict math, colours within 1/255; every march kernel agrees."""
+    import march_edit_cases as mc
+    verts, faces, center = scene
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "march_edits.npz"))
+    fn = PredefinedFunction.MirageSpherical
+    with MainView(verts, faces, center, mc.W, mc.H) as mv:
+        mv.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+        mv.reload_shader(fn.to_code())
+        mv.update_settings(make_settings())
+        mv.render_flags(0)
+        mv.sync()
+        stock = mv.mapping_texture().copy(), mv.ray_casting_texture().copy()
+        mv.reload_compute_shader(mc.partial_module(name))
+        assert set(mv.module_overrides()) == {new.split()[1].rstrip(":") for _, new in mc.CASES[name]}
+        frames = []
+        for kernel in (capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL):
+            mv.set_option(capi.OPT_KERNEL, kernel)
+            mv.render_flags(0)
+            mv.sync()
+            frames.append((mv.ray_casting_texture(), mv.mapping_texture(), mv.hit_ids()))
+        rgba8, endpoint, hit = frames[0]
+        assert np.abs(rgba8.astype(int) - z[f"rgba8_{name}"].astype(int)).max() <= 1
+        if name == "linear_mode":
+            assert np.array_equal(endpoint, stock[0])                 # `mapping` is not written in linear mode
+            assert (rgba8[..., 3][hit < 0] == 0).all()                # a miss stores vec4(0): alpha 0
+        else:
+            assert np.array_equal(endpoint.view(np.uint32), z[f"endpoint_{name}"].view(np.uint32))
+        assert not (np.array_equal(rgba8, stock[1]) and np.array_equal(endpoint, stock[0]))  # the edit changed the frame
+        for r, e, h in frames[1:]:
+            assert np.array_equal(r, rgba8) and np.array_equal(e.view(np.uint32), endpoint.view(np.uint32)) and np.array_equal(h, hit)
+        if name == "adaptive_sampling":
+            c = mv.counters()
+            assert c.accepted_steps == mc.W * mc.H * 51 and c.rejected_steps == 0
+        # production math with the edit: same hits, colours within 1/255 of the strict frame on >= 99.9 %
+        mv.set_option(capi.OPT_KERNEL, capi.KERNEL_TILES)
+        mv.set_option(capi.OPT_MATH, capi.MATH_FAST)
+        mv.render_flags(0)
+        mv.sync()
+        fast = mv.ray_casting_texture()
+        assert (np.abs(fast.astype(int) - rgba8.astype(int)).max(axis=-1) <= 1).mean() >= 0.99
+        mv.reload_compute_shader(None)
+        mv.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+        mv.render_flags(0)
+        mv.sync()
+        assert np.array_equal(mv.ray_casting_texture(), stock[1])    # back to the stock module
+
+
+def test_module_and_body_are_reloaded_as_one_step(product_lib, scene):
+    """MainView::reload_shader(device, Some(new_src), field_function) compiles the PAIR (src/main_view.rs:649-690): a helper
+    renamed in the module and in the body at once is accepted although neither half compiles against the other's old
+    state (round-1 advisor finding); a pair that does not compile changes nothing."""
+    verts, faces, center = scene
+    L = capi.lib()
+    import ctypes as C
+    with MainView(verts, faces, center, 64, 48) as mv:
+        mod_a = "fn bend(v: vec3<f32>, k: f32) -> vec3<f32> { return normalize(v + vec3<f32>(0.0, k, 0.0)); }"
+        mod_b = mod_a.replace("bend", "tilt")
+        err = C.create_string_buffer(8192)
+        assert L.linon_reload_shader(mv._view, mod_a.encode(), b"return bend(v, 0.1);", err, len(err)) == capi.OK, err.value
+        z = np.zeros((4, 3), np.float32)
+        v = np.tile(np.array([[0.0, 0.0, -1.0]], np.float32), (4, 1))
+        t = np.zeros(4, np.float32)
+        a = mv.debug_eval_field(z, z, z, v, t)
+        # the two-step route fails either way round ...
+        assert L.linon_reload_shader_source(mv._view, mod_b.encode(), err, len(err)) == capi.ERR_COMPILE  # body still calls bend
+        assert L.linon_set_field_function(mv._view, b"return tilt(v, 0.1);", err, len(err)) == capi.ERR_COMPILE  # module has no tilt
+        # ... the pair goes through, and computes the same
+        assert L.linon_reload_shader(mv._view, mod_b.encode(), b"return tilt(v, 0.1);", err, len(err)) == capi.OK, err.value
+        assert mv.module_overrides() == ["tilt"]
+        assert np.array_equal(mv.debug_eval_field(z, z, z, v, t), a)
+        # a bad pair changes nothing
+        assert L.linon_reload_shader(mv._view, mod_a.encode(), b"return tilt(v, 0.1);", err, len(err)) == capi.ERR_COMPILE
+        assert mv.module_overrides() == ["tilt"] and np.array_equal(mv.debug_eval_field(z, z, z, v, t), a)
+        assert L.linon_reload_shader(mv._view, None, b"return v;", err, len(err)) == capi.OK
+        assert mv.module_overrides() == []
+
+
+def test_a_rejected_mesh_leaves_the_current_one_in_place(product_lib, scene):
+    verts, faces, center = scene
+    with MainView(verts, faces, center, 64, 48) as mv:
+        mv.reload_shader(PredefinedFunction.TranslationX.to_code())
+        mv.render_flags(capi.RENDER_ADAPTIVE_OFF)
+        mv.sync()
+        before = mv.hit_ids().copy()
+        bad_faces = faces.copy()
+        bad_faces[5, 1] = 9999
+        with pytest.raises(LinonError):
+            mv.update_model(verts, bad_faces, center)
+        bad_verts = verts.copy()
+        bad_verts[3, 0] = np.nan
+        with pytest.raises(LinonError):
+            mv.update_model(bad_verts, faces, center)
+        mv.set_option(capi.OPT_FORCE_BVH, 1)  # re-stages the mesh from the host copies: must be the good one
+        mv.render_flags(capi.RENDER_ADAPTIVE_OFF)
+        mv.sync()
+        assert np.array_equal(mv.hit_ids(), before)
+        mv.set_option(capi.OPT_FORCE_BVH, 0)
+
+
+def test_an_overflowing_body_gives_the_same_frame_in_fast_and_strict_mode(product_lib, scene):
+    """field_weight == 1 with a body whose velocity overflows: the reference computes (1 - 1) * cur_dir + 1 * v = NaN once
+    cur_dir is infinite; the production build keeps the blend as written for generic bodies (no cur_dir = v shortcut), so
+    non-finite endpoints appear at the same pixels as in strict mode."""
+    verts, faces, center = scene
+    body = "return v * 1e20 * (1.0 + p.x * p.x);"
+    with MainView(verts, faces, center, 48, 32) as mv:
+        frames = {}
+        for math in (capi.MATH_STRICT, capi.MATH_FAST):
+            mv.set_option(capi.OPT_MATH, math)
+            mv.reload_shader(body)
+            mv.render_flags(capi.RENDER_ADAPTIVE_OFF)
+            mv.sync()
+            frames[math] = mv.mapping_texture().copy(), mv.hit_ids().copy()
+        a, b = frames[capi.MATH_STRICT], frames[capi.MATH_FAST]
+        assert np.array_equal(np.isnan(a[0][..., :3]).any(axis=-1), np.isnan(b[0][..., :3]).any(axis=-1))
+        assert np.isnan(a[0][..., :3]).any()
+        assert (a[1] == b[1]).mean() >= 0.99  # FMA contraction may move a hit across a triangle edge

@@ -1,0 +1,154 @@
+"""Hot reload of MARCH-LEVEL edits of main_view.wgsl: the constants of
+src/main_view.wgsl:65-76 (eps, backface_culling, use_lighting, linear_mode, the light constants), the module switches
+adaptive_sampling / sample_outline_rays (:227, :337) and the step-size / horizon / step-control literals of
+nonlinear_ray_color and sample_rays (:241-267, :287-288) are mapped to macros of the kernel template instead of being
+refused.  Each edit is rendered twice: by the device code of the march kernel executed on the host (tests/emu, strict math)
+and by the REFERENCE's own shader with the same edit applied to its text, transpiled by oracle/wgsl_ref - bit for bit.
+CPU only; the reference-side half needs the mount."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE
+from linon_b200 import _capi as capi
+from linon_b200.main_view import LinonError, PredefinedFunction as PF, compile_check, translate_wgsl_module
+
+HAS_REF = os.path.isdir(os.path.join(REFERENCE, "src"))
+W, H = 40, 28
+
+# (name, [(old text, new text) in main_view.wgsl], what the translator must report)
+CONST_EDITS = [
+    ("eps", [("const eps: f32 = 0.0000001;", "const eps: f32 = 0.001;")], "#define LINON_EPS (0.00100000005f)"),
+    ("backface_culling", [("const backface_culling: bool = false;", "const backface_culling: bool = true;")], "#define LINON_BACKFACE_CULLING 1"),
+    ("use_lighting", [("const use_lighting: bool = true;", "const use_lighting: bool = false;")], "#define LINON_USE_LIGHTING 0"),
+    ("light", [("const light_color: vec3<f32> = vec3<f32>(1.0, 1.0, 1.0);", "const light_color: vec3<f32> = vec3<f32>(0.9, 0.5, 0.25);"),
+               ("const ambient_strength: f32 = 0.01;", "const ambient_strength: f32 = 0.2;"),
+               ("const shininess: f32 = 64.0;", "const shininess: f32 = 8.0;")], "#define LINON_SHININESS (8.0f)"),
+    ("linear_mode", [("const linear_mode: bool = false;", "const linear_mode: bool = true;")], "#define LINON_LINEAR_MODE 1"),
+    ("adaptive_sampling", [("const adaptive_sampling: bool = true;", "const adaptive_sampling: bool = false;")], "// adaptive_sampling = 0"),
+]
+FN_EDITS = [
+    ("h_initial", [("let h_initial = 0.1;", "let h_initial = 0.05;")], "// h_initial = 0.05"),
+    ("horizon", [("for (; t <= 5.0;) {", "for (; t <= 3.0;) {")], "#define LINON_T_MAX (3.0f)"),
+    ("step control", [("diff > 10.0 * last_diff && h > 0.002", "diff > 4.0 * last_diff && h > 0.004"), ("            h = 0.001;\n", "            h = 0.003;\n"),
+                      ("if (2.0 * diff < last_diff", "if (3.0 * diff < last_diff")], "#define LINON_RESTORE_FACTOR (3.0f)"),
+    ("sample rays", [("    let h = 0.001;\n    let steps: i32 = 5000;", "    let h = 0.002;\n    let steps: i32 = 2500;")], "#define LINON_SAMPLE_STEPS 2500"),
+]
+
+
+def partial_module(edits):
+    """A module that only holds the edited declarations (modules need not repeat what they leave alone)."""
+    return "\n".join(new for _, new in edits)
+
+
+def reference_module(edits):
+    text = open(os.path.join(REFERENCE, "src", "main_view.wgsl"), encoding="utf-8").read()
+    for old, new in edits:
+        assert old in text, old
+        text = text.replace(old, new)
+    return text
+
+
+@pytest.mark.parametrize("name,edits,expect", CONST_EDITS, ids=[e[0] for e in CONST_EDITS])
+def test_constant_edits_are_mapped_to_the_kernel_template(product_lib, name, edits, expect):
+    text, names = translate_wgsl_module(partial_module(edits))
+    assert expect in text, text
+    assert all(new.split()[1].rstrip(":") in names for _, new in edits)
+    assert compile_check(PF.MirageSpherical.to_code(), flags=capi.RENDER_ADAPTIVE_OFF, math_mode=capi.MATH_FAST,
+                         module_src=partial_module(edits)) > 100_000
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's nonlinear_ray_color / sample_rays")
+@pytest.mark.parametrize("name,edits,expect", FN_EDITS, ids=[e[0] for e in FN_EDITS])
+def test_literal_edits_of_the_march_functions_are_mapped_too(product_lib, name, edits, expect):
+    text, names = translate_wgsl_module(reference_module(edits))
+    assert expect in text, text
+    assert ("sample_rays" if name == "sample rays" else "nonlinear_ray_color") in names
+    assert compile_check(PF.MirageSpherical.to_code(), flags=0, math_mode=capi.MATH_FAST, module_src=reference_module(edits)) > 100_000
+
+
+def test_the_unedited_module_installs_no_layer(product_lib):
+    if HAS_REF:
+        text, names = translate_wgsl_module(reference_module([]))
+        assert names == [] and text.strip() == ""
+
+
+@pytest.mark.parametrize("module,needle", [
+    ("const eps: f32 = 0.5;", "outside the range"),
+    ("const eps: f32 = 1.0 / 3.0;", "was edited"),                      # an expression, not a literal: the march itself
+    ("const shininess: f32 = -1.0;", "outside the range"),
+    ("const backface_culling: bool = 1;", "was edited"),
+    ("struct Camera { origin: vec4<f32> };", "was edited"),
+    ("fn hit_triangle(a: f32) -> f32 { return a; }", "was edited"),
+])
+def test_other_march_edits_are_still_refused_by_name(product_lib, module, needle):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl_module(module)
+    assert e.value.code == capi.ERR_UNSUPPORTED and needle in e.value.message, e.value.message
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs the reference's text")
+@pytest.mark.parametrize("edits,needle", [
+    ([("let k2 = field_function(cur_point, cur_point + 0.5 * h * k1", "let k2 = field_function(cur_point, cur_point + 0.25 * h * k1")], "nothing else of it"),
+    ([("let h_initial = 0.1;", "let h_initial = 7.0;")], "outside the range"),
+    ([("    let steps: i32 = 5000;", "    let steps: i32 = 5050;")], "multiple of 100"),
+    ([("cur_point = cur_point + step_dir;\n        t = t + h;\n        last_v = v;", "cur_point = cur_point + step_dir * 1.0;\n        t = t + h;\n        last_v = v;")], "was edited"),
+])
+def test_structural_edits_of_the_march_functions_are_refused(product_lib, edits, needle):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl_module(reference_module(edits))
+    assert e.value.code == capi.ERR_UNSUPPORTED and needle in e.value.message, e.value.message
+
+
+# ---- the edited kernel against the edited reference shader ---------------------------------------------------------------
+def _ref_frame(body, edits, variant, verts, faces, cam, st):
+    from oracle import cpu_oracle as co
+    from oracle import wgsl_reference as wr
+    from oracle.wgsl_ref import build_ref
+    with tempfile.TemporaryDirectory() as d:
+        lib = C.CDLL(build_ref.build_custom(body, d, variant=variant, module_edits=edits))
+        f = wr.RefFrame(W, H, co.make_camera(cam), co.make_settings(st), verts.shape[0], faces.shape[0], verts.ctypes.data,
+                        faces.ctypes.data, None, None, 0)
+        out = dict(rgba8=np.zeros((H, W, 4), np.uint8), endpoint=np.zeros((H, W, 4), np.float32), ray_samples=np.zeros((800, 8), np.float32))
+        o = wr.RefOutputs(None, out["rgba8"].ctypes.data, out["endpoint"].ctypes.data, out["ray_samples"].ctypes.data)
+        assert lib.wgslref_custom_main_view(C.byref(f), C.byref(o)) == 0
+    return out
+
+
+@pytest.mark.skipif(not HAS_REF, reason="the reference-side half needs the mount")
+@pytest.mark.parametrize("name,edits,expect", CONST_EDITS + FN_EDITS, ids=[e[0] for e in CONST_EDITS + FN_EDITS])
+def test_edited_kernel_equals_the_edited_reference_shader(product_lib, name, edits, expect):
+    """Strict math on the host emulation of the device code: endpoints and hit pattern bit for bit, colours within 1/255
+    (pow: libm here on both sides, the rgba8 rounding is the reference's)."""
+    from emu import emu
+    from oracle import np_oracle as npo
+    verts, faces, center = npo.default_scene()
+    verts, faces = np.ascontiguousarray(verts, np.float32), np.ascontiguousarray(faces, np.uint32)
+    cam = npo.camera_uniform(npo.default_camera(center, W, H))
+    st = dict(npo.default_settings())
+    fn = PF.MirageSpherical
+    adaptive_module = name != "adaptive_sampling"
+    # as the application renders (adaptive sampling per the module), except: the step-control literals only act in adaptive frames
+    flags = 0
+    ref = _ref_frame(fn.to_code(), edits, "default", verts, faces, cam, st)
+    lib = emu.build(fn.to_code(), flags, capi.MATH_STRICT, module_src=reference_module(edits))
+    if name == "sample rays":
+        from oracle import cpu_oracle as co
+        pos = co.sample_positions(cam, st, W, H)
+        got = emu.march(lib, verts, faces, cam, st, W, H, sample_pos=pos)
+        assert np.array_equal(got["ray_samples"].view(np.uint32), ref["ray_samples"].view(np.uint32))
+        return
+    got = emu.march(lib, verts, faces, cam, st, W, H)
+    assert np.abs(got["rgba8"].astype(int) - ref["rgba8"].astype(int)).max() <= 1, name
+    if name != "linear_mode":  # linear_mode never writes `mapping`
+        assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32)), name
+        assert (got["rgba8"][..., 3] == 255).all()
+    else:
+        assert (got["endpoint"] == 0).all() and (got["rgba8"][..., 3] < 255).any()  # alpha = hit distance, 0 on a miss
+    if name == "adaptive_sampling":
+        assert int(got["counters"][0]) == W * H * 51 and int(got["counters"][2]) == 0 and not adaptive_module
+    if name == "horizon":
+        assert int(got["counters"][0]) < W * H * 80

@@ -77,7 +77,7 @@ def test_edits_to_the_march_itself_are_refused_by_name(product_lib):
     """The CUDA march is a hand-written kernel template: a module that redefines one of its functions, constants, structs
     or bindings is not silently ignored."""
     for text, name in (("fn ray_color(origin: vec3<f32>, direction: vec3<f32>, max_dist: f32) -> vec4<f32> { return vec4<f32>(0.0); }", "ray_color"),
-                       ("const eps: f32 = 0.001;", "eps"),
+                       ("const eps: f32 = 1.0 / 1000.0;", "eps"),  # a literal value would be mapped (tests/test_march_edits_cpu.py)
                        ("struct Camera { origin: vec4<f32> }", "Camera"),
                        ("@group(0) @binding(7)\nvar<uniform> extra: vec4<f32>;", "extra")):
         with pytest.raises(LinonError) as e:
@@ -108,10 +108,19 @@ def reference_module():
 
 @needs_reference
 def test_the_hash_table_is_the_reference_module(product_lib):
-    items = scan_wgsl_module(reference_module())
+    items = scan_wgsl_module(reference_module(), full=True)
     table = open(os.path.join(ROOT, "linon_b200", "csrc", "host", "module_items.inc")).read()
-    rows = re.findall(r'\{"(\w+)", "(\w+)", 0x([0-9a-f]{16})ull\}', table)
-    assert [(k, n, f"{h:016x}") for k, n, h, _ in items] == rows and len(rows) == 45
+    rows = re.findall(r'\{"(\w+)", "(\w+)", 0x([0-9a-f]{16})ull, 0x([0-9a-f]{16})ull\}', table)
+    assert [(k, n, f"{h:016x}", f"{hm:016x}") for k, n, h, _, hm, _ in items] == rows and len(rows) == 45
+    # the literal tables of the two march functions (values only) and the ordinals of the literals that are mapped
+    lits = open(os.path.join(ROOT, "linon_b200", "csrc", "host", "module_literals.inc")).read()
+    by_name = {n: l for _, n, _, _, _, l in items}
+    for fn, holes in (("nonlinear_ray_color", {9: 0.1, 10: 5.0, 19: 10.0, 20: 0.002, 21: 0.001, 24: 2.0}), ("sample_rays", {1: 0.001, 2: 5000.0})):
+        m = re.search(r"kLit_%s\[\] = \{([^}]*)\}" % fn, lits)
+        assert [float(x) for x in m.group(1).split(",")] == by_name[fn]
+        m = re.search(r"kLitHoles_%s\[\] = \{([^}]*)\}" % fn, lits)
+        assert [int(x) for x in m.group(1).split(",")] == list(holes)
+        assert all(by_name[fn][k] == v for k, v in holes.items())
 
 
 @needs_reference
@@ -130,10 +139,12 @@ def test_an_edited_helper_pulls_in_the_unchanged_helpers_that_call_it(product_li
     assert names == ["refraction_index", "refraction"]  # refraction is unchanged but must bind to the new index
     assert "const auto c2 = 0.004f;" in cuda and "w_reflect(v_in, n_ref)" in cuda
     assert compile_check(PredefinedFunction.MiragePlane.to_code(), math_mode=capi.MATH_STRICT, module_src=edited) > 100_000
-    # PI may be edited (it is only used by field functions); the march's own constants may not
+    # PI may be edited (it is only used by field functions); so may the march's own constants (mapped to macros of the
+    # kernel template, tests/test_march_edits_cpu.py) - the structure of the march functions may not
     assert translate_wgsl_module(src.replace("const PI: f32 = 3.141592653589793;", "const PI: f32 = 3.14;"))[1] == ["PI"]
+    assert translate_wgsl_module(src.replace("const shininess: f32 = 64.0;", "const shininess: f32 = 8.0;"))[1] == ["shininess"]
     for old, new, name in (("let f = 1.0 / a;", "let f = 2.0 / a;", "hit_triangle"),
-                           ("const shininess: f32 = 64.0;", "const shininess: f32 = 8.0;", "shininess")):
+                           ("let spec = pow(intensity, shininess);", "let spec = pow(intensity, 2.0 * shininess);", "ray_color")):
         assert old in src
         with pytest.raises(LinonError) as e:
             translate_wgsl_module(src.replace(old, new))
