@@ -130,6 +130,13 @@ def static_source_hash() -> str:
     return h.hexdigest()[:16]
 
 
+def nvrtc_version():
+    """The NVRTC the library compiled the timed kernels with (opened by absolute path: torch's own copy is not used)."""
+    from linon_b200.main_view import nvrtc_info
+    path, (major, minor) = nvrtc_info()
+    return f"{major}.{minor} ({path})"
+
+
 def committed_profile(path: str, kernel_substring: str, identity: str | None, key: str = "cubin_hash"):
     """A committed ncu summary (tools/ncu_summary.py) is evidence about ONE binary: it names what it profiled - the FNV-1a
     hash of the NVRTC cubin (`cubin_hash`, march kernels) or the hash of the sources of the ahead-of-time kernels
@@ -729,7 +736,7 @@ def run_ours(args):
             kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass culling checks)",
             quiet_zone=("on" if last.get("quiet", 0) else "off") + ": straight steps (velocity = direction) while the whole warp is outside the "
                        "mirage's zone of influence, where the reference's own fp32 evaluation is the identity; every RK4 step is executed and counted",
-            plane_culling=True, march_cubin_hash=cubin_hash, march_regs=march_regs,
+            plane_culling=True, march_cubin_hash=cubin_hash, march_regs=march_regs, nvrtc=nvrtc_version(),
             parallelism=(f"row-blocks x{world}" + (", peer stores into rank 0 over NVLink during the march (no gather)" if peer_stores else ", grouped NCCL send/recv to rank 0 after the march")) if world > 1 else "single GPU",
             l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
         clocks=clocks,

@@ -302,6 +302,11 @@ int linon_get_timings(linon_view* v, linon_timings* out);
  * line tables are left out, so an edit that only moves lines keeps the identity).  A committed ncu capture names the hash of
  * the kernel it profiled; bench.py refuses its counters when the running kernel is a different binary. */
 int linon_march_cubin_hash(linon_view* v, uint64_t* out);
+/* The NVRTC that compiles the field functions (the reference's counterpart: naga + the driver's compiler behind
+ * create_shader_module, src/main_view.rs:96-102, 662-665).  The library opens the toolkit's libnvrtc privately by the absolute
+ * path recorded at build time, so a host process that already holds another libnvrtc.so.12 (torch ships one) gets the same
+ * kernels as every other process; LINON_NVRTC_LIB overrides the path.  Returns the file in use and its version. */
+int linon_nvrtc_info(char* path, size_t path_len, int* major, int* minor);
 /* Last error message of the handle (or of the failed linon_create when v is NULL). */
 const char* linon_last_error(const linon_view* v);
 

@@ -104,6 +104,7 @@ PROTOTYPES = [
     ("linon_get_counters", _I, [_P, C.POINTER(Counters)]),
     ("linon_get_timings", _I, [_P, C.POINTER(Timings)]),
     ("linon_march_cubin_hash", _I, [_P, C.POINTER(C.c_uint64)]),
+    ("linon_nvrtc_info", _I, [_P, _S, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("linon_last_error", _CP, [_P]),
     ("linon_translate_wgsl", _I, [_CP, _P, _S, _P, _S]),
     ("linon_compile_check", _I, [_CP, _U, _I, _U, C.POINTER(_S), _P, _S]),

@@ -120,6 +120,69 @@ struct Driver {
 Driver g_drv;
 std::mutex g_drv_mutex;
 
+// ---- NVRTC, loaded privately by absolute path --------------------------------------------------------------------------
+// A process that imported torch first already holds torch's own libnvrtc.so.12 (12.8 in this image) under the same soname,
+// and a library linked against "libnvrtc.so.12" would silently bind to that copy: the kernel a benchmark times would then be
+// compiled by another compiler than the one the tests and the ncu captures saw (found in round 2: two cubin hashes for one
+// variant).  The toolkit's NVRTC is therefore opened by the path recorded at build time (LINON_NVRTC_PATH; RTLD_LOCAL, its
+// own copy whatever else is loaded), LINON_NVRTC_LIB overrides it, the bare soname is the last resort.
+#ifndef LINON_NVRTC_PATH
+#define LINON_NVRTC_PATH ""
+#endif
+struct Nvrtc {
+    void* lib = nullptr;
+    std::string path, error;
+    int major = 0, minor = 0;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    nvrtcResult (*Version)(int*, int*) = nullptr;
+
+    bool load() {
+        if (lib) return true;
+        const char* env = getenv("LINON_NVRTC_LIB");
+        const char* candidates[] = {env ? env : "", LINON_NVRTC_PATH, "libnvrtc.so.12"};
+        for (const char* c : candidates) {
+            if (!c[0]) continue;
+            lib = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) {
+            const char* why = dlerror();
+            error = std::string("NVRTC not found (tried LINON_NVRTC_LIB, " LINON_NVRTC_PATH ", libnvrtc.so.12): ") + (why ? why : "");
+            return false;
+        }
+        auto sym = [&](const char* n) { return dlsym(lib, n); };
+        CreateProgram = (decltype(CreateProgram))sym("nvrtcCreateProgram");
+        DestroyProgram = (decltype(DestroyProgram))sym("nvrtcDestroyProgram");
+        CompileProgram = (decltype(CompileProgram))sym("nvrtcCompileProgram");
+        GetProgramLogSize = (decltype(GetProgramLogSize))sym("nvrtcGetProgramLogSize");
+        GetProgramLog = (decltype(GetProgramLog))sym("nvrtcGetProgramLog");
+        GetCUBINSize = (decltype(GetCUBINSize))sym("nvrtcGetCUBINSize");
+        GetCUBIN = (decltype(GetCUBIN))sym("nvrtcGetCUBIN");
+        GetErrorString = (decltype(GetErrorString))sym("nvrtcGetErrorString");
+        Version = (decltype(Version))sym("nvrtcVersion");
+        if (!CreateProgram || !DestroyProgram || !CompileProgram || !GetProgramLogSize || !GetProgramLog || !GetCUBINSize ||
+            !GetCUBIN || !GetErrorString || !Version) {
+            error = "the NVRTC library lacks a required entry point";
+            dlclose(lib);
+            lib = nullptr;
+            return false;
+        }
+        Version(&major, &minor);
+        Dl_info info;
+        if (dladdr((void*)CreateProgram, &info) && info.dli_fname) path = info.dli_fname;
+        return true;
+    }
+};
+Nvrtc g_nvrtc;
+std::mutex g_nvrtc_mutex;
+
 // ---- device-side parameter blocks (must match device/march_kernels.cuh) -------------------------------------
 struct MarchParamsH {
     float cam_origin[4], cam_view[4], cam_up[4];
@@ -282,8 +345,15 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
     // an edited helper layer may redefine what the predefined bodies call: they then run the generic translation
     const linon::MirageParams mirage = (var.math == 2 && var.specialize && layer.empty()) ? mirage_params(wgsl_body) : linon::MirageParams();
     const std::string src = build_source(cuda_body, mirage, layer);
+    {
+        std::lock_guard<std::mutex> lock(g_nvrtc_mutex);
+        if (!g_nvrtc.load()) {
+            log = g_nvrtc.error;
+            return false;
+        }
+    }
     nvrtcProgram prog = nullptr;
-    if (nvrtcCreateProgram(&prog, src.c_str(), "linon_march.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+    if (g_nvrtc.CreateProgram(&prog, src.c_str(), "linon_march.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
         log = "nvrtcCreateProgram failed";
         return false;
     }
@@ -334,16 +404,16 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
             fclose(f);
         }
         if (getenv("LINON_DUMP_SOURCE_ONLY")) {  // the caller only wants the text (tests/emu): skip the NVRTC compile
-            nvrtcDestroyProgram(&prog);
+            g_nvrtc.DestroyProgram(&prog);
             log = "LINON_DUMP_SOURCE_ONLY: source written, not compiled";
             return false;
         }
     }
-    const nvrtcResult rc = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    const nvrtcResult rc = g_nvrtc.CompileProgram(prog, (int)copts.size(), copts.data());
     size_t log_size = 0;
-    nvrtcGetProgramLogSize(prog, &log_size);
+    g_nvrtc.GetProgramLogSize(prog, &log_size);
     std::string full_log(log_size, '\0');
-    if (log_size > 1) nvrtcGetProgramLog(prog, &full_log[0]);
+    if (log_size > 1) g_nvrtc.GetProgramLog(prog, &full_log[0]);
     if (rc != NVRTC_SUCCESS) {
         // keep the diagnostics that point into the user's body first; fall back to the whole log
         std::string mine;
@@ -361,17 +431,17 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
             const size_t e = full_log.find("error");
             size_t eol = e == std::string::npos ? std::string::npos : full_log.find('\n', e);
             mine = "the field function does not fit the kernel template (" +
-                   (e == std::string::npos ? std::string(nvrtcGetErrorString(rc)) : full_log.substr(e, eol == std::string::npos ? std::string::npos : eol - e)) + ")";
+                   (e == std::string::npos ? std::string(g_nvrtc.GetErrorString(rc)) : full_log.substr(e, eol == std::string::npos ? std::string::npos : eol - e)) + ")";
         }
         log = mine;
-        nvrtcDestroyProgram(&prog);
+        g_nvrtc.DestroyProgram(&prog);
         return false;
     }
     size_t n = 0;
-    nvrtcGetCUBINSize(prog, &n);
+    g_nvrtc.GetCUBINSize(prog, &n);
     cubin.resize(n);
-    nvrtcGetCUBIN(prog, cubin.data());
-    nvrtcDestroyProgram(&prog);
+    g_nvrtc.GetCUBIN(prog, cubin.data());
+    g_nvrtc.DestroyProgram(&prog);
     log = full_log;
     return true;
 }
@@ -1398,6 +1468,15 @@ int linon_debug_profile(linon_view* v, uint64_t* out16) {
     CK(v, cudaSetDevice(v->device));
     CK(v, cudaMemcpyAsync(out16, v->d_counters, 128, cudaMemcpyDeviceToHost, v->stream));
     CK(v, cudaStreamSynchronize(v->stream));
+    return LINON_OK;
+}
+
+int linon_nvrtc_info(char* path, size_t path_len, int* major, int* minor) {
+    std::lock_guard<std::mutex> lock(g_nvrtc_mutex);
+    if (!g_nvrtc.load()) return LINON_ERR_COMPILE;
+    if (path && path_len) snprintf(path, path_len, "%s", g_nvrtc.path.c_str());
+    if (major) *major = g_nvrtc.major;
+    if (minor) *minor = g_nvrtc.minor;
     return LINON_OK;
 }
 

