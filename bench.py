@@ -124,7 +124,7 @@ def static_source_hash() -> str:
     """Identity of the ahead-of-time kernels (overlay, outline search, click positions): sha256 of their sources."""
     import hashlib
     h = hashlib.sha256()
-    for rel in ("static_kernels.cu", "overlay_direct.cuh", "outline_keys.cuh"):
+    for rel in ("static_kernels.cu", "overlay_direct.cuh", "overlay_tile.cuh", "outline_keys.cuh"):
         with open(os.path.join(ROOT, "linon_b200", "csrc", "device", rel), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -455,9 +455,14 @@ def run_configs_child(args):
         for mouse, label in (((0.5, 0.6), "click (0.5, 0.6)"), ((0.36, 0.55), "click on the mirage rim")):
             mv.update_settings(make_settings(overlay_mode=1, mouse_pos=mouse))
             emit(config="C4", size="1920x1080", function=fn.name, variant=label, **measure(mv, 0))
-        mv.update_settings(make_settings(overlay_mode=1))
+        # At 1920x1080 neighbouring endpoints of this frame differ so little that with the application's start-up scaling (50)
+        # no exponent reaches the 0.8 threshold (measured: max 0.41) and all eight searches fall back to pixel (0, 0); the GUI's
+        # slider goes from 1 to 100 (src/application.rs:315-317): its upper end puts the rim of the mirage above the threshold.
+        mv.update_settings(make_settings(overlay_mode=1, lyapunov_scaling=100.0))
         r = measure(mv, capi.RENDER_OUTLINE)
-        emit(config="C4", size="1920x1080", function=fn.name, variant="outline mode (8 searches over exponents >= 0.8)",
+        ex = mv.exponents()
+        emit(config="C4", size="1920x1080", function=fn.name, variant="outline mode (8 searches over exponents >= 0.8, lyapunov_scaling 100)",
+             exponents_above_threshold=int((ex >= 0.8).sum()),
              sample_positions=np.asarray(mv.read(capi.BUF_SAMPLE_POS)).round(5).tolist(), **r)
     emit(done=True)
     return 0
@@ -616,6 +621,7 @@ def run_ours(args):
         dev_ms.append(e0.elapsed_time(e1))
         t = mv.timings()
         overlay_ms.append(t.overlay_ms)
+        last["overlay_kernel"] = int(t.overlay_kernel)
         if world > 1:
             t, counters = last["timings"], last["counters"]
         else:
@@ -723,7 +729,9 @@ def run_ours(args):
         oprof, onote = committed_profile(OVERLAY_PROFILE, "overlay", static_source_hash(), "source_hash")
         overlay_roof = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
                             traffic=(oprof.get("dram_traffic_bytes") if (oprof and (W, H) == (BASE_W, BASE_H)) else None),
-                            kernel=(oprof or {}).get("kernel", "overlay"), algorithmic_bytes_per_launch=ob, launch_ms=o_ms,
+                            kernel={0: "overlay_kernel (hand-staged tile)", 1: "overlay_direct_kernel (four global taps per pixel)",
+                                    2: "overlay_tile_kernel (tile + halo by one TMA load per CTA, cp.async.bulk.tensor.2d + mbarrier)"}.get(last.get("overlay_kernel"), "overlay"),
+                            profiled_kernel=(oprof or {}).get("kernel"), algorithmic_bytes_per_launch=ob, launch_ms=o_ms,
                             peak_source=peak_src, profile=onote)
 
     line = dict(
@@ -803,7 +811,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--quiet-zone", type=int, default=None, choices=[0, 1, 2],
                     help="override LINON_OPT_QUIET_ZONE (library default: 2 = straight / identity steps outside the mirage's zone of influence)")
-    ap.add_argument("--overlay-kernel", type=int, default=None, choices=[0, 1], help="override LINON_OPT_OVERLAY_KERNEL")
+    ap.add_argument("--overlay-kernel", type=int, default=None, choices=[0, 1, 2], help="override LINON_OPT_OVERLAY_KERNEL (default 2: TMA tile kernel)")
     ap.add_argument("--peer-stores", type=int, default=1, choices=[0, 1],
                     help="N > 1: 1 (default since round 2: 12.86 vs 16.08 ms per step at N = 2, bit-equal frames) = every rank's march "
                          "stores straight into rank 0's frame buffers (CUDA IPC + NVLink); 0 = one grouped NCCL send/recv to rank 0 "

@@ -125,10 +125,13 @@ enum {
                                     = 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6).  1250 ... 4000: below
                                     1886 the reference's eta is 1 +- its rounding noise and the real-number deflection summed over
                                     the excluded shell is <= 1.85e-4 exp(6 - 12 r): 1e-9 rad at 1500 (mirage_fused.cuh) */
-    LINON_OPT_OVERLAY_KERNEL = 14, /* overlay stencil (src/overlay.wgsl:99-146).  0: 32x16 tile + halo of the endpoints staged in
-                                    shared memory (the round-1 default).  1 (default since round 2: 54.9 vs 91.0 us at C3 on the
-                                    driver's box, bit-equal): every pixel fetches its four taps through the read-only path, no
-                                    shared memory, no barrier (csrc/device/overlay_direct.cuh).  Bit-identical results */
+    LINON_OPT_OVERLAY_KERNEL = 14, /* overlay stencil (src/overlay.wgsl:99-146), bit-identical results in every variant.
+                                    0: 32x16 tile + halo of the endpoints staged in shared memory by the threads (round 1).
+                                    1: every pixel fetches its four taps through the read-only path, no shared memory, no
+                                    barrier (csrc/device/overlay_direct.cuh; 53 vs 91 us at C3).
+                                    2 (default): 32x32 tile + halo by ONE TMA load per CTA (cp.async.bulk.tensor.2d + mbarrier),
+                                    taps are four LDS.128 at compile-time offsets (csrc/device/overlay_tile.cuh); runs variant 1
+                                    when the driver cannot encode the tensor map or delta is outside 1..10 */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.
@@ -156,6 +159,8 @@ typedef struct linon_timings { /* CUDA-event times of the last render, milliseco
     int32_t march_block;        /* threads per CTA */
     float march_phase_a_ms;     /* persistent kernel: time of the pre-hit phase (march_ms covers both phases) */
     int32_t march_kernel;       /* the kernel that ran: 0 tiles, 1 persistent (two phases), 2 pairs, 3 persistent (one phase) */
+    int32_t overlay_kernel;     /* the overlay kernel that ran: 0 hand-staged tile, 1 direct, 2 TMA tile (LINON_OPT_OVERLAY_KERNEL;
+                                   2 falls back to 1 when no tensor map can be made) */
 } linon_timings;
 
 /* MainView::new (src/main_view.rs:82-458): allocates textures/buffers for width x height on CUDA device

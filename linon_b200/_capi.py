@@ -53,7 +53,7 @@ class Timings(C.Structure):
     _fields_ = [("march_ms", C.c_float), ("overlay_ms", C.c_float), ("sample_rays_ms", C.c_float),
                 ("outline_search_ms", C.c_float), ("jit_ms", C.c_float), ("march_regs", C.c_int32),
                 ("march_grid", C.c_int32), ("march_block", C.c_int32), ("march_phase_a_ms", C.c_float),
-                ("march_kernel", C.c_int32)]
+                ("march_kernel", C.c_int32), ("overlay_kernel", C.c_int32)]
 
 
 assert C.sizeof(Camera) == 112 and C.sizeof(Settings) == 24

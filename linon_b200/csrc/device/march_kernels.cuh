@@ -336,7 +336,14 @@ __device__ __forceinline__ void test_face(const float4* __restrict__ s_tri, int 
 __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri, const int* __restrict__ s_range,
                                                const float4* __restrict__ bvh, vec3f origin, vec3f direction,
                                                float max_dist, float origin_l1, float& t_best, int& id_best,
-                                               float& min_plane_dist, unsigned int& face_tests) {
+                                               float& min_plane_dist, unsigned int& face_tests, bool boxes_clear = false,
+                                               float box_floor = 0.0f) {
+    // boxes_clear (two-pass checks of the shared-memory path): the caller's first pass has already found every cluster box
+    // farther than an upper bound of this step's reach (box_floor = the smallest box distance), so the runs of groups those
+    // boxes bound are skipped without looking at them - by the argument of the box test below, from the same distances (every
+    // face of a cluster lies inside its inflated box; a box farther than 1.002 max_dist + 1e-5 (1 + |origin|_1) holds no face
+    // that can report t < max_dist).  On the final approach to a wall of the room this is the common case: the check then
+    // costs the room's planes and the faces of the one wall in reach instead of all plane groups and every box.
     t_best = -1.0f;
     id_best = -1;
 #if LINON_BVH
@@ -402,6 +409,10 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
         float box_dist = 0.0f;
 #if LINON_N_BOXES > 0
         const int box = (seg >> 24) - 1;
+        if (box >= 0 && boxes_clear) {
+            nearest = fminf(nearest, box_floor);  // min over the skipped boxes of their distances: what the loop would accumulate
+            continue;
+        }
         if (box >= 0) {
             const float4 lo = s_box[2 * box], hi = s_box[2 * box + 1];
             const float dx = fmaxf(fmaxf(lo.x - origin.x, origin.x - hi.x), 0.0f);
@@ -467,7 +478,7 @@ __device__ __forceinline__ void intersect_mesh(const float4* __restrict__ s_tri,
 // When the bound exceeds the reach no face can be hit on this step and the caller skips intersect_mesh - including
 // normalize(step_dir) and length(step_dir), which only feed it.
 #if LINON_CULL && !LINON_BVH
-__device__ __forceinline__ float nearest_geometry_distance(const float4* __restrict__ s_tri, vec3f origin) {
+__device__ __forceinline__ float nearest_geometry_distance(const float4* __restrict__ s_tri, vec3f origin, float& box_nearest) {
     const float4* __restrict__ s_plane = s_tri + 3 * LINON_N_FACES + LINON_N_GROUPS;
     float nearest = 3.0e38f;
 #pragma unroll LINON_GROUP_UNROLL
@@ -487,7 +498,10 @@ __device__ __forceinline__ float nearest_geometry_distance(const float4* __restr
         const float dz = fmaxf(fmaxf(lo.z - origin.z, origin.z - hi.z), 0.0f);
         nearest2 = fminf(nearest2, dx * dx + dy * dy + dz * dz);
     }
-    nearest = fminf(nearest, sqrtf(nearest2));
+    box_nearest = sqrtf(nearest2);
+    nearest = fminf(nearest, box_nearest);
+#else
+    box_nearest = 3.0e38f;
 #endif
     return nearest;
 }
@@ -939,10 +953,15 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     // rare.  With the default step (0.1, a tenth of the room) most checks do find a plane in reach and the
                     // first pass would be paid on top (measured: +30 % on the 51-step frames), so it is compiled out.
                     constexpr bool two_pass = LINON_H_INITIAL < 0.01f;
-                    float nearest = two_pass ? nearest_geometry_distance(s_tri, r.p) : 0.0f;
-                    if (!two_pass || !(nearest > SafeDistance::reach_bound(v_inf, kh, p_l1)))
+                    float box_nearest = 0.0f;
+                    float nearest = two_pass ? nearest_geometry_distance(s_tri, r.p, box_nearest) : 0.0f;
+                    const float reach_up = SafeDistance::reach_bound(v_inf, kh, p_l1);
+                    const bool boxes_clear = two_pass && box_nearest > reach_up;  // NaN compares false: every run is looked at
+                    if (!two_pass || !(nearest > reach_up))
 #else
                     float nearest = 0.0f;
+                    const float box_nearest = 0.0f;
+                    const bool boxes_clear = false;
 #endif
                     {
                         const vec3f step_dir = r.dir * h;
@@ -950,7 +969,8 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                         const vec3f dirn = w_normalize(step_dir);
                         float t_hit, plane_nearest;
                         int id;
-                        intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, plane_nearest, cnt.face_tests);
+                        intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, plane_nearest, cnt.face_tests,
+                                       boxes_clear, box_nearest);
                         // both are lower bounds of the distance to the geometry: keep the better one (inside a cluster's
                         // box the first-pass bound is 0 and the plane distances take over)
                         nearest = fmaxf(nearest, plane_nearest);

@@ -6,12 +6,14 @@
 //                        out, 4 exponent out), 8 in mode 0.  Endpoints are staged per CTA into shared memory
 //                        (tile + halo of `delta`, three float planes) so every texel is fetched from L2/HBM once
 //                        per tile instead of four times.
-//   overlay_direct_kernel  opt-in variant without the shared-memory stage (overlay_direct.cuh; LINON_OPT_OVERLAY_KERNEL)
+//   overlay_tile_kernel  the default (LINON_OPT_OVERLAY_KERNEL = 2): tile + halo by one TMA load per CTA (overlay_tile.cuh)
+//   overlay_direct_kernel  four global taps per pixel, no shared memory (overlay_direct.cuh; LINON_OPT_OVERLAY_KERNEL = 1)
 //   outline_search       the eight extreme / first-hit searches over exponents >= 0.8 that pick the "Outline"
 //                        sample rays (src/main_view.wgsl:381-468), restated as ONE parallel arg-reduction with
 //                        the intended stride W instead of eight serial W*H scans.
 //   click_positions      sample-ray positions around the clicked fragment, src/main_view.wgsl:469-472.
 //   fp32_peak_kernel     FFMA-chain microbenchmark: the measured FP32 roofline denominator.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -113,7 +115,7 @@ overlay_kernel(int W, int H, int overlay_mode, int delta, float scaling, const u
 #include "overlay_direct.cuh"
 namespace linon {
 
-// Direct variant (opt-in, LINON_OPT_OVERLAY_KERNEL = 1): no shared-memory staging, see overlay_direct.cuh
+// Direct variant (LINON_OPT_OVERLAY_KERNEL = 1): no shared-memory staging, see overlay_direct.cuh
 __global__ void __launch_bounds__(OVD_TX * OVD_WARPS, 8)  // 32 registers: 64 resident warps per SM
 overlay_direct_kernel(int W, int H, int overlay_mode, int delta, float scaling, const unsigned int* __restrict__ raycast,
                       const float4* __restrict__ endpoint, unsigned int* __restrict__ final_rgba,
@@ -122,9 +124,94 @@ overlay_direct_kernel(int W, int H, int overlay_mode, int delta, float scaling, 
                           scaling, raycast, endpoint, final_rgba, exponents);
 }
 
+// ---- tile variant (LINON_OPT_OVERLAY_KERNEL = 2, default): the endpoint tile + halo arrives by one TMA load per CTA ----
+__device__ __forceinline__ uint32_t ovt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ovt_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+}  // namespace linon
+#include "overlay_tile.cuh"
+namespace linon {
+
+// One CTA = one 32 x TH tile.  Thread 0 arms the mbarrier with the byte count of the box and issues the TMA; every thread
+// loads its colours, then waits on the barrier's phase and reads its taps from the tile (overlay_tile_thread).
+template <int TH, int D>
+__global__ void __launch_bounds__(OVT_TX * OVT_WARPS)
+overlay_tile_kernel(const __grid_constant__ CUtensorMap endpoint_map, int W, int H, int overlay_mode, float scaling,
+                    const unsigned int* __restrict__ raycast, unsigned int* __restrict__ final_rgba,
+                    float* __restrict__ exponents) {
+    constexpr int bw = OVT_TX + 2 * D, bh = TH + 2 * D;
+    __shared__ __align__(128) float4 tile[bw * bh];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int x0 = blockIdx.x * OVT_TX, y0 = blockIdx.y * TH;
+    const uint32_t bar_s = ovt_smem_u32(&bar);
+    if (overlay_mode == 1) {
+        if (tx == 0 && ty == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tx == 0 && ty == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"((uint32_t)(bw * bh * 16)) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(ovt_smem_u32(tile)), "l"(&endpoint_map), "r"(4 * (x0 - D)), "r"(y0 - D), "r"(bar_s) : "memory");
+        }
+    }
+    overlay_tile_thread<TH, D>(tx, ty, x0, y0, W, H, overlay_mode, scaling, raycast, tile, final_rgba, exponents,
+                               [bar_s] { ovt_mbar_wait(bar_s, 0); });
+}
+
+template <int D>
+static void launch_overlay_tile(cudaStream_t stream, const CUtensorMap& map, int W, int H, int overlay_mode, float scaling,
+                                const void* raycast, void* final_rgba, float* exponents, int tile_rows) {
+    dim3 block(OVT_TX, OVT_WARPS), grid((W + OVT_TX - 1) / OVT_TX, (H + tile_rows - 1) / tile_rows);
+    if constexpr (D <= OVT_TALL_MAX_DELTA) {
+        if (tile_rows == OVT_TH_TALL) {
+            overlay_tile_kernel<OVT_TH_TALL, D><<<grid, block, 0, stream>>>(map, W, H, overlay_mode, scaling, (const unsigned int*)raycast,
+                                                                            (unsigned int*)final_rgba, exponents);
+            return;
+        }
+    }
+    overlay_tile_kernel<OVT_TH, D><<<grid, block, 0, stream>>>(map, W, H, overlay_mode, scaling, (const unsigned int*)raycast,
+                                                                   (unsigned int*)final_rgba, exponents);
+}
+
+// Tile height of a frame: 32 x 64 tiles (8 pixels per thread, 27.5 M warp instructions at 3840 x 2160 against 29.9 M, 37.7 us
+// against 40.2 us under ncu) once the grid still fills every SM several times over; 32 x 32 below that (a 1000 x 777 frame:
+// 12.3 us against 13.8 us).  The tensor map's box must be made for the same height (overlay_tile_box).
+int overlay_tile_rows(int W, int H, int delta, int n_sm) {
+    const long long tall_ctas = (long long)((W + OVT_TX - 1) / OVT_TX) * ((H + OVT_TH_TALL - 1) / OVT_TH_TALL);
+    const bool fits = delta <= OVT_TALL_MAX_DELTA;  // the tall tile + halo must fit 48 KB of static shared memory
+    return (fits && tall_ctas >= 12LL * (n_sm > 0 ? n_sm : 148)) ? OVT_TH_TALL : OVT_TH;
+}
+
+void overlay_tile_box(int delta, int tile_rows, unsigned int* box_floats, unsigned int* box_rows) {
+    *box_floats = 4u * (unsigned int)(OVT_TX + 2 * delta);
+    *box_rows = (unsigned int)(tile_rows + 2 * delta);
+}
+
 void launch_overlay(cudaStream_t stream, int W, int H, int overlay_mode, int delta, float scaling, const void* raycast,
-                    const void* endpoint, void* final_rgba, float* exponents, int variant) {
-    if (variant == 1) {
+                    const void* endpoint, void* final_rgba, float* exponents, int variant, const void* endpoint_map,
+                    int tile_rows) {
+    if (variant == 2 && endpoint_map && delta >= 1 && delta <= OVT_MAX_DELTA && (tile_rows == OVT_TH || (tile_rows == OVT_TH_TALL && delta <= OVT_TALL_MAX_DELTA))) {
+        const CUtensorMap& map = *(const CUtensorMap*)endpoint_map;
+        switch (delta) {
+#define LINON_OVT_CASE(D) case D: launch_overlay_tile<D>(stream, map, W, H, overlay_mode, scaling, raycast, final_rgba, exponents, tile_rows); return;
+            LINON_OVT_CASE(1) LINON_OVT_CASE(2) LINON_OVT_CASE(3) LINON_OVT_CASE(4) LINON_OVT_CASE(5)
+            LINON_OVT_CASE(6) LINON_OVT_CASE(7) LINON_OVT_CASE(8) LINON_OVT_CASE(9) LINON_OVT_CASE(10)
+#undef LINON_OVT_CASE
+        }
+    }
+    if (variant >= 1) {
         dim3 block(OVD_TX, OVD_WARPS), grid((W + OVD_TX - 1) / OVD_TX, (H + OVD_TY - 1) / OVD_TY);
         overlay_direct_kernel<<<grid, block, 0, stream>>>(W, H, overlay_mode, delta, scaling, (const unsigned int*)raycast,
                                                           (const float4*)endpoint, (unsigned int*)final_rgba, exponents);

@@ -71,6 +71,10 @@ struct Driver {
     CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
     CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
     CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    // TMA descriptor of the endpoint image for the tile overlay kernel (optional: without it the direct kernel runs)
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     bool has_vmm = false;
     std::string error;
 
@@ -100,6 +104,7 @@ struct Driver {
         MemSetAccess = (decltype(MemSetAccess))sym("cuMemSetAccess");
         MemExportToShareableHandle = (decltype(MemExportToShareableHandle))sym("cuMemExportToShareableHandle");
         MemImportFromShareableHandle = (decltype(MemImportFromShareableHandle))sym("cuMemImportFromShareableHandle");
+        TensorMapEncodeTiled = (decltype(TensorMapEncodeTiled))sym("cuTensorMapEncodeTiled");
         has_vmm = MemGetAllocationGranularity && MemCreate && MemRelease && MemAddressReserve && MemAddressFree && MemMap &&
                   MemUnmap && MemSetAccess && MemExportToShareableHandle && MemImportFromShareableHandle;
         if (!ModuleLoadData || !ModuleUnload || !ModuleGetFunction || !LaunchKernel || !GetErrorString ||
@@ -499,7 +504,13 @@ struct linon_view {
     uint64_t module_clock = 0;  // use counter for the LRU eviction of `modules`
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 0, opt_overlay_kernel = 1;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 0, opt_overlay_kernel = 2;
+    // tile overlay kernel: tensor map over d_endpoint as a (4 W, H) fp32 tensor, box = tile + halo of the current delta
+    alignas(64) CUtensorMap endpoint_map;
+    const void* endpoint_map_ptr = nullptr;
+    uint32_t endpoint_map_w = 0, endpoint_map_h = 0;
+    int endpoint_map_delta = 0, endpoint_map_rows = 0;  // rows: tile height the box was made for (overlay_tile_rows)
+    bool endpoint_map_ok = false;
 
     linon_timings timings{};
     uint64_t last_rays = 0;
@@ -1070,6 +1081,34 @@ int linon_module_overrides(linon_view* v, char* names, size_t names_len) {
     return LINON_OK;
 }
 
+namespace {
+// (Re)encodes the TMA descriptor of the endpoint image when the buffer, the frame size or the delta changed.  Returns the
+// descriptor, or nullptr when the tile kernel cannot run (option off, delta outside the slider's range, driver without
+// cuTensorMapEncodeTiled, encode refused): launch_overlay then runs the direct kernel - same results, same device.
+const void* endpoint_tensor_map(linon_view* v) {
+    const int delta = v->settings.central_difference_delta;
+    if (v->opt_overlay_kernel != 2 || delta < 1 || delta > 10 || !g_drv.TensorMapEncodeTiled || !v->d_endpoint) return nullptr;
+    if (v->endpoint_map_ptr == v->d_endpoint && v->endpoint_map_w == v->W && v->endpoint_map_h == v->H && v->endpoint_map_delta == delta)
+        return v->endpoint_map_ok ? &v->endpoint_map : nullptr;
+    v->endpoint_map_rows = linon::overlay_tile_rows((int)v->W, (int)v->H, delta, v->sm_count);
+    v->endpoint_map_ptr = v->d_endpoint;
+    v->endpoint_map_w = v->W;
+    v->endpoint_map_h = v->H;
+    v->endpoint_map_delta = delta;
+    unsigned int box_floats = 0, box_rows = 0;
+    linon::overlay_tile_box(delta, v->endpoint_map_rows, &box_floats, &box_rows);
+    const cuuint64_t dims[2] = {(cuuint64_t)v->W * 4, (cuuint64_t)v->H};
+    const cuuint64_t strides[1] = {(cuuint64_t)v->W * 16};
+    const cuuint32_t box[2] = {box_floats, box_rows};
+    const cuuint32_t elem_strides[2] = {1, 1};
+    const CUresult r = g_drv.TensorMapEncodeTiled(&v->endpoint_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)v->d_endpoint, dims, strides, box,
+                                                  elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    v->endpoint_map_ok = r == CUDA_SUCCESS;
+    return v->endpoint_map_ok ? &v->endpoint_map : nullptr;
+}
+}  // namespace
+
 int linon_render(linon_view* v, uint32_t flags) {
     if (!v) return LINON_ERR_INVALID;
     const bool do_march = !(flags & LINON_RENDER_NO_MARCH);
@@ -1187,10 +1226,13 @@ int linon_render(linon_view* v, uint32_t flags) {
     }
 
     if (do_overlay) {
+        // mode 0 copies the colours and needs no tile either way; the tile kernel handles it without its TMA load
+        const void* ep_map = endpoint_tensor_map(v);
         CK(v, cudaEventRecord(v->ev[2], v->stream));
         linon::launch_overlay(v->stream, (int)v->W, (int)v->H, v->settings.overlay_mode, v->settings.central_difference_delta,
                               v->settings.lyapunov_scaling, v->d_raycast, v->d_endpoint, v->d_final, v->d_exponents,
-                              v->opt_overlay_kernel);
+                              v->opt_overlay_kernel, ep_map, v->endpoint_map_rows);
+        v->timings.overlay_kernel = (v->opt_overlay_kernel == 2 && !ep_map) ? 1 : v->opt_overlay_kernel;
         CK(v, cudaGetLastError());
         CK(v, cudaEventRecord(v->ev[3], v->stream));
         v->ran_overlay = true;
@@ -1441,7 +1483,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_PROFILE: if (value < 0 || value > 1) break; v->opt_profile = value; return LINON_OK;
         case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
         case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 2) break; v->opt_quiet = value; return LINON_OK;
-        case LINON_OPT_OVERLAY_KERNEL: if (value < 0 || value > 1) break; v->opt_overlay_kernel = value; return LINON_OK;
+        case LINON_OPT_OVERLAY_KERNEL: if (value < 0 || value > 2) break; v->opt_overlay_kernel = value; return LINON_OK;
         case LINON_OPT_QUIET_RADIUS: if (value != 0 && (value < 1250 || value > 4000)) break; v->opt_quiet_radius = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));

@@ -54,6 +54,7 @@ pub struct linon_timings {
     pub march_block: i32,
     pub march_phase_a_ms: f32,
     pub march_kernel: i32,
+    pub overlay_kernel: i32,
 }
 
 const _: () = assert!(std::mem::size_of::<linon_camera>() == 112);

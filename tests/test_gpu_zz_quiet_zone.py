@@ -3,9 +3,9 @@
 The option was written in round 1 without GPU time (validated on the host emulation of the exact NVRTC source,
 tests/test_emulation_cpu.py), first ran on hardware in the driver's round-1 GPU tests (all green) and is the shipped path
 since round 2: level 2 (fixed-step and adaptive frames) is the library default.  The same
-holds for the two other paths tested at the end of the file: peer stores (linon_redirect_output) and the direct overlay
-kernel (LINON_OPT_OVERLAY_KERNEL = 1, default since round 2; validated bit for bit against the oracle on the host in
-tests/test_overlay_emulation_cpu.py).  Full-size grading against the oracle: tests/test_gpu_fullsize.py and bench.py's
+holds for the two other paths tested at the end of the file: peer stores (linon_redirect_output) and the overlay kernels
+(LINON_OPT_OVERLAY_KERNEL: the TMA tile kernel is the default, the direct kernel its fallback; all validated bit for bit
+against the oracle on the host in tests/test_overlay_emulation_cpu.py).  Full-size grading against the oracle: tests/test_gpu_fullsize.py and bench.py's
 `parity` block.
 """
 import numpy as np
@@ -147,31 +147,39 @@ def test_peer_stores_assemble_the_frame_in_the_root_views_buffers(product_lib, s
             mv.close()
 
 
-@pytest.mark.parametrize("delta", [1, 2, 5, 10])
-@pytest.mark.parametrize("size", [(200, 150), (1920, 1080)])
-def test_direct_overlay_kernel_equals_the_staged_one_bit_for_bit(product_lib, oracle, scene, delta, size):
-    """LINON_OPT_OVERLAY_KERNEL = 1 (csrc/device/overlay_direct.cuh; opt-in, validated on the host against the oracle in
-    tests/test_overlay_emulation_cpu.py): same final image and same exponents as the measured default on the same frame,
-    and within the oracle's tolerance like test_gpu_units.test_overlay_matches_the_oracle."""
+@pytest.mark.parametrize("delta", [1, 2, 3, 4, 5, 7, 10])
+@pytest.mark.parametrize("size", [(200, 150), (97, 61), (1920, 1080), (3840, 2160)])
+def test_the_three_overlay_kernels_agree_bit_for_bit(product_lib, oracle, scene, delta, size):
+    """LINON_OPT_OVERLAY_KERNEL: 2 = the TMA tile kernel (default, csrc/device/overlay_tile.cuh), 1 = the direct kernel
+    (overlay_direct.cuh), 0 = the round-1 hand-staged kernel.  All three bodies are validated bit for bit against the oracle on
+    the host (tests/test_overlay_emulation_cpu.py); here the device runs them on the same frame - ragged sizes, tiles cut by
+    the frame's edge and by the 2 delta border, every tile-kernel instantiation the test names - and the results must be the
+    same words, within the oracle's tolerance like test_gpu_units.test_overlay_matches_the_oracle."""
     verts, faces, center = scene
     W, H = size
+    if (W, H) == (3840, 2160) and delta not in (1, 4, 5):
+        pytest.skip("the C3 frame size exercises the 32 x 64 tiles (delta <= 4) and the switch back to 32 x 32 (delta 5)")
     with MainView(verts, faces, center, W, H) as mv:
         mv.reload_shader(PredefinedFunction.MirageSphericalSigmoid.to_code())
-        st = make_settings(overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0)
+        st = make_settings(overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0 if W < 3000 else 100.0)
         mv.update_settings(st)
         mv.disable_adaptive_sampling()
         mv.set_option(capi.OPT_OVERLAY_KERNEL, 0)
         mv.render()
         mv.sync()
+        assert mv.timings().overlay_kernel == 0
         staged_final, staged_ex = mv.texture().copy(), mv.exponents().copy()
         raycast, ep = mv.ray_casting_texture(), mv.mapping_texture()
-        mv.set_option(capi.OPT_OVERLAY_KERNEL, 1)
-        mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
-        mv.sync()
-        final, ex = mv.texture(), mv.exponents()
-        assert np.array_equal(final, staged_final)
-        assert np.array_equal(ex.view(np.uint32), staged_ex.view(np.uint32))
-        assert (ex >= 0.8).any()
+        for kernel in (1, 2):
+            mv.set_option(capi.OPT_OVERLAY_KERNEL, kernel)
+            mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+            mv.sync()
+            assert mv.timings().overlay_kernel == kernel  # the tile kernel really ran (a driver without TMA descriptors reports 1)
+            final, ex = mv.texture(), mv.exponents()
+            assert np.array_equal(final, staged_final)
+            assert np.array_equal(ex.view(np.uint32), staged_ex.view(np.uint32))
+        if ((W, H) != (97, 61) or delta <= 5) and W < 3000:
+            assert (ex >= 0.8).any()
         if W * H <= 200 * 150:
             ref_final, ref_ex = oracle.overlay(raycast, ep, dict(field_weight=1.0, mouse_x=0.5, mouse_y=0.6, overlay_mode=1,
                                                                  central_difference_delta=delta, lyapunov_scaling=50.0))
@@ -179,9 +187,33 @@ def test_direct_overlay_kernel_equals_the_staged_one_bit_for_bit(product_lib, or
             assert np.abs(final.astype(int) - ref_final.astype(int)).max() <= 1
         # mode 0: exact copy, exponents untouched (src/overlay.wgsl:116-118)
         mv.update_settings(make_settings(overlay_mode=0, central_difference_delta=delta))
-        mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
-        mv.sync()
-        assert np.array_equal(mv.texture(), raycast) and np.array_equal(mv.exponents(), ex)
+        for kernel in (1, 2):
+            mv.set_option(capi.OPT_OVERLAY_KERNEL, kernel)
+            mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+            mv.sync()
+            assert np.array_equal(mv.texture(), raycast) and np.array_equal(mv.exponents(), ex)
+
+
+def test_the_tile_overlay_follows_a_resize_and_a_new_delta(product_lib, scene):
+    """The tensor map of the tile kernel describes one endpoint buffer, one frame size and one delta: after resize_texture and
+    after a change of central_difference_delta the kernel must read the new image with the new halo."""
+    verts, faces, center = scene
+    with MainView(verts, faces, center, 160, 120) as mv:
+        mv.reload_shader(PredefinedFunction.MirageSphericalSigmoid.to_code())
+        mv.disable_adaptive_sampling()
+        for (W, H), delta in (((160, 120), 1), ((160, 120), 4), ((224, 96), 4), ((224, 96), 2), ((64, 64), 2)):
+            if mv.size != (W, H):
+                mv.resize_texture(W, H)
+            mv.update_settings(make_settings(overlay_mode=1, central_difference_delta=delta, lyapunov_scaling=50.0))
+            mv.set_option(capi.OPT_OVERLAY_KERNEL, 2)
+            mv.render()
+            mv.sync()
+            assert mv.timings().overlay_kernel == 2
+            final, ex = mv.texture().copy(), mv.exponents().copy()
+            mv.set_option(capi.OPT_OVERLAY_KERNEL, 1)
+            mv.render_flags(capi.RENDER_NO_MARCH | capi.RENDER_NO_SAMPLE_RAYS)
+            mv.sync()
+            assert np.array_equal(mv.texture(), final) and np.array_equal(mv.exponents().view(np.uint32), ex.view(np.uint32))
 
 
 @pytest.mark.parametrize("fn", MIRAGES)

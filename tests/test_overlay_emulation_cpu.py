@@ -33,6 +33,11 @@ def _build(kind):
     if kind == "direct":
         driver, extra = os.path.join(_EMU, "overlay_driver.cpp"), open(os.path.join(_DEVICE, "overlay_direct.cuh"), "rb").read()
         flags = ["-fopenmp", "-I", _DEVICE]
+    elif kind in ("tile", "tile_tall"):
+        kind = "tile"
+        driver = os.path.join(_EMU, "overlay_tile_driver.cpp")
+        extra = open(os.path.join(_DEVICE, "overlay_direct.cuh"), "rb").read() + open(os.path.join(_DEVICE, "overlay_tile.cuh"), "rb").read()
+        flags = ["-fopenmp", "-I", _DEVICE]
     else:
         driver, extra = os.path.join(_EMU, "overlay_staged_driver.cpp"), _staged_kernel_text().encode()
         flags = []
@@ -51,12 +56,20 @@ def _build(kind):
     return C.CDLL(so)
 
 
-@pytest.fixture(scope="module", params=["direct", "staged"])
+@pytest.fixture(scope="module", params=["tile", "tile_tall", "direct", "staged"])
 def emu_overlay(request):
-    """direct: overlay_direct_kernel's per-thread body (opt-in variant).  staged: the measured default overlay_kernel, its text
+    """tile: overlay_tile_kernel's per-thread body (the default) on tiles filled the way its TMA load fills them
+    (tests/emu/overlay_tile_driver.cpp).  direct: overlay_direct_kernel's per-thread body.  staged: the measured default overlay_kernel, its text
     cut out of static_kernels.cu and run CTA by CTA in two passes around its single barrier (tests/emu/overlay_staged_driver.cpp)."""
     lib = _build(request.param)
-    entry = lib.emu_overlay_direct if request.param == "direct" else lib.emu_overlay_staged
+    tall = request.param == "tile_tall"
+    if request.param.startswith("tile"):
+        def entry(W, H, mode, delta, *rest):
+            # 32 x 64 tiles exist for delta <= 4 (static shared memory); the launcher uses 32 x 32 tiles beyond that
+            rc = lib.emu_overlay_tile(W, H, mode, delta, *rest, 1 if (tall and delta <= 4) else 0)
+            assert rc == 0
+    else:
+        entry = lib.emu_overlay_direct if request.param == "direct" else lib.emu_overlay_staged
 
     def run(raycast, endpoint, mode, delta, scaling, exponents=None):
         H, W = raycast.shape[:2]

@@ -35,14 +35,17 @@ def lines_of_cubin(cubin, kernel):
     start = next(i for i, l in enumerate(dis) if l.strip() == f".text.{kernel}:")
     res, cur = [], ("?", 0, "?", 0)
     file_re = re.compile(r'//## File "([^"]+)", line (\d+)')
+    chain_open = False  # an inlined instruction is annotated by consecutive lines, innermost frame first, outermost last
     for l in dis[start + 1:]:
         if l.startswith("//---------------------") or l.lstrip().startswith(".section"):
             break
         if "//## File" in l:
-            m = file_re.findall(l)
-            inner, outer = m[0], m[-1]
-            cur = (inner[0].split("/")[-1], int(inner[1]), outer[0].split("/")[-1], int(outer[1]))
+            f, n = file_re.findall(l)[0]
+            loc = (f.split("/")[-1], int(n))
+            cur = (cur[0], cur[1], loc[0], loc[1]) if chain_open else (loc[0], loc[1], loc[0], loc[1])
+            chain_open = True
             continue
+        chain_open = False
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
         if m:
             res.append((m.group(2).strip(), cur))

@@ -205,6 +205,106 @@ __global__ void __launch_bounds__(256, MINB) v_tma1(const __grid_constant__ CUte
     }
 }
 
+
+// the same arithmetic with ONE square root for both signs of the discriminant: sqrt(|discrim|) is sqrt(discrim) for
+// discrim >= 0 and sqrt(-discrim) otherwise, bit for bit (discrim = -0.0: sqrt gives -0.0 against +0.0 here, and the two sums
+// it enters, -a1 - root and -a1 + root with -a1 >= +0, are +0 or -a1 either way)
+__device__ __forceinline__ void ov_pixel1(const float4 xp, const float4 xm, const float4 yp, const float4 ym, float scaling,
+                                          unsigned int& c, float& scaled) {
+    const float gxx = 0.5f * (xp.x - xm.x);
+    const float gxy = 0.5f * (xp.y - xm.y);
+    const float gxz = 0.5f * (xp.z - xm.z);
+    const float gyx = 0.5f * (yp.x - ym.x);
+    const float gyy = 0.5f * (yp.y - ym.y);
+    const float gyz = 0.5f * (yp.z - ym.z);
+    const float m00 = gxx * gxx + gxy * gxy + gxz * gxz;
+    const float m01 = gxx * gyx + gxy * gyy + gxz * gyz;
+    const float m11 = gyx * gyx + gyy * gyy + gyz * gyz;
+    const float a0 = m00 * m11 - m01 * m01;
+    const float a1 = -(m00 + m11);
+    const float discrim = a1 * a1 - 4.0f * a0;
+    const float root = sqrtf(fabsf(discrim));
+    const bool real = discrim >= 0.0f;
+    const float e0 = (real ? (-a1 - root) : -a1) / 2.0f;
+    const float e1 = (real ? (-a1 + root) : root) / 2.0f;
+    const float exponent = sqrtf(fmaxf(e0, e1));
+    scaled = expf(scaling * exponent - 5.0f);
+    if (scaled >= 0.8f) {
+        const float alpha = fminf(1.0f, scaled) * 0.5f;
+        const float inv = 1.0f - alpha;
+        const unsigned int cx = c & 0xffu, cy = (c >> 8) & 0xffu, cz = (c >> 16) & 0xffu, cw = c >> 24;
+        c = ovd_unorm8(alpha * 1.0f + inv * ((float)cx / 255.0f)) | (ovd_unorm8(alpha * 1.0f + inv * ((float)cy / 255.0f)) << 8) |
+            (ovd_unorm8(alpha * 1.0f + inv * ((float)cz / 255.0f)) << 16) | (ovd_unorm8(alpha * 1.0f + inv * ((float)cw / 255.0f)) << 24);
+    }
+}
+
+// T3: T1 with (i) tiles that touch neither the frame's edge nor its 2 delta border take a loop without any bounds test (the
+// flag is uniform per CTA), (ii) ov_pixel1.  DT = compile-time delta only.
+template <int TH, int MINB, int DT>
+__global__ void __launch_bounds__(256, MINB) v_tma3(const __grid_constant__ CUtensorMap tm, int W, int H, int mode, int delta,
+                                                    float scaling, const unsigned int* __restrict__ rc,
+                                                    unsigned int* __restrict__ fin, float* __restrict__ ex) {
+    constexpr int ROWS = TH / 8;
+    constexpr int d = DT, bw = 32 + 2 * DT, padding = 2 * DT;
+    __shared__ __align__(128) float4 tile[bw * (TH + 2 * DT)];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * TH;
+    const bool stencil = mode == 1;
+    const uint32_t bar_s = smem_u32(&bar);
+    if (stencil) {
+        if (tid == 0) {
+            mbar_init(bar_s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar_s, (uint32_t)(bw * (TH + 2 * d) * 16));
+            tma_load_2d(smem_u32(tile), &tm, 4 * (x0 - d), y0 - d, bar_s);
+        }
+    }
+    const int x = x0 + tx;
+    const float4* t0 = tile + (ty + d) * bw + (tx + d);
+    const bool interior = stencil && x0 >= padding && x0 + 32 <= W - padding && y0 >= padding && y0 + TH <= H - padding;
+    if (interior) {
+        const int idx0 = (y0 + ty) * W + x;
+        unsigned int c[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) c[r] = rc[idx0 + 8 * r * W];
+        mbar_wait(bar_s, 0);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const float4* t = t0 + 8 * r * bw;
+            float scaled;
+            ov_pixel1(t[d], t[-d], t[d * bw], t[-d * bw], scaling, c[r], scaled);
+            ex[idx0 + 8 * r * W] = scaled;
+            fin[idx0 + 8 * r * W] = c[r];
+        }
+        return;
+    }
+    const bool inner_x = x >= padding && x < W - padding;
+    unsigned int c[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int y = y0 + ty + 8 * r;
+        c[r] = (x < W && y < H) ? rc[y * W + x] : 0u;
+    }
+    if (stencil) mbar_wait(bar_s, 0);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int y = y0 + ty + 8 * r;
+        if (x >= W || y >= H) continue;
+        const int idx = y * W + x;
+        if (stencil && inner_x && y >= padding && y < H - padding) {
+            const float4* t = t0 + 8 * r * bw;
+            float scaled;
+            ov_pixel1(t[d], t[-d], t[d * bw], t[-d * bw], scaling, c[r], scaled);
+            ex[idx] = scaled;
+        }
+        fin[idx] = c[r];
+    }
+}
+
 // T2: persistent CTAs, S-stage ring of tiles: the TMA of tile k+S is issued as soon as every thread has finished reading
 // the buffer of tile k; tiles are handed out in row-major order so CTAs that run together share their halos in L2.
 template <int TH, int MINB, int S, int DT>
@@ -213,7 +313,7 @@ __global__ void __launch_bounds__(256, MINB) v_tma2(const __grid_constant__ CUte
                                                     unsigned int* __restrict__ fin, float* __restrict__ ex) {
     constexpr int ROWS = TH / 8;
     constexpr int DMAX = DT ? DT : 10;
-    constexpr int TILE = (32 + 2 * DMAX) * (TH + 2 * DMAX);
+    constexpr int TILE = ((32 + 2 * DMAX) * (TH + 2 * DMAX) + 7) / 8 * 8;  // every stage 128-byte aligned (TMA destination)
     __shared__ __align__(128) float4 tile[S][TILE];
     __shared__ __align__(8) unsigned long long bar[S];
     const int d = DT ? DT : delta;
@@ -318,6 +418,12 @@ static int g_sms = 148;
         make_map(ep, W, H, d, TH);                                                                                                \
         v_tma1<TH, MINB, DT><<<dim3((W + 31) / 32, (H + TH - 1) / TH), dim3(32, 8)>>>(g_tm, W, H, m, d, s, rc, fin, ex);           \
     }
+#define TMA3(TH, MINB, DT)                                                                                                        \
+    [](int W, int H, int m, int d, float s, const unsigned int* rc, const float4* ep, unsigned int* fin, float* ex) {             \
+        if (d != DT) return;                                                                                                      \
+        make_map(ep, W, H, d, TH);                                                                                                \
+        v_tma3<TH, MINB, DT><<<dim3((W + 31) / 32, (H + TH - 1) / TH), dim3(32, 8)>>>(g_tm, W, H, m, d, s, rc, fin, ex);           \
+    }
 #define TMA2(TH, MINB, S, DT)                                                                                                     \
     [](int W, int H, int m, int d, float s, const unsigned int* rc, const float4* ep, unsigned int* fin, float* ex) {             \
         if (DT && d != DT) return;                                                                                                \
@@ -390,7 +496,15 @@ int main(int argc, char** argv) {
         {"tma1 32x16 tile/CTA, min 8 CTAs, delta=1 fixed", TMA1(16, 8, 1)},
         {"tma1 32x32 tile/CTA, min 6 CTAs, delta=1 fixed", TMA1(32, 6, 1)},
         {"tma1 32x32 tile/CTA, min 4 CTAs, delta=1 fixed", TMA1(32, 4, 1)},
+        {"tma1 32x32 tile/CTA, min 8 CTAs, delta=1 fixed", TMA1(32, 8, 1)},
+        {"tma1 32x64 tile/CTA, min 3 CTAs, delta=1 fixed", TMA1(64, 3, 1)},
+        {"tma1 32x64 tile/CTA, min 4 CTAs, delta=1 fixed", TMA1(64, 4, 1)},
         {"tma1 32x16 tile/CTA, min 6 CTAs, run-time delta", TMA1(16, 6, 0)},
+        {"tma3 32x32 interior fast path + one sqrt, min 6, delta=1", TMA3(32, 6, 1)},
+        {"tma3 32x32 interior fast path + one sqrt, min 4, delta=1", TMA3(32, 4, 1)},
+        {"tma3 32x64 interior fast path + one sqrt, min 3, delta=1", TMA3(64, 3, 1)},
+        {"tma3 32x16 interior fast path + one sqrt, min 8, delta=1", TMA3(16, 8, 1)},
+        {"tma3 32x32 interior fast path + one sqrt, min 4, delta=5", TMA3(32, 4, 5)},
         {"tma2 persistent 32x16, 8 CTAs/SM, 2 stages, delta=1", TMA2(16, 8, 2, 1)},
         {"tma2 persistent 32x16, 6 CTAs/SM, 3 stages, delta=1", TMA2(16, 6, 3, 1)},
         {"tma2 persistent 32x32, 4 CTAs/SM, 2 stages, delta=1", TMA2(32, 4, 2, 1)},
