@@ -48,6 +48,7 @@ BASE_W, BASE_H = 3840, 2160
 C5_W, C5_H = 8192, 8192
 ROWS_PER_BLOCK = 32
 DEFAULT_QUIET = 2     # the library's default level of LINON_OPT_QUIET_ZONE (include/linon_b200.h)
+DEFAULT_QUIET_RADIUS = 1500  # ... and of LINON_OPT_QUIET_RADIUS
 STEPS_PER_RAY = 5001  # h_initial = 0.001: the loop of src/main_view.wgsl:244 runs 5001 times; adaptive sampling cannot trigger
 MARCH_PROFILE = os.path.join(ROOT, "profiles", "r2_march_c3.json")
 OVERLAY_PROFILE = os.path.join(ROOT, "profiles", "r2_overlay_c3.json")
@@ -349,9 +350,10 @@ def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
     E = capi.RENDER_ENHANCE
     shipped_quiet, shipped_spec = DEFAULT_QUIET, 1
 
-    def one(name, quiet, spec, frames):
+    def one(name, quiet, spec, frames, radius=DEFAULT_QUIET_RADIUS):
         mv.set_option(capi.OPT_QUIET_ZONE, quiet)
         mv.set_option(capi.OPT_SPECIALIZE, spec)
+        mv.set_option(capi.OPT_QUIET_RADIUS, radius)
         t = timed_frames(mv, E, frames, warm=1, flush=flush)
         c = mv.counters()
         assert int(c.accepted_steps) == W * H * STEPS_PER_RAY and int(c.rejected_steps) == 0, (name, c.accepted_steps)
@@ -363,6 +365,11 @@ def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
     try:
         t, m = one("shipped", shipped_quiet, shipped_spec, 2)
         out["shipped"] = m
+        t, m = one("quiet_radius_saturation", shipped_quiet, shipped_spec, 2, radius=0)
+        variants["quiet_radius_saturation"] = dict(t, note="LINON_OPT_QUIET_RADIUS = 0: the sigmoid zone ends where the reference's fp32 sigmoid "
+                                                           "saturates (1.92 max_dist) and its own evaluation IS the identity, instead of the shipped "
+                                                           "1.5 max_dist, beyond which the real-number signal is 50x below the fp32 quantum")
+        out["quiet_radius_saturation"] = m
         t, m = one("quiet_zone_off", 0, 1, 2)
         variants["quiet_zone_off"] = dict(t, note="LINON_OPT_QUIET_ZONE = 0: every step evaluates the field (the round-1 headline kernel)")
         out["quiet_zone_off"] = m
@@ -373,6 +380,7 @@ def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
     finally:
         mv.set_option(capi.OPT_QUIET_ZONE, shipped_quiet)
         mv.set_option(capi.OPT_SPECIALIZE, shipped_spec)
+        mv.set_option(capi.OPT_QUIET_RADIUS, DEFAULT_QUIET_RADIUS)
     out["green"] = bool(out.get("shipped", {}).get("green")) and pinned is not False
     return out, variants
 

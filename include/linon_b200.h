@@ -121,10 +121,14 @@ enum {
                                     frames 7.4 -> 1.3 ms MirageSpherical, 9.1 -> 5.2 ms MirageSphericalSigmoid at level 2) and
                                     graded against the oracle at full size (tests/test_gpu_fullsize.py, bench.py `parity` and
                                     `configs`).  0: every step evaluates the field (the round-1 kernel) */
-    LINON_OPT_QUIET_RADIUS = 13, /* radius of the quiet zone of the SIGMOID mirage profiles in permille of their max_dist; 0 (default)
-                                    = 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6).  1250 ... 4000: below
-                                    1886 the reference's eta is 1 +- its rounding noise and the real-number deflection summed over
-                                    the excluded shell is <= 1.85e-4 exp(6 - 12 r): 1e-9 rad at 1500 (mirage_fused.cuh) */
+    LINON_OPT_QUIET_RADIUS = 13, /* radius of the quiet zone of the SIGMOID mirage profiles in permille of their max_dist.
+                                    1500 (default since round 2): between 1.5 and 1.8866 max_dist the reference's fp32 eta is 1 +- its
+                                    own rounding noise - the real-number signal there is |eta - 1| <= 1e-9, 50x below the fp32
+                                    quantum - and the deflection summed over the excluded shell is <= 1.85e-4 exp(6 - 12 r) =
+                                    1e-9 rad (mirage_fused.cuh); graded against the oracle at full size in every bench line
+                                    (C3: 12.9 -> 10.4 ms, same hit / colour / endpoint agreement as the saturation radius).
+                                    0: 1920, where the reference's own fp32 sigmoid saturates (>= 1886.6) and its evaluation IS the
+                                    identity.  1250 ... 4000 otherwise */
     LINON_OPT_OVERLAY_KERNEL = 14, /* overlay stencil (src/overlay.wgsl:99-146), bit-identical results in every variant.
                                     0: 32x16 tile + halo of the endpoints staged in shared memory by the threads (round 1).
                                     1: every pixel fetches its four taps through the read-only path, no shared memory, no
@@ -303,9 +307,11 @@ const char* linon_sharded_last_error(const linon_sharded* s);
 int linon_set_option(linon_view* v, int option, int value);
 int linon_get_counters(linon_view* v, linon_counters* out);
 int linon_get_timings(linon_view* v, linon_timings* out);
-/* FNV-1a (64 bit) over the machine code (.text.* sections) of the cubin whose march kernel ran last (0 before the first march;
- * line tables are left out, so an edit that only moves lines keeps the identity).  A committed ncu capture names the hash of
- * the kernel it profiled; bench.py refuses its counters when the running kernel is a different binary. */
+/* FNV-1a (64 bit) over the machine code of the march kernel that ran last (0 before the first march): the section
+ * .text.linon_march_tiles of the cubin for the default tile kernel - other kernels of the module, e.g. the sample rays, may change
+ * without changing it -, every .text section for the opt-in march kernels.  Line tables are left out, so an edit that only
+ * moves lines keeps the identity.  A committed ncu capture names the hash of the kernel it profiled; bench.py refuses its counters
+ * when the running kernel is a different binary. */
 int linon_march_cubin_hash(linon_view* v, uint64_t* out);
 /* The NVRTC that compiles the field functions (the reference's counterpart: naga + the driver's compiler behind
  * create_shader_module, src/main_view.rs:96-102, 662-665).  The library opens the toolkit's libnvrtc privately by the absolute

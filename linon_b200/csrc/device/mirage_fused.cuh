@@ -319,7 +319,8 @@ template <class S> struct LinonField {
     // max_dist the reference's eta is 1 +- its own rounding noise, the real-number signal being far below fp32 resolution -
     // per step |eta - 1| ~ 9e-6 E (h / 0.001) with E = exp(6 - 12 dist / max_dist) <= 1.2e-4, and the deflection summed over the
     // whole shell is (n(t_src) - n(t_env)) E(radius) <= 1.85e-4 E: 2e-8 rad at 1.25, 1e-9 rad (0.02 ulp of a direction
-    // component) at 1.5.  The default stays at the radius where the reference's own arithmetic saturates.
+    // component) at 1.5.  The kernel template's default is the radius where the reference's own arithmetic saturates; the
+    // library passes 1.5 unless told otherwise (include/linon_b200.h: LINON_OPT_QUIET_RADIUS).
     // With other sigmoid constants the saturation point moves: K dist / max_dist - C >= 16.64, same 1.77 % margin.
 #ifndef LINON_QUIET_RADIUS_SIGMOID
 #define LINON_QUIET_RADIUS_SIGMOID ((LINON_MIRAGE_SIG_K == 12.0f && LINON_MIRAGE_SIG_C == 6.0f) ? 1.92f : 1.0177f * (16.64f + LINON_MIRAGE_SIG_C) / LINON_MIRAGE_SIG_K)

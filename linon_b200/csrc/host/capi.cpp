@@ -228,7 +228,8 @@ struct Variant {
     int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
     int pair_min_blocks;  // resident CTAs / SM requested for it (0 = kernel default)
     int quiet;            // 1: fixed-step loops take straight steps where a fused mirage body is the identity (LINON_QUIET_ZONE)
-    int quiet_radius;     // sigmoid profiles: zone radius in permille of max_dist (0 = the default of mirage_fused.cuh)
+    int quiet_radius;     // sigmoid profiles: zone radius in permille of max_dist (0 = where the fp32 sigmoid saturates, 1.92:
+                          // the default of mirage_fused.cuh; the library's default is 1500, LINON_OPT_QUIET_RADIUS)
 };
 
 struct Module {
@@ -237,7 +238,8 @@ struct Module {
                eval_field = nullptr, eval_helper = nullptr, eval_hit = nullptr, eval_rk4 = nullptr;
     int regs_tiles = 0, regs_pairs = 0, regs_refill = 0, regs_phase_a = 0, regs_phase_b = 0;
     uint64_t last_use = 0;  // linon_view::module_clock at the last get_module
-    uint64_t cubin_hash = 0;  // FNV-1a of the cubin: ties a committed ncu capture to the kernel that is running
+    uint64_t cubin_hash = 0;  // FNV-1a of the cubin's code: ties a committed ncu capture to the kernel that is running
+    uint64_t tiles_hash = 0;  // ... of the tile march kernel alone (what linon_march_cubin_hash reports when that kernel ran)
 };
 
 // The translated body becomes LinonField<S>::eval.  The member typedefs re-declare the type names the translator
@@ -303,7 +305,9 @@ uint64_t fnv1a64(const char* p, size_t n, uint64_t h = 1469598103934665603ull) {
 // Identity of a module's MACHINE CODE: FNV-1a over the names and contents of the .text.* sections of the cubin (an ELF64
 // image), in section order.  The -lineinfo tables are left out on purpose: an edit that only moves lines in a source file
 // changes them, not the kernel - and a committed ncu capture is evidence about the kernel.
-uint64_t cubin_code_hash(const std::vector<char>& cubin) {
+// only_kernel: hash the code of that one kernel (section ".text.<name>"), so that a capture of the tile kernel stays valid when
+// another kernel of the module (sample rays, the opt-in march kernels) changes; nullptr: every .text section.
+uint64_t cubin_code_hash(const std::vector<char>& cubin, const char* only_kernel = nullptr) {
     const size_t n = cubin.size();
     const unsigned char* b = (const unsigned char*)cubin.data();
     auto rd = [&](size_t off, int bytes) -> uint64_t {
@@ -325,6 +329,7 @@ uint64_t cubin_code_hash(const std::vector<char>& cubin) {
         const char* nm = cubin.data() + str_off + name;
         const size_t nlen = strnlen(nm, n - (str_off + name));
         if (nlen < 5 || memcmp(nm, ".text", 5) != 0 || off + size > n) continue;
+        if (only_kernel && (nlen != 6 + strlen(only_kernel) || memcmp(nm + 6, only_kernel, nlen - 6) != 0)) continue;
         h = fnv1a64(nm, nlen, h);
         h = fnv1a64(cubin.data() + off, size, h);
     }
@@ -504,7 +509,7 @@ struct linon_view {
     uint64_t module_clock = 0;  // use counter for the LRU eviction of `modules`
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 0, opt_overlay_kernel = 2;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 1500, opt_overlay_kernel = 2;
     // tile overlay kernel: tensor map over d_endpoint as a (4 W, H) fp32 tensor, box = tile + halo of the current delta
     alignas(64) CUtensorMap endpoint_map;
     const void* endpoint_map_ptr = nullptr;
@@ -644,6 +649,7 @@ int get_module(linon_view* v, const std::string& body, const Variant& var, Modul
     if (!compile_cubin(body, var, v->layer, cubin, log)) return v->fail(LINON_ERR_COMPILE, log);
     Module m;
     m.cubin_hash = cubin_code_hash(cubin);
+    m.tiles_hash = cubin_code_hash(cubin, "linon_march_tiles");
     CUresult r = g_drv.ModuleLoadData(&m.mod, cubin.data());
     if (r != CUDA_SUCCESS) return v->fail(LINON_ERR_CUDA, "cuModuleLoadData: " + g_drv.err_str(r));
     struct { const char* name; CUfunction* f; } fns[] = {
@@ -1221,7 +1227,7 @@ int linon_render(linon_view* v, uint32_t flags) {
         }
         CK(v, cudaEventRecord(v->ev[1], v->stream));
         v->ran_march = true;
-        v->last_cubin_hash = mod->cubin_hash;
+        v->last_cubin_hash = v->timings.march_kernel == 0 ? mod->tiles_hash : mod->cubin_hash;
         v->last_rays = (uint64_t)v->local_rows * v->W;
     }
 
@@ -1602,7 +1608,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (cubin_bytes) *cubin_bytes = cubin.size();
     if (const char* hf = getenv("LINON_DUMP_CUBIN_HASH")) {  // developer aid: the hash linon_march_cubin_hash reports for this variant
         if (FILE* f = fopen(hf, "w")) {
-            fprintf(f, "%016llx\n", (unsigned long long)cubin_code_hash(cubin));
+            fprintf(f, "%016llx\n", (unsigned long long)cubin_code_hash(cubin, "linon_march_tiles"));
             fclose(f);
         }
     }
