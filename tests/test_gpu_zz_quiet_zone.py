@@ -53,9 +53,17 @@ def test_quiet_zone_culling_never_changes_a_result(view, fn, flags):
     a = render(view, fn, flags=flags, cull=1)
     checks_on = view.counters().culling_checks
     q_on = quiet_steps(view)
+    hash_on = view.march_cubin_hash()
     b = render(view, fn, flags=flags, cull=0)
     for k in a:
-        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+        same = np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8))
+        if not same:  # say what differs: which binaries ran, how many pixels, by how much
+            px = (a[k].reshape(a[k].shape[0], a[k].shape[1], -1) != b[k].reshape(b[k].shape[0], b[k].shape[1], -1)).any(axis=-1)
+            ys, xs = np.nonzero(px)
+            detail = dict(buffer=k, cubin_cull1=hash_on, cubin_cull0=view.march_cubin_hash(), pixels=int(px.sum()),
+                          first=[(int(y), int(x), a[k][y, x].tolist(), b[k][y, x].tolist()) for y, x in list(zip(ys, xs))[:4]],
+                          quiet_steps=(q_on, quiet_steps(view)))
+            assert same, detail
     assert q_on == quiet_steps(view) > 0
     assert checks_on < view.counters().culling_checks
 
