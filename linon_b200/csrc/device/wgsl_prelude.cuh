@@ -165,7 +165,15 @@ LINON_HD float s_abs(float x) { return fabsf(x); }
 LINON_HD float s_min(float a, float b) { return fminf(a, b); }
 LINON_HD float s_max(float a, float b) { return fmaxf(a, b); }
 LINON_HD float s_sqrt(float x) { return sqrtf(x); }
+// Fast mode names the reciprocal square root itself (MUFU.RSQ).  --use_fast_math folds 1 / sqrtf(x) and a / sqrtf(x) into it
+// only as long as no earlier compilation of the same process asked for --prec-sqrt=true: NVRTC 12.9 keeps that switch, and a
+// production kernel compiled after a strict or fused one came out with MUFU.SQRT + MUFU.RCP instead (12 more special-function
+// evaluations per module, different last bits; found in round 2 - tests/test_capi_cpu.py pins the order independence).
+#if LINON_FAST_MATH && LINON_DEVICE_BUILD
+LINON_HD float s_inverseSqrt(float x) { return rsqrtf(x); }
+#else
 LINON_HD float s_inverseSqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
 LINON_HD float s_exp(float x) { return expf(x); }
 LINON_HD float s_exp2(float x) { return exp2f(x); }
 LINON_HD float s_log(float x) { return logf(x); }
@@ -437,9 +445,16 @@ template <class A> LINON_HD A w_length(vec4t<A> a) { return s_sqrt(w_dot(a, a));
 template <class A, class B> LINON_HD P<A, B> w_distance(vec2t<A> a, vec2t<B> b) { return w_length(a - b); }
 template <class A, class B> LINON_HD P<A, B> w_distance(vec3t<A> a, vec3t<B> b) { return w_length(a - b); }
 template <class A, class B> LINON_HD P<A, B> w_distance(vec4t<A> a, vec4t<B> b) { return w_length(a - b); }
+#if LINON_FAST_MATH && LINON_DEVICE_BUILD
+// a * rsqrt(a.a): what --use_fast_math makes of a / sqrt(a.a) in a fresh process, said explicitly (see s_inverseSqrt)
+template <class A> LINON_HD vec2t<A> w_normalize(vec2t<A> a) { return a * w_inverseSqrt(w_dot(a, a)); }
+template <class A> LINON_HD vec3t<A> w_normalize(vec3t<A> a) { return a * w_inverseSqrt(w_dot(a, a)); }
+template <class A> LINON_HD vec4t<A> w_normalize(vec4t<A> a) { return a * w_inverseSqrt(w_dot(a, a)); }
+#else
 template <class A> LINON_HD vec2t<A> w_normalize(vec2t<A> a) { return a / w_length(a); }
 template <class A> LINON_HD vec3t<A> w_normalize(vec3t<A> a) { return a / w_length(a); }
 template <class A> LINON_HD vec4t<A> w_normalize(vec4t<A> a) { return a / w_length(a); }
+#endif
 template <class A, class B> LINON_HD vec2t<P<A, B>> w_reflect(vec2t<A> e1, vec2t<B> e2) {
     typedef P<A, B> S; return e1 - (S(2.0f) * w_dot(e2, e1)) * e2; }
 template <class A, class B> LINON_HD vec3t<P<A, B>> w_reflect(vec3t<A> e1, vec3t<B> e2) {

@@ -394,7 +394,11 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
     } else if (var.math == 1) {
         opts.insert(opts.end(), {"--fmad=true", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
     } else {
-        opts.push_back("--use_fast_math");
+        // every option --use_fast_math implies is ALSO passed explicitly: NVRTC 12.9 keeps --prec-div / --prec-sqrt / --ftz of an
+        // earlier compilation of the same process when a later one only says --use_fast_math, so a fast-math kernel compiled
+        // after a strict or fused one came out as different machine code (found in round 2: a long test session compiled
+        // production kernels that a fresh process never produces; tests/test_capi_cpu.py pins the order independence)
+        opts.insert(opts.end(), {"--use_fast_math", "--fmad=true", "--ftz=true", "--prec-div=false", "--prec-sqrt=false"});
         opts.push_back("-DLINON_FAST_MATH=1");
     }
     if (var.max_regs > 0) {

@@ -183,3 +183,33 @@ def test_nvrtc_is_the_toolkits_copy_whatever_else_the_process_loaded(product_lib
     cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     assert seen[0][0] == os.path.realpath(os.path.join(cuda_home, "lib64", "libnvrtc.so.12"))
     assert "site-packages" not in seen[0][0]
+
+
+def test_a_production_kernel_does_not_depend_on_what_was_compiled_before_it(product_lib, tmp_path):
+    """NVRTC 12.9 keeps --prec-sqrt / --prec-div / --ftz of an earlier compilation of the same process when a later one says
+    --use_fast_math: after a strict or fused compile the folds `1 / sqrtf(x)` -> rsqrt and `a / sqrtf(x)` -> a * rsqrt no longer
+    happened, and a long session (the GPU test suite, an editing session that toggles math modes) ran production kernels with
+    other machine code and other last bits than a fresh process - the culling-identity test failed only late in the full suite.
+    The fast build therefore names rsqrt itself and passes every implied option explicitly; the tile kernel's code hash of the
+    headline variant, of an adaptive one and of a generic translation must not depend on the compile order."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys\n"
+        "from linon_b200 import _capi as capi\n"
+        "from linon_b200.main_view import PredefinedFunction as P, compile_check\n"
+        "def h(fn, flags, math, spec='1'):\n"
+        "    os.environ.update(LINON_CHECK_QUIET_ZONE='2', LINON_CHECK_SPECIALIZE=spec)\n"
+        "    compile_check(fn.to_code(), flags=flags, math_mode=math)\n"
+        "    return open(os.environ['LINON_DUMP_CUBIN_HASH']).read().strip()\n"
+        "V = [(P.MirageSphericalSigmoid, capi.RENDER_ENHANCE, '1'), (P.MirageSpherical, 0, '1'), (P.MiragePlaneSigmoid, capi.RENDER_ADAPTIVE_OFF, '0')]\n"
+        "first = [h(fn, fl, capi.MATH_FAST, sp) for fn, fl, sp in V]\n"
+        "h(P.Rotation, 0, capi.MATH_FUSED); h(P.MirageSpherical, capi.RENDER_ENHANCE, capi.MATH_STRICT)\n"
+        "again = [h(fn, fl, capi.MATH_FAST, sp) for fn, fl, sp in V]\n"
+        "print(' '.join(first)); print(' '.join(again))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LINON_DUMP_CUBIN_HASH=str(tmp_path / "h.txt"), PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    first, again = r.stdout.strip().splitlines()[-2:]
+    assert first == again and len(set(first.split())) == 3
