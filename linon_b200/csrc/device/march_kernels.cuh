@@ -108,6 +108,9 @@
 #undef LINON_QUIET_ZONE
 #define LINON_QUIET_ZONE 0  // the body does not define LinonField<float>::quiet_steps (generic translations never do)
 #endif
+#ifndef LINON_QUIET_AHEAD
+#define LINON_QUIET_AHEAD 3  // small steps: regular quiet steps taken after a plan that found no run, before the next plan
+#endif
 #ifndef LINON_WARP_STATS
 #define LINON_WARP_STATS 0  // 1 (developer aid; tests/emu sets it): warp-level event counts of the fixed-step tile loops in
 #endif                      // counters[5..11]: plans, runs, full steps, quiet single steps, check events, directional bounds, straight warp-steps
@@ -919,7 +922,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 quiet = nq_warp > 0;
                 // (small steps only: with the default step a ray crosses a tenth of the room per step and the situation
                 // has changed by the next one)
-                constexpr int ahead = LINON_H_INITIAL < 0.01f ? 3 : 1;
+                constexpr int ahead = LINON_H_INITIAL < 0.01f ? LINON_QUIET_AHEAD : 1;
                 quiet_ahead = min(nq_warp, ahead) - 1;  // <= 0: the next step plans again
             }
             if (quiet) ++cnt.quiet;

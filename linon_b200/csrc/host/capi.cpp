@@ -401,6 +401,16 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
         opts.insert(opts.end(), {"--use_fast_math", "--fmad=true", "--ftz=true", "--prec-div=false", "--prec-sqrt=false"});
         opts.push_back("-DLINON_FAST_MATH=1");
     }
+    if (const char* dev = getenv("LINON_DEV_DEFINES")) {  // developer aid (parameter sweeps): extra -D options, space separated;
+        std::string d = dev;                               // NOT part of the variant key - one process per value
+        size_t pos = 0;
+        while (pos < d.size()) {
+            size_t e = d.find(' ', pos);
+            if (e == std::string::npos) e = d.size();
+            if (e > pos && d.compare(pos, 2, "-D") == 0) opts.push_back(d.substr(pos, e - pos));
+            pos = e + 1;
+        }
+    }
     if (var.max_regs > 0) {
         // __launch_bounds__ wins over --maxrregcount, so the cap is passed as resident CTAs per SM as well
         opts.push_back("--maxrregcount=" + std::to_string(var.max_regs));
