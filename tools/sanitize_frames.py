@@ -5,7 +5,7 @@
 
 Exercises: the four march kernels (tiles, persistent two-phase with the device queue, pairs, refill) in fixed-step,
 adaptive and Enhance variants, with and without the quiet zone, the hierarchy (BVH) path, sample rays, click positions,
-the outline search + finalize, both overlay kernels, and peer stores (three views of one process assembling a frame in
+the outline search + finalize, the three overlay kernels (incl. the TMA tile kernel), and peer stores (three views of one process assembling a frame in
 the root view's buffers).  Prints one line per case; exits non-zero if a frame disagrees with the tile kernel's.
 """
 import sys
@@ -40,7 +40,7 @@ with MainView(verts, faces, center, W, H) as mv:
                     mv.set_option(capi.OPT_MATH, capi.MATH_STRICT if quiet == 0 else capi.MATH_FAST)
                     mv.set_option(capi.OPT_KERNEL, kernel)
                     mv.set_option(capi.OPT_QUIET_ZONE, 2 if quiet else 0)
-                    for ok in (1, 0):
+                    for ok in (2, 1, 0):  # TMA tile kernel (default), direct taps, hand-staged tile
                         mv.set_option(capi.OPT_OVERLAY_KERNEL, ok)
                         mv.render_flags(flags)
                         mv.sync()
