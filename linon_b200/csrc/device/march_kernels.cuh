@@ -108,6 +108,12 @@
 #undef LINON_QUIET_ZONE
 #define LINON_QUIET_ZONE 0  // the body does not define LinonField<float>::quiet_steps (generic translations never do)
 #endif
+#ifndef LINON_WINDOW
+#define LINON_WINDOW 32         // quiet-zone runs: steps ahead within which a lane resolves its wall hit at plan time (0: off)
+#endif
+#ifndef LINON_WINDOW_CHECKS
+#define LINON_WINDOW_CHECKS 4   // ... and the checks it may spend on it per plan
+#endif
 #ifndef LINON_QUIET_AHEAD
 #define LINON_QUIET_AHEAD 3  // small steps: regular quiet steps taken after a plan that found no run, before the next plan
 #endif
@@ -865,6 +871,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         bool searching = true;  // warp-uniform
 #if LINON_QUIET_ZONE
         int quiet_ahead = 0;    // warp-uniform: steps from here known to be quiet for every lane (see below)
+        int clear_until = 0;    // window (below): steps before this index are verified clear of the geometry for this lane
 #endif
         for (; i < n_steps && searching; ++i) {
 #if LINON_QUIET_ZONE
@@ -891,7 +898,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 const float cost_up = __fmul_ru(sd.cost_linf(q_inf, kh), 1.000001f);
                 // steps whose budget stays positive (0.9999 covers the division and keeps the budget after the run > 0)
                 // (fmaxf first: a NaN - 0 / 0 for a ray that does not move - and a negative budget give 0)
-                const int nb = (int)fminf(fmaxf(__fdividef(sd.budget * 0.9999f, cost_up), 0.0f), 268435456.0f);
+                int nb = (int)fminf(fmaxf(__fdividef(sd.budget * 0.9999f, cost_up), 0.0f), 268435456.0f);
                 int n_clear = nb;  // steps this lane can take without a culling check
 #if LINON_CULL && !LINON_BVH
                 // the budget is what limits the run (a wall nearby, or a run that just ended): ask how far the straight ray
@@ -901,6 +908,80 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     const vec3f d = r.dir * h;
                     const float travel_max = (float)(n_steps - i) * l1_norm(d);
                     if (!has_color) n_clear = max(n_clear, straight_clear_steps(s_tri, r.p, d, travel_max, P.plane_w_max));
+                }
+#endif
+#if LINON_CULL && !LINON_BVH && LINON_WINDOW > 0
+                // Window (small steps only): a lane whose run the geometry cuts short within the next LINON_WINDOW steps
+                // resolves what happens at its wall NOW instead of stopping the whole warp there.  While a ray is quiet its
+                // positions are a known chain - p_(j+1) = fma(h, dir, p_j), the very FFMAs the run executes - so the lane walks
+                // a private copy to its first step that is not known to be clear and performs the regular culling check of
+                // that step, and of the next ones, until a face is hit or LINON_WINDOW_CHECKS steps are verified clear one by
+                // one.  Every check is the check the step-by-step path would perform at that step, at the same position, with
+                // the same direction: results are bit-identical, only their order in time changes (a hit is known a few steps
+                // early, which nothing else depends on - the ray marches on either way).  All lanes of the warp that are about
+                // to reach a wall do this together, each at its own step, so the final approach to a wall costs a few check
+                // rounds with most lanes active instead of one round per step with one to three (round 2 ncu: the checks
+                // were 19 % of the instructions and 30 % of the stall samples of the C3 frame).
+                if (LINON_H_INITIAL < 0.01f) {
+                    n_clear = max(n_clear, clear_until - i);  // what an earlier window has already verified step by step
+                    const int horizon = min(min(__reduce_min_sync(0xffffffffu, nq), n_steps - i), LINON_WINDOW);  // straight for all
+                    const bool limited = !has_color && n_clear < horizon;
+                    if (__any_sync(0xffffffffu, limited)) {
+                        LINON_WARP_EVENT(12, 1);
+                        vec3f pj = r.p;
+                        int jc = limited ? n_clear : 0;  // steps [0, jc) of this lane are known to be clear
+                        const int jmax = __reduce_max_sync(0xffffffffu, jc);
+                        for (int k = 0; k < jmax; ++k)
+                            if (k < jc) pj = advance_point(pj, r.dir, h);
+                        const vec3f w_step = r.dir * h;
+                        const float w_max_dist = w_length(w_step);
+                        const vec3f w_dirn = w_normalize(w_step);
+#pragma unroll 1
+                        for (int k = 0; k < LINON_WINDOW_CHECKS; ++k) {
+                            const bool act = limited && !has_color && jc < horizon;
+                            if (!__any_sync(0xffffffffu, act)) break;
+                            LINON_WARP_EVENT(13, 1);
+                            if (act) {
+                                const float p_l1 = l1_norm(pj);
+                                ++cnt.checks;
+                                float box_nearest = 0.0f;
+                                float nearest = nearest_geometry_distance(s_tri, pj, box_nearest);
+                                const float reach_up = SafeDistance::reach_bound(q_inf, kh, p_l1);
+                                if (!(nearest > reach_up)) {
+                                    float t_hit, plane_nearest;
+                                    int id;
+                                    intersect_mesh(s_tri, s_range, P.bvh, pj, w_dirn, w_max_dist, p_l1, t_hit, id, plane_nearest,
+                                                   cnt.face_tests, box_nearest > reach_up, box_nearest);
+                                    nearest = fmaxf(nearest, plane_nearest);
+                                    if (t_hit > 0.0f && t_hit < w_max_dist) {
+                                        color = shade(s_tri, id, w_dirn);
+                                        hit = LINON_FACE_ID(s_tri, id);
+                                        has_color = true;
+                                        cnt.prehit = i + jc + 1;  // the hit belongs to step i + jc
+                                        sd.budget = __int_as_float(0x7f800000);  // a lane that has hit never asks again
+                                    }
+                                }
+                                if (!has_color) {
+                                    // the checked step is clear, and so are the steps the safe-distance budget of THIS check
+                                    // covers (SafeDistance: the same refresh and the same cost the step-by-step path applies
+                                    // after a check at this position) - inside a cluster's box, where the directional bound
+                                    // says "now", that is what carries the lane to the face
+                                    SafeDistance wsd;
+                                    wsd.checked(nearest, p_l1, P.plane_w_max);
+                                    const float wcost = __fmul_ru(wsd.cost_linf(q_inf, kh), 1.000001f);
+                                    const int covered = (int)fminf(fmaxf(__fdividef(wsd.budget * 0.9999f, wcost), 1.0f), 1048576.0f);
+                                    const int skip = min(covered, horizon - jc);  // >= 1: the step just checked
+                                    for (int q = 0; q < skip; ++q) pj = advance_point(pj, r.dir, h);
+                                    jc += covered;  // may pass the horizon: the lane is then done with this window
+                                }
+                            }
+                        }
+                        if (limited) {
+                            n_clear = has_color ? 0x7fffffff : jc;
+                            clear_until = i + jc;
+                            if (has_color) nb = 268435456;  // its budget is infinite now: the run below must not spend it
+                        }
+                    }
                 }
 #endif
                 const int n_lane = LINON_CULL ? min(nq, n_clear) : 0;  // without culling every pre-hit step runs the face loop

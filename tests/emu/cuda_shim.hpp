@@ -224,6 +224,13 @@ inline int __reduce_min_sync(unsigned int mask, int v) {
         if ((mask >> l & 1u) && (s.present >> l & 1u)) r = std::min(r, (int)(long long)s.operand[l]);
     return r;
 }
+inline int __reduce_max_sync(unsigned int mask, int v) {
+    const emu::Snapshot& s = emu::collective((unsigned long long)(long long)v, emu_full(mask));
+    int r = v;
+    for (int l = 0; l < emu::kLanes; ++l)
+        if ((mask >> l & 1u) && (s.present >> l & 1u)) r = std::max(r, (int)(long long)s.operand[l]);
+    return r;
+}
 inline unsigned int __reduce_min_sync(unsigned int mask, unsigned int v) {
     const emu::Snapshot& s = emu::collective(v, emu_full(mask));
     unsigned int r = v;
