@@ -109,10 +109,13 @@
 #define LINON_QUIET_ZONE 0  // the body does not define LinonField<float>::quiet_steps (generic translations never do)
 #endif
 #ifndef LINON_WINDOW
-#define LINON_WINDOW 32         // quiet-zone runs: steps ahead within which a lane resolves its wall hit at plan time (0: off)
+#define LINON_WINDOW 64         // quiet-zone runs: steps ahead within which a lane resolves its wall hit at plan time (0: off)
+#endif
+#ifndef LINON_WINDOW_REFINE
+#define LINON_WINDOW_REFINE 1   // ... after asking the directional bound once more from where the window starts
 #endif
 #ifndef LINON_WINDOW_CHECKS
-#define LINON_WINDOW_CHECKS 4   // ... and the checks it may spend on it per plan
+#define LINON_WINDOW_CHECKS 2   // ... and the checks it may spend on it per plan (sweep at C3: 2 -> 8.39 ms, 4 -> 8.48, 8 -> 8.9)
 #endif
 #ifndef LINON_QUIET_AHEAD
 #define LINON_QUIET_AHEAD 3  // small steps: regular quiet steps taken after a plan that found no run, before the next plan
@@ -936,6 +939,19 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                         const vec3f w_step = r.dir * h;
                         const float w_max_dist = w_length(w_step);
                         const vec3f w_dirn = w_normalize(w_step);
+#if LINON_WINDOW_REFINE
+                        // n_clear was asked from far away (0.1 % of thousands of steps is several steps): ask the directional
+                        // bound again from the walked position, where the same 0.1 % is nothing, and walk on to the step that
+                        // reaches the wall - the first check then is the one that finds the face
+                        {
+                            const int more = limited ? min(straight_clear_steps(s_tri, pj, w_step, (float)(n_steps - i) * l1_norm(w_step),
+                                                                               P.plane_w_max), max(horizon - jc, 0)) : 0;
+                            const int more_max = __reduce_max_sync(0xffffffffu, more);
+                            for (int k = 0; k < more_max; ++k)
+                                if (k < more) pj = advance_point(pj, r.dir, h);
+                            jc += more;
+                        }
+#endif
 #pragma unroll 1
                         for (int k = 0; k < LINON_WINDOW_CHECKS; ++k) {
                             const bool act = limited && !has_color && jc < horizon;
@@ -981,6 +997,8 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                             clear_until = i + jc;
                             if (has_color) nb = 268435456;  // its budget is infinite now: the run below must not spend it
                         }
+                        searching = __any_sync(0xffffffffu, !has_color);  // the last lane may have hit in here: the run below still
+                                                                          // executes, then the loop hands over to the coasting loop
                     }
                 }
 #endif
