@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, 2-GPU call:  gpurun --gpus 2 --timeout 900 -- 'bash tools/r2_call17_n2.sh'   (final defaults: TMA overlay, radius 1500)
 set -u
-OUT=gpurun_out/r2c17
+OUT=gpurun_out/r2c25
 mkdir -p "$OUT"
 timeout 300 python -m pytest tests/test_gpu_sharded.py -q -m gpu -rxXs -p no:cacheprovider > "$OUT/tests_sharded.log" 2>&1; echo "sharded tests rc=$?" >> "$OUT/rc.txt"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > "$OUT/bench_n2_peer.json" 2> "$OUT/bench_n2_peer.err"; echo "bench n2 rc=$?" >> "$OUT/rc.txt"
