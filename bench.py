@@ -51,6 +51,7 @@ DEFAULT_QUIET = 2     # the library's default level of LINON_OPT_QUIET_ZONE (inc
 DEFAULT_QUIET_RADIUS = 1500  # ... and of LINON_OPT_QUIET_RADIUS
 STEPS_PER_RAY = 5001  # h_initial = 0.001: the loop of src/main_view.wgsl:244 runs 5001 times; adaptive sampling cannot trigger
 MARCH_PROFILE = os.path.join(ROOT, "profiles", "r2_march_c3.json")
+MARCH_PROFILE_STEP_BY_STEP = os.path.join(ROOT, "profiles", "r2_march_c3_step_by_step.json")  # LINON_OPT_COLLAPSE_RUNS = 0
 OVERLAY_PROFILE = os.path.join(ROOT, "profiles", "r2_overlay_c3.json")
 
 
@@ -350,21 +351,31 @@ def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
     E = capi.RENDER_ENHANCE
     shipped_quiet, shipped_spec = DEFAULT_QUIET, 1
 
-    def one(name, quiet, spec, frames, radius=DEFAULT_QUIET_RADIUS):
+    def one(name, quiet, spec, frames, radius=DEFAULT_QUIET_RADIUS, collapse=1):
         mv.set_option(capi.OPT_QUIET_ZONE, quiet)
         mv.set_option(capi.OPT_SPECIALIZE, spec)
         mv.set_option(capi.OPT_QUIET_RADIUS, radius)
+        mv.set_option(capi.OPT_COLLAPSE_RUNS, collapse)
         t = timed_frames(mv, E, frames, warm=1, flush=flush)
         c = mv.counters()
         assert int(c.accepted_steps) == W * H * STEPS_PER_RAY and int(c.rejected_steps) == 0, (name, c.accepted_steps)
         m = sr.grade(frame_buffers(mv), rf, fixed_step=True, max_excluded_fraction=0.02)
+        q = int(mv.debug_profile()[15])
         t.update(mrays_s=W * H / (t["ms_per_step"] * 1e-3) / 1e6, cubin_hash=mv.march_cubin_hash(),
-                 quiet_steps=int(mv.debug_profile()[15]), culling_checks=int(c.culling_checks), face_tests=int(c.face_tests))
+                 quiet_steps=q, culling_checks=int(c.culling_checks), face_tests=int(c.face_tests))
+        if quiet and spec:  # executed-work model of the fused path (linon_b200/flops.py), for the roofline of this variant
+            from linon_b200 import flops as fl
+            t["model_executed_flops"] = fl.fused_march_flops(c, FN_ID, field_weight_is_one=True, quiet_steps=q, collapsed_runs=bool(collapse))
         return t, m
 
     try:
         t, m = one("shipped", shipped_quiet, shipped_spec, 2)
         out["shipped"] = m
+        t, m = one("runs_step_by_step", shipped_quiet, shipped_spec, 2, collapse=0)
+        variants["runs_step_by_step"] = dict(t, note="LINON_OPT_COLLAPSE_RUNS = 0: every straight step of a quiet run is executed as one FFMA per "
+                                                     "coordinate instead of binade by binade (bit-identical frames); the FP32 roofline fraction "
+                                                     "of this variant is reported beside the default's (roofline.step_by_step)")
+        out["runs_step_by_step"] = m
         t, m = one("quiet_radius_saturation", shipped_quiet, shipped_spec, 2, radius=0)
         variants["quiet_radius_saturation"] = dict(t, note="LINON_OPT_QUIET_RADIUS = 0: the sigmoid zone ends where the reference's fp32 sigmoid "
                                                            "saturates (1.92 max_dist) and its own evaluation IS the identity, instead of the shipped "
@@ -381,6 +392,7 @@ def c3_parity_and_variants(mv, W, H, cpu, parity_seconds, flush):
         mv.set_option(capi.OPT_QUIET_ZONE, shipped_quiet)
         mv.set_option(capi.OPT_SPECIALIZE, shipped_spec)
         mv.set_option(capi.OPT_QUIET_RADIUS, DEFAULT_QUIET_RADIUS)
+        mv.set_option(capi.OPT_COLLAPSE_RUNS, 1)
     out["green"] = bool(out.get("shipped", {}).get("green")) and pinned is not False
     return out, variants
 
@@ -721,7 +733,7 @@ def run_ours(args):
     fp32_peak, sms = measure_fp32_peak(local_rank)
     m_ms = float(np.mean(march_ms))
 
-    model_flops = fl.fused_march_flops(counters, FN_ID, field_weight_is_one=True, quiet_steps=last.get("quiet", 0))
+    model_flops = fl.fused_march_flops(counters, FN_ID, field_weight_is_one=True, quiet_steps=last.get("quiet", 0), collapsed_runs=True)
     prof, prof_note = committed_profile(MARCH_PROFILE, "linon_march_tiles", cubin_hash)
     ncu_flops = None
     if prof is not None and world == 1 and prof.get("fp32_flops_executed"):
@@ -793,6 +805,21 @@ def run_ours(args):
     if world == 1 and not args.no_parity:
         try:
             line["parity"], line["variants"] = c3_parity_and_variants(mv, W, H, cpu, args.parity_seconds, flush)
+            sbs = line["variants"].get("runs_step_by_step")
+            if sbs and sbs.get("model_executed_flops"):
+                # the same kernel with every straight step executed (LINON_OPT_COLLAPSE_RUNS = 0): executed FP32 work / its march time
+                sprof, snote = committed_profile(MARCH_PROFILE_STEP_BY_STEP, "linon_march_tiles", sbs["cubin_hash"])
+                s_ncu = float(sprof["fp32_flops_executed"]) if sprof and sprof.get("fp32_flops_executed") else None
+                s_flops = min(sbs["model_executed_flops"], s_ncu) if s_ncu else sbs["model_executed_flops"]
+                s_ach = s_flops / (sbs["march_ms"] * 1e-3) / 1e12
+                line["roofline"]["step_by_step"] = dict(
+                    achieved=s_ach, frac=s_ach / line["roofline"]["peak"], launch_ms=sbs["march_ms"],
+                    numerators=dict(model_executed_flops=sbs["model_executed_flops"], ncu_executed_flops=s_ncu), ncu_profile=snote,
+                    frac_on_ncu_count=(s_ncu / (sbs["march_ms"] * 1e-3) / 1e12 / line["roofline"]["peak"]) if s_ncu else None,
+                    issue_slot_utilization_ncu=(sprof.get("sm__inst_issued.avg.pct_of_peak_sustained_active") if sprof else None),
+                    note="LINON_OPT_COLLAPSE_RUNS = 0: the straight steps of quiet runs executed one by one (3 FMA each) - the kernel the "
+                         "north star's FP32 target is about; the shipped default takes those stretches binade by binade, executes less and "
+                         "finishes sooner, so its fraction of the FP32 peak is lower at a shorter frame time")
         except Exception as e:  # noqa: BLE001
             line["parity"] = dict(error=f"{type(e).__name__}: {e}"[:400], green=False)
     if world == 1 and not args.no_configs:

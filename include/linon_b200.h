@@ -136,6 +136,13 @@ enum {
                                     2 (default): 32x32 tile + halo by ONE TMA load per CTA (cp.async.bulk.tensor.2d + mbarrier),
                                     taps are four LDS.128 at compile-time offsets (csrc/device/overlay_tile.cuh); runs variant 1
                                     when the driver cannot encode the tensor map or delta is outside 1..10 */
+    LINON_OPT_COLLAPSE_RUNS = 15, /* quiet-zone runs of 160 steps or more.  1 (default): taken binade by binade - inside one binade of a
+                                    coordinate the rounded increment of p <- fma(h, dir, p) is a constant multiple of the ulp, so a
+                                    stretch of k steps is one FMA, q + k delta, bit for bit (march_kernels.cuh: advance_coord; pinned
+                                    against the step-by-step chain on random and adversarial inputs and by the frames of the kernel
+                                    without runs; C3 march 8.4 -> 6.4 ms).  0: every straight step is executed as one FFMA per
+                                    coordinate - the variant the FP32 roofline fraction of DESIGN.md section 5 is quoted for beside
+                                    the default; every bench line times and grades both */
     LINON_OPT_CULL = 8           /* 1 (default): exact culling of the face loop - a per-ray lower bound on the distance to the
                                     nearest face plane skips the loop entirely while no plane is in reach, and plane groups
                                     out of reach are skipped inside it; results are bit-identical with 0.

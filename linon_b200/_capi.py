@@ -22,6 +22,7 @@ BUF_RAY_SAMPLES, BUF_SAMPLE_POS = 5, 6
 OPT_MATH, OPT_KERNEL, OPT_BLOCK, OPT_CTAS_PER_SM, OPT_REFILL_MIN, OPT_FACE_UNROLL, OPT_MAX_REGS, OPT_PROFILE, OPT_CULL = range(9)
 OPT_PAIR_MIN_BLOCKS, OPT_SPECIALIZE, OPT_FORCE_BVH, OPT_QUIET_ZONE, OPT_QUIET_RADIUS = 9, 10, 11, 12, 13
 OPT_OVERLAY_KERNEL = 14
+OPT_COLLAPSE_RUNS = 15
 MATH_STRICT, MATH_FUSED, MATH_FAST = 0, 1, 2
 KERNEL_TILES, KERNEL_PERSISTENT, KERNEL_PAIRS, KERNEL_REFILL = 0, 1, 2, 3
 

@@ -108,6 +108,12 @@
 #undef LINON_QUIET_ZONE
 #define LINON_QUIET_ZONE 0  // the body does not define LinonField<float>::quiet_steps (generic translations never do)
 #endif
+#ifndef LINON_COLLAPSE_RUNS
+#define LINON_COLLAPSE_RUNS 0   // quiet runs: n straight steps per coordinate binade by binade instead of one by one (advance_coord)
+#endif
+#ifndef LINON_COLLAPSE_MIN
+#define LINON_COLLAPSE_MIN 160   // ... from this run length on (sweep at C3: 32 .. 512 within 2 %, 96 - 256 best)
+#endif
 #ifndef LINON_WINDOW
 #define LINON_WINDOW 64         // quiet-zone runs: steps ahead within which a lane resolves its wall hit at plan time (0: off)
 #endif
@@ -810,6 +816,64 @@ __device__ __forceinline__ vec3f advance_point(vec3f p, vec3f dir, float h) {
 #endif
 }
 
+#if !LINON_STRICT_MATH
+// n straight steps of ONE coordinate, p <- fma(d, h, p) n times, bit for bit - without executing them one by one.
+// While p stays inside one binade every p is a multiple of the binade's ulp u, so fl(p + a), a = d h exactly, is
+// p + rn_u(a): the rounded increment delta is the SAME for every step that starts and ends in the binade (a tie, a exactly
+// half-way between two multiples of u, is the exception: its rounding depends on the parity of p).  One real step gives
+// q = fl(p + a) and delta = q - p (exact: same binade); then k further steps are q + k delta, which is representable (a
+// multiple of u inside the binade) and hence exactly what one FMA returns.  k is limited by the binade: a step that starts at
+// magnitude m must end at m + |delta| <= 2^(E+1) when the magnitude grows (above 2^(E+1) the grid is coarser, and the rounded
+// sum lands on 2^(E+1) or below either way) and at m - |delta| >= 2^E + 2u when it shrinks (below 2^E the grid is finer).
+// Near zero, across a binade boundary, on a (near-)tie, for NaN / inf / tiny p: single steps, the loop always advances.
+// The rays of a quiet run do exactly this n times per coordinate (advance_point); a run of 700 steps that crosses two binade
+// boundaries costs three real steps and three jumps per coordinate.  Pinned against the step-by-step loop on random and
+// adversarial inputs (tests/test_emulation_cpu.py: test_collapsed_runs_equal_the_step_by_step_chain) and by the frames that
+// must equal the kernel without runs (culling off) bit for bit.
+__device__ __forceinline__ float advance_coord(float p, const float d, const float h, int n) {
+    while (n > 0) {
+        const float q = __fmaf_rn(d, h, p);  // one real step
+        --n;
+        if (q == p) return p;                // a rounds to nothing here: every further step returns the same value
+        const int bp = __float_as_int(p), bq = __float_as_int(q);
+        const int e = bp & 0x7f800000;
+        if (n > 0 && ((bp ^ bq) & 0xff800000) == 0 && e >= (64 << 23) && e < (254 << 23)) {  // same sign and binade, plainly normal
+            const float delta = q - p;                                // exact
+            const float u = __int_as_float(e - (23 << 23));          // the binade's ulp
+            const float res = __fmaf_rn(d, h, -delta);               // a - delta, |.| <= u / 2 (rounded: only its size matters)
+            if (fabsf(res) < 0.499999f * u) {                        // not a tie, not even nearly
+                const float lo = __int_as_float(e);                  // 2^E
+                const float mq = fabsf(q), ad = fabsf(delta);
+                const bool growing = ((__float_as_int(delta) ^ bp) & 0x80000000) == 0;
+                const float room = growing ? (2.0f * lo - mq) : (mq - lo - 2.0f * u);  // exact differences
+                // k further steps need room / |delta| >= k; 0.999999 and - 1 cover the approximate division
+                const float kf = floorf(__fdividef(room, ad) * 0.999999f) - 1.0f;
+                const int k = (int)fminf(fmaxf(kf, 0.0f), (float)n);
+                p = __fmaf_rn((float)k, delta, q);                   // exact: a multiple of u inside the binade
+                n -= k;
+                continue;
+            }
+        }
+        p = q;
+    }
+    return p;
+}
+#endif
+
+// n straight steps of a quiet run: advance_point n times.  LINON_COLLAPSE_RUNS: runs of at least LINON_COLLAPSE_MIN steps are
+// taken binade by binade (advance_coord: ~40 instructions per real step + jump and coordinate, a few of them per run, against
+// 3.4 instructions per step of the loop - measured at C3: 8.43 -> 7.12 ms; the 51-step frames and the 50-step stretches between
+// two samples of a sample ray are faster one by one: 0.27 vs 0.35 ms at 1080p).  n must be warp-uniform here.
+__device__ __forceinline__ vec3f advance_point_n(vec3f p, vec3f dir, float h, int n) {
+#if LINON_COLLAPSE_RUNS && !LINON_STRICT_MATH
+    if (n >= LINON_COLLAPSE_MIN)
+        return vec3f(advance_coord(p.x, dir.x, h, n), advance_coord(p.y, dir.y, h, n), advance_coord(p.z, dir.z, h, n));
+#endif
+#pragma unroll 8
+    for (int k = 0; k < n; ++k) p = advance_point(p, dir, h);
+    return p;
+}
+
 extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) linon_march_tiles(const MarchParams P) {
     LINON_MESH_PROLOGUE(P)
 
@@ -1005,8 +1069,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 const int n_lane = LINON_CULL ? min(nq, n_clear) : 0;  // without culling every pre-hit step runs the face loop
                 const int n = min(__reduce_min_sync(0xffffffffu, n_lane), n_steps - i);
                 if (n > 0) {
-#pragma unroll 8
-                    for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
+                    r.p = advance_point_n(r.p, r.dir, h, n);
                     r.t = __fmaf_rn((float)n, h, r.t);
                     // within the budget: take the run from it (+inf stays +inf); beyond it (the directional bound allowed
                     // more): the budget is spent, the next regular step runs a check and refreshes it
@@ -1101,8 +1164,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                 if (n > 0) {
                     LINON_WARP_EVENT(6, 1);
                     LINON_WARP_EVENT(11, n);
-#pragma unroll 8
-                    for (int k = 0; k < n; ++k) r.p = advance_point(r.p, r.dir, h);
+                    r.p = advance_point_n(r.p, r.dir, h, n);
                     r.t = __fmaf_rn((float)n, h, r.t);
                     cnt.quiet += (unsigned int)n;
                     i += n - 1;
@@ -1711,8 +1773,13 @@ __constant__ float c_sample_colors[8][3] = {  // src/main_view.wgsl:326-335
     {1.0f, 1.0f, 0.0f}, {0.5f, 0.5f, 0.5f}, {0.0f, 0.0f, 1.0f}, {0.5f, 0.0f, 0.5f}};
 
 extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleParams S) {
-    const int k = threadIdx.x;
+    // ONE RAY PER CTA (grid = 8, one warp each; every lane carries the same ray, lane 0 stores): the reference marches the eight
+    // rays on threads gid.x < 8 of one workgroup (src/main_view.wgsl:281-314), and in one warp their control flow interleaves -
+    // whenever ANY of the eight is inside a mirage's zone of influence all eight pay a full Runge-Kutta evaluation and a zone
+    // query per step.  Eight warps on eight SMs follow their own ray each; the arithmetic of a ray is unchanged.
+    const int k = blockIdx.x;
     if (k >= 8) return;
+    const bool writer = threadIdx.x == 0;
     const MarchParams& P = S.march;
     const WgslCamera cam = make_camera(P);
     const WgslSettings st = P.settings;
@@ -1727,37 +1794,39 @@ extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleP
     const float h = LINON_SAMPLE_H;
     const float4 colour = make_float4(c_sample_colors[k][0], c_sample_colors[k][1], c_sample_colors[k][2], 0.5f);
 #if LINON_QUIET_ZONE && LINON_FW_ONE
-    // LINON_QUIET_ZONE (opt-in): outside the body's zone of influence the Runge-Kutta velocity is the direction itself, so the
-    // ray asks once how many steps it stays outside (quiet_steps: exact entry of the straight line into the zone) and takes
-    // them as straight steps - every one of the 5000 steps is still executed and every 50th still sampled.  Per lane, no
-    // collective: only lanes 0..7 are alive here.  The serial chain of a sample ray is what a small frame waits for.
+    // LINON_QUIET_ZONE: outside the body's zone of influence the Runge-Kutta velocity is the direction itself, so the ray asks
+    // once how many steps it stays outside (quiet_steps: exact entry of the straight line into the zone) and takes them as
+    // straight steps, up to the next sampled step at a time - every one of the 5000 steps is accounted for bit by bit
+    // (advance_point_n) and every 50th is still sampled.
     int quiet_left = 0;
 #endif
     constexpr int sample_step_size = LINON_SAMPLE_STEPS / 100;  // steps / sample_steps, src/main_view.wgsl:292-293
     for (int i = 0; i < LINON_SAMPLE_STEPS; ++i) {
+        if (i % sample_step_size == 0 && writer) {  // the sample is the position BEFORE the step's advance (:304-309)
+            const int index = k * 100 + i / sample_step_size;
+            S.ray_samples[2 * index] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
+            S.ray_samples[2 * index + 1] = colour;
+        }
 #if LINON_QUIET_ZONE && LINON_FW_ONE
         if (quiet_left == 0) quiet_left = min(LinonField<float>::quiet_steps(r.p, r.dir, h), LINON_SAMPLE_STEPS);
-        vec3f v;
         if (quiet_left > 0) {
-            v = r.dir;
-            --quiet_left;
-        } else {
-            v = rk4_velocity(r, h, st, cam);
+            // straight steps up to (not including) the next sampled step, the end of the quiet run or the last step
+            const int to_sample = sample_step_size - i % sample_step_size;
+            const int n = min(min(quiet_left, to_sample), LINON_SAMPLE_STEPS - i);
+            r.p = advance_point_n(r.p, r.dir, h, n);
+            r.t = __fmaf_rn((float)n, h, r.t);
+            quiet_left -= n;
+            i += n - 1;  // the loop header adds the last one
+            continue;
         }
-#else
-        const vec3f v = rk4_velocity(r, h, st, cam);
 #endif
+        const vec3f v = rk4_velocity(r, h, st, cam);
 #if LINON_FW_ONE
         r.dir = v;
 #else
         r.dir = (1.0f - st.field_weight) * r.dir + st.field_weight * v;
 #endif
         const vec3f step_dir = r.dir * h;
-        if (i % sample_step_size == 0) {
-            const int index = k * 100 + i / sample_step_size;
-            S.ray_samples[2 * index] = make_float4(r.p.x, r.p.y, r.p.z, 1.0f);
-            S.ray_samples[2 * index + 1] = colour;
-        }
         r.p = r.p + step_dir;
         r.t = r.t + h;
     }

@@ -228,6 +228,7 @@ struct Variant {
     int pairs;            // 1: also build linon_march_pairs (LinonField<f32x2>, two rays per thread)
     int pair_min_blocks;  // resident CTAs / SM requested for it (0 = kernel default)
     int quiet;            // 1: fixed-step loops take straight steps where a fused mirage body is the identity (LINON_QUIET_ZONE)
+    int collapse;         // 1: quiet runs of at least LINON_COLLAPSE_MIN steps are taken binade by binade (advance_coord)
     int quiet_radius;     // sigmoid profiles: zone radius in permille of max_dist (0 = where the fp32 sigmoid saturates, 1.92:
                           // the default of mirage_fused.cuh; the library's default is 1500, LINON_OPT_QUIET_RADIUS)
 };
@@ -384,6 +385,7 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
                                      "-DLINON_FW_ONE=" + std::to_string(var.fw_one),
                                      "-DLINON_BVH=" + std::to_string(var.bvh),
                                      "-DLINON_QUIET_ZONE=" + std::to_string(var.quiet),
+                                     "-DLINON_COLLAPSE_RUNS=" + std::to_string(var.collapse),
                                      // strict: ptxas would contract mul.rn.f32x2 + add.rn.f32x2 whatever --fmad says
                                      "-DLINON_PACKED_OPS=" + std::to_string((var.math == 0 || getenv("LINON_DEV_UNPACKED")) ? 0 : 1),
                                      "-DLINON_STRICT_MATH=" + std::to_string(var.math == 0 ? 1 : 0)};
@@ -471,8 +473,8 @@ bool compile_cubin(const std::string& wgsl_body, const Variant& var, const linon
 }
 
 std::string variant_key(const std::string& body, const Variant& v, const linon::ModuleLayer& layer) {
-    return layer.members + "\x01" + layer.preamble + "\x01" + layer.march_defines + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
-               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh, v.quiet, v.quiet_radius) + body;
+    return layer.members + "\x01" + layer.preamble + "\x01" + layer.march_defines + "\x01" + fmt("%a|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|", (double)v.h_initial, v.adaptive, v.n_faces, v.n_groups, v.n_p1, v.n_boxes, v.n_segs, v.cull, v.math,
+               v.block, v.unroll, v.refill_min, v.max_regs, v.profile, v.pairs, v.pair_min_blocks, v.specialize, v.fw_one, v.bvh, v.quiet, v.quiet_radius, v.collapse) + body;
 }
 
 }  // namespace
@@ -523,7 +525,7 @@ struct linon_view {
     uint64_t module_clock = 0;  // use counter for the LRU eviction of `modules`
 
     int opt_math = 2, opt_kernel = 0, opt_pair_min_blocks = 0, opt_specialize = 1, opt_force_bvh = 0, opt_block = 256, opt_ctas_per_sm = 0, opt_refill_min = 1, opt_unroll = 4,
-        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 1500, opt_overlay_kernel = 2;
+        opt_max_regs = 0, opt_profile = 0, opt_cull = 1, opt_quiet = 2, opt_quiet_radius = 1500, opt_overlay_kernel = 2, opt_collapse = 1;
     // tile overlay kernel: tensor map over d_endpoint as a (4 W, H) fp32 tensor, box = tile + halo of the current delta
     alignas(64) CUtensorMap endpoint_map;
     const void* endpoint_map_ptr = nullptr;
@@ -756,6 +758,7 @@ Variant make_variant(const linon_view* v, uint32_t flags) {
     // (1: fixed-step variants only, 2: adaptive variants as well)
     var.quiet = (v->opt_quiet > (var.adaptive ? 1 : 0) && v->opt_math == 2 && v->opt_specialize) ? 1 : 0;
     var.quiet_radius = var.quiet ? v->opt_quiet_radius : 0;
+    var.collapse = var.quiet ? v->opt_collapse : 0;
     return var;
 }
 
@@ -1176,7 +1179,7 @@ int linon_render(linon_view* v, uint32_t flags) {
         S.pos16 = v->d_pos16;
         S.ray_samples = v->d_ray_samples;
         CK(v, cudaEventRecord(v->ev[4], v->aux));
-        const int rc = launch(v, mod->sample, 1, 32, v->aux, &S);
+        const int rc = launch(v, mod->sample, 8, 32, v->aux, &S);  // one ray per CTA (march_kernels.cuh: linon_sample_rays)
         if (rc != LINON_OK) return rc;
         CK(v, cudaEventRecord(v->ev[5], v->aux));
         v->ran_sample = true;
@@ -1504,6 +1507,7 @@ int linon_set_option(linon_view* v, int option, int value) {
         case LINON_OPT_CULL: if (value < 0 || value > 1) break; v->opt_cull = value; return LINON_OK;
         case LINON_OPT_QUIET_ZONE: if (value < 0 || value > 2) break; v->opt_quiet = value; return LINON_OK;
         case LINON_OPT_OVERLAY_KERNEL: if (value < 0 || value > 2) break; v->opt_overlay_kernel = value; return LINON_OK;
+        case LINON_OPT_COLLAPSE_RUNS: if (value < 0 || value > 1) break; v->opt_collapse = value; return LINON_OK;
         case LINON_OPT_QUIET_RADIUS: if (value != 0 && (value < 1250 || value > 4000)) break; v->opt_quiet_radius = value; return LINON_OK;
     }
     return v->fail(LINON_ERR_INVALID, fmt("linon_set_option(%d, %d): invalid", option, value));
@@ -1603,6 +1607,7 @@ int compile_check_impl(const char* module_src, const char* wgsl_body, uint32_t f
     if (const char* k = getenv("LINON_CHECK_BVH")) tmp.use_bvh = atoi(k) != 0;
     if (const char* k = getenv("LINON_CHECK_QUIET_ZONE")) tmp.opt_quiet = atoi(k);
     if (const char* k = getenv("LINON_CHECK_QUIET_RADIUS")) tmp.opt_quiet_radius = atoi(k);
+    if (const char* k = getenv("LINON_CHECK_COLLAPSE")) tmp.opt_collapse = atoi(k);
     if (const char* k = getenv("LINON_CHECK_CULL")) tmp.opt_cull = atoi(k);
     Variant var = make_variant(&tmp, flags);
     if (var.n_faces == 0 && !tmp.use_bvh) default_mesh_counts(var);

@@ -50,7 +50,11 @@ SAFE_STEP_V2 = 8                     # step_dir (3), |s|_1 (2), cost (2), budget
 QUIET_STEP = 6  # LINON_OPT_QUIET_ZONE: a straight step is the position update alone (3 FMA)
 
 
-def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True, quiet_steps: int = 0) -> float:
+QUIET_STEP_COLLAPSED = 0  # ... and nothing at all where runs are collapsed (LINON_COLLAPSE_RUNS, march_kernels.cuh: advance_coord): the
+                          # steps of a run are not executed one by one, and the few real steps and jumps per run are not counted
+
+
+def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True, quiet_steps: int = 0, collapsed_runs: bool = False) -> float:
     """Executed-work model of the fast-mode mirage path in fixed-step variants (Enhance, adaptive off).
 
     quiet_steps: accepted steps taken as straight steps (counter 15 of linon_debug_profile with LINON_OPT_QUIET_ZONE on).
@@ -59,7 +63,7 @@ def fused_march_flops(counters, fn_id: int, field_weight_is_one: bool = True, qu
     f_stage, f_last, f_prev = FUSED_FLOPS[fn_id]
     step = FUSED_STEP_FIXED + (0 if field_weight_is_one else 10) + 2 * f_stage + f_last + f_prev
     full_steps = counters.accepted_steps - quiet_steps
-    flops = full_steps * step + quiet_steps * QUIET_STEP + counters.face_tests * FACE_TEST
+    flops = full_steps * step + quiet_steps * (QUIET_STEP_COLLAPSED if collapsed_runs else QUIET_STEP) + counters.face_tests * FACE_TEST
     flops += counters.prehit_steps * SAFE_STEP_V2 * (full_steps / max(counters.accepted_steps, 1))
     flops += counters.culling_checks * (PREHIT_EXTRA + CHECK_EXTRA + 3) + counters.plane_tests * PLANE_TEST
     return float(flops)

@@ -70,6 +70,20 @@ static int run_grid(void (*entry)(void*), void* arg, int n_blocks, int n_threads
     return bad;
 }
 
+#if !LINON_STRICT_MATH
+// advance_coord (march_kernels.cuh: n straight steps of one coordinate without executing them one by one) against the chain it
+// replaces, p <- fma(d, h, p) n times with the host's correctly rounded fmaf
+void emu_advance_coord(int cases, const float* p, const float* d, float h, const int* n, float* jumped, float* stepped) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < cases; ++i) {
+        jumped[i] = advance_coord(p[i], d[i], h, n[i]);
+        float x = p[i];
+        for (int k = 0; k < n[i]; ++k) x = fmaf(d[i], h, x);
+        stepped[i] = x;
+    }
+}
+#endif
+
 #if LINON_QUIET_ZONE
 // the two planning functions of the quiet zone on arrays of rays (property tests): steps outside the body's zone of
 // influence and, for the start-up tables of `verts / faces`, steps of a straight ray that cannot reach a face
@@ -153,12 +167,12 @@ int emu_march(const EmuFrame* f) {
     std::vector<float4> q_state;
     P.work = work.data();
     int bad = 0;
-    if (f->ray_samples) {  // linon_sample_rays: one CTA, lanes 0..7 carry the eight rays
+    if (f->ray_samples) {  // linon_sample_rays: eight CTAs of one warp, one ray each
         SampleParams S;
         S.march = P;
         S.pos16 = f->pos16;
         S.ray_samples = (float4*)f->ray_samples;
-        bad = run_grid(sample_entry, &S, 1, 1, 1, 1);
+        bad = run_grid(sample_entry, &S, 8, n_threads, 1, 1);
     } else if (f->kernel == 0) {
         bad = run_grid(kernel_entry, &P, (int)(P.n_ray_slots / 32u), n_threads, f->tile_row_step, (int)tiles_x);
     } else if (f->kernel == 2) {

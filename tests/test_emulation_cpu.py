@@ -443,3 +443,44 @@ def test_emulated_sample_rays_with_the_quiet_zone(product_lib, oracle, fn):
         err_q = np.abs(quiet[:, :3].astype(np.float64) - ref[:, :3]).max()
         err_p = np.abs(plain[:, :3].astype(np.float64) - ref[:, :3]).max()
         assert err_q <= max(2.0 * err_p, 2e-5), (err_q, err_p)
+
+
+def test_collapsed_runs_equal_the_step_by_step_chain(product_lib):
+    """advance_coord (march_kernels.cuh, LINON_COLLAPSE_RUNS): n straight steps of a coordinate, p <- fma(d, h, p), taken binade by
+    binade - one real step, then k steps as q + k delta while every step starts and ends inside the binade.  Must equal the chain
+    bit for bit: random coordinates of a frame, zero crossings, starts on and next to binade boundaries, increments that are exact
+    half-ulps (ties), increments below the ulp (the coordinate does not move), tiny / huge / non-finite values."""
+    import ctypes as C
+    lib = emu.build(PredefinedFunction.MirageSphericalSigmoid.to_code(), capi.RENDER_ENHANCE, capi.MATH_FAST, quiet_zone=1)
+    rng = np.random.default_rng(11)
+    h = np.float32(0.001)
+    P, D, N = [], [], []
+
+    def add(p, d, n):
+        P.append(np.asarray(p, np.float32).ravel()); D.append(np.asarray(d, np.float32).ravel()); N.append(np.asarray(n, np.int32).ravel())
+
+    m = 400_000
+    add(rng.uniform(-3, 3, m), rng.uniform(-1.5, 1.5, m), rng.integers(0, 5002, m))                       # a frame's coordinates
+    add(rng.uniform(-2e-3, 2e-3, m // 4), rng.uniform(-1.5, 1.5, m // 4), rng.integers(0, 3000, m // 4))   # around zero
+    pw = np.ldexp(1.0, rng.integers(-12, 3, m // 4)).astype(np.float32) * rng.choice([-1.0, 1.0], m // 4).astype(np.float32)
+    off = rng.integers(-3, 4, m // 4).astype(np.int32)
+    near = (pw.view(np.int32) + off).view(np.float32)                                                     # on / next to a binade boundary
+    add(near, rng.uniform(-1.5, 1.5, m // 4), rng.integers(0, 2000, m // 4))
+    # ties: d h exactly an odd multiple of half an ulp of p (h = 2^-10 here would be needed for exact products: use d = c / h
+    # rounded - not exact - plus true ties with a power-of-two step in a second call below)
+    add(rng.uniform(0.5, 1.0, m // 8), rng.uniform(-1e-4, 1e-4, m // 8), rng.integers(0, 5002, m // 8))    # |a| < ulp: stuck or crawling
+    add([0.0, -0.0, 1e-30, -1e-30, 3e38, -3e38, np.inf, -np.inf, np.nan, 1.0, 1.0], [1, 1, 1, -1, 1, 1, 1, 1, 1, 0, np.nan],
+        [100, 100, 5000, 5000, 100, 100, 10, 10, 10, 5000, 7])
+    p, d, n = np.concatenate(P), np.concatenate(D), np.concatenate(N)
+    assert p.size == d.size == n.size
+    for hh, pp, dd, nn in ((h, p, d, n),
+                           # exact ties: h = 2^-10, d a multiple of 2^-14 -> d h is a multiple of 2^-24 = half an ulp in [0.5, 1)
+                           (np.float32(2.0 ** -10), rng.uniform(0.5, 1.0, 200_000).astype(np.float32),
+                            (rng.integers(-4000, 4000, 200_000) * 2.0 ** -14).astype(np.float32), rng.integers(0, 3000, 200_000).astype(np.int32))):
+        pp, dd, nn = np.ascontiguousarray(pp, np.float32), np.ascontiguousarray(dd, np.float32), np.ascontiguousarray(nn, np.int32)
+        a, b = np.zeros_like(pp), np.zeros_like(pp)
+        lib.emu_advance_coord(C.c_int(pp.size), C.c_void_p(pp.ctypes.data), C.c_void_p(dd.ctypes.data), C.c_float(float(hh)),
+                              C.c_void_p(nn.ctypes.data), C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+        same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+        bad = np.nonzero(~same)[0]
+        assert bad.size == 0, [(float(pp[i]), float(dd[i]), int(nn[i]), float(a[i]), float(b[i])) for i in bad[:5]]
