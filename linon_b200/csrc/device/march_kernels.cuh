@@ -846,9 +846,14 @@ __device__ __forceinline__ float advance_coord(float p, const float d, const flo
                 const float mq = fabsf(q), ad = fabsf(delta);
                 const bool growing = ((__float_as_int(delta) ^ bp) & 0x80000000) == 0;
                 const float room = growing ? (2.0f * lo - mq) : (mq - lo - 2.0f * u);  // exact differences
-                // k further steps need room / |delta| >= k; 0.999999 and - 1 cover the approximate division
-                const float kf = floorf(__fdividef(room, ad) * 0.999999f) - 1.0f;
-                const int k = (int)fminf(fmaxf(kf, 0.0f), (float)n);
+                // k further steps need k |delta| <= room.  The approximate quotient is corrected by the exact test: k |delta| and
+                // room are multiples of u below 2^(E+1), so fma(k, |delta|, -room) is exact; a quotient beyond the remaining
+                // steps (up to 2^24 |delta| / |delta|) is clamped first, where the estimate's error no longer matters
+                float kf = fminf(floorf(__fdividef(room, ad)), (float)n);
+                kf = fmaxf(kf, 0.0f);
+                if (__fmaf_rn(kf, ad, -room) > 0.0f) kf -= 1.0f;   // estimate one too high
+                if (__fmaf_rn(kf, ad, -room) > 0.0f) kf -= 1.0f;   // (two ulps of the division at most)
+                const int k = (int)fmaxf(kf, 0.0f);
                 p = __fmaf_rn((float)k, delta, q);                   // exact: a multiple of u inside the binade
                 n -= k;
                 continue;
