@@ -761,9 +761,13 @@ def run_ours(args):
         config=workload_config(world, W, H),
         implementation=dict(
             math_mode="fast (--use_fast_math; whole-step restatement of the predefined mirage body: RK4 stage 1 = identity, scaled coordinates, one reciprocal per stage)",
-            kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass culling checks)",
+            kernel="linon_march_tiles (one thread per pixel, 8x4 tiles, converged fixed-step loop split by warp phase, full-mask votes, two-pass "
+                   "culling checks, wall hits of quiet runs resolved at plan time)",
             quiet_zone=("on" if last.get("quiet", 0) else "off") + ": straight steps (velocity = direction) while the whole warp is outside the "
-                       "mirage's zone of influence, where the reference's own fp32 evaluation is the identity; every RK4 step is executed and counted",
+                       "mirage's zone of influence (1.5 max_dist: beyond it the real-number signal is 50x below the fp32 quantum); every RK4 step is "
+                       "counted, and the straight steps of a run are taken binade by binade - k steps inside one binade of a coordinate are one "
+                       "exact FMA, bit-identical with executing them one by one (LINON_OPT_COLLAPSE_RUNS; variants.runs_step_by_step and "
+                       "roofline.step_by_step time and grade the step-by-step kernel in this same run)",
             plane_culling=True, march_cubin_hash=cubin_hash, march_regs=march_regs, nvrtc=nvrtc_version(),
             parallelism=(f"row-blocks x{world}" + (", peer stores into rank 0 over NVLink during the march (no gather)" if peer_stores else ", grouped NCCL send/recv to rank 0 after the march")) if world > 1 else "single GPU",
             l2="flushed between steps (256 MiB write); outputs 199 MB/frame exceed L2, inputs are 1.5 KB of uniforms"),
@@ -789,7 +793,8 @@ def run_ours(args):
                       algorithmic_bytes_per_launch=fl.MARCH_BYTES_PER_PIXEL * int(counters.rays),
                       note="issue-slot bound fp32 CUDA-core kernel (no dense contraction; HBM traffic is 24 B per 5001-step ray): "
                            "the numerator is work actually executed (smaller of hand count and, when the committed capture is of "
-                           "this very binary, the ncu count), never culled or skipped work"),
+                           "this very binary, the ncu count), never culled or skipped work - the straight steps of collapsed runs are "
+                           "credited with nothing; roofline.step_by_step is the same kernel with those steps executed one by one"),
         roofline_overlay=overlay_roof,
         counters=dict(accepted=acc, rejected=rej, prehit=pre, face_tests=ftests, plane_tests=ptests,
                       culling_checks=checks, quiet_steps=quiet_steps, quiet_fraction=quiet_steps / max(acc, 1.0)),

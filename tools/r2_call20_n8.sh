@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, 8-GPU call:  gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_call20_n8.sh'   (final defaults)
 set -u
-OUT=gpurun_out/r2c24
+OUT=gpurun_out/r2c30
 mkdir -p "$OUT"
 run() { # n tag
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $1 --steps 10 --warmup 3 > "$OUT/bench_n$1_$2.json" 2> "$OUT/bench_n$1_$2.err"; echo "bench n$1 $2 rc=$?" >> "$OUT/rc.txt"
