@@ -68,6 +68,29 @@ def test_quiet_zone_culling_never_changes_a_result(view, fn, flags):
     assert checks_on < view.counters().culling_checks
 
 
+@pytest.mark.parametrize("fn", MIRAGES)
+@pytest.mark.parametrize("size", [(160, 120), (333, 197)])
+def test_collapsed_runs_equal_the_step_by_step_frames(product_lib, scene, fn, size):
+    """LINON_OPT_COLLAPSE_RUNS (default 1): quiet runs of 160 steps or more are taken binade by binade (advance_coord) instead of one
+    FFMA per coordinate and step.  Same bits in every buffer and the same step counters as with the option off, on the device
+    (the host emulation pins the function itself against the chain on adversarial inputs, tests/test_emulation_cpu.py)."""
+    verts, faces, center = scene
+    W, H = size
+    with MainView(verts, faces, center, W, H) as mv:
+        frames = {}
+        for collapse in (1, 0):
+            mv.set_option(capi.OPT_COLLAPSE_RUNS, collapse)
+            frames[collapse] = render(mv, fn, flags=capi.RENDER_ENHANCE)
+            c = mv.counters()
+            frames[collapse]["counters"] = (int(c.accepted_steps), int(c.prehit_steps), int(c.face_tests), int(c.culling_checks), quiet_steps(mv))
+            frames[collapse]["hash"] = mv.march_cubin_hash()
+        assert frames[1]["hash"] != frames[0]["hash"]  # two different binaries really ran
+        for k in ("hit_id", "rgba8", "endpoint"):
+            assert np.array_equal(frames[1][k].view(np.uint8), frames[0][k].view(np.uint8)), k
+        assert frames[1]["counters"] == frames[0]["counters"]
+        assert frames[1]["counters"][4] > 0.5 * W * H * 5001  # most steps are straight steps (plane mirages: 82 %, spherical: 97 %)
+
+
 def test_quiet_zone_enhance_frame_meets_the_north_star(product_lib, oracle, scene):
     """C3 at reduced resolution (5001 steps per ray): against the oracle, and against the same kernel without the option."""
     verts, faces, center = scene
