@@ -19,17 +19,17 @@ from linon_b200.main_view import MainView, PredefinedFunction, default_scene, ma
 
 out_path = "gpurun_out/configs.json"
 reps = 3
-quiet_zone = 0
-overlay_kernel = 0
+quiet_zone = 2       # the library's defaults (include/linon_b200.h); the sweep of bench.py's `configs` block supersedes this tool
+overlay_kernel = 2
 args = sys.argv[1:]
 for i, a in enumerate(args):
     if a == "--out":
         out_path = args[i + 1]
     if a == "--reps":
         reps = int(args[i + 1])
-    if a == "--quiet-zone":  # LINON_OPT_QUIET_ZONE (opt-in): 1 fixed-step variants, 2 adaptive variants as well
+    if a == "--quiet-zone":  # LINON_OPT_QUIET_ZONE: 0 off, 1 fixed-step variants, 2 adaptive variants as well (default)
         quiet_zone = int(args[i + 1])
-    if a == "--overlay-kernel":  # LINON_OPT_OVERLAY_KERNEL (opt-in): 1 = direct kernel without the shared-memory stage
+    if a == "--overlay-kernel":  # LINON_OPT_OVERLAY_KERNEL: 0 hand-staged tile, 1 direct taps, 2 TMA tile (default)
         overlay_kernel = int(args[i + 1])
 
 verts, faces, center = default_scene()
