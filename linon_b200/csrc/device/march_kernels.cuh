@@ -21,6 +21,15 @@
 //                        sm_100 (FFMA2 / FMUL2 / FADD2), LinonField<f32x2>.  The host retries with 0 when a user
 //                        body does not instantiate for f32x2 (data-dependent control flow).
 //   LINON_PAIR_MIN_BLOCKS  resident CTAs / SM requested for linon_march_pairs (register cap)
+//   LINON_QUIET_ZONE     1: fixed-step loops take straight steps (and adaptive attempts identity steps) where the spliced fused
+//                        mirage body declares itself the identity (mirage_fused.cuh: quiet_steps); LINON_QUIET_RADIUS_SIGMOID its
+//                        radius for the sigmoid profiles
+//   LINON_WINDOW / LINON_WINDOW_CHECKS / LINON_WINDOW_REFINE   quiet runs: a lane about to reach a wall resolves its hit at plan
+//                        time over this many steps / with this many checks per plan / after asking the directional bound again
+//   LINON_COLLAPSE_RUNS / LINON_COLLAPSE_MIN   quiet runs of at least MIN steps are taken binade by binade (advance_coord)
+//   LINON_QUIET_AHEAD    regular quiet steps after a plan that found no run, before the next plan
+//   LINON_EPS, LINON_BACKFACE_CULLING, LINON_USE_LIGHTING, LINON_LINEAR_MODE, LINON_LIGHT_*, LINON_AMBIENT, LINON_SHININESS,
+//   LINON_T_MAX, LINON_SAMPLE_H, LINON_SAMPLE_STEPS ...   the march-level constants of an edited main_view.wgsl (hot reload)
 //
 // The march kernels share every per-ray device function, so their per-pixel results are bit-identical in strict mode:
 //   linon_march_tiles       one thread per pixel, 8x4 pixel tiles per warp (the straightforward mapping)
