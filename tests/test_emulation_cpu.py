@@ -197,7 +197,10 @@ def test_quiet_zone_enhance_frames_meet_the_north_star(product_lib, oracle, fn, 
     (PredefinedFunction.MirageSphericalSigmoid, capi.RENDER_ENHANCE, (40, 28), 0),
     (PredefinedFunction.MiragePlane, capi.RENDER_ENHANCE, (40, 28), 13),
     (PredefinedFunction.MirageSpherical, capi.RENDER_ADAPTIVE_OFF, (96, 72), 40),
-    (PredefinedFunction.MiragePlaneSigmoid, capi.RENDER_ADAPTIVE_OFF, (96, 72), 0)])
+    (PredefinedFunction.MiragePlaneSigmoid, capi.RENDER_ADAPTIVE_OFF, (96, 72), 0),
+    # Enhance frames from other points of the orbit (round 2: window resolve and collapsed runs act on these)
+    (PredefinedFunction.MirageSpherical, capi.RENDER_ENHANCE, (56, 36), 27),
+    (PredefinedFunction.MiragePlaneSigmoid, capi.RENDER_ENHANCE, (48, 32), 50)])
 def test_quiet_zone_culling_never_changes_a_result(product_lib, fn, flags, size, orbit_frame):
     """Straight runs skip culling checks on the strength of two bounds (the safe-distance budget and the directional bound
     of straight_clear_steps).  With LINON_CULL = 0 every pre-hit step runs the loop over all 36 faces instead: the frames must
