@@ -93,6 +93,24 @@ pub const LINON_BUF_HIT_ID_I32: c_int = 4;
 pub const LINON_BUF_RAY_SAMPLES: c_int = 5; // `ray_samples_buffer`, 800 x 32 B (src/ray_samples.rs:8-27)
 pub const LINON_BUF_SAMPLE_POS: c_int = 6;
 
+// linon_set_option keys (include/linon_b200.h, enum linon_option); defaults are the shipped configuration
+pub const LINON_OPT_MATH: c_int = 0;
+pub const LINON_OPT_KERNEL: c_int = 1;
+pub const LINON_OPT_BLOCK: c_int = 2;
+pub const LINON_OPT_CTAS_PER_SM: c_int = 3;
+pub const LINON_OPT_REFILL_MIN: c_int = 4;
+pub const LINON_OPT_FACE_UNROLL: c_int = 5;
+pub const LINON_OPT_MAX_REGS: c_int = 6;
+pub const LINON_OPT_PROFILE: c_int = 7;
+pub const LINON_OPT_CULL: c_int = 8;
+pub const LINON_OPT_PAIR_MIN_BLOCKS: c_int = 9;
+pub const LINON_OPT_SPECIALIZE: c_int = 10;
+pub const LINON_OPT_FORCE_BVH: c_int = 11;
+pub const LINON_OPT_QUIET_ZONE: c_int = 12; // 2 (default): fixed-step and adaptive frames
+pub const LINON_OPT_QUIET_RADIUS: c_int = 13; // 1500 (default); 0 = the saturation radius
+pub const LINON_OPT_OVERLAY_KERNEL: c_int = 14; // 0 staged, 1 direct, 2 TMA tile (default)
+pub const LINON_OPT_COLLAPSE_RUNS: c_int = 15; // 1 (default): long straight runs taken binade by binade
+
 extern "C" {
     pub fn linon_create(device: c_int, width: u32, height: u32, out: *mut *mut linon_view) -> c_int;
     pub fn linon_destroy(v: *mut linon_view);
@@ -103,6 +121,9 @@ extern "C" {
     pub fn linon_set_field_function(v: *mut linon_view, wgsl_body: *const c_char, err: *mut c_char, err_len: usize) -> c_int;
     /// reload_shader(device, Some(new_src), ..): the helper layer of an edited main_view.wgsl; NULL / "" = stock module
     pub fn linon_reload_shader_source(v: *mut linon_view, wgsl_module_source: *const c_char, err: *mut c_char, err_len: usize) -> c_int;
+    /// reload_shader(device, Some(new_src), field_function) as one step: module and body validated and committed together
+    pub fn linon_reload_shader(v: *mut linon_view, wgsl_module_source: *const c_char, wgsl_body: *const c_char, err: *mut c_char,
+                               err_len: usize) -> c_int;
     pub fn linon_module_overrides(v: *mut linon_view, names: *mut c_char, names_len: usize) -> c_int;
     pub fn linon_render(v: *mut linon_view, flags: u32) -> c_int;
     pub fn linon_sync(v: *mut linon_view) -> c_int;

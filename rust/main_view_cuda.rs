@@ -111,10 +111,12 @@ impl MainView {
     /// backface_culling, use_lighting, linear_mode, the light constants, adaptive_sampling, sample_outline_rays, the step /
     /// horizon / step-control literals); any other edit to the march is an Err naming the declaration, and nothing changes
     /// on any Err (:677-679).
-    pub fn reload_compute_shader(&mut self, new_src: &str) -> Result<(), String> {
+    pub fn reload_compute_shader(&mut self, new_src: &str, field_function: &str) -> Result<(), String> {
         let src = CString::new(new_src).map_err(|e| e.to_string())?;
+        let body = CString::new(field_function).map_err(|e| e.to_string())?;
         let mut err = vec![0u8; 16384];
-        let rc = unsafe { sys::linon_reload_shader_source(self.view, src.as_ptr(), err.as_mut_ptr() as *mut _, err.len()) };
+        // module and body together, like :649-690 compiles them: both are committed or neither is
+        let rc = unsafe { sys::linon_reload_shader(self.view, src.as_ptr(), body.as_ptr(), err.as_mut_ptr() as *mut _, err.len()) };
         if rc != sys::LINON_OK {
             let end = err.iter().position(|&b| b == 0).unwrap_or(err.len());
             return Err(String::from_utf8_lossy(&err[..end]).into_owned());
