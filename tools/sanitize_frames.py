@@ -18,6 +18,7 @@ from linon_b200 import _capi as capi  # noqa: E402
 from linon_b200.main_view import MainView, PredefinedFunction, default_scene, make_settings  # noqa: E402
 
 small = "--small" in sys.argv
+enhance = not small or "--enhance" in sys.argv  # the 5 001-step frame: window resolve and collapsed runs of the quiet zone
 W, H = (40, 24) if small else (72, 48)
 verts, faces, center = default_scene()
 bad = 0
@@ -32,7 +33,7 @@ with MainView(verts, faces, center, W, H) as mv:
     for fn in (PredefinedFunction.MirageSphericalSigmoid, PredefinedFunction.Rotation):
         mv.reload_shader(fn.to_code())
         for flags, name in ((0, "adaptive"), (capi.RENDER_ADAPTIVE_OFF, "fixed"), (capi.RENDER_ENHANCE, "enhance")):
-            if flags == capi.RENDER_ENHANCE and (small or fn != PredefinedFunction.MirageSphericalSigmoid):
+            if flags == capi.RENDER_ENHANCE and (not enhance or fn != PredefinedFunction.MirageSphericalSigmoid):
                 continue
             ref = None
             for kernel in (capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL):
