@@ -66,3 +66,26 @@ def test_reference_arm_uses_every_core_under_torchrun():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert line["config"] == bench.workload_config(2, *bench.workload_size(2))
+
+
+def test_the_committed_march_captures_are_of_the_kernels_this_tree_builds(tmp_path):
+    """bench.py refuses an ncu capture whose code hash is not the running kernel's.  NVRTC's output for one source text and one
+    option list is the same on every host (this container without a GPU and every B200 box of rounds' calls produced the same
+    two hashes), so the tie can be checked here: the headline variant (C3: MirageSphericalSigmoid, Enhance, fast math, quiet
+    zone, collapsed runs) and its step-by-step twin, compiled by this tree in a fresh process, hash to what
+    profiles/r2_march_c3*.json say they profiled.  A change to the march template without a new capture fails here first."""
+    code = (
+        "import os\n"
+        "from linon_b200 import _capi as capi\n"
+        "from linon_b200.main_view import PredefinedFunction as P, compile_check\n"
+        "for collapse in ('1', '0'):\n"
+        "    os.environ.update(LINON_CHECK_QUIET_ZONE='2', LINON_CHECK_COLLAPSE=collapse)\n"
+        "    compile_check(P.MirageSphericalSigmoid.to_code(), flags=capi.RENDER_ENHANCE, math_mode=capi.MATH_FAST)\n"
+        "    print(open(os.environ['LINON_DUMP_CUBIN_HASH']).read().strip())\n")
+    env = dict(os.environ, LINON_DUMP_CUBIN_HASH=str(tmp_path / "h.txt"), PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    built = r.stdout.strip().splitlines()[-2:]
+    for path, h in zip((bench.MARCH_PROFILE, bench.MARCH_PROFILE_STEP_BY_STEP), built):
+        committed = [k["cubin_hash"] for k in json.load(open(path)) if k.get("kernel") == "linon_march_tiles"]
+        assert committed == [h], (path, committed, h)
