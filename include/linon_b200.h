@@ -214,7 +214,13 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
  * Also hot-reloaded: the march-level CONSTANTS of the module - eps, backface_culling, use_lighting, linear_mode, light_color,
  * ambient_strength, shininess (src/main_view.wgsl:65-76), adaptive_sampling and sample_outline_rays (:227, :337) and the VALUES
  * of the step size, horizon and step-control literals of nonlinear_ray_color / sample_rays (:241-267, :287-288) - which
- * become macros of the kernel template (a changed h_initial disables Enhance's text replacement, like in the reference). */
+ * become macros of the kernel template (a changed h_initial disables Enhance's text replacement, like in the reference).
+ * Also hot-reloaded: the SHADING BLOCK of ray_color (`if (t > 0.0 && t < max_dist) { ... }`, :199-218) - the statements that
+ * turn the nearest hit into a colour.  When ray_color differs from the reference's inside that block only (the face loop must
+ * stay the reference's, token for token: it is the kernel's own intersection code), the block is translated from the user's
+ * text and called at every geometric hit with ray_color's live values (origin, direction, max_dist, t, d1, d2) and the module's
+ * constants; the march accepts the hit when the returned alpha is positive (`has_color = result.color.a > 0.0`, :262-263) and
+ * keeps marching otherwise, like the reference.  Such a module runs the generic translation of the field function. */
 int linon_reload_shader_source(linon_view* v, const char* wgsl_module_source, char* err, size_t err_len);
 /* MainView::reload_shader(device, Some(new_src), field_function) as ONE step (:649-690 compiles new_src with the new field
  * function spliced in): the module and the body are validated together and committed together, or neither is - a helper

@@ -670,6 +670,39 @@ __device__ __forceinline__ vec3f shade(const float4* __restrict__ s_tri, int id,
 #endif
 }
 
+// A hit the shader accepts: `result.color = ray_color(..); has_color = result.color.a > 0.0`, src/main_view.wgsl:262-263.  The
+// stock shading block returns alpha = t > 0 (or 1 without lighting), so every geometric hit is accepted and this is shade().
+// LINON_USER_SHADE (linon_reload_shader with an edited shading block of ray_color, src/main_view.wgsl:199-218): the block is
+// the user's text, translated to LinonField<float>::linon_ray_color_shade (wgsl_translate.cpp), and decides by its own alpha -
+// a hit it declines (alpha <= 0, or no return: ray_color's final `return vec4(0)`) leaves the ray marching, like the reference.
+__device__ __forceinline__ bool shade_hit(const float4* __restrict__ s_tri, int id, vec3f origin, vec3f direction, float max_dist,
+                                          float t_hit, vec3f& color, float& alpha) {
+#ifdef LINON_USER_SHADE
+    const float4 b = s_tri[3 * id + 1], c = s_tri[3 * id + 2];
+    const vec4f r = LinonField<float>::linon_ray_color_shade(origin, direction, max_dist, t_hit, vec3f(b.x, b.y, b.z),
+                                                             vec3f(c.x, c.y, c.z));
+    alpha = r.w;
+    color = vec3f(r.x, r.y, r.z);
+    return r.w > 0.0f;
+#else
+    color = shade(s_tri, id, direction);
+    alpha = LINON_USE_LIGHTING ? t_hit : 1.0f;
+    return true;
+#endif
+}
+__device__ __forceinline__ bool shade_hit(const float4* __restrict__ s_tri, int id, vec3f origin, vec3f direction, float max_dist,
+                                          float t_hit, vec3f& color) {
+    float alpha;
+#ifdef LINON_USER_SHADE
+    vec3f c;
+    if (!shade_hit(s_tri, id, origin, direction, max_dist, t_hit, c, alpha)) return false;  // `color` keeps its value: only
+    color = c;                                                                               // has_color makes it count
+    return true;
+#else
+    return shade_hit(s_tri, id, origin, direction, max_dist, t_hit, color, alpha);
+#endif
+}
+
 // rgba8unorm store conversion: clamp to [0,1], x255, round to nearest even; NaN -> 0.
 __device__ __forceinline__ unsigned char unorm8(float x) {
     x = fminf(fmaxf(x, 0.0f), 1.0f);  // fmaxf(NaN, 0) = 0
@@ -908,10 +941,18 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         uchar4 c = make_uchar4(0, 0, 0, 0);
         int hit = -1;
         if (t_hit > 0.0f && t_hit < 100.0f) {
+#ifdef LINON_USER_SHADE
+            vec3f rgb;
+            float alpha;
+            shade_hit(s_tri, id, r.p, r.dir, 100.0f, t_hit, rgb, alpha);  // stored whatever its alpha says, :369-370
+            c = pack_color(rgb);
+            c.w = unorm8(alpha);
+#else
             const vec3f rgb = shade(s_tri, id, r.dir);
             c = pack_color(rgb);
 #if LINON_USE_LIGHTING
             c.w = unorm8(t_hit);  // vec4<f32>(result, t), src/main_view.wgsl:217
+#endif
 #endif
             hit = LINON_FACE_ID(s_tri, id);
         }
@@ -1047,8 +1088,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                                     intersect_mesh(s_tri, s_range, P.bvh, pj, w_dirn, w_max_dist, p_l1, t_hit, id, plane_nearest,
                                                    cnt.face_tests, box_nearest > reach_up, box_nearest);
                                     nearest = fmaxf(nearest, plane_nearest);
-                                    if (t_hit > 0.0f && t_hit < w_max_dist) {
-                                        color = shade(s_tri, id, w_dirn);
+                                    if (t_hit > 0.0f && t_hit < w_max_dist && shade_hit(s_tri, id, pj, w_dirn, w_max_dist, t_hit, color)) {
                                         hit = LINON_FACE_ID(s_tri, id);
                                         has_color = true;
                                         cnt.prehit = i + jc + 1;  // the hit belongs to step i + jc
@@ -1153,8 +1193,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                         // both are lower bounds of the distance to the geometry: keep the better one (inside a cluster's
                         // box the first-pass bound is 0 and the plane distances take over)
                         nearest = fmaxf(nearest, plane_nearest);
-                        if (t_hit > 0.0f && t_hit < max_dist) {
-                            color = shade(s_tri, id, dirn);
+                        if (t_hit > 0.0f && t_hit < max_dist && shade_hit(s_tri, id, r.p, dirn, max_dist, t_hit, color)) {
                             hit = LINON_FACE_ID(s_tri, id);
                             has_color = true;        // result.color.a = t > 0
                             cnt.prehit = i + 1;      // accepted steps that ran the pre-hit path, this one included
@@ -1256,8 +1295,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                     ++cnt.checks;
                     sd.checked(nearest, p_l1, P.plane_w_max);
-                    if (t_hit > 0.0f && t_hit < max_dist) {
-                        color = shade(s_tri, id, dirn);
+                    if (t_hit > 0.0f && t_hit < max_dist && shade_hit(s_tri, id, r.p, dirn, max_dist, t_hit, color)) {
                         hit = LINON_FACE_ID(s_tri, id);
                         has_color = true;           // result.color.a = t > 0
                         cnt.prehit = cnt.accepted + 1;  // accepted steps that ran the pre-hit path, this one included
@@ -1326,9 +1364,8 @@ __device__ __forceinline__ void pair_prehit(const float4* __restrict__ s_tri, co
         cnt.face_tests += __float_as_uint(r.w);
         ++cnt.checks;
         px.sd.checked(r.z, p_l1, plane_w_max);
-        if (r.x > 0.0f && r.x < max_dist) {
-            const int id = __float_as_int(r.y);
-            px.color = shade(s_tri, id, dirn);
+        const int id = __float_as_int(r.y);
+        if (r.x > 0.0f && r.x < max_dist && shade_hit(s_tri, id, p, dirn, max_dist, r.x, px.color)) {
             px.hit = id;
             px.has_color = true;
             px.prehit = step_index + 1;  // accepted steps that ran the pre-hit path, this one included
@@ -1563,8 +1600,7 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                         intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                         ++cnt.checks;
                         sd.checked(nearest, p_l1, P.plane_w_max);
-                        if (t_hit > 0.0f && t_hit < max_dist) {
-                            color = shade(s_tri, id, dirn);
+                        if (t_hit > 0.0f && t_hit < max_dist && shade_hit(s_tri, id, r.p, dirn, max_dist, t_hit, color)) {
                             hit = LINON_FACE_ID(s_tri, id);
                             has_color = true;
                             cnt.prehit += steps + 1;
@@ -1658,9 +1694,10 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
                     intersect_mesh(s_tri, s_range, P.bvh, r.p, dirn, max_dist, p_l1, t_hit, id, nearest, cnt.face_tests);
                     ++cnt.checks;
                     sd.checked(nearest, p_l1, P.plane_w_max);
-                    hit_now = t_hit > 0.0f && t_hit < max_dist;
+                    vec3f rgb;
+                    hit_now = t_hit > 0.0f && t_hit < max_dist && shade_hit(s_tri, id, r.p, dirn, max_dist, t_hit, rgb);
                     if (hit_now) {
-                        P.raycast[pix] = pack_color(shade(s_tri, id, dirn));
+                        P.raycast[pix] = pack_color(rgb);
                         P.hit_id[pix] = LINON_FACE_ID(s_tri, id);
                     }
                 }

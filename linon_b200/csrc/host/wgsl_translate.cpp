@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -1083,6 +1084,8 @@ const Pristine kPristine[] = {
     {"", "", 0, 0}};
 // the numeric literals of the reference's nonlinear_ray_color and sample_rays in order of appearance (values only)
 #include "module_literals.inc"
+// ray_color with the statements of its shading block removed (src/main_view.wgsl:177-220 without :200-217)
+#include "module_shade.inc"
 
 // library helpers a field function may call (README.md:37-44): an edited version overrides the prelude's
 const char* const kLibraryHelpers[] = {"rotateX", "rotateY", "rotateZ", "translate", "refraction_index", "refraction",
@@ -1366,7 +1369,8 @@ bool const_value(const std::vector<Tok>& t, const RawItem& it, std::vector<doubl
 
 // A pristine-named module constant with another value: true = mapped to the kernel template (layer updated); false with
 // err empty = not a constant this path knows; false with err set = known but outside the supported range.
-bool apply_march_const(const std::vector<Tok>& t, const RawItem& it, ModuleLayer& layer, std::string& err) {
+bool apply_march_const(const std::vector<Tok>& t, const RawItem& it, ModuleLayer& layer, std::string& err,
+                       std::map<std::string, std::string>& values) {
     const std::string& name = it.info.name;
     std::vector<double> n;
     std::vector<std::string> id;
@@ -1396,6 +1400,7 @@ bool apply_march_const(const std::vector<Tok>& t, const RawItem& it, ModuleLayer
         }
         if (name == "adaptive_sampling") layer.adaptive_sampling = b ? 1 : 0;
         if (name == "sample_outline_rays") layer.sample_outline_rays = b ? 1 : 0;
+        values[name] = b ? "true" : "false";
     } else if (name == "eps" || name == "ambient_strength" || name == "shininess") {
         if (n.size() != 1 || !std::isfinite(n[0])) return false;
         if (name == "eps") {
@@ -1408,6 +1413,7 @@ bool apply_march_const(const std::vector<Tok>& t, const RawItem& it, ModuleLayer
             if (!(n[0] >= 0.0 && n[0] <= 1e4)) return out_of_range("0 <= shininess <= 10000");
             layer.march_defines += "#define LINON_SHININESS " + f32_literal(n[0]) + "\n";
         }
+        values[name] = f32_literal(n[0]);
     } else if (name == "light_color" || name == "object_color") {
         if (n.size() != 3 && n.size() != 1) return false;
         if (n.size() == 1) n = {n[0], n[0], n[0]};  // vec3<f32>(x) splats
@@ -1417,6 +1423,7 @@ bool apply_march_const(const std::vector<Tok>& t, const RawItem& it, ModuleLayer
             layer.march_defines += "#define LINON_LIGHT_R " + f32_literal(n[0]) + "\n#define LINON_LIGHT_G " + f32_literal(n[1]) +
                                    "\n#define LINON_LIGHT_B " + f32_literal(n[2]) + "\n";
         // object_color is declared and never used by the reference's shader: any value renders the same frame
+        values[name] = "vec3f(" + f32_literal(n[0]) + ", " + f32_literal(n[1]) + ", " + f32_literal(n[2]) + ")";
     } else {
         return false;
     }
@@ -1488,6 +1495,96 @@ bool apply_march_literals(const RawItem& it, ModuleLayer& layer, std::string& er
     return true;
 }
 
+
+// ray_color edited inside its shading block only (`if (t > 0.0 && t < max_dist) { ... }`, src/main_view.wgsl:199-218 - the last
+// `if` of the function): locates the block in the user's text.  The tokens outside it must hash to the reference's.
+bool find_shade_block(const std::vector<Tok>& t, const RawItem& it, int& open, int& close) {
+    auto is_p = [&](int i, const char* p) { return t[i].kind == PUNCT && t[i].text == p; };
+    int depth = 0, last_if = -1;
+    for (int j = it.brace_open + 1; j < it.brace_close; ++j) {
+        if (is_p(j, "{") || is_p(j, "(") || is_p(j, "[")) ++depth;
+        if (is_p(j, "}") || is_p(j, ")") || is_p(j, "]")) --depth;
+        if (depth == 0 && t[j].kind == IDENT && t[j].text == "if") last_if = j;
+    }
+    if (last_if < 0) return false;
+    int j = last_if + 1;
+    while (j < it.brace_close && !is_p(j, "(")) ++j;
+    for (depth = 0; j < it.brace_close; ++j) {  // the condition
+        if (is_p(j, "(")) ++depth;
+        if (is_p(j, ")") && --depth == 0) break;
+    }
+    ++j;
+    while (j < it.brace_close && (t[j].kind == WS || t[j].kind == NL)) ++j;
+    if (j >= it.brace_close || !is_p(j, "{")) return false;
+    open = j;
+    for (depth = 0; j < it.brace_close; ++j) {
+        if (is_p(j, "{")) ++depth;
+        if (is_p(j, "}") && --depth == 0) break;
+    }
+    if (j >= it.brace_close) return false;
+    close = j;
+    uint64_t h = 1469598103934665603ull;
+    for (int k = it.begin; k < it.end; ++k) {
+        if (k > open && k < close) continue;
+        if (t[k].kind == WS || t[k].kind == NL) continue;
+        h = fnv1a(h, t[k].text);
+    }
+    return h == kRayColorRestHash;
+}
+
+// The user's shading block as a member of LinonField<S>: `vec4f linon_ray_color_shade(origin, direction, max_dist, t, d1, d2)`
+// (march_kernels.cuh: shade_hit calls it at every geometric hit).  The variables of ray_color that are live in the block
+// (t, d1, d2: the nearest hit and its triangle's edges) arrive as values; the module's march-level constants are declared
+// with the values of the user's module (const_values) or the reference's; a block that falls through returns ray_color's
+// final `vec4<f32>(0.0, 0.0, 0.0, 0.0)`.
+bool emit_shade_block(const std::vector<Tok>& t, const RawItem& it, int open, int close, const std::string& preamble,
+                      std::set<std::string> module_names, const std::map<std::string, std::string>& const_values, std::string& out,
+                      std::string& err) {
+    std::string block;
+    for (int j = open + 1; j < close; ++j) block += t[j].text;
+    int line = it.info.line;
+    for (int j = it.begin; j < open; ++j)
+        if (t[j].kind == NL) ++line;
+    const std::string text =
+        "fn linon_ray_color_shade(origin: vec3<f32>, direction: vec3<f32>, max_dist: f32, linon_t: f32, linon_d1: vec3<f32>, "
+        "linon_d2: vec3<f32>) -> vec4<f32> { var t: f32 = linon_t; var d1: vec3<f32> = linon_d1; var d2: vec3<f32> = linon_d2; " +
+        block + "\nreturn vec4<f32>(0.0, 0.0, 0.0, 0.0);\n}\n";
+    Lexer lx(text);
+    if (!lx.run()) {
+        err = "ray_color: " + lx.err;
+        return false;
+    }
+    std::vector<RawItem> items;
+    if (!split_module(lx.out, items, err) || items.size() != 1 || items[0].info.kind != "fn") {
+        err = "ray_color: the shading block does not parse as statements" + (err.empty() ? std::string() : " (" + err + ")");
+        return false;
+    }
+    items[0].info.line = line;  // diagnostics cite the user's main_view.wgsl lines: the header above sits on the block's `{` line
+    items[0].info.name = "ray_color";
+    struct Default { const char* name; const char* type; const char* value; };
+    static const Default kDefaults[] = {  // src/main_view.wgsl:65-74, :227, :337
+        {"backface_culling", "bool", "false"}, {"light_color", "vec3f", "vec3f(1.0f, 1.0f, 1.0f)"},
+        {"ambient_strength", "wg_f32", "(0.01f)"}, {"shininess", "wg_f32", "(64.0f)"},
+        {"object_color", "vec3f", "vec3f(0.5f, 0.5f, 0.5f)"}, {"linear_mode", "bool", "false"}, {"use_lighting", "bool", "true"},
+        {"eps", "wg_f32", "(0.0000001f)"}, {"adaptive_sampling", "bool", "true"}, {"sample_outline_rays", "bool", "false"}};
+    std::string consts;
+    for (const Default& d : kDefaults) {
+        const auto v = const_values.find(d.name);
+        consts += std::string("const ") + d.type + " " + d.name + " = " + (v != const_values.end() ? v->second : std::string(d.value)) + "; ";
+        module_names.insert(d.name);
+    }
+    std::string member;
+    if (!emit_function(lx.out, items[0], preamble + consts, module_names, member, err)) return false;
+    const size_t at = member.find(" ray_color(");
+    if (at == std::string::npos) {
+        err = "ray_color: internal error while emitting the shading block";
+        return false;
+    }
+    member.replace(at, std::strlen(" ray_color("), " linon_ray_color_shade(");
+    out += member;
+    return true;
+}
+
 }  // namespace
 
 bool scan_wgsl_module(const std::string& src, std::vector<ModuleItem>& items, std::string& error) {
@@ -1523,6 +1620,8 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
     }
     // ---- classify ---------------------------------------------------------------------------------------------------
     std::vector<int> emit_fn, emit_const, unchanged_helpers;
+    std::map<std::string, std::string> const_values;  // march-level constants the module edits, as CUDA expressions
+    int shade_item = -1, shade_open = -1, shade_close = -1;
     for (int k = 0; k < (int)items.size(); ++k) {
         const RawItem& it = items[k];
         const std::string& kind = it.info.kind;
@@ -1550,10 +1649,21 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
             emit_const.push_back(k);
             continue;
         }
+        // ray_color edited in its shading block only: the block is translated from the user's text (after the loop, when
+        // the constants of the whole module are known)
+        if (kind == "fn" && name == "ray_color" && p) {
+            int bo = -1, bc = -1;
+            if (find_shade_block(t, it, bo, bc)) {
+                shade_item = k;
+                shade_open = bo;
+                shade_close = bc;
+                continue;
+            }
+        }
         // march-level constants and literals: mapped to macros of the kernel template (march_kernels.cuh)
         {
             std::string merr;
-            if (kind == "const" && p && apply_march_const(t, it, layer, merr)) continue;
+            if (kind == "const" && p && apply_march_const(t, it, layer, merr, const_values)) continue;
             if (kind == "fn" && p && p->masked_hash == it.info.masked_hash && apply_march_literals(it, layer, merr)) continue;
             if (!merr.empty()) {
                 unsupported = true;
@@ -1609,6 +1719,15 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
             return false;
         }
         layer.names += (layer.names.empty() ? "" : ",") + items[k].info.name;
+    }
+    if (shade_item >= 0) {
+        if (!emit_shade_block(t, items[shade_item], shade_open, shade_close, layer.preamble, module_names, const_values,
+                              layer.members, err)) {
+            error = "WGSL module error: " + err;
+            return false;
+        }
+        layer.march_defines += "#define LINON_USER_SHADE 1\n";
+        layer.names += (layer.names.empty() ? "" : ",") + std::string("ray_color");
     }
     return true;
 }

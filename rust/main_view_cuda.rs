@@ -109,7 +109,8 @@ impl MainView {
     /// (src/application.rs:228-232) when the watcher on src/main_view.wgsl fires (src/main.rs:206-222): the CUDA path
     /// installs the module's helper layer (new / edited helper functions and constants) and its march-level constants (eps,
     /// backface_culling, use_lighting, linear_mode, the light constants, adaptive_sampling, sample_outline_rays, the step /
-    /// horizon / step-control literals); any other edit to the march is an Err naming the declaration, and nothing changes
+    /// horizon / step-control literals) and the shading block of ray_color (translated from the user's text); any other edit
+    /// to the march is an Err naming the declaration, and nothing changes
     /// on any Err (:677-679).
     pub fn reload_compute_shader(&mut self, new_src: &str, field_function: &str) -> Result<(), String> {
         let src = CString::new(new_src).map_err(|e| e.to_string())?;

@@ -15,6 +15,44 @@ CASES = {
 }
 W, H = 64, 48
 
+# Edits INSIDE the shading block of ray_color (src/main_view.wgsl:199-218), which the CUDA path translates from the user's
+# text.  Such a module has to carry the whole function (its face loop must be the reference's, token for token), so these
+# cases exist as text only where the reference is mounted: tests/golden/make_march_edits.py writes the edited modules to
+# tests/golden/_shade_modules/ (git-ignored: they are the reference's source) next to the frames it commits.
+_NORMAL = "        let normal = normalize(cross(d1, d2));\n"
+SHADE_CASES = {
+    "tint": [("let result = (ambient + diffuse + specular) * abs(normal);",
+              "let result = (ambient + 0.5 * diffuse + specular) * abs(normal) + vec3<f32>(0.1, 0.0, 0.05);")],
+    "noop": [(_NORMAL, _NORMAL + "        let unused = 2.0 * t;\n")],
+    # a hit the shader declines (alpha 0): the reference keeps marching through that wall (has_color = color.a > 0.0, :262-263)
+    "declined": [(_NORMAL, _NORMAL + "        if (abs(normal.x) > 0.5) {\n            return vec4<f32>(1.0, 0.0, 0.0, 0.0);\n        }\n")],
+    "depth": [("        let ambient = ambient_strength * light_color;\n",
+               "        return vec4<f32>(vec3<f32>(t / max_dist, shininess / 128.0, ambient_strength), 1.0);\n"
+               "        let ambient = ambient_strength * light_color;\n"),
+              ("const shininess: f32 = 64.0;", "const shininess: f32 = 32.0;")],
+    "linear_shade": [("const linear_mode: bool = false;", "const linear_mode: bool = true;"),
+                     ("return vec4<f32>(result, t);", "return vec4<f32>(result.zyx, 0.5 * t);")],
+}
+SHADE_MODULE_DIR = "_shade_modules"
+
+
+def edited_reference_module(reference_root, edits):
+    import os
+    text = open(os.path.join(reference_root, "src", "main_view.wgsl"), encoding="utf-8").read()
+    for old, new in edits:
+        assert old in text, old
+        text = text.replace(old, new)
+    return text
+
+
+def shade_module_text(name, reference_root="/root/reference"):
+    """The edited module of a SHADE case: from the mounted reference, else from the scratch copy the generator left; None if neither."""
+    import os
+    if os.path.isdir(os.path.join(reference_root, "src")):
+        return edited_reference_module(reference_root, SHADE_CASES[name])
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", SHADE_MODULE_DIR, name + ".wgsl")
+    return open(p, encoding="utf-8").read() if os.path.exists(p) else None
+
 
 def partial_module(name):
     return "\n".join(new for _, new in CASES[name])

@@ -530,6 +530,80 @@ def test_main_view_mirror_follows_the_reference(product_lib, scene):
         assert (mv.hit_ids() >= 0).any()
 
 
+@pytest.mark.parametrize("name", ["tint", "noop", "declined", "depth", "linear_shade"])
+def test_an_edited_shading_block_hot_reloads_against_the_edited_reference_shader(product_lib, scene, name):
+    """ray_color edited inside its shading block (src/main_view.wgsl:199-218): the block is translated from the user's text and
+    called at every geometric hit (march_kernels.cuh: shade_hit); a hit the block declines (alpha <= 0) leaves the ray marching
+    like `has_color = result.color.a > 0.0` (:262-263).  Frames equal tests/golden/march_edits.npz - the REFERENCE's shader with
+    the same edit, transpiled and run on the CPU - endpoints bit for bit in strict math, colours within 1/255, every march
+    kernel.  The module text is the reference's own file with the edit: available where the reference is mounted or where
+    tests/golden/make_march_edits.py left its scratch copies; skipped elsewhere (the CPU suite runs the same comparison on
+    the emulated device code, tests/test_march_edits_cpu.py)."""
+    import march_edit_cases as mc
+    module = mc.shade_module_text(name)
+    if module is None:
+        pytest.skip("needs the text of the reference's ray_color (mount or tests/golden/_shade_modules)")
+    verts, faces, center = scene
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "march_edits.npz"))
+    fn = PredefinedFunction.MirageSpherical
+    with MainView(verts, faces, center, mc.W, mc.H) as mv:
+        mv.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+        mv.reload_shader(fn.to_code())
+        mv.update_settings(make_settings())
+        mv.render_flags(0)
+        mv.sync()
+        stock = mv.mapping_texture().copy(), mv.ray_casting_texture().copy()
+        mv.reload_compute_shader(module)
+        assert "ray_color" in mv.module_overrides()
+        frames = []
+        for kernel in (capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL):
+            mv.set_option(capi.OPT_KERNEL, kernel)
+            mv.render_flags(0)
+            mv.sync()
+            frames.append((mv.ray_casting_texture(), mv.mapping_texture(), mv.hit_ids()))
+        rgba8, endpoint, hit = frames[0]
+        assert np.abs(rgba8.astype(int) - z[f"rgba8_{name}"].astype(int)).max() <= 1
+        if name == "linear_shade":
+            assert np.array_equal(endpoint, stock[0])  # `mapping` is not written in linear mode
+        else:
+            assert np.array_equal(endpoint.view(np.uint32), z[f"endpoint_{name}"].view(np.uint32))
+        if name == "noop":
+            assert np.array_equal(rgba8, stock[1])     # the reference's own block through the translator: the stock frame
+        else:
+            assert not np.array_equal(rgba8, stock[1])
+        if name == "declined":
+            # rays pass through the two side walls: 43 % of the pixels end on a surface instead of 63 %
+            assert 0 < (hit >= 0).sum() < 0.8 * (z["rgba8_tint"][..., :3].max(axis=-1) > 0).sum()
+        for r, e, h in frames[1:]:
+            assert np.array_equal(r, rgba8) and np.array_equal(e.view(np.uint32), endpoint.view(np.uint32)) and np.array_equal(h, hit)
+        # fixed-step frames with and without culling agree (a declined hit does not disturb the safe-distance budgets)
+        per_cull = []
+        for cull in (1, 0):
+            mv.set_option(capi.OPT_KERNEL, capi.KERNEL_TILES)
+            mv.set_option(capi.OPT_CULL, cull)
+            mv.render_flags(capi.RENDER_ADAPTIVE_OFF)
+            mv.sync()
+            per_cull.append((mv.ray_casting_texture(), mv.mapping_texture()))
+        mv.set_option(capi.OPT_CULL, 1)
+        if name != "linear_shade":
+            assert np.array_equal(per_cull[0][0], per_cull[1][0]) and np.array_equal(per_cull[0][1].view(np.uint32), per_cull[1][1].view(np.uint32))
+        # production math with the edit: same surfaces; colours within 1/255 of the strict frame - except "depth", whose red
+        # channel is t / max_dist: where inside its step a ray meets the wall, which in an adaptive frame follows the step
+        # sequence and with it rounding noise (SURVEY F20; 45 % agreement measured)
+        mv.set_option(capi.OPT_MATH, capi.MATH_FAST)
+        mv.render_flags(0)
+        mv.sync()
+        fast = mv.ray_casting_texture()
+        assert (mv.hit_ids() == hit).mean() >= 0.98
+        if name != "depth":
+            assert (np.abs(fast.astype(int) - rgba8.astype(int)).max(axis=-1) <= 1).mean() >= 0.99
+        mv.reload_compute_shader(None)
+        mv.set_option(capi.OPT_MATH, capi.MATH_STRICT)
+        mv.render_flags(0)
+        mv.sync()
+        assert np.array_equal(mv.ray_casting_texture(), stock[1])    # back to the stock module
+
+
 @pytest.mark.parametrize("name", ["eps", "backface_culling", "use_lighting", "light", "linear_mode", "adaptive_sampling"])
 def test_march_level_constants_hot_reload_against_the_edited_reference_shader(product_lib, scene, name):
     """The file watcher path (src/main.rs:206-222) with an edit to a march-level constant of main_view.wgsl

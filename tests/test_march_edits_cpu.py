@@ -38,6 +38,12 @@ FN_EDITS = [
     ("sample rays", [("    let h = 0.001;\n    let steps: i32 = 5000;", "    let h = 0.002;\n    let steps: i32 = 2500;")], "#define LINON_SAMPLE_STEPS 2500"),
 ]
 
+# edits INSIDE the shading block of ray_color (src/main_view.wgsl:199-218): the block is translated from the user's text
+import march_edit_cases as mc  # noqa: E402
+
+_EXPECT = {"depth": "const wg_f32 shininess = (32.0f)"}
+SHADE_EDITS = [(name, edits, _EXPECT.get(name, "linon_ray_color_shade")) for name, edits in mc.SHADE_CASES.items()]
+
 
 def partial_module(edits):
     """A module that only holds the edited declarations (modules need not repeat what they leave alone)."""
@@ -118,8 +124,44 @@ def _ref_frame(body, edits, variant, verts, faces, cam, st):
     return out
 
 
+@pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's ray_color")
+@pytest.mark.parametrize("name,edits,expect", SHADE_EDITS, ids=[e[0] for e in SHADE_EDITS])
+def test_edits_of_the_shading_block_are_translated(product_lib, name, edits, expect):
+    text, names = translate_wgsl_module(reference_module(edits))
+    assert expect in text and "#define LINON_USER_SHADE 1" in text, text
+    assert "ray_color" in names
+    assert compile_check(PF.MirageSpherical.to_code(), flags=0, math_mode=capi.MATH_FAST, module_src=reference_module(edits)) > 100_000
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's ray_color")
+def test_a_partial_module_may_hold_ray_color_alone(product_lib):
+    full = reference_module(SHADE_EDITS[0][1])
+    fn = full[full.index("fn ray_color("):full.index("struct NonlinearRayColorResult")]
+    text, names = translate_wgsl_module(fn + "\nconst ambient_strength: f32 = 0.25;\n")
+    assert "const wg_f32 ambient_strength = (0.25f)" in text and set(names) == {"ray_color", "ambient_strength"}
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's ray_color")
+@pytest.mark.parametrize("edits,needle", [
+    # the face loop of ray_color is the kernel's own intersection code: still refused
+    ([("(t < 0.0 || t_new < t)) {", "(t < 0.0 || t_new <= t)) {")], "was edited"),
+    ([("    return vec4<f32>(0.0, 0.0, 0.0, 0.0);\n}\n\nstruct NonlinearRayColorResult", "    return vec4<f32>(0.0, 0.0, 0.0, 1.0);\n}\n\nstruct NonlinearRayColorResult")], "was edited"),
+])
+def test_edits_of_ray_color_outside_the_shading_block_are_refused(product_lib, edits, needle):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl_module(reference_module(edits))
+    assert e.value.code == capi.ERR_UNSUPPORTED and needle in e.value.message, e.value.message
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's ray_color")
+def test_an_error_inside_the_shading_block_cites_the_modules_line(product_lib):
+    with pytest.raises(LinonError) as e:
+        translate_wgsl_module(reference_module([("let diff = intensity;", "let diff = intensity * faces.data[0].a;")]))
+    assert e.value.code == capi.ERR_COMPILE and "main_view.wgsl(212)" in e.value.message and "faces" in e.value.message, e.value.message
+
+
 @pytest.mark.skipif(not HAS_REF, reason="the reference-side half needs the mount")
-@pytest.mark.parametrize("name,edits,expect", CONST_EDITS + FN_EDITS, ids=[e[0] for e in CONST_EDITS + FN_EDITS])
+@pytest.mark.parametrize("name,edits,expect", CONST_EDITS + FN_EDITS + SHADE_EDITS, ids=[e[0] for e in CONST_EDITS + FN_EDITS + SHADE_EDITS])
 def test_edited_kernel_equals_the_edited_reference_shader(product_lib, name, edits, expect):
     """Strict math on the host emulation of the device code: endpoints and hit pattern bit for bit, colours within 1/255
     (pow: libm here on both sides, the rgba8 rounding is the reference's)."""
@@ -143,7 +185,7 @@ def test_edited_kernel_equals_the_edited_reference_shader(product_lib, name, edi
         return
     got = emu.march(lib, verts, faces, cam, st, W, H)
     assert np.abs(got["rgba8"].astype(int) - ref["rgba8"].astype(int)).max() <= 1, name
-    if name != "linear_mode":  # linear_mode never writes `mapping`
+    if "linear" not in name:  # linear_mode never writes `mapping`
         assert np.array_equal(got["endpoint"].view(np.uint32), ref["endpoint"].view(np.uint32)), name
         assert (got["rgba8"][..., 3] == 255).all()
     else:

@@ -124,6 +124,29 @@ def test_the_hash_table_is_the_reference_module(product_lib):
 
 
 @needs_reference
+def test_the_rest_hash_of_ray_color_is_the_reference_function_without_its_shading_block(product_lib):
+    """module_shade.inc: ray_color of the reference with the statements of `if (t > 0.0 && t < max_dist) { ... }` removed hashes
+    to the committed value - what tells an edit inside the block from one to the face loop (wgsl_translate.cpp)."""
+    src = reference_module()
+    start = src.index("fn ray_color(")
+    cond = src.rindex("if (t > 0.0 && t < max_dist) {", start, src.index("struct NonlinearRayColorResult", start))
+    depth, k = 0, src.index("{", cond)
+    open_brace = k
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[k], 0)
+        if depth == 0:
+            break
+        k += 1
+    emptied = src[:open_brace + 1] + src[k:]
+    h = [it[2] for it in scan_wgsl_module(emptied, full=True) if it[1] == "ray_color"]
+    committed = open(os.path.join(ROOT, "linon_b200", "csrc", "host", "module_shade.inc")).read()
+    assert re.search(r"kRayColorRestHash = 0x([0-9a-f]{16})ull", committed).group(1) == f"{h[0]:016x}"
+    # an emptied block is itself an edit inside the block: accepted, and every hit is declined (ray_color's final return)
+    text, names = translate_wgsl_module(emptied)
+    assert names == ["ray_color"] and "linon_ray_color_shade" in text
+
+
+@needs_reference
 def test_the_unedited_reference_module_installs_nothing(product_lib):
     src = reference_module()
     assert translate_wgsl_module(src) == ("", [])
@@ -144,8 +167,10 @@ def test_an_edited_helper_pulls_in_the_unchanged_helpers_that_call_it(product_li
     assert translate_wgsl_module(src.replace("const PI: f32 = 3.141592653589793;", "const PI: f32 = 3.14;"))[1] == ["PI"]
     assert translate_wgsl_module(src.replace("const shininess: f32 = 64.0;", "const shininess: f32 = 8.0;"))[1] == ["shininess"]
     for old, new, name in (("let f = 1.0 / a;", "let f = 2.0 / a;", "hit_triangle"),
-                           ("let spec = pow(intensity, shininess);", "let spec = pow(intensity, 2.0 * shininess);", "ray_color")):
+                           ("if (t_new > 0.0 && t_new < max_dist", "if (t_new >= 0.0 && t_new < max_dist", "ray_color")):  # its face loop
         assert old in src
         with pytest.raises(LinonError) as e:
             translate_wgsl_module(src.replace(old, new))
         assert e.value.code == capi.ERR_UNSUPPORTED and f"'{name}'" in e.value.message
+    # ... except inside the shading block of ray_color, which is translated from the user's text
+    assert translate_wgsl_module(src.replace("let spec = pow(intensity, shininess);", "let spec = pow(intensity, 2.0 * shininess);"))[1] == ["ray_color"]
