@@ -29,6 +29,7 @@
 //   LINON_COLLAPSE_RUNS / LINON_COLLAPSE_MIN   quiet runs of at least MIN steps are taken binade by binade (advance_coord)
 //   LINON_QUIET_AHEAD    regular quiet steps after a plan that found no run, before the next plan
 //   LINON_EPS, LINON_BACKFACE_CULLING, LINON_USE_LIGHTING, LINON_LINEAR_MODE, LINON_LIGHT_*, LINON_AMBIENT, LINON_SHININESS,
+//   LINON_FOCAL_LENGTH, LINON_VIEWPORT_HEIGHT, LINON_LINEAR_MAX_DIST (literals of main_view), LINON_USER_SHADE,
 //   LINON_T_MAX, LINON_SAMPLE_H, LINON_SAMPLE_STEPS ...   the march-level constants of an edited main_view.wgsl (hot reload)
 //
 // The march kernels share every per-ray device function, so their per-pixel results are bit-identical in strict mode:
@@ -166,6 +167,15 @@
 #ifndef LINON_LINEAR_MODE
 #define LINON_LINEAR_MODE 0            // const linear_mode, :72 (1: one straight ray_color(origin, dir, 100.0) per pixel, no march)
 #endif
+#ifndef LINON_FOCAL_LENGTH
+#define LINON_FOCAL_LENGTH 0.035f      // `let focal_length` of main_view, :355
+#endif
+#ifndef LINON_VIEWPORT_HEIGHT
+#define LINON_VIEWPORT_HEIGHT 0.025f   // `let viewport_height` of main_view, :356
+#endif
+#ifndef LINON_LINEAR_MAX_DIST
+#define LINON_LINEAR_MAX_DIST 100.0f   // the reach of linear_mode's one ray_color call, :369
+#endif
 #ifndef LINON_AMBIENT
 #define LINON_AMBIENT 0.01f            // const ambient_strength, :68
 #endif
@@ -265,8 +275,8 @@ __device__ __forceinline__ vec3t<S> camera_ray_dir(const MarchParams& P, S px, S
     const float aspect_ratio = width / height;
     const vec3f view_direction = ld3(P.cam_view);
     const vec3f up = ld3(P.cam_up);
-    const float focal_length = 0.035f;
-    const float viewport_height = 0.025f;
+    const float focal_length = LINON_FOCAL_LENGTH;
+    const float viewport_height = LINON_VIEWPORT_HEIGHT;
     const float viewport_width = aspect_ratio * viewport_height;
     const vec3f w = -view_direction;
     const vec3f horizontal = w_cross(up, w);
@@ -936,15 +946,15 @@ extern "C" __global__ void __launch_bounds__(LINON_BLOCK, LINON_MIN_BLOCKS) lino
         init_ray(P, x, local_row, r);
         float t_hit, nearest;
         int id;
-        intersect_mesh(s_tri, s_range, P.bvh, r.p, r.dir, 100.0f, l1_norm(r.p), t_hit, id, nearest, cnt.face_tests);
+        intersect_mesh(s_tri, s_range, P.bvh, r.p, r.dir, LINON_LINEAR_MAX_DIST, l1_norm(r.p), t_hit, id, nearest, cnt.face_tests);
         const size_t pix = (size_t)texture_row(P, local_row) * P.width + x;
         uchar4 c = make_uchar4(0, 0, 0, 0);
         int hit = -1;
-        if (t_hit > 0.0f && t_hit < 100.0f) {
+        if (t_hit > 0.0f && t_hit < LINON_LINEAR_MAX_DIST) {
 #ifdef LINON_USER_SHADE
             vec3f rgb;
             float alpha;
-            shade_hit(s_tri, id, r.p, r.dir, 100.0f, t_hit, rgb, alpha);  // stored whatever its alpha says, :369-370
+            shade_hit(s_tri, id, r.p, r.dir, LINON_LINEAR_MAX_DIST, t_hit, rgb, alpha);  // stored whatever its alpha says, :369-370
             c = pack_color(rgb);
             c.w = unorm8(alpha);
 #else

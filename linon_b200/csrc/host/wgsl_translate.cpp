@@ -1438,6 +1438,7 @@ bool apply_march_literals(const RawItem& it, ModuleLayer& layer, std::string& er
     size_t n_pristine = 0;
     if (name == "nonlinear_ray_color") { pristine = kLit_nonlinear_ray_color; n_pristine = sizeof(kLit_nonlinear_ray_color) / sizeof(double); }
     if (name == "sample_rays") { pristine = kLit_sample_rays; n_pristine = sizeof(kLit_sample_rays) / sizeof(double); }
+    if (name == "main_view") { pristine = kLit_main_view; n_pristine = sizeof(kLit_main_view) / sizeof(double); }
     if (!pristine || it.info.literals.size() != n_pristine) return false;
     struct Hole { int ordinal; const char* what; };
     // ordinals verified against the reference's text by tools/gen_module_hashes.py (kLitHoles_* in module_literals.inc)
@@ -1445,15 +1446,19 @@ bool apply_march_literals(const RawItem& it, ModuleLayer& layer, std::string& er
         const double v = it.info.literals[k];
         if (v == pristine[k]) continue;
         const char* what = nullptr;
-        const int* holes = name == "nonlinear_ray_color" ? kLitHoles_nonlinear_ray_color : kLitHoles_sample_rays;
         static const char* const names_nl[] = {"h_initial", "t_max", "reject_factor", "reject_min_h", "small_h", "restore_factor"};
         static const char* const names_sr[] = {"sample_h", "sample_steps"};
-        const int n_holes = name == "nonlinear_ray_color" ? 6 : 2;
+        static const char* const names_mv[] = {"focal_length", "viewport_height", "linear_max_dist"};
+        const int* holes = name == "nonlinear_ray_color" ? kLitHoles_nonlinear_ray_color : (name == "sample_rays" ? kLitHoles_sample_rays : kLitHoles_main_view);
+        const char* const* hole_names = name == "nonlinear_ray_color" ? names_nl : (name == "sample_rays" ? names_sr : names_mv);
+        const int n_holes = name == "nonlinear_ray_color" ? 6 : (name == "sample_rays" ? 2 : 3);
         for (int q = 0; q < n_holes; ++q)
-            if (holes[q] == (int)k) what = (name == "nonlinear_ray_color" ? names_nl : names_sr)[q];
+            if (holes[q] == (int)k) what = hole_names[q];
         if (!what) {
-            err = "the function '" + name + "' was edited (literal " + std::to_string(k + 1) + " of " + std::to_string(n_pristine) +
-                  "); the CUDA path maps its step size, horizon and step-control constants to the kernel template, nothing else of it";
+            err = "the function '" + name + "' was edited (literal " + std::to_string(k + 1) + " of " + std::to_string(n_pristine) + "); the CUDA path maps " +
+                  (name == "main_view" ? "its focal length, viewport height and the reach of linear_mode"
+                                       : "its step size, horizon and step-control constants") +
+                  " to the kernel template, nothing else of it";
             return false;
         }
         auto bad = [&](const char* range) {
@@ -1485,6 +1490,15 @@ bool apply_march_literals(const RawItem& it, ModuleLayer& layer, std::string& er
         } else if (w == "sample_h") {
             if (!(v >= 1e-5 && v <= 1.0)) return bad("1e-5 <= h <= 1");
             layer.march_defines += "#define LINON_SAMPLE_H " + f32_literal(v) + "\n";
+        } else if (w == "focal_length") {
+            if (!(v >= 1e-4 && v <= 10.0)) return bad("1e-4 <= focal_length <= 10");
+            layer.march_defines += "#define LINON_FOCAL_LENGTH " + f32_literal(v) + "\n";
+        } else if (w == "viewport_height") {
+            if (!(v >= 1e-4 && v <= 10.0)) return bad("1e-4 <= viewport_height <= 10");
+            layer.march_defines += "#define LINON_VIEWPORT_HEIGHT " + f32_literal(v) + "\n";
+        } else if (w == "linear_max_dist") {
+            if (!(v > 0.0 && v <= 1e6)) return bad("0 < reach <= 1e6");
+            layer.march_defines += "#define LINON_LINEAR_MAX_DIST " + f32_literal(v) + "\n";
         } else if (w == "sample_steps") {
             const long steps = (long)v;
             if ((double)steps != v || steps < 100 || steps > 1000000 || steps % 100 != 0) return bad("a multiple of 100 in 100 ... 1 000 000: 100 samples per ray");

@@ -33,6 +33,14 @@ SHADE_CASES = {
     "linear_shade": [("const linear_mode: bool = false;", "const linear_mode: bool = true;"),
                      ("return vec4<f32>(result, t);", "return vec4<f32>(result.zyx, 0.5 * t);")],
 }
+# literals of main_view the kernel template takes as macros: the pinhole camera (:355-356), the reach of linear_mode's ray (:369).
+# Such a module carries the whole entry point, so these too exist as text only where the reference is mounted.
+SHADE_CASES.update({
+    "camera": [("let focal_length = 0.035;", "let focal_length = 0.05;"), ("let viewport_height = 0.025;", "let viewport_height = 0.03;")],
+    "linear_reach": [("const linear_mode: bool = false;", "const linear_mode: bool = true;"),
+                     ("let color = ray_color(origin, dir, 100.0);", "let color = ray_color(origin, dir, 2.25);")],
+})
+OVERRIDES = {"camera": "main_view", "linear_reach": "main_view"}  # the declaration a case edits (default: ray_color)
 SHADE_MODULE_DIR = "_shade_modules"
 
 

@@ -530,9 +530,11 @@ def test_main_view_mirror_follows_the_reference(product_lib, scene):
         assert (mv.hit_ids() >= 0).any()
 
 
-@pytest.mark.parametrize("name", ["tint", "noop", "declined", "depth", "linear_shade"])
+@pytest.mark.parametrize("name", ["tint", "noop", "declined", "depth", "linear_shade", "camera", "linear_reach"])
 def test_an_edited_shading_block_hot_reloads_against_the_edited_reference_shader(product_lib, scene, name):
-    """ray_color edited inside its shading block (src/main_view.wgsl:199-218): the block is translated from the user's text and
+    """(The cases "camera" and "linear_reach" edit literals of main_view instead - focal length, viewport height, the reach of
+    linear_mode's ray, :355-356, :369 - which become macros of the kernel template; same procedure.)
+    ray_color edited inside its shading block (src/main_view.wgsl:199-218): the block is translated from the user's text and
     called at every geometric hit (march_kernels.cuh: shade_hit); a hit the block declines (alpha <= 0) leaves the ray marching
     like `has_color = result.color.a > 0.0` (:262-263).  Frames equal tests/golden/march_edits.npz - the REFERENCE's shader with
     the same edit, transpiled and run on the CPU - endpoints bit for bit in strict math, colours within 1/255, every march
@@ -554,7 +556,7 @@ def test_an_edited_shading_block_hot_reloads_against_the_edited_reference_shader
         mv.sync()
         stock = mv.mapping_texture().copy(), mv.ray_casting_texture().copy()
         mv.reload_compute_shader(module)
-        assert "ray_color" in mv.module_overrides()
+        assert mc.OVERRIDES.get(name, "ray_color") in mv.module_overrides()
         frames = []
         for kernel in (capi.KERNEL_TILES, capi.KERNEL_PERSISTENT, capi.KERNEL_PAIRS, capi.KERNEL_REFILL):
             mv.set_option(capi.OPT_KERNEL, kernel)
@@ -563,7 +565,7 @@ def test_an_edited_shading_block_hot_reloads_against_the_edited_reference_shader
             frames.append((mv.ray_casting_texture(), mv.mapping_texture(), mv.hit_ids()))
         rgba8, endpoint, hit = frames[0]
         assert np.abs(rgba8.astype(int) - z[f"rgba8_{name}"].astype(int)).max() <= 1
-        if name == "linear_shade":
+        if name.startswith("linear"):
             assert np.array_equal(endpoint, stock[0])  # `mapping` is not written in linear mode
         else:
             assert np.array_equal(endpoint.view(np.uint32), z[f"endpoint_{name}"].view(np.uint32))
@@ -585,7 +587,7 @@ def test_an_edited_shading_block_hot_reloads_against_the_edited_reference_shader
             mv.sync()
             per_cull.append((mv.ray_casting_texture(), mv.mapping_texture()))
         mv.set_option(capi.OPT_CULL, 1)
-        if name != "linear_shade":
+        if not name.startswith("linear"):
             assert np.array_equal(per_cull[0][0], per_cull[1][0]) and np.array_equal(per_cull[0][1].view(np.uint32), per_cull[1][1].view(np.uint32))
         # production math with the edit: same surfaces; colours within 1/255 of the strict frame - except "depth", whose red
         # channel is t / max_dist: where inside its step a ray meets the wall, which in an adaptive frame follows the step

@@ -36,13 +36,19 @@ FN_EDITS = [
     ("step control", [("diff > 10.0 * last_diff && h > 0.002", "diff > 4.0 * last_diff && h > 0.004"), ("            h = 0.001;\n", "            h = 0.003;\n"),
                       ("if (2.0 * diff < last_diff", "if (3.0 * diff < last_diff")], "#define LINON_RESTORE_FACTOR (3.0f)"),
     ("sample rays", [("    let h = 0.001;\n    let steps: i32 = 5000;", "    let h = 0.002;\n    let steps: i32 = 2500;")], "#define LINON_SAMPLE_STEPS 2500"),
+    # the pinhole camera of main_view (:355-356) and the reach of linear_mode's single ray_color call (:369)
+    ("camera", [("let focal_length = 0.035;", "let focal_length = 0.05;"), ("let viewport_height = 0.025;", "let viewport_height = 0.03;")],
+     "#define LINON_FOCAL_LENGTH (0.0500000007f)"),
+    ("linear reach", [("const linear_mode: bool = false;", "const linear_mode: bool = true;"),
+                      ("let color = ray_color(origin, dir, 100.0);", "let color = ray_color(origin, dir, 2.25);")], "#define LINON_LINEAR_MAX_DIST (2.25f)"),
 ]
+_FN_OF = {"sample rays": "sample_rays", "camera": "main_view", "linear reach": "main_view"}
 
 # edits INSIDE the shading block of ray_color (src/main_view.wgsl:199-218): the block is translated from the user's text
 import march_edit_cases as mc  # noqa: E402
 
 _EXPECT = {"depth": "const wg_f32 shininess = (32.0f)"}
-SHADE_EDITS = [(name, edits, _EXPECT.get(name, "linon_ray_color_shade")) for name, edits in mc.SHADE_CASES.items()]
+SHADE_EDITS = [(name, edits, _EXPECT.get(name, "linon_ray_color_shade")) for name, edits in mc.SHADE_CASES.items() if name not in mc.OVERRIDES]
 
 
 def partial_module(edits):
@@ -72,7 +78,7 @@ def test_constant_edits_are_mapped_to_the_kernel_template(product_lib, name, edi
 def test_literal_edits_of_the_march_functions_are_mapped_too(product_lib, name, edits, expect):
     text, names = translate_wgsl_module(reference_module(edits))
     assert expect in text, text
-    assert ("sample_rays" if name == "sample rays" else "nonlinear_ray_color") in names
+    assert _FN_OF.get(name, "nonlinear_ray_color") in names
     assert compile_check(PF.MirageSpherical.to_code(), flags=0, math_mode=capi.MATH_FAST, module_src=reference_module(edits)) > 100_000
 
 
@@ -177,12 +183,13 @@ def test_edited_kernel_equals_the_edited_reference_shader(product_lib, name, edi
     flags = 0
     ref = _ref_frame(fn.to_code(), edits, "default", verts, faces, cam, st)
     lib = emu.build(fn.to_code(), flags, capi.MATH_STRICT, module_src=reference_module(edits))
-    if name == "sample rays":
+    if name in ("sample rays", "camera"):  # the sample rays leave through the same pinhole (:475-478)
         from oracle import cpu_oracle as co
         pos = co.sample_positions(cam, st, W, H)
         got = emu.march(lib, verts, faces, cam, st, W, H, sample_pos=pos)
         assert np.array_equal(got["ray_samples"].view(np.uint32), ref["ray_samples"].view(np.uint32))
-        return
+        if name == "sample rays":
+            return
     got = emu.march(lib, verts, faces, cam, st, W, H)
     assert np.abs(got["rgba8"].astype(int) - ref["rgba8"].astype(int)).max() <= 1, name
     if "linear" not in name:  # linear_mode never writes `mapping`

@@ -115,7 +115,8 @@ def test_the_hash_table_is_the_reference_module(product_lib):
     # the literal tables of the two march functions (values only) and the ordinals of the literals that are mapped
     lits = open(os.path.join(ROOT, "linon_b200", "csrc", "host", "module_literals.inc")).read()
     by_name = {n: l for _, n, _, _, _, l in items}
-    for fn, holes in (("nonlinear_ray_color", {9: 0.1, 10: 5.0, 19: 10.0, 20: 0.002, 21: 0.001, 24: 2.0}), ("sample_rays", {1: 0.001, 2: 5000.0})):
+    for fn, holes in (("nonlinear_ray_color", {9: 0.1, 10: 5.0, 19: 10.0, 20: 0.002, 21: 0.001, 24: 2.0}), ("sample_rays", {1: 0.001, 2: 5000.0}),
+                      ("main_view", {4: 0.035, 5: 0.025, 10: 100.0})):
         m = re.search(r"kLit_%s\[\] = \{([^}]*)\}" % fn, lits)
         assert [float(x) for x in m.group(1).split(",")] == by_name[fn]
         m = re.search(r"kLitHoles_%s\[\] = \{([^}]*)\}" % fn, lits)
