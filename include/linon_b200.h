@@ -214,8 +214,8 @@ int linon_set_field_function(linon_view* v, const char* wgsl_body, char* err, si
  * Also hot-reloaded: the march-level CONSTANTS of the module - eps, backface_culling, use_lighting, linear_mode, light_color,
  * ambient_strength, shininess (src/main_view.wgsl:65-76), adaptive_sampling and sample_outline_rays (:227, :337) and the VALUES
  * of the step size, horizon and step-control literals of nonlinear_ray_color / sample_rays (:241-267, :287-288) and of the
- * focal length, viewport height (:355-356) and the reach of linear_mode's ray (:369) in main_view - which
- * become macros of the kernel template (a changed h_initial disables Enhance's text replacement, like in the reference).
+ * focal length, viewport height (:355-356) and the reach of linear_mode's ray (:369) in main_view, and the colours of
+ * `var<private> sample_colors` (:326-335, non-negative literals) - which become macros of the kernel template (a changed h_initial disables Enhance's text replacement, like in the reference).
  * Also hot-reloaded: the SHADING BLOCK of ray_color (`if (t > 0.0 && t < max_dist) { ... }`, :199-218) - the statements that
  * turn the nearest hit into a colour.  When ray_color differs from the reference's inside that block only (the face loop must
  * stay the reference's, token for token: it is the kernel's own intersection code), the block is translated from the user's

@@ -29,7 +29,7 @@
 //   LINON_COLLAPSE_RUNS / LINON_COLLAPSE_MIN   quiet runs of at least MIN steps are taken binade by binade (advance_coord)
 //   LINON_QUIET_AHEAD    regular quiet steps after a plan that found no run, before the next plan
 //   LINON_EPS, LINON_BACKFACE_CULLING, LINON_USE_LIGHTING, LINON_LINEAR_MODE, LINON_LIGHT_*, LINON_AMBIENT, LINON_SHININESS,
-//   LINON_FOCAL_LENGTH, LINON_VIEWPORT_HEIGHT, LINON_LINEAR_MAX_DIST (literals of main_view), LINON_USER_SHADE,
+//   LINON_FOCAL_LENGTH, LINON_VIEWPORT_HEIGHT, LINON_LINEAR_MAX_DIST (literals of main_view), LINON_SAMPLE_COLORS, LINON_USER_SHADE,
 //   LINON_T_MAX, LINON_SAMPLE_H, LINON_SAMPLE_STEPS ...   the march-level constants of an edited main_view.wgsl (hot reload)
 //
 // The march kernels share every per-ray device function, so their per-pixel results are bit-identical in strict mode:
@@ -1829,9 +1829,12 @@ struct SampleParams {
     float4* ray_samples;  // 800 x {position, colour}
 };
 
-__constant__ float c_sample_colors[8][3] = {  // src/main_view.wgsl:326-335
-    {1.0f, 0.0f, 0.0f}, {0.5f, 0.5f, 0.0f}, {0.0f, 1.0f, 0.0f}, {0.5f, 1.0f, 0.0f},
-    {1.0f, 1.0f, 0.0f}, {0.5f, 0.5f, 0.5f}, {0.0f, 0.0f, 1.0f}, {0.5f, 0.0f, 0.5f}};
+#ifndef LINON_SAMPLE_COLORS  // `var<private> sample_colors`, src/main_view.wgsl:326-335 (an edited module passes its own values)
+#define LINON_SAMPLE_COLORS                                                            \
+    {1.0f, 0.0f, 0.0f}, {0.5f, 0.5f, 0.0f}, {0.0f, 1.0f, 0.0f}, {0.5f, 1.0f, 0.0f}, \
+    {1.0f, 1.0f, 0.0f}, {0.5f, 0.5f, 0.5f}, {0.0f, 0.0f, 1.0f}, {0.5f, 0.0f, 0.5f}
+#endif
+__constant__ float c_sample_colors[8][3] = {LINON_SAMPLE_COLORS};
 
 extern "C" __global__ void __launch_bounds__(32) linon_sample_rays(const SampleParams S) {
     // ONE RAY PER CTA (grid = 8, one warp each; every lane carries the same ray, lane 0 stores): the reference marches the eight

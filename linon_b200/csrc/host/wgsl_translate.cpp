@@ -1679,6 +1679,30 @@ bool translate_wgsl_module(const std::string& src, ModuleLayer& layer, std::stri
             std::string merr;
             if (kind == "const" && p && apply_march_const(t, it, layer, merr, const_values)) continue;
             if (kind == "fn" && p && p->masked_hash == it.info.masked_hash && apply_march_literals(it, layer, merr)) continue;
+            // `var<private> sample_colors` with other VALUES (:326-335): the colours the sample kernel writes next to each position
+            if (kind == "var" && name == "sample_colors" && p && p->masked_hash == it.info.masked_hash) {
+                std::vector<double> n;
+                std::vector<std::string> id;
+                if (const_value(t, it, n, id) && n.size() == 25) {  // the 8 of the constructor's type, then 8 x 3 components
+                    bool ok = true;
+                    std::string rows;
+                    for (int c = 0; c < 8 && ok; ++c) {
+                        rows += c ? ", {" : "{";
+                        for (int q = 0; q < 3; ++q) {
+                            const double x = n[1 + 3 * c + q];
+                            ok = ok && std::isfinite(x) && std::fabs(x) <= 1e3;
+                            rows += (q ? ", " : "") + f32_literal(x);
+                        }
+                        rows += "}";
+                    }
+                    if (ok) {
+                        layer.march_defines += "#define LINON_SAMPLE_COLORS " + rows + "\n";
+                        layer.names += (layer.names.empty() ? "" : ",") + name;
+                        continue;
+                    }
+                    merr = "a component of 'sample_colors' is outside the range the CUDA path supports (|component| <= 1000)";
+                }
+            }
             if (!merr.empty()) {
                 unsupported = true;
                 error = "main_view.wgsl line " + std::to_string(it.info.line) + ": " + merr;

@@ -461,6 +461,34 @@ def test_outline_mode_positions_match_the_serial_search(product_lib, oracle, sce
         assert np.array_equal(mv.read(capi.BUF_SAMPLE_POS), np.tile(np.array([0.0, 1.0], np.float32), (8, 1)))
 
 
+def test_edited_sample_colors_hot_reload(product_lib, scene):
+    """`var<private> sample_colors` with other values (src/main_view.wgsl:326-335; a partial module holds the declaration alone):
+    the sample kernel stores the user's colours next to unchanged positions, and the stock module brings the stock colours back."""
+    verts, faces, center = scene
+    colours = np.array([[1.0, 0.0, 0.0], [0.5, 0.5, 0.0], [0.0, 1.0, 0.0], [0.5, 1.0, 0.0],
+                        [1.0, 1.0, 0.0], [0.25, 0.75, 0.5], [0.0, 0.125, 1.0], [0.5, 0.0, 0.5]], np.float32)
+    module = ("var<private> sample_colors: array<vec3<f32>, 8> = array<vec3<f32>, 8>(\n" +
+              "".join("    vec3<f32>(%s, %s, %s),\n" % tuple(repr(float(x)) for x in c) for c in colours) + ");\n")
+    with MainView(verts, faces, center, 96, 64) as mv:
+        mv.reload_shader(PredefinedFunction.MirageSpherical.to_code())
+        mv.update_settings(make_settings())
+        mv.render_flags(0)
+        mv.sync()
+        stock = mv.ray_samples().copy()
+        mv.reload_compute_shader(module)
+        assert mv.module_overrides() == ["sample_colors"]
+        mv.render_flags(0)
+        mv.sync()
+        got = mv.ray_samples()
+        assert np.array_equal(got[:, :4].view(np.uint32), stock[:, :4].view(np.uint32))      # the same 800 positions
+        assert np.array_equal(got[:, 4:7].reshape(8, 100, 3), np.repeat(colours[:, None, :], 100, axis=1))
+        assert not np.array_equal(got[:, 4:7], stock[:, 4:7])
+        mv.reload_compute_shader(None)
+        mv.render_flags(0)
+        mv.sync()
+        assert np.array_equal(mv.ray_samples().view(np.uint32), stock.view(np.uint32))
+
+
 # ---- shards ----------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("world,rpb,kernel", [(2, 32, capi.KERNEL_TILES), (3, 8, capi.KERNEL_PERSISTENT), (8, 16, capi.KERNEL_TILES)])
 def test_row_block_shards_reassemble_bit_exactly(product_lib, scene, world, rpb, kernel):

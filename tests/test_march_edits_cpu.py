@@ -41,8 +41,11 @@ FN_EDITS = [
      "#define LINON_FOCAL_LENGTH (0.0500000007f)"),
     ("linear reach", [("const linear_mode: bool = false;", "const linear_mode: bool = true;"),
                       ("let color = ray_color(origin, dir, 100.0);", "let color = ray_color(origin, dir, 2.25);")], "#define LINON_LINEAR_MAX_DIST (2.25f)"),
+    # the colours the sample kernel stores next to each position (`var<private> sample_colors`, :326-335)
+    ("sample colours", [("    vec3<f32>(0.5, 0.5, 0.5),\n    vec3<f32>(0.0, 0.0, 1.0),", "    vec3<f32>(0.25, 0.75, 0.5),\n    vec3<f32>(0.0, 0.125, 1.0),")],
+     "#define LINON_SAMPLE_COLORS {(1.0f), (0.0f), (0.0f)}"),
 ]
-_FN_OF = {"sample rays": "sample_rays", "camera": "main_view", "linear reach": "main_view"}
+_FN_OF = {"sample rays": "sample_rays", "camera": "main_view", "linear reach": "main_view", "sample colours": "sample_colors"}
 
 # edits INSIDE the shading block of ray_color (src/main_view.wgsl:199-218): the block is translated from the user's text
 import march_edit_cases as mc  # noqa: E402
@@ -183,12 +186,12 @@ def test_edited_kernel_equals_the_edited_reference_shader(product_lib, name, edi
     flags = 0
     ref = _ref_frame(fn.to_code(), edits, "default", verts, faces, cam, st)
     lib = emu.build(fn.to_code(), flags, capi.MATH_STRICT, module_src=reference_module(edits))
-    if name in ("sample rays", "camera"):  # the sample rays leave through the same pinhole (:475-478)
+    if name in ("sample rays", "camera", "sample colours"):  # the sample rays leave through the same pinhole (:475-478)
         from oracle import cpu_oracle as co
         pos = co.sample_positions(cam, st, W, H)
         got = emu.march(lib, verts, faces, cam, st, W, H, sample_pos=pos)
         assert np.array_equal(got["ray_samples"].view(np.uint32), ref["ray_samples"].view(np.uint32))
-        if name == "sample rays":
+        if name != "camera":
             return
     got = emu.march(lib, verts, faces, cam, st, W, H)
     assert np.abs(got["rgba8"].astype(int) - ref["rgba8"].astype(int)).max() <= 1, name
