@@ -80,9 +80,15 @@ def test_user_edit_constructs_compile_for_sm100a(product_lib, name):
     assert compile_check(USER_EDITS[name]) > 0
 
 
-@pytest.mark.parametrize("fn", PREDEFINED)
-@pytest.mark.parametrize("flags,math", [(0, capi.MATH_FUSED), (capi.RENDER_ENHANCE, capi.MATH_FAST),
-                                        (capi.RENDER_ADAPTIVE_OFF, capi.MATH_STRICT)])
+# every body in the production mode; the other two modes on one body per family (mirage with / without sigmoid, rotation,
+# attractor) - the GPU suite runs all nine in every mode anyway, this is the build check that needs no GPU
+_MODES = [(fn, capi.RENDER_ENHANCE, capi.MATH_FAST) for fn in PREDEFINED]
+_MODES += [(fn, flags, math) for flags, math in ((0, capi.MATH_FUSED), (capi.RENDER_ADAPTIVE_OFF, capi.MATH_STRICT))
+           for fn in (PredefinedFunction.MirageSpherical, PredefinedFunction.MiragePlaneSigmoid, PredefinedFunction.Rotation,
+                      PredefinedFunction.LorenzAttractor)]
+
+
+@pytest.mark.parametrize("fn,flags,math", _MODES)
 def test_predefined_bodies_compile_for_sm100a(product_lib, fn, flags, math):
     assert compile_check(fn.to_code(), flags=flags, math_mode=math) > 100_000  # a real cubin came back
 
