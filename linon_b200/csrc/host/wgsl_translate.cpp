@@ -1561,8 +1561,8 @@ bool emit_shade_block(const std::vector<Tok>& t, const RawItem& it, int open, in
         if (t[j].kind == NL) ++line;
     const std::string text =
         "fn linon_ray_color_shade(origin: vec3<f32>, direction: vec3<f32>, max_dist: f32, linon_t: f32, linon_d1: vec3<f32>, "
-        "linon_d2: vec3<f32>) -> vec4<f32> { var t: f32 = linon_t; var d1: vec3<f32> = linon_d1; var d2: vec3<f32> = linon_d2; " +
-        block + "\nreturn vec4<f32>(0.0, 0.0, 0.0, 0.0);\n}\n";
+        "linon_d2: vec3<f32>) -> vec4<f32> { { var t: f32 = linon_t; var d1: vec3<f32> = linon_d1; var d2: vec3<f32> = linon_d2; " +
+        block + "\n}\nreturn vec4<f32>(0.0, 0.0, 0.0, 0.0);\n}\n";  // inner scope: t, d1, d2 may shadow a module constant, like in WGSL
     Lexer lx(text);
     if (!lx.run()) {
         err = "ray_color: " + lx.err;

@@ -151,6 +151,14 @@ def test_a_partial_module_may_hold_ray_color_alone(product_lib):
 
 
 @pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's ray_color")
+def test_the_blocks_variables_may_shadow_a_module_constant_like_in_wgsl(product_lib):
+    module = reference_module([("let diff = intensity;", "let diff = intensity * d1_scale;"),
+                               ("const PI: f32 = 3.141592653589793;", "const PI: f32 = 3.141592653589793;\nconst d1_scale: f32 = 0.5;\nconst d1: f32 = 2.0;")])
+    assert translate_wgsl_module(module)[1] == ["d1_scale", "d1", "ray_color"]
+    assert compile_check(PF.Rotation.to_code(), flags=0, math_mode=capi.MATH_FAST, module_src=module) > 100_000
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs the text of the reference's ray_color")
 @pytest.mark.parametrize("edits,needle", [
     # the face loop of ray_color is the kernel's own intersection code: still refused
     ([("(t < 0.0 || t_new < t)) {", "(t < 0.0 || t_new <= t)) {")], "was edited"),
