@@ -294,7 +294,25 @@ inline float __fsub_rd(float a, float b) { return emu_round_dir((double)a - b, -
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fmul_ru(float a, float b) { return emu_round_dir((double)a * b, +1); }
 inline float __fmul_rd(float a, float b) { return emu_round_dir((double)a * b, -1); }
+#ifdef LINON_EMU_FDIVIDEF_ULPS
+// The device's __fdividef is approximate (a MUFU.RCP and a multiply: up to 2 ulp off) where the host divides exactly, so an
+// emulated frame could hide a dependence on the quotient's last bits.  This variant moves every quotient by a pseudo-random
+// -N ... +N ulps: results that are exact by construction (tests/test_emulation_cpu.py) must not notice.
+inline float __fdividef(float a, float b) {
+    float q = a / b;
+    uint32_t ua, ub, uq;
+    memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); memcpy(&uq, &q, 4);
+    if ((uq & 0x7f800000u) == 0x7f800000u || (uq & 0x7fffffffu) < 0x00800000u + 16u) return q;  // inf / NaN / zero / subnormal
+    uint32_t h = ua * 2654435761u ^ (ub + 0x9e3779b9u) * 2246822519u;
+    h ^= h >> 15; h *= 3266489917u; h ^= h >> 13;
+    const int n = (int)(h % (2u * LINON_EMU_FDIVIDEF_ULPS + 1u)) - (int)LINON_EMU_FDIVIDEF_ULPS;
+    uq += (uint32_t)n;  // magnitude moves by n ulps (sign bit untouched: no borrow at these magnitudes)
+    memcpy(&q, &uq, 4);
+    return q;
+}
+#else
 inline float __fdividef(float a, float b) { return a / b; }
+#endif
 inline float __frcp_rn(float a) { return 1.0f / a; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __frsqrt_rn(float a) { return 1.0f / sqrtf(a); }

@@ -34,7 +34,7 @@ def _cxx():
 
 
 def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int = 1, opt: str = "-O1", pairs: bool = False,
-          quiet_radius: int = 0, bvh: bool = False, n_faces: int = 36, module_src: str | None = None):
+          quiet_radius: int = 0, bvh: bool = False, n_faces: int = 36, module_src: str | None = None, extra_defines=()):
     """-> ctypes library with emu_march for this variant of the march module (pairs: also linon_march_pairs)."""
     from linon_b200.main_view import compile_check
     os.makedirs(_CACHE, exist_ok=True)
@@ -62,7 +62,7 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
     text = open(dump, "rb").read()
     os.unlink(dump)
     shim = open(os.path.join(_HERE, "cuda_shim.hpp"), "rb").read() + open(os.path.join(_HERE, "emu_driver.cpp"), "rb").read()
-    key = hashlib.sha1(text + shim + opt.encode()).hexdigest()[:20]
+    key = hashlib.sha1(text + shim + opt.encode() + " ".join(extra_defines).encode()).hexdigest()[:20]
     src = os.path.join(_CACHE, f"march_{key}.cu.inc")
     so = os.path.join(_CACHE, f"libemu_{key}.so")
     if not os.path.exists(so):
@@ -73,7 +73,7 @@ def build(body: str, flags: int, math_mode: int, quiet_zone: int = 0, cull: int 
             f.write(text)
         cmd = [_cxx(), opt, "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w", "-DLINON_WARP_STATS=1",
                f'-DLINON_EMU_SOURCE="{src}"', "-I", _HERE, "-I", os.path.join(_ROOT, "linon_b200", "csrc", "host"),
-               *defines, os.path.join(_HERE, "emu_driver.cpp"), "-o", so + ".tmp"]
+               *defines, *extra_defines, os.path.join(_HERE, "emu_driver.cpp"), "-o", so + ".tmp"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("emulation build failed:\n" + r.stderr[-6000:])

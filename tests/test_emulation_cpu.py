@@ -219,6 +219,38 @@ def test_quiet_zone_culling_never_changes_a_result(product_lib, fn, flags, size,
     assert int(a["counters"][4]) < 0.25 * int(b["counters"][4])           # ... and most checks are gone
 
 
+@pytest.mark.parametrize("fn,flags,size,orbit_frame", [
+    (PredefinedFunction.MirageSphericalSigmoid, capi.RENDER_ENHANCE, (40, 28), 0),
+    (PredefinedFunction.MiragePlaneSigmoid, capi.RENDER_ENHANCE, (48, 32), 50),
+    (PredefinedFunction.MirageSpherical, capi.RENDER_ADAPTIVE_OFF, (96, 72), 40)])
+def test_results_do_not_depend_on_the_last_bits_of_the_approximate_division(product_lib, fn, flags, size, orbit_frame):
+    """The one intrinsic the emulation cannot reproduce: __fdividef is a MUFU.RCP and a multiply on the device (up to 2 ulp off),
+    an exact division on the host.  It is used where a result is made exact afterwards or carries a margin - the number of steps
+    of a collapsed run per binade segment (corrected by an exact FMA test), the length of a quiet run and the steps a
+    safe-distance budget covers (rounded down behind a relative margin of 1e-4).  With every quotient moved by a pseudo-random
+    -4 ... +4 ulps (tests/emu/cuda_shim.hpp) the frames are still the frames of the kernel without culling, bit for bit, and
+    advance_coord is still the chain of single steps."""
+    import ctypes as C
+    W, H = size
+    verts, faces, cam = _frame_inputs(W, H, orbit_frame)
+    noisy = emu.build(fn.to_code(), flags, capi.MATH_FAST, quiet_zone=1, cull=1, extra_defines=("-DLINON_EMU_FDIVIDEF_ULPS=4u",))
+    plain = emu.build(fn.to_code(), flags, capi.MATH_FAST, quiet_zone=1, cull=0)
+    a, b = emu.march(noisy, verts, faces, cam, SETTINGS, W, H), emu.march(plain, verts, faces, cam, SETTINGS, W, H)
+    for k in ("hit_id", "rgba8", "endpoint"):
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    assert int(a["counters"][15]) == int(b["counters"][15]) > 0
+    if flags == capi.RENDER_ENHANCE:
+        rng = np.random.default_rng(5)
+        m = 300_000
+        p = (rng.uniform(-3, 3, m) * rng.choice([1e-3, 1.0, 1.0, 30.0], m)).astype(np.float32)
+        d = rng.uniform(-1.5, 1.5, m).astype(np.float32)
+        n = rng.integers(0, 5002, m).astype(np.int32)
+        x, y = np.zeros_like(p), np.zeros_like(p)
+        noisy.emu_advance_coord(C.c_int(m), C.c_void_p(p.ctypes.data), C.c_void_p(d.ctypes.data), C.c_float(0.001),
+                                C.c_void_p(n.ctypes.data), C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data))
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
 @pytest.mark.parametrize("fn", MIRAGES)
 def test_quiet_zone_adaptive_frames_meet_the_north_star_on_hit_and_colour(product_lib, oracle, fn):
     """Option level 2: adaptive frames (C1 / C2 as the application renders them).  Graded like the GPU test of the adaptive
