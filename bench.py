@@ -682,6 +682,10 @@ def run_ours(args):
                         dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(cvec)
+    # this rank's own straight steps of the timed frame: the C5 block below renders another frame through frame(), which
+    # overwrites last[...] when world > 1 (round 2, N = 2 / 4 lines: the roofline's hand count mixed the C3 counters with the
+    # 8192^2 frame's straight steps and came out negative)
+    quiet_local = last.get("quiet", 0)
 
     # ---- C5 (BASELINE.json configs[4]): the 8192 x 8192 Enhance frame of the orbit, sharded over the same ranks: the
     # fixed-size record of every N (strong scaling is read across the N = 1, 2, 4, 8 lines) ----
@@ -733,7 +737,7 @@ def run_ours(args):
     fp32_peak, sms = measure_fp32_peak(local_rank)
     m_ms = float(np.mean(march_ms))
 
-    model_flops = fl.fused_march_flops(counters, FN_ID, field_weight_is_one=True, quiet_steps=last.get("quiet", 0), collapsed_runs=True)
+    model_flops = fl.fused_march_flops(counters, FN_ID, field_weight_is_one=True, quiet_steps=quiet_local, collapsed_runs=True)
     prof, prof_note = committed_profile(MARCH_PROFILE, "linon_march_tiles", cubin_hash)
     ncu_flops = None
     if prof is not None and world == 1 and prof.get("fp32_flops_executed"):
